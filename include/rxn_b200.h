@@ -1,0 +1,301 @@
+/*
+ * rxn_b200.h — C ABI of the B200-native batched reaction path for PFLOTRAN.
+ *
+ * The reference (petsc/pflotran) has no C or plugin ABI for this path: the
+ * boundary is the set of public Fortran module procedures of Reaction_module
+ * (src/pflotran/reaction.F90:38-70) called one cell at a time from the loops in
+ * src/pflotran/reactive_transport.F90.  Each entry point below is the BATCHED
+ * replacement of one of those loops; the citation on each declaration names the
+ * reference loop / routine it replaces.  A thin `use iso_c_binding` module
+ * (fortran/rxn_b200_shim.F90) binds these names 1:1.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no aborts: every function returns an RxnStatus;
+ *     rxn_last_error() returns the message (reference: option%io_buffer +
+ *     printErrMsg, src/pflotran/option.F90:630-677).
+ *   - all reals are IEEE double (PetscReal), all indices int32 (PetscInt),
+ *     species ids are 1-BASED exactly as stored by the reference, so Fortran can
+ *     pass `c_loc(reaction%eqcplxspecid)` etc. without repacking.
+ *   - array shapes are the Fortran shapes in Fortran memory order; see
+ *     RxnSpecList.
+ *   - host buffers belong to the caller and are only touched during the call.
+ *   - one handle is bound to one CUDA device; calls are synchronous at return.
+ */
+#ifndef RXN_B200_H
+#define RXN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum RxnStatus {
+  RXN_OK = 0,
+  RXN_ERR_INVALID = 1,      /* bad argument / inconsistent descriptor            */
+  RXN_ERR_UNSUPPORTED = 2,  /* tables enable a reaction type outside the path    */
+  RXN_ERR_CUDA = 3,         /* CUDA runtime error (message has the detail)       */
+  RXN_ERR_NO_DEVICE = 4,    /* no usable GPU: there is NO CPU fallback           */
+  RXN_ERR_CELL_FAILED = 5   /* >=1 cell raised a flag the reference would abort on */
+} RxnStatus;
+
+/* RReact dt handling (reference src/pflotran/reaction.F90:3347,3362,3424-3426
+ * vs :5189-5191): AS_WRITTEN keeps residual = accum - fixed_accum [mol] with J/dt;
+ * DT_CONSISTENT uses residual = (accum - fixed_accum)/dt as the live global-implicit
+ * caller does (src/pflotran/reactive_transport.F90:2564). */
+typedef enum RxnDtMode { RXN_DT_AS_WRITTEN = 0, RXN_DT_CONSISTENT = 1 } RxnDtMode;
+
+/* per-cell exit reason / flags written by rxn_react_batch (flags_out) */
+enum {
+  RXN_EXIT_RESIDUAL   = 1,   /* max|residual| < max_residual_tolerance  (reaction.F90:3443) */
+  RXN_EXIT_REL_CHANGE = 2,   /* max rel. change < tolerance             (reaction.F90:3476) */
+  RXN_FLAG_CAPPED       = 1 << 8,   /* iteration cap hit (reference would spin, :3478-3496) */
+  RXN_FLAG_LU_ZERO_ROW  = 1 << 9,   /* ludcmp all-zero row (reference MPI_Abort, utility.F90:423) */
+  RXN_FLAG_ACT_DIVERGED = 1 << 10,  /* activity-coef Newton > 50 its (reaction.F90:3864) */
+  RXN_FLAG_NONFINITE    = 1 << 11,
+  RXN_FLAG_INACTIVE     = 1 << 12   /* cell skipped: imat<=0 (reactive_transport.F90:1699) */
+};
+
+/* reaction_aux.F90:23-27 */
+enum { RXN_ACT_COEF_FREQUENCY_OFF = 0, RXN_ACT_COEF_FREQUENCY_TIMESTEP = 1,
+       RXN_ACT_COEF_FREQUENCY_NEWTON_ITER = 2,
+       RXN_ACT_COEF_ALGORITHM_LAG = 3, RXN_ACT_COEF_ALGORITHM_NEWTON = 4 };
+/* reaction_surf_complex_aux.F90:19-22 */
+enum { RXN_NULL_SURFACE = 0, RXN_COLLOID_SURFACE = 1, RXN_MINERAL_SURFACE = 2, RXN_ROCK_SURFACE = 3 };
+/* pflotran_constants.F90:94-96 */
+enum { RXN_SORPTION_LINEAR = 1, RXN_SORPTION_LANGMUIR = 2, RXN_SORPTION_FREUNDLICH = 3 };
+/* logK evaluation: 0 tables hold logK at the (isothermal) reference temperature;
+ * 1 per-cell 5-term fit (reaction_aux.F90:1461-1488); 2 per-cell 17-term hpt form (:1529-1571) */
+enum { RXN_LOGK_FIXED = 0, RXN_LOGK_FIT5 = 1, RXN_LOGK_HPT = 2 };
+
+/*
+ * A reaction list in the reference's compressed form:
+ *   Fortran  specid(0:m,n)  -> id[r*id_ld + 0] = nspec, id[r*id_ld + i] = species i (1-based id)
+ *   Fortran  stoich(0:m,n)  -> stoich_off = 0 : stoich of species i at stoich[r*stoich_ld + i]
+ *   Fortran  stoich(m,n)    -> stoich_off = 1 : stoich of species i at stoich[r*stoich_ld + i - 1]
+ * h2oid[r] > 0 means H2O takes part with stoichiometry h2ostoich[r].
+ */
+typedef struct RxnSpecList {
+  const int32_t *id;
+  const double *stoich;
+  const int32_t *h2oid;
+  const double *h2ostoich;
+  const double *logK;      /* [n]                     */
+  const double *logKcoef;  /* [n][num_logK_coef] or NULL */
+  int32_t id_ld;
+  int32_t stoich_ld;
+  int32_t stoich_off;
+  int32_t n;
+} RxnSpecList;
+
+/* Flat view of reaction_type (reference src/pflotran/reaction_aux.F90:142-335),
+ * mineral_type (reaction_mineral_aux.F90:77-128) and surface_complexation_type
+ * (reaction_surf_complex_aux.F90:68-128).  Pointers may be NULL when the count is 0. */
+typedef struct RxnTablesDesc {
+  int32_t struct_size;            /* = sizeof(RxnTablesDesc) */
+  int32_t naqcomp;
+  int32_t ncomp;                  /* must equal naqcomp (no immobile/colloid dofs) */
+  int32_t logK_mode;              /* RXN_LOGK_*            */
+  int32_t num_logK_coef;
+  int32_t use_log_formulation;
+  int32_t act_coef_update_frequency;
+  int32_t act_coef_update_algorithm;
+  int32_t use_activity_h2o;
+  int32_t h2o_aq_id;              /* species_idx%h2o_aq_id, 0 if none */
+  int32_t h_ion_id;               /* species_idx%h_ion_id (>0 primary, <0 complex, 0 none) */
+  int32_t reserved0;
+  double debyeA, debyeB, debyeBdot;
+  double max_dlnC, max_relative_change_tolerance, max_residual_tolerance;
+  const double *primary_spec_Z;   /* [naqcomp] */
+  const double *primary_spec_a0;  /* [naqcomp] */
+
+  /* aqueous complexes: eqcplxspecid(0:m,n), eqcplxstoich(0:m,n) -> stoich_off 0 */
+  RxnSpecList eqcplx;
+  const double *eqcplx_Z;
+  const double *eqcplx_a0;
+
+  /* kinetic minerals: kinmnrlspecid(0:m,n), kinmnrlstoich(m,n) -> stoich_off 1 */
+  RxnSpecList kinmnrl;
+  const double *kinmnrl_rate_constant;
+  const double *kinmnrl_activation_energy;
+  const double *kinmnrl_molar_vol;
+  const double *kinmnrl_affinity_threshold;
+  const double *kinmnrl_rate_limiter;
+  const double *kinmnrl_Temkin_const;      /* NULL <=> not associated() */
+  const double *kinmnrl_min_scale_factor;  /* NULL <=> not associated() */
+  const double *kinmnrl_affinity_power;    /* NULL <=> not associated() */
+  const int32_t *kinmnrl_num_prefactors;   /* [nkin] */
+  const double *kinmnrl_pref_rate;               /* (maxpref, nkin)              */
+  const double *kinmnrl_pref_activation_energy;  /* (maxpref, nkin)              */
+  const int32_t *kinmnrl_prefactor_id;           /* (0:maxprefspec, maxpref, nkin) */
+  const double *kinmnrl_pref_alpha;              /* (maxprefspec, maxpref, nkin)   */
+  const double *kinmnrl_pref_beta;
+  const double *kinmnrl_pref_atten_coef;
+  int32_t max_num_prefactors;
+  int32_t max_num_prefactor_species;
+
+  /* all minerals + passive gases: used only by constraint equilibration */
+  RxnSpecList mnrl;     /* mnrlstoich(m,n) -> stoich_off 1 */
+  RxnSpecList paseq;    /* paseqstoich(0:m,n) -> stoich_off 0 */
+
+  /* surface complexation */
+  RxnSpecList srfcplx;  /* srfcplxstoich(m,n) -> stoich_off 1 */
+  const double *srfcplx_free_site_stoich;
+  const double *srfcplx_Z;
+  int32_t nsrfcplxrxn;
+  int32_t srfcplxrxn_to_complex_ld;           /* srfcplxrxn_to_complex(0:mc, nrxn) */
+  const int32_t *srfcplxrxn_to_surf;
+  const int32_t *srfcplxrxn_surf_type;
+  const int32_t *srfcplxrxn_to_complex;
+  const int32_t *srfcplxrxn_stoich_flag;
+  const double *srfcplxrxn_site_density;
+  int32_t neqsrfcplxrxn;
+  int32_t nkinmrsrfcplxrxn;
+  const int32_t *eqsrfcplxrxn_to_srfcplxrxn;
+  const int32_t *kinmrsrfcplxrxn_to_srfcplxrxn;
+  const int32_t *kinmr_nrate;                 /* (0:nkinmr): [0] = max */
+  const double *kinmr_rate;                   /* (maxrate, nkinmr) */
+  const double *kinmr_frac;                   /* (maxrate, nkinmr) */
+  int32_t kinmr_ld;                           /* = maxrate */
+  int32_t nkinsrfcplxrxn;                     /* must be 0 (RKineticSurfCplx: next) */
+
+  /* ion exchange: eqionx_rxn_cationid(0:mc,n), eqionx_rxn_k(mc,n) */
+  int32_t neqionxrxn;
+  int32_t eqionx_ld;                          /* = mc (ids use mc+1) */
+  const int32_t *eqionx_rxn_cationid;
+  const double *eqionx_rxn_k;
+  const double *eqionx_rxn_CEC;
+  const int32_t *eqionx_rxn_Z_flag;
+  const int32_t *eqionx_rxn_to_surf;
+
+  /* KD isotherms */
+  int32_t neqkdrxn;
+  int32_t reserved1;
+  const int32_t *eqkdspecid;
+  const int32_t *eqkdtype;
+  const int32_t *eqkdmineral;
+  const double *eqkddistcoef;
+  const double *eqkdlangmuirb;
+  const double *eqkdfreundlichn;
+
+  /* reaction types outside the path: all must be 0, else RXN_ERR_UNSUPPORTED
+   * (active gas/RTotalGas, immobile, colloids, general, radioactive decay, microbial,
+   * immobile decay, sandbox, CLM, solid solution, CO2 flow modes -> RTotalCO2). */
+  int32_t nactive_gas, nimmobile, ncoll, ngeneral_rxn, nradiodecay_rxn, nmicrobial_rxn,
+          nimmobile_decay_rxn, has_sandbox, has_clm, has_solid_solution, co2_flow_mode,
+          numerical_derivatives;
+} RxnTablesDesc;
+
+/* Per-cell state fields (reactive_transport_auxvar_type, reference
+ * src/pflotran/reactive_transport_aux.F90:18-73; global_auxvar_type global_aux.F90:11-33;
+ * material_auxvar_type material_aux.F90:26-43).  Device layout is SoA FP64,
+ * field[row][cell], cell index fastest, leading dimension padded. */
+typedef enum RxnField {
+  RXN_F_PRI_MOLAL = 0,        /* rows = naqcomp                          */
+  RXN_F_TOTAL,                /* naqcomp   total(:,1)                    */
+  RXN_F_SEC_MOLAL,            /* neqcplx                                 */
+  RXN_F_PRI_ACT_COEF,         /* naqcomp                                 */
+  RXN_F_SEC_ACT_COEF,         /* neqcplx                                 */
+  RXN_F_LN_ACT_H2O,           /* 1                                       */
+  RXN_F_TOTAL_SORB_EQ,        /* naqcomp                                 */
+  RXN_F_FREE_SITE_CONC,       /* nsrfcplxrxn  srfcplxrxn_free_site_conc  */
+  RXN_F_EQSRFCPLX_CONC,       /* nsrfcplx                                */
+  RXN_F_KINMR_TOTAL_SORB,     /* nkinmr*(maxrate+1)*naqcomp: row = (rxn*(maxrate+1)+rate)*naq+comp */
+  RXN_F_EQIONX_REF_CATION_SORBED_CONC, /* neqionxrxn                      */
+  RXN_F_EQIONX_CONC,          /* neqionxrxn*eqionx_ld: row = rxn*ld + cation */
+  RXN_F_MNRL_VOLFRAC,         /* nkinmnrl                                */
+  RXN_F_MNRL_AREA,            /* nkinmnrl                                */
+  RXN_F_MNRL_RATE,            /* nkinmnrl                                */
+  RXN_F_DEN_KG, RXN_F_SAT, RXN_F_TEMP, RXN_F_PRES,         /* 1 each      */
+  RXN_F_VOLUME, RXN_F_POROSITY, RXN_F_SOIL_PARTICLE_DENSITY,
+  RXN_F_DTOTAL,               /* naqcomp^2, column-major: row = j*naq + i (GI entry points only) */
+  RXN_F_DTOTAL_SORB_EQ,       /* naqcomp^2, column-major                                         */
+  RXN_F_COUNT
+} RxnField;
+
+typedef struct RxnTables RxnTables;   /* opaque */
+typedef struct RxnState RxnState;     /* opaque */
+
+/* replaces: reading `reaction` (reaction_type) inside every per-cell call.
+ * Copies and repacks the tables to the device; immutable afterwards. */
+int rxn_tables_create(const RxnTablesDesc *desc, int device, RxnTables **out);
+int rxn_tables_destroy(RxnTables *t);
+
+/* replaces: RTAuxVarInit per ghosted cell (reactive_transport_aux.F90:213-400),
+ * allocation loop reactive_transport.F90:271-274.  Initial values as the reference:
+ * act coefs = 1, free_site_conc = 1e-9, eqionx_ref_cation_sorbed_conc = 1e-9, rest 0. */
+int rxn_state_create(const RxnTables *t, int64_t ncells_ghosted, RxnState **out);
+int rxn_state_destroy(RxnState *s);
+int64_t rxn_state_ncells(const RxnState *s);
+int32_t rxn_field_rows(const RxnTables *t, int field);
+
+/* replaces: direct field access by PatchGetVariable (patch.F90:3529-4788), checkpoint
+ * (pm_rt.F90:1159-1305) and CondControlAssignTranInitCond (condition_control.F90:498-949).
+ * host element (row r, cell c) lives at host[r*row_stride + c*cell_stride]. */
+int rxn_state_upload(RxnState *s, int field, const double *host, int64_t row_stride,
+                     int64_t cell_stride);
+int rxn_state_download(const RxnState *s, int field, double *host, int64_t row_stride,
+                       int64_t cell_stride);
+
+/* replaces: R2 reads + the imat<=0 / nG2L<0 skips (reactive_transport.F90:1699, 3791-3794).
+ * Any pointer may be NULL (field left unchanged). active: 1 = compute, 0 = skip. */
+int rxn_set_cell_scalars(RxnState *s, const double *den_kg, const double *sat, const double *temp,
+                         const double *pres, const double *volume, const double *porosity,
+                         const double *soil_particle_density, const uint8_t *active);
+
+/* replaces: the RTReact cell loop (reactive_transport.F90:1697-1724) = RReact per cell
+ * (reaction.F90:3322-3511).  tran_xx: AoS nlocal x ncomp, in: transported totals [mol/L],
+ * out: free-ion molalities.  l2g: ghosted (state) index of local cell i, 0-based, or NULL
+ * for identity.  iters_out/flags_out: int32[nlocal] or NULL. */
+int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nlocal, double dt,
+                    int dt_mode, int32_t *iters_out, int32_t *flags_out);
+/* same, with tran_xx / iters / flags already resident on the state's device (no PCIe). */
+int rxn_react_batch_device(RxnState *s, double *d_tran_xx, const int32_t *d_l2g, int64_t nlocal,
+                           double dt, int dt_mode, int32_t *d_iters, int32_t *d_flags);
+
+/* replaces: RTUpdateAuxVars cells part (reactive_transport.F90:3790-3846) and
+ * RTUpdateActivityCoefficients (:3620-3700).  xx_loc: AoS nghosted x ncomp free-ion
+ * molalities (NULL: keep the state's pri_molal). */
+int rxn_update_auxvars_batch(RxnState *s, const double *xx_loc, int update_act_coefs);
+
+/* replaces: RTUpdateFixedAccumulation (reactive_transport.F90:786-843).
+ * accum_out: AoS nlocal x ncomp [mol]. */
+int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int64_t nlocal,
+                          double *accum_out);
+
+/* replaces: accumulation + reaction loops of RTResidualNonFlux (reactive_transport.F90:
+ * 2545-2586, 2735-2758): res_out[cell] = (RTAccumulation + RAccumulationSorb)/dt + RReaction.
+ * The caller subtracts its fixed accumulation / dt.  AoS nlocal x ncomp. */
+int rxn_residual_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt,
+                              double *res_out);
+/* replaces: RTJacobianNonFlux loops (reactive_transport.F90:3342-3389, 3445-3465):
+ * jac_out[cell] = RTAccumulationDerivative + RAccumulationSorbDerivative + RReactionDerivative,
+ * ncomp x ncomp column-major per block, ready for MatSetValuesBlockedLocal
+ * (MAT_ROW_ORIENTED = FALSE, discretization.F90:857). */
+int rxn_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt,
+                              double *jac_out);
+
+/* replaces: RTUpdateKineticState loop (reactive_transport.F90:692-705) =
+ * RUpdateKineticState per cell (reaction.F90:5320-5429). */
+int rxn_update_kinetic_state_batch(RxnState *s, double dt);
+
+/* timing of the last batched kernel sequence on the handle's stream, in ms (CUDA events). */
+float rxn_last_kernel_ms(const RxnState *s);
+/* number of kernels this library has launched since load (bench.py: gpu_launches). */
+int64_t rxn_launch_count(void);
+
+/* raw device pointer of a field (row-major [rows][ld]); for zero-copy callers and benchmarks */
+int rxn_state_device_ptr(RxnState *s, int field, double **d_ptr, int64_t *ld);
+int rxn_device_alloc(RxnState *s, int64_t bytes, void **d_ptr);
+int rxn_device_free(RxnState *s, void *d_ptr);
+int rxn_device_copy(RxnState *s, void *dst, const void *src, int64_t bytes, int kind /*0 h2d,1 d2h,2 d2d*/);
+int rxn_device_sync(RxnState *s);
+
+/* replaces: option%io_buffer */
+int rxn_last_error(char *buf, int32_t len);
+const char *rxn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXN_B200_H */

@@ -1,0 +1,138 @@
+"""ctypes wrapper of the CPU oracle (oracle/liborc.so).
+
+TEST INFRASTRUCTURE: import only from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from pflotran_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, 'liborc.so')
+    src = os.path.join(_HERE, 'rxn_oracle.cpp')
+    hdr = os.path.join(_HERE, '..', 'include', 'rxn_b200.h')
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(['make', '-C', _HERE, '-B', 'liborc.so'], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_create.restype = C.c_void_p
+        _LIB.orc_create.argtypes = [C.POINTER(abi.RxnTablesDesc)]
+        _LIB.orc_destroy.argtypes = [C.c_void_p]
+    return _LIB
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8)) if a is not None else None
+
+
+def _f64(a):
+    return a.ctypes.data_as(abi.c_f64p) if a is not None else None
+
+
+def _i32(a):
+    return a.ctypes.data_as(abi.c_i32p) if a is not None else None
+
+
+class Oracle:
+    def __init__(self, tables):
+        self.t = tables
+        self.desc = abi.make_desc(tables)
+        self.h = C.c_void_p(lib().orc_create(C.byref(self.desc)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def react(self, st: abi.HostState, tran_xx: np.ndarray, dt: float, dt_mode: int = abi.RXN_DT_CONSISTENT,
+              maxit: int = 1000, nthreads: int = 1):
+        """RTReact loop.  tran_xx [ncells, ncomp] in: totals, out: free-ion (in place)."""
+        assert tran_xx.flags.c_contiguous and tran_xx.dtype == np.float64
+        n = st.ncells
+        iters = np.zeros(n, dtype=np.int32)
+        flags = np.zeros(n, dtype=np.int32)
+        v = st.view()
+        rc = lib().orc_react_batch(self.h, C.byref(v), _f64(tran_xx), _u8(st.active), C.c_double(dt),
+                                   C.c_int(dt_mode), _i32(iters), _i32(flags), C.c_int(maxit), C.c_int(nthreads))
+        assert rc == 0
+        return iters, flags
+
+    def update_auxvars(self, st: abi.HostState, xx_loc: Optional[np.ndarray], update_act_coefs: bool,
+                       nthreads: int = 1):
+        v = st.view()
+        rc = lib().orc_update_auxvars_batch(self.h, C.byref(v), _f64(xx_loc), _u8(st.active),
+                                            C.c_int(int(update_act_coefs)), C.c_int(nthreads))
+        assert rc == 0
+
+    def fixed_accum(self, st: abi.HostState, xx: Optional[np.ndarray], nthreads: int = 1) -> np.ndarray:
+        out = np.zeros((st.ncells, self.t.ncomp))
+        v = st.view()
+        rc = lib().orc_fixed_accum_batch(self.h, C.byref(v), _f64(xx), _u8(st.active), _f64(out), C.c_int(nthreads))
+        assert rc == 0
+        return out
+
+    def residual_jacobian(self, st: abi.HostState, dt: float, nthreads: int = 1):
+        n = self.t.ncomp
+        res = np.zeros((st.ncells, n))
+        jac = np.zeros((st.ncells, n * n))
+        v = st.view()
+        rc = lib().orc_residual_jacobian_batch(self.h, C.byref(v), _u8(st.active), C.c_double(dt), _f64(res),
+                                               _f64(jac), C.c_int(nthreads))
+        assert rc == 0
+        return res, jac
+
+    def update_kinetic_state(self, st: abi.HostState, dt: float, nthreads: int = 1):
+        v = st.view()
+        rc = lib().orc_update_kinetic_state_batch(self.h, C.byref(v), _u8(st.active), C.c_double(dt), C.c_int(nthreads))
+        assert rc == 0
+
+    def activity_coefficients(self, st: abi.HostState, nthreads: int = 1):
+        v = st.view()
+        assert lib().orc_activity_coefficients_batch(self.h, C.byref(v), C.c_int(nthreads)) == 0
+
+    def equilibrate(self, st: abi.HostState, cell: int, ctype, conc, cid, free_ion_guess=None,
+                    use_prev: bool = False, molal: Optional[bool] = None):
+        naq = self.t.naqcomp
+        ctype = np.ascontiguousarray(ctype, dtype=np.int32)
+        conc = np.ascontiguousarray(conc, dtype=np.float64)
+        cid = np.ascontiguousarray(cid, dtype=np.int32)
+        fig = None if free_ion_guess is None else np.ascontiguousarray(free_ion_guess, dtype=np.float64)
+        basis = np.zeros(naq)
+        nit = C.c_int32(0)
+        if molal is None:
+            molal = bool(self.t.initialize_with_molality)
+        v = st.view()
+        rc = lib().orc_equilibrate_constraint(self.h, C.byref(v), C.c_int64(cell), _i32(ctype), _f64(conc),
+                                              _i32(cid), _f64(fig), C.c_int(int(use_prev)), C.c_int(int(molal)),
+                                              _f64(basis), C.byref(nit))
+        if rc != 0:
+            raise RuntimeError('ReactionEquilibrateConstraint failed rc=%d' % rc)
+        return basis, nit.value
+
+    @staticmethod
+    def rsolve(res, jac, conc, use_log):
+        n = len(res)
+        res = np.array(res, dtype=np.float64)
+        jac = np.array(jac, dtype=np.float64, order='F').ravel(order='F').copy()
+        conc = np.array(conc, dtype=np.float64)
+        upd = np.zeros(n)
+        rc = lib().orc_rsolve(_f64(res), _f64(jac), _f64(conc), _f64(upd), C.c_int(n), C.c_int(int(use_log)))
+        return rc, upd

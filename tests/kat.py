@@ -1,0 +1,106 @@
+"""Harness that replays the reference's start-up sequence for 1-cell batch decks so the
+oracle can be compared with the reference's .regression.gold files.
+
+Sequence restated (test infrastructure, drives oracle functions only):
+  1. PatchInitCouplerConstraints (src/pflotran/patch.F90:3346-3461): equilibrate the
+     constraint on the coupler's own auxvar with den_kg = reference water density,
+     porosity = option%reference_porosity = 0.25 (option.F90:479), sat = 1.
+  2. CondControlAssignTranInitCond (condition_control.F90:498-949): cell auxvar is fresh
+     (act coefs 1, free site 1e-9); xx = basis_molarity / den_kg * 1000; mineral volume
+     fractions / areas from the constraint; multirate sorbed + free sites copied.
+  3. RTUpdateAuxVars once without, then twice with activity-coefficient updates
+     (condition_control.F90:940-946).
+"""
+import math
+import os
+import re
+
+import numpy as np
+
+from pflotran_b200 import abi
+from pflotran_b200.chem import read_deck, build_tables
+from pflotran_b200.chem.setup import constraint_arrays, mineral_arrays
+from oracle.pyoracle import Oracle
+
+
+def read_gold(path):
+    out = {}
+    name = None
+    with open(path) as f:
+        for line in f:
+            m = re.match(r'^-- (\w+): (.*) --', line)
+            if m:
+                name = m.group(2).strip()
+                out[name] = {}
+                continue
+            m = re.match(r'^\s*(\w[\w ()-]*):\s+(\S+)\s*$', line)
+            if m and name is not None:
+                try:
+                    out[name][m.group(1).strip()] = float(m.group(2))
+                except ValueError:
+                    pass
+    return out
+
+
+def fill_scalars(st, t, porosity, volume=1.0):
+    st['DEN_KG'][:] = t.reference_water_density
+    st['SAT'][:] = 1.0
+    st['TEMP'][:] = t.reference_temperature
+    st['PRES'][:] = t.reference_pressure
+    st['VOLUME'][:] = volume
+    st['POROSITY'][:] = porosity
+    st['SOIL_PARTICLE_DENSITY'][:] = -999.0
+
+
+def initial_cell(deck_path, constraint='initial', porosity=None, volume=1.0):
+    deck = read_deck(deck_path)
+    t = build_tables(deck)
+    orc = Oracle(t)
+    c = deck.constraints[constraint]
+    ctype, conc, cid, guess = constraint_arrays(t, c)
+    vf, area = mineral_arrays(t, c)
+    # 1. coupler auxvar
+    cst = abi.HostState(t, 1)
+    fill_scalars(cst, t, 0.25, volume)
+    cst['MNRL_VOLFRAC'][:, 0] = vf
+    cst['MNRL_AREA'][:, 0] = area
+    basis_molarity, nit = orc.equilibrate(cst, 0, ctype, conc, cid, guess, use_prev=False)
+    # 2. the grid cell
+    st = abi.HostState(t, 1)
+    fill_scalars(st, t, deck.porosity if porosity is None else porosity, volume)
+    st['MNRL_VOLFRAC'][:, 0] = vf
+    st['MNRL_AREA'][:, 0] = area
+    if t.nkinmrsrfcplxrxn > 0:
+        st['KINMR_TOTAL_SORB'][:] = cst['KINMR_TOTAL_SORB']
+        st['FREE_SITE_CONC'][:] = cst['FREE_SITE_CONC']
+    xx = (basis_molarity / t.reference_water_density * 1000.0).reshape(1, -1).copy()
+    # 3.
+    orc.update_auxvars(st, xx, False)
+    if t.act_coef_update_frequency != 0:
+        orc.update_auxvars(st, xx, True)
+        orc.update_auxvars(st, xx, True)
+    return deck, t, orc, st, xx, nit, cst
+
+
+def outputs(t, st, cell=0):
+    """Variables as the reference prints them (patch.F90 PatchGetVariable)."""
+    o = {}
+    if t.h_ion_id > 0:
+        h = t.h_ion_id - 1
+        o['pH'] = -math.log10(st['PRI_ACT_COEF'][h, cell] * st['PRI_MOLAL'][h, cell])
+    den = st['DEN_KG'][0, cell]
+    for i, n in enumerate(t.primary_species_names):
+        tot = st['TOTAL'][i, cell]
+        o['Total ' + n] = tot / den * 1000.0 if t.initialize_with_molality else tot
+        o['Free ' + n] = st['PRI_MOLAL'][i, cell] if t.initialize_with_molality else \
+            st['PRI_MOLAL'][i, cell] * den / 1000.0
+        o['Gamma ' + n] = st['PRI_ACT_COEF'][i, cell]
+        o['Total Sorbed ' + n] = st['TOTAL_SORB_EQ'][i, cell]
+    for i, n in enumerate(t.kinmnrl_names):
+        o[n + ' VF'] = st['MNRL_VOLFRAC'][i, cell]
+        o[n + ' Rate'] = st['MNRL_RATE'][i, cell]
+    for i, n in enumerate(t.srfcplx_names):
+        o[n] = st['EQSRFCPLX_CONC'][i, cell]
+    for i, n in enumerate(t.srfcplxrxn_site_names):
+        o['Free ' + n] = st['FREE_SITE_CONC'][i, cell]
+    return o
