@@ -227,6 +227,13 @@ int rxn_tables_destroy(RxnTables *t);
 int rxn_state_create(const RxnTables *t, int64_t ncells_ghosted, RxnState **out);
 int rxn_state_destroy(RxnState *s);
 int64_t rxn_state_ncells(const RxnState *s);
+/* DTOTAL / DTOTAL_SORB_EQ (naq^2 rows each) are not kept in HBM unless asked for: the
+ * flux-side consumers (TFluxDerivative, transport.F90:368-626) need them, RReact does not.
+ * After this call rxn_update_auxvars_batch / rxn_react_batch also store that field. */
+int rxn_state_materialize(RxnState *s, int field);
+/* 0 = automatic, 1 = one thread per cell, 2 = cooperative lane-group per cell (fails if the
+ * tables do not fit it).  Benchmark / test control only; results are the same path. */
+int rxn_set_react_kernel(RxnState *s, int which);
 int32_t rxn_field_rows(const RxnTables *t, int field);
 
 /* replaces: direct field access by PatchGetVariable (patch.F90:3529-4788), checkpoint
@@ -275,6 +282,11 @@ int rxn_residual_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, d
 int rxn_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt,
                               double *jac_out);
 
+/* both of the above in one launch (the reference evaluates RTResidual and RTJacobian on the
+ * same iterate); either output may be NULL. */
+int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt,
+                                       double *res_out, double *jac_out);
+
 /* replaces: RTUpdateKineticState loop (reactive_transport.F90:692-705) =
  * RUpdateKineticState per cell (reaction.F90:5320-5429). */
 int rxn_update_kinetic_state_batch(RxnState *s, double dt);
@@ -290,6 +302,9 @@ int rxn_device_alloc(RxnState *s, int64_t bytes, void **d_ptr);
 int rxn_device_free(RxnState *s, void *d_ptr);
 int rxn_device_copy(RxnState *s, void *dst, const void *src, int64_t bytes, int kind /*0 h2d,1 d2h,2 d2d*/);
 int rxn_device_sync(RxnState *s);
+/* pinned host memory for the caller's tran_xx / result buffers (optional, faster PCIe) */
+int rxn_host_alloc(int64_t bytes, void **h_ptr);
+int rxn_host_free(void *h_ptr);
 
 /* replaces: option%io_buffer */
 int rxn_last_error(char *buf, int32_t len);

@@ -585,7 +585,10 @@ def read_deck(path: str) -> Deck:
         elif kw == 'MATERIAL_PROPERTY':
             for t in rd.block():
                 if t[0].upper() == 'POROSITY' and porosity is None:
-                    porosity = fnum(t[1])
+                    try:
+                        porosity = fnum(t[1])
+                    except ValueError:      # POROSITY DATASET name: per-cell values, not ours
+                        porosity = None
                 elif t[0].upper() in ('PERMEABILITY', 'SATURATION_FUNCTION'):
                     # nested blocks
                     if len(t) == 1 or t[0].upper() == 'PERMEABILITY':

@@ -1,0 +1,518 @@
+// rxn_b200.cu — C ABI (include/rxn_b200.h) of the B200-native batched reaction path.
+//
+// Host side: validates and packs the reference's reaction tables into one device blob, owns
+// the SoA FP64 cell state in HBM, and launches the batched kernels (rxn_kernels.cuh).
+// There is NO CPU fallback: without a usable CUDA device every entry point fails with
+// RXN_ERR_NO_DEVICE / RXN_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rxn_b200.h"
+#include "rxn_kernels.cuh"
+#include "rxn_pack.h"
+#include "rxn_tile.cuh"
+
+using namespace rxn;
+
+namespace {
+
+thread_local std::string g_err;
+long long g_launches = 0;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RXN_ERR_NO_DEVICE : RXN_ERR_CUDA, \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+}  // namespace
+
+struct RxnTables {
+  DevTab h;
+  TilePlan tile;           // cooperative (lane-group per cell) kernel plan, rxn_tile.cuh
+  double *d_blob = nullptr;
+  size_t blob_bytes = 0;
+  int device = 0;
+  int rows[RXN_F_COUNT];
+  int nvariant = 0;        // template instantiation (max naq)
+};
+
+struct RxnState {
+  const RxnTables *t = nullptr;
+  DevState S;
+  uint8_t *d_active = nullptr;
+  long long ncells = 0, ld = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  // grow-only scratch for the host-buffer entry points
+  void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[4] = {0, 0, 0, 0};
+  int react_kernel = 0;    // 0 auto, 1 thread-per-cell, 2 tile
+};
+
+namespace {
+
+int ensure_scratch(RxnState *s, int k, size_t bytes, void **out) {
+  if (s->scratch_bytes[k] < bytes) {
+    if (s->scratch[k]) cudaFree(s->scratch[k]);
+    s->scratch[k] = nullptr;
+    s->scratch_bytes[k] = 0;
+    CU(cudaMalloc(&s->scratch[k], bytes));
+    s->scratch_bytes[k] = bytes;
+  }
+  *out = s->scratch[k];
+  return RXN_OK;
+}
+
+inline unsigned nblocks(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// dispatch on the compile-time bound of naqcomp (rxn_variant.cu)
+#define RXN_DISPATCH(nv, FN, ...)                    \
+  do {                                               \
+    switch (nv) {                                    \
+      case 4: FN<4>(__VA_ARGS__); break;             \
+      case 8: FN<8>(__VA_ARGS__); break;             \
+      case 16: FN<16>(__VA_ARGS__); break;           \
+      default: FN<24>(__VA_ARGS__); break;           \
+    }                                                \
+    ++g_launches;                                    \
+  } while (0)
+
+// AoS/strided host image <-> SoA field.  tmp element (row r, cell c) at tmp[r*rs + c*cs].
+__global__ void k_field_from_strided(double *dst, long long ld, long long ncells, int rows, const double *__restrict__ tmp,
+                                     long long rs, long long cs) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  for (int r = 0; r < rows; ++r) dst[r * ld + c] = tmp[r * rs + c * cs];
+}
+__global__ void k_field_to_strided(const double *__restrict__ src, long long ld, long long ncells, int rows, double *tmp,
+                                   long long rs, long long cs) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  for (int r = 0; r < rows; ++r) tmp[r * rs + c * cs] = src[r * ld + c];
+}
+__global__ void k_fill(double *dst, long long n, double v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+
+int check_launch(RxnState *s, bool timed) {
+  if (timed) {
+    CU(cudaEventRecord(s->ev1, s->stream));
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  if (timed) CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+  return RXN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rxn_version(void) { return "pflotran_b200 rxn 0.2 (sm_100a)"; }
+
+int rxn_last_error(char *buf, int32_t len) {
+  if (buf && len > 0) {
+    strncpy(buf, g_err.c_str(), (size_t)len - 1);
+    buf[len - 1] = 0;
+  }
+  return (int)g_err.size();
+}
+
+int64_t rxn_launch_count(void) { return g_launches; }
+
+int rxn_tables_create(const RxnTablesDesc *d, int device, RxnTables **out) {
+  if (!d || !out) return fail(RXN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  PackResult R;
+  int rc = pack_tables(d, R);
+  if (rc != RXN_OK) return fail(rc, "%s", R.err.c_str());
+  RxnTables *t = new RxnTables();
+  t->h = R.h;
+  DevTab &h = t->h;
+  Packer &P = R.P;
+  memcpy(t->rows, R.rows, sizeof t->rows);
+  t->blob_bytes = (size_t)h.ndbl * 8 + (size_t)h.nint * 4;
+  if (t->blob_bytes > 160 * 1024) { delete t; return fail(RXN_ERR_UNSUPPORTED, "chemistry tables (%zu bytes) exceed the shared-memory staging budget", t->blob_bytes); }
+  std::vector<unsigned char> blob = blob_bytes(R);
+  t->nvariant = variant_for(h.naq);
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { delete t; return fail(RXN_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e)); }
+  if (device < 0 || device >= ndev) { delete t; return fail(RXN_ERR_INVALID, "device %d out of range (%d devices)", device, ndev); }
+  t->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&t->d_blob, t->blob_bytes) != cudaSuccess ||
+      cudaMemcpy(t->d_blob, blob.data(), t->blob_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    int rc2 = fail(RXN_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete t;
+    return rc2;
+  }
+  rc = tile_plan_build(d, h, P.d, P.i, &t->tile);
+  if (rc != RXN_OK) { int rc2 = fail(rc, "tile plan: %s", t->tile.err.c_str()); cudaFree(t->d_blob); delete t; return rc2; }
+  *out = t;
+  return RXN_OK;
+}
+
+int rxn_tables_destroy(RxnTables *t) {
+  if (!t) return RXN_OK;
+  cudaSetDevice(t->device);
+  if (t->d_blob) cudaFree(t->d_blob);
+  tile_plan_free(&t->tile);
+  delete t;
+  return RXN_OK;
+}
+
+int32_t rxn_field_rows(const RxnTables *t, int field) {
+  if (!t || field < 0 || field >= RXN_F_COUNT) return -1;
+  return t->rows[field];
+}
+
+static int alloc_field(RxnState *s, int f) {
+  if (s->S.f[f] || s->t->rows[f] == 0) return RXN_OK;
+  const size_t n = (size_t)s->t->rows[f] * s->ld;
+  CU(cudaMalloc(&s->S.f[f], n * 8));
+  double v = 0.0;
+  if (f == RXN_F_PRI_ACT_COEF || f == RXN_F_SEC_ACT_COEF) v = 1.0;                 // reactive_transport_aux.F90:240-260
+  if (f == RXN_F_FREE_SITE_CONC || f == RXN_F_EQIONX_REF_CATION_SORBED_CONC) v = 1.0e-9;   // :300, :335
+  if (v == 0.0) CU(cudaMemsetAsync(s->S.f[f], 0, n * 8, s->stream));
+  else { k_fill<<<nblocks((long long)n, 256), 256, 0, s->stream>>>(s->S.f[f], (long long)n, v); ++g_launches; }
+  return RXN_OK;
+}
+
+int rxn_state_create(const RxnTables *t, int64_t ncells, RxnState **out) {
+  if (!t || !out || ncells < 1) return fail(RXN_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  CU(cudaSetDevice(t->device));
+  RxnState *s = new RxnState();
+  s->t = t;
+  s->ncells = ncells;
+  s->ld = (ncells + 31) / 32 * 32;
+  memset(&s->S, 0, sizeof s->S);
+  s->S.ld = s->ld; s->S.ncells = ncells;
+  if (const char *e = getenv("RXN_REACT_KERNEL")) s->react_kernel = atoi(e);
+  int rc = RXN_OK;
+  if (cudaStreamCreate(&s->stream) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
+    rc = fail(RXN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int f = 0; f < RXN_F_COUNT && rc == RXN_OK; ++f) {
+    if (f == RXN_F_DTOTAL || f == RXN_F_DTOTAL_SORB_EQ) continue;   // materialised on demand
+    rc = alloc_field(s, f);
+  }
+  if (rc == RXN_OK && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = fail(RXN_ERR_CUDA, "state init failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc != RXN_OK) { rxn_state_destroy(s); return rc; }
+  *out = s;
+  return RXN_OK;
+}
+
+int rxn_state_destroy(RxnState *s) {
+  if (!s) return RXN_OK;
+  cudaSetDevice(s->t->device);
+  for (int f = 0; f < RXN_F_COUNT; ++f) if (s->S.f[f]) cudaFree(s->S.f[f]);
+  if (s->d_active) cudaFree(s->d_active);
+  for (int k = 0; k < 4; ++k) if (s->scratch[k]) cudaFree(s->scratch[k]);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return RXN_OK;
+}
+
+int64_t rxn_state_ncells(const RxnState *s) { return s ? s->ncells : -1; }
+
+int rxn_state_materialize(RxnState *s, int field) {
+  if (!s || field < 0 || field >= RXN_F_COUNT) return fail(RXN_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(s->t->device));
+  int rc = alloc_field(s, field);
+  if (rc != RXN_OK) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  return RXN_OK;
+}
+
+int rxn_state_upload(RxnState *s, int field, const double *host, int64_t rs, int64_t cs) {
+  if (!s || !host || field < 0 || field >= RXN_F_COUNT) return fail(RXN_ERR_INVALID, "bad argument");
+  const int rows = s->t->rows[field];
+  if (rows == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  int rc = alloc_field(s, field);
+  if (rc != RXN_OK) return rc;
+  if (cs == 1) {
+    CU(cudaMemcpy2DAsync(s->S.f[field], (size_t)s->ld * 8, host, (size_t)rs * 8, (size_t)s->ncells * 8, rows, cudaMemcpyHostToDevice, s->stream));
+  } else {
+    const size_t span = (size_t)(rows - 1) * rs + (size_t)(s->ncells - 1) * cs + 1;
+    void *tmp;
+    rc = ensure_scratch(s, 0, span * 8, &tmp);
+    if (rc != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(tmp, host, span * 8, cudaMemcpyHostToDevice, s->stream));
+    k_field_from_strided<<<nblocks(s->ncells, 256), 256, 0, s->stream>>>(s->S.f[field], s->ld, s->ncells, rows, (const double *)tmp, rs, cs);
+    ++g_launches;
+  }
+  return check_launch(s, false);
+}
+
+int rxn_state_download(const RxnState *cs_, int field, double *host, int64_t rs, int64_t cs) {
+  RxnState *s = const_cast<RxnState *>(cs_);
+  if (!s || !host || field < 0 || field >= RXN_F_COUNT) return fail(RXN_ERR_INVALID, "bad argument");
+  const int rows = s->t->rows[field];
+  if (rows == 0) return RXN_OK;
+  if (!s->S.f[field]) return fail(RXN_ERR_INVALID, "field %d is not materialised (call rxn_state_materialize first)", field);
+  CU(cudaSetDevice(s->t->device));
+  if (cs == 1) {
+    CU(cudaMemcpy2DAsync(host, (size_t)rs * 8, s->S.f[field], (size_t)s->ld * 8, (size_t)s->ncells * 8, rows, cudaMemcpyDeviceToHost, s->stream));
+  } else {
+    const size_t span = (size_t)(rows - 1) * rs + (size_t)(s->ncells - 1) * cs + 1;
+    void *tmp;
+    int rc = ensure_scratch(s, 0, span * 8, &tmp);
+    if (rc != RXN_OK) return rc;
+    // strided destinations may interleave with caller data: start from the caller's bytes
+    CU(cudaMemcpyAsync(tmp, host, span * 8, cudaMemcpyHostToDevice, s->stream));
+    k_field_to_strided<<<nblocks(s->ncells, 256), 256, 0, s->stream>>>(s->S.f[field], s->ld, s->ncells, rows, (double *)tmp, rs, cs);
+    ++g_launches;
+    CU(cudaMemcpyAsync(host, tmp, span * 8, cudaMemcpyDeviceToHost, s->stream));
+  }
+  return check_launch(s, false);
+}
+
+int rxn_set_cell_scalars(RxnState *s, const double *den_kg, const double *sat, const double *temp, const double *pres,
+                         const double *volume, const double *porosity, const double *soil_particle_density,
+                         const uint8_t *active) {
+  if (!s) return fail(RXN_ERR_INVALID, "null state");
+  CU(cudaSetDevice(s->t->device));
+  const double *src[7] = {den_kg, sat, temp, pres, volume, porosity, soil_particle_density};
+  const int fld[7] = {RXN_F_DEN_KG, RXN_F_SAT, RXN_F_TEMP, RXN_F_PRES, RXN_F_VOLUME, RXN_F_POROSITY, RXN_F_SOIL_PARTICLE_DENSITY};
+  for (int k = 0; k < 7; ++k)
+    if (src[k]) CU(cudaMemcpyAsync(s->S.f[fld[k]], src[k], (size_t)s->ncells * 8, cudaMemcpyHostToDevice, s->stream));
+  if (active) {
+    if (!s->d_active) CU(cudaMalloc(&s->d_active, (size_t)s->ld));
+    CU(cudaMemcpyAsync(s->d_active, active, (size_t)s->ncells, cudaMemcpyHostToDevice, s->stream));
+    s->S.active = s->d_active;
+  }
+  return check_launch(s, false);
+}
+
+int rxn_set_react_kernel(RxnState *s, int which) {
+  if (!s || which < 0 || which > 2) return fail(RXN_ERR_INVALID, "bad argument");
+  s->react_kernel = which;
+  return RXN_OK;
+}
+
+static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
+                        int32_t *d_iters, int32_t *d_flags) {
+  const RxnTables *t = s->t;
+  bool use_tile = t->tile.usable && s->react_kernel != 1;
+  if (s->react_kernel == 2 && !t->tile.usable) return fail(RXN_ERR_UNSUPPORTED, "tile kernel unavailable for these tables: %s", t->tile.err.c_str());
+  if (use_tile) {
+    tile_launch_react(t->tile, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->stream);
+    ++g_launches;
+  } else {
+    const int threads = t->nvariant <= 8 ? 128 : 64;
+    const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
+    RXN_DISPATCH(t->nvariant, run_react, L, t->h, (const double *)t->d_blob, s->S, d_xx, d_l2g, (long long)nlocal, dt, dt_mode,
+                 d_iters, d_flags);
+  }
+  return RXN_OK;
+}
+
+int rxn_react_batch_device(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
+                           int32_t *d_iters, int32_t *d_flags) {
+  if (!s || !d_xx || nlocal < 0 || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
+  if (nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  int rc = launch_react(s, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags);
+  if (rc != RXN_OK) return rc;
+  return check_launch(s, true);
+}
+
+int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nlocal, double dt, int dt_mode,
+                    int32_t *iters_out, int32_t *flags_out) {
+  if (!s || !tran_xx || nlocal < 0 || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
+  if (nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const int n = s->t->h.naq;
+  void *d_xx, *d_l2g = nullptr, *d_it, *d_fl;
+  int rc;
+  if ((rc = ensure_scratch(s, 0, (size_t)nlocal * n * 8, &d_xx)) != RXN_OK) return rc;
+  if ((rc = ensure_scratch(s, 2, (size_t)nlocal * 4, &d_it)) != RXN_OK) return rc;
+  if ((rc = ensure_scratch(s, 3, (size_t)nlocal * 4, &d_fl)) != RXN_OK) return rc;
+  if (l2g) {
+    if ((rc = ensure_scratch(s, 1, (size_t)nlocal * 4, &d_l2g)) != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
+  }
+  CU(cudaMemcpyAsync(d_xx, tran_xx, (size_t)nlocal * n * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  rc = launch_react(s, (double *)d_xx, (const int32_t *)d_l2g, nlocal, dt, dt_mode, (int32_t *)d_it, (int32_t *)d_fl);
+  if (rc != RXN_OK) return rc;
+  CU(cudaEventRecord(s->ev1, s->stream));
+  CU(cudaMemcpyAsync(tran_xx, d_xx, (size_t)nlocal * n * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (iters_out) CU(cudaMemcpyAsync(iters_out, d_it, (size_t)nlocal * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (flags_out) CU(cudaMemcpyAsync(flags_out, d_fl, (size_t)nlocal * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+  return RXN_OK;
+}
+
+int rxn_update_auxvars_batch(RxnState *s, const double *xx_loc, int update_act_coefs) {
+  if (!s) return fail(RXN_ERR_INVALID, "null state");
+  CU(cudaSetDevice(s->t->device));
+  const RxnTables *t = s->t;
+  void *d_xx = nullptr;
+  if (xx_loc) {
+    int rc = ensure_scratch(s, 0, (size_t)s->ncells * t->h.naq * 8, &d_xx);
+    if (rc != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(d_xx, xx_loc, (size_t)s->ncells * t->h.naq * 8, cudaMemcpyHostToDevice, s->stream));
+  }
+  CU(cudaEventRecord(s->ev0, s->stream));
+  const int threads = t->nvariant <= 8 ? 128 : 64;
+  const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
+  RXN_DISPATCH(t->nvariant, run_update_auxvars, L, t->h, (const double *)t->d_blob, s->S, (const double *)d_xx, update_act_coefs);
+  return check_launch(s, true);
+}
+
+int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int64_t nlocal, double *accum_out) {
+  if (!s || !accum_out || nlocal < 0) return fail(RXN_ERR_INVALID, "bad argument");
+  if (nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const RxnTables *t = s->t;
+  const int n = t->h.naq;
+  void *d_xx = nullptr, *d_l2g = nullptr, *d_out;
+  int rc;
+  if ((rc = ensure_scratch(s, 2, (size_t)nlocal * n * 8, &d_out)) != RXN_OK) return rc;
+  if (xx) {
+    if ((rc = ensure_scratch(s, 0, (size_t)nlocal * n * 8, &d_xx)) != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(d_xx, xx, (size_t)nlocal * n * 8, cudaMemcpyHostToDevice, s->stream));
+  }
+  if (l2g) {
+    if ((rc = ensure_scratch(s, 1, (size_t)nlocal * 4, &d_l2g)) != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
+  }
+  CU(cudaMemsetAsync(d_out, 0, (size_t)nlocal * n * 8, s->stream));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  const int threads = t->nvariant <= 8 ? 128 : 64;
+  const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
+  RXN_DISPATCH(t->nvariant, run_fixed_accum, L, t->h, (const double *)t->d_blob, s->S, (const double *)d_xx, (const int *)d_l2g,
+               (long long)nlocal, (double *)d_out);
+  CU(cudaEventRecord(s->ev1, s->stream));
+  CU(cudaMemcpyAsync(accum_out, d_out, (size_t)nlocal * n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+  return RXN_OK;
+}
+
+int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt, double *res_out,
+                                       double *jac_out) {
+  if (!s || nlocal < 0 || !(dt > 0.0) || (!res_out && !jac_out)) return fail(RXN_ERR_INVALID, "bad argument");
+  if (nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const RxnTables *t = s->t;
+  const int n = t->h.naq;
+  void *d_res = nullptr, *d_jac = nullptr, *d_l2g = nullptr;
+  int rc;
+  if (res_out) { if ((rc = ensure_scratch(s, 2, (size_t)nlocal * n * 8, &d_res)) != RXN_OK) return rc; CU(cudaMemsetAsync(d_res, 0, (size_t)nlocal * n * 8, s->stream)); }
+  if (jac_out) { if ((rc = ensure_scratch(s, 0, (size_t)nlocal * n * n * 8, &d_jac)) != RXN_OK) return rc; CU(cudaMemsetAsync(d_jac, 0, (size_t)nlocal * n * n * 8, s->stream)); }
+  if (l2g) {
+    if ((rc = ensure_scratch(s, 1, (size_t)nlocal * 4, &d_l2g)) != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
+  }
+  CU(cudaEventRecord(s->ev0, s->stream));
+  const int threads = t->nvariant <= 8 ? 128 : 64;
+  const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
+  RXN_DISPATCH(t->nvariant, run_residual_jacobian, L, t->h, (const double *)t->d_blob, s->S, (const int *)d_l2g, (long long)nlocal,
+               dt, (double *)d_res, (double *)d_jac);
+  CU(cudaEventRecord(s->ev1, s->stream));
+  if (res_out) CU(cudaMemcpyAsync(res_out, d_res, (size_t)nlocal * n * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (jac_out) CU(cudaMemcpyAsync(jac_out, d_jac, (size_t)nlocal * n * n * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+  return RXN_OK;
+}
+
+int rxn_residual_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt, double *res_out) {
+  if (!res_out) return fail(RXN_ERR_INVALID, "null res_out");
+  return rxn_residual_jacobian_blocks_batch(s, l2g, nlocal, dt, res_out, nullptr);
+}
+int rxn_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt, double *jac_out) {
+  if (!jac_out) return fail(RXN_ERR_INVALID, "null jac_out");
+  return rxn_residual_jacobian_blocks_batch(s, l2g, nlocal, dt, nullptr, jac_out);
+}
+
+int rxn_update_kinetic_state_batch(RxnState *s, double dt) {
+  if (!s || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(s->t->device));
+  const RxnTables *t = s->t;
+  CU(cudaEventRecord(s->ev0, s->stream));
+  const int threads = 128;
+  const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
+  RXN_DISPATCH(t->nvariant, run_update_kinetic_state, L, t->h, (const double *)t->d_blob, s->S, dt);
+  return check_launch(s, true);
+}
+
+float rxn_last_kernel_ms(const RxnState *s) { return s ? s->last_ms : -1.f; }
+
+int rxn_state_device_ptr(RxnState *s, int field, double **d_ptr, int64_t *ld) {
+  if (!s || field < 0 || field >= RXN_F_COUNT || !d_ptr) return fail(RXN_ERR_INVALID, "bad argument");
+  *d_ptr = s->S.f[field];
+  if (ld) *ld = s->ld;
+  return RXN_OK;
+}
+int rxn_device_alloc(RxnState *s, int64_t bytes, void **d_ptr) {
+  if (!s || !d_ptr || bytes <= 0) return fail(RXN_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaMalloc(d_ptr, (size_t)bytes));
+  return RXN_OK;
+}
+int rxn_device_free(RxnState *s, void *d_ptr) {
+  if (!s) return fail(RXN_ERR_INVALID, "null state");
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaFree(d_ptr));
+  return RXN_OK;
+}
+int rxn_device_copy(RxnState *s, void *dst, const void *src, int64_t bytes, int kind) {
+  if (!s || !dst || !src || bytes < 0) return fail(RXN_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(s->t->device));
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  CU(cudaMemcpyAsync(dst, src, (size_t)bytes, k, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return RXN_OK;
+}
+int rxn_device_sync(RxnState *s) {
+  if (!s) return fail(RXN_ERR_INVALID, "null state");
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaStreamSynchronize(s->stream));
+  return RXN_OK;
+}
+int rxn_host_alloc(int64_t bytes, void **h_ptr) {
+  if (!h_ptr || bytes <= 0) return fail(RXN_ERR_INVALID, "bad argument");
+  CU(cudaMallocHost(h_ptr, (size_t)bytes));
+  return RXN_OK;
+}
+int rxn_host_free(void *h_ptr) {
+  CU(cudaFreeHost(h_ptr));
+  return RXN_OK;
+}
+
+}  // extern "C"

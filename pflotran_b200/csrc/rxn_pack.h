@@ -1,0 +1,235 @@
+// rxn_pack.h — host-side validation and packing of RxnTablesDesc into the device blob.
+// Pure C++ (no CUDA): reference reaction_type / mineral_type / surface_complexation_type
+// compressed tables (reaction_aux.F90:142-335, reaction_mineral_aux.F90:77-128,
+// reaction_surf_complex_aux.F90:68-128) -> CSR lists with 0-based ids + DevTab offsets.
+#pragma once
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rxn_tab.h"
+
+namespace rxn {
+
+struct Packer {
+  std::vector<double> d;
+  std::vector<int32_t> i;
+  int D(const double *p, size_t n) {
+    int o = (int)d.size();
+    for (size_t k = 0; k < n; ++k) d.push_back(p ? p[k] : 0.0);
+    return o;
+  }
+  int I(const int32_t *p, size_t n) {
+    int o = (int)i.size();
+    for (size_t k = 0; k < n; ++k) i.push_back(p ? p[k] : 0);
+    return o;
+  }
+};
+
+struct PackResult {
+  DevTab h;
+  Packer P;
+  int rows[RXN_F_COUNT];
+  std::string err;
+  int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+// RxnSpecList (Fortran compressed form, 1-based ids) -> CSR with 0-based ids
+inline int pack_spec(PackResult &R, const RxnSpecList &s, int ncoef, int naq, DSpec &o, const char *what) {
+  Packer &P = R.P;
+  o.n = s.n;
+  std::vector<int32_t> ptr(1, 0), id;
+  std::vector<double> st, h2ost((size_t)std::max(s.n, 0), 0.0), logK((size_t)std::max(s.n, 0), 0.0);
+  for (int r = 0; r < s.n; ++r) {
+    const int ns = s.id[(size_t)r * s.id_ld];
+    if (ns < 0 || ns >= s.id_ld + 1) return R.fail(RXN_ERR_INVALID, "%s %d: bad species count %d", what, r, ns);
+    for (int k = 1; k <= ns; ++k) {
+      const int sp = s.id[(size_t)r * s.id_ld + k];
+      if (sp < 1 || sp > naq) return R.fail(RXN_ERR_INVALID, "%s %d: species id %d out of range", what, r, sp);
+      id.push_back(sp - 1);
+      st.push_back(s.stoich[(size_t)r * s.stoich_ld + k - s.stoich_off]);
+    }
+    ptr.push_back((int32_t)id.size());
+    if (s.h2oid && s.h2oid[r] > 0 && s.h2ostoich) h2ost[r] = s.h2ostoich[r];
+    if (s.logK) logK[r] = s.logK[r];
+  }
+  o.o_ptr = P.I(ptr.data(), ptr.size());
+  o.o_id = P.I(id.data(), id.size());
+  o.o_st = P.D(st.data(), st.size());
+  o.o_h2ost = P.D(h2ost.data(), h2ost.size());
+  o.o_logK = P.D(logK.data(), logK.size());
+  o.o_coef = (s.logKcoef && ncoef > 0 && s.n > 0) ? P.D(s.logKcoef, (size_t)s.n * ncoef) : -1;
+  return RXN_OK;
+}
+
+inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
+  if (!d) return R.fail(RXN_ERR_INVALID, "null descriptor");
+  if (d->struct_size != (int)sizeof(RxnTablesDesc))
+    return R.fail(RXN_ERR_INVALID, "RxnTablesDesc.struct_size %d != %d", d->struct_size, (int)sizeof(RxnTablesDesc));
+  // reaction types outside the path
+  if (d->nactive_gas || d->nimmobile || d->ncoll || d->ngeneral_rxn || d->nradiodecay_rxn || d->nmicrobial_rxn ||
+      d->nimmobile_decay_rxn || d->has_sandbox || d->has_clm || d->has_solid_solution || d->co2_flow_mode ||
+      d->numerical_derivatives || d->nkinsrfcplxrxn)
+    return R.fail(RXN_ERR_UNSUPPORTED,
+                  "tables enable a reaction type outside the B200 path (active gas %d, immobile %d, colloids %d, general %d, "
+                  "radioactive decay %d, microbial %d, immobile decay %d, sandbox %d, CLM %d, solid solution %d, CO2 flow mode %d, "
+                  "numerical Jacobian %d, kinetic surface complexation %d)",
+                  d->nactive_gas, d->nimmobile, d->ncoll, d->ngeneral_rxn, d->nradiodecay_rxn, d->nmicrobial_rxn,
+                  d->nimmobile_decay_rxn, d->has_sandbox, d->has_clm, d->has_solid_solution, d->co2_flow_mode,
+                  d->numerical_derivatives, d->nkinsrfcplxrxn);
+  if (d->naqcomp < 1 || d->ncomp != d->naqcomp)
+    return R.fail(RXN_ERR_UNSUPPORTED, "ncomp (%d) must equal naqcomp (%d) >= 1", d->ncomp, d->naqcomp);
+  if (d->naqcomp > RXN_MAX_NAQ) return R.fail(RXN_ERR_UNSUPPORTED, "naqcomp %d > %d", d->naqcomp, (int)RXN_MAX_NAQ);
+  if (d->nkinmrsrfcplxrxn > 2) return R.fail(RXN_ERR_UNSUPPORTED, "more than 2 multirate surface complexation reactions");
+  if (d->max_num_prefactors > RXN_MAX_PREF || d->max_num_prefactor_species > RXN_MAX_PREF_SPEC)
+    return R.fail(RXN_ERR_UNSUPPORTED, "mineral prefactor table too large");
+  if (d->logK_mode != RXN_LOGK_FIXED && !((d->logK_mode == RXN_LOGK_FIT5 && d->num_logK_coef == 5) ||
+                                          (d->logK_mode == RXN_LOGK_HPT && d->num_logK_coef == 17)))
+    return R.fail(RXN_ERR_INVALID, "logK_mode %d with %d coefficients", d->logK_mode, d->num_logK_coef);
+  if (d->act_coef_update_algorithm != RXN_ACT_COEF_ALGORITHM_LAG && d->act_coef_update_algorithm != RXN_ACT_COEF_ALGORITHM_NEWTON)
+    return R.fail(RXN_ERR_INVALID, "act_coef_update_algorithm %d", d->act_coef_update_algorithm);
+
+  DevTab &h = R.h;
+  Packer &P = R.P;
+  memset(&h, 0, sizeof h);
+  const int naq = d->naqcomp;
+  h.naq = naq; h.ncplx = d->eqcplx.n; h.nkin = d->kinmnrl.n; h.nsrf = d->srfcplx.n; h.nrxn = d->nsrfcplxrxn;
+  h.neq = d->neqsrfcplxrxn; h.nmr = d->nkinmrsrfcplxrxn; h.nionx = d->neqionxrxn; h.nkd = d->neqkdrxn;
+  h.neqsorb = h.neq + h.nionx + h.nkd;
+  h.logK_mode = d->logK_mode; h.ncoef = d->num_logK_coef; h.use_log = d->use_log_formulation;
+  h.act_freq = d->act_coef_update_frequency; h.act_alg = d->act_coef_update_algorithm;
+  h.use_act_h2o = d->use_activity_h2o; h.h2o_aq_id = d->h2o_aq_id;
+  h.has_Temkin = d->kinmnrl_Temkin_const != nullptr; h.has_scale = d->kinmnrl_min_scale_factor != nullptr;
+  h.has_power = d->kinmnrl_affinity_power != nullptr;
+  h.maxpref = d->max_num_prefactors; h.maxprefspec = d->max_num_prefactor_species;
+  h.mr_ld = d->kinmr_ld; h.ionx_ld = d->eqionx_ld;
+  h.maxit = 10000;
+  if (const char *e = getenv("RXN_MAX_NEWTON_ITERATIONS")) h.maxit = std::max(1, atoi(e));
+  h.debyeA = d->debyeA; h.debyeB = d->debyeB; h.debyeBdot = d->debyeBdot;
+  h.max_dlnC = d->max_dlnC; h.rel_tol = d->max_relative_change_tolerance; h.res_tol = d->max_residual_tolerance;
+  int rc;
+#define RXN_TRY(x) do { rc = (x); if (rc != RXN_OK) return rc; } while (0)
+  h.o_Z = P.D(d->primary_spec_Z, naq); h.o_a0 = P.D(d->primary_spec_a0, naq);
+  RXN_TRY(pack_spec(R, d->eqcplx, h.ncoef, naq, h.cplx, "aqueous complex"));
+  h.o_cplxZ = P.D(d->eqcplx_Z, h.ncplx); h.o_cplxa0 = P.D(d->eqcplx_a0, h.ncplx);
+  RXN_TRY(pack_spec(R, d->kinmnrl, h.ncoef, naq, h.kin, "kinetic mineral"));
+  const int nk = h.nkin;
+  h.o_k_rate = P.D(d->kinmnrl_rate_constant, nk); h.o_k_Ea = P.D(d->kinmnrl_activation_energy, nk);
+  h.o_k_molar_vol = P.D(d->kinmnrl_molar_vol, nk); h.o_k_aff = P.D(d->kinmnrl_affinity_threshold, nk);
+  h.o_k_lim = P.D(d->kinmnrl_rate_limiter, nk); h.o_k_Temkin = P.D(d->kinmnrl_Temkin_const, nk);
+  h.o_k_scale = P.D(d->kinmnrl_min_scale_factor, nk); h.o_k_power = P.D(d->kinmnrl_affinity_power, nk);
+  h.o_k_npref = P.I(d->kinmnrl_num_prefactors, nk);
+  {
+    const size_t np = (size_t)nk * std::max(h.maxpref, 1), nps = std::max(h.maxprefspec, 1);
+    h.o_pref_rate = P.D(d->kinmnrl_pref_rate, np); h.o_pref_Ea = P.D(d->kinmnrl_pref_activation_energy, np);
+    h.o_pref_id = P.I(d->kinmnrl_prefactor_id, np * (h.maxprefspec + 1));
+    h.o_pref_alpha = P.D(d->kinmnrl_pref_alpha, np * nps); h.o_pref_beta = P.D(d->kinmnrl_pref_beta, np * nps);
+    h.o_pref_atten = P.D(d->kinmnrl_pref_atten_coef, np * nps);
+    if (d->kinmnrl_prefactor_id && d->kinmnrl_num_prefactors)
+      for (int im = 0; im < nk; ++im)
+        for (int ip = 0; ip < d->kinmnrl_num_prefactors[im]; ++ip) {
+          const int32_t *row = d->kinmnrl_prefactor_id + ((size_t)im * std::max(h.maxpref, 1) + ip) * (h.maxprefspec + 1);
+          for (int k = 1; k <= row[0]; ++k)
+            if (row[k] < 1 || row[k] > naq)
+              return R.fail(RXN_ERR_UNSUPPORTED,
+                            "mineral %d prefactor %d on a secondary species (id %d): the reference branch "
+                            "(reaction_mineral.F90:977-979) clobbers its loop variables; not supported",
+                            im + 1, ip + 1, row[k]);
+        }
+  }
+  RXN_TRY(pack_spec(R, d->srfcplx, h.ncoef, naq, h.srf, "surface complex"));
+  h.o_srf_site_st = P.D(d->srfcplx_free_site_stoich, h.nsrf);
+  h.o_rxn_to_surf = P.I(d->srfcplxrxn_to_surf, h.nrxn); h.o_rxn_surf_type = P.I(d->srfcplxrxn_surf_type, h.nrxn);
+  h.o_rxn_flag = P.I(d->srfcplxrxn_stoich_flag, h.nrxn); h.o_rxn_density = P.D(d->srfcplxrxn_site_density, h.nrxn);
+  {
+    std::vector<int32_t> cptr(1, 0), cid;
+    for (int r = 0; r < h.nrxn; ++r) {
+      const int ld = d->srfcplxrxn_to_complex_ld, n = d->srfcplxrxn_to_complex[(size_t)r * ld];
+      if (n > RXN_MAX_SRFCPLX_PER_RXN)
+        return R.fail(RXN_ERR_UNSUPPORTED, "surface complexation reaction %d has %d complexes (> %d)", r + 1, n, (int)RXN_MAX_SRFCPLX_PER_RXN);
+      for (int k = 1; k <= n; ++k) {
+        const int ic = d->srfcplxrxn_to_complex[(size_t)r * ld + k];
+        if (ic < 1 || ic > h.nsrf) return R.fail(RXN_ERR_INVALID, "surface complexation reaction %d: complex id %d out of range", r + 1, ic);
+        cid.push_back(ic - 1);
+      }
+      cptr.push_back((int32_t)cid.size());
+      const int st = d->srfcplxrxn_surf_type[r];
+      if (st == RXN_COLLOID_SURFACE) return R.fail(RXN_ERR_UNSUPPORTED, "colloid surface");
+      if (st == RXN_MINERAL_SURFACE && (d->srfcplxrxn_to_surf[r] < 1 || d->srfcplxrxn_to_surf[r] > nk))
+        return R.fail(RXN_ERR_INVALID, "surface complexation reaction %d: mineral id out of range", r + 1);
+    }
+    h.o_rxn_cptr = P.I(cptr.data(), cptr.size()); h.o_rxn_cid = P.I(cid.data(), cid.size());
+    std::vector<int32_t> eq, mr, mrn;
+    for (int i = 0; i < h.neq; ++i) eq.push_back(d->eqsrfcplxrxn_to_srfcplxrxn[i] - 1);
+    for (int i = 0; i < h.nmr; ++i) {
+      mr.push_back(d->kinmrsrfcplxrxn_to_srfcplxrxn[i] - 1);
+      mrn.push_back(d->kinmr_nrate[i + 1]);
+    }
+    h.o_eq_rxn = P.I(eq.data(), eq.size()); h.o_mr_rxn = P.I(mr.data(), mr.size()); h.o_mr_nrate = P.I(mrn.data(), mrn.size());
+    h.o_mr_rate = P.D(d->kinmr_rate, (size_t)h.nmr * h.mr_ld); h.o_mr_frac = P.D(d->kinmr_frac, (size_t)h.nmr * h.mr_ld);
+  }
+  {
+    std::vector<int32_t> iptr(1, 0), cat;
+    std::vector<double> kk;
+    for (int r = 0; r < h.nionx; ++r) {
+      const int ld = h.ionx_ld + 1, n = d->eqionx_rxn_cationid[(size_t)r * ld];
+      for (int k = 1; k <= n; ++k) {
+        const int ic = d->eqionx_rxn_cationid[(size_t)r * ld + k];
+        if (ic < 1 || ic > naq) return R.fail(RXN_ERR_INVALID, "ion exchange reaction %d: cation id %d out of range", r + 1, ic);
+        cat.push_back(ic - 1);
+        kk.push_back(d->eqionx_rxn_k[(size_t)r * h.ionx_ld + k - 1]);
+      }
+      iptr.push_back((int32_t)cat.size());
+      if (d->eqionx_rxn_to_surf && d->eqionx_rxn_to_surf[r] > nk)
+        return R.fail(RXN_ERR_INVALID, "ion exchange reaction %d: mineral id out of range", r + 1);
+    }
+    h.o_ionx_ptr = P.I(iptr.data(), iptr.size()); h.o_ionx_cat = P.I(cat.data(), cat.size());
+    h.o_ionx_k = P.D(kk.data(), kk.size()); h.o_ionx_CEC = P.D(d->eqionx_rxn_CEC, h.nionx);
+    h.o_ionx_Zflag = P.I(d->eqionx_rxn_Z_flag, h.nionx); h.o_ionx_to_surf = P.I(d->eqionx_rxn_to_surf, h.nionx);
+  }
+  for (int r = 0; r < h.nkd; ++r) {
+    if (d->eqkdspecid[r] < 1 || d->eqkdspecid[r] > naq) return R.fail(RXN_ERR_INVALID, "KD reaction %d: species id out of range", r + 1);
+    if (d->eqkdmineral && d->eqkdmineral[r] > nk) return R.fail(RXN_ERR_INVALID, "KD reaction %d: mineral id out of range", r + 1);
+  }
+  h.o_kd_spec = P.I(d->eqkdspecid, h.nkd); h.o_kd_type = P.I(d->eqkdtype, h.nkd); h.o_kd_mnrl = P.I(d->eqkdmineral, h.nkd);
+  h.o_kd_coef = P.D(d->eqkddistcoef, h.nkd); h.o_kd_b = P.D(d->eqkdlangmuirb, h.nkd); h.o_kd_n = P.D(d->eqkdfreundlichn, h.nkd);
+#undef RXN_TRY
+  if (P.i.size() & 1) P.i.push_back(0);
+  h.ndbl = (int)P.d.size(); h.nint = (int)P.i.size();
+
+  const int maxrate = d->kinmr_ld;
+  int *r = R.rows;
+  r[RXN_F_PRI_MOLAL] = naq; r[RXN_F_TOTAL] = naq; r[RXN_F_SEC_MOLAL] = h.ncplx; r[RXN_F_PRI_ACT_COEF] = naq;
+  r[RXN_F_SEC_ACT_COEF] = h.ncplx; r[RXN_F_LN_ACT_H2O] = 1; r[RXN_F_TOTAL_SORB_EQ] = naq;
+  r[RXN_F_FREE_SITE_CONC] = h.nrxn; r[RXN_F_EQSRFCPLX_CONC] = h.nsrf;
+  r[RXN_F_KINMR_TOTAL_SORB] = h.nmr * (maxrate + 1) * naq;
+  r[RXN_F_EQIONX_REF_CATION_SORBED_CONC] = h.nionx; r[RXN_F_EQIONX_CONC] = h.nionx * h.ionx_ld;
+  r[RXN_F_MNRL_VOLFRAC] = nk; r[RXN_F_MNRL_AREA] = nk; r[RXN_F_MNRL_RATE] = nk;
+  r[RXN_F_DEN_KG] = r[RXN_F_SAT] = r[RXN_F_TEMP] = r[RXN_F_PRES] = r[RXN_F_VOLUME] = r[RXN_F_POROSITY] =
+      r[RXN_F_SOIL_PARTICLE_DENSITY] = 1;
+  r[RXN_F_DTOTAL] = naq * naq; r[RXN_F_DTOTAL_SORB_EQ] = naq * naq;
+  return RXN_OK;
+}
+
+inline std::vector<unsigned char> blob_bytes(const PackResult &R) {
+  std::vector<unsigned char> blob((size_t)R.h.ndbl * 8 + (size_t)R.h.nint * 4);
+  memcpy(blob.data(), R.P.d.data(), (size_t)R.h.ndbl * 8);
+  memcpy(blob.data() + (size_t)R.h.ndbl * 8, R.P.i.data(), (size_t)R.h.nint * 4);
+  return blob;
+}
+
+inline int variant_for(int naq) { return naq <= 4 ? 4 : naq <= 8 ? 8 : naq <= 16 ? 16 : 24; }
+
+}  // namespace rxn

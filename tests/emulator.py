@@ -1,0 +1,109 @@
+"""ctypes wrapper of tests/emul/libemul.so — the HOST compilation of the CUDA device routines.
+
+TEST INFRASTRUCTURE (see tests/emul/emul.cpp): lets the CPU-only suite compare the device
+code's logic and the table packer with the oracle.  Never imported by pflotran_b200.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from pflotran_b200 import abi
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emul')
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, 'libemul.so')
+    deps = [os.path.join(_HERE, 'emul.cpp')] + [os.path.join(_ROOT, 'pflotran_b200', 'csrc', f)
+                                                 for f in ('rxn_device.cuh', 'rxn_pack.h', 'rxn_tab.h')] + \
+        [os.path.join(_ROOT, 'include', 'rxn_b200.h')]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off',
+                               '-o', so, os.path.join(_HERE, 'emul.cpp')])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.emu_create.restype = C.c_void_p
+        _LIB.emu_create.argtypes = [C.POINTER(abi.RxnTablesDesc), C.c_char_p, C.c_int]
+        _LIB.emu_destroy.argtypes = [C.c_void_p]
+        _LIB.emu_set_maxit.argtypes = [C.c_void_p, C.c_int]
+        _LIB.emu_pack_status.argtypes = [C.POINTER(abi.RxnTablesDesc), C.c_char_p, C.c_int]
+    return _LIB
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+
+
+def pack_status(tables_or_desc):
+    d = tables_or_desc if isinstance(tables_or_desc, abi.RxnTablesDesc) else abi.make_desc(tables_or_desc)
+    buf = C.create_string_buffer(1024)
+    rc = lib().emu_pack_status(C.byref(d), buf, 1024)
+    return rc, buf.value.decode()
+
+
+class Emulator:
+    def __init__(self, tables):
+        self.t = tables
+        self.desc = abi.make_desc(tables)
+        buf = C.create_string_buffer(1024)
+        h = lib().emu_create(C.byref(self.desc), buf, 1024)
+        if not h:
+            raise RuntimeError(buf.value.decode())
+        self.h = C.c_void_p(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().emu_destroy(self.h)
+        except Exception:
+            pass
+
+    def react(self, st, tran_xx, dt, dt_mode=abi.RXN_DT_CONSISTENT, l2g=None, maxit=None):
+        if maxit is not None:
+            lib().emu_set_maxit(self.h, maxit)
+        n = tran_xx.shape[0]
+        iters = np.zeros(n, dtype=np.int32)
+        flags = np.zeros(n, dtype=np.int32)
+        v = st.view()
+        rc = lib().emu_react_batch(self.h, C.byref(v), _p(tran_xx, C.c_double), _p(st.active, C.c_uint8),
+                                   _p(l2g, C.c_int32), C.c_int64(n), C.c_double(dt), C.c_int(dt_mode),
+                                   _p(iters, C.c_int32), _p(flags, C.c_int32))
+        assert rc == 0
+        return iters, flags
+
+    def update_auxvars(self, st, xx_loc, update_act_coefs):
+        v = st.view()
+        assert lib().emu_update_auxvars_batch(self.h, C.byref(v), _p(xx_loc, C.c_double), _p(st.active, C.c_uint8),
+                                              C.c_int(int(update_act_coefs))) == 0
+
+    def fixed_accum(self, st, xx, l2g=None):
+        n = st.ncells if l2g is None else len(l2g)
+        out = np.zeros((n, self.t.ncomp))
+        v = st.view()
+        assert lib().emu_fixed_accum_batch(self.h, C.byref(v), _p(xx, C.c_double), _p(st.active, C.c_uint8),
+                                           _p(l2g, C.c_int32), C.c_int64(n), _p(out, C.c_double)) == 0
+        return out
+
+    def residual_jacobian(self, st, dt, l2g=None):
+        n = st.ncells if l2g is None else len(l2g)
+        nc = self.t.ncomp
+        res = np.zeros((n, nc))
+        jac = np.zeros((n, nc * nc))
+        v = st.view()
+        assert lib().emu_residual_jacobian_batch(self.h, C.byref(v), _p(st.active, C.c_uint8), _p(l2g, C.c_int32),
+                                                 C.c_int64(n), C.c_double(dt), _p(res, C.c_double),
+                                                 _p(jac, C.c_double)) == 0
+        return res, jac
+
+    def update_kinetic_state(self, st, dt):
+        v = st.view()
+        assert lib().emu_update_kinetic_state_batch(self.h, C.byref(v), _p(st.active, C.c_uint8), C.c_double(dt)) == 0

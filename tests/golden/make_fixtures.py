@@ -1,0 +1,76 @@
+"""Generates the committed fixtures under tests/golden/ from the reference's own decks and
+thermodynamic databases.  Run in the BUILD container only (needs /root/reference):
+
+    python tests/golden/make_fixtures.py
+
+For every workload it writes tests/golden/<name>.json holding
+  * the flat chemistry tables (ReactionTables) built from the deck + .dat database,
+  * the equilibrated 1-cell base state of the deck's initial constraint (oracle run of
+    ReactionEquilibrateConstraint + RTUpdateAuxVars, the reference's start-up sequence),
+  * the gold values of the reference's .regression.gold file when the deck has one.
+The GPU box has no /root/reference: tests, smoke() and bench.py read only these files.
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import numpy as np  # noqa: E402
+
+import kat  # noqa: E402
+from pflotran_b200 import abi  # noqa: E402
+
+REF = '/root/reference'
+
+WORKLOADS = {
+    # name: (deck, constraint, gold or None)
+    'calcite': ('example_problems/100_100_100/calcite/pflotran.in', 'initial', None),
+    'hanford300a_eq': ('regression_tests/default/543/543_hanford_srfcplx_base.in', 'groundwater', None),
+    'hanford300a_mr': ('regression_tests/default/543/543_hanford_srfcplx_mr.in', 'groundwater', None),
+    'hpt_calcite': ('regression_tests/geothermal_hpt/1D_Calcite/calcite_tran_only_hpt.in', 'initial', None),
+    'carbonate_unit': ('regression_tests/ascem/batch/carbonate-unit-activity.in', 'initial',
+                       'regression_tests/ascem/batch/carbonate-unit-activity.regression.gold'),
+    'carbonate_dh': ('regression_tests/ascem/batch/carbonate-debye-huckel-activity.in', 'initial',
+                     'regression_tests/ascem/batch/carbonate-debye-huckel-activity.regression.gold'),
+    'ca_carbonate_unit': ('regression_tests/ascem/batch/ca-carbonate-unit-activity.in', 'initial',
+                          'regression_tests/ascem/batch/ca-carbonate-unit-activity.regression.gold'),
+    'ca_carbonate_dh': ('regression_tests/ascem/batch/ca-carbonate-debye-huckel-activity.in', 'initial',
+                        'regression_tests/ascem/batch/ca-carbonate-debye-huckel-activity.regression.gold'),
+    'calcite_kinetics': ('regression_tests/ascem/batch/calcite-kinetics.in', 'initial',
+                         'regression_tests/ascem/batch/calcite-kinetics.regression.gold'),
+    'ion_exchange': ('regression_tests/ascem/batch/ion-exchange-valocchi.in', 'initial',
+                     'regression_tests/ascem/batch/ion-exchange-valocchi.regression.gold'),
+    'surface_complexation': ('regression_tests/ascem/batch/surface-complexation-1.in', 'initial',
+                             'regression_tests/ascem/batch/surface-complexation-1.regression.gold'),
+    'kd_w_mineral': ('regression_tests/default/batch/solute_KD_w_mineral.in', 'initial',
+                     'regression_tests/default/batch/solute_KD_w_mineral.regression.gold'),
+    'kd_wo_mineral': ('regression_tests/default/batch/solute_KD_wo_mineral.in', 'initial',
+                      'regression_tests/default/batch/solute_KD_wo_mineral.regression.gold'),
+}
+
+
+def main():
+    for name, (deck, constraint, gold) in WORKLOADS.items():
+        path = os.path.join(REF, deck)
+        d, t, orc, st, xx, nit, cst = kat.initial_cell(path, constraint=constraint)
+        base = {f: [repr(float(x)) for x in st[f][:, 0]] for f in abi.FIELDS
+                if f not in ('DTOTAL', 'DTOTAL_SORB_EQ')}
+        out = {
+            'name': name, 'deck': deck, 'constraint': constraint, 'equilibrate_iterations': int(nit),
+            'porosity': d.porosity, 'tables': t.to_dict(), 'base': base,
+        }
+        if gold:
+            g = kat.read_gold(os.path.join(REF, gold))
+            out['gold_file'] = gold
+            out['gold'] = {k: v for k, v in g.items() if isinstance(v, dict) and v}
+        with open(os.path.join(HERE, name + '.json'), 'w') as f:
+            json.dump(out, f, separators=(',', ':'))
+        print(name, t.work_counts(), 'equilibrate its', nit, os.path.getsize(os.path.join(HERE, name + '.json')), 'bytes')
+
+
+if __name__ == '__main__':
+    main()
