@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — reaction cell-updates/s of the batched RReact path on N B200s (one rank per GPU).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (CUDA, through the C ABI)
+  python bench.py --impl reference --steps 3 --warmup 1    # reference arm: the CPU path on host cores
+
+A step = one RTReact pass (reference src/pflotran/reactive_transport.F90:1605-1806) over this
+rank's batch of synthetic cells (pflotran_b200/synth.py).  Every step starts from the
+same inputs (transported totals in tran_xx, initial guess = base state), restored on the device
+inside the timed region, so no step is cheaper than the first.
+
+Timed regions (CUDA events on the library's stream, barrier + synchronize on both sides, max
+over ranks):
+  value  : K x (device-side input restore + react kernel), inputs resident in HBM
+  e2e    : K x (pinned host tran_xx -> H2D -> restore + kernel -> D2H of free-ion result, iteration
+           counts and flags) through the public host-buffer call Realization.RTReact
+  roofline.achieved : the react kernel alone (rxn_last_kernel_ms, CUDA events around the launch)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from pflotran_b200 import abi, synth  # noqa: E402
+
+METRIC = 'reaction cell-updates/sec'
+UNIT = 'cell-updates/s'
+DEFAULT_CELLS = {'hanford300a_eq': 10_000_000, 'hanford300a_mr': 5_000_000, 'calcite': 1_000_000,
+                 'hpt_calcite': 1_000_000}
+WORKLOAD_DESC = {
+    'hanford300a_eq': 'hanford/300A U(VI) chemistry (15 primaries, 88 complexes, 2 kinetic minerals, equilibrium surface '
+                      'complexation; deck regression_tests/default/543/543_hanford_srfcplx_base.in), synthetic grid',
+    'hanford300a_mr': '300A chemistry with 50-rate multirate surface complexation (543_hanford_srfcplx_mr.in)',
+    'calcite': 'example_problems/100_100_100 calcite chemistry (4 primaries, 5 complexes, 1 kinetic mineral)',
+    'hpt_calcite': 'geothermal-hpt.dat calcite chemistry, per-cell T,P dependent logK',
+}
+RESET_FIELDS = ['PRI_MOLAL', 'PRI_ACT_COEF', 'SEC_MOLAL', 'SEC_ACT_COEF', 'LN_ACT_H2O', 'TOTAL_SORB_EQ', 'FREE_SITE_CONC',
+                'EQIONX_REF_CATION_SORBED_CONC']
+
+
+# ------------------------------------------------------------------------------------------------
+def work_model(t, iters_sum: float, ncells: int):
+    """Algorithmic work per SURVEY.md 8d: flop-equivalents (W = 20 per transcendental) and
+    compulsory bytes for `ncells` cell-updates whose Newton iteration counts sum to iters_sum."""
+    naq, ncomp, ncplx, nkin = t.naqcomp, t.ncomp, t.neqcplx, t.nkinmnrl
+    S = int(sum(t.eqcplxspecid[k, 0] for k in range(ncplx)))
+    S2 = int(sum(int(t.eqcplxspecid[k, 0]) ** 2 for k in range(ncplx)))
+    nsrf, nrxn = t.nsrfcplx, t.nsrfcplxrxn
+    nrate = t.kinmr_max_nrate if t.nkinmrsrfcplxrxn else 0
+    srf_n2 = int(sum(int(t.srfcplxspecid[k, 0]) ** 2 for k in range(nsrf)))
+    F_rtotal = 7 * S + 2 * ncplx + 2 * S2 + naq + naq * naq
+    F_lu = (2.0 / 3.0) * ncomp ** 3 + 4 * ncomp ** 2
+    F_sorb = 12 * srf_n2 + 4 * naq * (1 + (1 if nrate else 0)) if nsrf else 0
+    kin_n2 = int(sum(int(t.kinmnrlspecid[k, 0]) ** 2 for k in range(nkin)))
+    F_min = 20 * nkin + 2 * kin_n2
+    k = iters_sum / ncells
+    a = k if t.act_coef_update_frequency == 2 else (1 if t.act_coef_update_frequency == 1 else 0)
+    F = (k + 1) * (F_rtotal + F_sorb) + k * (F_lu + 4 * naq * naq + F_min) + a * 15 * (naq + ncplx)
+    its_site = 2
+    Nt = (k + 1) * (2 * naq + ncplx + S + nsrf * its_site) + k * (nkin * 2 + 2 * naq) + a * (naq + ncplx + 1)
+    flop_eq = F + 20.0 * Nt
+    rd = ncomp + naq + ncplx + 7 + 2 * nkin + nrxn + naq * nrate * t.nkinmrsrfcplxrxn
+    wr = ncomp + naq + naq + ncplx + naq + ncplx + nkin + nrxn + nsrf + naq + naq * t.nkinmrsrfcplxrxn + 1
+    return {'flop_eq_per_cell': flop_eq, 'flops_per_cell': F, 'transcendentals_per_cell': Nt,
+            'bytes_per_cell': 8.0 * (rd + wr), 'mean_newton_iterations': k}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7 or not (t0 <= ts <= t1 + 0.2):
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(w, ncells_sample: int, start: int, dt: float, threads: int, repeats: int = 1):
+    """Times the CPU restatement of the reference's RTReact loop (oracle/, kind "port": no Fortran
+    compiler exists in this image) on `ncells_sample` cells with `threads` host threads."""
+    from oracle.pyoracle import Oracle
+    cells = synth.make_cells(w, start, ncells_sample)
+    orc = Oracle(w.tables)
+    best = None
+    iters = None
+    for _ in range(repeats):
+        st = synth.host_state(w, cells)
+        xx = cells['tran_xx'].copy()
+        t0 = time.perf_counter()
+        iters, flags = orc.react(st, xx, dt, abi.RXN_DT_CONSISTENT, maxit=10000, nthreads=threads)
+        el = time.perf_counter() - t0
+        best = el if best is None else min(best, el)
+    return ncells_sample / best, best, float(iters.mean())
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    w = synth.Workload(args.workload)
+    threads = os.cpu_count() or 1
+    # size the per-step sample for ~6 s of CPU work
+    rate0, _, _ = cpu_reference_rate(w, 4096 * max(1, threads // 4), 0, args.dt, threads)
+    sample = int(max(4096, min(DEFAULT_CELLS[args.workload], rate0 * 6.0)) // 4096 * 4096)
+    for _ in range(args.warmup):
+        cpu_reference_rate(w, min(sample, 8192 * threads), 0, args.dt, threads)
+    t_tot = 0.0
+    k_mean = 0.0
+    for s in range(args.steps):
+        rate, el, km = cpu_reference_rate(w, sample, 0, args.dt, threads)
+        t_tot += el
+        k_mean = km
+    value = sample * args.steps / t_tot
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD_DESC[args.workload], 'name': args.workload, 'cells_per_step': sample,
+                   'dt_s': args.dt, 'dt_mode': 'DT_CONSISTENT', 'mean_newton_iterations': k_mean},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': 'first %d cells of the synthetic workload per step; C++ restatement of the reference '
+                                   'RTReact loop (oracle/rxn_oracle.cpp), %d host threads, static partition' % (sample, threads)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pflotran_b200 import reactive_transport as rt
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    w = synth.Workload(args.workload)
+    t = w.tables
+    n = args.cells or DEFAULT_CELLS[args.workload]
+    ncomp = t.ncomp
+    start = rank * n                       # weak scaling: every rank owns n cells, globally numbered
+    cells = synth.make_cells(w, start, n)
+    rx = rt.Reaction(t, device=local_rank)
+    rz = rt.Realization(rx, n)
+    if args.kernel:
+        rz.set_react_kernel(args.kernel)
+    for f, v in w.base.items():
+        rz.broadcast(f, v)
+    rz.set_cell_scalars(porosity=cells['porosity'], temp=cells['temp'], pres=cells['pres'])
+    if t.nkinmnrl:
+        rz.upload('MNRL_VOLFRAC', cells['volfrac'])
+    mr_field = w.base.get('KINMR_TOTAL_SORB')
+
+    xx_host = rt.pinned_empty((n, ncomp))
+    xx_host[:] = cells['tran_xx']
+    xx0_host = cells['tran_xx']
+    it_host = rt.pinned_empty((n,), np.int32)
+    fl_host = rt.pinned_empty((n,), np.int32)
+    nb = n * ncomp * 8
+    d_xx0 = rz.device_alloc(nb)
+    d_xx = rz.device_alloc(nb)
+    d_it = rz.device_alloc(n * 4)
+    d_fl = rz.device_alloc(n * 4)
+    rz.device_copy(d_xx0, xx0_host, nb, 0)
+
+    def restore():
+        for f in RESET_FIELDS:
+            if rx.field_rows(f):
+                rz.broadcast(f, w.base[f])
+
+    def step_device():
+        restore()
+        rz.device_copy(d_xx, d_xx0, nb, 2)
+        rz.RTReact_device(d_xx, n, args.dt, abi.RXN_DT_CONSISTENT, 0, d_it, d_fl)
+        return rz.last_kernel_ms()
+
+    def step_e2e():
+        restore()
+        xx_host[:] = xx0_host          # the caller's Vec content for this step (host memcpy, part of the step)
+        rz.RTReact(xx_host, args.dt, abi.RXN_DT_CONSISTENT, iters=it_host, flags=fl_host)
+
+    fp64_peak = rz.probe_fp64_tflops()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = rt.launch_count()
+    barrier()
+    tw0 = time.perf_counter()
+    rz.timer_start()
+    kern_ms = []
+    for _ in range(args.steps):
+        kern_ms.append(step_device())
+    dev_ms = rz.timer_stop()
+    barrier()
+    tw1 = time.perf_counter()
+    launches = rt.launch_count() - l0
+    clocks = sampler.stop(tw0, tw1)
+    dev_ms = max_over_ranks(dev_ms)
+    rz.device_copy(it_host, d_it, n * 4, 1)
+    rz.device_copy(fl_host, d_fl, n * 4, 1)
+    iters_sum = float(it_host.sum(dtype=np.int64))
+    bad = int(((fl_host != abi.RXN_EXIT_RESIDUAL) & (fl_host != abi.RXN_EXIT_REL_CHANGE)).sum())
+    iters_sum_all = sum_over_ranks(iters_sum)
+    bad_all = int(sum_over_ranks(float(bad)))
+    kern_ms_max = max_over_ranks(statistics.mean(kern_ms))
+
+    # end-to-end through the host-buffer call
+    step_e2e()
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - te0)
+
+    if rank == 0:
+        total_cells = n * world
+        value = total_cells * args.steps / (dev_ms * 1e-3)
+        wm = work_model(t, iters_sum_all, total_cells)
+        peaks, peak_src = measured_peaks()
+        kern_s = kern_ms_max * 1e-3
+        fp64_ach = wm['flop_eq_per_cell'] * n / kern_s / 1e12
+        hbm_ach = wm['bytes_per_cell'] * n / kern_s / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD_DESC[args.workload], 'name': args.workload, 'cells_per_gpu': n,
+                       'total_cells': total_cells, 'dt_s': args.dt, 'dt_mode': 'DT_CONSISTENT',
+                       'mean_newton_iterations': wm['mean_newton_iterations'], 'cells_with_nonreference_flags': bad_all,
+                       'l2_policy': 'inputs (%.1f GB of cell state per GPU) larger than L2; no flush needed'
+                                    % (n * wm['bytes_per_cell'] / 1e9),
+                       'kernel': {0: 'auto', 1: 'thread-per-cell', 2: 'lane-group-per-cell'}[args.kernel]},
+            'e2e': {'value': total_cells * args.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': nb,
+                    'd2h_bytes_per_step': nb + 2 * n * 4},
+            'gpu_launches': int(launches * world),
+            'clocks': clocks,
+            'roofline': {'bound': 'fp64', 'achieved': fp64_ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': fp64_ach / fp64_peak,
+                         'traffic': None,
+                         'note': 'FP64 CUDA-core path: achieved = flop-equivalents (SURVEY.md 8d, W=20 per exp/log/sqrt/pow) x cells '
+                                 '/ react-kernel time (CUDA events); peak = DFMA probe measured in this run (rxn_probe_fp64)',
+                         'kernel_ms': kern_ms_max, 'flop_eq_per_cell': wm['flop_eq_per_cell'],
+                         'transcendentals_per_cell': wm['transcendentals_per_cell']},
+            'roofline_hbm': {'bound': 'hbm', 'achieved': hbm_ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                             'frac': hbm_ach / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_src,
+                             'bytes_per_cell': wm['bytes_per_cell']},
+        }
+        # CPU baseline: bounded sample on the host cores of this box
+        threads = os.cpu_count() or 1
+        rate0, _, _ = cpu_reference_rate(w, 4096 * max(1, threads // 4), 0, args.dt, threads)
+        sample = int(max(4096, min(n, rate0 * 10.0)) // 4096 * 4096)
+        rate, el, km = cpu_reference_rate(w, sample, 0, args.dt, threads)
+        line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': 'first %d cells of the same workload, %.1f s, C++ restatement of the reference loop '
+                                          '(no Fortran compiler in the image)' % (sample, el)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='hanford300a_eq', choices=sorted(DEFAULT_CELLS))
+    ap.add_argument('--cells', type=int, default=0, help='cells per GPU (default: the BASELINE config size)')
+    ap.add_argument('--dt', type=float, default=3600.0)
+    ap.add_argument('--kernel', type=int, default=0, choices=[0, 1, 2])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

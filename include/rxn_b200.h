@@ -244,6 +244,11 @@ int rxn_state_upload(RxnState *s, int field, const double *host, int64_t row_str
 int rxn_state_download(const RxnState *s, int field, double *host, int64_t row_stride,
                        int64_t cell_stride);
 
+/* replaces: assigning one constraint's equilibrated state to every cell of a region
+ * (CondControlAssignTranInitCond, condition_control.F90:498-949): field(row, c) = row_values[row]
+ * for all cells c. */
+int rxn_state_broadcast(RxnState *s, int field, const double *row_values);
+
 /* replaces: R2 reads + the imat<=0 / nG2L<0 skips (reactive_transport.F90:1699, 3791-3794).
  * Any pointer may be NULL (field left unchanged). active: 1 = compute, 0 = skip. */
 int rxn_set_cell_scalars(RxnState *s, const double *den_kg, const double *sat, const double *temp,
@@ -293,6 +298,12 @@ int rxn_update_kinetic_state_batch(RxnState *s, double dt);
 
 /* timing of the last batched kernel sequence on the handle's stream, in ms (CUDA events). */
 float rxn_last_kernel_ms(const RxnState *s);
+/* CUDA-event bracket on the handle's stream around any sequence of calls (bench.py) */
+int rxn_timer_start(RxnState *s);
+int rxn_timer_stop(RxnState *s, float *ms);
+/* measured FP64 FMA throughput of the handle's device in TFLOP/s (2 flop per DFMA): the
+ * roofline denominator for this FP64 CUDA-core path, which MEASURED_PEAKS.json does not hold */
+int rxn_probe_fp64(RxnState *s, double *tflops);
 /* number of kernels this library has launched since load (bench.py: gpu_launches). */
 int64_t rxn_launch_count(void);
 

@@ -63,7 +63,7 @@ struct RxnState {
   uint8_t *d_active = nullptr;
   long long ncells = 0, ld = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   float last_ms = 0.f;
   // grow-only scratch for the host-buffer entry points
   void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -111,6 +111,20 @@ __global__ void k_field_to_strided(const double *__restrict__ src, long long ld,
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncells) return;
   for (int r = 0; r < rows; ++r) tmp[r * rs + c * cs] = src[r * ld + c];
+}
+__global__ void k_broadcast(double *dst, long long ld, long long ncells, int rows, const double *__restrict__ vals) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  for (int r = 0; r < rows; ++r) dst[r * ld + c] = vals[r];
+}
+// FP64 FMA throughput probe (roofline denominator measured on the box): 8 independent chains/thread
+__global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 __global__ void k_fill(double *dst, long long n, double v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,6 +248,8 @@ int rxn_state_destroy(RxnState *s) {
   for (int k = 0; k < 4; ++k) if (s->scratch[k]) cudaFree(s->scratch[k]);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->tev0) cudaEventDestroy(s->tev0);
+  if (s->tev1) cudaEventDestroy(s->tev1);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return RXN_OK;
@@ -268,6 +284,22 @@ int rxn_state_upload(RxnState *s, int field, const double *host, int64_t rs, int
     k_field_from_strided<<<nblocks(s->ncells, 256), 256, 0, s->stream>>>(s->S.f[field], s->ld, s->ncells, rows, (const double *)tmp, rs, cs);
     ++g_launches;
   }
+  return check_launch(s, false);
+}
+
+int rxn_state_broadcast(RxnState *s, int field, const double *row_values) {
+  if (!s || !row_values || field < 0 || field >= RXN_F_COUNT) return fail(RXN_ERR_INVALID, "bad argument");
+  const int rows = s->t->rows[field];
+  if (rows == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  int rc = alloc_field(s, field);
+  if (rc != RXN_OK) return rc;
+  void *tmp;
+  rc = ensure_scratch(s, 1, (size_t)rows * 8, &tmp);
+  if (rc != RXN_OK) return rc;
+  CU(cudaMemcpyAsync(tmp, row_values, (size_t)rows * 8, cudaMemcpyHostToDevice, s->stream));
+  k_broadcast<<<nblocks(s->ncells, 256), 256, 0, s->stream>>>(s->S.f[field], s->ld, s->ncells, rows, (const double *)tmp);
+  ++g_launches;
   return check_launch(s, false);
 }
 
@@ -469,6 +501,50 @@ int rxn_update_kinetic_state_batch(RxnState *s, double dt) {
   const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
   RXN_DISPATCH(t->nvariant, run_update_kinetic_state, L, t->h, (const double *)t->d_blob, s->S, dt);
   return check_launch(s, true);
+}
+
+int rxn_timer_start(RxnState *s) {
+  if (!s) return fail(RXN_ERR_INVALID, "null state");
+  CU(cudaSetDevice(s->t->device));
+  if (!s->tev0) { CU(cudaEventCreate(&s->tev0)); CU(cudaEventCreate(&s->tev1)); }
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaEventRecord(s->tev0, s->stream));
+  return RXN_OK;
+}
+int rxn_timer_stop(RxnState *s, float *ms) {
+  if (!s || !ms || !s->tev0) return fail(RXN_ERR_INVALID, "timer not started");
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaEventRecord(s->tev1, s->stream));
+  CU(cudaEventSynchronize(s->tev1));
+  CU(cudaEventElapsedTime(ms, s->tev0, s->tev1));
+  return RXN_OK;
+}
+
+int rxn_probe_fp64(RxnState *s, double *tflops) {
+  if (!s || !tflops) return fail(RXN_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(s->t->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, s->t->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  void *out;
+  int rc = ensure_scratch(s, 3, (size_t)blocks * threads * 8, &out);
+  if (rc != RXN_OK) return rc;
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(a, s->stream));
+    k_dfma_probe<<<blocks, threads, 0, s->stream>>>((double *)out, iters, 0.999999, 1.0e-9);
+    ++g_launches;
+    CU(cudaEventRecord(b, s->stream));
+    CU(cudaEventSynchronize(b));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+  return RXN_OK;
 }
 
 float rxn_last_kernel_ms(const RxnState *s) { return s ? s->last_ms : -1.f; }

@@ -1,0 +1,312 @@
+"""Host-side mirror of the reference's reactive-transport cell loops over the C ABI.
+
+The reference boundary is a set of Fortran module procedures called one cell at a time
+from src/pflotran/reactive_transport.F90 (RTReact :1605, RTUpdateAuxVars :3704,
+RTUpdateActivityCoefficients :3620, RTUpdateFixedAccumulation :726, the accumulation +
+reaction loops of RTResidualNonFlux :2436 / RTJacobianNonFlux :3247, RTUpdateKineticState
+:642).  `Realization` below offers the same operations, same names and argument meaning, as
+batched calls into librxn_b200.so (include/rxn_b200.h).  It is plumbing: ctypes marshalling
+only, no chemistry arithmetic, and NO fallback — if the CUDA library cannot be loaded or no
+GPU is present the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librxn_b200.so')
+_LIB = None
+
+c_i64 = C.c_int64
+c_dp = abi.c_f64p
+c_ip = abi.c_i32p
+
+
+class RxnError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__('rxn_b200 status %d: %s' % (status, msg))
+        self.status = status
+
+
+def lib():
+    """Load librxn_b200.so (built by __graft_entry__.build() / pflotran_b200/csrc/Makefile)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RxnError(abi.RXN_ERR_NO_DEVICE, 'CUDA library %s is missing: build it with '
+                           '`python -c "import __graft_entry__ as g; g.build()"`; there is no CPU fallback' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.rxn_version.restype = C.c_char_p
+        L.rxn_launch_count.restype = c_i64
+        L.rxn_state_ncells.restype = c_i64
+        L.rxn_last_kernel_ms.restype = C.c_float
+        L.rxn_tables_create.argtypes = [C.POINTER(abi.RxnTablesDesc), C.c_int, C.POINTER(C.c_void_p)]
+        L.rxn_tables_destroy.argtypes = [C.c_void_p]
+        L.rxn_state_create.argtypes = [C.c_void_p, c_i64, C.POINTER(C.c_void_p)]
+        L.rxn_state_destroy.argtypes = [C.c_void_p]
+        L.rxn_state_ncells.argtypes = [C.c_void_p]
+        L.rxn_field_rows.argtypes = [C.c_void_p, C.c_int]
+        L.rxn_state_materialize.argtypes = [C.c_void_p, C.c_int]
+        L.rxn_set_react_kernel.argtypes = [C.c_void_p, C.c_int]
+        L.rxn_state_upload.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
+        L.rxn_state_download.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
+        L.rxn_state_broadcast.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.rxn_set_cell_scalars.argtypes = [C.c_void_p] + [c_dp] * 7 + [C.POINTER(C.c_uint8)]
+        L.rxn_react_batch.argtypes = [C.c_void_p, c_dp, c_ip, c_i64, C.c_double, C.c_int, c_ip, c_ip]
+        L.rxn_react_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_double, C.c_int,
+                                             C.c_void_p, C.c_void_p]
+        L.rxn_update_auxvars_batch.argtypes = [C.c_void_p, c_dp, C.c_int]
+        L.rxn_fixed_accum_batch.argtypes = [C.c_void_p, c_dp, c_ip, c_i64, c_dp]
+        L.rxn_residual_blocks_batch.argtypes = [C.c_void_p, c_ip, c_i64, C.c_double, c_dp]
+        L.rxn_jacobian_blocks_batch.argtypes = [C.c_void_p, c_ip, c_i64, C.c_double, c_dp]
+        L.rxn_residual_jacobian_blocks_batch.argtypes = [C.c_void_p, c_ip, c_i64, C.c_double, c_dp, c_dp]
+        L.rxn_update_kinetic_state_batch.argtypes = [C.c_void_p, C.c_double]
+        L.rxn_last_kernel_ms.argtypes = [C.c_void_p]
+        L.rxn_state_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(c_i64)]
+        L.rxn_device_alloc.argtypes = [C.c_void_p, c_i64, C.POINTER(C.c_void_p)]
+        L.rxn_device_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.rxn_device_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_int]
+        L.rxn_device_sync.argtypes = [C.c_void_p]
+        L.rxn_host_alloc.argtypes = [c_i64, C.POINTER(C.c_void_p)]
+        L.rxn_host_free.argtypes = [C.c_void_p]
+        L.rxn_last_error.argtypes = [C.c_char_p, C.c_int32]
+        L.rxn_timer_start.argtypes = [C.c_void_p]
+        L.rxn_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.rxn_probe_fp64.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        _LIB = L
+    return _LIB
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(2048)
+    lib().rxn_last_error(buf, 2048)
+    return buf.value.decode(errors='replace')
+
+
+def _ck(rc: int):
+    if rc != abi.RXN_OK:
+        raise RxnError(rc, last_error())
+
+
+def _dp(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_dp)
+
+
+def _ip(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_ip)
+
+
+class Reaction:
+    """The shared `reaction` object (reaction_type, reaction_aux.F90:142-335) on one GPU."""
+
+    def __init__(self, tables, device: int = 0):
+        self.tables = tables
+        self.desc = tables if isinstance(tables, abi.RxnTablesDesc) else abi.make_desc(tables)
+        self.h = C.c_void_p()
+        _ck(lib().rxn_tables_create(C.byref(self.desc), device, C.byref(self.h)))
+        self.device = device
+
+    def field_rows(self, field: str) -> int:
+        return lib().rxn_field_rows(self.h, abi.F[field])
+
+    def close(self):
+        if self.h:
+            lib().rxn_tables_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Realization:
+    """Per-rank cell state (rt_auxvars + global/material auxvars of the ghosted cells,
+    reactive_transport.F90:271-274) resident in HBM, with the reference's cell loops as methods."""
+
+    def __init__(self, reaction: Reaction, ncells_ghosted: int):
+        self.reaction = reaction
+        self.ncells = int(ncells_ghosted)
+        self.ncomp = reaction.desc.ncomp
+        self.h = C.c_void_p()
+        _ck(lib().rxn_state_create(reaction.h, self.ncells, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().rxn_state_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state access (PatchGetVariable / checkpoint / CondControlAssignTranInitCond) ----
+    def upload(self, field: str, a: np.ndarray):
+        """a: [rows, ncells] (SoA) float64."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        assert a.shape == (self.reaction.field_rows(field), self.ncells), (field, a.shape)
+        _ck(lib().rxn_state_upload(self.h, abi.F[field], _dp(a), self.ncells, 1))
+
+    def upload_aos(self, field: str, a: np.ndarray):
+        """a: [ncells, rows] (the reference's Vec layout, dof fastest)."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == (self.ncells, self.reaction.field_rows(field))
+        _ck(lib().rxn_state_upload(self.h, abi.F[field], _dp(a), 1, a.shape[1]))
+
+    def download(self, field: str) -> np.ndarray:
+        rows = self.reaction.field_rows(field)
+        a = np.zeros((rows, self.ncells))
+        if rows:
+            _ck(lib().rxn_state_download(self.h, abi.F[field], _dp(a), self.ncells, 1))
+        return a
+
+    def download_aos(self, field: str) -> np.ndarray:
+        rows = self.reaction.field_rows(field)
+        a = np.zeros((self.ncells, rows))
+        if rows:
+            _ck(lib().rxn_state_download(self.h, abi.F[field], _dp(a), 1, rows))
+        return a
+
+    def broadcast(self, field: str, row_values: np.ndarray):
+        """Same value in every cell: a uniform initial condition."""
+        v = np.ascontiguousarray(row_values, dtype=np.float64).ravel()
+        assert v.shape[0] == self.reaction.field_rows(field)
+        if v.shape[0]:
+            _ck(lib().rxn_state_broadcast(self.h, abi.F[field], _dp(v)))
+
+    def materialize(self, field: str):
+        _ck(lib().rxn_state_materialize(self.h, abi.F[field]))
+
+    def upload_host_state(self, st: abi.HostState):
+        for f in abi.FIELDS:
+            if f in ('DTOTAL', 'DTOTAL_SORB_EQ'):
+                continue
+            if st[f].shape[0]:
+                self.upload(f, st[f])
+        self.set_cell_scalars(active=st.active)
+
+    def download_host_state(self, st: abi.HostState):
+        for f in abi.FIELDS:
+            if f in ('DTOTAL', 'DTOTAL_SORB_EQ'):
+                continue
+            if st[f].shape[0]:
+                st[f][:] = self.download(f)
+
+    def set_cell_scalars(self, den_kg=None, sat=None, temp=None, pres=None, volume=None, porosity=None,
+                         soil_particle_density=None, active=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+                for a in (den_kg, sat, temp, pres, volume, porosity, soil_particle_density)]
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
+        _ck(lib().rxn_set_cell_scalars(self.h, *[_dp(a) for a in arrs],
+                                       None if act is None else act.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def set_react_kernel(self, which: int):
+        _ck(lib().rxn_set_react_kernel(self.h, which))
+
+    # ---- the cell loops ----
+    def RTReact(self, tran_xx: np.ndarray, dt: float, dt_mode: int = abi.RXN_DT_CONSISTENT,
+                l2g: Optional[np.ndarray] = None, iters: Optional[np.ndarray] = None,
+                flags: Optional[np.ndarray] = None):
+        """reactive_transport.F90:1605 — tran_xx [nlocal, ncomp]: in totals, out free-ion (in place).
+        Returns (num_iterations[nlocal], flags[nlocal])."""
+        assert tran_xx.dtype == np.float64 and tran_xx.flags.c_contiguous and tran_xx.shape[1] == self.ncomp
+        n = tran_xx.shape[0]
+        if iters is None:
+            iters = np.zeros(n, dtype=np.int32)
+        if flags is None:
+            flags = np.zeros(n, dtype=np.int32)
+        _ck(lib().rxn_react_batch(self.h, _dp(tran_xx), _ip(l2g), n, dt, dt_mode, _ip(iters), _ip(flags)))
+        return iters, flags
+
+    def RTUpdateAuxVars(self, xx_loc: Optional[np.ndarray], update_activity_coefs: bool):
+        """reactive_transport.F90:3704 (cells part) — xx_loc [nghosted, ncomp] free-ion molalities."""
+        if xx_loc is not None:
+            assert xx_loc.shape == (self.ncells, self.ncomp)
+        _ck(lib().rxn_update_auxvars_batch(self.h, _dp(xx_loc), int(update_activity_coefs)))
+
+    def RTUpdateFixedAccumulation(self, xx: Optional[np.ndarray], l2g: Optional[np.ndarray] = None) -> np.ndarray:
+        """reactive_transport.F90:726 — returns accum [nlocal, ncomp] in mol."""
+        n = self.ncells if l2g is None else len(l2g)
+        out = np.zeros((n, self.ncomp))
+        _ck(lib().rxn_fixed_accum_batch(self.h, _dp(xx), _ip(l2g), n, _dp(out)))
+        return out
+
+    def RTResidualJacobianNonFlux(self, dt: float, l2g: Optional[np.ndarray] = None, residual=True, jacobian=True):
+        """Accumulation + reaction parts of RTResidualNonFlux (:2436) and RTJacobianNonFlux (:3247):
+        res [nlocal, ncomp], jac [nlocal, ncomp*ncomp] (column-major blocks)."""
+        n = self.ncells if l2g is None else len(l2g)
+        res = np.zeros((n, self.ncomp)) if residual else None
+        jac = np.zeros((n, self.ncomp * self.ncomp)) if jacobian else None
+        _ck(lib().rxn_residual_jacobian_blocks_batch(self.h, _ip(l2g), n, dt, _dp(res), _dp(jac)))
+        return res, jac
+
+    def RTUpdateKineticState(self, dt: float):
+        """reactive_transport.F90:642."""
+        _ck(lib().rxn_update_kinetic_state_batch(self.h, dt))
+
+    # ---- device-resident variants and measurement helpers (bench.py) ----
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        _ck(lib().rxn_device_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int):
+        _ck(lib().rxn_device_free(self.h, C.c_void_p(ptr)))
+
+    def device_copy(self, dst, src, nbytes: int, kind: int):
+        """kind 0: host->device, 1: device->host, 2: device->device; dst/src are ints or numpy arrays."""
+        d = dst.ctypes.data if isinstance(dst, np.ndarray) else dst
+        s_ = src.ctypes.data if isinstance(src, np.ndarray) else src
+        _ck(lib().rxn_device_copy(self.h, C.c_void_p(d), C.c_void_p(s_), nbytes, kind))
+
+    def RTReact_device(self, d_xx: int, nlocal: int, dt: float, dt_mode: int = abi.RXN_DT_CONSISTENT,
+                       d_l2g: int = 0, d_iters: int = 0, d_flags: int = 0):
+        """RTReact with tran_xx / iters / flags already resident in this GPU's HBM."""
+        _ck(lib().rxn_react_batch_device(self.h, C.c_void_p(d_xx), C.c_void_p(d_l2g or None), nlocal, dt, dt_mode,
+                                         C.c_void_p(d_iters or None), C.c_void_p(d_flags or None)))
+
+    def timer_start(self):
+        _ck(lib().rxn_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _ck(lib().rxn_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def probe_fp64_tflops(self) -> float:
+        v = C.c_double()
+        _ck(lib().rxn_probe_fp64(self.h, C.byref(v)))
+        return float(v.value)
+
+    def last_kernel_ms(self) -> float:
+        return float(lib().rxn_last_kernel_ms(self.h))
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array over page-locked host memory (cudaMallocHost); never freed (process lifetime)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _ck(lib().rxn_host_alloc(max(n, 8), C.byref(p)))
+    buf = (C.c_char * max(n, 8)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def launch_count() -> int:
+    return int(lib().rxn_launch_count())

@@ -1,0 +1,38 @@
+"""Shared helpers of the parity tests: run one entry point through two backends (oracle /
+emulated device code / CUDA library) on the same seeded synthetic cells and compare."""
+import numpy as np
+
+from pflotran_b200 import abi, synth
+
+STATE_FIELDS = ['PRI_MOLAL', 'TOTAL', 'SEC_MOLAL', 'PRI_ACT_COEF', 'SEC_ACT_COEF', 'LN_ACT_H2O', 'TOTAL_SORB_EQ',
+                'FREE_SITE_CONC', 'EQSRFCPLX_CONC', 'KINMR_TOTAL_SORB', 'EQIONX_REF_CATION_SORBED_CONC', 'EQIONX_CONC',
+                'MNRL_VOLFRAC', 'MNRL_RATE']
+
+# north_star: relative 1e-10 on converged free-ion and mineral concentrations, identical flags
+RTOL = 1.0e-10
+
+
+def rel_err(a, b, floor=1e-300):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, what=''):
+    for f in fields:
+        a, b = st_a[f], st_b[f]
+        if not a.size:
+            continue
+        if cells is not None:
+            a, b = a[:, cells], b[:, cells]
+        # values far below the row's scale are differences of O(1) sums: compare them on that scale
+        scale = np.maximum(np.abs(b), 1e-13 * np.max(np.abs(b), axis=1, keepdims=True))
+        err = np.abs(a - b) / np.maximum(scale, 1e-300)
+        bad = ~(err <= rtol) & ~((a == b) | (np.isnan(a) & np.isnan(b)))
+        assert not bad.any(), '%s field %s: max rel err %.3e at %s' % (what, f, np.nanmax(err), np.argwhere(bad)[:3])
+
+
+def workload_cells(name, n, start=0, **kw):
+    w = synth.Workload(name)
+    cells = synth.make_cells(w, start, n, **kw)
+    return w, cells

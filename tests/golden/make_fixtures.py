@@ -59,7 +59,14 @@ def main():
         d, t, orc, st, xx, nit, cst = kat.initial_cell(path, constraint=constraint)
         base = {f: [repr(float(x)) for x in st[f][:, 0]] for f in abi.FIELDS
                 if f not in ('DTOTAL', 'DTOTAL_SORB_EQ')}
+        from pflotran_b200.chem.setup import constraint_arrays, mineral_arrays
+        ctype, conc, cid, guess = constraint_arrays(t, d.constraints[constraint])
+        vf, area = mineral_arrays(t, d.constraints[constraint])
+        cons = {'ctype': [int(x) for x in ctype], 'conc': [repr(float(x)) for x in conc], 'cid': [int(x) for x in cid],
+                'guess': None if guess is None else [repr(float(x)) for x in guess],
+                'volfrac': [repr(float(x)) for x in vf], 'area': [repr(float(x)) for x in area]}
         out = {
+            'constraint_arrays': cons,
             'name': name, 'deck': deck, 'constraint': constraint, 'equilibrate_iterations': int(nit),
             'porosity': d.porosity, 'tables': t.to_dict(), 'base': base,
         }

@@ -82,6 +82,38 @@ def initial_cell(deck_path, constraint='initial', porosity=None, volume=1.0):
     return deck, t, orc, st, xx, nit, cst
 
 
+def initial_cell_from_fixture(w, porosity=None, volume=1.0):
+    """Same start-up sequence as initial_cell(), driven only by a committed fixture
+    (tests/golden/<name>.json): no deck, no database, no /root/reference."""
+    t = w.tables
+    orc = Oracle(t)
+    ca = w.meta['constraint_arrays']
+    ctype = np.array(ca['ctype'], dtype=np.int32)
+    conc = np.array([float(x) for x in ca['conc']])
+    cid = np.array(ca['cid'], dtype=np.int32)
+    guess = None if ca['guess'] is None else np.array([float(x) for x in ca['guess']])
+    vf = np.array([float(x) for x in ca['volfrac']])
+    area = np.array([float(x) for x in ca['area']])
+    cst = abi.HostState(t, 1)
+    fill_scalars(cst, t, 0.25, volume)
+    cst['MNRL_VOLFRAC'][:, 0] = vf
+    cst['MNRL_AREA'][:, 0] = area
+    basis_molarity, nit = orc.equilibrate(cst, 0, ctype, conc, cid, guess, use_prev=False)
+    st = abi.HostState(t, 1)
+    fill_scalars(st, t, w.meta['porosity'] if porosity is None else porosity, volume)
+    st['MNRL_VOLFRAC'][:, 0] = vf
+    st['MNRL_AREA'][:, 0] = area
+    if t.nkinmrsrfcplxrxn > 0:
+        st['KINMR_TOTAL_SORB'][:] = cst['KINMR_TOTAL_SORB']
+        st['FREE_SITE_CONC'][:] = cst['FREE_SITE_CONC']
+    xx = (basis_molarity / t.reference_water_density * 1000.0).reshape(1, -1).copy()
+    orc.update_auxvars(st, xx, False)
+    if t.act_coef_update_frequency != 0:
+        orc.update_auxvars(st, xx, True)
+        orc.update_auxvars(st, xx, True)
+    return t, orc, st, xx, nit, cst
+
+
 def outputs(t, st, cell=0):
     """Variables as the reference prints them (patch.F90 PatchGetVariable)."""
     o = {}

@@ -1,0 +1,96 @@
+"""CPU-only parity of the CUDA device routines (compiled for the host by tests/emul) and of
+the table packer against the oracle, on the seeded synthetic workloads.  This is the logic
+check that runs in the build container; the same comparisons run against the real CUDA
+library in test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+from pflotran_b200 import abi, synth
+from oracle.pyoracle import Oracle
+from emulator import Emulator, pack_status
+from common import assert_state_close, workload_cells, RTOL, rel_err
+
+WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation',
+             'calcite_kinetics', 'kd_wo_mineral']
+
+
+@pytest.mark.parametrize('name', WORKLOADS)
+@pytest.mark.parametrize('dt,mode', [(3600.0, abi.RXN_DT_CONSISTENT), (1.0, abi.RXN_DT_AS_WRITTEN)])
+def test_react(name, dt, mode):
+    w, cells = workload_cells(name, 600)
+    st_o = synth.host_state(w, cells)
+    st_e = st_o.copy()
+    xo = cells['tran_xx'].copy()
+    xe = xo.copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, dt, mode, maxit=10000)
+    it_e, fl_e = Emulator(w.tables).react(st_e, xe, dt, mode)
+    assert (it_o == it_e).all() and (fl_o == fl_e).all()
+    ok = (fl_o & ~3) == 0
+    assert rel_err(xe[ok], xo[ok]).max() <= RTOL
+    assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name)
+
+
+@pytest.mark.parametrize('name', ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'])
+def test_global_implicit_entry_points(name):
+    w, cells = workload_cells(name, 300)
+    st_o = synth.host_state(w, cells)
+    orc, emu = Oracle(w.tables), Emulator(w.tables)
+    # a perturbed iterate: free-ion molalities around the base state
+    rng = np.random.default_rng(7)
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((300, w.ncomp))))
+    st_e = st_o.copy()
+    orc.update_auxvars(st_o, xx, True)
+    emu.update_auxvars(st_e, xx, True)
+    assert_state_close(st_e, st_o, what=name + ' update_auxvars')
+    a_o = orc.fixed_accum(st_o, xx)
+    a_e = emu.fixed_accum(st_e, xx)
+    assert rel_err(a_e, a_o).max() <= RTOL
+    r_o, j_o = orc.residual_jacobian(st_o, 1800.0)
+    r_e, j_e = emu.residual_jacobian(st_e, 1800.0)
+    n = w.ncomp
+    rs = np.maximum(np.abs(r_o), 1e-12 * np.abs(r_o).max(axis=1, keepdims=True))
+    assert (np.abs(r_e - r_o) / np.maximum(rs, 1e-300)).max() <= RTOL
+    js = np.maximum(np.abs(j_o), 1e-12 * np.abs(j_o).max(axis=1, keepdims=True))
+    assert (np.abs(j_e - j_o) / np.maximum(js, 1e-300)).max() <= RTOL
+    orc.update_kinetic_state(st_o, 1800.0)
+    emu.update_kinetic_state(st_e, 1800.0)
+    assert_state_close(st_e, st_o, what=name + ' kinetic state')
+
+
+def test_inactive_cells_and_l2g():
+    w, cells = workload_cells('calcite', 64)
+    st_o = synth.host_state(w, cells)
+    st_o.active[::5] = 0
+    st_e = st_o.copy()
+    xo = cells['tran_xx'].copy()
+    xe = xo.copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0)
+    it_e, fl_e = Emulator(w.tables).react(st_e, xe, 3600.0)
+    assert (fl_e[::5] == abi.RXN_FLAG_INACTIVE).all() and (it_e[::5] == 0).all()
+    assert (it_o == it_e).all() and (fl_o == fl_e).all()
+    np.testing.assert_array_equal(xe[::5], cells['tran_xx'][::5])     # skipped cells untouched
+    # local->ghosted map: 16 local cells living at ghosted slots 40..55 in reverse order
+    st2 = synth.host_state(w, cells)
+    l2g = np.arange(55, 39, -1, dtype=np.int32)
+    x2 = np.ascontiguousarray(cells['tran_xx'][l2g])
+    it2, fl2 = Emulator(w.tables).react(st2, x2, 3600.0, l2g=l2g)
+    st_ref = synth.host_state(w, cells)
+    xr = cells['tran_xx'].copy()
+    itr, flr = Oracle(w.tables).react(st_ref, xr, 3600.0)
+    assert (it2 == itr[l2g]).all()
+    assert rel_err(x2, xr[l2g]).max() <= RTOL
+
+
+def test_packer_rejects_unsupported():
+    w = synth.Workload('calcite')
+    d = abi.make_desc(w.tables)
+    for fld in ['nactive_gas', 'nimmobile', 'ncoll', 'ngeneral_rxn', 'nradiodecay_rxn', 'nmicrobial_rxn',
+                'nimmobile_decay_rxn', 'has_sandbox', 'has_clm', 'has_solid_solution', 'co2_flow_mode',
+                'numerical_derivatives', 'nkinsrfcplxrxn']:
+        setattr(d, fld, 1)
+        rc, msg = pack_status(d)
+        assert rc == abi.RXN_ERR_UNSUPPORTED and 'outside the B200 path' in msg, fld
+        setattr(d, fld, 0)
+    assert pack_status(d)[0] == abi.RXN_OK
+    d.struct_size = 8
+    assert pack_status(d)[0] == abi.RXN_ERR_INVALID

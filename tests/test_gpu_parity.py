@@ -1,0 +1,165 @@
+"""GPU parity tests: the CUDA library, called through the C ABI, against the CPU oracle on the
+same seeded synthetic inputs.  Bar (BASELINE.json north_star): relative 1e-10 on converged
+free-ion and mineral concentrations, identical Newton iteration counts and exit flags."""
+import numpy as np
+import pytest
+
+from pflotran_b200 import abi, synth, reactive_transport as rt
+from oracle.pyoracle import Oracle
+from common import assert_state_close, workload_cells, RTOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation',
+             'calcite_kinetics', 'kd_wo_mineral']
+
+
+def _gpu_state(w, st):
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, st.ncells)
+    rz.upload_host_state(st)
+    return rx, rz
+
+
+@pytest.mark.parametrize('name', WORKLOADS)
+@pytest.mark.parametrize('dt,mode', [(3600.0, abi.RXN_DT_CONSISTENT), (1.0, abi.RXN_DT_AS_WRITTEN)])
+@pytest.mark.parametrize('kernel', [1, 2])
+def test_react(name, dt, mode, kernel):
+    n = 5000
+    w, cells = workload_cells(name, n)
+    st_o = synth.host_state(w, cells)
+    st_g = st_o.copy()
+    rx, rz = _gpu_state(w, st_g)
+    try:
+        rz.set_react_kernel(kernel)
+        xo = cells['tran_xx'].copy()
+        xg = xo.copy()
+        it_g, fl_g = rz.RTReact(xg, dt, mode)
+    except rt.RxnError as e:
+        if kernel == 2 and e.status == abi.RXN_ERR_UNSUPPORTED:
+            pytest.skip('cooperative kernel not available for these tables: %s' % e)
+        raise
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, dt, mode, maxit=10000, nthreads=8)
+    rz.download_host_state(st_g)
+    assert (it_o == it_g).all(), 'iteration counts differ in %d cells' % (it_o != it_g).sum()
+    assert (fl_o == fl_g).all()
+    ok = (fl_o & ~3) == 0
+    assert rel_err(xg[ok], xo[ok]).max() <= RTOL
+    assert_state_close(st_g, st_o, cells=np.where(ok)[0], what=name)
+
+
+@pytest.mark.parametrize('name', ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'])
+def test_global_implicit_entry_points(name):
+    n = 3000
+    w, cells = workload_cells(name, n)
+    st_o = synth.host_state(w, cells)
+    st_g = st_o.copy()
+    rx, rz = _gpu_state(w, st_g)
+    orc = Oracle(w.tables)
+    rng = np.random.default_rng(7)
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((n, w.ncomp))))
+    orc.update_auxvars(st_o, xx, True, nthreads=8)
+    rz.RTUpdateAuxVars(xx, True)
+    rz.download_host_state(st_g)
+    assert_state_close(st_g, st_o, what=name + ' RTUpdateAuxVars')
+    a_o = orc.fixed_accum(st_o, xx, nthreads=8)
+    a_g = rz.RTUpdateFixedAccumulation(xx)
+    assert rel_err(a_g, a_o).max() <= RTOL
+    r_o, j_o = orc.residual_jacobian(st_o, 1800.0, nthreads=8)
+    r_g, j_g = rz.RTResidualJacobianNonFlux(1800.0)
+    rs = np.maximum(np.abs(r_o), 1e-12 * np.abs(r_o).max(axis=1, keepdims=True))
+    assert (np.abs(r_g - r_o) / np.maximum(rs, 1e-300)).max() <= RTOL
+    js = np.maximum(np.abs(j_o), 1e-12 * np.abs(j_o).max(axis=1, keepdims=True))
+    assert (np.abs(j_g - j_o) / np.maximum(js, 1e-300)).max() <= RTOL
+    orc.update_kinetic_state(st_o, 1800.0, nthreads=8)
+    rz.RTUpdateKineticState(1800.0)
+    rz.download_host_state(st_g)
+    assert_state_close(st_g, st_o, what=name + ' RTUpdateKineticState')
+
+
+def test_state_roundtrip_layouts():
+    w, cells = workload_cells('hanford300a_eq', 1000)
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, 1000)
+    rng = np.random.default_rng(3)
+    a = rng.random((w.ncomp, 1000))
+    rz.upload('PRI_MOLAL', a)
+    np.testing.assert_array_equal(rz.download('PRI_MOLAL'), a)
+    np.testing.assert_array_equal(rz.download_aos('PRI_MOLAL'), a.T)
+    rz.upload_aos('TOTAL', np.ascontiguousarray(a.T))
+    np.testing.assert_array_equal(rz.download('TOTAL'), a)
+    rz.broadcast('SEC_MOLAL', w.base['SEC_MOLAL'])
+    s = rz.download('SEC_MOLAL')
+    assert (s == w.base['SEC_MOLAL'][:, None]).all()
+    # reference initial values (reactive_transport_aux.F90:213-400)
+    rz2 = rt.Realization(rx, 33)
+    assert (rz2.download('PRI_ACT_COEF') == 1.0).all() and (rz2.download('FREE_SITE_CONC') == 1.0e-9).all()
+    assert (rz2.download('PRI_MOLAL') == 0.0).all()
+
+
+def test_inactive_cells_l2g_and_empty():
+    w, cells = workload_cells('calcite', 64)
+    st = synth.host_state(w, cells)
+    st.active[::5] = 0
+    st_o = st.copy()
+    rx, rz = _gpu_state(w, st)
+    xg = cells['tran_xx'].copy()
+    it_g, fl_g = rz.RTReact(xg, 3600.0)
+    xo = cells['tran_xx'].copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0)
+    assert (it_o == it_g).all() and (fl_o == fl_g).all()
+    assert (fl_g[::5] == abi.RXN_FLAG_INACTIVE).all()
+    np.testing.assert_array_equal(xg[::5], cells['tran_xx'][::5])
+    # l2g map + empty batch
+    st2 = synth.host_state(w, cells)
+    rx2, rz2 = _gpu_state(w, st2)
+    l2g = np.arange(55, 39, -1, dtype=np.int32)
+    x2 = np.ascontiguousarray(cells['tran_xx'][l2g])
+    it2, fl2 = rz2.RTReact(x2, 3600.0, l2g=l2g)
+    st_r = synth.host_state(w, cells)
+    xr = cells['tran_xx'].copy()
+    itr, flr = Oracle(w.tables).react(st_r, xr, 3600.0)
+    assert (it2 == itr[l2g]).all() and rel_err(x2, xr[l2g]).max() <= RTOL
+    e = np.zeros((0, w.ncomp))
+    it0, fl0 = rz2.RTReact(e, 3600.0)
+    assert it0.shape == (0,)
+
+
+def test_unsupported_tables_rejected():
+    w = synth.Workload('calcite')
+    d = abi.make_desc(w.tables)
+    d.ngeneral_rxn = 1
+    with pytest.raises(rt.RxnError) as e:
+        rt.Reaction(d)
+    assert e.value.status == abi.RXN_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize('name,n', [('calcite', 1_000_000), ('hanford300a_eq', 200_000)])
+def test_full_size_sampled_against_oracle(name, n):
+    """BASELINE-size batches: the whole batch runs on the GPU, a seeded sample of cells is
+    re-run by the oracle (cells are independent, so any subset must agree), and the size-
+    independent property holds everywhere: free-ion output re-speciates to the stored totals
+    and every cell reports a reference exit reason."""
+    w, cells = workload_cells(name, n)
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, n)
+    for f, v in w.base.items():
+        rz.broadcast(f, v)
+    rz.set_cell_scalars(porosity=cells['porosity'], temp=cells['temp'], pres=cells['pres'])
+    if w.tables.nkinmnrl:
+        rz.upload('MNRL_VOLFRAC', cells['volfrac'])
+    xg = cells['tran_xx'].copy()
+    it_g, fl_g = rz.RTReact(xg, 3600.0)
+    assert ((fl_g == abi.RXN_EXIT_RESIDUAL) | (fl_g == abi.RXN_EXIT_REL_CHANGE)).all()
+    assert it_g.min() >= 1
+    pm = rz.download('PRI_MOLAL')
+    np.testing.assert_array_equal(pm.T, xg)                      # tran_xx out == stored pri_molal
+    sample = np.sort(np.random.default_rng(11).choice(n, 3000, replace=False))
+    sub = {k: (v[sample] if v.ndim == 1 else (v[sample] if k == 'tran_xx' else v[:, sample])) for k, v in cells.items()}
+    st_o = synth.host_state(w, sub)
+    xo = sub['tran_xx'].copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, nthreads=8)
+    assert (it_o == it_g[sample]).all() and (fl_o == fl_g[sample]).all()
+    assert rel_err(xg[sample], xo).max() <= RTOL
+    tot = rz.download('TOTAL')
+    assert rel_err(tot[:, sample], st_o['TOTAL']).max() <= RTOL
