@@ -184,7 +184,7 @@ int rxn_tables_create(const RxnTablesDesc *d, int device, RxnTables **out) {
     delete t;
     return rc2;
   }
-  rc = tile_plan_build(d, h, P.d, P.i, &t->tile);
+  rc = tile_plan_build(d, h, P.d, P.i, t->blob_bytes, device, &t->tile);
   if (rc != RXN_OK) { int rc2 = fail(rc, "tile plan: %s", t->tile.err.c_str()); cudaFree(t->d_blob); delete t; return rc2; }
   *out = t;
   return RXN_OK;
@@ -352,14 +352,21 @@ int rxn_set_react_kernel(RxnState *s, int which) {
 static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
                         int32_t *d_iters, int32_t *d_flags) {
   const RxnTables *t = s->t;
-  bool use_tile = t->tile.usable && s->react_kernel != 1;
-  if (s->react_kernel == 2 && !t->tile.usable) return fail(RXN_ERR_UNSUPPORTED, "tile kernel unavailable for these tables: %s", t->tile.err.c_str());
+  // the cooperative kernel keeps dtotal only as Newton scratch: states with DTOTAL materialised use thread-per-cell
+  const bool tile_ok = t->tile.usable && !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
+  const bool use_tile = tile_ok && s->react_kernel != 1;
+  if (s->react_kernel == 2 && !tile_ok)
+    return fail(RXN_ERR_UNSUPPORTED, "cooperative kernel unavailable: %s", t->tile.usable ? "DTOTAL is materialised" : t->tile.err.c_str());
   if (use_tile) {
-    tile_launch_react(t->tile, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->stream);
+    int rc = tile_launch_react(t->tile, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->stream);
+    if (rc != RXN_OK) return fail(rc, "no cooperative kernel variant for G=%d R=%d", t->tile.tt.G, t->tile.tt.R);
     ++g_launches;
   } else {
-    const int threads = t->nvariant <= 8 ? 128 : 64;
-    const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
+    int threads = t->nvariant <= 8 ? 128 : 64;
+    if (const char *e = getenv("RXN_TPC_BLOCK")) threads = std::max(32, atoi(e));
+    unsigned grid = nblocks(nlocal, threads);
+    if (const char *e = getenv("RXN_TPC_GRID")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(e)));
+    const LaunchCfg L{grid, threads, t->blob_bytes, s->stream};
     RXN_DISPATCH(t->nvariant, run_react, L, t->h, (const double *)t->d_blob, s->S, d_xx, d_l2g, (long long)nlocal, dt, dt_mode,
                  d_iters, d_flags);
   }

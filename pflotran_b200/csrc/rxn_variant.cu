@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(128)
 k_react(const __grid_constant__ DevTab tab, const double *__restrict__ blob, DevState S, double *tran_xx,
         const int *__restrict__ l2g, long long nlocal, double dt, int dt_mode, int *iters, int *flags) {
   Tab T = stage_tables(tab, blob);
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nlocal) cell_react<N>(T, S, i, tran_xx, l2g, dt, dt_mode, iters, flags);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += (long long)gridDim.x * blockDim.x)
+    cell_react<N>(T, S, i, tran_xx, l2g, dt, dt_mode, iters, flags);
 }
 
 template <int N>

@@ -18,7 +18,7 @@ def rel_err(a, b, floor=1e-300):
     return np.abs(a - b) / np.maximum(np.abs(b), floor)
 
 
-def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, what=''):
+def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, what='', tables=None):
     for f in fields:
         a, b = st_a[f], st_b[f]
         if not a.size:
@@ -27,6 +27,11 @@ def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, w
             a, b = a[:, cells], b[:, cells]
         # values far below the row's scale are differences of O(1) sums: compare them on that scale
         scale = np.maximum(np.abs(b), 1e-13 * np.max(np.abs(b), axis=1, keepdims=True))
+        if f == 'MNRL_RATE' and tables is not None:
+            # rate = -area*k*(1 - QK) (reaction_mineral.F90:795-816): near equilibrium 1 - QK cancels, so a
+            # relative perturbation eps of the molalities moves the rate by ~eps*area*k*QK*sum|nu|, not eps*|rate|
+            area = st_b['MNRL_AREA'] if cells is None else st_b['MNRL_AREA'][:, cells]
+            scale = np.maximum(scale, area * np.abs(np.asarray(tables.kinmnrl_rate_constant))[:, None])
         err = np.abs(a - b) / np.maximum(scale, 1e-300)
         bad = ~(err <= rtol) & ~((a == b) | (np.isnan(a) & np.isnan(b)))
         assert not bad.any(), '%s field %s: max rel err %.3e at %s' % (what, f, np.nanmax(err), np.argwhere(bad)[:3])

@@ -45,7 +45,7 @@ def test_react(name, dt, mode, kernel):
     assert (fl_o == fl_g).all()
     ok = (fl_o & ~3) == 0
     assert rel_err(xg[ok], xo[ok]).max() <= RTOL
-    assert_state_close(st_g, st_o, cells=np.where(ok)[0], what=name)
+    assert_state_close(st_g, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
 
 
 @pytest.mark.parametrize('name', ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'])
