@@ -359,7 +359,7 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
     return fail(RXN_ERR_UNSUPPORTED, "cooperative kernel unavailable: %s", t->tile.usable ? "DTOTAL is materialised" : t->tile.err.c_str());
   if (use_tile) {
     int rc = tile_launch_react(t->tile, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->stream);
-    if (rc != RXN_OK) return fail(rc, "no cooperative kernel variant for G=%d R=%d", t->tile.tt.G, t->tile.tt.R);
+    if (rc != RXN_OK) return fail(rc, "no cooperative kernel variant for G=%d", t->tile.tt.G);
     ++g_launches;
   } else {
     int threads = t->nvariant <= 8 ? 128 : 64;

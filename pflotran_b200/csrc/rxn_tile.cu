@@ -13,17 +13,16 @@
 
 namespace rxn {
 
-constexpr int TILE_MAX_THREADS = 768;
 constexpr int CODE_LAST = 1 << 16;
 
-template <int G, int R>
+template <int G>
 void tile_launch_variant(const TilePlan &p, const DevTab &h, const double *blob, const DevState &S, double *tran_xx,
                          const int32_t *l2g, long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags,
                          cudaStream_t stream);
-#define RXN_TILE_SHAPES(X) X(4, 1) X(4, 2) X(4, 4) X(8, 1) X(8, 2) X(8, 3) X(16, 1) X(16, 2) X(32, 1)
-#define RXN_TILE_DECL(g, r)                                                                                              \
-  extern template void tile_launch_variant<g, r>(const TilePlan &, const DevTab &, const double *, const DevState &, double *, \
-                                                 const int32_t *, long long, double, int, int32_t *, int32_t *, cudaStream_t);
+#define RXN_TILE_SHAPES(X) X(1) X(2) X(4) X(8) X(16) X(32)
+#define RXN_TILE_DECL(g)                                                                                              \
+  extern template void tile_launch_variant<g>(const TilePlan &, const DevTab &, const double *, const DevState &, double *, \
+                                              const int32_t *, long long, double, int, int32_t *, int32_t *, cudaStream_t);
 RXN_TILE_SHAPES(RXN_TILE_DECL)
 #undef RXN_TILE_DECL
 
@@ -45,11 +44,9 @@ int tile_plan_build(const RxnTablesDesc *d, const DevTab &h, const std::vector<d
   int G = n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 8 : 16, R = (n + G - 1) / G;
   if (const char *e = getenv("RXN_TILE_G")) {
     const int g = atoi(e);
-    if (g == 4 || g == 8 || g == 16 || g == 32) { G = g; R = (n + G - 1) / G; }
+    if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) { G = g; R = (n + G - 1) / G; }
   }
-  if (R > 4) return unusable("more than 4 rows per lane");
-  tt.G = G; tt.R = R; tt.NP = G * R; tt.LDJ = tt.NP + 1;
-  if ((tt.LDJ & 1) == 0) tt.LDJ += 1;
+  tt.G = G; tt.NP = (n + 1) & ~1; if (tt.NP < G) tt.NP = G; tt.LDJ = tt.NP + 2;             // b in column NP, rows 16-byte aligned
 
   std::vector<double> pd;
   std::vector<int32_t> pi;
@@ -69,12 +66,13 @@ int tile_plan_build(const RxnTablesDesc *d, const DevTab &h, const std::vector<d
     cls[key] = id;
     return id;
   };
+  std::vector<double> pz2(n), cz2(std::max(h.ncplx, 1), 0.0);
+  for (int i = 0; i < n; ++i) pz2[i] = bd[h.o_Z + i] * bd[h.o_Z + i];
+  for (int k = 0; k < h.ncplx; ++k) cz2[k] = bd[h.o_cplxZ + k] * bd[h.o_cplxZ + k];
   std::vector<int32_t> pcls(n), ccls(h.ncplx);
   for (int i = 0; i < n; ++i) pcls[i] = class_of(bd[h.o_Z + i], bd[h.o_a0 + i]);
   for (int k = 0; k < h.ncplx; ++k) ccls[k] = class_of(bd[h.o_cplxZ + k], bd[h.o_cplxa0 + k]);
   tt.ncls = (int)z2.size();
-  tt.o_cls_z2 = D(z2); tt.o_cls_a0 = D(a0);
-  tt.o_pri_cls = I(pcls); tt.o_cplx_cls = I(ccls);
 
   // -logK * LOG_TO_LN (fixed-temperature tables)
   std::vector<double> nlk;
@@ -82,7 +80,6 @@ int tile_plan_build(const RxnTablesDesc *d, const DevTab &h, const std::vector<d
   for (int k = 0; k < h.nkin; ++k) nlk.push_back(-bd[h.kin.o_logK + k] * RXN_LOG_TO_LN);
   for (int k = 0; k < h.nsrf; ++k) nlk.push_back(-bd[h.srf.o_logK + k] * RXN_LOG_TO_LN);
   if (nlk.empty()) nlk.push_back(0.0);
-  tt.o_nlk = D(nlk);
   tt.percell_logK = h.logK_mode != RXN_LOGK_FIXED;
 
   // plans
@@ -105,7 +102,7 @@ int tile_plan_build(const RxnTablesDesc *d, const DevTab &h, const std::vector<d
         terms.push_back({k, st[a] * st[b]});
       }
     }
-  auto build = [&](std::vector<Entry> &E, int &T, int &o_coef, int &o_code, int &o_ent, int &nterms) {
+  auto build = [&](std::vector<Entry> &E, int &T, int &o_rec, int &nterms) {
     for (auto &e : E) if (e.terms.empty()) e.terms.push_back({h.ncplx, 0.0});
     std::vector<int> order(E.size());
     std::iota(order.begin(), order.end(), 0);
@@ -116,34 +113,36 @@ int tile_plan_build(const RxnTablesDesc *d, const DevTab &h, const std::vector<d
       int best = 0;
       for (int l = 1; l < G; ++l) if (load[l] < load[best]) best = l;
       lane[best].push_back(e);
-      load[best] += (int)E[e].terms.size() + 1;               // +1: cost of closing an entry
+      load[best] += (int)E[e].terms.size() + 2;               // +2: cost of closing an entry
     }
     T = 0; nterms = 0;
-    size_t maxent = 0;
     for (int l = 0; l < G; ++l) {
       int t = 0;
       for (int e : lane[l]) t += (int)E[e].terms.size();
       T = std::max(T, t);
       nterms += t;
-      maxent = std::max(maxent, lane[l].size());
     }
-    std::vector<double> coef((size_t)T * G, 0.0);
-    std::vector<int32_t> code((size_t)T * G, h.ncplx), ent(std::max<size_t>(maxent, 1) * G, 0);
+    struct Rec { double coef; int32_t code; int32_t key; };
+    static_assert(sizeof(Rec) == 16, "plan record must be 16 bytes");
+    std::vector<Rec> rec((size_t)T * G, Rec{0.0, h.ncplx, 0});
     for (int l = 0; l < G; ++l) {
-      int t = 0, ne = 0;
-      for (int e : lane[l]) {
+      int t = 0;
+      for (int e : lane[l])
         for (size_t q = 0; q < E[e].terms.size(); ++q, ++t) {
-          coef[(size_t)t * G + l] = E[e].terms[q].second;
-          code[(size_t)t * G + l] = E[e].terms[q].first | (q + 1 == E[e].terms.size() ? CODE_LAST : 0);
+          const bool last = q + 1 == E[e].terms.size();
+          rec[(size_t)t * G + l] = Rec{E[e].terms[q].second, E[e].terms[q].first | (last ? CODE_LAST : 0), last ? E[e].key : 0};
         }
-        ent[(size_t)ne * G + l] = E[e].key;
-        ++ne;
-      }
     }
-    o_coef = D(coef); o_code = I(code); o_ent = I(ent);
+    std::vector<double> raw(rec.size() * 2);
+    if (!rec.empty()) memcpy(raw.data(), rec.data(), rec.size() * 16);
+    o_rec = D(raw);
   };
-  build(EA, tt.TA, tt.o_A_coef, tt.o_A_code, tt.o_A_ent, p->termsA);
-  build(EB, tt.TB, tt.o_B_coef, tt.o_B_code, tt.o_B_ent, p->termsB);
+  build(EA, tt.TA, tt.o_A_rec, p->termsA);                   // records first: 16-byte aligned in shared memory
+  build(EB, tt.TB, tt.o_B_rec, p->termsB);
+  tt.o_cls_z2 = D(z2); tt.o_cls_a0 = D(a0);
+  tt.o_pz2 = D(pz2); tt.o_cz2 = D(cz2);
+  tt.o_nlk = D(nlk);
+  tt.o_pri_cls = I(pcls); tt.o_cplx_cls = I(ccls);
   if (pi.size() & 1) pi.push_back(0);
   tt.ndbl = (int)pd.size(); tt.nint = (int)pi.size();
 
@@ -153,30 +152,37 @@ int tile_plan_build(const RxnTablesDesc *d, const DevTab &h, const std::vector<d
   tt.maxsrf = maxsrf;
   tt.need_gam = h.maxpref > 0;
   int o = tt.NP * tt.LDJ;
-  tt.c_m = o; o += tt.NP;
-  tt.c_invm = o; o += tt.NP;
-  tt.c_lna = o; o += tt.NP;
-  tt.c_tot = o; o += tt.NP;
-  tt.c_gam = o; o += tt.need_gam ? tt.NP : 0;
-  tt.c_sm = o; o += h.ncplx + 1;
-  tt.c_lng = o; o += tt.ncls;
-  tt.c_sc = o; o += h.nrxn > 0 ? maxsrf : 0;
-  tt.c_dsx = o; o += h.nrxn > 0 ? tt.NP : 0;
-  tt.c_free = o; o += h.nrxn;
-  tt.c_lk = o; o += tt.percell_logK ? (h.ncplx + h.nkin + h.nsrf) : 0;
-  if ((o & 1) == 0) o += 1;                                   // odd stride: groups of a warp hit different banks
+  auto vec = [&](int len) { const int at = o; o += len; return at; };
+  tt.c_m = vec(tt.NP); tt.c_invm = vec(tt.NP); tt.c_lna = vec(tt.NP); tt.c_tot = vec(tt.NP);
+  tt.c_lgp = vec(tt.NP); tt.c_fix = vec(tt.NP);
+  tt.c_tsorb = vec(h.neqsorb > 0 ? tt.NP : 0);
+  tt.c_gam = vec(tt.need_gam ? tt.NP : 0);
+  tt.c_sm = vec(h.ncplx + 1);
+  tt.c_lng = vec(tt.ncls);
+  tt.c_sc = vec(h.nrxn > 0 ? maxsrf : 0);
+  tt.c_dsx = vec(tt.NP);                                      // sorption dSx/dm, reused as LU row scales
+  tt.c_free = vec(h.nrxn);
+  tt.c_mnrl = vec(2 * h.nkin);                                // mnrl_volfrac | mnrl_area
+  tt.c_r0 = vec(h.nmr * tt.NP); tt.c_seq = vec(h.nmr * tt.NP);
+  tt.c_lk = vec(tt.percell_logK ? (h.ncplx + h.nkin + h.nsrf) : 0);
+  while ((o & 15) != 2) ++o;                                  // 16-byte aligned; groups of a warp start in different banks
   tt.pc_dbl = o;
 
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return unusable("cudaGetDeviceProperties failed");
   const size_t smem_max = prop.sharedMemPerBlockOptin;
-  const size_t fixed = main_blob_bytes + (size_t)tt.ndbl * 8 + (size_t)tt.nint * 4;
-  int threads = TILE_MAX_THREADS;
-  if (const char *e = getenv("RXN_TILE_THREADS")) threads = std::max(32, std::min(TILE_MAX_THREADS, atoi(e) / 32 * 32));
-  while (threads > 32 && fixed + (size_t)(threads / G) * tt.pc_dbl * 8 > smem_max) threads -= 32;
-  if (fixed + (size_t)(threads / G) * tt.pc_dbl * 8 > smem_max) return unusable("tables do not fit in shared memory");
-  tt.threads = threads;
-  tt.cpb = threads / G;
+  const size_t fixed = main_blob_bytes + (size_t)tt.ndbl * 8 + (size_t)tt.nint * 4 + 32;
+  const size_t avail = smem_max > fixed ? smem_max - fixed : 0;
+  int cpb = (int)std::min<size_t>(avail / ((size_t)tt.pc_dbl * 8), (size_t)tile_max_threads(G) / G);
+  if (cpb < 1) return unusable("tables do not fit in shared memory");
+  const int maxgpw = 32 / G;                                  // lane groups a warp can hold
+  int warps = (cpb + maxgpw - 1) / maxgpw;
+  if (const char *e = getenv("RXN_TILE_WARPS")) warps = std::max(warps, std::min(tile_max_threads(G) / 32, atoi(e)));
+  if (const char *e = getenv("RXN_TILE_CELLS")) cpb = std::max(1, std::min(cpb, atoi(e)));
+  tt.gpw = (cpb + warps - 1) / warps;
+  tt.cpb = cpb;
+  tt.threads = 32 * warps;
+  const int threads = tt.threads;
   p->smem_bytes = fixed + (size_t)tt.cpb * tt.pc_dbl * 8;
   p->grid = prop.multiProcessorCount;                         // x resident CTAs per SM (occupancy query at launch)
 
@@ -192,8 +198,8 @@ int tile_plan_build(const RxnTablesDesc *d, const DevTab &h, const std::vector<d
   p->usable = true;
   p->err.clear();
   if (getenv("RXN_TILE_VERBOSE"))
-    fprintf(stderr, "[rxn tile] G=%d R=%d threads=%d cells/CTA=%d smem=%zu B (per cell %d B) grid=%d ncls=%d planA T=%d (%d terms) planB T=%d (%d terms)\n",
-            G, R, threads, tt.cpb, p->smem_bytes, tt.pc_dbl * 8, p->grid, tt.ncls, tt.TA, p->termsA, tt.TB, p->termsB);
+    fprintf(stderr, "[rxn tile] G=%d rows/lane=%d threads=%d (cells/warp %d) cells/CTA=%d smem=%zu B (per cell %d B) grid=%d ncls=%d planA T=%d (%d terms) planB T=%d (%d terms)\n",
+            G, R, threads, tt.gpw, tt.cpb, p->smem_bytes, tt.pc_dbl * 8, p->grid, tt.ncls, tt.TA, p->termsA, tt.TB, p->termsB);
   return RXN_OK;
 }
 
@@ -205,8 +211,8 @@ void tile_plan_free(TilePlan *p) {
 
 int tile_launch_react(const TilePlan &p, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
                       long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, cudaStream_t stream) {
-#define RXN_TILE_CASE(g, r) \
-  if (p.tt.G == g && p.tt.R == r) { tile_launch_variant<g, r>(p, h, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags, stream); return RXN_OK; }
+#define RXN_TILE_CASE(g) \
+  if (p.tt.G == g) { tile_launch_variant<g>(p, h, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags, stream); return RXN_OK; }
   RXN_TILE_SHAPES(RXN_TILE_CASE)
 #undef RXN_TILE_CASE
   return RXN_ERR_UNSUPPORTED;

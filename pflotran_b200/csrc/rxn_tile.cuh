@@ -37,17 +37,20 @@
 
 namespace rxn {
 
+// CTA size bound per lane-group width (registers per thread = 64K / bound)
+constexpr int tile_max_threads(int G) { return G <= 2 ? 128 : G <= 8 ? 384 : G == 16 ? 768 : 1024; }
+
 struct TileTab {
-  int G, R, NP, LDJ, threads, cpb;
+  int G, NP, LDJ, threads, cpb, gpw;   // gpw: lane groups (cells) per warp
   int ncls, maxsrf, need_gam, percell_logK;
-  // plan blob: doubles
-  int o_cls_z2, o_cls_a0, o_nlk, o_A_coef, o_B_coef;
+  // plan blob: doubles.  *_rec: 16-byte records {double coef; int code; int key}, lane l at [t*G + l]
+  int o_A_rec, o_B_rec, o_cls_z2, o_cls_a0, o_pz2, o_cz2, o_nlk;
   // plan blob: ints
-  int o_pri_cls, o_cplx_cls, o_A_code, o_A_ent, o_B_code, o_B_ent;
+  int o_pri_cls, o_cplx_cls;
   int TA, TB;
   int ndbl, nint;
-  // per-cell shared memory (offsets in doubles)
-  int c_m, c_invm, c_lna, c_tot, c_gam, c_sm, c_lng, c_sc, c_dsx, c_free, c_lk, pc_dbl;
+  // per-cell shared memory (offsets in doubles; J = [NP rows][LDJ] at 0, b = column NP)
+  int c_m, c_invm, c_lna, c_tot, c_lgp, c_fix, c_tsorb, c_gam, c_sm, c_lng, c_sc, c_dsx, c_free, c_mnrl, c_r0, c_seq, c_lk, pc_dbl;
 };
 
 struct TilePlan {

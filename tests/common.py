@@ -27,6 +27,17 @@ def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, w
             a, b = a[:, cells], b[:, cells]
         # values far below the row's scale are differences of O(1) sums: compare them on that scale
         scale = np.maximum(np.abs(b), 1e-13 * np.max(np.abs(b), axis=1, keepdims=True))
+        if f == 'TOTAL' and tables is not None and tables.neqcplx:
+            # total_i = m_i + sum_k nu_ik sec_molal_k (reaction.F90:4095-4124) cancels when nu changes sign (H+):
+            # a relative perturbation eps of the terms moves it by eps * (m_i + sum_k |nu_ik| sec_molal_k)
+            ids, st = np.asarray(tables.eqcplxspecid), np.asarray(tables.eqcplxstoich)
+            sm = st_b['SEC_MOLAL'] if cells is None else st_b['SEC_MOLAL'][:, cells]
+            mag = np.abs(st_b['PRI_MOLAL'] if cells is None else st_b['PRI_MOLAL'][:, cells]).copy()
+            for k in range(tables.neqcplx):
+                for q in range(1, ids[k, 0] + 1):
+                    mag[ids[k, q] - 1] += abs(st[k, q]) * np.abs(sm[k])
+            den = (st_b['DEN_KG'] if cells is None else st_b['DEN_KG'][:, cells]) * 1.0e-3
+            scale = np.maximum(scale, mag * den)
         if f == 'MNRL_RATE' and tables is not None:
             # rate = -area*k*(1 - QK) (reaction_mineral.F90:795-816): near equilibrium 1 - QK cancels, so a
             # relative perturbation eps of the molalities moves the rate by ~eps*area*k*QK*sum|nu|, not eps*|rate|
