@@ -71,3 +71,26 @@ def test_product_does_not_import_oracle():
                     if re.search(r'(from|import)\s+oracle|oracle/|liborc|libemul|tests/emul', t):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_fortran_shim_binds_exported_symbols_in_struct_order():
+    """fortran/rxn_b200_shim.F90 (not compilable here: no Fortran compiler) names only exported
+    symbols, and its bind(C) mirror of RxnTablesDesc lists the fields in the order of the C struct."""
+    src = open(os.path.join(ROOT, 'fortran', 'rxn_b200_shim.F90')).read()
+    bound = re.findall(r"bind\(C,\s*name='(rxn_[a-z_0-9]+)'\)", src)
+    assert len(bound) >= 18
+    L = C.CDLL(rt.LIB_PATH)
+    for n in bound:
+        assert hasattr(L, n), 'shim binds %s which librxn_b200.so does not export' % n
+    body = src[src.index('type, bind(C), public :: rxn_tables_desc_type'):src.index('end type rxn_tables_desc_type')]
+    body = re.sub(r'!.*', '', body).replace('&\n', ' ')
+    f_fields = []
+    for line in body.splitlines()[1:]:
+        if '::' in line:
+            f_fields += [x.strip() for x in line.split('::')[1].split(',') if x.strip()]
+    c_fields = [n for n, _ in abi.RxnTablesDesc._fields_]
+    assert [f.lower() for f in f_fields] == [c.lower() for c in c_fields]
+    # field enum values
+    for i, name in enumerate(abi.FIELDS):
+        m = re.search(r'RXN_F_%s\s*=\s*(\d+)' % name, src)
+        assert m and int(m.group(1)) == i, name
