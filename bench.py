@@ -313,7 +313,8 @@ def run_ours(args):
                        'mean_newton_iterations': wm['mean_newton_iterations'], 'cells_with_nonreference_flags': bad_all,
                        'l2_policy': 'inputs (%.1f GB of cell state per GPU) larger than L2; no flush needed'
                                     % (n * wm['bytes_per_cell'] / 1e9),
-                       'kernel': {0: 'auto', 1: 'thread-per-cell', 2: 'lane-group-per-cell'}[args.kernel]},
+                       'kernel': {0: 'auto (resident-lane when the tables allow it)', 1: 'thread-per-cell (local memory)',
+                                  2: 'lane-group-per-cell', 3: 'resident-lane'}[args.kernel]},
             'e2e': {'value': total_cells * args.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': nb,
                     'd2h_bytes_per_step': nb + 2 * n * 4},
             'gpu_launches': int(launches * world),
@@ -351,7 +352,7 @@ def main():
     ap.add_argument('--workload', default='hanford300a_eq', choices=sorted(DEFAULT_CELLS))
     ap.add_argument('--cells', type=int, default=0, help='cells per GPU (default: the BASELINE config size)')
     ap.add_argument('--dt', type=float, default=3600.0)
-    ap.add_argument('--kernel', type=int, default=0, choices=[0, 1, 2])
+    ap.add_argument('--kernel', type=int, default=0, choices=[0, 1, 2, 3])
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

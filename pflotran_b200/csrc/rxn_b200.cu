@@ -19,6 +19,7 @@
 #include "rxn_kernels.cuh"
 #include "rxn_pack.h"
 #include "rxn_tile.cuh"
+#include "rxn_lane.cuh"
 
 using namespace rxn;
 
@@ -50,6 +51,7 @@ int fail(int code, const char *fmt, ...) {
 struct RxnTables {
   DevTab h;
   TilePlan tile;           // cooperative (lane-group per cell) kernel plan, rxn_tile.cuh
+  mutable LaneKernel lane; // resident-lane (thread per cell, state in shared memory) kernel, rxn_lane.cuh
   double *d_blob = nullptr;
   size_t blob_bytes = 0;
   int device = 0;
@@ -68,7 +70,8 @@ struct RxnState {
   // grow-only scratch for the host-buffer entry points
   void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[4] = {0, 0, 0, 0};
-  int react_kernel = 0;    // 0 auto, 1 thread-per-cell, 2 tile
+  int react_kernel = 0;    // 0 auto, 1 thread-per-cell, 2 cooperative tile, 3 resident lane
+  unsigned long long *d_counter = nullptr;   // work counter of the resident-lane kernel
 };
 
 namespace {
@@ -186,6 +189,8 @@ int rxn_tables_create(const RxnTablesDesc *d, int device, RxnTables **out) {
   }
   rc = tile_plan_build(d, h, P.d, P.i, t->blob_bytes, device, &t->tile);
   if (rc != RXN_OK) { int rc2 = fail(rc, "tile plan: %s", t->tile.err.c_str()); cudaFree(t->d_blob); delete t; return rc2; }
+  rc = lane_kernel_build(h, P.d, P.i, device, &t->lane);
+  if (rc != RXN_OK) { int rc2 = fail(rc, "lane plan: %s", t->lane.plan.err.c_str()); tile_plan_free(&t->tile); cudaFree(t->d_blob); delete t; return rc2; }
   *out = t;
   return RXN_OK;
 }
@@ -195,6 +200,7 @@ int rxn_tables_destroy(RxnTables *t) {
   cudaSetDevice(t->device);
   if (t->d_blob) cudaFree(t->d_blob);
   tile_plan_free(&t->tile);
+  lane_kernel_free(&t->lane);
   delete t;
   return RXN_OK;
 }
@@ -245,6 +251,7 @@ int rxn_state_destroy(RxnState *s) {
   cudaSetDevice(s->t->device);
   for (int f = 0; f < RXN_F_COUNT; ++f) if (s->S.f[f]) cudaFree(s->S.f[f]);
   if (s->d_active) cudaFree(s->d_active);
+  if (s->d_counter) cudaFree(s->d_counter);
   for (int k = 0; k < 4; ++k) if (s->scratch[k]) cudaFree(s->scratch[k]);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -344,7 +351,7 @@ int rxn_set_cell_scalars(RxnState *s, const double *den_kg, const double *sat, c
 }
 
 int rxn_set_react_kernel(RxnState *s, int which) {
-  if (!s || which < 0 || which > 2) return fail(RXN_ERR_INVALID, "bad argument");
+  if (!s || which < 0 || which > 3) return fail(RXN_ERR_INVALID, "bad argument");
   s->react_kernel = which;
   return RXN_OK;
 }
@@ -352,11 +359,23 @@ int rxn_set_react_kernel(RxnState *s, int which) {
 static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
                         int32_t *d_iters, int32_t *d_flags) {
   const RxnTables *t = s->t;
-  // the cooperative kernel keeps dtotal only as Newton scratch: states with DTOTAL materialised use thread-per-cell
-  const bool tile_ok = t->tile.usable && !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
-  const bool use_tile = tile_ok && s->react_kernel != 1;
+  // the shared-memory kernels keep dtotal only as Newton scratch: states with DTOTAL materialised use thread-per-cell
+  const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
+  const bool tile_ok = t->tile.usable && no_dtotal, lane_ok = t->lane.plan.usable && no_dtotal;
   if (s->react_kernel == 2 && !tile_ok)
     return fail(RXN_ERR_UNSUPPORTED, "cooperative kernel unavailable: %s", t->tile.usable ? "DTOTAL is materialised" : t->tile.err.c_str());
+  if (s->react_kernel == 3 && !lane_ok)
+    return fail(RXN_ERR_UNSUPPORTED, "resident-lane kernel unavailable: %s", t->lane.plan.usable ? "DTOTAL is materialised" : t->lane.plan.err.c_str());
+  const bool use_lane = lane_ok && (s->react_kernel == 0 || s->react_kernel == 3);
+  const bool use_tile = !use_lane && tile_ok && s->react_kernel != 1;
+  if (use_lane) {
+    if (!s->d_counter) CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+    int rc = lane_launch_react(t->lane, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->d_counter, s->stream);
+    if (rc != RXN_OK) return fail(rc, "resident-lane kernel launch failed (N=%d CPB=%d): %s", t->lane.plan.lt.N, t->lane.plan.lt.CPB,
+                                  cudaGetErrorString(cudaGetLastError()));
+    ++g_launches;
+    return RXN_OK;
+  }
   if (use_tile) {
     int rc = tile_launch_react(t->tile, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->stream);
     if (rc != RXN_OK) return fail(rc, "no cooperative kernel variant for G=%d", t->tile.tt.G);

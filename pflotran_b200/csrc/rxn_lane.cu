@@ -1,0 +1,89 @@
+// rxn_lane.cu — host side of the resident-lane RReact kernel: shape selection, plan upload, launch dispatch.
+#include <cstdio>
+#include <cstdlib>
+
+#include "rxn_lane.cuh"
+
+namespace rxn {
+
+#define RXN_LANE_DECL(n, cpb)                                                                                                 \
+  template <> int lane_launch_variant<n, cpb>(const LaneTab &, size_t, int, const DevTab &, const double *, const double *,    \
+                                              const DevState &, double *, const int32_t *, long long, double, int, int32_t *, \
+                                              int32_t *, unsigned long long *, cudaStream_t);
+RXN_LANE_SHAPES(RXN_LANE_DECL)
+#undef RXN_LANE_DECL
+
+int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, int device, LaneKernel *k) {
+  LanePlan &p = k->plan;
+  p.usable = false;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { p.err = "cudaGetDeviceProperties failed"; return RXN_OK; }
+  k->sm_count = prop.multiProcessorCount;
+  const int N = lane_N_for(h.naq);
+  if (N == 0) { p.err = "naq exceeds the compiled shapes"; return RXN_OK; }
+  int force_cpb = 0;
+  if (const char *e = getenv("RXN_LANE_CPB")) force_cpb = atoi(e);
+  static const LaneShape shapes[] = {
+#define RXN_LANE_ROW(n, cpb) {n, cpb},
+      RXN_LANE_SHAPES(RXN_LANE_ROW)
+#undef RXN_LANE_ROW
+  };
+  for (const LaneShape &s : shapes) {
+    if (s.N != N) continue;
+    if (force_cpb && s.CPB != force_cpb) continue;
+    int rc = lane_plan_build(h, bd, bi, s.N, s.CPB, prop.sharedMemPerBlockOptin, &p);
+    if (rc != RXN_OK) return rc;
+    if (p.usable) break;
+    if (p.err.find("does not fit") == std::string::npos) break;     // chemistry, not shape, is the obstacle
+  }
+  if (!p.usable) return RXN_OK;
+  if (cudaMalloc(&k->d_blob, p.blob.size()) != cudaSuccess ||
+      cudaMemcpy(k->d_blob, p.blob.data(), p.blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    p.usable = false;
+    p.err = std::string("plan upload failed: ") + cudaGetErrorString(cudaGetLastError());
+    return RXN_ERR_CUDA;
+  }
+  k->mr_ld = h.mr_ld;
+  for (int i = 0; i < h.nmr; ++i) k->mr_nrate.push_back(bi[h.o_mr_nrate + i]);
+  k->mr_rate.assign(bd.begin() + h.o_mr_rate, bd.begin() + h.o_mr_rate + (size_t)h.nmr * h.mr_ld);
+  k->mr_frac.assign(bd.begin() + h.o_mr_frac, bd.begin() + h.o_mr_frac + (size_t)h.nmr * h.mr_ld);
+  if (getenv("RXN_LANE_VERBOSE"))
+    fprintf(stderr, "[rxn lane] N=%d CPB=%d smem=%zu B blob=%zu B classes=%d spec %d terms/%d steps, planA %d/%d, planB %d/%d\n",
+            p.lt.N, p.lt.CPB, p.smem_bytes, p.blob.size(), p.lt.ncls, p.terms_spec, p.steps_spec, p.terms_A, p.steps_A, p.terms_B,
+            p.steps_B);
+  return RXN_OK;
+}
+
+void lane_kernel_free(LaneKernel *k) {
+  if (k->d_blob) cudaFree(k->d_blob);
+  k->d_blob = nullptr;
+  k->plan.usable = false;
+}
+
+int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
+                      long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
+                      cudaStream_t stream) {
+  LaneTab lt = k.plan.lt;
+  // K1 = sum_r k_r/(1 + k_r dt) f_r (multirate_prepare, rxn_device.cuh): the same for every cell
+  for (int ikr = 0; ikr < lt.nmr && ikr < 2; ++ikr) {
+    double K1 = 0.0;
+    for (int irate = 0; irate < k.mr_nrate[ikr]; ++irate) {
+      const double rate = k.mr_rate[(size_t)ikr * k.mr_ld + irate], frac = k.mr_frac[(size_t)ikr * k.mr_ld + irate];
+      const double kdt = rate * dt;
+      const double one_plus_kdt = 1.0 + kdt;
+      const double kk = rate / one_plus_kdt;
+      K1 = K1 + kk * frac;
+    }
+    lt.mrK1[ikr] = K1;
+  }
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXN_ERR_CUDA;
+#define RXN_LANE_CASE(n, cpb)                                                                                                    \
+  if (lt.N == n && lt.CPB == cpb)                                                                                                \
+    return lane_launch_variant<n, cpb>(lt, k.plan.smem_bytes, k.sm_count, h, k.d_blob, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, \
+                                       iters, flags, counter, stream);
+  RXN_LANE_SHAPES(RXN_LANE_CASE)
+#undef RXN_LANE_CASE
+  return RXN_ERR_UNSUPPORTED;
+}
+
+}  // namespace rxn

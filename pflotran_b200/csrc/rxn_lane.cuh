@@ -1,0 +1,36 @@
+// rxn_lane.cuh — host interface of the resident-lane RReact kernel (plan: rxn_lane.h,
+// device code: rxn_lane_dev.cuh, one translation unit per shape: rxn_lane_variant.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rxn_lane.h"
+
+namespace rxn {
+
+// shapes compiled into the library: X(N, CPB), per N in descending CPB order (keep in sync with the Makefile)
+#define RXN_LANE_SHAPES(X)                                                                                       \
+  X(4, 512) X(4, 256) X(4, 128) X(4, 64) X(8, 192) X(8, 128) X(8, 64) X(12, 96) X(12, 64) X(12, 32)             \
+  X(15, 64) X(15, 60) X(15, 56) X(15, 48) X(15, 32) X(16, 64) X(16, 56) X(16, 48) X(16, 32)                     \
+  X(24, 32) X(24, 28) X(24, 24) X(24, 16)
+
+struct LaneKernel {
+  LanePlan plan;
+  double *d_blob = nullptr;
+  int sm_count = 0;
+  std::vector<double> mr_rate, mr_frac;   // host copies for the per-launch K1 sums
+  std::vector<int> mr_nrate;
+  int mr_ld = 0;
+};
+
+template <int N, int CPB>
+int lane_launch_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
+                        const DevState &S, double *tran_xx, const int32_t *l2g, long long nlocal, double dt, int dt_mode,
+                        int32_t *iters, int32_t *flags, unsigned long long *counter, cudaStream_t stream);
+
+int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, int device, LaneKernel *k);
+void lane_kernel_free(LaneKernel *k);
+int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
+                      long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
+                      cudaStream_t stream);
+
+}  // namespace rxn

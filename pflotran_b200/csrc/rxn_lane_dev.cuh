@@ -1,0 +1,814 @@
+// rxn_lane_dev.cuh — device code of the resident-lane RReact kernel (design: rxn_lane.h).
+// One thread = one cell; per-cell arrays in shared memory, lane-fastest; tables + term streams
+// staged once per persistent CTA.  Reference routines restated (file:line at each site):
+// RReact reaction.F90:3322-3511, RTotal :4057-4158, RActivityCoefficients (LAG) :3994-4050,
+// RTotalSorbEqSurfCplx1 reaction_surf_complex.F90:658-934, RMultiRateSorption :566-654,
+// RKineticMineral reaction_mineral.F90:564-1000, RSolve reaction.F90:4835-4880,
+// ludcmp/lubksb utility.F90:393-523.
+//
+// The per-lane routines contain no warp-level operation, so the same source is compiled for the
+// host by tests/emul (RXN_LANE_HOST) and checked against the oracle in the CPU-only suite.
+//
+// Deviations from the reference's operation order (REASSOC, all <= 1e-14 relative; parity is
+// measured in tests/): those of the cooperative kernel (rxn_tile.cuh) plus
+//   - J is assembled as dR_i/d ln m_j (column j times m_j): in the log formulation the reference's
+//     (.../m_j)*m_j pair is not executed; the row norms of RSolve use |Jln_ij|/m_j;
+//   - long sums of RTotal are split over 4 accumulators (WIDE groups), combined (a0+a1)+(a2+a3).
+#pragma once
+#include "rxn_lane.h"
+
+#ifndef RXN_LANE_HOST
+#include <cuda_runtime.h>
+#define LANE_DEV static __device__ __forceinline__
+#define LANE_COLD static __device__ __noinline__
+#else
+#define LANE_DEV static inline
+#define LANE_COLD static inline
+struct double2 { double x, y; };
+struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+#endif
+
+namespace rxn {
+namespace lane {
+
+#define RXN_LOG_TO_LN 2.30258509299           /* pflotran_constants.F90:48 (truncated on purpose) */
+#define RXN_IDEAL_GAS_CONSTANT 8.31446        /* pflotran_constants.F90:53 */
+
+#ifndef RXN_LANE_HOST
+extern __shared__ __align__(16) double tsm[];
+#else
+static thread_local double *tsm = nullptr;
+#endif
+
+#define TSM2 (reinterpret_cast<double2 *>(tsm))
+#define TD(lt, o) (tsm[(o)])
+#define TI(lt, o) (reinterpret_cast<const int *>(tsm)[2 * (lt).blob_dbl + (o)])
+#define TI4(lt, o4) (reinterpret_cast<const int4 *>(tsm)[((lt).blob_dbl >> 1) + (o4)])    /* o4 in units of 4 ints */
+#define TD2(lt, o2) (reinterpret_cast<const double2 *>(tsm)[(o2)])                          /* o2 in units of 2 doubles */
+
+#define GSL(S, field, row, cell) ((S).f[field][(long long)(row) * (S).ld + (cell)])
+
+// per-lane context: registers
+template <int N>
+struct Lane {
+  int t;                  // lane id within the CTA
+  int jb;                 // double2 index of this lane's J(0,0) pair
+  int vm, vlna, vlng, vsm, vtot, vscr, vsc, vfree, vmnrl, vr0, vseq, vlk;   // double index of element 0 of each slot
+  double fix[N];          // fixed accumulation (reaction.F90:3370-3400)
+  double den_kg_per_L, psv, psvd, v_t, volume, porosity, soil_density, temp, ln_act_h2o, den_kg;
+  long long item, cell;
+  int iter, flags;
+};
+
+template <int N, int CPB>
+LANE_DEV void lane_bind(const LaneTab &lt, Lane<N> &c, int t) {
+  c.t = t;
+  c.jb = lt.o_J2 + t;
+  const int v = lt.o_vec + t;
+  c.vm = v + lt.s_m * CPB; c.vlna = v + lt.s_lna * CPB; c.vlng = v + lt.s_lng * CPB; c.vsm = v + lt.s_sm * CPB;
+  c.vtot = v + lt.s_tot * CPB; c.vscr = v + lt.s_scr * CPB; c.vsc = v + lt.s_sc * CPB; c.vfree = v + lt.s_free * CPB;
+  c.vmnrl = v + lt.s_mnrl * CPB; c.vr0 = v + lt.s_r0 * CPB; c.vseq = v + lt.s_seq * CPB; c.vlk = v + lt.s_lk * CPB;
+}
+
+// J element (i, j) of this lane, j = N is the right-hand side b
+#define JP(c, i, p) TSM2[(c).jb + ((i) * LDJ2 + (p)) * CPB]
+#define JE(c, i, j) tsm[2 * ((c).jb + ((i) * LDJ2 + ((j) >> 1)) * CPB) + ((j) & 1)]
+
+LANE_COLD double c_exp(double x) { return exp(x); }
+LANE_COLD double c_log(double x) { return log(x); }
+LANE_COLD double c_pow(double x, double y) { return pow(x, y); }
+
+// ---------------------------------------------------------------------------------------------
+// RActivityCoefficients, LAG algorithm — reaction.F90:3994-4050.  One Debye-Hueckel exponent per
+// (Z^2, a0) class; ln gamma is kept (never exponentiated inside the Newton loop).
+template <int N, int CPB>
+LANE_DEV void lane_act_coefs(const LaneTab &lt, Lane<N> &c) {
+  const int n = lt.n, ncplx = lt.ncplx;
+  double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0, psum = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const double mm = tsm[c.vm + i * CPB];
+    p0 = fma(mm, TD(lt, lt.d_pz2 + i), p0);
+    if (lt.use_act_h2o && i + 1 != lt.h2o_aq_id) psum += mm;
+  }
+  int k = 0;
+#pragma unroll 1
+  for (; k + 4 <= ncplx; k += 4) {                             // REASSOC: 4 partial sums, Z^2 premultiplied
+    const double s0 = tsm[c.vsm + k * CPB], s1 = tsm[c.vsm + (k + 1) * CPB], s2 = tsm[c.vsm + (k + 2) * CPB],
+                 s3 = tsm[c.vsm + (k + 3) * CPB];
+    p0 = fma(s0, TD(lt, lt.d_cz2 + k), p0); p1 = fma(s1, TD(lt, lt.d_cz2 + k + 1), p1);
+    p2 = fma(s2, TD(lt, lt.d_cz2 + k + 2), p2); p3 = fma(s3, TD(lt, lt.d_cz2 + k + 3), p3);
+    if (lt.use_act_h2o) psum += (s0 + s1) + (s2 + s3);
+  }
+#pragma unroll 1
+  for (; k < ncplx; ++k) {
+    const double s0 = tsm[c.vsm + k * CPB];
+    p1 = fma(s0, TD(lt, lt.d_cz2 + k), p1);
+    if (lt.use_act_h2o) psum += s0;
+  }
+  const double I = 0.5 * ((p0 + p1) + (p2 + p3));
+  const double sqrt_I = sqrt(I);
+  tsm[c.vlng] = 0.0;
+#pragma unroll 2
+  for (int q = 1; q < lt.ncls; ++q)
+    tsm[c.vlng + q * CPB] =
+        (-TD(lt, lt.d_cls_z2 + q) * sqrt_I * lt.debyeA / (1.0 + TD(lt, lt.d_cls_a0 + q) * lt.debyeB * sqrt_I) + lt.debyeBdot * I) * RXN_LOG_TO_LN;
+  if (lt.use_act_h2o) {                                        // :4043-4050
+    const double a = 1.0 - 0.017 * psum;
+    c.ln_act_h2o = (a > 0.0) ? c_log(a) : 0.0;
+    tsm[c.vlna + (lt.n + 1) * CPB] = c.ln_act_h2o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// term streams: 4 accumulators advance together, one {coef[4], offset[4]} record per step
+LANE_DEV void lane_run_group(const LaneTab &lt, int t, int c0, int o0, int nsteps, double &a0, double &a1, double &a2, double &a3) {
+#pragma unroll 2
+  for (int s = 0; s < nsteps; ++s) {
+    const double2 ca = TD2(lt, (c0 + 1 + s) * 2), cb = TD2(lt, (c0 + 1 + s) * 2 + 1);
+    const int4 of = TI4(lt, o0 + s);
+    a0 = fma(ca.x, tsm[of.x + t], a0);
+    a1 = fma(ca.y, tsm[of.y + t], a1);
+    a2 = fma(cb.x, tsm[of.z + t], a2);
+    a3 = fma(cb.y, tsm[of.w + t], a3);
+  }
+}
+
+// ln a_i = ln m_i + ln gamma_i, then sec_molal_k = exp(lnQK_k - ln gamma_k)   (RTotal, reaction.F90:4090-4122)
+template <int N, int CPB>
+LANE_DEV void lane_speciate(const LaneTab &lt, Lane<N> &c) {
+  const int n = lt.n, t = c.t;
+#pragma unroll 3
+  for (int i = 0; i < n; ++i)
+    tsm[c.vlna + i * CPB] = log(tsm[c.vm + i * CPB]) + tsm[c.vlng + TI(lt, lt.i_pcls + i) * CPB];
+#pragma unroll 1
+  for (int g = 0; g < lt.spec.ng; ++g) {
+    const int4 hd = TI4(lt, (lt.spec.g0 >> 2) + 2 * g), h2 = TI4(lt, (lt.spec.g0 >> 2) + 2 * g + 1);
+    const int c0 = hd.x, o0 = hd.y, nsteps = hd.z, cb = h2.x >> 2;
+    const int4 m0 = TI4(lt, cb), m1 = TI4(lt, cb + 1), m2 = TI4(lt, cb + 2), m3 = TI4(lt, cb + 3);
+    double a0, a1, a2, a3;
+    if (lt.percell_logK) {
+      a0 = tsm[c.vlk + (m0.z < 0 ? 0 : m0.z) * CPB]; a1 = tsm[c.vlk + (m1.z < 0 ? 0 : m1.z) * CPB];
+      a2 = tsm[c.vlk + (m2.z < 0 ? 0 : m2.z) * CPB]; a3 = tsm[c.vlk + (m3.z < 0 ? 0 : m3.z) * CPB];
+    } else {
+      const double2 ia = TD2(lt, c0 * 2), ib = TD2(lt, c0 * 2 + 1);
+      a0 = ia.x; a1 = ia.y; a2 = ib.x; a3 = ib.y;
+    }
+    lane_run_group(lt, t, c0, o0, nsteps, a0, a1, a2, a3);
+    // REASSOC: exp(lnQK)/gamma_k -> exp(lnQK - ln gamma_k)
+    const double e0 = exp(a0 - tsm[m0.y + t]), e1 = exp(a1 - tsm[m1.y + t]), e2 = exp(a2 - tsm[m2.y + t]),
+                 e3 = exp(a3 - tsm[m3.y + t]);
+    tsm[m0.x + t] = e0; tsm[m1.x + t] = e1; tsm[m2.x + t] = e2; tsm[m3.x + t] = e3;
+  }
+}
+
+// plan A: tot_i <- sum_k nu_ik sm_k ; plan B: Jln_ij = Jln_ji <- (sum_k nu_ik nu_jk sm_k) * scale
+template <int N, int CPB, bool JAC>
+LANE_DEV void lane_plan(const LaneTab &lt, Lane<N> &c, double scale) {
+  const LaneStream S = JAC ? lt.planB : lt.planA;
+  const int t = c.t, t2 = 2 * c.t;
+#pragma unroll 1
+  for (int g = 0; g < S.ng; ++g) {
+    const int4 hd = TI4(lt, (S.g0 >> 2) + 2 * g), h2 = TI4(lt, (S.g0 >> 2) + 2 * g + 1);
+    const int c0 = hd.x, o0 = hd.y, nsteps = hd.z, mode = hd.w, cb = h2.x >> 2;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    lane_run_group(lt, t, c0, o0, nsteps, a0, a1, a2, a3);
+    if (mode == LANE_WIDE) {
+      const double a = (a0 + a1) + (a2 + a3);
+      const int4 d = TI4(lt, cb);
+      if (!JAC) tsm[d.x + t] = a;
+      else { const double v = a * scale; tsm[d.x + t2] = v; tsm[d.y + t2] = v; }
+    } else if (!JAC) {
+      const int4 d = TI4(lt, cb);
+      tsm[d.x + t] = a0; tsm[d.y + t] = a1; tsm[d.z + t] = a2; tsm[d.w + t] = a3;
+    } else {
+      const int4 d0 = TI4(lt, cb), d1 = TI4(lt, cb + 1);
+      const double v0 = a0 * scale, v1 = a1 * scale, v2 = a2 * scale, v3 = a3 * scale;
+      tsm[d0.x + t2] = v0; tsm[d0.y + t2] = v0; tsm[d0.z + t2] = v1; tsm[d0.w + t2] = v1;
+      tsm[d1.x + t2] = v2; tsm[d1.y + t2] = v2; tsm[d1.z + t2] = v3; tsm[d1.w + t2] = v3;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RTotalSorbEqSurfCplx1 — reaction_surf_complex.F90:658-934, one surface complexation reaction.
+//   target_i (tsm[tb + i*ts]: column N of J for equilibrium reactions, the S_eq vector for multirate ones)
+//            += total sorbed of primary i
+//   addJ: Jln(i, j) += fac * d(total_sorb_i)/d ln m_j
+template <int N, int CPB>
+LANE_DEV void lane_srf_rxn(const LaneTab &lt, Lane<N> &c, const DevState &S, int irxn, double fac, bool addJ, bool store_conc, int tb,
+                           int ts) {
+  constexpr int LDJ2 = (N + 2) / 2;
+  const int n = lt.n;
+  const double tol = 1.0e-12;
+  const int c0 = TI(lt, lt.i_rxn_cptr + irxn), c1 = TI(lt, lt.i_rxn_cptr + irxn + 1);
+  const int nlk0 = lt.d_nlk + lt.ncplx + lt.nkin;
+  double free_site_conc = tsm[c.vfree + irxn * CPB];
+  double site_density;
+  const int surf_type = TI(lt, lt.i_rxn_surf_type + irxn);
+  const double dens = TD(lt, lt.d_rxn_density + irxn);
+  if (surf_type == RXN_MINERAL_SURFACE) site_density = dens * tsm[c.vmnrl + (TI(lt, lt.i_rxn_to_surf + irxn) - 1) * CPB];
+  else if (surf_type == RXN_ROCK_SURFACE) site_density = dens * c.soil_density * (1.0 - c.porosity);
+  else site_density = dens;
+  if (site_density < 1.0e-40) return;                         // :749
+  const int stoich_flag = TI(lt, lt.i_rxn_flag + irxn);
+  bool one_more = false;
+  int num_iterations = 0;
+  double damping_factor = 1.0;
+#pragma unroll 1
+  for (;;) {                                                  // :760-829
+    num_iterations = num_iterations + 1;
+    const double ln_free_site = c_log(free_site_conc);
+    double total = free_site_conc;
+#pragma unroll 1
+    for (int j = c0; j < c1; ++j) {
+      const int icplx = TI(lt, lt.i_rxn_cid + j);
+      double lnQK = lt.percell_logK ? tsm[c.vlk + (lt.ncplx + lt.nkin + icplx) * CPB] : TD(lt, nlk0 + icplx);
+      const double sh2o = TD(lt, lt.d_sh2o + icplx), site_st = TD(lt, lt.d_site_st + icplx);
+      if (sh2o != 0.0) lnQK = lnQK + sh2o * c.ln_act_h2o;
+      lnQK = lnQK + site_st * ln_free_site;
+      const int p1 = TI(lt, lt.i_sptr + icplx + 1);
+#pragma unroll 1
+      for (int p = TI(lt, lt.i_sptr + icplx); p < p1; ++p) lnQK = lnQK + TD(lt, lt.d_sst + p) * tsm[c.vlna + TI(lt, lt.i_sid + p) * CPB];
+      const double s = c_exp(lnQK);
+      tsm[c.vsc + (j - c0) * CPB] = s;
+      total = total + site_st * s;
+    }
+    if (one_more) break;
+    if (stoich_flag) {
+      const double res = site_density - total;
+      double dres_dfree_site = 1.0;
+#pragma unroll 1
+      for (int j = c0; j < c1; ++j)
+        dres_dfree_site = dres_dfree_site + TD(lt, lt.d_site_st + TI(lt, lt.i_rxn_cid + j)) * tsm[c.vsc + (j - c0) * CPB] / free_site_conc;
+      const double dfree_site_conc = res / dres_dfree_site;
+      if (num_iterations > 1000) damping_factor = 0.5;
+      free_site_conc = free_site_conc + damping_factor * dfree_site_conc;
+      const double rel_change = fabs(dfree_site_conc / free_site_conc);
+      if (rel_change < tol) one_more = true;
+      if (num_iterations > 100000) { c.flags |= RXN_FLAG_CAPPED; one_more = true; }   // reference would spin
+    } else {
+      total = total / free_site_conc;
+      free_site_conc = site_density / total;
+      one_more = true;
+    }
+  }
+  tsm[c.vfree + irxn * CPB] = free_site_conc;
+  if (store_conc) {
+#pragma unroll 1
+    for (int j = c0; j < c1; ++j) GSL(S, RXN_F_EQSRFCPLX_CONC, TI(lt, lt.i_rxn_cid + j), c.cell) += tsm[c.vsc + (j - c0) * CPB];
+  }
+  if (addJ) {                                                  // :838-866
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) tsm[c.vscr + i * CPB] = 0.0;
+    double tempreal = 0.0;
+#pragma unroll 1
+    for (int j = c0; j < c1; ++j) {
+      const int icplx = TI(lt, lt.i_rxn_cid + j);
+      const double sc = tsm[c.vsc + (j - c0) * CPB], site_st = TD(lt, lt.d_site_st + icplx);
+      const int p1 = TI(lt, lt.i_sptr + icplx + 1);
+#pragma unroll 1
+      for (int p = TI(lt, lt.i_sptr + icplx); p < p1; ++p) {
+        const int o = c.vscr + TI(lt, lt.i_sid + p) * CPB;
+        tsm[o] = tsm[o] + TD(lt, lt.d_sst + p) * site_st * sc;
+      }
+      tempreal = tempreal + site_st * site_st * sc;
+    }
+    tempreal = tempreal / free_site_conc;
+    tempreal = tempreal + 1.0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) tsm[c.vscr + i * CPB] = -tsm[c.vscr + i * CPB] / tempreal;   // dSx/d ln m_i (the reference divides by m_i)
+  }
+#pragma unroll 1
+  for (int k = c0; k < c1; ++k) {                              // :872-931
+    const int icplx = TI(lt, lt.i_rxn_cid + k);
+    const double sc = tsm[c.vsc + (k - c0) * CPB];
+    const int p0 = TI(lt, lt.i_sptr + icplx), p1 = TI(lt, lt.i_sptr + icplx + 1);
+#pragma unroll 1
+    for (int p = p0; p < p1; ++p) {
+      const int o = tb + TI(lt, lt.i_sid + p) * ts;
+      tsm[o] = tsm[o] + TD(lt, lt.d_sst + p) * sc;
+    }
+    if (!addJ) continue;
+    const double nui_Si_over_Sx = TD(lt, lt.d_site_st + icplx) * sc / free_site_conc;
+#pragma unroll 1
+    for (int q = p0; q < p1; ++q) {
+      const int jc = TI(lt, lt.i_sid + q);
+      const double tr = TD(lt, lt.d_sst + q) * sc + nui_Si_over_Sx * tsm[c.vscr + jc * CPB];
+#pragma unroll 1
+      for (int p = p0; p < p1; ++p) {
+        const int i = TI(lt, lt.i_sid + p);
+        JE(c, i, jc) = JE(c, i, jc) + (TD(lt, lt.d_sst + p) * tr) * fac;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RKineticMineral — reaction_mineral.F90:564-1000 (tables with prefactors use the cooperative kernel)
+template <int N, int CPB>
+LANE_DEV void lane_kinetic_mineral(const LaneTab &lt, Lane<N> &c) {
+  constexpr int LDJ2 = (N + 2) / 2;
+#pragma unroll 1
+  for (int imnrl = 0; imnrl < lt.nkin; ++imnrl) {
+    double rate_out = 0.0;
+    do {
+      double lnQK = lt.percell_logK ? tsm[c.vlk + (lt.ncplx + imnrl) * CPB] : TD(lt, lt.d_nlk + lt.ncplx + imnrl);
+      const double h2ost = TD(lt, lt.d_kh2o + imnrl);
+      if (h2ost != 0.0) lnQK = lnQK + h2ost * c.ln_act_h2o;
+      const int p0 = TI(lt, lt.i_kptr + imnrl), p1 = TI(lt, lt.i_kptr + imnrl + 1);
+#pragma unroll 1
+      for (int p = p0; p < p1; ++p) lnQK = lnQK + TD(lt, lt.d_kst + p) * tsm[c.vlna + TI(lt, lt.i_kid + p) * CPB];
+      double QK;
+      if (lnQK <= 6.90776) QK = c_exp(lnQK); else QK = 1.0e3;
+      const double k_scale = lt.has_scale ? TD(lt, lt.d_k_scale + imnrl) : 1.0;
+      const double k_Temkin = lt.has_Temkin ? TD(lt, lt.d_k_Temkin + imnrl) : 1.0;
+      const double k_power = lt.has_power ? TD(lt, lt.d_k_power + imnrl) : 1.0;
+      const double k_lim = TD(lt, lt.d_k_lim + imnrl);
+      const double k_aff = TD(lt, lt.d_k_aff + imnrl);
+      double affinity_factor;
+      if (lt.has_Temkin) {
+        if (lt.has_scale) affinity_factor = 1.0 - c_pow(QK, 1.0 / (k_scale * k_Temkin));
+        else affinity_factor = 1.0 - c_pow(QK, 1.0 / k_Temkin);
+      } else if (lt.has_scale) {
+        affinity_factor = 1.0 - c_pow(QK, 1.0 / k_scale);
+      } else {
+        affinity_factor = 1.0 - QK;
+      }
+      const double sign_ = copysign(1.0, affinity_factor);
+      const double volfrac = tsm[c.vmnrl + imnrl * CPB];
+      if (!(volfrac > 0 || sign_ < 0.0)) break;                 // :723
+      if (k_aff > 0.0) {
+        if (sign_ < 0.0 && QK < k_aff) break;
+      }
+      if (k_lim > 0.0) affinity_factor = affinity_factor / (1.0 + (1.0 - affinity_factor) / k_lim);
+      double arrhenius_factor = 1.0;
+      const double Ea = TD(lt, lt.d_k_Ea + imnrl);
+      if (Ea > 0.0) arrhenius_factor = c_exp(Ea / RXN_IDEAL_GAS_CONSTANT * (1.0 / (25.0 + 273.15) - 1.0 / (c.temp + 273.15)));
+      const double sum_prefactor_rate = TD(lt, lt.d_k_rate + imnrl) * arrhenius_factor;
+      double Im_const = -tsm[c.vmnrl + (lt.nkin + imnrl) * CPB], Im;
+      if (lt.has_scale) Im_const = Im_const / k_scale;
+      if (lt.has_power) Im = Im_const * sign_ * c_pow(fabs(affinity_factor), k_power) * sum_prefactor_rate;
+      else Im = Im_const * sign_ * fabs(affinity_factor) * sum_prefactor_rate;
+      rate_out = Im;
+
+      Im_const = Im_const * c.volume;
+      Im = Im * c.volume;
+      double dIm_dQK;
+      if (lt.has_power) dIm_dQK = -Im * k_power / fabs(affinity_factor);
+      else dIm_dQK = -Im_const * sum_prefactor_rate;
+      if (lt.has_Temkin) {
+        if (lt.has_scale) dIm_dQK = dIm_dQK * (1.0 / (k_scale * k_Temkin)) / QK * (1.0 - affinity_factor);
+        else dIm_dQK = dIm_dQK * (1.0 / k_Temkin) / QK * (1.0 - affinity_factor);
+      } else if (lt.has_scale) {
+        dIm_dQK = dIm_dQK * (1.0 / k_scale) / QK * (1.0 - affinity_factor);
+      }
+      const double den = (k_lim <= 0.0) ? 1.0 : 1.0 + (1.0 - affinity_factor) / k_lim;
+#pragma unroll 1
+      for (int p = p0; p < p1; ++p) {
+        const int ip = TI(lt, lt.i_kid + p);
+        const double stp = TD(lt, lt.d_kst + p);
+        JE(c, ip, N) = JE(c, ip, N) + stp * Im;
+#pragma unroll 1
+        for (int q = p0; q < p1; ++q) {
+          const int jcomp = TI(lt, lt.i_kid + q);
+          const double dQK_dCj = TD(lt, lt.d_kst + q) * QK;     // d/d ln m_j: the reference's exp(-ln m_j) factor is not applied
+          const double dQK_dmj = dQK_dCj * c.den_kg * 1.0e-3;
+          if (k_lim <= 0.0) JE(c, ip, jcomp) = JE(c, ip, jcomp) + stp * dIm_dQK * dQK_dmj;
+          else JE(c, ip, jcomp) = JE(c, ip, jcomp) + stp * dIm_dQK * (1.0 + QK / k_lim / den) * dQK_dmj / den;
+        }
+      }
+    } while (false);
+    tsm[c.vmnrl + (2 * lt.nkin + imnrl) * CPB] = rate_out;      // :575 (zeroed) / :816
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RSolve (reaction.F90:4835-4880) + ludcmp/lubksb (utility.F90:393-523) on [Jln | b] in shared memory.
+// Right-looking elimination with the pivot row in registers; per element the same
+// a(i,j) -= a(i,k)*a(k,j), k ascending, as Crout; pivot = last maximum of vv(i)*|a(i,k)|, i >= k.
+// b (column N) goes through the elimination (= forward substitution of lubksb); row-oriented back
+// substitution in the reference's order (REASSOC: times the stored reciprocal pivot instead of a
+// division).  The k loop is a run-time loop; the column range of step k is selected once per step
+// (dispatch on the first pair) so the row loop has no per-row control.  The solution replaces b.
+// Returns 1 if a row is all zero (reference: MPI_Abort).
+template <int N, int CPB, int P0>
+LANE_DEV void lane_lu_swap(Lane<N> &c, int rk, int ri, double2 *pr) {
+  constexpr int LDJ2 = (N + 2) / 2;
+#pragma unroll
+  for (int p = P0; p < LDJ2; ++p) {
+    pr[p] = TSM2[ri + p * CPB];
+    const double2 tk = TSM2[rk + p * CPB];
+    TSM2[ri + p * CPB] = tk;
+    TSM2[rk + p * CPB] = pr[p];
+  }
+}
+template <int N, int CPB, int P0>
+LANE_DEV void lane_lu_elim(Lane<N> &c, int k, int ek, double dum, const double2 *pr) {
+  constexpr int LDJ2 = (N + 2) / 2;
+#pragma unroll 1
+  for (int i = k + 1; i < N; ++i) {
+    const double lik = tsm[ek + i * (2 * LDJ2 * CPB)] * dum;
+    const int ri = c.jb + i * (LDJ2 * CPB);
+#pragma unroll
+    for (int p = P0; p < LDJ2; ++p) {                          // whole pairs: a stale column <= k may be rewritten, it is dead
+      double2 a = TSM2[ri + p * CPB];
+      a.x = a.x - lik * pr[p].x;
+      a.y = a.y - lik * pr[p].y;
+      TSM2[ri + p * CPB] = a;
+    }
+  }
+}
+template <int N, int CPB, int P>
+LANE_DEV void lane_lu_swap_from(Lane<N> &c, int ps, int rk, int ri, double2 *pr) {
+  if constexpr (P < (N + 2) / 2) {
+    if (ps == P) lane_lu_swap<N, CPB, P>(c, rk, ri, pr);
+    else lane_lu_swap_from<N, CPB, P + 1>(c, ps, rk, ri, pr);
+  }
+}
+template <int N, int CPB, int P>
+LANE_DEV void lane_lu_elim_from(Lane<N> &c, int pe, int k, int ek, double dum, const double2 *pr) {
+  if constexpr (P < (N + 2) / 2) {
+    if (pe == P) lane_lu_elim<N, CPB, P>(c, k, ek, dum, pr);
+    else lane_lu_elim_from<N, CPB, P + 1>(c, pe, k, ek, dum, pr);
+  }
+}
+
+template <int N, int CPB>
+LANE_DEV int lane_rsolve(const LaneTab &lt, Lane<N> &c) {
+  constexpr int LDJ2 = (N + 2) / 2;
+  const double tiny = 1.0e-20;
+  const bool use_log = lt.use_log != 0;
+  bool zero = false;
+  {
+    double invm[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) invm[j] = 1.0 / tsm[c.vm + j * CPB];
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+      double2 r[LDJ2];
+#pragma unroll
+      for (int p = 0; p < LDJ2; ++p) r[p] = JP(c, i, p);
+      double mx = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double v = (j & 1) ? r[j >> 1].y : r[j >> 1].x;
+        mx = fmax(mx, fabs(v) * invm[j]);
+      }
+      const double norm = 1.0 / fmax(1.0, mx);
+      double aamax = 0.0;
+#pragma unroll
+      for (int j = 0; j <= N; ++j) {
+        double v = (j & 1) ? r[j >> 1].y : r[j >> 1].x;
+        if (j < N) {
+          if (!use_log) v = v * invm[j];
+          v = v * norm;
+          aamax = fmax(aamax, fabs(v));
+        } else {
+          v = v * norm;
+        }
+        if (j & 1) r[j >> 1].y = v; else r[j >> 1].x = v;
+      }
+#pragma unroll
+      for (int p = 0; p < LDJ2; ++p) JP(c, i, p) = r[p];
+      if (aamax <= 0.0) zero = true;
+      tsm[c.vscr + i * CPB] = 1.0 / aamax;
+    }
+  }
+  if (zero) return 1;
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    const int ek = 2 * (c.jb + (k >> 1) * CPB) + (k & 1);       // element (0, k); row stride 2*LDJ2*CPB
+    double best = 0.0;
+    int imax = k;
+#pragma unroll 1
+    for (int i = k; i < N; ++i) {
+      const double dum = tsm[c.vscr + i * CPB] * fabs(tsm[ek + i * (2 * LDJ2 * CPB)]);
+      if (dum >= best) { best = dum; imax = i; }
+    }
+    // swap rows k and imax from the pair holding column k on (columns left of it are never read again)
+    double2 pr[LDJ2];
+    const int rk = c.jb + k * (LDJ2 * CPB), ri = c.jb + imax * (LDJ2 * CPB);
+    lane_lu_swap_from<N, CPB, 0>(c, k >> 1, rk, ri, pr);
+    tsm[c.vscr + imax * CPB] = tsm[c.vscr + k * CPB];
+    double piv = tsm[ek + k * (2 * LDJ2 * CPB)];
+    if (piv == 0.0) {
+      piv = tiny;
+      tsm[ek + k * (2 * LDJ2 * CPB)] = tiny;
+    }
+    const double dum = 1.0 / piv;
+    tsm[c.vscr + k * CPB] = dum;                               // vv(k) is dead: keep 1/a(k,k) for the back substitution
+    lane_lu_elim_from<N, CPB, 0>(c, (k + 1) >> 1, k, ek, dum, pr);
+  }
+  {
+    double x[N];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {                         // lubksb :511-520
+      double2 r[LDJ2];
+#pragma unroll
+      for (int p = ((i + 1) >> 1); p < LDJ2; ++p) r[p] = JP(c, i, p);
+      double sum = (N & 1) ? r[N >> 1].y : r[N >> 1].x;
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) sum = sum - ((j & 1) ? r[j >> 1].y : r[j >> 1].x) * x[j];
+      x[i] = sum * tsm[c.vscr + i * CPB];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) JE(c, i, N) = x[i];
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lane life cycle: load a cell -> trips (one Newton iteration each) -> finish (closing RTAuxVarCompute + write back)
+
+// RUpdateTempDependentCoefs reaction.F90:5433-5524 -> -logK*LOG_TO_LN of this cell's T (and P)
+template <int N, int CPB>
+LANE_COLD void lane_percell_logK(int ncoef, int logK_mode, int vlk, double temp, double pres, const double *blob_d, DSpec s0, DSpec s1,
+                                 DSpec s2) {
+  const double tk = temp + 273.15;
+  int o = 0;
+#pragma unroll 1
+  for (int l = 0; l < 3; ++l) {
+    const DSpec sp = l == 0 ? s0 : l == 1 ? s1 : s2;
+#pragma unroll 1
+    for (int r = 0; r < sp.n; ++r, ++o) {
+      double lk;
+      const bool fixed = sp.o_coef < 0 || (l == 2 && logK_mode == RXN_LOGK_HPT);   // :5517-5521: hpt not applied to srfcplx
+      if (fixed) lk = blob_d[sp.o_logK + r];
+      else {
+        const double *cf = blob_d + sp.o_coef + r * ncoef;
+        if (logK_mode == RXN_LOGK_HPT) {                      // reaction_aux.F90:1529-1571
+          const double tr = tk / 273.15, pr = pres / 1.0e7;
+          const double logtr = log(tr) / log(10.0);
+          lk = cf[0] + cf[1] * tr + cf[2] / tr + cf[3] * logtr + cf[4] * tr * tr + cf[5] / tr / tr + cf[6] * sqrt(tr) + cf[7] * pr +
+               cf[8] * pr * tr + cf[9] * pr / tr + cf[10] * pr * logtr + cf[11] / pr + cf[12] / pr * tr + cf[13] / pr / tr +
+               cf[14] * pr * pr + cf[15] * pr * pr * tr + cf[16] * pr * pr / tr;
+        } else {                                              // reaction_aux.F90:1461-1488
+          lk = cf[0] * log(tk) + cf[1] + cf[2] * tk + cf[3] / tk + cf[4] / (tk * tk);
+        }
+      }
+      tsm[vlk + o * CPB] = -lk * RXN_LOG_TO_LN;
+    }
+  }
+}
+
+template <int N, int CPB>
+LANE_DEV void lane_load(const LaneTab &lt, Lane<N> &c, const DevState &S, const double *blob_d, const int *blob_i, const DevTab &h,
+                        long long item, long long cell, const double *tran_xx, double tran_dt) {
+  const int n = lt.n;
+  c.item = item; c.cell = cell;
+  c.flags = 0; c.iter = 0;
+  c.ln_act_h2o = GSL(S, RXN_F_LN_ACT_H2O, 0, cell);
+  c.den_kg = GSL(S, RXN_F_DEN_KG, 0, cell);
+  c.temp = GSL(S, RXN_F_TEMP, 0, cell);
+  c.volume = GSL(S, RXN_F_VOLUME, 0, cell);
+  c.porosity = GSL(S, RXN_F_POROSITY, 0, cell);
+  c.soil_density = GSL(S, RXN_F_SOIL_PARTICLE_DENSITY, 0, cell);
+  const double sat = GSL(S, RXN_F_SAT, 0, cell);
+  c.psv = c.porosity * sat * 1000.0 * c.volume;
+  c.psvd = c.porosity * sat * 1000.0 * c.volume / tran_dt;                     // :5189
+  c.v_t = c.volume / tran_dt;                                                  // :4590
+  c.den_kg_per_L = c.den_kg * 1.0 * 1.0e-3;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (i < n) {
+      tsm[c.vm + i * CPB] = GSL(S, RXN_F_PRI_MOLAL, i, cell);
+      double fx = c.psv * tran_xx[item * n + i];                               // :3370, RTAccumulation :5072-5148
+      if (lt.neqsorb > 0) fx = fx + GSL(S, RXN_F_TOTAL_SORB_EQ, i, cell) * c.volume;   // RAccumulationSorb :4539-4568
+      c.fix[i] = fx;
+    } else {
+      // padding row of the shape: m = 1, no complexes -> total = den, residual = psv*den - fix = 0 exactly,
+      // Jln_ii = den*psvd: the row stays decoupled and its Newton update is 0
+      tsm[c.vm + i * CPB] = 1.0;
+      tsm[c.vtot + i * CPB] = 0.0;
+      c.fix[i] = c.psv * ((1.0 + 0.0) * c.den_kg_per_L);
+    }
+  }
+  tsm[c.vlna + n * CPB] = 0.0;
+  tsm[c.vlna + (n + 1) * CPB] = c.ln_act_h2o;
+  tsm[c.vsm + lt.ncplx * CPB] = 0.0;
+  if (lt.act_off) {                                            // ln gamma from the state, one class per species
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) tsm[c.vlng + i * CPB] = c_log(GSL(S, RXN_F_PRI_ACT_COEF, i, cell));
+#pragma unroll 1
+    for (int k = 0; k < lt.ncplx; ++k) tsm[c.vlng + (n + k) * CPB] = c_log(GSL(S, RXN_F_SEC_ACT_COEF, k, cell));
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < lt.ncplx; ++k) tsm[c.vsm + k * CPB] = GSL(S, RXN_F_SEC_MOLAL, k, cell);   // lagged, for I
+  }
+#pragma unroll 1
+  for (int q = 0; q < lt.nrxn; ++q) tsm[c.vfree + q * CPB] = GSL(S, RXN_F_FREE_SITE_CONC, q, cell);
+#pragma unroll 1
+  for (int q = 0; q < lt.nkin; ++q) {                          // read-only inside RReact
+    tsm[c.vmnrl + q * CPB] = GSL(S, RXN_F_MNRL_VOLFRAC, q, cell);
+    tsm[c.vmnrl + (lt.nkin + q) * CPB] = GSL(S, RXN_F_MNRL_AREA, q, cell);
+  }
+  if (lt.percell_logK)
+    lane_percell_logK<N, CPB>(lt.ncoef, lt.logK_mode, c.vlk, c.temp, GSL(S, RXN_F_PRES, 0, cell), blob_d, h.cplx, h.kin, h.srf);
+  // multirate_prepare (rxn_device.cuh; REASSOC): R0_i = sum_r k_r/(1+k_r dt) S_r,i
+#pragma unroll 1
+  for (int ikr = 0; ikr < lt.nmr; ++ikr) {
+    const int nrate = blob_i[h.o_mr_nrate + ikr];
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) tsm[c.vr0 + (ikr * N + i) * CPB] = 0.0;
+#pragma unroll 1
+    for (int irate = 0; irate < nrate; ++irate) {
+      const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
+      const double kdt = rate * tran_dt;
+      const double one_plus_kdt = 1.0 + kdt;
+      const double kk = rate / one_plus_kdt;
+      const long long row0 = ((long long)ikr * (h.mr_ld + 1) + (irate + 1)) * n;
+#pragma unroll 3
+      for (int i = 0; i < n; ++i) {
+        const int o = c.vr0 + (ikr * N + i) * CPB;
+        tsm[o] = tsm[o] + kk * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + i, cell);
+      }
+    }
+  }
+}
+
+// x / d with r = 1/d precomputed (one Newton correction: the quotient the division unit returns, bar double rounding)
+LANE_DEV double lane_div(double x, double d, double r) {
+#ifndef RXN_LANE_HOST
+  const double q = x * r;
+  return fma(fma(-d, q, x), r, q);
+#else
+  (void)r;
+  return x / d;
+#endif
+}
+
+// One trip of a lane through the Newton loop of RReact (reaction.F90:3411-3500): one iteration, or - when
+// `closing` - the shortened last pass that redoes RTotal for the closing RTAuxVarCompute (:3507) after an
+// abnormal exit changed pri_molal.  Returns 0 to continue, -1 after a closing pass, else the exit reason /
+// flag; `recompute` is set when the closing RTAuxVarCompute needs such a pass.
+template <int N, int CPB>
+LANE_DEV int lane_trip(const LaneTab &lt, Lane<N> &c, const DevState &S, double tran_dt, double inv_dt, int dt_mode, bool closing,
+                       bool &recompute) {
+  constexpr int LDJ2 = (N + 2) / 2;
+  const int n = lt.n;
+  const int bcol = 2 * (c.jb + (N >> 1) * CPB) + (N & 1), brow = 2 * LDJ2 * CPB;   // b_i = tsm[bcol + i*brow]
+  recompute = false;
+  if (!closing) {
+    c.iter = c.iter + 1;
+    // :3407-3409 (once, before the loop) and :3413-3418 (every iteration): the call before the loop and
+    // the call of iteration 1 see identical inputs, so one evaluation serves both
+    if (!lt.act_off && (c.iter == 1 || lt.act_newton_iter)) lane_act_coefs<N, CPB>(lt, c);
+  }
+  // RTAuxVarCompute :3419 -> RTotal + RTotalSorb
+  lane_speciate<N, CPB>(lt, c);
+  lane_plan<N, CPB, false>(lt, c, 0.0);
+  if (closing) {
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) tsm[c.vtot + i * CPB] = (tsm[c.vm + i * CPB] + tsm[c.vtot + i * CPB]) * c.den_kg_per_L;
+    return -1;
+  }
+  {
+    double2 z; z.x = 0.0; z.y = 0.0;
+#pragma unroll 8
+    for (int e = 0; e < N * LDJ2; ++e) TSM2[c.jb + e * CPB] = z;
+  }
+  const double dp = c.den_kg_per_L * c.psvd;                   // dtotal * psvd_t  (:3429-3437; RTAccumulationDerivative :5189-5204)
+  lane_plan<N, CPB, true>(lt, c, dp);
+#pragma unroll
+  for (int i = 0; i < N; ++i) JE(c, i, i) = fma(tsm[c.vm + i * CPB], dp, JE(c, i, i));   // REASSOC: (1 + D_ii/m_i) m_i
+  // sorption: equilibrium reactions (RTotalSorb :4182-4216, sorbed totals -> b) and the equilibrium part of the
+  // multirate reactions (RMultiRateSorption reaction_surf_complex.F90:566-654, S_eq -> its own vector), one call site.
+  // REASSOC: the multirate derivative block enters J before the mineral block.
+#pragma unroll 1
+  for (int task = 0; task < lt.neq + lt.nmr; ++task) {
+    const bool eq = task < lt.neq;
+    const int ikr = task - lt.neq;
+    int tb = bcol, ts = brow;
+    double fac = c.v_t;
+    if (!eq) {
+      tb = c.vseq + ikr * N * CPB; ts = CPB;
+      fac = c.volume * lt.mrK1[ikr];
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) tsm[tb + i * ts] = 0.0;
+    }
+    lane_srf_rxn<N, CPB>(lt, c, S, TI(lt, (eq ? lt.i_eq_rxn : lt.i_mr_rxn - lt.neq) + task), fac, true, false, tb, ts);
+  }
+  const bool consistent = dt_mode == RXN_DT_CONSISTENT;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double tot = (tsm[c.vm + i * CPB] + tsm[c.vtot + i * CPB]) * c.den_kg_per_L;   // :4095,4124,4148
+    tsm[c.vtot + i * CPB] = tot;
+    double res = c.psv * tot;
+    res = res - c.fix[i];                                      // :3424-3426
+    if (lt.neqsorb > 0) res = res + JE(c, i, N) * c.volume;
+    if (consistent) res = lane_div(res, tran_dt, inv_dt);
+    JE(c, i, N) = res;
+  }
+  // RReaction :3440 (minerals, then multirate)
+  if (lt.nkin > 0) lane_kinetic_mineral<N, CPB>(lt, c);
+#pragma unroll 1
+  for (int ikr = 0; ikr < lt.nmr; ++ikr) {
+#pragma unroll 1
+    for (int i = 0; i < n; ++i)
+      tsm[bcol + i * brow] += c.volume * (lt.mrK1[ikr] * tsm[c.vseq + (ikr * N + i) * CPB] - tsm[c.vr0 + (ikr * N + i) * CPB]);
+  }
+  double mx = 0.0;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double v = JE(c, i, N);
+    mx = fmax(mx, fabs(v));
+    if (!isfinite(v)) bad = true;
+  }
+  if (bad) { recompute = true; return RXN_FLAG_NONFINITE; }
+  if (mx < lt.res_tol) return RXN_EXIT_RESIDUAL;               // :3443
+  if (lane_rsolve<N, CPB>(lt, c)) { recompute = true; return RXN_FLAG_LU_ZERO_ROW; }
+  double maxrel = 0.0, min_ratio = 1.0e20;
+  if (!lt.use_log) {                                           // :3459-3471
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const double prev = tsm[c.vm + i * CPB], u = tsm[bcol + i * brow];
+      if (prev <= u) {
+        const double ratio = fabs(prev / u);
+        if (ratio < min_ratio) min_ratio = ratio;
+      }
+    }
+  }
+  // the new solution is staged in b: it is discarded when the relative change has converged (:3476)
+#pragma unroll 3
+  for (int i = 0; i < n; ++i) {
+    double u = tsm[bcol + i * brow];
+    const double prev = tsm[c.vm + i * CPB];
+    double nw;
+    if (lt.use_log) {                                          // :3454-3458
+      u = copysign(1.0, u) * fmin(fabs(u), lt.max_dlnC);
+      nw = prev * exp(-u);
+    } else {
+      if (min_ratio < 1.0) u = u * min_ratio * 0.99;
+      nw = prev - u;
+    }
+    const double rc = fabs((nw - prev) / prev);
+    if (!isfinite(rc)) bad = true;
+    maxrel = fmax(maxrel, rc);
+    if (c.iter > 50) nw = 0.1 * (nw - prev) + prev;            // :3478-3496
+    tsm[bcol + i * brow] = nw;
+  }
+  if (bad) { recompute = true; return RXN_FLAG_NONFINITE; }
+  if (maxrel < lt.rel_tol) return RXN_EXIT_REL_CHANGE;         // :3476 (update discarded)
+#pragma unroll 5
+  for (int i = 0; i < n; ++i) tsm[c.vm + i * CPB] = tsm[bcol + i * brow];   // :3498
+  if (c.iter >= lt.maxit) { recompute = true; return RXN_FLAG_CAPPED; }   // GPU-only guard (reference spins)
+  return 0;
+}
+
+// closing RTAuxVarCompute (:3507) + write back (store_cell of the thread-per-cell path + reactive_transport.F90:1711).
+// After a normal exit pri_molal and the activity coefficients are those of the last RTotal, so sec_molal and
+// total are already final; only RTotalSorb sees a different input (the warm-start free-site concentration).
+template <int N, int CPB>
+LANE_DEV void lane_finish(const LaneTab &lt, Lane<N> &c, const DevState &S, const DevTab &h, double *tran_xx, int32_t *iters,
+                          int32_t *flags, int status) {
+  constexpr int LDJ2 = (N + 2) / 2;
+  const int n = lt.n;
+  const long long cell = c.cell;
+  const int bcol = 2 * (c.jb + (N >> 1) * CPB) + (N & 1), brow = 2 * LDJ2 * CPB;
+  if (lt.neqsorb > 0) {
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) tsm[bcol + i * brow] = 0.0;
+    if (lt.neq > 0) {                                          // RZeroSorb :4162-4178
+#pragma unroll 1
+      for (int k = 0; k < lt.nsrf; ++k) GSL(S, RXN_F_EQSRFCPLX_CONC, k, cell) = 0.0;
+    }
+#pragma unroll 1
+    for (int ieq = 0; ieq < lt.neq; ++ieq) lane_srf_rxn<N, CPB>(lt, c, S, TI(lt, lt.i_eq_rxn + ieq), 0.0, false, true, bcol, brow);
+  }
+#pragma unroll 3
+  for (int i = 0; i < n; ++i) {
+    const double mm = tsm[c.vm + i * CPB];
+    tran_xx[c.item * n + i] = mm;
+    GSL(S, RXN_F_PRI_MOLAL, i, cell) = mm;
+    GSL(S, RXN_F_TOTAL, i, cell) = tsm[c.vtot + i * CPB];
+    if (lt.neqsorb > 0) GSL(S, RXN_F_TOTAL_SORB_EQ, i, cell) = tsm[bcol + i * brow];
+  }
+#pragma unroll 1
+  for (int ikr = 0; ikr < lt.nmr; ++ikr)
+#pragma unroll 1
+    for (int i = 0; i < n; ++i)
+      GSL(S, RXN_F_KINMR_TOTAL_SORB, (long long)ikr * (h.mr_ld + 1) * n + i, cell) = tsm[c.vseq + (ikr * N + i) * CPB];
+  if (!lt.act_off) {
+#pragma unroll 3
+    for (int q = 0; q < lt.ncls; ++q) tsm[c.vlng + q * CPB] = exp(tsm[c.vlng + q * CPB]);   // gamma per class
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) GSL(S, RXN_F_PRI_ACT_COEF, i, cell) = tsm[c.vlng + TI(lt, lt.i_pcls + i) * CPB];
+#pragma unroll 4
+    for (int k = 0; k < lt.ncplx; ++k) GSL(S, RXN_F_SEC_ACT_COEF, k, cell) = tsm[c.vlng + TI(lt, lt.i_ccls + k) * CPB];
+  }
+#pragma unroll 4
+  for (int k = 0; k < lt.ncplx; ++k) GSL(S, RXN_F_SEC_MOLAL, k, cell) = tsm[c.vsm + k * CPB];
+#pragma unroll 1
+  for (int q = 0; q < lt.nrxn; ++q) GSL(S, RXN_F_FREE_SITE_CONC, q, cell) = tsm[c.vfree + q * CPB];
+#pragma unroll 1
+  for (int q = 0; q < lt.nkin; ++q) GSL(S, RXN_F_MNRL_RATE, q, cell) = tsm[c.vmnrl + (2 * lt.nkin + q) * CPB];
+  GSL(S, RXN_F_LN_ACT_H2O, 0, cell) = c.ln_act_h2o;
+  if (iters) iters[c.item] = c.iter;
+  if (flags) flags[c.item] = status | c.flags;
+}
+
+}  // namespace lane
+}  // namespace rxn

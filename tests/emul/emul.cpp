@@ -14,6 +14,10 @@
 using std::isfinite;
 #include "../../pflotran_b200/csrc/rxn_pack.h"
 #include "../../pflotran_b200/csrc/rxn_device.cuh"
+#undef RXN_LOG_TO_LN
+#undef RXN_IDEAL_GAS_CONSTANT
+#define RXN_LANE_HOST 1
+#include "../../pflotran_b200/csrc/rxn_lane_dev.cuh"
 
 using namespace rxn;
 
@@ -40,6 +44,53 @@ static DevState mk_state(const HostView *v, const uint8_t *active) {
     case 16: { constexpr int N = 16; CALL; } break; \
     default: { constexpr int N = 24; CALL; } break; \
   }
+
+// resident-lane RReact kernel (rxn_lane_dev.cuh) with one lane: plan built for CPB = 1, the per-lane routines
+// driven cell by cell exactly as the persistent CUDA lanes drive them (load -> trips -> closing pass -> finish)
+template <int N>
+static void lane_cells(const LanePlan &P, const Emu *e, DevState &S, double *tran_xx, const int32_t *l2g, int64_t nlocal, double dt,
+                       int dt_mode, int32_t *iters, int32_t *flags) {
+  using namespace rxn::lane;
+  LaneTab lt = P.lt;
+  const DevTab &h = e->R.h;
+  for (int ikr = 0; ikr < lt.nmr && ikr < 2; ++ikr) {
+    double K1 = 0.0;
+    for (int irate = 0; irate < e->T.i[h.o_mr_nrate + ikr]; ++irate) {
+      const double rate = e->T.d[h.o_mr_rate + ikr * h.mr_ld + irate], frac = e->T.d[h.o_mr_frac + ikr * h.mr_ld + irate];
+      const double kdt = rate * dt;
+      const double one_plus_kdt = 1.0 + kdt;
+      const double kk = rate / one_plus_kdt;
+      K1 = K1 + kk * frac;
+    }
+    lt.mrK1[ikr] = K1;
+  }
+  std::vector<double> sm((size_t)lt.smem_dbl + 16, 0.0);
+  memcpy(sm.data(), P.blob.data(), P.blob.size());
+  tsm = sm.data();
+  const double inv_dt = 1.0 / dt;
+  for (long long i = 0; i < nlocal; ++i) {
+    const long long cell = l2g ? l2g[i] : i;
+    if (S.active && !S.active[cell]) {
+      if (iters) iters[i] = 0;
+      if (flags) flags[i] = RXN_FLAG_INACTIVE;
+      continue;
+    }
+    Lane<N> c;
+    lane_bind<N, 1>(lt, c, 0);
+    lane_load<N, 1>(lt, c, S, e->T.d, e->T.i, h, i, cell, tran_xx, dt);
+    int pending = 0;
+    for (;;) {
+      bool recompute;
+      const int st = lane_trip<N, 1>(lt, c, S, dt, inv_dt, dt_mode, pending != 0, recompute);
+      if (pending != 0) { lane_finish<N, 1>(lt, c, S, h, tran_xx, iters, flags, pending); break; }
+      if (st != 0) {
+        if (recompute) pending = st;
+        else { lane_finish<N, 1>(lt, c, S, h, tran_xx, iters, flags, st); break; }
+      }
+    }
+  }
+  tsm = nullptr;
+}
 
 extern "C" {
 
@@ -75,6 +126,31 @@ int emu_react_batch(void *h, const HostView *v, double *tran_xx, const uint8_t *
   for (long long i = 0; i < nlocal; ++i) EMU_DISPATCH(e->nv, cell_react<N>(e->T, S, i, tran_xx, l2g, dt, dt_mode, iters, flags));
   return 0;
 }
+int emu_react_lane(void *hh, const HostView *v, double *tran_xx, const uint8_t *active, const int32_t *l2g, int64_t nlocal, double dt,
+                   int dt_mode, int32_t *iters, int32_t *flags, char *err, int errlen, int32_t *stats) {
+  Emu *e = (Emu *)hh;
+  DevState S = mk_state(v, active);
+  LanePlan P;
+  const int N = lane_N_for(e->R.h.naq);
+  if (N == 0) { if (err) snprintf(err, errlen, "naq exceeds the compiled shapes"); return RXN_ERR_UNSUPPORTED; }
+  int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P);
+  if (rc != RXN_OK || !P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
+  if (stats) {
+    stats[0] = P.lt.N; stats[1] = (int)P.blob.size(); stats[2] = (int)(P.smem_bytes - (size_t)P.lt.o_J2 * 16);
+    stats[3] = P.terms_spec; stats[4] = P.steps_spec; stats[5] = P.terms_A; stats[6] = P.steps_A; stats[7] = P.terms_B; stats[8] = P.steps_B;
+    stats[9] = P.lt.ncls;
+  }
+  switch (N) {
+    case 4: lane_cells<4>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
+    case 8: lane_cells<8>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
+    case 12: lane_cells<12>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
+    case 15: lane_cells<15>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
+    case 16: lane_cells<16>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
+    default: lane_cells<24>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
+  }
+  return 0;
+}
+
 int emu_update_auxvars_batch(void *h, const HostView *v, const double *xx_loc, const uint8_t *active, int update_act_coefs) {
   Emu *e = (Emu *)h;
   DevState S = mk_state(v, active);

@@ -19,7 +19,7 @@ _LIB = None
 def build(force=False):
     so = os.path.join(_HERE, 'libemul.so')
     deps = [os.path.join(_HERE, 'emul.cpp')] + [os.path.join(_ROOT, 'pflotran_b200', 'csrc', f)
-                                                 for f in ('rxn_device.cuh', 'rxn_pack.h', 'rxn_tab.h')] + \
+                                                 for f in ('rxn_device.cuh', 'rxn_pack.h', 'rxn_tab.h', 'rxn_lane.h', 'rxn_lane_dev.cuh')] + \
         [os.path.join(_ROOT, 'include', 'rxn_b200.h')]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off',
@@ -78,6 +78,25 @@ class Emulator:
                                    _p(l2g, C.c_int32), C.c_int64(n), C.c_double(dt), C.c_int(dt_mode),
                                    _p(iters, C.c_int32), _p(flags, C.c_int32))
         assert rc == 0
+        return iters, flags
+
+    def react_lane(self, st, tran_xx, dt, dt_mode=abi.RXN_DT_CONSISTENT, l2g=None, maxit=None):
+        """RReact through the resident-lane kernel's per-lane routines (rxn_lane_dev.cuh), one lane."""
+        if maxit is not None:
+            lib().emu_set_maxit(self.h, maxit)
+        n = tran_xx.shape[0]
+        iters = np.zeros(n, dtype=np.int32)
+        flags = np.zeros(n, dtype=np.int32)
+        v = st.view()
+        buf = C.create_string_buffer(512)
+        stats = np.zeros(16, dtype=np.int32)
+        rc = lib().emu_react_lane(self.h, C.byref(v), _p(tran_xx, C.c_double), _p(st.active, C.c_uint8),
+                                  _p(l2g, C.c_int32), C.c_int64(n), C.c_double(dt), C.c_int(dt_mode),
+                                  _p(iters, C.c_int32), _p(flags, C.c_int32), buf, 512, _p(stats, C.c_int32))
+        if rc != 0:
+            raise NotImplementedError(buf.value.decode())
+        self.lane_stats = dict(zip(['N', 'blob_bytes', 'cell_bytes', 'terms_spec', 'steps_spec', 'terms_A', 'steps_A',
+                                    'terms_B', 'steps_B', 'ncls'], stats.tolist()))
         return iters, flags
 
     def update_auxvars(self, st, xx_loc, update_act_coefs):

@@ -30,6 +30,52 @@ def test_react(name, dt, mode):
     assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name)
 
 
+LANE_WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'surface_complexation', 'calcite_kinetics']
+
+
+@pytest.mark.parametrize('name', LANE_WORKLOADS)
+@pytest.mark.parametrize('dt,mode', [(3600.0, abi.RXN_DT_CONSISTENT), (1.0, abi.RXN_DT_AS_WRITTEN)])
+def test_react_resident_lane(name, dt, mode):
+    """Per-lane routines of the resident-lane kernel (rxn_lane_dev.cuh: term streams, ln-m Jacobian, LU in the
+    lane-strided layout, closing pass), driven cell by cell on the host, against the oracle."""
+    w, cells = workload_cells(name, 600)
+    st_o = synth.host_state(w, cells)
+    st_e = st_o.copy()
+    xo = cells['tran_xx'].copy()
+    xe = xo.copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, dt, mode, maxit=10000)
+    it_e, fl_e = Emulator(w.tables).react_lane(st_e, xe, dt, mode)
+    assert (it_o == it_e).all() and (fl_o == fl_e).all()
+    ok = (fl_o & ~3) == 0
+    assert rel_err(xe[ok], xo[ok]).max() <= RTOL
+    assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
+
+
+def test_resident_lane_iteration_cap_and_inactive():
+    """Abnormal exit (iteration cap): pri_molal moved after the last RTotal, so the closing pass must redo it."""
+    w, cells = workload_cells('hanford300a_eq', 200)
+    st_o = synth.host_state(w, cells)
+    st_o.active[::7] = 0
+    st_e = st_o.copy()
+    xo = cells['tran_xx'].copy()
+    xe = xo.copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=3)
+    it_e, fl_e = Emulator(w.tables).react_lane(st_e, xe, 3600.0, abi.RXN_DT_CONSISTENT, maxit=3)
+    assert (fl_e & abi.RXN_FLAG_CAPPED).any() and (fl_e[::7] == abi.RXN_FLAG_INACTIVE).all()
+    assert (it_o == it_e).all() and (fl_o == fl_e).all()
+    act = np.where(st_o.active != 0)[0]
+    assert rel_err(xe[act], xo[act]).max() <= RTOL
+    assert_state_close(st_e, st_o, cells=act, what='capped', tables=w.tables)
+
+
+def test_resident_lane_rejects_what_it_does_not_cover():
+    for name in ['ion_exchange', 'kd_wo_mineral']:
+        w, cells = workload_cells(name, 8)
+        st = synth.host_state(w, cells)
+        with pytest.raises(NotImplementedError):
+            Emulator(w.tables).react_lane(st, cells['tran_xx'].copy(), 3600.0)
+
+
 @pytest.mark.parametrize('name', ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'])
 def test_global_implicit_entry_points(name):
     w, cells = workload_cells(name, 300)

@@ -23,7 +23,7 @@ def _gpu_state(w, st):
 
 @pytest.mark.parametrize('name', WORKLOADS)
 @pytest.mark.parametrize('dt,mode', [(3600.0, abi.RXN_DT_CONSISTENT), (1.0, abi.RXN_DT_AS_WRITTEN)])
-@pytest.mark.parametrize('kernel', [1, 2])
+@pytest.mark.parametrize('kernel', [1, 2, 3])
 def test_react(name, dt, mode, kernel):
     n = 5000
     w, cells = workload_cells(name, n)
@@ -36,8 +36,8 @@ def test_react(name, dt, mode, kernel):
         xg = xo.copy()
         it_g, fl_g = rz.RTReact(xg, dt, mode)
     except rt.RxnError as e:
-        if kernel == 2 and e.status == abi.RXN_ERR_UNSUPPORTED:
-            pytest.skip('cooperative kernel not available for these tables: %s' % e)
+        if kernel in (2, 3) and e.status == abi.RXN_ERR_UNSUPPORTED:
+            pytest.skip('shared-memory kernel not available for these tables: %s' % e)
         raise
     it_o, fl_o = Oracle(w.tables).react(st_o, xo, dt, mode, maxit=10000, nthreads=8)
     rz.download_host_state(st_g)
