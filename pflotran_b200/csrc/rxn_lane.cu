@@ -6,10 +6,10 @@
 
 namespace rxn {
 
-#define RXN_LANE_DECL(n, cpb)                                                                                                 \
-  template <> int lane_launch_variant<n, cpb>(const LaneTab &, size_t, int, const DevTab &, const double *, const double *,    \
-                                              const DevState &, double *, const int32_t *, long long, double, int, int32_t *, \
-                                              int32_t *, unsigned long long *, cudaStream_t);
+#define RXN_LANE_DECL(n, cpb, g)                                                                                                 \
+  template <> int lane_launch_variant<n, cpb, g>(const LaneTab &, size_t, int, const DevTab &, const double *, const double *,    \
+                                                 const DevState &, double *, const int32_t *, long long, double, int, int32_t *, \
+                                                 int32_t *, unsigned long long *, cudaStream_t);
 RXN_LANE_SHAPES(RXN_LANE_DECL)
 #undef RXN_LANE_DECL
 
@@ -21,18 +21,21 @@ int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std:
   k->sm_count = prop.multiProcessorCount;
   const int N = lane_N_for(h.naq);
   if (N == 0) { p.err = "naq exceeds the compiled shapes"; return RXN_OK; }
-  int force_cpb = 0;
+  int force_cpb = 0, force_g = 0;
   if (const char *e = getenv("RXN_LANE_CPB")) force_cpb = atoi(e);
+  if (const char *e = getenv("RXN_LANE_G")) force_g = atoi(e);
   static const LaneShape shapes[] = {
-#define RXN_LANE_ROW(n, cpb) {n, cpb},
+#define RXN_LANE_ROW(n, cpb, g) {n, cpb, g},
       RXN_LANE_SHAPES(RXN_LANE_ROW)
 #undef RXN_LANE_ROW
   };
   for (const LaneShape &s : shapes) {
     if (s.N != N) continue;
     if (force_cpb && s.CPB != force_cpb) continue;
+    if (force_g && s.G != force_g) continue;
     int rc = lane_plan_build(h, bd, bi, s.N, s.CPB, prop.sharedMemPerBlockOptin, &p);
     if (rc != RXN_OK) return rc;
+    k->G = s.G;
     if (p.usable) break;
     if (p.err.find("does not fit") == std::string::npos) break;     // chemistry, not shape, is the obstacle
   }
@@ -48,8 +51,8 @@ int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std:
   k->mr_rate.assign(bd.begin() + h.o_mr_rate, bd.begin() + h.o_mr_rate + (size_t)h.nmr * h.mr_ld);
   k->mr_frac.assign(bd.begin() + h.o_mr_frac, bd.begin() + h.o_mr_frac + (size_t)h.nmr * h.mr_ld);
   if (getenv("RXN_LANE_VERBOSE"))
-    fprintf(stderr, "[rxn lane] N=%d CPB=%d smem=%zu B blob=%zu B classes=%d spec %d terms/%d steps, planA %d/%d, planB %d/%d\n",
-            p.lt.N, p.lt.CPB, p.smem_bytes, p.blob.size(), p.lt.ncls, p.terms_spec, p.steps_spec, p.terms_A, p.steps_A, p.terms_B,
+    fprintf(stderr, "[rxn lane] N=%d CPB=%d G=%d smem=%zu B blob=%zu B classes=%d spec %d terms/%d steps, planA %d/%d, planB %d/%d\n",
+            p.lt.N, p.lt.CPB, k->G, p.smem_bytes, p.blob.size(), p.lt.ncls, p.terms_spec, p.steps_spec, p.terms_A, p.steps_A, p.terms_B,
             p.steps_B);
   return RXN_OK;
 }
@@ -77,9 +80,9 @@ int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const 
     lt.mrK1[ikr] = K1;
   }
   if (cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXN_ERR_CUDA;
-#define RXN_LANE_CASE(n, cpb)                                                                                                    \
-  if (lt.N == n && lt.CPB == cpb)                                                                                                \
-    return lane_launch_variant<n, cpb>(lt, k.plan.smem_bytes, k.sm_count, h, k.d_blob, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, \
+#define RXN_LANE_CASE(n, cpb, g)                                                                                                 \
+  if (lt.N == n && lt.CPB == cpb && k.G == g)                                                                                    \
+    return lane_launch_variant<n, cpb, g>(lt, k.plan.smem_bytes, k.sm_count, h, k.d_blob, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, \
                                        iters, flags, counter, stream);
   RXN_LANE_SHAPES(RXN_LANE_CASE)
 #undef RXN_LANE_CASE

@@ -7,14 +7,19 @@
 
 namespace rxn {
 
-// shapes compiled into the library: X(N, CPB), per N in descending CPB order (keep in sync with the Makefile)
-#define RXN_LANE_SHAPES(X)                                                                                       \
-  X(4, 512) X(4, 256) X(4, 128) X(4, 64) X(8, 192) X(8, 128) X(8, 64) X(12, 96) X(12, 64) X(12, 32)             \
-  X(15, 64) X(15, 60) X(15, 56) X(15, 48) X(15, 32) X(16, 64) X(16, 56) X(16, 48) X(16, 32)                     \
-  X(24, 32) X(24, 28) X(24, 24) X(24, 16)
+// shapes compiled into the library: X(N, CPB, G) = matrix dimension, resident cells per CTA, lanes per cell;
+// per N in order of preference (keep in sync with LANE_SHAPES in the Makefile)
+#define RXN_LANE_SHAPES(X)                                                                                         \
+  X(4, 512, 1) X(4, 448, 1) X(4, 384, 1) X(4, 256, 1) X(4, 128, 1)                                                                           \
+  X(8, 192, 1) X(8, 128, 1) X(8, 64, 1) X(8, 128, 2)                                                               \
+  X(12, 64, 4) X(12, 96, 2) X(12, 96, 1) X(12, 64, 1)                                                              \
+  X(15, 64, 4) X(15, 60, 4) X(15, 56, 4) X(15, 48, 4) X(15, 64, 2) X(15, 60, 2) X(15, 64, 1) X(15, 60, 1)          \
+  X(16, 64, 4) X(16, 56, 4) X(16, 48, 4) X(16, 64, 1)                                                              \
+  X(24, 32, 4) X(24, 28, 4) X(24, 24, 4) X(24, 16, 4) X(24, 28, 1)
 
 struct LaneKernel {
   LanePlan plan;
+  int G = 1;             // lanes per cell of the selected shape
   double *d_blob = nullptr;
   int sm_count = 0;
   std::vector<double> mr_rate, mr_frac;   // host copies for the per-launch K1 sums
@@ -22,7 +27,7 @@ struct LaneKernel {
   int mr_ld = 0;
 };
 
-template <int N, int CPB>
+template <int N, int CPB, int G>
 int lane_launch_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
                         const DevState &S, double *tran_xx, const int32_t *l2g, long long nlocal, double dt, int dt_mode,
                         int32_t *iters, int32_t *flags, unsigned long long *counter, cudaStream_t stream);

@@ -81,7 +81,7 @@ struct LanePlan {
 };
 
 // supported (N, CPB) shapes, largest CPB first per N (instantiated in rxn_lane_variant.cu)
-struct LaneShape { int N, CPB; };
+struct LaneShape { int N, CPB, G; };
 
 inline int lane_N_for(int naq) {
   const int cand[] = {4, 8, 12, 15, 16, 24};
@@ -232,9 +232,17 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
     std::vector<const Entry *> wide, quad;
     for (auto &e : E) (allow_wide && e.terms.size() >= 8 ? wide : quad).push_back(&e);
     std::stable_sort(quad.begin(), quad.end(), [](const Entry *a, const Entry *b) { return a->terms.size() > b->terms.size(); });
-    for (auto *e : wide) emit_group(B, LANE_WIDE, {e}, ndest);
-    for (size_t g = 0; g < quad.size(); g += 4)
-      emit_group(B, LANE_QUAD, std::vector<const Entry *>(quad.begin() + g, quad.begin() + std::min(g + 4, quad.size())), ndest);
+    // groups in descending step count: the lanes of a cell take consecutive groups, so their loop trip counts stay close
+    struct Grp { int mode, nsteps; std::vector<const Entry *> mem; };
+    std::vector<Grp> groups;
+    for (auto *e : wide) groups.push_back(Grp{LANE_WIDE, ((int)e->terms.size() + 3) / 4, {e}});
+    for (size_t g = 0; g < quad.size(); g += 4) {
+      Grp q{LANE_QUAD, 0, std::vector<const Entry *>(quad.begin() + g, quad.begin() + std::min(g + 4, quad.size()))};
+      for (auto *e : q.mem) q.nsteps = std::max(q.nsteps, (int)e->terms.size());
+      groups.push_back(q);
+    }
+    std::stable_sort(groups.begin(), groups.end(), [](const Grp &a, const Grp &b) { return a.nsteps > b.nsteps; });
+    for (auto &g : groups) emit_group(B, g.mode, g.mem, ndest);
     S.ng = B.ng;
   };
 

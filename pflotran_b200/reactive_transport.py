@@ -20,7 +20,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librxn_b200.so')
+# RXN_B200_LIB: an alternative build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get('RXN_B200_LIB') or os.path.join(_HERE, 'librxn_b200.so')
 _LIB = None
 
 c_i64 = C.c_int64

@@ -11,6 +11,7 @@
 #define __host__
 #define __forceinline__ inline
 #include <cmath>
+#include <thread>
 using std::isfinite;
 #include "../../pflotran_b200/csrc/rxn_pack.h"
 #include "../../pflotran_b200/csrc/rxn_device.cuh"
@@ -45,19 +46,54 @@ static DevState mk_state(const HostView *v, const uint8_t *active) {
     default: { constexpr int N = 24; CALL; } break; \
   }
 
-// resident-lane RReact kernel (rxn_lane_dev.cuh) with one lane: plan built for CPB = 1, the per-lane routines
-// driven cell by cell exactly as the persistent CUDA lanes drive them (load -> trips -> closing pass -> finish)
-template <int N>
-static void lane_cells(const LanePlan &P, const Emu *e, DevState &S, double *tran_xx, const int32_t *l2g, int64_t nlocal, double dt,
-                       int dt_mode, int32_t *iters, int32_t *flags) {
+// resident-lane RReact kernel (rxn_lane_dev.cuh): plan built for one resident cell (CPB = 1); the G lanes of the
+// cell's group are G host threads that run the per-lane routines exactly as the persistent CUDA lanes do
+// (load -> trips -> closing pass -> finish), meeting at a barrier where the device has __syncwarp / shuffles.
+struct LaneJob {
+  const LanePlan *P; const Emu *e; DevState *S; double *tran_xx; const int32_t *l2g; int64_t nlocal; double dt; int dt_mode;
+  int32_t *iters, *flags;
+};
+template <int N, int G>
+static void lane_thread(const LaneJob *J, LaneTab lt, int l) {
   using namespace rxn::lane;
-  LaneTab lt = P.lt;
-  const DevTab &h = e->R.h;
+  g_hl = l;
+  const DevTab &h = J->e->R.h;
+  const DevState &S = *J->S;
+  const double inv_dt = 1.0 / J->dt;
+  for (long long i = 0; i < J->nlocal; ++i) {
+    const long long cell = J->l2g ? J->l2g[i] : i;
+    if (S.active && !S.active[cell]) {
+      if (l == 0) {
+        if (J->iters) J->iters[i] = 0;
+        if (J->flags) J->flags[i] = RXN_FLAG_INACTIVE;
+      }
+      continue;
+    }
+    Lane<N, G> c;
+    lane_bind<N, 1, G>(lt, c, 0, l, 0u);
+    lane_load<N, 1, G>(lt, c, S, J->e->T.d, J->e->T.i, h, i, cell, J->tran_xx, J->dt);
+    int pending = 0;
+    for (;;) {
+      bool recompute;
+      const int st = lane_trip<N, 1, G>(lt, c, S, J->dt, inv_dt, J->dt_mode, pending != 0, recompute);
+      if (pending != 0) { lane_finish<N, 1, G>(lt, c, S, h, J->tran_xx, J->iters, J->flags, pending); break; }
+      if (st != 0) {
+        if (recompute) pending = st;
+        else { lane_finish<N, 1, G>(lt, c, S, h, J->tran_xx, J->iters, J->flags, st); break; }
+      }
+    }
+  }
+}
+template <int N, int G>
+static void lane_cells(const LaneJob &J) {
+  using namespace rxn::lane;
+  LaneTab lt = J.P->lt;
+  const DevTab &h = J.e->R.h;
   for (int ikr = 0; ikr < lt.nmr && ikr < 2; ++ikr) {
     double K1 = 0.0;
-    for (int irate = 0; irate < e->T.i[h.o_mr_nrate + ikr]; ++irate) {
-      const double rate = e->T.d[h.o_mr_rate + ikr * h.mr_ld + irate], frac = e->T.d[h.o_mr_frac + ikr * h.mr_ld + irate];
-      const double kdt = rate * dt;
+    for (int irate = 0; irate < J.e->T.i[h.o_mr_nrate + ikr]; ++irate) {
+      const double rate = J.e->T.d[h.o_mr_rate + ikr * h.mr_ld + irate], frac = J.e->T.d[h.o_mr_frac + ikr * h.mr_ld + irate];
+      const double kdt = rate * J.dt;
       const double one_plus_kdt = 1.0 + kdt;
       const double kk = rate / one_plus_kdt;
       K1 = K1 + kk * frac;
@@ -65,31 +101,24 @@ static void lane_cells(const LanePlan &P, const Emu *e, DevState &S, double *tra
     lt.mrK1[ikr] = K1;
   }
   std::vector<double> sm((size_t)lt.smem_dbl + 16, 0.0);
-  memcpy(sm.data(), P.blob.data(), P.blob.size());
+  memcpy(sm.data(), J.P->blob.data(), J.P->blob.size());
   tsm = sm.data();
-  const double inv_dt = 1.0 / dt;
-  for (long long i = 0; i < nlocal; ++i) {
-    const long long cell = l2g ? l2g[i] : i;
-    if (S.active && !S.active[cell]) {
-      if (iters) iters[i] = 0;
-      if (flags) flags[i] = RXN_FLAG_INACTIVE;
-      continue;
-    }
-    Lane<N> c;
-    lane_bind<N, 1>(lt, c, 0);
-    lane_load<N, 1>(lt, c, S, e->T.d, e->T.i, h, i, cell, tran_xx, dt);
-    int pending = 0;
-    for (;;) {
-      bool recompute;
-      const int st = lane_trip<N, 1>(lt, c, S, dt, inv_dt, dt_mode, pending != 0, recompute);
-      if (pending != 0) { lane_finish<N, 1>(lt, c, S, h, tran_xx, iters, flags, pending); break; }
-      if (st != 0) {
-        if (recompute) pending = st;
-        else { lane_finish<N, 1>(lt, c, S, h, tran_xx, iters, flags, st); break; }
-      }
-    }
-  }
+  HostGroup hg;
+  pthread_barrier_init(&hg.bar, nullptr, G);
+  g_hg = &hg;
+  std::vector<std::thread> th;
+  for (int l = 1; l < G; ++l) th.emplace_back(lane_thread<N, G>, &J, lt, l);
+  lane_thread<N, G>(&J, lt, 0);
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&hg.bar);
+  g_hg = nullptr;
   tsm = nullptr;
+}
+template <int N>
+static void lane_cells_g(const LaneJob &J, int G) {
+  if (G == 1) lane_cells<N, 1>(J);
+  else if (G == 2) lane_cells<N, 2>(J);
+  else lane_cells<N, 4>(J);
 }
 
 extern "C" {
@@ -127,12 +156,13 @@ int emu_react_batch(void *h, const HostView *v, double *tran_xx, const uint8_t *
   return 0;
 }
 int emu_react_lane(void *hh, const HostView *v, double *tran_xx, const uint8_t *active, const int32_t *l2g, int64_t nlocal, double dt,
-                   int dt_mode, int32_t *iters, int32_t *flags, char *err, int errlen, int32_t *stats) {
+                   int dt_mode, int32_t *iters, int32_t *flags, int G, char *err, int errlen, int32_t *stats) {
   Emu *e = (Emu *)hh;
   DevState S = mk_state(v, active);
   LanePlan P;
   const int N = lane_N_for(e->R.h.naq);
   if (N == 0) { if (err) snprintf(err, errlen, "naq exceeds the compiled shapes"); return RXN_ERR_UNSUPPORTED; }
+  if (G != 1 && G != 2 && G != 4) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4"); return RXN_ERR_INVALID; }
   int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P);
   if (rc != RXN_OK || !P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
   if (stats) {
@@ -140,13 +170,14 @@ int emu_react_lane(void *hh, const HostView *v, double *tran_xx, const uint8_t *
     stats[3] = P.terms_spec; stats[4] = P.steps_spec; stats[5] = P.terms_A; stats[6] = P.steps_A; stats[7] = P.terms_B; stats[8] = P.steps_B;
     stats[9] = P.lt.ncls;
   }
+  LaneJob J{&P, e, &S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags};
   switch (N) {
-    case 4: lane_cells<4>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
-    case 8: lane_cells<8>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
-    case 12: lane_cells<12>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
-    case 15: lane_cells<15>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
-    case 16: lane_cells<16>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
-    default: lane_cells<24>(P, e, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags); break;
+    case 4: lane_cells_g<4>(J, G); break;
+    case 8: lane_cells_g<8>(J, G); break;
+    case 12: lane_cells_g<12>(J, G); break;
+    case 15: lane_cells_g<15>(J, G); break;
+    case 16: lane_cells_g<16>(J, G); break;
+    default: lane_cells_g<24>(J, G); break;
   }
   return 0;
 }

@@ -35,23 +35,26 @@ LANE_WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 
 
 @pytest.mark.parametrize('name', LANE_WORKLOADS)
 @pytest.mark.parametrize('dt,mode', [(3600.0, abi.RXN_DT_CONSISTENT), (1.0, abi.RXN_DT_AS_WRITTEN)])
-def test_react_resident_lane(name, dt, mode):
+@pytest.mark.parametrize('G', [1, 2, 4])
+def test_react_resident_lane(name, dt, mode, G):
     """Per-lane routines of the resident-lane kernel (rxn_lane_dev.cuh: term streams, ln-m Jacobian, LU in the
-    lane-strided layout, closing pass), driven cell by cell on the host, against the oracle."""
-    w, cells = workload_cells(name, 600)
+    cell-fastest layout, closing pass) with G lanes per cell (host threads meeting at barriers where the device
+    has __syncwarp / shuffles), driven cell by cell on the host, against the oracle."""
+    w, cells = workload_cells(name, 300 if G > 1 else 600)
     st_o = synth.host_state(w, cells)
     st_e = st_o.copy()
     xo = cells['tran_xx'].copy()
     xe = xo.copy()
     it_o, fl_o = Oracle(w.tables).react(st_o, xo, dt, mode, maxit=10000)
-    it_e, fl_e = Emulator(w.tables).react_lane(st_e, xe, dt, mode)
+    it_e, fl_e = Emulator(w.tables).react_lane(st_e, xe, dt, mode, G=G)
     assert (it_o == it_e).all() and (fl_o == fl_e).all()
     ok = (fl_o & ~3) == 0
     assert rel_err(xe[ok], xo[ok]).max() <= RTOL
     assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
 
 
-def test_resident_lane_iteration_cap_and_inactive():
+@pytest.mark.parametrize('G', [1, 4])
+def test_resident_lane_iteration_cap_and_inactive(G):
     """Abnormal exit (iteration cap): pri_molal moved after the last RTotal, so the closing pass must redo it."""
     w, cells = workload_cells('hanford300a_eq', 200)
     st_o = synth.host_state(w, cells)
@@ -60,7 +63,7 @@ def test_resident_lane_iteration_cap_and_inactive():
     xo = cells['tran_xx'].copy()
     xe = xo.copy()
     it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=3)
-    it_e, fl_e = Emulator(w.tables).react_lane(st_e, xe, 3600.0, abi.RXN_DT_CONSISTENT, maxit=3)
+    it_e, fl_e = Emulator(w.tables).react_lane(st_e, xe, 3600.0, abi.RXN_DT_CONSISTENT, maxit=3, G=G)
     assert (fl_e & abi.RXN_FLAG_CAPPED).any() and (fl_e[::7] == abi.RXN_FLAG_INACTIVE).all()
     assert (it_o == it_e).all() and (fl_o == fl_e).all()
     act = np.where(st_o.active != 0)[0]

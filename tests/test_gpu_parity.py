@@ -150,16 +150,21 @@ def test_full_size_sampled_against_oracle(name, n):
         rz.upload('MNRL_VOLFRAC', cells['volfrac'])
     xg = cells['tran_xx'].copy()
     it_g, fl_g = rz.RTReact(xg, 3600.0)
-    assert ((fl_g == abi.RXN_EXIT_RESIDUAL) | (fl_g == abi.RXN_EXIT_REL_CHANGE)).all()
+    # a handful of "reaction front" cells drive the reference's Newton iteration itself to NaN (the oracle agrees
+    # cell by cell, see the flag comparison below); everything else must leave through a reference exit
+    conv = (fl_g == abi.RXN_EXIT_RESIDUAL) | (fl_g == abi.RXN_EXIT_REL_CHANGE)
+    assert conv.mean() >= 0.9999 and ((fl_g[~conv] & abi.RXN_FLAG_NONFINITE) != 0).all()
     assert it_g.min() >= 1
     pm = rz.download('PRI_MOLAL')
     np.testing.assert_array_equal(pm.T, xg)                      # tran_xx out == stored pri_molal
-    sample = np.sort(np.random.default_rng(11).choice(n, 3000, replace=False))
+    sample = np.sort(np.union1d(np.random.default_rng(11).choice(n, 3000, replace=False), np.where(~conv)[0][:64]))
     sub = {k: (v[sample] if v.ndim == 1 else (v[sample] if k == 'tran_xx' else v[:, sample])) for k, v in cells.items()}
     st_o = synth.host_state(w, sub)
     xo = sub['tran_xx'].copy()
     it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, nthreads=8)
     assert (it_o == it_g[sample]).all() and (fl_o == fl_g[sample]).all()
-    assert rel_err(xg[sample], xo).max() <= RTOL
+    ok = conv[sample]
+    assert rel_err(xg[sample][ok], xo[ok]).max() <= RTOL
     tot = rz.download('TOTAL')
-    assert rel_err(tot[:, sample], st_o['TOTAL']).max() <= RTOL
+    assert_state_close({'TOTAL': tot[:, sample], 'SEC_MOLAL': rz.download('SEC_MOLAL')[:, sample]},
+                       st_o, fields=['TOTAL', 'SEC_MOLAL'], cells=np.where(ok)[0], what=name + ' full size', tables=w.tables)
