@@ -313,8 +313,7 @@ def run_ours(args):
                        'mean_newton_iterations': wm['mean_newton_iterations'], 'cells_with_nonreference_flags': bad_all,
                        'l2_policy': 'inputs (%.1f GB of cell state per GPU) larger than L2; no flush needed'
                                     % (n * wm['bytes_per_cell'] / 1e9),
-                       'kernel': {0: 'auto (resident-lane when the tables allow it)', 1: 'thread-per-cell (local memory)',
-                                  2: 'lane-group-per-cell', 3: 'resident-lane'}[args.kernel]},
+                       'kernel': rz.react_kernel_info()},
             'e2e': {'value': total_cells * args.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': nb,
                     'd2h_bytes_per_step': nb + 2 * n * 4},
             'gpu_launches': int(launches * world),

@@ -231,9 +231,13 @@ int64_t rxn_state_ncells(const RxnState *s);
  * flux-side consumers (TFluxDerivative, transport.F90:368-626) need them, RReact does not.
  * After this call rxn_update_auxvars_batch / rxn_react_batch also store that field. */
 int rxn_state_materialize(RxnState *s, int field);
-/* 0 = automatic, 1 = one thread per cell, 2 = cooperative lane-group per cell (fails if the
- * tables do not fit it).  Benchmark / test control only; results are the same path. */
+/* RReact kernel: 0 = automatic (resident-lane if the tables allow it, else cooperative, else thread per cell),
+ * 1 = one thread per cell with per-thread arrays in local memory, 2 = cooperative lane-group per cell,
+ * 3 = resident-lane (cell state in shared memory, persistent lanes); 2 and 3 fail if the tables do not fit them.
+ * Benchmark / test control only; results are the same path. */
 int rxn_set_react_kernel(RxnState *s, int which);
+/* one-line description of the kernel rxn_react_batch would launch for this state (shape, shared memory) */
+int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len);
 int32_t rxn_field_rows(const RxnTables *t, int field);
 
 /* replaces: direct field access by PatchGetVariable (patch.F90:3529-4788), checkpoint

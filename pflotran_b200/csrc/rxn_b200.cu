@@ -356,6 +356,24 @@ int rxn_set_react_kernel(RxnState *s, int which) {
   return RXN_OK;
 }
 
+int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
+  if (!s || !buf || len < 1) return fail(RXN_ERR_INVALID, "bad argument");
+  const RxnTables *t = s->t;
+  const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
+  const bool tile_ok = t->tile.usable && no_dtotal, lane_ok = t->lane.plan.usable && no_dtotal;
+  if (lane_ok && (s->react_kernel == 0 || s->react_kernel == 3))
+    snprintf(buf, (size_t)len, "resident-lane N=%d cells/CTA=%d lanes/cell=%d threads=%d smem=%zu B plan=%zu B (spec %d, planA %d, planB %d terms)",
+             t->lane.plan.lt.N, t->lane.plan.lt.CPB, t->lane.G, ((t->lane.plan.lt.CPB * t->lane.G + 31) / 32) * 32, t->lane.plan.smem_bytes,
+             t->lane.plan.blob.size(), t->lane.plan.terms_spec, t->lane.plan.terms_A, t->lane.plan.terms_B);
+  else if (tile_ok && s->react_kernel != 1 && s->react_kernel != 3)
+    snprintf(buf, (size_t)len, "cooperative lane-group G=%d cells/CTA=%d threads=%d smem=%zu B", t->tile.tt.G, t->tile.tt.cpb,
+             t->tile.tt.threads, t->tile.smem_bytes);
+  else
+    snprintf(buf, (size_t)len, "thread-per-cell N<=%d (lane: %s; tile: %s)", t->nvariant,
+             t->lane.plan.usable ? "DTOTAL materialised" : t->lane.plan.err.c_str(), t->tile.usable ? "DTOTAL materialised" : t->tile.err.c_str());
+  return RXN_OK;
+}
+
 static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
                         int32_t *d_iters, int32_t *d_flags) {
   const RxnTables *t = s->t;

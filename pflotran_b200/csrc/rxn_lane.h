@@ -1,5 +1,5 @@
 // rxn_lane.h — "resident lane" RReact kernel: plan structures and the host-side plan builder
-// (pure C++, no CUDA: also compiled by the CPU test harness tests/emul).
+// (pure C++, no CUDA: the CPU-only test harness compiles it as well).
 //
 // Design.  One THREAD solves one cell, as the north star asks, but nothing of a
 // cell lives in local memory: the Newton system [J | b] (naq x (naq+1) doubles), sec_molal,
@@ -52,6 +52,7 @@ struct LaneTab {
   int ncls, act_off, act_newton_iter, use_act_h2o, h2o_aq_id, use_log, percell_logK, maxit;
   int has_Temkin, has_scale, has_power, maxsrf;
   int logK_mode, ncoef;
+  int coop_io;          // long per-complex arrays move warp-cooperatively (many complexes / multirate), else by the cell's own lanes
   double debyeA, debyeB, debyeBdot, max_dlnC, rel_tol, res_tol;
   int blob_dbl, blob_int;
   int o_J2, o_vec, smem_dbl;
@@ -114,6 +115,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
   lt.percell_logK = h.logK_mode != RXN_LOGK_FIXED; lt.maxit = h.maxit;
   lt.has_Temkin = h.has_Temkin; lt.has_scale = h.has_scale; lt.has_power = h.has_power;
   lt.logK_mode = h.logK_mode; lt.ncoef = h.ncoef;
+  lt.coop_io = h.ncplx >= 32 || h.nmr > 0;
   lt.debyeA = h.debyeA; lt.debyeB = h.debyeB; lt.debyeBdot = h.debyeBdot;
   lt.max_dlnC = h.max_dlnC; lt.rel_tol = h.rel_tol; lt.res_tol = h.res_tol;
 

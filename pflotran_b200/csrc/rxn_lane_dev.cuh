@@ -13,7 +13,7 @@
 // pivot, convergence tests) are xor-butterflies, so every lane of a group holds bit-identical
 // copies and the group's control flow is uniform.
 //
-// The same source is compiled for the host by tests/emul (RXN_LANE_HOST: one thread per lane,
+// The same source is compiled for the host by the CPU-only test harness (RXN_LANE_HOST: one thread per lane,
 // butterflies through a barrier) and checked against the oracle in the CPU-only suite.
 //
 // Deviations from the reference's operation order (REASSOC, all <= 1e-14 relative; parity is
@@ -519,7 +519,11 @@ LANE_DEV void lane_kinetic_mineral(const LaneTab &lt, Lane<N, G> &c) {
 template <int N, int CPB, int G, int P0>
 LANE_DEV void lane_lu_elim(const Lane<N, G> &c, int i0, int ek, int kodd, double dum, const double2 *pr, double &best, int &imax) {
   constexpr int LDJ2 = (N + 2) / 2;
-#pragma unroll 1
+#ifndef LANE_ELIM_UNROLL
+#define LANE_ELIM_UNROLL 1
+#endif
+  constexpr int UE = LANE_ELIM_UNROLL;
+#pragma unroll UE
   for (int i = i0; i < N; i += G) {
     const double lik = tsm[ek + i * (2 * LDJ2 * CPB)] * dum;
     const double vvi = tsm[c.vscr + i * CPB];
@@ -709,19 +713,30 @@ LANE_DEV void lane_load(const LaneTab &lt, Lane<N, G> &c, const DevState &S, con
   c.psvd = c.porosity * sat * 1000.0 * c.volume / tran_dt;                     // :5189
   c.v_t = c.volume / tran_dt;                                                  // :4590
   c.den_kg_per_L = c.den_kg * 1.0 * 1.0e-3;
+  {
+    // all row loads first (clamped row index: no control flow between them), then the stores
+    double pm[R], xx[R], ts[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i = c.l + r * G;
-    if (i < n) {
-      tsm[c.vm + i * CPB] = GSL(S, RXN_F_PRI_MOLAL, i, cell);
-      double fx = c.psv * tran_xx[item * n + i];                               // :3370, RTAccumulation :5072-5148
-      if (lt.neqsorb > 0) fx = fx + GSL(S, RXN_F_TOTAL_SORB_EQ, i, cell) * c.volume;   // RAccumulationSorb :4539-4568
-      c.fix[r] = fx;
-    } else {
-      // padding row of the shape: m = 1, no complexes -> total = den, residual = psv*den - fix = 0 exactly,
-      // Jln_ii = den*psvd: the row stays decoupled and its Newton update is 0
-      if (i < N) tsm[c.vm + i * CPB] = 1.0;
-      c.fix[r] = c.psv * ((1.0 + 0.0) * c.den_kg_per_L);
+    for (int r = 0; r < R; ++r) {
+      const int i = c.l + r * G, ic = i < n ? i : n - 1;
+      pm[r] = GSL(S, RXN_F_PRI_MOLAL, ic, cell);
+      xx[r] = tran_xx[item * n + ic];
+      ts[r] = lt.neqsorb > 0 ? GSL(S, RXN_F_TOTAL_SORB_EQ, ic, cell) : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = c.l + r * G;
+      if (i < n) {
+        tsm[c.vm + i * CPB] = pm[r];
+        double fx = c.psv * xx[r];                               // :3370, RTAccumulation :5072-5148
+        if (lt.neqsorb > 0) fx = fx + ts[r] * c.volume;          // RAccumulationSorb :4539-4568
+        c.fix[r] = fx;
+      } else {
+        // padding row of the shape: m = 1, no complexes -> total = den, residual = psv*den - fix = 0 exactly,
+        // Jln_ii = den*psvd: the row stays decoupled and its Newton update is 0
+        if (i < N) tsm[c.vm + i * CPB] = 1.0;
+        c.fix[r] = c.psv * ((1.0 + 0.0) * c.den_kg_per_L);
+      }
     }
   }
   if (c.l == 0) {
@@ -734,17 +749,10 @@ LANE_DEV void lane_load(const LaneTab &lt, Lane<N, G> &c, const DevState &S, con
     for (int i = c.l; i < n; i += G) tsm[c.vlng + i * CPB] = c_log(GSL(S, RXN_F_PRI_ACT_COEF, i, cell));
 #pragma unroll 1
     for (int k = c.l; k < lt.ncplx; k += G) tsm[c.vlng + (n + k) * CPB] = c_log(GSL(S, RXN_F_SEC_ACT_COEF, k, cell));
-  } else {
-    // lagged sec_molal (for the ionic strength): batches of 24 independent loads per lane
-    constexpr int LB = 24;
-#pragma unroll 1
-    for (int k0 = c.l; k0 < lt.ncplx; k0 += LB * G) {
-      double buf[LB];
-#pragma unroll
-      for (int u = 0; u < LB; ++u) buf[u] = (k0 + u * G < lt.ncplx) ? GSL(S, RXN_F_SEC_MOLAL, k0 + u * G, cell) : 0.0;
-#pragma unroll
-      for (int u = 0; u < LB; ++u) if (k0 + u * G < lt.ncplx) tsm[c.vsm + (k0 + u * G) * CPB] = buf[u];
-    }
+  }
+  if (!lt.coop_io && !lt.act_off) {
+#pragma unroll 4
+    for (int k = c.l; k < lt.ncplx; k += G) tsm[c.vsm + k * CPB] = GSL(S, RXN_F_SEC_MOLAL, k, cell);   // lagged, for I
   }
 #pragma unroll 1
   for (int q = c.l; q < lt.nrxn; q += G) tsm[c.vfree + q * CPB] = GSL(S, RXN_F_FREE_SITE_CONC, q, cell);
@@ -755,62 +763,89 @@ LANE_DEV void lane_load(const LaneTab &lt, Lane<N, G> &c, const DevState &S, con
   }
   if (lt.percell_logK)
     lane_percell_logK<CPB, G>(c.l, lt.ncoef, lt.logK_mode, c.vlk, c.temp, GSL(S, RXN_F_PRES, 0, cell), blob_d, h.cplx, h.kin, h.srf);
-  // multirate_prepare (rxn_device.cuh; REASSOC): R0_i = sum_r k_r/(1+k_r dt) S_r,i
-#pragma unroll 1
-  for (int ikr = 0; ikr < lt.nmr; ++ikr) {
-    const int nrate = blob_i[h.o_mr_nrate + ikr];
-#pragma unroll 1
-    for (int i = c.l; i < n; i += G) {
-      double acc = 0.0;
-#pragma unroll 5
-      for (int irate = 0; irate < nrate; ++irate) {
-        const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
-        const double kdt = rate * tran_dt;
-        const double one_plus_kdt = 1.0 + kdt;
-        const double kk = rate / one_plus_kdt;
-        acc = acc + kk * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + (irate + 1)) * n + i, cell);
-      }
-      tsm[c.vr0 + (ikr * N + i) * CPB] = acc;
-    }
-  }
   grp_sync<G>(c.gm);
 }
 
-// L2 prefetch of the inputs lane_load will read for `cell` (issued one cell ahead, see the kernel's work loop)
-template <int N, int CPB, int G>
-LANE_DEV void lane_prefetch(const LaneTab &lt, int l, const DevState &S, const DevTab &h, long long item, long long cell,
-                            const double *tran_xx) {
-#ifndef RXN_LANE_HOST
+// Warp-cooperative part of taking / finishing a cell: the long per-complex arrays move with all W lanes of the warp
+// (lane w takes elements w, w+W, ...), whichever group the cell belongs to.  On the host W = 1.
+//   in : lagged sec_molal (for the ionic strength, reaction.F90:3994-4010) and, for multirate sorption,
+//        R0_i = sum_r k_r/(1+k_r dt) S_r,i (multirate_prepare, rxn_device.cuh; REASSOC: even and odd rates summed
+//        separately, then added)
+//   out: sec_molal and sec_act_coef
+// lagged sec_molal of up to 3 cells at once (their loads overlap)
+template <int N, int CPB>
+LANE_DEV void lane_coop_in_sm(const LaneTab &lt, const DevState &S, const int (&slot)[3], const long long (&cell)[3], int cnt, int w, int W) {
+  if (lt.act_off) return;
+#pragma unroll 1
+  for (int k0 = w; k0 < lt.ncplx; k0 += 4 * W) {
+    double b[3][4];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * W;
+        b[g][u] = (g < cnt && k < lt.ncplx) ? GSL(S, RXN_F_SEC_MOLAL, k, cell[g]) : 0.0;
+      }
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * W;
+        if (g < cnt && k < lt.ncplx) tsm[lt.o_vec + (lt.s_sm + k) * CPB + slot[g]] = b[g][u];
+      }
+  }
+}
+template <int N, int CPB>
+LANE_DEV void lane_coop_in_mr(const LaneTab &lt, const DevState &S, const DevTab &h, const double *blob_d, const int *blob_i, int slot,
+                              long long cell, double tran_dt, int w, int W) {
+  const int vr0 = lt.o_vec + lt.s_r0 * CPB + slot;
   const int n = lt.n;
-  auto pf = [](const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
-  if (l == 0) {
-    pf(&GSL(S, RXN_F_LN_ACT_H2O, 0, cell)); pf(&GSL(S, RXN_F_DEN_KG, 0, cell)); pf(&GSL(S, RXN_F_TEMP, 0, cell));
-    pf(&GSL(S, RXN_F_VOLUME, 0, cell)); pf(&GSL(S, RXN_F_POROSITY, 0, cell)); pf(&GSL(S, RXN_F_SOIL_PARTICLE_DENSITY, 0, cell));
-    pf(&GSL(S, RXN_F_SAT, 0, cell));
-    pf(tran_xx + item * n); pf(tran_xx + item * n + n - 1);
-    if (lt.percell_logK) pf(&GSL(S, RXN_F_PRES, 0, cell));
-  }
-#pragma unroll 1
-  for (int i = l; i < n; i += G) {
-    pf(&GSL(S, RXN_F_PRI_MOLAL, i, cell));
-    if (lt.neqsorb > 0) pf(&GSL(S, RXN_F_TOTAL_SORB_EQ, i, cell));
-    if (lt.act_off) pf(&GSL(S, RXN_F_PRI_ACT_COEF, i, cell));
-  }
-#pragma unroll 4
-  for (int k = l; k < lt.ncplx; k += G) pf(lt.act_off ? &GSL(S, RXN_F_SEC_ACT_COEF, k, cell) : &GSL(S, RXN_F_SEC_MOLAL, k, cell));
-#pragma unroll 1
-  for (int q = l; q < lt.nrxn; q += G) pf(&GSL(S, RXN_F_FREE_SITE_CONC, q, cell));
-#pragma unroll 1
-  for (int q = l; q < lt.nkin; q += G) { pf(&GSL(S, RXN_F_MNRL_VOLFRAC, q, cell)); pf(&GSL(S, RXN_F_MNRL_AREA, q, cell)); }
 #pragma unroll 1
   for (int ikr = 0; ikr < lt.nmr; ++ikr) {
-    const int nrate = h.mr_ld;
-#pragma unroll 4
-    for (int e = l; e < nrate * n; e += G) pf(&GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + 1) * n + e, cell));
-  }
-#else
-  (void)lt; (void)l; (void)S; (void)h; (void)item; (void)cell; (void)tran_xx;
+    const int nrate = blob_i[h.o_mr_nrate + ikr];
+    const long long row0 = ((long long)ikr * (h.mr_ld + 1) + 1) * n;
+    // lane (i, half): half = 0 even rates, 1 odd rates
+    const int H = (W >= 2 * n) ? 2 : 1, per = W / H;
+#pragma unroll 1
+    for (int i0 = 0; i0 < n; i0 += per) {
+      const int i = i0 + (w % per), half = w / per;
+      double acc0 = 0.0, acc1 = 0.0;
+      if (i < n && half < H) {
+        if (H == 2) {
+#pragma unroll 5
+          for (int irate = half; irate < nrate; irate += 2) {
+            const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
+            const double kk = rate / (1.0 + rate * tran_dt);
+            acc0 = acc0 + kk * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell);
+          }
+        } else {
+#pragma unroll 5
+          for (int irate = 0; irate < nrate; irate += 2) {
+            const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
+            acc0 = acc0 + rate / (1.0 + rate * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell);
+            if (irate + 1 < nrate) {
+              const double rate1 = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate + 1];
+              acc1 = acc1 + rate1 / (1.0 + rate1 * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)(irate + 1) * n + i, cell);
+            }
+          }
+        }
+      }
+#ifndef RXN_LANE_HOST
+      if (H == 2) acc1 = __shfl_xor_sync(0xffffffffu, acc0, per);   // the odd-rate sum of lane (i, 1)
 #endif
+      if (i < n && half == 0) tsm[vr0 + (ikr * N + i) * CPB] = acc0 + acc1;
+    }
+  }
+}
+
+template <int N, int CPB>
+LANE_DEV void lane_coop_out(const LaneTab &lt, const DevState &S, int slot, long long cell, int w, int W) {
+  const int vsm = lt.o_vec + lt.s_sm * CPB + slot, vlng = lt.o_vec + lt.s_lng * CPB + slot;
+#pragma unroll 4
+  for (int k = w; k < lt.ncplx; k += W) {
+    GSL(S, RXN_F_SEC_MOLAL, k, cell) = tsm[vsm + k * CPB];
+    if (!lt.act_off) GSL(S, RXN_F_SEC_ACT_COEF, k, cell) = tsm[vlng + TI(lt, lt.i_ccls + k) * CPB];
+  }
 }
 
 // x / d with r = 1/d precomputed (one Newton correction: the quotient the division unit returns, bar double rounding)
@@ -1004,11 +1039,14 @@ LANE_DEV void lane_finish(const LaneTab &lt, Lane<N, G> &c, const DevState &S, c
     grp_sync<G>(c.gm);
 #pragma unroll 1
     for (int i = c.l; i < n; i += G) GSL(S, RXN_F_PRI_ACT_COEF, i, cell) = tsm[c.vlng + TI(lt, lt.i_pcls + i) * CPB];
-#pragma unroll 4
-    for (int k = c.l; k < lt.ncplx; k += G) GSL(S, RXN_F_SEC_ACT_COEF, k, cell) = tsm[c.vlng + TI(lt, lt.i_ccls + k) * CPB];
   }
-#pragma unroll 4
-  for (int k = c.l; k < lt.ncplx; k += G) GSL(S, RXN_F_SEC_MOLAL, k, cell) = tsm[c.vsm + k * CPB];
+  if (!lt.coop_io) {
+#pragma unroll 2
+    for (int k = c.l; k < lt.ncplx; k += G) {
+      GSL(S, RXN_F_SEC_MOLAL, k, cell) = tsm[c.vsm + k * CPB];
+      if (!lt.act_off) GSL(S, RXN_F_SEC_ACT_COEF, k, cell) = tsm[c.vlng + TI(lt, lt.i_ccls + k) * CPB];
+    }
+  }
 #pragma unroll 1
   for (int q = c.l; q < lt.nrxn; q += G) GSL(S, RXN_F_FREE_SITE_CONC, q, cell) = tsm[c.vfree + q * CPB];
 #pragma unroll 1

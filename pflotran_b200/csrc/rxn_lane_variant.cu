@@ -33,77 +33,80 @@ k_react_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab 
   lane_bind<N, CPB, G>(lt, c, s, l, gm);
   bool active = false, exhausted = s >= lt.cells;              // uniform over a group
   int pending = 0;                                             // exit status waiting for its closing pass
-  long long next_item = -1;                                    // item reserved (and prefetched into L2) for this group
   const double inv_dt = 1.0 / dt;
-  // one-cell-ahead reservation + L2 prefetch: only when every group gets several cells anyway (small batches
-  // would lose balance: a reserved item cannot be taken over by an idle group)
-#ifndef LANE_NO_PREFETCH
-  const bool kPrefetch = nlocal >= 4LL * gridDim.x * CPB;
-#else
-  const bool kPrefetch = false;
-#endif
 #pragma unroll 1
   for (;;) {
+    bool fresh = false;                                        // this group took a cell in this round of the outer loop
 #pragma unroll 1
     for (;;) {                                                 // hand out work to the idle groups of this warp
-      // a group without a cell first takes its reserved item; every idle or reservation-less group then draws from the counter
-      const bool idle = !active && !exhausted;
-      long long i = -1;
-      if (idle && next_item >= 0) { i = next_item; next_item = -1; }
-      const bool want = !exhausted && ((idle && i < 0) || (kPrefetch && next_item == -1 && (active || i >= 0)));
+      const bool want = !active && !exhausted;
       const unsigned wm = __ballot_sync(0xffffffffu, want) & leaders;
-      if (wm != 0u) {
-        const int leader = __ffs(wm) - 1;
-        unsigned long long base = 0;
-        if (ln == leader) base = atomicAdd(counter, (unsigned long long)__popc(wm));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (want) {
-          const long long got = (long long)base + __popc(wm & ((1u << (ln & ~(G - 1))) - 1u));
-          if (got >= nlocal) {
-            if (idle && i < 0) exhausted = true;               // nothing left for a group that has no cell
-            else next_item = -2;                                // no further reservation attempts
-          } else if (idle && i < 0) {
-            i = got;
-          } else {
-            next_item = got;
-            const long long pc = l2g ? l2g[got] : got;
-            if (!(S.active && !S.active[pc])) lane_prefetch<N, CPB, G>(lt, l, S, h, got, pc, tran_xx);
-          }
-        }
-      }
-      if (idle && i >= 0) {
-        const long long cell = l2g ? l2g[i] : i;
-        if (S.active && !S.active[cell]) {                     // imat <= 0 (reactive_transport.F90:1699)
-          if (l == 0) {
-            if (iters) iters[i] = 0;
-            if (flags) flags[i] = RXN_FLAG_INACTIVE;
-          }
+      if (wm == 0u) break;
+      const int leader = __ffs(wm) - 1;
+      unsigned long long base = 0;
+      if (ln == leader) base = atomicAdd(counter, (unsigned long long)__popc(wm));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (want) {
+        const long long i = (long long)base + __popc(wm & ((1u << (ln & ~(G - 1))) - 1u));
+        if (i >= nlocal) {
+          exhausted = true;
         } else {
-          lane_load<N, CPB, G>(lt, c, S, bd, bi, h, i, cell, tran_xx, dt);
-          active = true;
-          pending = 0;
+          const long long cell = l2g ? l2g[i] : i;
+          if (S.active && !S.active[cell]) {                   // imat <= 0 (reactive_transport.F90:1699)
+            if (l == 0) {
+              if (iters) iters[i] = 0;
+              if (flags) flags[i] = RXN_FLAG_INACTIVE;
+            }
+          } else {
+            lane_load<N, CPB, G>(lt, c, S, bd, bi, h, i, cell, tran_xx, dt);
+            active = true;
+            fresh = true;
+            pending = 0;
+          }
         }
       }
-      // another round while some group is still without a cell (inactive cell drawn, or reservation just consumed)
-      const bool again = !active && !exhausted;
-      if (!__any_sync(0xffffffffu, again || (kPrefetch && !exhausted && next_item == -1 && active))) break;
     }
     if (!__any_sync(0xffffffffu, active)) break;
+    // the long arrays of the cells just taken: all 32 lanes of the warp, one cell after the other
+    for (unsigned fm = lt.coop_io ? (__ballot_sync(0xffffffffu, fresh) & leaders) : 0u; fm != 0u;) {
+      int slot[3], cnt = 0;
+      long long cell[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int g = fm != 0u ? __ffs(fm) - 1 : 0;
+        slot[q] = __shfl_sync(0xffffffffu, c.s, g);
+        cell[q] = __shfl_sync(0xffffffffu, c.cell, g);
+        if (fm != 0u) { cnt = q + 1; fm &= fm - 1u; }
+      }
+      lane_coop_in_sm<N, CPB>(lt, S, slot, cell, cnt, ln, 32);
+      if (lt.nmr > 0)
+        for (int q = 0; q < cnt; ++q) lane_coop_in_mr<N, CPB>(lt, S, h, bd, bi, slot[q], cell[q], dt, ln, 32);
+    }
+    __syncwarp();
+    bool fin = false;
     if (active) {
       bool recompute;
       const int st = lane_trip<N, CPB, G>(lt, c, S, dt, inv_dt, dt_mode, pending != 0, recompute);
       if (pending != 0) {
         lane_finish<N, CPB, G>(lt, c, S, h, tran_xx, iters, flags, pending);
-        active = false;
+        active = false; fin = true;
       } else if (st != 0) {
         if (recompute) {
           pending = st;
         } else {
           lane_finish<N, CPB, G>(lt, c, S, h, tran_xx, iters, flags, st);
-          active = false;
+          active = false; fin = true;
         }
       }
     }
+    __syncwarp();
+    for (unsigned fm = lt.coop_io ? (__ballot_sync(0xffffffffu, fin) & leaders) : 0u; fm != 0u; fm &= fm - 1u) {
+      const int g = __ffs(fm) - 1;
+      const int slot = __shfl_sync(0xffffffffu, c.s, g);
+      const long long cell = __shfl_sync(0xffffffffu, c.cell, g);
+      lane_coop_out<N, CPB>(lt, S, slot, cell, ln, 32);
+    }
+    __syncwarp();
   }
 }
 

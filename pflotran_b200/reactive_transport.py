@@ -55,6 +55,7 @@ def lib():
         L.rxn_field_rows.argtypes = [C.c_void_p, C.c_int]
         L.rxn_state_materialize.argtypes = [C.c_void_p, C.c_int]
         L.rxn_set_react_kernel.argtypes = [C.c_void_p, C.c_int]
+        L.rxn_react_kernel_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
         L.rxn_state_upload.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
         L.rxn_state_download.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
         L.rxn_state_broadcast.argtypes = [C.c_void_p, C.c_int, c_dp]
@@ -220,6 +221,11 @@ class Realization:
 
     def set_react_kernel(self, which: int):
         _ck(lib().rxn_set_react_kernel(self.h, which))
+
+    def react_kernel_info(self) -> str:
+        buf = C.create_string_buffer(512)
+        _ck(lib().rxn_react_kernel_info(self.h, buf, 512))
+        return buf.value.decode()
 
     # ---- the cell loops ----
     def RTReact(self, tran_xx: np.ndarray, dt: float, dt_mode: int = abi.RXN_DT_CONSISTENT,

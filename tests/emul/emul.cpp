@@ -72,14 +72,27 @@ static void lane_thread(const LaneJob *J, LaneTab lt, int l) {
     Lane<N, G> c;
     lane_bind<N, 1, G>(lt, c, 0, l, 0u);
     lane_load<N, 1, G>(lt, c, S, J->e->T.d, J->e->T.i, h, i, cell, J->tran_xx, J->dt);
+    if (l == 0 && lt.coop_io) {                                  // the warp-cooperative part, one "lane"
+      const int slot3[3] = {0, 0, 0};
+      const long long cell3[3] = {cell, cell, cell};
+      lane_coop_in_sm<N, 1>(lt, S, slot3, cell3, 1, 0, 1);
+      if (lt.nmr > 0) lane_coop_in_mr<N, 1>(lt, S, h, J->e->T.d, J->e->T.i, 0, cell, J->dt, 0, 1);
+    }
+    grp_sync<G>(0u);
     int pending = 0;
     for (;;) {
       bool recompute;
       const int st = lane_trip<N, 1, G>(lt, c, S, J->dt, inv_dt, J->dt_mode, pending != 0, recompute);
-      if (pending != 0) { lane_finish<N, 1, G>(lt, c, S, h, J->tran_xx, J->iters, J->flags, pending); break; }
-      if (st != 0) {
+      bool fin = false;
+      if (pending != 0) { lane_finish<N, 1, G>(lt, c, S, h, J->tran_xx, J->iters, J->flags, pending); fin = true; }
+      else if (st != 0) {
         if (recompute) pending = st;
-        else { lane_finish<N, 1, G>(lt, c, S, h, J->tran_xx, J->iters, J->flags, st); break; }
+        else { lane_finish<N, 1, G>(lt, c, S, h, J->tran_xx, J->iters, J->flags, st); fin = true; }
+      }
+      if (fin) {
+        if (l == 0 && lt.coop_io) lane_coop_out<N, 1>(lt, S, 0, cell, 0, 1);
+        grp_sync<G>(0u);
+        break;
       }
     }
   }
