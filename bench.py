@@ -45,6 +45,9 @@ WORKLOAD_DESC = {
     'calcite': 'example_problems/100_100_100 calcite chemistry (4 primaries, 5 complexes, 1 kinetic mineral)',
     'hpt_calcite': 'geothermal-hpt.dat calcite chemistry, per-cell T,P dependent logK',
 }
+# DRAM bytes per cell-update of the react kernel from the committed `ncu --set full` captures
+# (dram__bytes_read.sum + dram__bytes_write.sum over the cells of the profiled launch): profiles/r01_r9_lane_g2.metrics.csv
+NCU_DRAM_BYTES_PER_CELL = {'hanford300a_eq': (755.823872e6 + 1234.784e6) / 600000}
 RESET_FIELDS = ['PRI_MOLAL', 'PRI_ACT_COEF', 'SEC_MOLAL', 'SEC_ACT_COEF', 'LN_ACT_H2O', 'TOTAL_SORB_EQ', 'FREE_SITE_CONC',
                 'EQIONX_REF_CATION_SORBED_CONC']
 
@@ -319,13 +322,18 @@ def run_ours(args):
             'gpu_launches': int(launches * world),
             'clocks': clocks,
             'roofline': {'bound': 'fp64', 'achieved': fp64_ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': fp64_ach / fp64_peak,
-                         'traffic': None,
+                         'traffic': (NCU_DRAM_BYTES_PER_CELL[args.workload] * n if args.workload in NCU_DRAM_BYTES_PER_CELL
+                                     and not args.kernel else None),
                          'note': 'FP64 CUDA-core path: achieved = flop-equivalents (SURVEY.md 8d, W=20 per exp/log/sqrt/pow) x cells '
                                  '/ react-kernel time (CUDA events); peak = DFMA probe measured in this run (rxn_probe_fp64)',
                          'kernel_ms': kern_ms_max, 'flop_eq_per_cell': wm['flop_eq_per_cell'],
                          'transcendentals_per_cell': wm['transcendentals_per_cell']},
             'roofline_hbm': {'bound': 'hbm', 'achieved': hbm_ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                             'frac': hbm_ach / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_src,
+                             'frac': hbm_ach / peaks['hbm_gbs'],
+                             'traffic': (NCU_DRAM_BYTES_PER_CELL[args.workload] * n if args.workload in NCU_DRAM_BYTES_PER_CELL
+                                         and not args.kernel else None),
+                             'traffic_source': 'ncu --set full capture of this kernel, per cell x cells of one launch '
+                                               '(profiles/r01_r9_lane_g2.metrics.csv)', 'peak_source': peak_src,
                              'bytes_per_cell': wm['bytes_per_cell']},
         }
         # CPU baseline: bounded sample on the host cores of this box
