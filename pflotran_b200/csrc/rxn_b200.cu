@@ -72,6 +72,7 @@ struct RxnState {
   size_t scratch_bytes[4] = {0, 0, 0, 0};
   int react_kernel = 0;    // 0 auto, 1 thread-per-cell, 2 cooperative tile, 3 resident lane
   unsigned long long *d_counter = nullptr;   // work counter of the resident-lane kernel
+  int gi_kernel = 0;       // residual/Jacobian blocks: 0 auto (resident-lane layout if the tables allow it), 1 thread per cell
 };
 
 namespace {
@@ -233,6 +234,7 @@ int rxn_state_create(const RxnTables *t, int64_t ncells, RxnState **out) {
   memset(&s->S, 0, sizeof s->S);
   s->S.ld = s->ld; s->S.ncells = ncells;
   if (const char *e = getenv("RXN_REACT_KERNEL")) s->react_kernel = atoi(e);
+  if (const char *e = getenv("RXN_GI_KERNEL")) s->gi_kernel = atoi(e);
   int rc = RXN_OK;
   if (cudaStreamCreate(&s->stream) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
     rc = fail(RXN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -514,10 +516,17 @@ int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t 
     CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
   }
   CU(cudaEventRecord(s->ev0, s->stream));
-  const int threads = t->nvariant <= 8 ? 128 : 64;
-  const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
-  RXN_DISPATCH(t->nvariant, run_residual_jacobian, L, t->h, (const double *)t->d_blob, s->S, (const int *)d_l2g, (long long)nlocal,
-               dt, (double *)d_res, (double *)d_jac);
+  if (t->lane.plan_gi.usable && s->gi_kernel != 1) {
+    rc = lane_launch_gi(t->lane, t->h, t->d_blob, s->S, (const int32_t *)d_l2g, (long long)nlocal, dt, (double *)d_res, (double *)d_jac,
+                        s->stream);
+    if (rc != RXN_OK) return fail(rc, "resident-lane residual/Jacobian kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ++g_launches;
+  } else {
+    const int threads = t->nvariant <= 8 ? 128 : 64;
+    const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
+    RXN_DISPATCH(t->nvariant, run_residual_jacobian, L, t->h, (const double *)t->d_blob, s->S, (const int *)d_l2g, (long long)nlocal,
+                 dt, (double *)d_res, (double *)d_jac);
+  }
   CU(cudaEventRecord(s->ev1, s->stream));
   if (res_out) CU(cudaMemcpyAsync(res_out, d_res, (size_t)nlocal * n * 8, cudaMemcpyDeviceToHost, s->stream));
   if (jac_out) CU(cudaMemcpyAsync(jac_out, d_jac, (size_t)nlocal * n * n * 8, cudaMemcpyDeviceToHost, s->stream));

@@ -12,6 +12,11 @@ namespace rxn {
                                                  int32_t *, unsigned long long *, cudaStream_t);
 RXN_LANE_SHAPES(RXN_LANE_DECL)
 #undef RXN_LANE_DECL
+#define RXN_LANE_DECL(n, cpb, g)                                                                                                    \
+  template <> int lane_launch_gi_variant<n, cpb, g>(const LaneTab &, size_t, int, const DevTab &, const double *, const double *,   \
+                                                    const DevState &, const int32_t *, long long, double, double *, double *, cudaStream_t);
+RXN_LANE_SHAPES(RXN_LANE_DECL)
+#undef RXN_LANE_DECL
 
 int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, int device, LaneKernel *k) {
   LanePlan &p = k->plan;
@@ -29,16 +34,42 @@ int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std:
       RXN_LANE_SHAPES(RXN_LANE_ROW)
 #undef RXN_LANE_ROW
   };
-  for (const LaneShape &s : shapes) {
-    if (s.N != N) continue;
-    if (force_cpb && s.CPB != force_cpb) continue;
-    if (force_g && s.G != force_g) continue;
-    int rc = lane_plan_build(h, bd, bi, s.N, s.CPB, prop.sharedMemPerBlockOptin, &p);
-    if (rc != RXN_OK) return rc;
-    k->G = s.G;
-    if (p.usable) break;
-    if (p.err.find("does not fit") == std::string::npos) break;     // chemistry, not shape, is the obstacle
+  auto pick = [&](LanePlan &pl, int &Gout, bool gamma_state) {
+    for (const LaneShape &s : shapes) {
+      if (s.N != N) continue;
+      if (force_cpb && s.CPB != force_cpb) continue;
+      if (force_g && s.G != force_g) continue;
+      int rc = lane_plan_build(h, bd, bi, s.N, s.CPB, prop.sharedMemPerBlockOptin, &pl, gamma_state);
+      if (rc != RXN_OK) return rc;
+      Gout = s.G;
+      if (pl.usable) break;
+      if (pl.err.find("does not fit") == std::string::npos) break;     // chemistry, not shape, is the obstacle
+    }
+    return (int)RXN_OK;
+  };
+  int rc0 = pick(p, k->G, false);
+  if (rc0 != RXN_OK) return rc0;
+  rc0 = pick(k->plan_gi, k->G_gi, true);
+  if (rc0 != RXN_OK) return rc0;
+  if (h.nmr > 0 && k->plan_gi.usable) {
+    // measured (profiles/r01_r9_bench_gi.txt): the 750 multirate sorbed totals per cell are read faster by the
+    // thread-per-cell kernel (one thread per cell at full occupancy) than by 2 lanes x 48 resident cells
+    k->plan_gi.usable = false;
+    k->plan_gi.err = "multirate sorption: residual/Jacobian blocks stay on the thread-per-cell kernel";
   }
+  if (k->plan_gi.usable) {
+    if (cudaMalloc(&k->d_blob_gi, k->plan_gi.blob.size()) != cudaSuccess ||
+        cudaMemcpy(k->d_blob_gi, k->plan_gi.blob.data(), k->plan_gi.blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      k->plan_gi.usable = false;
+      k->plan_gi.err = std::string("plan upload failed: ") + cudaGetErrorString(cudaGetLastError());
+      return RXN_ERR_CUDA;
+    }
+  }
+  k->mr_ld = h.mr_ld;
+  k->mr_nrate.clear();
+  for (int i = 0; i < h.nmr; ++i) k->mr_nrate.push_back(bi[h.o_mr_nrate + i]);
+  k->mr_rate.assign(bd.begin() + h.o_mr_rate, bd.begin() + h.o_mr_rate + (size_t)h.nmr * h.mr_ld);
+  k->mr_frac.assign(bd.begin() + h.o_mr_frac, bd.begin() + h.o_mr_frac + (size_t)h.nmr * h.mr_ld);
   if (!p.usable) return RXN_OK;
   if (cudaMalloc(&k->d_blob, p.blob.size()) != cudaSuccess ||
       cudaMemcpy(k->d_blob, p.blob.data(), p.blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -46,10 +77,6 @@ int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std:
     p.err = std::string("plan upload failed: ") + cudaGetErrorString(cudaGetLastError());
     return RXN_ERR_CUDA;
   }
-  k->mr_ld = h.mr_ld;
-  for (int i = 0; i < h.nmr; ++i) k->mr_nrate.push_back(bi[h.o_mr_nrate + i]);
-  k->mr_rate.assign(bd.begin() + h.o_mr_rate, bd.begin() + h.o_mr_rate + (size_t)h.nmr * h.mr_ld);
-  k->mr_frac.assign(bd.begin() + h.o_mr_frac, bd.begin() + h.o_mr_frac + (size_t)h.nmr * h.mr_ld);
   if (getenv("RXN_LANE_VERBOSE"))
     fprintf(stderr, "[rxn lane] N=%d CPB=%d G=%d smem=%zu B blob=%zu B classes=%d spec %d terms/%d steps, planA %d/%d, planB %d/%d\n",
             p.lt.N, p.lt.CPB, k->G, p.smem_bytes, p.blob.size(), p.lt.ncls, p.terms_spec, p.steps_spec, p.terms_A, p.steps_A, p.terms_B,
@@ -59,14 +86,12 @@ int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std:
 
 void lane_kernel_free(LaneKernel *k) {
   if (k->d_blob) cudaFree(k->d_blob);
-  k->d_blob = nullptr;
-  k->plan.usable = false;
+  if (k->d_blob_gi) cudaFree(k->d_blob_gi);
+  k->d_blob = k->d_blob_gi = nullptr;
+  k->plan.usable = k->plan_gi.usable = false;
 }
 
-int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
-                      long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
-                      cudaStream_t stream) {
-  LaneTab lt = k.plan.lt;
+static void lane_set_mrK1(const LaneKernel &k, LaneTab &lt, double dt) {
   // K1 = sum_r k_r/(1 + k_r dt) f_r (multirate_prepare, rxn_device.cuh): the same for every cell
   for (int ikr = 0; ikr < lt.nmr && ikr < 2; ++ikr) {
     double K1 = 0.0;
@@ -79,6 +104,26 @@ int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const 
     }
     lt.mrK1[ikr] = K1;
   }
+}
+
+int lane_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, const int32_t *l2g, long long nlocal, double dt,
+                   double *res_out, double *jac_out, cudaStream_t stream) {
+  LaneTab lt = k.plan_gi.lt;
+  lane_set_mrK1(k, lt, dt);
+#define RXN_LANE_CASE(n, cpb, g)                                                                                                   \
+  if (lt.N == n && lt.CPB == cpb && k.G_gi == g)                                                                                   \
+    return lane_launch_gi_variant<n, cpb, g>(lt, k.plan_gi.smem_bytes, k.sm_count, h, k.d_blob_gi, blob, S, l2g, nlocal, dt, res_out, \
+                                             jac_out, stream);
+  RXN_LANE_SHAPES(RXN_LANE_CASE)
+#undef RXN_LANE_CASE
+  return RXN_ERR_UNSUPPORTED;
+}
+
+int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
+                      long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
+                      cudaStream_t stream) {
+  LaneTab lt = k.plan.lt;
+  lane_set_mrK1(k, lt, dt);
   if (cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXN_ERR_CUDA;
 #define RXN_LANE_CASE(n, cpb, g)                                                                                                 \
   if (lt.N == n && lt.CPB == cpb && k.G == g)                                                                                    \

@@ -21,6 +21,9 @@ namespace rxn {
 struct LaneKernel {
   LanePlan plan;
   int G = 1;             // lanes per cell of the selected shape
+  LanePlan plan_gi;      // global-implicit residual/Jacobian kernel: same streams, activity coefficients from the state
+  double *d_blob_gi = nullptr;
+  int G_gi = 1;
   double *d_blob = nullptr;
   int sm_count = 0;
   std::vector<double> mr_rate, mr_frac;   // host copies for the per-launch K1 sums
@@ -33,10 +36,18 @@ int lane_launch_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, cons
                         const DevState &S, double *tran_xx, const int32_t *l2g, long long nlocal, double dt, int dt_mode,
                         int32_t *iters, int32_t *flags, unsigned long long *counter, cudaStream_t stream);
 
+template <int N, int CPB, int G>
+int lane_launch_gi_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
+                           const DevState &S, const int32_t *l2g, long long nlocal, double dt, double *res_out, double *jac_out,
+                           cudaStream_t stream);
+
 int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, int device, LaneKernel *k);
 void lane_kernel_free(LaneKernel *k);
 int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
                       long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
                       cudaStream_t stream);
+
+int lane_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, const int32_t *l2g, long long nlocal, double dt,
+                   double *res_out, double *jac_out, cudaStream_t stream);
 
 }  // namespace rxn

@@ -53,6 +53,7 @@ struct LaneTab {
   int has_Temkin, has_scale, has_power, maxsrf;
   int logK_mode, ncoef;
   int coop_io;          // long per-complex arrays move warp-cooperatively (many complexes / multirate), else by the cell's own lanes
+  int gamma_state;      // global-implicit plan: activity coefficients are the state's (one class per species; complexes divide by gamma)
   double debyeA, debyeB, debyeBdot, max_dlnC, rel_tol, res_tol;
   int blob_dbl, blob_int;
   int o_J2, o_vec, smem_dbl;
@@ -95,13 +96,13 @@ inline int lane_N_for(int naq) {
 // shared memory one CTA may use.  Returns RXN_OK and sets p->usable (false + p->err if this chemistry
 // or shape cannot use the kernel).
 inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, int N, int CPB,
-                           size_t smem_max, LanePlan *p) {
+                           size_t smem_max, LanePlan *p, bool gamma_state = false) {
   p->usable = false;
   LaneTab &lt = p->lt;
   memset(&lt, 0, sizeof lt);
   auto unusable = [&](const char *why) { p->err = why; return RXN_OK; };
   const int n = h.naq;
-  if (h.act_alg == RXN_ACT_COEF_ALGORITHM_NEWTON && h.act_freq != RXN_ACT_COEF_FREQUENCY_OFF)
+  if (!gamma_state && h.act_alg == RXN_ACT_COEF_ALGORITHM_NEWTON && h.act_freq != RXN_ACT_COEF_FREQUENCY_OFF)
     return unusable("NEWTON activity-coefficient algorithm runs on the thread-per-cell kernel");
   if (h.nionx > 0 || h.nkd > 0) return unusable("ion exchange / KD isotherms run on the thread-per-cell kernel");
   if (h.maxpref > 0) return unusable("mineral prefactors run on the cooperative kernel");
@@ -116,6 +117,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
   lt.has_Temkin = h.has_Temkin; lt.has_scale = h.has_scale; lt.has_power = h.has_power;
   lt.logK_mode = h.logK_mode; lt.ncoef = h.ncoef;
   lt.coop_io = h.ncplx >= 32 || h.nmr > 0;
+  lt.gamma_state = gamma_state;
   lt.debyeA = h.debyeA; lt.debyeB = h.debyeB; lt.debyeBdot = h.debyeBdot;
   lt.max_dlnC = h.max_dlnC; lt.rel_tol = h.rel_tol; lt.res_tol = h.res_tol;
 
@@ -131,7 +133,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
   // is its own class and ln gamma is taken from the state at load time.
   std::vector<double> z2(1, 0.0), a0(1, 0.0);
   std::vector<int32_t> pcls(n), ccls(std::max(h.ncplx, 1), 0);
-  if (lt.act_off) {
+  if (lt.act_off || gamma_state) {
     z2.assign(n + h.ncplx, 0.0); a0.assign(n + h.ncplx, 0.0);
     for (int i = 0; i < n; ++i) pcls[i] = i;
     for (int k = 0; k < h.ncplx; ++k) ccls[k] = n + k;

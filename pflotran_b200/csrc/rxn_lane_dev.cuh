@@ -268,10 +268,14 @@ LANE_DEV void lane_speciate(const LaneTab &lt, Lane<N, G> &c) {
       a0 = ia.x; a1 = ia.y; a2 = ib.x; a3 = ib.y;
     }
     lane_run_group(lt, s, c0, o0, nsteps, a0, a1, a2, a3);
-    // REASSOC: exp(lnQK)/gamma_k -> exp(lnQK - ln gamma_k)
-    const double e0 = exp(a0 - tsm[m0.y + s]), e1 = exp(a1 - tsm[m1.y + s]), e2 = exp(a2 - tsm[m2.y + s]),
-                 e3 = exp(a3 - tsm[m3.y + s]);
-    tsm[m0.x + s] = e0; tsm[m1.x + s] = e1; tsm[m2.x + s] = e2; tsm[m3.x + s] = e3;
+    if (lt.gamma_state) {                                      // sec_molal = exp(lnQK)/gamma_k, gamma_k as stored in the state (:4112)
+      const double e0 = exp(a0) / tsm[m0.y + s], e1 = exp(a1) / tsm[m1.y + s], e2 = exp(a2) / tsm[m2.y + s], e3 = exp(a3) / tsm[m3.y + s];
+      tsm[m0.x + s] = e0; tsm[m1.x + s] = e1; tsm[m2.x + s] = e2; tsm[m3.x + s] = e3;
+    } else {                                                   // REASSOC: exp(lnQK)/gamma_k -> exp(lnQK - ln gamma_k)
+      const double e0 = exp(a0 - tsm[m0.y + s]), e1 = exp(a1 - tsm[m1.y + s]), e2 = exp(a2 - tsm[m2.y + s]),
+                   e3 = exp(a3 - tsm[m3.y + s]);
+      tsm[m0.x + s] = e0; tsm[m1.x + s] = e1; tsm[m2.x + s] = e2; tsm[m3.x + s] = e3;
+    }
   }
   grp_sync<G>(c.gm);
 }
@@ -1056,6 +1060,151 @@ LANE_DEV void lane_finish(const LaneTab &lt, Lane<N, G> &c, const DevState &S, c
     if (iters) iters[c.item] = c.iter;
     if (flags) flags[c.item] = status | c.flags;
   }
+  grp_sync<G>(c.gm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Global-implicit block of one cell: accumulation + reaction parts of RTResidualNonFlux
+// (reactive_transport.F90:2545-2586, 2735-2758) and RTJacobianNonFlux (:3342-3389, 3445-3465), as
+// cell_residual_jacobian of the thread-per-cell path: total / dtotal re-evaluated from pri_molal and the state's
+// activity coefficients, res = (RTAccumulation + RAccumulationSorb)/dt + RReaction, jac = accumulation derivative block
+// + reaction derivative block (column-major, with respect to m_j: the ln-m block divided by m_j on the way out).
+template <int N, int CPB, int G>
+LANE_DEV void lane_gi_cell(const LaneTab &lt, Lane<N, G> &c, const DevState &S, const double *blob_d, const int *blob_i, const DevTab &h,
+                           long long item, long long cell, double dt, double *res_out, double *jac_out) {
+  constexpr int LDJ2 = (N + 2) / 2;
+  const int n = lt.n;
+  const int bcol = 2 * (c.jb + (N >> 1) * CPB) + (N & 1), brow = 2 * LDJ2 * CPB;
+  c.item = item; c.cell = cell; c.flags = 0; c.iter = 0;
+  c.ln_act_h2o = GSL(S, RXN_F_LN_ACT_H2O, 0, cell);
+  c.den_kg = GSL(S, RXN_F_DEN_KG, 0, cell);
+  c.temp = GSL(S, RXN_F_TEMP, 0, cell);
+  c.volume = GSL(S, RXN_F_VOLUME, 0, cell);
+  c.porosity = GSL(S, RXN_F_POROSITY, 0, cell);
+  c.soil_density = GSL(S, RXN_F_SOIL_PARTICLE_DENSITY, 0, cell);
+  const double sat = GSL(S, RXN_F_SAT, 0, cell);
+  c.psv = c.porosity * sat * 1000.0 * c.volume;
+  c.psvd = c.porosity * sat * 1000.0 * c.volume / dt;
+  c.v_t = c.volume / dt;
+  c.den_kg_per_L = c.den_kg * 1.0 * 1.0e-3;
+  grp_sync<G>(c.gm);
+#pragma unroll 2
+  for (int i = c.l; i < N; i += G) {
+    tsm[c.vm + i * CPB] = i < n ? GSL(S, RXN_F_PRI_MOLAL, i, cell) : 1.0;
+    if (i < n) tsm[c.vlng + i * CPB] = log(GSL(S, RXN_F_PRI_ACT_COEF, i, cell));      // ln_act = ln_conc + log(pri_act_coef) :4090
+  }
+#pragma unroll 8
+  for (int k = c.l; k < lt.ncplx; k += G) tsm[c.vlng + (n + k) * CPB] = GSL(S, RXN_F_SEC_ACT_COEF, k, cell);
+  if (c.l == 0) {
+    tsm[c.vlna + n * CPB] = 0.0;
+    tsm[c.vlna + (n + 1) * CPB] = c.ln_act_h2o;
+    tsm[c.vsm + lt.ncplx * CPB] = 0.0;
+  }
+#pragma unroll 1
+  for (int q = c.l; q < lt.nrxn; q += G) tsm[c.vfree + q * CPB] = GSL(S, RXN_F_FREE_SITE_CONC, q, cell);
+#pragma unroll 1
+  for (int q = c.l; q < lt.nkin; q += G) {
+    tsm[c.vmnrl + q * CPB] = GSL(S, RXN_F_MNRL_VOLFRAC, q, cell);
+    tsm[c.vmnrl + (lt.nkin + q) * CPB] = GSL(S, RXN_F_MNRL_AREA, q, cell);
+  }
+  if (lt.percell_logK)
+    lane_percell_logK<CPB, G>(c.l, lt.ncoef, lt.logK_mode, c.vlk, c.temp, GSL(S, RXN_F_PRES, 0, cell), blob_d, h.cplx, h.kin, h.srf);
+#pragma unroll 1
+  for (int ikr = 0; ikr < lt.nmr; ++ikr) {                     // multirate_prepare (rxn_device.cuh)
+    const int nrate = blob_i[h.o_mr_nrate + ikr];
+#pragma unroll 1
+    for (int i = c.l; i < n; i += G) {
+      double acc0 = 0.0, acc1 = 0.0;                            // even / odd rates, as lane_coop_in_mr
+#pragma unroll 4
+      for (int irate = 0; irate < nrate; irate += 2) {
+        const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
+        acc0 = acc0 + rate / (1.0 + rate * dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + irate + 1) * n + i, cell);
+        if (irate + 1 < nrate) {
+          const double rate1 = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate + 1];
+          acc1 = acc1 + rate1 / (1.0 + rate1 * dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + irate + 2) * n + i, cell);
+        }
+      }
+      tsm[c.vr0 + (ikr * N + i) * CPB] = acc0 + acc1;
+    }
+  }
+  grp_sync<G>(c.gm);
+  // RTAuxVarCompute: RTotal + RTotalSorb
+  lane_speciate<N, CPB, G>(lt, c);
+  lane_plan<N, CPB, G, false>(lt, c, 0.0);
+  {
+    double2 z; z.x = 0.0; z.y = 0.0;
+#pragma unroll 8
+    for (int e = c.l; e < N * LDJ2; e += G) TSM2[c.jb + e * CPB] = z;
+  }
+  grp_sync<G>(c.gm);
+  const double dp = c.den_kg_per_L * c.psvd;
+  lane_plan<N, CPB, G, true>(lt, c, dp);
+  grp_sync<G>(c.gm);
+#pragma unroll 1
+  for (int i = c.l; i < N; i += G) JE(c, i, i) = fma(tsm[c.vm + i * CPB], dp, JE(c, i, i));
+  if (lt.neq > 0) {                                            // RZeroSorb :4162-4178
+#pragma unroll 1
+    for (int k = c.l; k < lt.nsrf; k += G) GSL(S, RXN_F_EQSRFCPLX_CONC, k, cell) = 0.0;
+  }
+#pragma unroll 1
+  for (int task = 0; task < lt.neq + lt.nmr; ++task) {
+    const bool eq = task < lt.neq;
+    const int ikr = task - lt.neq;
+    int tb = bcol, ts = brow;
+    double fac = c.v_t;
+    if (!eq) {
+      tb = c.vseq + ikr * N * CPB; ts = CPB;
+      fac = c.volume * lt.mrK1[ikr];
+#pragma unroll 1
+      for (int i = c.l; i < n; i += G) tsm[tb + i * ts] = 0.0;
+    }
+    lane_srf_rxn<N, CPB, G>(lt, c, S, TI(lt, (eq ? lt.i_eq_rxn : lt.i_mr_rxn - lt.neq) + task), fac, true, eq, tb, ts);
+  }
+#pragma unroll 1
+  for (int i = c.l; i < n; i += G) {
+    const double tot = (tsm[c.vm + i * CPB] + tsm[c.vtot + i * CPB]) * c.den_kg_per_L;
+    GSL(S, RXN_F_TOTAL, i, cell) = tot;
+    double res = c.psv * tot;                                  // RTAccumulation :5072-5148
+    if (lt.neqsorb > 0) {
+      const double tsorb = tsm[bcol + i * brow];
+      GSL(S, RXN_F_TOTAL_SORB_EQ, i, cell) = tsorb;
+      res = res + tsorb * c.volume;                            // RAccumulationSorb :4539-4568
+    }
+    tsm[bcol + i * brow] = res / dt;
+  }
+  if (lt.nkin > 0) lane_kinetic_mineral<N, CPB, G>(lt, c);
+#pragma unroll 1
+  for (int ikr = 0; ikr < lt.nmr; ++ikr) {
+#pragma unroll 1
+    for (int i = c.l; i < n; i += G) {
+      tsm[bcol + i * brow] += c.volume * (lt.mrK1[ikr] * tsm[c.vseq + (ikr * N + i) * CPB] - tsm[c.vr0 + (ikr * N + i) * CPB]);
+      GSL(S, RXN_F_KINMR_TOTAL_SORB, (long long)ikr * (h.mr_ld + 1) * n + i, cell) = tsm[c.vseq + (ikr * N + i) * CPB];
+    }
+  }
+  grp_sync<G>(c.gm);
+  // outputs
+  if (res_out) {
+#pragma unroll 1
+    for (int i = c.l; i < n; i += G) res_out[item * n + i] = tsm[bcol + i * brow];
+  }
+  if (jac_out) {
+#pragma unroll 1
+    for (int j = c.l; j < n; j += G) tsm[c.vscr + j * CPB] = 1.0 / tsm[c.vm + j * CPB];
+    grp_sync<G>(c.gm);
+    double *jo = jac_out + item * (long long)(n * n);
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+      const double invm = tsm[c.vscr + j * CPB];
+#pragma unroll 2
+      for (int i = c.l; i < n; i += G) jo[i + j * n] = JE(c, i, j) * invm;
+    }
+  }
+#pragma unroll 4
+  for (int k = c.l; k < lt.ncplx; k += G) GSL(S, RXN_F_SEC_MOLAL, k, cell) = tsm[c.vsm + k * CPB];
+#pragma unroll 1
+  for (int q = c.l; q < lt.nrxn; q += G) GSL(S, RXN_F_FREE_SITE_CONC, q, cell) = tsm[c.vfree + q * CPB];
+#pragma unroll 1
+  for (int q = c.l; q < lt.nkin; q += G) GSL(S, RXN_F_MNRL_RATE, q, cell) = tsm[c.vmnrl + (2 * lt.nkin + q) * CPB];
   grp_sync<G>(c.gm);
 }
 

@@ -110,7 +110,49 @@ k_react_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab 
   }
 }
 
+// Global-implicit residual / Jacobian blocks: no Newton loop, every lane group takes cells base+s, base+s+grid*CPB, ...
+template <int N, int CPB, int G>
+__global__ void __launch_bounds__(((CPB * G + 31) / 32) * 32, 1)
+k_gi_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h, const double *__restrict__ pblob,
+          const double *__restrict__ blob, DevState S, const int32_t *__restrict__ l2g, long long nlocal, double dt, double *res_out,
+          double *jac_out) {
+  const int words = lt.blob_dbl + lt.blob_int / 2;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) tsm[w] = pblob[w];
+  __syncthreads();
+  const int t = threadIdx.x, ln = t & 31;
+  const int s = t / G, l = t % G;
+  const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (ln & ~(G - 1)));
+  const double *bd = blob;
+  const int *bi = reinterpret_cast<const int *>(blob + h.ndbl);
+  Lane<N, G> c;
+  lane_bind<N, CPB, G>(lt, c, s, l, gm);
+#pragma unroll 1
+  for (long long base = (long long)blockIdx.x * CPB; base < nlocal; base += (long long)gridDim.x * CPB) {
+    const long long item = base + s;
+    if (s < lt.cells && item < nlocal) {
+      const long long cell = l2g ? l2g[item] : item;
+      if (!(S.active && !S.active[cell])) lane_gi_cell<N, CPB, G>(lt, c, S, bd, bi, h, item, cell, dt, res_out, jac_out);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace lane
+
+template <>
+int lane_launch_gi_variant<LANE_N, LANE_CPB, LANE_G>(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob,
+                                                     const double *blob, const DevState &S, const int32_t *l2g, long long nlocal, double dt,
+                                                     double *res_out, double *jac_out, cudaStream_t stream) {
+  auto kern = lane::k_gi_lane<LANE_N, LANE_CPB, LANE_G>;
+  constexpr int threads = ((LANE_CPB * LANE_G + 31) / 32) * 32;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return RXN_ERR_CUDA;
+  int bps = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem_bytes) != cudaSuccess || bps < 1) bps = 1;
+  const long long want = (nlocal + LANE_CPB - 1) / LANE_CPB;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sm_count * bps));
+  kern<<<grid, threads, smem_bytes, stream>>>(lt, h, pblob, blob, S, l2g, nlocal, dt, res_out, jac_out);
+  return RXN_OK;
+}
 
 template <>
 int lane_launch_variant<LANE_N, LANE_CPB, LANE_G>(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob,

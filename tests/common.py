@@ -18,6 +18,20 @@ def rel_err(a, b, floor=1e-300):
     return np.abs(a - b) / np.maximum(np.abs(b), floor)
 
 
+def total_magnitude(st, tables, cells=None):
+    """m_i + sum_k |nu_ik| sec_molal_k, times den_kg*1e-3: the scale on which total_i (reaction.F90:4095-4124) carries
+    a relative perturbation of its terms when the stoichiometries change sign (H+).  [naq, ncells]"""
+    pick = (lambda a: a) if cells is None else (lambda a: a[:, cells])
+    mag = np.abs(pick(st['PRI_MOLAL'])).copy()
+    if tables.neqcplx:
+        ids, stc = np.asarray(tables.eqcplxspecid), np.asarray(tables.eqcplxstoich)
+        sm = pick(st['SEC_MOLAL'])
+        for k in range(tables.neqcplx):
+            for q in range(1, ids[k, 0] + 1):
+                mag[ids[k, q] - 1] += abs(stc[k, q]) * np.abs(sm[k])
+    return mag * pick(st['DEN_KG']) * 1.0e-3
+
+
 def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, what='', tables=None):
     for f in fields:
         a, b = st_a[f], st_b[f]

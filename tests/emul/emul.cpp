@@ -127,6 +127,60 @@ static void lane_cells(const LaneJob &J) {
   g_hg = nullptr;
   tsm = nullptr;
 }
+struct LaneGiJob {
+  const LanePlan *P; const Emu *e; DevState *S; const int32_t *l2g; int64_t nlocal; double dt; double *res, *jac;
+};
+template <int N, int G>
+static void lane_gi_thread(const LaneGiJob *J, LaneTab lt, int l) {
+  using namespace rxn::lane;
+  g_hl = l;
+  const DevTab &h = J->e->R.h;
+  const DevState &S = *J->S;
+  for (long long i = 0; i < J->nlocal; ++i) {
+    const long long cell = J->l2g ? J->l2g[i] : i;
+    if (S.active && !S.active[cell]) continue;
+    Lane<N, G> c;
+    lane_bind<N, 1, G>(lt, c, 0, l, 0u);
+    lane_gi_cell<N, 1, G>(lt, c, S, J->e->T.d, J->e->T.i, h, i, cell, J->dt, J->res, J->jac);
+  }
+}
+template <int N, int G>
+static void lane_gi_cells(const LaneGiJob &J) {
+  using namespace rxn::lane;
+  LaneTab lt = J.P->lt;
+  const DevTab &h = J.e->R.h;
+  for (int ikr = 0; ikr < lt.nmr && ikr < 2; ++ikr) {
+    double K1 = 0.0;
+    for (int irate = 0; irate < J.e->T.i[h.o_mr_nrate + ikr]; ++irate) {
+      const double rate = J.e->T.d[h.o_mr_rate + ikr * h.mr_ld + irate], frac = J.e->T.d[h.o_mr_frac + ikr * h.mr_ld + irate];
+      const double kdt = rate * J.dt;
+      const double one_plus_kdt = 1.0 + kdt;
+      const double kk = rate / one_plus_kdt;
+      K1 = K1 + kk * frac;
+    }
+    lt.mrK1[ikr] = K1;
+  }
+  std::vector<double> sm((size_t)lt.smem_dbl + 16, 0.0);
+  memcpy(sm.data(), J.P->blob.data(), J.P->blob.size());
+  tsm = sm.data();
+  HostGroup hg;
+  pthread_barrier_init(&hg.bar, nullptr, G);
+  g_hg = &hg;
+  std::vector<std::thread> th;
+  for (int l = 1; l < G; ++l) th.emplace_back(lane_gi_thread<N, G>, &J, lt, l);
+  lane_gi_thread<N, G>(&J, lt, 0);
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&hg.bar);
+  g_hg = nullptr;
+  tsm = nullptr;
+}
+template <int N>
+static void lane_gi_cells_g(const LaneGiJob &J, int G) {
+  if (G == 1) lane_gi_cells<N, 1>(J);
+  else if (G == 2) lane_gi_cells<N, 2>(J);
+  else lane_gi_cells<N, 4>(J);
+}
+
 template <int N>
 static void lane_cells_g(const LaneJob &J, int G) {
   if (G == 1) lane_cells<N, 1>(J);
@@ -191,6 +245,28 @@ int emu_react_lane(void *hh, const HostView *v, double *tran_xx, const uint8_t *
     case 15: lane_cells_g<15>(J, G); break;
     case 16: lane_cells_g<16>(J, G); break;
     default: lane_cells_g<24>(J, G); break;
+  }
+  return 0;
+}
+
+int emu_gi_lane(void *hh, const HostView *v, const uint8_t *active, const int32_t *l2g, int64_t nlocal, double dt, double *res_out,
+                double *jac_out, int G, char *err, int errlen) {
+  Emu *e = (Emu *)hh;
+  DevState S = mk_state(v, active);
+  LanePlan P;
+  const int N = lane_N_for(e->R.h.naq);
+  if (N == 0) { if (err) snprintf(err, errlen, "naq exceeds the compiled shapes"); return RXN_ERR_UNSUPPORTED; }
+  if (G != 1 && G != 2 && G != 4) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4"); return RXN_ERR_INVALID; }
+  int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P, true);
+  if (rc != RXN_OK || !P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
+  LaneGiJob J{&P, e, &S, l2g, nlocal, dt, res_out, jac_out};
+  switch (N) {
+    case 4: lane_gi_cells_g<4>(J, G); break;
+    case 8: lane_gi_cells_g<8>(J, G); break;
+    case 12: lane_gi_cells_g<12>(J, G); break;
+    case 15: lane_gi_cells_g<15>(J, G); break;
+    case 16: lane_gi_cells_g<16>(J, G); break;
+    default: lane_gi_cells_g<24>(J, G); break;
   }
   return 0;
 }

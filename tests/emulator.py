@@ -123,6 +123,20 @@ class Emulator:
                                                  _p(jac, C.c_double)) == 0
         return res, jac
 
+    def residual_jacobian_lane(self, st, dt, l2g=None, G=1):
+        """Global-implicit blocks through the resident-lane routines (rxn_lane_dev.cuh: lane_gi_cell)."""
+        n = st.ncells if l2g is None else len(l2g)
+        nc = self.t.ncomp
+        res = np.zeros((n, nc))
+        jac = np.zeros((n, nc * nc))
+        v = st.view()
+        buf = C.create_string_buffer(512)
+        rc = lib().emu_gi_lane(self.h, C.byref(v), _p(st.active, C.c_uint8), _p(l2g, C.c_int32), C.c_int64(n), C.c_double(dt),
+                               _p(res, C.c_double), _p(jac, C.c_double), C.c_int(G), buf, 512)
+        if rc != 0:
+            raise NotImplementedError(buf.value.decode())
+        return res, jac
+
     def update_kinetic_state(self, st, dt):
         v = st.view()
         assert lib().emu_update_kinetic_state_batch(self.h, C.byref(v), _p(st.active, C.c_uint8), C.c_double(dt)) == 0
