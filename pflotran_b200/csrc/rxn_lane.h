@@ -61,7 +61,8 @@ struct LaneTab {
   int jsink;            // J-region sink element (double index relative to 2*t) for padded plan-B closers
   // term streams
   LaneStream spec, planA, planB;
-  int d_coef, i_off;    // coef blocks (4 doubles per step, init block first) / offset blocks (4 ints per step)
+  int d_coef, i_off;    // coef blocks (4 doubles per step, init block first) / offset blocks (4 ints per step, BYTE offsets
+                        // into shared memory so that a gather address is one add: offset + 8*cell)
   // activity classes
   int d_cls_z2, d_cls_a0, d_pz2, d_cz2, i_pcls, i_ccls;
   int d_nlk;            // -logK*LOG_TO_LN for [complexes | minerals | surface complexes] (fixed logK)
@@ -355,7 +356,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
     const int ngroups = (int)ghdr.size() / 8;
     for (int g = 0; g < ngroups; ++g) {
       const int o0 = gh[g * 8 + 1], nsteps = gh[g * 8 + 2];
-      for (int q = 0; q < nsteps * 4; ++q) ti[lt.i_off + o0 * 4 + q] += lt.o_vec;
+      for (int q = 0; q < nsteps * 4; ++q) ti[lt.i_off + o0 * 4 + q] = (ti[lt.i_off + o0 * 4 + q] + lt.o_vec) * 8;   // byte offsets
     }
     auto fix_closers = [&](const LaneStream &S, int ndest) {
       for (int g = 0; g < S.ng; ++g) {

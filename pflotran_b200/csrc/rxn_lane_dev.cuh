@@ -58,6 +58,7 @@ static thread_local int g_hl = 0;
 #endif
 
 #define TSM2 (reinterpret_cast<double2 *>(tsm))
+#define TSB(ob) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(tsm) + (ob)))   /* byte offset */
 #define TD(lt, o) (tsm[(o)])
 #define TI(lt, o) (reinterpret_cast<const int *>(tsm)[2 * (lt).blob_dbl + (o)])
 #define TI4(lt, o4) (reinterpret_cast<const int4 *>(tsm)[((lt).blob_dbl >> 1) + (o4)])    /* o4 in units of 4 ints */
@@ -235,14 +236,15 @@ LANE_DEV void lane_act_coefs(const LaneTab &lt, Lane<N, G> &c) {
 #endif
 LANE_DEV void lane_run_group(const LaneTab &lt, int s, int c0, int o0, int nsteps, double &a0, double &a1, double &a2, double &a3) {
   constexpr int U = LANE_UNROLL;
+  const char *cell8 = reinterpret_cast<const char *>(tsm + s);   // a gather address is this + the record's byte offset
 #pragma unroll U
   for (int q = 0; q < nsteps; ++q) {
     const double2 ca = TD2(lt, (c0 + 1 + q) * 2), cb = TD2(lt, (c0 + 1 + q) * 2 + 1);
     const int4 of = TI4(lt, o0 + q);
-    a0 = fma(ca.x, tsm[of.x + s], a0);
-    a1 = fma(ca.y, tsm[of.y + s], a1);
-    a2 = fma(cb.x, tsm[of.z + s], a2);
-    a3 = fma(cb.y, tsm[of.w + s], a3);
+    a0 = fma(ca.x, *reinterpret_cast<const double *>(cell8 + of.x), a0);
+    a1 = fma(ca.y, *reinterpret_cast<const double *>(cell8 + of.y), a1);
+    a2 = fma(cb.x, *reinterpret_cast<const double *>(cell8 + of.z), a2);
+    a3 = fma(cb.y, *reinterpret_cast<const double *>(cell8 + of.w), a3);
   }
 }
 

@@ -32,7 +32,37 @@ def total_magnitude(st, tables, cells=None):
     return mag * pick(st['DEN_KG']) * 1.0e-3
 
 
-def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, what='', tables=None):
+def residual_scale(st, tables, r_o, a_o, dt):
+    """Scale of the global-implicit residual block: res = accumulation/dt + sum_m nu_im Im_m V (reaction.F90:5072-5148,
+    reaction_mineral.F90:795-830).  Near equilibrium accumulation/dt and the mineral terms cancel, and Im = -area k (1-QK)
+    itself is a difference: a relative perturbation eps of the inputs moves the residual by
+    eps * (|accumulation/dt| + sum_m |nu_im| area_m |k_m| V).  [ncells, ncomp]"""
+    sc = np.maximum(np.abs(r_o), np.abs(a_o) / dt)
+    if tables.nkinmnrl:
+        ids, stc = np.asarray(tables.kinmnrlspecid), np.asarray(tables.kinmnrlstoich)
+        kk = np.abs(np.asarray(tables.kinmnrl_rate_constant))
+        mn = np.zeros_like(sc)
+        for m in range(tables.nkinmnrl):
+            for q in range(1, ids[m, 0] + 1):
+                mn[:, ids[m, q] - 1] += abs(stc[m, q - 1 if stc.shape[1] < ids.shape[1] else q]) * st['MNRL_AREA'][m] * kk[m] * st['VOLUME'][0]
+        sc = np.maximum(sc, mn)
+    return np.maximum(sc, 1e-12 * np.abs(r_o).max(axis=1, keepdims=True))
+
+
+def jacobian_scale(st, j_o, ncomp):
+    """Scale of the entries of a Jacobian block (column-major, d/dm_j): the Newton solve works on the block with column j
+    times m_j and every row divided by its maximum (RSolve, reaction.F90:4851-4870), so an entry matters relative to
+    the largest |J_ij'| m_j' of its row: scale_ij = max(|J_ij|, max_j'(|J_ij'| m_j') / m_j).  Entries far below that are
+    differences of the accumulation and kinetic derivative terms (they cancel near equilibrium).  [ncells, ncomp^2]"""
+    n = j_o.shape[0]
+    J = np.abs(j_o).reshape(n, ncomp, ncomp).transpose(0, 2, 1)          # [cell, i, j]
+    m = np.abs(st['PRI_MOLAL']).T[:, None, :]                             # [cell, 1, j]
+    rowmax = (J * m).max(axis=2, keepdims=True)
+    sc = np.maximum(J, rowmax / np.maximum(m, 1e-300))
+    return sc.transpose(0, 2, 1).reshape(n, ncomp * ncomp)
+
+
+def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, what='', tables=None, kinetic_dt=None):
     for f in fields:
         a, b = st_a[f], st_b[f]
         if not a.size:
@@ -57,6 +87,11 @@ def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, w
             # relative perturbation eps of the molalities moves the rate by ~eps*area*k*QK*sum|nu|, not eps*|rate|
             area = st_b['MNRL_AREA'] if cells is None else st_b['MNRL_AREA'][:, cells]
             scale = np.maximum(scale, area * np.abs(np.asarray(tables.kinmnrl_rate_constant))[:, None])
+        if f == 'MNRL_VOLFRAC' and tables is not None and kinetic_dt is not None:
+            # after RUpdateKineticState: volfrac += rate*molar_vol*dt (reaction.F90:5354-5364) with rate on the scale area*k
+            area = st_b['MNRL_AREA'] if cells is None else st_b['MNRL_AREA'][:, cells]
+            scale = np.maximum(scale, area * (np.abs(np.asarray(tables.kinmnrl_rate_constant)) *
+                                              np.abs(np.asarray(tables.kinmnrl_molar_vol)))[:, None] * kinetic_dt)
         err = np.abs(a - b) / np.maximum(scale, 1e-300)
         bad = ~(err <= rtol) & ~((a == b) | (np.isnan(a) & np.isnan(b)))
         assert not bad.any(), '%s field %s: max rel err %.3e at %s' % (what, f, np.nanmax(err), np.argwhere(bad)[:3])

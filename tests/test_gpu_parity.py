@@ -6,7 +6,7 @@ import pytest
 
 from pflotran_b200 import abi, synth, reactive_transport as rt
 from oracle.pyoracle import Oracle
-from common import assert_state_close, workload_cells, RTOL, rel_err, total_magnitude
+from common import assert_state_close, workload_cells, RTOL, rel_err, total_magnitude, residual_scale, jacobian_scale
 
 pytestmark = pytest.mark.gpu
 
@@ -93,16 +93,14 @@ def test_global_implicit_entry_points(name):
     assert (np.abs(a_g - a_o) / np.maximum(a_scale, 1e-300)).max() <= RTOL
     r_o, j_o = orc.residual_jacobian(st_o, 1800.0, nthreads=8)
     r_g, j_g = rz.RTResidualJacobianNonFlux(1800.0)
-    # residual = accumulation/dt + kinetic terms (reaction.F90:5072-5148, reaction_mineral.F90:816-830): near equilibrium the two
-    # cancel, so a relative perturbation eps of either moves the residual by eps*|accumulation/dt|: compare on that scale
-    rs = np.maximum(np.maximum(np.abs(r_o), np.abs(a_o) / 1800.0), 1e-12 * np.abs(r_o).max(axis=1, keepdims=True))
+    rs = residual_scale(st_o, w.tables, r_o, a_o, 1800.0)
     assert (np.abs(r_g - r_o) / np.maximum(rs, 1e-300)).max() <= RTOL
-    js = np.maximum(np.abs(j_o), 1e-12 * np.abs(j_o).max(axis=1, keepdims=True))
+    js = jacobian_scale(st_o, j_o, w.ncomp)
     assert (np.abs(j_g - j_o) / np.maximum(js, 1e-300)).max() <= RTOL
     orc.update_kinetic_state(st_o, 1800.0, nthreads=8)
     rz.RTUpdateKineticState(1800.0)
     rz.download_host_state(st_g)
-    assert_state_close(st_g, st_o, what=name + ' RTUpdateKineticState', tables=w.tables)
+    assert_state_close(st_g, st_o, what=name + ' RTUpdateKineticState', tables=w.tables, kinetic_dt=1800.0)
 
 
 def test_state_roundtrip_layouts():
