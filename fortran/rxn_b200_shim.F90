@@ -134,7 +134,7 @@ module Rxn_B200_module
             rxn_state_download, rxn_state_broadcast, rxn_set_cell_scalars, rxn_react_batch, &
             rxn_update_auxvars_batch, rxn_fixed_accum_batch, rxn_residual_blocks_batch, &
             rxn_jacobian_blocks_batch, rxn_residual_jacobian_blocks_batch, &
-            rxn_update_kinetic_state_batch, rxn_last_kernel_ms, rxn_last_error
+            rxn_update_kinetic_state_batch, rxn_equilibrate_constraint_batch, rxn_last_kernel_ms, rxn_last_error
 
   interface
 
@@ -271,6 +271,26 @@ module Rxn_B200_module
       import :: c_int, c_double, c_ptr
       type(c_ptr), value :: state
       real(c_double), value :: dt
+    end function
+
+    ! replaces: ReactionEquilibrateConstraint (reaction.F90:1308-2046) cell by cell
+    ! (CondControlAssignTranInitCond condition_control.F90:725-741, PatchInitCouplerConstraints patch.F90:3346-3461)
+    integer(c_int) function rxn_equilibrate_constraint_batch(state, constraint_type, constraint_conc, conc_stride, &
+                                                             constraint_id, free_ion_guess, use_prev_soln_as_guess, &
+                                                             initialize_with_molality, l2g, nlocal, basis_molarity_out, &
+                                                             iters_out, status_out) &
+        bind(C, name='rxn_equilibrate_constraint_batch')
+      import :: c_int, c_int32_t, c_int64_t, c_ptr
+      type(c_ptr), value :: state
+      type(c_ptr), value :: constraint_type      ! integer(c_int32_t) (naqcomp): aq_species_constraint%constraint_type
+      type(c_ptr), value :: constraint_conc      ! real(c_double) (naqcomp) or (conc_stride, nlocal)
+      integer(c_int64_t), value :: conc_stride   ! 0: one constraint for all cells
+      type(c_ptr), value :: constraint_id        ! integer(c_int32_t) (naqcomp): constraint_spec_id (1-based mineral / gas id)
+      type(c_ptr), value :: free_ion_guess       ! real(c_double) (naqcomp) or c_null_ptr
+      integer(c_int), value :: use_prev_soln_as_guess, initialize_with_molality
+      type(c_ptr), value :: l2g                  ! integer(c_int32_t) (nlocal) ghosted id - 1, or c_null_ptr
+      integer(c_int64_t), value :: nlocal
+      type(c_ptr), value :: basis_molarity_out, iters_out, status_out
     end function
 
     real(c_float) function rxn_last_kernel_ms(state) bind(C, name='rxn_last_kernel_ms')

@@ -236,9 +236,28 @@ int rxn_state_materialize(RxnState *s, int field);
  * 3 = resident-lane (cell state in shared memory, persistent lanes); 2 and 3 fail if the tables do not fit them.
  * Benchmark / test control only; results are the same path. */
 int rxn_set_react_kernel(RxnState *s, int which);
+/* constraint types of ReactionEquilibrateConstraint (transport_constraint.F90:217-330, reaction_aux.F90 CONSTRAINT_*) */
+enum { RXN_CONSTRAINT_NULL = 0, RXN_CONSTRAINT_FREE = 1, RXN_CONSTRAINT_TOTAL = 2, RXN_CONSTRAINT_LOG = 3, RXN_CONSTRAINT_PH = 4,
+       RXN_CONSTRAINT_MINERAL = 5, RXN_CONSTRAINT_GAS = 6, RXN_CONSTRAINT_CHARGE_BAL = 7, RXN_CONSTRAINT_TOTAL_SORB = 9 };
+/* per-cell status of rxn_equilibrate_constraint_batch: 0 converged; the others are the reference's fatal errors */
+enum { RXN_EQ_OK = 0, RXN_EQ_NO_H_ION = 2, RXN_EQ_BAD_CONSTRAINT = 3, RXN_EQ_LU_ZERO_ROW = 4, RXN_EQ_ZERO_CONCENTRATION = 5,
+       RXN_EQ_NOT_CONVERGED = 6 };
+
 /* one-line description of the kernel rxn_react_batch would launch for this state (shape, shared memory) */
 int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len);
 int32_t rxn_field_rows(const RxnTables *t, int field);
+
+/* replaces: ReactionEquilibrateConstraint (reaction.F90:1308-2046) applied cell by cell: initial / boundary condition
+ * speciation (CondControlAssignTranInitCond condition_control.F90:725-741, PatchInitCouplerConstraints patch.F90:3346-3461).
+ * One constraint for all cells (conc_stride = 0) or one concentration row per cell (conc_stride = naqcomp, dataset-driven
+ * conditions); constraint_type / constraint_id [naqcomp] (RXN_CONSTRAINT_*, 1-based mineral / gas ids); free_ion_guess
+ * [naqcomp] or NULL.  The cell state (den_kg, temp, mineral volume fractions, ...) must be set; on return it holds the
+ * equilibrated pri_molal, activity coefficients, totals, sorbed state and the multirate sorbed totals.
+ * basis_molarity_out [nlocal][naqcomp] (or NULL), iters_out / status_out [nlocal] (or NULL). */
+int rxn_equilibrate_constraint_batch(RxnState *s, const int32_t *constraint_type, const double *constraint_conc, int64_t conc_stride,
+                                     const int32_t *constraint_id, const double *free_ion_guess, int use_prev_soln_as_guess,
+                                     int initialize_with_molality, const int32_t *l2g, int64_t nlocal, double *basis_molarity_out,
+                                     int32_t *iters_out, int32_t *status_out);
 
 /* replaces: direct field access by PatchGetVariable (patch.F90:3529-4788), checkpoint
  * (pm_rt.F90:1159-1305) and CondControlAssignTranInitCond (condition_control.F90:498-949).

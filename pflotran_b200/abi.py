@@ -20,6 +20,8 @@ RXN_DT_AS_WRITTEN, RXN_DT_CONSISTENT = 0, 1
 RXN_EXIT_RESIDUAL, RXN_EXIT_REL_CHANGE = 1, 2
 RXN_FLAG_CAPPED, RXN_FLAG_LU_ZERO_ROW, RXN_FLAG_ACT_DIVERGED, RXN_FLAG_NONFINITE, RXN_FLAG_INACTIVE = \
     1 << 8, 1 << 9, 1 << 10, 1 << 11, 1 << 12
+# per-cell status of rxn_equilibrate_constraint_batch / constraint types (include/rxn_b200.h)
+RXN_EQ_OK, RXN_EQ_NO_H_ION, RXN_EQ_BAD_CONSTRAINT, RXN_EQ_LU_ZERO_ROW, RXN_EQ_ZERO_CONCENTRATION, RXN_EQ_NOT_CONVERGED = 0, 2, 3, 4, 5, 6
 
 FIELDS = [
     'PRI_MOLAL', 'TOTAL', 'SEC_MOLAL', 'PRI_ACT_COEF', 'SEC_ACT_COEF', 'LN_ACT_H2O',

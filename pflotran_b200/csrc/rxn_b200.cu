@@ -545,6 +545,57 @@ int rxn_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, d
   return rxn_residual_jacobian_blocks_batch(s, l2g, nlocal, dt, nullptr, jac_out);
 }
 
+int rxn_equilibrate_constraint_batch(RxnState *s, const int32_t *constraint_type, const double *constraint_conc, int64_t conc_stride,
+                                     const int32_t *constraint_id, const double *free_ion_guess, int use_prev_soln_as_guess,
+                                     int initialize_with_molality, const int32_t *l2g, int64_t nlocal, double *basis_molarity_out,
+                                     int32_t *iters_out, int32_t *status_out) {
+  if (!s || !constraint_type || !constraint_conc || !constraint_id || nlocal < 0) return fail(RXN_ERR_INVALID, "bad argument");
+  const RxnTables *t = s->t;
+  const int n = t->h.naq;
+  if (conc_stride != 0 && conc_stride < n) return fail(RXN_ERR_INVALID, "conc_stride must be 0 or >= naqcomp");
+  if (nlocal == 0) return RXN_OK;
+  for (int i = 0; i < n; ++i) {
+    if (constraint_type[i] == RXN_CONSTRAINT_MINERAL && (constraint_id[i] < 1 || constraint_id[i] > t->h.mnrl.n))
+      return fail(RXN_ERR_INVALID, "constraint %d: mineral id %d out of range", i + 1, constraint_id[i]);
+    if (constraint_type[i] == RXN_CONSTRAINT_GAS && (constraint_id[i] < 1 || constraint_id[i] > t->h.gas.n))
+      return fail(RXN_ERR_INVALID, "constraint %d: gas id %d out of range", i + 1, constraint_id[i]);
+  }
+  CU(cudaSetDevice(t->device));
+  // scratch 0: [conc | basis]   scratch 1: l2g   scratch 2: [ctype | cid | iters | status]   scratch 3: guess
+  const size_t nconc = conc_stride ? (size_t)nlocal * conc_stride : (size_t)n;
+  void *d_dbl, *d_l2g = nullptr, *d_int, *d_guess = nullptr;
+  int rc;
+  if ((rc = ensure_scratch(s, 0, (nconc + (size_t)nlocal * n) * 8, &d_dbl)) != RXN_OK) return rc;
+  if ((rc = ensure_scratch(s, 2, ((size_t)2 * n + 2 * (size_t)nlocal) * 4, &d_int)) != RXN_OK) return rc;
+  double *d_conc = (double *)d_dbl, *d_basis = d_conc + nconc;
+  int32_t *d_ctype = (int32_t *)d_int, *d_cid = d_ctype + n, *d_it = d_cid + n, *d_st = d_it + nlocal;
+  CU(cudaMemcpyAsync(d_conc, constraint_conc, nconc * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_ctype, constraint_type, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_cid, constraint_id, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+  if (free_ion_guess) {
+    if ((rc = ensure_scratch(s, 3, (size_t)n * 8, &d_guess)) != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(d_guess, free_ion_guess, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+  }
+  if (l2g) {
+    if ((rc = ensure_scratch(s, 1, (size_t)nlocal * 4, &d_l2g)) != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
+  }
+  CU(cudaEventRecord(s->ev0, s->stream));
+  const int threads = t->nvariant <= 8 ? 128 : 64;
+  const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
+  RXN_DISPATCH(t->nvariant, run_equilibrate, L, t->h, (const double *)t->d_blob, s->S, (const int *)d_ctype, (const double *)d_conc,
+               (long long)conc_stride, (const int *)d_cid, (const double *)d_guess, use_prev_soln_as_guess, initialize_with_molality,
+               (const int *)d_l2g, (long long)nlocal, d_basis, (int *)d_it, (int *)d_st);
+  CU(cudaEventRecord(s->ev1, s->stream));
+  if (basis_molarity_out) CU(cudaMemcpyAsync(basis_molarity_out, d_basis, (size_t)nlocal * n * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (iters_out) CU(cudaMemcpyAsync(iters_out, d_it, (size_t)nlocal * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (status_out) CU(cudaMemcpyAsync(status_out, d_st, (size_t)nlocal * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+  return RXN_OK;
+}
+
 int rxn_update_kinetic_state_batch(RxnState *s, double dt) {
   if (!s || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(s->t->device));

@@ -977,4 +977,209 @@ __device__ void cell_update_kinetic_state(const Tab &T, const DevState &S, long 
   }
 }
 
+// RTotalSorbMultiRateAsEQ — reaction_surf_complex.F90:506-562
+template <int N>
+__device__ void rtotal_sorb_multirate_as_eq(const Tab &T, const DevState &S, Cell<N> &c, double *scratch_dsorb) {
+  const DevTab &h = *T.h;
+  const int naq = h.naq;
+  double total_sorb_eq[N];
+  for (int ikr = 0; ikr < h.nmr; ++ikr) {
+    const int irxn = T.i[h.o_mr_rxn + ikr];
+    for (int i = 0; i < naq; ++i) total_sorb_eq[i] = 0.0;
+    for (int e = 0; e < naq * naq; ++e) scratch_dsorb[e] = 0.0;
+    sorb_eq_surfcplx1<N>(T, S, c, irxn, false, total_sorb_eq, scratch_dsorb);
+    const long long row0 = (long long)ikr * (h.mr_ld + 1) * naq;
+    for (int i = 0; i < naq; ++i) G(S, RXN_F_KINMR_TOTAL_SORB, row0 + i, c.cell) = total_sorb_eq[i];
+  }
+}
+
+// ln(Q/K) of a mineral / gas of the constraint lists at the stored logK (reaction.F90:1730-1790)
+template <int N>
+__device__ double constraint_lnQK(const Tab &T, const DSpec &sp, int r, const Cell<N> &c, double *Jrow, int naq, bool fill) {
+  double lnQK = -T.d[sp.o_logK + r] * RXN_LOG_TO_LN;
+  const double h2ost = T.d[sp.o_h2ost + r];
+  if (h2ost != 0.0) lnQK = lnQK + h2ost * c.ln_act_h2o;
+  for (int p = T.i[sp.o_ptr + r]; p < T.i[sp.o_ptr + r + 1]; ++p) {
+    const int j = T.i[sp.o_id + p];
+    lnQK = lnQK + T.d[sp.o_st + p] * log(c.m[j] * c.gam[j]);
+  }
+  if (fill)
+    for (int p = T.i[sp.o_ptr + r]; p < T.i[sp.o_ptr + r + 1]; ++p) {
+      const int j = T.i[sp.o_id + p];
+      Jrow[(size_t)j * naq] = T.d[sp.o_st + p] / c.m[j];
+    }
+  return lnQK;
+}
+
+// ReactionEquilibrateConstraint — reaction.F90:1308-2046, one cell.  Returns RXN_EQ_*.
+template <int N>
+__device__ int cell_equilibrate(const Tab &T, const DevState &S, long long cell, const int *constraint_type, const double *conc_in,
+                                const int *constraint_id, const double *free_ion_guess, int use_prev, int init_molal,
+                                double *basis_molarity, int *num_iterations_out) {
+  const DevTab &h = *T.h;
+  const int naq = h.naq;
+  const double *Z = T.d + h.o_Z;
+  Cell<N> c;
+  load_cell<N>(T, S, cell, c);
+  double conc[N], Res[N], total_conc[N], free_conc[N], prev_molal[N];
+  double Jac[N * N], dsorb[N * N], dtot[N * N];
+  double convert_molal_to_molar, convert_molar_to_molal;
+  const double xmass = 1.0;
+  if (init_molal) { convert_molal_to_molar = c.den_kg * xmass / 1000.0; convert_molar_to_molal = 1.0; }
+  else { convert_molal_to_molar = 1.0; convert_molar_to_molal = 1000.0 / c.den_kg / xmass; }
+  for (int i = 0; i < naq; ++i) {
+    conc[i] = conc_in[i];
+    total_conc[i] = 0.0;
+    free_conc[i] = use_prev ? c.m[i] : (free_ion_guess ? free_ion_guess[i] : 1.0e-9);
+  }
+  for (int i = 0; i < naq; ++i) {                                     // :1409-1470
+    switch (constraint_type[i]) {
+      case RXN_CONSTRAINT_NULL: case RXN_CONSTRAINT_TOTAL: total_conc[i] = conc[i] * convert_molal_to_molar; break;
+      case RXN_CONSTRAINT_TOTAL_SORB: total_conc[i] = conc[i]; break;
+      case RXN_CONSTRAINT_FREE: free_conc[i] = conc[i] * convert_molar_to_molal; break;
+      case RXN_CONSTRAINT_LOG: free_conc[i] = pow(10.0, conc[i]) * convert_molar_to_molal; break;
+      case RXN_CONSTRAINT_CHARGE_BAL: if (!use_prev) free_conc[i] = conc[i] * convert_molar_to_molal; break;
+      case RXN_CONSTRAINT_PH:
+        if (h.h_ion_id == 0) return RXN_EQ_NO_H_ION;
+        free_conc[i] = pow(10.0, -conc[i]);
+        break;
+      case RXN_CONSTRAINT_MINERAL: if (!use_prev) free_conc[i] = conc[i] * convert_molar_to_molal; break;
+      case RXN_CONSTRAINT_GAS: if (conc[i] <= 0.0) conc[i] = pow(10.0, conc[i]); break;
+      default: return RXN_EQ_BAD_CONSTRAINT;
+    }
+  }
+  for (int i = 0; i < naq; ++i) c.m[i] = free_conc[i];
+  int num_iterations = 0, num_it_act_coef_turned_on = 0;
+  bool compute_activity_coefs = use_prev != 0;
+  bool charge_balance_warning_flag = false;
+  for (;;) {                                                            // :1553-1990
+    for (int i = 0; i < naq; ++i)
+      if (constraint_type[i] == RXN_CONSTRAINT_FREE || constraint_type[i] == RXN_CONSTRAINT_LOG) c.m[i] = free_conc[i];
+    if (h.act_freq != RXN_ACT_COEF_FREQUENCY_OFF && compute_activity_coefs) activity_coefficients<N>(T, S, c);
+    compute_ln<N>(T, c);
+    rtotal<N>(T, S, c, dtot);
+    if (h.neqsorb + h.nmr > 0) {
+      if (h.neqsorb > 0) rtotal_sorb<N>(T, S, c, dsorb);
+      if (h.nmr > 0) rtotal_sorb_multirate_as_eq<N>(T, S, c, Jac);      // Jac is free here: scratch
+    }
+    for (int e = 0; e < naq * naq; ++e) Jac[e] = 0.0;
+#define JAC(i, j) Jac[(i) + (size_t)(j) * naq]
+    for (int icomp = 0; icomp < naq; ++icomp) {
+      switch (constraint_type[icomp]) {
+        case RXN_CONSTRAINT_NULL: case RXN_CONSTRAINT_TOTAL:
+          Res[icomp] = c.total[icomp] - total_conc[icomp];
+          for (int j = 0; j < naq; ++j) JAC(icomp, j) = dtot[icomp + (size_t)j * naq];
+          break;
+        case RXN_CONSTRAINT_TOTAL_SORB:
+          Res[icomp] = c.tsorb[icomp] - total_conc[icomp];
+          for (int j = 0; j < naq; ++j) JAC(icomp, j) = dsorb[icomp + (size_t)j * naq];
+          break;
+        case RXN_CONSTRAINT_FREE: case RXN_CONSTRAINT_LOG:
+          Res[icomp] = 0.0;
+          JAC(icomp, icomp) = 1.0;
+          break;
+        case RXN_CONSTRAINT_CHARGE_BAL:
+          Res[icomp] = 0.0;
+          for (int jcomp = 0; jcomp < naq; ++jcomp) {
+            Res[icomp] = Res[icomp] + Z[jcomp] * c.total[jcomp];
+            for (int kcomp = 0; kcomp < naq; ++kcomp)
+              JAC(icomp, jcomp) = JAC(icomp, jcomp) + Z[kcomp] * dtot[kcomp + (size_t)jcomp * naq];
+          }
+          if (c.m[icomp] < 1.0e-20 && !charge_balance_warning_flag) {
+            if ((Res[icomp] > 0.0 && Z[icomp] > 0.0) || (Res[icomp] < 0.0 && Z[icomp] < 0.0)) {
+              charge_balance_warning_flag = true;
+              c.m[icomp] = (double)1.e-3f;                              // the reference literal is single precision
+            }
+          }
+          break;
+        case RXN_CONSTRAINT_PH:
+          Res[icomp] = 0.0;
+          if (h.h_ion_id > 0) {
+            c.m[icomp] = pow(10.0, -conc[icomp]) / c.gam[icomp];
+            JAC(icomp, icomp) = 1.0;
+          } else {
+            const int icplx = -h.h_ion_id - 1;
+            double lnQK = -logK_of(T, h.cplx, icplx, c, false) * RXN_LOG_TO_LN;
+            const double h2ost = T.d[h.cplx.o_h2ost + icplx];
+            if (h2ost != 0.0) lnQK = lnQK + h2ost * c.ln_act_h2o;
+            for (int p = T.i[h.cplx.o_ptr + icplx]; p < T.i[h.cplx.o_ptr + icplx + 1]; ++p) {
+              const int j = T.i[h.cplx.o_id + p];
+              lnQK = lnQK + T.d[h.cplx.o_st + p] * log(c.m[j] * c.gam[j]);
+            }
+            lnQK = lnQK + conc[icomp] * RXN_LOG_TO_LN;
+            const double QK = exp(lnQK);
+            Res[icomp] = 1.0 - QK;
+            for (int p = T.i[h.cplx.o_ptr + icplx]; p < T.i[h.cplx.o_ptr + icplx + 1]; ++p) {
+              const int j = T.i[h.cplx.o_id + p];
+              JAC(icomp, j) = -QK / c.m[j] * T.d[h.cplx.o_st + p];
+            }
+          }
+          break;
+        case RXN_CONSTRAINT_MINERAL:
+          Res[icomp] = constraint_lnQK<N>(T, h.mnrl, constraint_id[icomp] - 1, c, &JAC(icomp, 0), naq, true);
+          break;
+        case RXN_CONSTRAINT_GAS:
+          Res[icomp] = constraint_lnQK<N>(T, h.gas, constraint_id[icomp] - 1, c, &JAC(icomp, 0), naq, true) - log(conc[icomp]);
+          break;
+      }
+    }
+#undef JAC
+    double maximum_residual = 0.0;
+    for (int i = 0; i < naq; ++i) maximum_residual = fmax(maximum_residual, fabs(Res[i]));
+    bool use_log_formulation;
+    if (h.use_log) {                                                    // :1900-1912
+      if (num_iterations > 3 && num_iterations < 9) use_log_formulation = (num_iterations % 2 == 0);
+      else use_log_formulation = true;
+    } else {
+      use_log_formulation = false;
+    }
+    if (rsolve<N>(Res, Jac, c.m, naq, use_log_formulation)) return RXN_EQ_LU_ZERO_ROW;
+    double *update = Res;
+    for (int i = 0; i < naq; ++i) prev_molal[i] = c.m[i];
+    if (use_log_formulation) {
+      for (int i = 0; i < naq; ++i) update[i] = copysign(1.0, update[i]) * fmin(fabs(update[i]), h.max_dlnC);
+      for (int i = 0; i < naq; ++i) c.m[i] = c.m[i] * exp(-update[i]);
+    } else {
+      double min_ratio = 1.0e20;
+      for (int i = 0; i < naq; ++i) {
+        if (prev_molal[i] <= update[i]) {
+          const double ratio = fabs(prev_molal[i] / update[i]);
+          if (ratio < min_ratio) min_ratio = ratio;
+        }
+      }
+      if (min_ratio <= 1.0) for (int i = 0; i < naq; ++i) update[i] = update[i] * min_ratio * 0.99;
+      for (int i = 0; i < naq; ++i) c.m[i] = prev_molal[i] - update[i];
+    }
+    double mn = c.m[0];
+    for (int i = 1; i < naq; ++i) mn = fmin(mn, c.m[i]);
+    if (!(mn > 0.0)) return RXN_EQ_ZERO_CONCENTRATION;                  // "Zero concentrations found in constraint"
+    double maximum_relative_change = 0.0;
+    for (int i = 0; i < naq; ++i) maximum_relative_change = fmax(maximum_relative_change, fabs((c.m[i] - prev_molal[i]) / prev_molal[i]));
+    num_iterations = num_iterations + 1;
+    if (num_iterations >= 10000) return RXN_EQ_NOT_CONVERGED;
+    if (maximum_residual < h.res_tol && maximum_relative_change < h.rel_tol) {
+      if (compute_activity_coefs && num_iterations - num_it_act_coef_turned_on > 1) break;
+      if (!compute_activity_coefs) num_it_act_coef_turned_on = num_iterations;
+      compute_activity_coefs = true;
+    }
+  }
+  if (h.neqsorb + h.nmr > 0) {                                          // :1995-2012
+    if (h.neqsorb > 0) rtotal_sorb<N>(T, S, c, dsorb);
+    if (h.nmr > 0) rtotal_sorb_multirate_as_eq<N>(T, S, c, Jac);
+  }
+  for (int ikr = 0; ikr < h.nmr; ++ikr) {                               // :2014-2026
+    const long long blk = (long long)ikr * (h.mr_ld + 1) * naq;
+    const int nrate = T.i[h.o_mr_nrate + ikr];
+    for (int irate = 0; irate < nrate; ++irate) {
+      const double frac = T.d[h.o_mr_frac + ikr * h.mr_ld + irate];
+      for (int i = 0; i < naq; ++i)
+        G(S, RXN_F_KINMR_TOTAL_SORB, blk + (long long)(irate + 1) * naq + i, cell) = frac * G(S, RXN_F_KINMR_TOTAL_SORB, blk + i, cell);
+    }
+  }
+  if (basis_molarity) for (int i = 0; i < naq; ++i) basis_molarity[i] = c.m[i] * c.den_kg / 1000.0;
+  *num_iterations_out = num_iterations;
+  store_cell<N>(T, S, c, nullptr, nullptr);
+  return RXN_EQ_OK;
+}
+
 }  // namespace rxn

@@ -149,6 +149,9 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
                             im + 1, ip + 1, row[k]);
         }
   }
+  RXN_TRY(pack_spec(R, d->mnrl, 0, naq, h.mnrl, "mineral"));
+  RXN_TRY(pack_spec(R, d->paseq, 0, naq, h.gas, "passive gas"));
+  h.h_ion_id = d->h_ion_id;
   RXN_TRY(pack_spec(R, d->srfcplx, h.ncoef, naq, h.srf, "surface complex"));
   h.o_srf_site_st = P.D(d->srfcplx_free_site_stoich, h.nsrf);
   h.o_rxn_to_surf = P.I(d->srfcplxrxn_to_surf, h.nrxn); h.o_rxn_surf_type = P.I(d->srfcplxrxn_surf_type, h.nrxn);

@@ -28,6 +28,8 @@ struct DevTab {
   int ndbl, nint;   // blob sizes
   double debyeA, debyeB, debyeBdot, max_dlnC, rel_tol, res_tol;
   DSpec cplx, kin, srf;
+  DSpec mnrl, gas;  // all minerals / passive gases: constraint equilibration only (logK at the reference temperature)
+  int h_ion_id;     // species_idx%h_ion_id: > 0 primary, < 0 complex, 0 none
   int o_Z, o_a0, o_cplxZ, o_cplxa0;                                        // dbl
   int o_k_rate, o_k_Ea, o_k_molar_vol, o_k_aff, o_k_lim, o_k_Temkin, o_k_scale, o_k_power;  // dbl [nkin]
   int o_k_npref;                                                            // int [nkin]

@@ -66,6 +66,28 @@ k_update_kinetic_state(const __grid_constant__ DevTab tab, const double *__restr
   if (cell < S.ncells) cell_update_kinetic_state<N>(T, S, cell, dt);
 }
 
+// ReactionEquilibrateConstraint applied cell by cell (reaction.F90:1308-2046; condition_control.F90:725-741)
+template <int N>
+__global__ void __launch_bounds__(128)
+k_equilibrate(const __grid_constant__ DevTab tab, const double *__restrict__ blob, DevState S, const int *__restrict__ ctype,
+              const double *__restrict__ conc, long long conc_stride, const int *__restrict__ cid, const double *__restrict__ guess,
+              int use_prev, int init_molal, const int *__restrict__ l2g, long long nlocal, double *basis_out, int *iters, int *status) {
+  Tab T = stage_tables(tab, blob);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  const long long cell = l2g ? l2g[i] : i;
+  if (S.active && !S.active[cell]) {
+    if (iters) iters[i] = 0;
+    if (status) status[i] = RXN_EQ_OK;
+    return;
+  }
+  int nit = 0;
+  const int rc = cell_equilibrate<N>(T, S, cell, ctype, conc + i * conc_stride, cid, guess, use_prev, init_molal,
+                                     basis_out ? basis_out + i * tab.naq : nullptr, &nit);
+  if (iters) iters[i] = nit;
+  if (status) status[i] = rc;
+}
+
 template <class K>
 static void set_smem(K kernel, size_t smem) {
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -94,6 +116,14 @@ template <> void run_residual_jacobian<RXN_N>(LaunchCfg L, const DevTab &tab, co
 template <> void run_update_kinetic_state<RXN_N>(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S, double dt) {
   set_smem(k_update_kinetic_state<RXN_N>, L.smem);
   k_update_kinetic_state<RXN_N><<<L.grid, L.block, L.smem, L.stream>>>(tab, blob, S, dt);
+}
+
+template <> void run_equilibrate<RXN_N>(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S, const int *ctype,
+                                        const double *conc, long long conc_stride, const int *cid, const double *guess, int use_prev,
+                                        int init_molal, const int *l2g, long long nlocal, double *basis_out, int *iters, int *status) {
+  set_smem(k_equilibrate<RXN_N>, L.smem);
+  k_equilibrate<RXN_N><<<L.grid, L.block, L.smem, L.stream>>>(tab, blob, S, ctype, conc, conc_stride, cid, guess, use_prev, init_molal,
+                                                           l2g, nlocal, basis_out, iters, status);
 }
 
 }  // namespace rxn

@@ -56,6 +56,8 @@ def lib():
         L.rxn_state_materialize.argtypes = [C.c_void_p, C.c_int]
         L.rxn_set_react_kernel.argtypes = [C.c_void_p, C.c_int]
         L.rxn_react_kernel_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+        L.rxn_equilibrate_constraint_batch.argtypes = [C.c_void_p, c_ip, c_dp, c_i64, c_ip, c_dp, C.c_int, C.c_int, c_ip, c_i64,
+                                                       c_dp, c_ip, c_ip]
         L.rxn_state_upload.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
         L.rxn_state_download.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
         L.rxn_state_broadcast.argtypes = [C.c_void_p, C.c_int, c_dp]
@@ -263,6 +265,23 @@ class Realization:
         jac = np.zeros((n, self.ncomp * self.ncomp)) if jacobian else None
         _ck(lib().rxn_residual_jacobian_blocks_batch(self.h, _ip(l2g), n, dt, _dp(res), _dp(jac)))
         return res, jac
+
+    def ReactionEquilibrateConstraint(self, ctype, conc, cid, free_ion_guess=None, use_prev: bool = False,
+                                      molal: bool = True, l2g: Optional[np.ndarray] = None):
+        """reaction.F90:1308 for every cell (condition_control.F90:725-741): conc [naq] (one constraint) or
+        [nlocal, naq] (per-cell concentrations).  Returns basis_molarity [nlocal, naq], iters, status (RXN_EQ_*)."""
+        n = self.ncells if l2g is None else len(l2g)
+        ctype = np.ascontiguousarray(ctype, dtype=np.int32)
+        cid = np.ascontiguousarray(cid, dtype=np.int32)
+        conc = np.ascontiguousarray(conc, dtype=np.float64)
+        stride = 0 if conc.ndim == 1 else conc.shape[1]
+        guess = None if free_ion_guess is None else np.ascontiguousarray(free_ion_guess, dtype=np.float64)
+        basis = np.zeros((n, self.ncomp))
+        iters = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        _ck(lib().rxn_equilibrate_constraint_batch(self.h, _ip(ctype), _dp(conc), stride, _ip(cid), _dp(guess), int(use_prev),
+                                                   int(molal), _ip(l2g), n, _dp(basis), _ip(iters), _ip(status)))
+        return basis, iters, status
 
     def RTUpdateKineticState(self, dt: float):
         """reactive_transport.F90:642."""

@@ -291,6 +291,21 @@ int emu_residual_jacobian_batch(void *h, const HostView *v, const uint8_t *activ
   for (long long i = 0; i < nlocal; ++i) EMU_DISPATCH(e->nv, cell_residual_jacobian<N>(e->T, S, i, l2g, dt, res_out, jac_out));
   return 0;
 }
+int emu_equilibrate_batch(void *h, const HostView *v, const uint8_t *active, const int32_t *ctype, const double *conc, int64_t conc_stride,
+                          const int32_t *cid, const double *guess, int use_prev, int init_molal, int64_t nlocal, double *basis,
+                          int32_t *iters, int32_t *status) {
+  Emu *e = (Emu *)h;
+  DevState S = mk_state(v, active);
+  const int n = e->R.h.naq;
+  for (long long i = 0; i < nlocal; ++i) {
+    if (active && !active[i]) { iters[i] = 0; status[i] = 0; continue; }
+    int nit = 0, rc = 0;
+    EMU_DISPATCH(e->nv, rc = cell_equilibrate<N>(e->T, S, i, ctype, conc + i * conc_stride, cid, guess, use_prev, init_molal,
+                                                 basis ? basis + i * n : nullptr, &nit));
+    iters[i] = nit; status[i] = rc;
+  }
+  return 0;
+}
 int emu_update_kinetic_state_batch(void *h, const HostView *v, const uint8_t *active, double dt) {
   Emu *e = (Emu *)h;
   DevState S = mk_state(v, active);

@@ -137,6 +137,20 @@ class Emulator:
             raise NotImplementedError(buf.value.decode())
         return res, jac
 
+    def equilibrate_batch(self, st, ctype, conc, cid, free_ion_guess=None, use_prev=False, molal=True):
+        n = st.ncells
+        ctype = np.ascontiguousarray(ctype, dtype=np.int32); cid = np.ascontiguousarray(cid, dtype=np.int32)
+        conc = np.ascontiguousarray(conc, dtype=np.float64)
+        stride = 0 if conc.ndim == 1 else conc.shape[1]
+        guess = None if free_ion_guess is None else np.ascontiguousarray(free_ion_guess, dtype=np.float64)
+        basis = np.zeros((n, self.t.ncomp)); iters = np.zeros(n, dtype=np.int32); status = np.zeros(n, dtype=np.int32)
+        v = st.view()
+        assert lib().emu_equilibrate_batch(self.h, C.byref(v), _p(st.active, C.c_uint8), _p(ctype, C.c_int32), _p(conc, C.c_double),
+                                           C.c_int64(stride), _p(cid, C.c_int32), _p(guess, C.c_double), C.c_int(int(use_prev)),
+                                           C.c_int(int(molal)), C.c_int64(n), _p(basis, C.c_double), _p(iters, C.c_int32),
+                                           _p(status, C.c_int32)) == 0
+        return basis, iters, status
+
     def update_kinetic_state(self, st, dt):
         v = st.view()
         assert lib().emu_update_kinetic_state_batch(self.h, C.byref(v), _p(st.active, C.c_uint8), C.c_double(dt)) == 0

@@ -82,11 +82,20 @@ def initial_cell(deck_path, constraint='initial', porosity=None, volume=1.0):
     return deck, t, orc, st, xx, nit, cst
 
 
-def initial_cell_from_fixture(w, porosity=None, volume=1.0):
-    """Same start-up sequence as initial_cell(), driven only by a committed fixture
-    (tests/golden/<name>.json): no deck, no database, no /root/reference."""
-    t = w.tables
-    orc = Oracle(t)
+class OracleBackend:
+    """equilibrate / update_auxvars on a 1-cell HostState through the oracle."""
+
+    def __init__(self, t):
+        self.orc = Oracle(t)
+
+    def equilibrate(self, st, ctype, conc, cid, guess):
+        return self.orc.equilibrate(st, 0, ctype, conc, cid, guess, use_prev=False)
+
+    def update_auxvars(self, st, xx, act):
+        self.orc.update_auxvars(st, xx, act)
+
+
+def fixture_constraint(w):
     ca = w.meta['constraint_arrays']
     ctype = np.array(ca['ctype'], dtype=np.int32)
     conc = np.array([float(x) for x in ca['conc']])
@@ -94,11 +103,21 @@ def initial_cell_from_fixture(w, porosity=None, volume=1.0):
     guess = None if ca['guess'] is None else np.array([float(x) for x in ca['guess']])
     vf = np.array([float(x) for x in ca['volfrac']])
     area = np.array([float(x) for x in ca['area']])
+    return ctype, conc, cid, guess, vf, area
+
+
+def initial_cell_from_fixture(w, porosity=None, volume=1.0, backend=None):
+    """Same start-up sequence as initial_cell(), driven only by a committed fixture
+    (tests/golden/<name>.json): no deck, no database, no /root/reference.  `backend` (default: the oracle)
+    supplies equilibrate() and update_auxvars() - the device routines under test plug in here."""
+    t = w.tables
+    orc = backend or OracleBackend(t)
+    ctype, conc, cid, guess, vf, area = fixture_constraint(w)
     cst = abi.HostState(t, 1)
     fill_scalars(cst, t, 0.25, volume)
     cst['MNRL_VOLFRAC'][:, 0] = vf
     cst['MNRL_AREA'][:, 0] = area
-    basis_molarity, nit = orc.equilibrate(cst, 0, ctype, conc, cid, guess, use_prev=False)
+    basis_molarity, nit = orc.equilibrate(cst, ctype, conc, cid, guess)
     st = abi.HostState(t, 1)
     fill_scalars(st, t, w.meta['porosity'] if porosity is None else porosity, volume)
     st['MNRL_VOLFRAC'][:, 0] = vf
@@ -111,7 +130,7 @@ def initial_cell_from_fixture(w, porosity=None, volume=1.0):
     if t.act_coef_update_frequency != 0:
         orc.update_auxvars(st, xx, True)
         orc.update_auxvars(st, xx, True)
-    return t, orc, st, xx, nit, cst
+    return t, (orc.orc if isinstance(orc, OracleBackend) else orc), st, xx, nit, cst
 
 
 def outputs(t, st, cell=0):

@@ -168,3 +168,69 @@ def test_packer_rejects_unsupported():
     assert pack_status(d)[0] == abi.RXN_OK
     d.struct_size = 8
     assert pack_status(d)[0] == abi.RXN_ERR_INVALID
+
+
+# ---- ReactionEquilibrateConstraint on the device routines -------------------------------------------
+class _EmuBackend:
+    """equilibrate / update_auxvars of the KAT start-up sequence through the host compilation of the device code."""
+
+    def __init__(self, t):
+        self.emu = Emulator(t)
+        self.t = t
+
+    def equilibrate(self, st, ctype, conc, cid, guess):
+        basis, it, status = self.emu.equilibrate_batch(st, ctype, conc, cid, guess, False, bool(self.t.initialize_with_molality))
+        assert status[0] == 0
+        return basis[0], int(it[0])
+
+    def update_auxvars(self, st, xx, act):
+        self.emu.update_auxvars(st, xx, act)
+
+
+@pytest.mark.parametrize('name', ['carbonate_unit', 'carbonate_dh', 'ca_carbonate_unit', 'ca_carbonate_dh', 'ion_exchange',
+                                  'surface_complexation'])
+def test_equilibrate_constraint_device_code_hits_reference_gold(name):
+    """cell_equilibrate (rxn_device.cuh) + RTUpdateAuxVars reproduce the reference's 14-digit gold files (free, pH,
+    charge-balance, mineral and total constraints), with the oracle's iteration count."""
+    import kat
+    w = synth.Workload(name)
+    t, be, st, xx, nit, cst = kat.initial_cell_from_fixture(w, backend=_EmuBackend(w.tables))
+    t2, orc, st_o, xx_o, nit_o, cst_o = kat.initial_cell_from_fixture(w)
+    assert nit == nit_o
+    out = kat.outputs(t, st)
+    for var, vals in w.gold.items():
+        if var in ('Transport', 'Material ID') or var.endswith('Site Density'):
+            continue
+        g = vals['1']
+        assert abs(out[var] - g) <= 1.0e-12 * max(1.0, abs(g)), '%s %s: %.14e gold %.14e' % (name, var, out[var], g)
+    assert_state_close(cst, cst_o, what=name + ' constraint cell', tables=w.tables)
+
+
+@pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite'])
+def test_equilibrate_constraint_batch_per_cell_concentrations(name):
+    """A batch of cells with their own constraint concentrations, water density and temperature against the oracle."""
+    import kat
+    w = synth.Workload(name)
+    t = w.tables
+    ctype, conc, cid, guess, vf, area = kat.fixture_constraint(w)
+    n = 24
+    rng = np.random.default_rng(5)
+    st = abi.HostState(t, n)
+    kat.fill_scalars(st, t, 0.25)
+    st['DEN_KG'][0] = t.reference_water_density * (1.0 + 0.01 * rng.standard_normal(n))
+    if t.logK_mode != 0:
+        st['TEMP'][0] = 25.0 + 100.0 * rng.random(n)
+    st['MNRL_VOLFRAC'][:] = vf[:, None]
+    st['MNRL_AREA'][:] = area[:, None]
+    concs = np.tile(conc, (n, 1))
+    scale = np.exp(0.05 * rng.standard_normal((n, t.naqcomp)))
+    lin = np.isin(ctype, [0, 1, 2, 7, 9])                         # concentrations (not pH / log / mineral ids): perturb
+    concs[:, lin] *= scale[:, lin]
+    st_o = st.copy()
+    basis_e, it_e, status = Emulator(t).equilibrate_batch(st, ctype, concs, cid, guess, False, bool(t.initialize_with_molality))
+    orc = Oracle(t)
+    for c in range(n):
+        b, it = orc.equilibrate(st_o, c, ctype, concs[c], cid, guess, use_prev=False)
+        assert it == it_e[c] and status[c] == 0
+        assert rel_err(basis_e[c], b).max() <= RTOL
+    assert_state_close(st, st_o, what=name + ' equilibrated batch', tables=t)
