@@ -818,14 +818,14 @@ LANE_DEV void lane_coop_in_mr(const LaneTab &lt, const DevState &S, const DevTab
       double acc0 = 0.0, acc1 = 0.0;
       if (i < n && half < H) {
         if (H == 2) {
-#pragma unroll 5
+#pragma unroll 4
           for (int irate = half; irate < nrate; irate += 2) {
             const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
             const double kk = rate / (1.0 + rate * tran_dt);
             acc0 = acc0 + kk * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell);
           }
         } else {
-#pragma unroll 5
+#pragma unroll 1
           for (int irate = 0; irate < nrate; irate += 2) {
             const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
             acc0 = acc0 + rate / (1.0 + rate * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell);

@@ -72,6 +72,31 @@ def test_react_resident_lane_group_widths(name, G, monkeypatch):
     assert_state_close(st_g, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
 
 
+@pytest.mark.parametrize('kernel', [1, 2, 3])
+def test_react_iteration_cap_takes_the_closing_pass(kernel, monkeypatch):
+    """Abnormal exit (GPU-only iteration cap, where the reference would spin): pri_molal moved after the last RTotal,
+    so the closing RTAuxVarCompute has to redo the speciation; every kernel must agree with the oracle's capped run."""
+    monkeypatch.setenv('RXN_MAX_NEWTON_ITERATIONS', '3')
+    n = 6000
+    w, cells = workload_cells('hanford300a_eq', n)
+    st_o = synth.host_state(w, cells)
+    st_o.active[::11] = 0
+    st_g = st_o.copy()
+    rx, rz = _gpu_state(w, st_g)
+    rz.set_cell_scalars(active=st_g.active)
+    rz.set_react_kernel(kernel)
+    xo = cells['tran_xx'].copy()
+    xg = xo.copy()
+    it_g, fl_g = rz.RTReact(xg, 3600.0, abi.RXN_DT_CONSISTENT)
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=3, nthreads=8)
+    rz.download_host_state(st_g)
+    assert (fl_g & abi.RXN_FLAG_CAPPED).any() and (fl_g[::11] == abi.RXN_FLAG_INACTIVE).all()
+    assert (it_o == it_g).all() and (fl_o == fl_g).all()
+    act = np.where((st_o.active != 0) & ((fl_o & abi.RXN_FLAG_NONFINITE) == 0))[0]
+    assert rel_err(xg[act], xo[act]).max() <= RTOL
+    assert_state_close(st_g, st_o, cells=act, what='capped', tables=w.tables)
+
+
 @pytest.mark.parametrize('name', ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'])
 def test_global_implicit_entry_points(name):
     n = 3000
