@@ -19,7 +19,8 @@ st['DEN_KG'][0] = t.reference_water_density * (1.0 + 0.01 * rng.standard_normal(
 st['MNRL_VOLFRAC'][:] = vf[:, None]; st['MNRL_AREA'][:] = area[:, None]
 concs = np.tile(conc, (n, 1))
 lin = np.isin(ctype, [0, 1, 2, 7, 9])
-concs[:, lin] *= np.exp(0.05 * rng.standard_normal((n, t.naqcomp)))[:, lin]
+sigma = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
+concs[:, lin] *= np.exp(sigma * rng.standard_normal((n, t.naqcomp)))[:, lin]
 rx = rt.Reaction(t); rz = rt.Realization(rx, n)
 ms = []
 for _ in range(3):
@@ -35,6 +36,6 @@ for c in range(m):
     except RuntimeError:        # the reference's fatal errors (singular Newton matrix, zero concentration) for this constraint
         cpu_failed += 1
 cpu = m / (time.perf_counter() - t0)
-print(json.dumps({'workload': name, 'cells': n, 'kernel_ms': min(ms[1:]), 'gpu_cells_per_s': n / (min(ms[1:]) * 1e-3),
+print(json.dumps({'workload': name, 'cells': n, 'sigma': sigma, 'kernel_ms': min(ms[1:]), 'gpu_cells_per_s': n / (min(ms[1:]) * 1e-3),
                   'mean_iterations': float(it.mean()), 'failed': int((status != 0).sum()), 'failed_status_histogram': {int(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))},
                   'cpu_oracle_cells_per_s_1_thread': cpu, 'cpu_failed_of_%d' % m: cpu_failed}))
