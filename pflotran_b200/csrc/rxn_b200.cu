@@ -72,6 +72,10 @@ struct RxnState {
   size_t scratch_bytes[4] = {0, 0, 0, 0};
   int react_kernel = 0;    // 0 auto, 1 thread-per-cell, 2 cooperative tile, 3 resident lane
   unsigned long long *d_counter = nullptr;   // work counter of the resident-lane kernel
+  // host-buffer RReact: chunks of the batch move over PCIe while the previous / next chunk is being solved
+  enum { NCHUNK = 8 };
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_in[NCHUNK] = {}, ev_k[NCHUNK] = {};
   int gi_kernel = 0;       // residual/Jacobian blocks: 0 auto (resident-lane layout if the tables allow it), 1 thread per cell
 };
 
@@ -254,6 +258,12 @@ int rxn_state_destroy(RxnState *s) {
   for (int f = 0; f < RXN_F_COUNT; ++f) if (s->S.f[f]) cudaFree(s->S.f[f]);
   if (s->d_active) cudaFree(s->d_active);
   if (s->d_counter) cudaFree(s->d_counter);
+  if (s->h2d) cudaStreamDestroy(s->h2d);
+  if (s->d2h) cudaStreamDestroy(s->d2h);
+  for (int c = 0; c < RxnState::NCHUNK; ++c) {
+    if (s->ev_in[c]) cudaEventDestroy(s->ev_in[c]);
+    if (s->ev_k[c]) cudaEventDestroy(s->ev_k[c]);
+  }
   for (int k = 0; k < 4; ++k) if (s->scratch[k]) cudaFree(s->scratch[k]);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -437,6 +447,50 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
   if (l2g) {
     if ((rc = ensure_scratch(s, 1, (size_t)nlocal * 4, &d_l2g)) != RXN_OK) return rc;
     CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
+  }
+  const RxnTables *t = s->t;
+  const bool lane = t->lane.plan.usable && !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ] &&
+                    (s->react_kernel == 0 || s->react_kernel == 3);
+  if (lane && nlocal >= 262144 && !getenv("RXN_NO_PIPELINE")) {
+    // resident-lane kernel on a large batch: NCHUNK chunks; chunk c+1 crosses PCIe while chunk c is solved and chunk
+    // c-1 returns (full duplex), so the host-buffer call costs about the kernel time
+    if (!s->h2d) {
+      CU(cudaStreamCreate(&s->h2d)); CU(cudaStreamCreate(&s->d2h));
+      for (int c = 0; c < RxnState::NCHUNK; ++c) {
+        CU(cudaEventCreateWithFlags(&s->ev_in[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_k[c], cudaEventDisableTiming));
+      }
+    }
+    if (!s->d_counter) CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+    CU(cudaStreamSynchronize(s->stream));                       // the l2g copy above / earlier work on the scratch buffers
+    const int64_t chunk = (((nlocal + RxnState::NCHUNK - 1) / RxnState::NCHUNK) + 63) / 64 * 64;
+    int nch = 0;
+    for (int64_t off = 0; off < nlocal; off += chunk, ++nch) {
+      const int64_t len = std::min<int64_t>(chunk, nlocal - off);
+      CU(cudaMemcpyAsync((double *)d_xx + off * n, tran_xx + off * n, (size_t)len * n * 8, cudaMemcpyHostToDevice, s->h2d));
+      CU(cudaEventRecord(s->ev_in[nch], s->h2d));
+    }
+    CU(cudaEventRecord(s->ev0, s->stream));
+    int c = 0;
+    for (int64_t off = 0; off < nlocal; off += chunk, ++c) {
+      const int64_t len = std::min<int64_t>(chunk, nlocal - off);
+      CU(cudaStreamWaitEvent(s->stream, s->ev_in[c], 0));
+      rc = lane_launch_react(t->lane, t->h, t->d_blob, s->S, (double *)d_xx + off * n, d_l2g ? (const int32_t *)d_l2g + off : nullptr,
+                             len, dt, dt_mode, (int32_t *)d_it + off, (int32_t *)d_fl + off, s->d_counter, s->stream, d_l2g ? 0 : off);
+      if (rc != RXN_OK) return fail(rc, "resident-lane kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      ++g_launches;
+      CU(cudaEventRecord(s->ev_k[c], s->stream));
+      CU(cudaStreamWaitEvent(s->d2h, s->ev_k[c], 0));
+      CU(cudaMemcpyAsync(tran_xx + off * n, (double *)d_xx + off * n, (size_t)len * n * 8, cudaMemcpyDeviceToHost, s->d2h));
+      if (iters_out) CU(cudaMemcpyAsync(iters_out + off, (int32_t *)d_it + off, (size_t)len * 4, cudaMemcpyDeviceToHost, s->d2h));
+      if (flags_out) CU(cudaMemcpyAsync(flags_out + off, (int32_t *)d_fl + off, (size_t)len * 4, cudaMemcpyDeviceToHost, s->d2h));
+    }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->d2h));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    return RXN_OK;
   }
   CU(cudaMemcpyAsync(d_xx, tran_xx, (size_t)nlocal * n * 8, cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev0, s->stream));

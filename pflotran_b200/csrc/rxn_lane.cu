@@ -9,7 +9,7 @@ namespace rxn {
 #define RXN_LANE_DECL(n, cpb, g)                                                                                                 \
   template <> int lane_launch_variant<n, cpb, g>(const LaneTab &, size_t, int, const DevTab &, const double *, const double *,    \
                                                  const DevState &, double *, const int32_t *, long long, double, int, int32_t *, \
-                                                 int32_t *, unsigned long long *, cudaStream_t);
+                                                 int32_t *, unsigned long long *, long long, cudaStream_t);
 RXN_LANE_SHAPES(RXN_LANE_DECL)
 #undef RXN_LANE_DECL
 #define RXN_LANE_DECL(n, cpb, g)                                                                                                    \
@@ -121,14 +121,14 @@ int lane_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const Dev
 
 int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
                       long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, long long cell0) {
   LaneTab lt = k.plan.lt;
   lane_set_mrK1(k, lt, dt);
   if (cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXN_ERR_CUDA;
 #define RXN_LANE_CASE(n, cpb, g)                                                                                                 \
   if (lt.N == n && lt.CPB == cpb && k.G == g)                                                                                    \
     return lane_launch_variant<n, cpb, g>(lt, k.plan.smem_bytes, k.sm_count, h, k.d_blob, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, \
-                                       iters, flags, counter, stream);
+                                       iters, flags, counter, cell0, stream);
   RXN_LANE_SHAPES(RXN_LANE_CASE)
 #undef RXN_LANE_CASE
   return RXN_ERR_UNSUPPORTED;

@@ -34,7 +34,7 @@ struct LaneKernel {
 template <int N, int CPB, int G>
 int lane_launch_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
                         const DevState &S, double *tran_xx, const int32_t *l2g, long long nlocal, double dt, int dt_mode,
-                        int32_t *iters, int32_t *flags, unsigned long long *counter, cudaStream_t stream);
+                        int32_t *iters, int32_t *flags, unsigned long long *counter, long long cell0, cudaStream_t stream);
 
 template <int N, int CPB, int G>
 int lane_launch_gi_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
@@ -45,7 +45,7 @@ int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std:
 void lane_kernel_free(LaneKernel *k);
 int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
                       long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
-                      cudaStream_t stream);
+                      cudaStream_t stream, long long cell0 = 0);
 
 int lane_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, const int32_t *l2g, long long nlocal, double dt,
                    double *res_out, double *jac_out, cudaStream_t stream);

@@ -19,7 +19,7 @@ template <int N, int CPB, int G>
 __global__ void __launch_bounds__(((CPB * G + 31) / 32) * 32, 1)
 k_react_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h, const double *__restrict__ pblob,
              const double *__restrict__ blob, DevState S, double *tran_xx, const int32_t *__restrict__ l2g, long long nlocal,
-             double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter) {
+             double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter, long long cell0) {
   const int words = lt.blob_dbl + lt.blob_int / 2;
   for (int w = threadIdx.x; w < words; w += blockDim.x) tsm[w] = pblob[w];
   __syncthreads();
@@ -51,7 +51,7 @@ k_react_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab 
         if (i >= nlocal) {
           exhausted = true;
         } else {
-          const long long cell = l2g ? l2g[i] : i;
+          const long long cell = l2g ? l2g[i] : i + cell0;    // cell0: first cell of this chunk of the batch
           if (S.active && !S.active[cell]) {                   // imat <= 0 (reactive_transport.F90:1699)
             if (l == 0) {
               if (iters) iters[i] = 0;
@@ -158,7 +158,7 @@ template <>
 int lane_launch_variant<LANE_N, LANE_CPB, LANE_G>(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob,
                                                   const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
                                                   long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags,
-                                                  unsigned long long *counter, cudaStream_t stream) {
+                                                  unsigned long long *counter, long long cell0, cudaStream_t stream) {
   auto kern = lane::k_react_lane<LANE_N, LANE_CPB, LANE_G>;
   constexpr int threads = ((LANE_CPB * LANE_G + 31) / 32) * 32;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return RXN_ERR_CUDA;
@@ -166,7 +166,7 @@ int lane_launch_variant<LANE_N, LANE_CPB, LANE_G>(const LaneTab &lt, size_t smem
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem_bytes) != cudaSuccess || bps < 1) bps = 1;
   const long long want = (nlocal + LANE_CPB - 1) / LANE_CPB;
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sm_count * bps));
-  kern<<<grid, threads, smem_bytes, stream>>>(lt, h, pblob, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags, counter);
+  kern<<<grid, threads, smem_bytes, stream>>>(lt, h, pblob, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags, counter, cell0);
   return RXN_OK;
 }
 

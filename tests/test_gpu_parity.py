@@ -309,3 +309,39 @@ def test_equilibrate_constraint_gpu_batch(name):
     # molarities agree to 2e-14); the short, well-conditioned solves must also agree in their iteration counts.
     if np.mean(it_o) < 40:
         assert (np.array(it_o) == it_g[::7]).all()
+
+
+def test_react_chunked_host_path_with_l2g():
+    """rxn_react_batch moves large batches in chunks (PCIe copies overlapping the kernel); with a local->ghosted map the
+    chunks address the state through l2g, without one through a chunk base: both must give the single-launch answer."""
+    n = 300_000
+    w, cells = workload_cells('calcite', n)
+
+    def run(l2g, pipeline, monkey_env):
+        import os
+        if pipeline:
+            os.environ.pop('RXN_NO_PIPELINE', None)
+        else:
+            os.environ['RXN_NO_PIPELINE'] = '1'
+        rx = rt.Reaction(w.tables)
+        rz = rt.Realization(rx, n)
+        for f, v in w.base.items():
+            rz.broadcast(f, v)
+        rz.set_cell_scalars(porosity=cells['porosity'], temp=cells['temp'], pres=cells['pres'])
+        rz.upload('MNRL_VOLFRAC', cells['volfrac'])
+        xx = np.ascontiguousarray(cells['tran_xx'] if l2g is None else cells['tran_xx'][l2g])
+        it, fl = rz.RTReact(xx, 3600.0, l2g=l2g)
+        os.environ.pop('RXN_NO_PIPELINE', None)
+        return xx, it, fl, rz.download('TOTAL')
+
+    x0, it0, fl0, tot0 = run(None, False, None)
+    x1, it1, fl1, tot1 = run(None, True, None)
+    np.testing.assert_array_equal(x1, x0)
+    np.testing.assert_array_equal(it1, it0)
+    np.testing.assert_array_equal(tot1, tot0)
+    perm = np.arange(n - 1, -1, -1, dtype=np.int32)
+    x2, it2, fl2, tot2 = run(perm, True, None)
+    np.testing.assert_array_equal(x2, x0[perm])
+    np.testing.assert_array_equal(it2, it0[perm])
+    np.testing.assert_array_equal(fl2, fl0[perm])
+    np.testing.assert_array_equal(tot2, tot0)
