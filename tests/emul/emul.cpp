@@ -223,11 +223,11 @@ int emu_react_batch(void *h, const HostView *v, double *tran_xx, const uint8_t *
   return 0;
 }
 int emu_react_lane(void *hh, const HostView *v, double *tran_xx, const uint8_t *active, const int32_t *l2g, int64_t nlocal, double dt,
-                   int dt_mode, int32_t *iters, int32_t *flags, int G, char *err, int errlen, int32_t *stats) {
+                   int dt_mode, int32_t *iters, int32_t *flags, int G, int forceN, char *err, int errlen, int32_t *stats) {
   Emu *e = (Emu *)hh;
   DevState S = mk_state(v, active);
   LanePlan P;
-  const int N = lane_N_for(e->R.h.naq);
+  const int N = forceN >= e->R.h.naq ? forceN : lane_N_for(e->R.h.naq);
   if (N == 0) { if (err) snprintf(err, errlen, "naq exceeds the compiled shapes"); return RXN_ERR_UNSUPPORTED; }
   if (G != 1 && G != 2 && G != 4) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4"); return RXN_ERR_INVALID; }
   int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P);

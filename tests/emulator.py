@@ -80,7 +80,7 @@ class Emulator:
         assert rc == 0
         return iters, flags
 
-    def react_lane(self, st, tran_xx, dt, dt_mode=abi.RXN_DT_CONSISTENT, l2g=None, maxit=None, G=1):
+    def react_lane(self, st, tran_xx, dt, dt_mode=abi.RXN_DT_CONSISTENT, l2g=None, maxit=None, G=1, N=0):
         """RReact through the resident-lane kernel's per-lane routines (rxn_lane_dev.cuh), G lanes per cell."""
         if maxit is not None:
             lib().emu_set_maxit(self.h, maxit)
@@ -92,7 +92,7 @@ class Emulator:
         stats = np.zeros(16, dtype=np.int32)
         rc = lib().emu_react_lane(self.h, C.byref(v), _p(tran_xx, C.c_double), _p(st.active, C.c_uint8),
                                   _p(l2g, C.c_int32), C.c_int64(n), C.c_double(dt), C.c_int(dt_mode),
-                                  _p(iters, C.c_int32), _p(flags, C.c_int32), C.c_int(G), buf, 512, _p(stats, C.c_int32))
+                                  _p(iters, C.c_int32), _p(flags, C.c_int32), C.c_int(G), C.c_int(N), buf, 512, _p(stats, C.c_int32))
         if rc != 0:
             raise NotImplementedError(buf.value.decode())
         self.lane_stats = dict(zip(['N', 'blob_bytes', 'cell_bytes', 'terms_spec', 'steps_spec', 'terms_A', 'steps_A',

@@ -71,6 +71,25 @@ def test_resident_lane_iteration_cap_and_inactive(G):
     assert_state_close(st_e, st_o, cells=act, what='capped', tables=w.tables)
 
 
+@pytest.mark.parametrize('name,N,G', [('hanford300a_eq', 16, 2), ('hanford300a_eq', 24, 4), ('calcite', 8, 1), ('calcite', 12, 2)])
+def test_resident_lane_padded_shapes(name, N, G):
+    """naq smaller than the compiled matrix dimension: the padding rows (m = 1, zero residual, decoupled) must not change
+    anything - iteration counts, flags and values as with the exact shape."""
+    w, cells = workload_cells(name, 200)
+    st_o = synth.host_state(w, cells)
+    st_e = st_o.copy()
+    xo = cells['tran_xx'].copy()
+    xe = xo.copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=10000)
+    em = Emulator(w.tables)
+    it_e, fl_e = em.react_lane(st_e, xe, 3600.0, abi.RXN_DT_CONSISTENT, G=G, N=N)
+    assert em.lane_stats['N'] == N
+    assert (it_o == it_e).all() and (fl_o == fl_e).all()
+    ok = (fl_o & ~3) == 0
+    assert rel_err(xe[ok], xo[ok]).max() <= RTOL
+    assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
+
+
 def test_resident_lane_rejects_what_it_does_not_cover():
     for name in ['ion_exchange', 'kd_wo_mineral']:
         w, cells = workload_cells(name, 8)

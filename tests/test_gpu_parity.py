@@ -72,6 +72,28 @@ def test_react_resident_lane_group_widths(name, G, monkeypatch):
     assert_state_close(st_g, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
 
 
+@pytest.mark.parametrize('name,N', [('hanford300a_eq', 16), ('hanford300a_eq', 24), ('calcite', 8), ('calcite', 12)])
+def test_react_resident_lane_padded_shapes(name, N, monkeypatch):
+    """naq smaller than the compiled matrix dimension (RXN_LANE_N forces a padded shape): same answers."""
+    monkeypatch.setenv('RXN_LANE_N', str(N))
+    n = 20000
+    w, cells = workload_cells(name, n)
+    st_o = synth.host_state(w, cells)
+    st_g = st_o.copy()
+    rx, rz = _gpu_state(w, st_g)
+    rz.set_react_kernel(3)
+    assert 'N=%d ' % N in rz.react_kernel_info()
+    xo = cells['tran_xx'].copy()
+    xg = xo.copy()
+    it_g, fl_g = rz.RTReact(xg, 3600.0, abi.RXN_DT_CONSISTENT)
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=10000, nthreads=8)
+    rz.download_host_state(st_g)
+    assert (it_o == it_g).all() and (fl_o == fl_g).all()
+    ok = (fl_o & ~3) == 0
+    assert rel_err(xg[ok], xo[ok]).max() <= RTOL
+    assert_state_close(st_g, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
+
+
 @pytest.mark.parametrize('kernel', [1, 2, 3])
 def test_react_iteration_cap_takes_the_closing_pass(kernel, monkeypatch):
     """Abnormal exit (GPU-only iteration cap, where the reference would spin): pri_molal moved after the last RTotal,
@@ -329,7 +351,7 @@ def test_react_chunked_host_path_with_l2g():
             rz.broadcast(f, v)
         rz.set_cell_scalars(porosity=cells['porosity'], temp=cells['temp'], pres=cells['pres'])
         rz.upload('MNRL_VOLFRAC', cells['volfrac'])
-        xx = np.ascontiguousarray(cells['tran_xx'] if l2g is None else cells['tran_xx'][l2g])
+        xx = cells['tran_xx'].copy() if l2g is None else np.ascontiguousarray(cells['tran_xx'][l2g])
         it, fl = rz.RTReact(xx, 3600.0, l2g=l2g)
         os.environ.pop('RXN_NO_PIPELINE', None)
         return xx, it, fl, rz.download('TOTAL')
