@@ -260,9 +260,9 @@ def run_ours(args):
         return rz.last_kernel_ms()
 
     # e2e: RTReact overwrites the caller's (pinned) Vec in place, so every timed step gets its own pre-filled buffer; when
-    # that would pin more than 16 GB the one buffer is re-filled inside the timed region instead (and counted)
+    # that would pin more than 16 GB on the node the one buffer is re-filled inside the timed region instead (and counted)
     e2e_bufs = [xx_host]
-    if nb * (args.steps + 1) <= 16 * 2 ** 30:
+    if nb * (args.steps + 1) * world <= 16 * 2 ** 30:      # pinned host memory of all ranks of the node together
         for _ in range(args.steps):
             b = rt.pinned_empty((n, ncomp))
             b[:] = xx0_host
