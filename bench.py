@@ -48,7 +48,7 @@ WORKLOAD_DESC = {
 }
 # DRAM bytes per cell-update of the react kernel from the committed `ncu --set full` captures
 # (dram__bytes_read.sum + dram__bytes_write.sum over the cells of the profiled launch): profiles/r01_r9_lane_g2.metrics.csv
-NCU_DRAM_BYTES_PER_CELL = {'hanford300a_eq': (755.823872e6 + 1234.784e6) / 600000}
+NCU_DRAM_BYTES_PER_CELL = {'hanford300a_eq': (758.277120e6 + 1237.866e6) / 600000}
 RESET_FIELDS = ['PRI_MOLAL', 'PRI_ACT_COEF', 'SEC_MOLAL', 'SEC_ACT_COEF', 'LN_ACT_H2O', 'TOTAL_SORB_EQ', 'FREE_SITE_CONC',
                 'EQIONX_REF_CATION_SORBED_CONC']
 
