@@ -134,7 +134,8 @@ module Rxn_B200_module
             rxn_state_download, rxn_state_broadcast, rxn_set_cell_scalars, rxn_react_batch, &
             rxn_update_auxvars_batch, rxn_fixed_accum_batch, rxn_residual_blocks_batch, &
             rxn_jacobian_blocks_batch, rxn_residual_jacobian_blocks_batch, &
-            rxn_update_kinetic_state_batch, rxn_equilibrate_constraint_batch, rxn_last_kernel_ms, rxn_last_error
+            rxn_update_kinetic_state_batch, rxn_equilibrate_constraint_batch, rxn_update_auxvars_batch_device, &
+            rxn_residual_jacobian_blocks_batch_device, rxn_last_kernel_ms, rxn_last_error
 
   interface
 
@@ -291,6 +292,23 @@ module Rxn_B200_module
       type(c_ptr), value :: l2g                  ! integer(c_int32_t) (nlocal) ghosted id - 1, or c_null_ptr
       integer(c_int64_t), value :: nlocal
       type(c_ptr), value :: basis_molarity_out, iters_out, status_out
+    end function
+
+    ! device-resident variants (PETSc VECCUDA / MATAIJCUSPARSE arrays: VecCUDAGetArray / MatSeqAIJCUSPARSE pointers)
+    integer(c_int) function rxn_update_auxvars_batch_device(state, d_xx_loc, update_act_coefs) &
+        bind(C, name='rxn_update_auxvars_batch_device')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, d_xx_loc
+      integer(c_int), value :: update_act_coefs
+    end function
+
+    integer(c_int) function rxn_residual_jacobian_blocks_batch_device(state, d_l2g, nlocal, dt, d_res, d_jac) &
+        bind(C, name='rxn_residual_jacobian_blocks_batch_device')
+      import :: c_int, c_int64_t, c_double, c_ptr
+      type(c_ptr), value :: state, d_l2g
+      integer(c_int64_t), value :: nlocal
+      real(c_double), value :: dt
+      type(c_ptr), value :: d_res, d_jac
     end function
 
     real(c_float) function rxn_last_kernel_ms(state) bind(C, name='rxn_last_kernel_ms')

@@ -319,6 +319,13 @@ int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t 
  * RUpdateKineticState per cell (reaction.F90:5320-5429). */
 int rxn_update_kinetic_state_batch(RxnState *s, double dt);
 
+/* Device-resident variants of the global-implicit entry points (PETSc VECCUDA / MATAIJCUSPARSE arrays stay
+ * on the GPU, no PCIe round trip per Newton iteration).  Pointers are device pointers owned by the caller
+ * (rxn_device_alloc or the caller's own allocations on the state's device); same semantics otherwise. */
+int rxn_update_auxvars_batch_device(RxnState *s, const double *d_xx_loc, int update_act_coefs);
+int rxn_residual_jacobian_blocks_batch_device(RxnState *s, const int32_t *d_l2g, int64_t nlocal, double dt, double *d_res,
+                                              double *d_jac);
+
 /* timing of the last batched kernel sequence on the handle's stream, in ms (CUDA events). */
 float rxn_last_kernel_ms(const RxnState *s);
 /* CUDA-event bracket on the handle's stream around any sequence of calls (bench.py) */

@@ -554,6 +554,45 @@ int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int
   return RXN_OK;
 }
 
+static int launch_residual_jacobian(RxnState *s, const int32_t *d_l2g, int64_t nlocal, double dt, double *d_res, double *d_jac) {
+  const RxnTables *t = s->t;
+  if (t->lane.plan_gi.usable && s->gi_kernel != 1) {
+    int rc = lane_launch_gi(t->lane, t->h, t->d_blob, s->S, d_l2g, (long long)nlocal, dt, d_res, d_jac, s->stream);
+    if (rc != RXN_OK) return fail(rc, "resident-lane residual/Jacobian kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ++g_launches;
+  } else {
+    const int threads = t->nvariant <= 8 ? 128 : 64;
+    const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
+    RXN_DISPATCH(t->nvariant, run_residual_jacobian, L, t->h, (const double *)t->d_blob, s->S, (const int *)d_l2g, (long long)nlocal,
+                 dt, d_res, d_jac);
+  }
+  return RXN_OK;
+}
+
+// device-resident variant (PETSc VECCUDA / MATAIJCUSPARSE arrays): d_res / d_jac are device pointers the
+// caller owns; blocks of inactive cells are left untouched
+int rxn_residual_jacobian_blocks_batch_device(RxnState *s, const int32_t *d_l2g, int64_t nlocal, double dt, double *d_res,
+                                              double *d_jac) {
+  if (!s || nlocal < 0 || !(dt > 0.0) || (!d_res && !d_jac)) return fail(RXN_ERR_INVALID, "bad argument");
+  if (nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  int rc = launch_residual_jacobian(s, d_l2g, nlocal, dt, d_res, d_jac);
+  if (rc != RXN_OK) return rc;
+  return check_launch(s, true);
+}
+
+int rxn_update_auxvars_batch_device(RxnState *s, const double *d_xx_loc, int update_act_coefs) {
+  if (!s) return fail(RXN_ERR_INVALID, "null state");
+  CU(cudaSetDevice(s->t->device));
+  const RxnTables *t = s->t;
+  CU(cudaEventRecord(s->ev0, s->stream));
+  const int threads = t->nvariant <= 8 ? 128 : 64;
+  const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
+  RXN_DISPATCH(t->nvariant, run_update_auxvars, L, t->h, (const double *)t->d_blob, s->S, d_xx_loc, update_act_coefs);
+  return check_launch(s, true);
+}
+
 int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt, double *res_out,
                                        double *jac_out) {
   if (!s || nlocal < 0 || !(dt > 0.0) || (!res_out && !jac_out)) return fail(RXN_ERR_INVALID, "bad argument");
@@ -570,17 +609,7 @@ int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t 
     CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
   }
   CU(cudaEventRecord(s->ev0, s->stream));
-  if (t->lane.plan_gi.usable && s->gi_kernel != 1) {
-    rc = lane_launch_gi(t->lane, t->h, t->d_blob, s->S, (const int32_t *)d_l2g, (long long)nlocal, dt, (double *)d_res, (double *)d_jac,
-                        s->stream);
-    if (rc != RXN_OK) return fail(rc, "resident-lane residual/Jacobian kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    ++g_launches;
-  } else {
-    const int threads = t->nvariant <= 8 ? 128 : 64;
-    const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
-    RXN_DISPATCH(t->nvariant, run_residual_jacobian, L, t->h, (const double *)t->d_blob, s->S, (const int *)d_l2g, (long long)nlocal,
-                 dt, (double *)d_res, (double *)d_jac);
-  }
+  if ((rc = launch_residual_jacobian(s, (const int32_t *)d_l2g, nlocal, dt, (double *)d_res, (double *)d_jac)) != RXN_OK) return rc;
   CU(cudaEventRecord(s->ev1, s->stream));
   if (res_out) CU(cudaMemcpyAsync(res_out, d_res, (size_t)nlocal * n * 8, cudaMemcpyDeviceToHost, s->stream));
   if (jac_out) CU(cudaMemcpyAsync(jac_out, d_jac, (size_t)nlocal * n * n * 8, cudaMemcpyDeviceToHost, s->stream));

@@ -56,6 +56,8 @@ def lib():
         L.rxn_state_materialize.argtypes = [C.c_void_p, C.c_int]
         L.rxn_set_react_kernel.argtypes = [C.c_void_p, C.c_int]
         L.rxn_react_kernel_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+        L.rxn_update_auxvars_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.rxn_residual_jacobian_blocks_batch_device.argtypes = [C.c_void_p, C.c_void_p, c_i64, C.c_double, C.c_void_p, C.c_void_p]
         L.rxn_equilibrate_constraint_batch.argtypes = [C.c_void_p, c_ip, c_dp, c_i64, c_ip, c_dp, C.c_int, C.c_int, c_ip, c_i64,
                                                        c_dp, c_ip, c_ip]
         L.rxn_state_upload.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
@@ -301,6 +303,13 @@ class Realization:
         d = dst.ctypes.data if isinstance(dst, np.ndarray) else dst
         s_ = src.ctypes.data if isinstance(src, np.ndarray) else src
         _ck(lib().rxn_device_copy(self.h, C.c_void_p(d), C.c_void_p(s_), nbytes, kind))
+
+    def RTUpdateAuxVars_device(self, d_xx_loc: int, update_activity_coefs: bool):
+        _ck(lib().rxn_update_auxvars_batch_device(self.h, C.c_void_p(d_xx_loc), int(update_activity_coefs)))
+
+    def RTResidualJacobianNonFlux_device(self, nlocal: int, dt: float, d_res: int = 0, d_jac: int = 0, d_l2g: int = 0):
+        _ck(lib().rxn_residual_jacobian_blocks_batch_device(self.h, C.c_void_p(d_l2g or None), nlocal, dt,
+                                                            C.c_void_p(d_res or None), C.c_void_p(d_jac or None)))
 
     def RTReact_device(self, d_xx: int, nlocal: int, dt: float, dt_mode: int = abi.RXN_DT_CONSISTENT,
                        d_l2g: int = 0, d_iters: int = 0, d_flags: int = 0):

@@ -367,3 +367,33 @@ def test_react_chunked_host_path_with_l2g():
     np.testing.assert_array_equal(it2, it0[perm])
     np.testing.assert_array_equal(fl2, fl0[perm])
     np.testing.assert_array_equal(tot2, tot0)
+
+
+def test_global_implicit_device_resident_entry_points():
+    """rxn_update_auxvars_batch_device / rxn_residual_jacobian_blocks_batch_device (device pointers) give
+    bit for bit what the host-buffer entry points give."""
+    n = 20000
+    w, cells = workload_cells('hanford300a_eq', n)
+    st = synth.host_state(w, cells)
+    rng = np.random.default_rng(7)
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((n, w.ncomp))))
+    nc = w.ncomp
+    rx, rz = _gpu_state(w, st.copy())
+    rz.RTUpdateAuxVars(xx, True)
+    r_h, j_h = rz.RTResidualJacobianNonFlux(1800.0)
+    rx2, rz2 = _gpu_state(w, st.copy())
+    d_xx = rz2.device_alloc(n * nc * 8)
+    d_res = rz2.device_alloc(n * nc * 8)
+    d_jac = rz2.device_alloc(n * nc * nc * 8)
+    rz2.device_copy(d_xx, xx, n * nc * 8, 0)
+    rz2.RTUpdateAuxVars_device(d_xx, True)
+    rz2.RTResidualJacobianNonFlux_device(n, 1800.0, d_res, d_jac)
+    r_d = np.zeros((n, nc))
+    j_d = np.zeros((n, nc * nc))
+    rz2.device_copy(r_d, d_res, n * nc * 8, 1)
+    rz2.device_copy(j_d, d_jac, n * nc * nc * 8, 1)
+    np.testing.assert_array_equal(r_d, r_h)
+    np.testing.assert_array_equal(j_d, j_h)
+    np.testing.assert_array_equal(rz2.download('TOTAL'), rz.download('TOTAL'))
+    for p in (d_xx, d_res, d_jac):
+        rz2.device_free(p)
