@@ -135,7 +135,10 @@ module Rxn_B200_module
             rxn_update_auxvars_batch, rxn_fixed_accum_batch, rxn_residual_blocks_batch, &
             rxn_jacobian_blocks_batch, rxn_residual_jacobian_blocks_batch, &
             rxn_update_kinetic_state_batch, rxn_equilibrate_constraint_batch, rxn_update_auxvars_batch_device, &
-            rxn_residual_jacobian_blocks_batch_device, rxn_last_kernel_ms, rxn_last_error
+            rxn_residual_jacobian_blocks_batch_device, rxn_connset_create, rxn_connset_destroy, &
+            rxn_connset_structure, rxn_connset_device_structure, rxn_connset_flux_coefs, rxn_flux_residual_batch, &
+            rxn_flux_jacobian_batch, rxn_flux_residual_batch_device, rxn_flux_jacobian_batch_device, &
+            rxn_last_kernel_ms, rxn_last_error
 
   interface
 
@@ -309,6 +312,62 @@ module Rxn_B200_module
       integer(c_int64_t), value :: nlocal
       real(c_double), value :: dt
       type(c_ptr), value :: d_res, d_jac
+    end function
+
+    ! flux side (RTResidualFlux / RTJacobianFlux interior loops, TFluxCoef / TFlux / TFluxDerivative): the connection set is
+    ! grid%internal_connection_set_list flattened in loop order with 0-based ghosted ids; ghost_to_local = grid%nG2L - 1
+    integer(c_int) function rxn_connset_create(state, nconn, id_up, id_dn, ghost_to_local, nlocal, active, connset) &
+        bind(C, name='rxn_connset_create')
+      import :: c_int, c_int64_t, c_ptr
+      type(c_ptr), value :: state
+      integer(c_int64_t), value :: nconn, nlocal
+      type(c_ptr), value :: id_up, id_dn, ghost_to_local, active
+      type(c_ptr) :: connset
+    end function
+
+    integer(c_int) function rxn_connset_destroy(connset) bind(C, name='rxn_connset_destroy')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: connset
+    end function
+
+    integer(c_int) function rxn_connset_structure(connset, nnz_blocks, row_ptr, col) bind(C, name='rxn_connset_structure')
+      import :: c_int, c_int64_t, c_ptr
+      type(c_ptr), value :: connset
+      integer(c_int64_t) :: nnz_blocks
+      type(c_ptr), value :: row_ptr, col
+    end function
+
+    integer(c_int) function rxn_connset_device_structure(connset, d_row_ptr, d_col) bind(C, name='rxn_connset_device_structure')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: connset
+      type(c_ptr) :: d_row_ptr, d_col
+    end function
+
+    integer(c_int) function rxn_connset_flux_coefs(connset, area, velocity, disp_over_dist, fraction_upwind, use_upwinding) &
+        bind(C, name='rxn_connset_flux_coefs')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: connset, area, velocity, disp_over_dist, fraction_upwind
+      integer(c_int), value :: use_upwinding
+    end function
+
+    integer(c_int) function rxn_flux_residual_batch(state, connset, res_out) bind(C, name='rxn_flux_residual_batch')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, connset, res_out
+    end function
+
+    integer(c_int) function rxn_flux_jacobian_batch(state, connset, val_out) bind(C, name='rxn_flux_jacobian_batch')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, connset, val_out
+    end function
+
+    integer(c_int) function rxn_flux_residual_batch_device(state, connset, d_res) bind(C, name='rxn_flux_residual_batch_device')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, connset, d_res
+    end function
+
+    integer(c_int) function rxn_flux_jacobian_batch_device(state, connset, d_val) bind(C, name='rxn_flux_jacobian_batch_device')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, connset, d_val
     end function
 
     real(c_float) function rxn_last_kernel_ms(state) bind(C, name='rxn_last_kernel_ms')

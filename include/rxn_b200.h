@@ -326,6 +326,38 @@ int rxn_update_auxvars_batch_device(RxnState *s, const double *d_xx_loc, int upd
 int rxn_residual_jacobian_blocks_batch_device(RxnState *s, const int32_t *d_l2g, int64_t nlocal, double dt, double *d_res,
                                               double *d_jac);
 
+/* ---- Flux side of the global-implicit transport residual / Jacobian ------------------------------
+ * replaces: the interior-connection loops of RTResidualFlux (reactive_transport.F90:2252-2310) and RTJacobianFlux
+ * (:3094-3140) with TFluxCoef (transport.F90:756-819), TFlux (:368-439) and TFluxDerivative (:529-622), liquid phase.
+ * They consume total / dtotal of the state where rxn_update_auxvars_batch left them (RXN_F_DTOTAL materialised).
+ *
+ * A connection set is the reference's connection list (grid%internal_connection_set_list flattened in loop order):
+ * id_up / id_dn ghosted cell ids (0-based), ghost_to_local = grid%nG2L - 1 (< 0 for ghost cells, NULL = identity),
+ * active = imat > 0 per ghosted cell (NULL = all; a connection with an inactive side is skipped).  The library turns it
+ * into the row view (per local cell: its connections in connection order), which is also the block-CSR structure of
+ * the flux Jacobian: slot row_ptr[r] is the diagonal block of local row r, slots row_ptr[r]+1 .. row_ptr[r+1]-1 its
+ * connections in connection order; col = ghosted id of the column cell; blocks n x n column-major, as
+ * MatSetValuesBlockedLocal receives Jup / Jdn. */
+typedef struct RxnConnSet RxnConnSet;
+int rxn_connset_create(RxnState *s, int64_t nconn, const int32_t *id_up, const int32_t *id_dn, const int32_t *ghost_to_local,
+                       int64_t nlocal, const uint8_t *active, RxnConnSet **out);
+int rxn_connset_destroy(RxnConnSet *c);
+/* block-CSR structure: *nnz_blocks = row_ptr[nlocal]; row_ptr (nlocal+1) and col (nnz_blocks) may be NULL */
+int rxn_connset_structure(const RxnConnSet *c, int64_t *nnz_blocks, int32_t *row_ptr, int32_t *col);
+int rxn_connset_device_structure(const RxnConnSet *c, const int32_t **d_row_ptr, const int32_t **d_col);
+/* TFluxCoef for every connection, on the device.  Host arrays: area (connection%area), velocity
+ * (patch%internal_velocities(1,:)), disp_over_dist (patch%internal_tran_coefs(:,1,:), nconn x naqcomp, component fastest),
+ * fraction_upwind (connection%dist(-1,:); may be NULL with use_upwinding).  Call again when the flow field changes. */
+int rxn_connset_flux_coefs(RxnConnSet *c, const double *area, const double *velocity, const double *disp_over_dist,
+                           const double *fraction_upwind, int use_upwinding);
+/* res_out: AoS nlocal x ncomp, r_p after the interior-flux loop (starts from r_p = 0, reactive_transport.F90:2249) */
+int rxn_flux_residual_batch(RxnState *s, RxnConnSet *c, double *res_out);
+/* val_out: nnz_blocks x ncomp x ncomp, the flux Jacobian in the block-CSR structure above (starts from zero) */
+int rxn_flux_jacobian_batch(RxnState *s, RxnConnSet *c, double *val_out);
+/* same with the outputs resident on the state's device (PETSc VECCUDA array / MATSEQBAIJ value array on the GPU) */
+int rxn_flux_residual_batch_device(RxnState *s, RxnConnSet *c, double *d_res);
+int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val);
+
 /* timing of the last batched kernel sequence on the handle's stream, in ms (CUDA events). */
 float rxn_last_kernel_ms(const RxnState *s);
 /* CUDA-event bracket on the handle's stream around any sequence of calls (bench.py) */

@@ -127,6 +127,39 @@ class Oracle:
             raise RuntimeError('ReactionEquilibrateConstraint failed rc=%d' % rc)
         return basis, nit.value
 
+    # ---- flux side: TFluxCoef / RTResidualFlux / RTJacobianFlux interior loops
+    @staticmethod
+    def flux_coefs(conn, naq, use_upwinding=True):
+        nconn = len(conn['id_up'])
+        Tu = np.zeros((nconn, naq))
+        Td = np.zeros((nconn, naq))
+        assert lib().orc_flux_coefs(C.c_int(naq), C.c_int64(nconn), _f64(conn['area']), _f64(conn['velocity']), _f64(conn['disp']),
+                                    _f64(conn['fraction_upwind']), C.c_int(int(use_upwinding)), _f64(Tu), _f64(Td)) == 0
+        return Tu, Td
+
+    def flux_residual(self, st: abi.HostState, conn, Tu, Td, nlocal):
+        naq = self.t.naqcomp
+        r = np.zeros((nlocal, naq))
+        v = st.view()
+        assert lib().orc_flux_residual(C.byref(v), _u8(st.active), C.c_int(naq), C.c_int64(len(conn['id_up'])), _i32(conn['id_up']),
+                                       _i32(conn['id_dn']), _i32(conn.get('g2l')), _f64(Tu), _f64(Td), C.c_int64(nlocal), _f64(r)) == 0
+        return r
+
+    def flux_jacobian(self, st: abi.HostState, conn, Tu, Td, nlocal):
+        naq = self.t.naqcomp
+        v = st.view()
+        L = lib()
+        L.orc_flux_jacobian.restype = C.c_int64
+        row_ptr = np.zeros(nlocal + 1, dtype=np.int32)
+        a = lambda col, val: (C.byref(v), _u8(st.active), C.c_int(naq), C.c_int64(len(conn['id_up'])), _i32(conn['id_up']),
+                              _i32(conn['id_dn']), _i32(conn.get('g2l')), _f64(Tu), _f64(Td), C.c_int64(nlocal),
+                              C.c_int64(st.ncells), _i32(row_ptr), _i32(col), _f64(val))
+        nnzb = L.orc_flux_jacobian(*a(None, None))
+        col = np.zeros(nnzb, dtype=np.int32)
+        val = np.zeros((nnzb, naq * naq))
+        assert L.orc_flux_jacobian(*a(col, val)) == nnzb
+        return row_ptr, col, val
+
     @staticmethod
     def rsolve(res, jac, conc, use_log):
         n = len(res)

@@ -1343,6 +1343,107 @@ int orc_rsolve(double *Res, double *Jac, const double *conc, double *update, int
   return RSolve(Res, Jac, conc, update, n, use_log != 0);
 }
 
+// ---------------------------------------------------------------- flux side
+// The reference has no unit test of TFlux/TFluxDerivative (they are exercised only through whole transport
+// regressions): this part of the oracle is UNPINNED by gold files; tests pin it with hand-computed connections
+// and conservation.
+//
+// TFluxCoef, transport.F90:756-819 (liquid phase; ngas = 0).  disp: harmonic_dispersion_over_dist(:,1) per
+// connection [nconn][naq]; velocity: internal_velocities(1,conn); fraction_upwind: dist(-1,conn).
+// Out: T_up / T_dn [nconn][naq] in L water / s.
+int orc_flux_coefs(int naq, int64_t nconn, const double *area, const double *velocity, const double *disp,
+                   const double *fraction_upwind, int use_upwinding, double *T_up, double *T_dn) {
+  for (int64_t c = 0; c < nconn; ++c) {
+    const double q = velocity[c];
+    for (int i = 0; i < naq; ++i) {
+      const double hd = disp[c * naq + i];
+      double cu, cd;
+      if (use_upwinding) {
+        if (q > 0.0) { cu = hd + q; cd = -hd; }           // :794-796
+        else { cu = hd; cd = -hd + q; }                  // :797-799
+      } else {
+        cu = hd + (1.0 - fraction_upwind[c]) * q;        // :804-807
+        cd = -hd + fraction_upwind[c] * q;
+      }
+      T_up[c * naq + i] = cu * area[c] * 1000.0;         // :813-814
+      T_dn[c * naq + i] = cd * area[c] * 1000.0;
+    }
+  }
+  return 0;
+}
+
+// Interior-connection loop of RTResidualFlux, reactive_transport.F90:2252-2310, with TFlux, transport.F90:368-439.
+// id_up/id_dn: ghosted ids (0-based); g2l: ghosted -> local (0-based, < 0 for ghost cells; NULL = identity);
+// active: imat > 0 per ghosted cell (NULL = all).  r [nlocal][naq] is zeroed first (r_p = 0.d0, :2249).
+int orc_flux_residual(const View *v, const uint8_t *active, int naq, int64_t nconn, const int32_t *id_up,
+                      const int32_t *id_dn, const int32_t *g2l, const double *T_up, const double *T_dn, int64_t nlocal,
+                      double *r) {
+  std::fill(r, r + nlocal * naq, 0.0);
+  const double *tot = v->f[RXN_F_TOTAL];
+  std::vector<double> Res(naq);
+  for (int64_t c = 0; c < nconn; ++c) {
+    const int64_t gu = id_up[c], gd = id_dn[c];
+    if (active && (!active[gu] || !active[gd])) continue;               // :2264-2265
+    for (int i = 0; i < naq; ++i)                                        // transport.F90:402-403
+      Res[i] = T_up[c * naq + i] * tot[i * v->ld + gu] + T_dn[c * naq + i] * tot[i * v->ld + gd];
+    const int64_t lu = g2l ? g2l[gu] : gu, ld_ = g2l ? g2l[gd] : gd;
+    if (lu >= 0) for (int i = 0; i < naq; ++i) r[lu * naq + i] = r[lu * naq + i] + Res[i];     // :2298-2302
+    if (ld_ >= 0) for (int i = 0; i < naq; ++i) r[ld_ * naq + i] = r[ld_ * naq + i] - Res[i];  // :2304-2308
+  }
+  return 0;
+}
+
+// Interior-connection loop of RTJacobianFlux, reactive_transport.F90:3094-3140, with TFluxDerivative,
+// transport.F90:529-622: Jup(i,j) = dtotal_up(i,j) coef_up(i), Jdn likewise; row up gets (up,up) += Jup,
+// (up,dn) += Jdn; row dn gets (dn,dn) += -Jdn, (dn,up) += -Jup (MatSetValuesBlockedLocal, ADD_VALUES).
+// The matrix is returned as block CSR over the local rows: slot 0 of a row is its diagonal block, then one slot
+// per connection of the row in connection order; blocks column-major, col = ghosted id.  Returns the number of
+// blocks (row_ptr[nlocal]); col/val may be NULL to size the arrays.
+int64_t orc_flux_jacobian(const View *v, const uint8_t *active, int naq, int64_t nconn, const int32_t *id_up,
+                          const int32_t *id_dn, const int32_t *g2l, const double *T_up, const double *T_dn, int64_t nlocal,
+                          int64_t nghosted, int32_t *row_ptr, int32_t *col, double *val) {
+  std::vector<int64_t> deg(nlocal, 1);
+  auto skip = [&](int64_t c) { return active && (!active[id_up[c]] || !active[id_dn[c]]); };
+  auto loc = [&](int64_t g) { return g2l ? (int64_t)g2l[g] : g; };
+  for (int64_t c = 0; c < nconn; ++c) {
+    if (skip(c)) continue;
+    if (loc(id_up[c]) >= 0) ++deg[loc(id_up[c])];
+    if (loc(id_dn[c]) >= 0) ++deg[loc(id_dn[c])];
+  }
+  row_ptr[0] = 0;
+  for (int64_t r = 0; r < nlocal; ++r) row_ptr[r + 1] = (int32_t)(row_ptr[r] + deg[r]);
+  const int64_t nnzb = row_ptr[nlocal];
+  if (!col || !val) return nnzb;
+  const int nn = naq * naq;
+  std::fill(val, val + nnzb * nn, 0.0);
+  for (int64_t g = 0; g < nghosted; ++g) if (loc(g) >= 0) col[row_ptr[loc(g)]] = (int32_t)g;
+  std::vector<int64_t> cur(nlocal);
+  for (int64_t r = 0; r < nlocal; ++r) cur[r] = row_ptr[r] + 1;
+  const double *D = v->f[RXN_F_DTOTAL];
+  std::vector<double> Jup(nn), Jdn(nn);
+  for (int64_t c = 0; c < nconn; ++c) {
+    if (skip(c)) continue;
+    const int64_t gu = id_up[c], gd = id_dn[c];
+    for (int j = 0; j < naq; ++j)
+      for (int i = 0; i < naq; ++i) {                                   // transport.F90:575-582
+        Jup[j * naq + i] = D[(int64_t)(j * naq + i) * v->ld + gu] * T_up[c * naq + i];
+        Jdn[j * naq + i] = D[(int64_t)(j * naq + i) * v->ld + gd] * T_dn[c * naq + i];
+      }
+    const int64_t lu = loc(gu), ld_ = loc(gd);
+    if (lu >= 0) {                                                       // :3122-3127
+      double *dg = val + (int64_t)row_ptr[lu] * nn, *od = val + cur[lu] * nn;
+      for (int e = 0; e < nn; ++e) { dg[e] = dg[e] + Jup[e]; od[e] = od[e] + Jdn[e]; }
+      col[cur[lu]++] = (int32_t)gd;
+    }
+    if (ld_ >= 0) {                                                      // :3129-3137
+      double *dg = val + (int64_t)row_ptr[ld_] * nn, *od = val + cur[ld_] * nn;
+      for (int e = 0; e < nn; ++e) { dg[e] = dg[e] + (-Jdn[e]); od[e] = od[e] + (-Jup[e]); }
+      col[cur[ld_]++] = (int32_t)gu;
+    }
+  }
+  return nnzb;
+}
+
 int orc_desc_size(void) { return (int)sizeof(RxnTablesDesc); }
 
 }  // extern "C"

@@ -20,6 +20,7 @@
 #include "rxn_pack.h"
 #include "rxn_tile.cuh"
 #include "rxn_lane.cuh"
+#include "rxn_flux.cuh"
 
 using namespace rxn;
 
@@ -77,6 +78,16 @@ struct RxnState {
   cudaStream_t h2d = nullptr, d2h = nullptr;
   cudaEvent_t ev_in[NCHUNK] = {}, ev_k[NCHUNK] = {};
   int gi_kernel = 0;       // residual/Jacobian blocks: 0 auto (resident-lane layout if the tables allow it), 1 thread per cell
+};
+
+// Row view of a connection list + the flux coefficients of the current flow field (rxn_flux.h)
+struct RxnConnSet {
+  RxnState *s = nullptr;
+  FluxRows R;
+  int n = 0;
+  int32_t *d_row_ptr = nullptr, *d_col = nullptr, *d_ent = nullptr, *d_l2g = nullptr;
+  double *d_T = nullptr;        // [T_up | T_dn], each SoA [component][connection]
+  bool have_coefs = false;
 };
 
 namespace {
@@ -731,6 +742,152 @@ int rxn_probe_fp64(RxnState *s, double *tflops) {
   }
   cudaEventDestroy(a); cudaEventDestroy(b);
   *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+  return RXN_OK;
+}
+
+// ------------------------------------------------------------------ flux side (rxn_flux.h)
+int rxn_connset_create(RxnState *s, int64_t nconn, const int32_t *id_up, const int32_t *id_dn, const int32_t *ghost_to_local,
+                       int64_t nlocal, const uint8_t *active, RxnConnSet **out) {
+  if (!s || !out || nconn < 0 || nlocal < 0 || (nconn > 0 && (!id_up || !id_dn))) return fail(RXN_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  CU(cudaSetDevice(s->t->device));
+  RxnConnSet *c = new RxnConnSet();
+  c->s = s;
+  c->n = s->t->h.naq;
+  if (!flux_rows_build(s->ncells, nlocal, nconn, id_up, id_dn, ghost_to_local, active, &c->R)) {
+    const std::string e = c->R.err;
+    delete c;
+    return fail(RXN_ERR_INVALID, "connection set: %s", e.c_str());
+  }
+  auto up = [&](int32_t **d, const std::vector<int32_t> &v) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, std::max<size_t>(v.size(), 1) * 4);
+    if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(*d, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+    return e;
+  };
+  cudaError_t e = up(&c->d_row_ptr, c->R.row_ptr);
+  if (e == cudaSuccess) e = up(&c->d_col, c->R.col);
+  if (e == cudaSuccess) e = up(&c->d_ent, c->R.ent);
+  if (e == cudaSuccess) e = up(&c->d_l2g, c->R.l2g);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_T, std::max<size_t>((size_t)2 * c->n * nconn, 1) * 8);
+  if (e != cudaSuccess) {
+    rxn_connset_destroy(c);
+    return fail(RXN_ERR_CUDA, "connection set upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return RXN_OK;
+}
+
+int rxn_connset_destroy(RxnConnSet *c) {
+  if (!c) return RXN_OK;
+  cudaSetDevice(c->s->t->device);
+  cudaFree(c->d_row_ptr); cudaFree(c->d_col); cudaFree(c->d_ent); cudaFree(c->d_l2g); cudaFree(c->d_T);
+  delete c;
+  return RXN_OK;
+}
+
+int rxn_connset_structure(const RxnConnSet *c, int64_t *nnz_blocks, int32_t *row_ptr, int32_t *col) {
+  if (!c) return fail(RXN_ERR_INVALID, "null connection set");
+  if (nnz_blocks) *nnz_blocks = c->R.nnzb;
+  if (row_ptr) memcpy(row_ptr, c->R.row_ptr.data(), c->R.row_ptr.size() * 4);
+  if (col) memcpy(col, c->R.col.data(), c->R.col.size() * 4);
+  return RXN_OK;
+}
+
+int rxn_connset_device_structure(const RxnConnSet *c, const int32_t **d_row_ptr, const int32_t **d_col) {
+  if (!c) return fail(RXN_ERR_INVALID, "null connection set");
+  if (d_row_ptr) *d_row_ptr = c->d_row_ptr;
+  if (d_col) *d_col = c->d_col;
+  return RXN_OK;
+}
+
+int rxn_connset_flux_coefs(RxnConnSet *c, const double *area, const double *velocity, const double *disp_over_dist,
+                           const double *fraction_upwind, int use_upwinding) {
+  if (!c || !area || !velocity || !disp_over_dist || (!use_upwinding && !fraction_upwind)) return fail(RXN_ERR_INVALID, "bad argument");
+  RxnState *s = c->s;
+  const long long nc = c->R.nconn;
+  const int n = c->n;
+  if (nc == 0) { c->have_coefs = true; return RXN_OK; }
+  CU(cudaSetDevice(s->t->device));
+  void *tmp;
+  int rc = ensure_scratch(s, 0, (size_t)nc * (n + 3) * 8, &tmp);
+  if (rc != RXN_OK) return rc;
+  double *d_area = (double *)tmp, *d_vel = d_area + nc, *d_fu = d_vel + nc, *d_disp = d_fu + nc;
+  CU(cudaMemcpyAsync(d_area, area, (size_t)nc * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_vel, velocity, (size_t)nc * 8, cudaMemcpyHostToDevice, s->stream));
+  if (fraction_upwind) CU(cudaMemcpyAsync(d_fu, fraction_upwind, (size_t)nc * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_disp, disp_over_dist, (size_t)nc * n * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_flux_coefs<<<nblocks(nc, 256), 256, (size_t)256 * (n | 1) * 8, s->stream>>>(n, nc, d_area, d_vel, d_disp, d_fu, use_upwinding, c->d_T,
+                                                                                c->d_T + (size_t)n * nc);
+  ++g_launches;
+  c->have_coefs = true;
+  return check_launch(s, true);
+}
+
+static int flux_ready(RxnState *s, RxnConnSet *c, int field, const char *what) {
+  if (!s || !c || c->s != s) return fail(RXN_ERR_INVALID, "bad argument (the connection set belongs to another state)");
+  if (!c->have_coefs) return fail(RXN_ERR_INVALID, "rxn_connset_flux_coefs has not been called");
+  if (!s->S.f[field]) return fail(RXN_ERR_INVALID, "%s is not materialised (rxn_state_materialize, then rxn_update_auxvars_batch)", what);
+  return RXN_OK;
+}
+
+int rxn_flux_residual_batch_device(RxnState *s, RxnConnSet *c, double *d_res) {
+  int rc = flux_ready(s, c, RXN_F_TOTAL, "total");
+  if (rc != RXN_OK) return rc;
+  if (!d_res) return fail(RXN_ERR_INVALID, "null output");
+  if (c->R.nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const int n = c->n;
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_flux_residual<<<nblocks(c->R.nlocal, 128), 128, (size_t)128 * (n | 1) * 8, s->stream>>>(
+      n, c->R.nlocal, c->R.nconn, c->d_row_ptr, c->d_col, c->d_ent, c->d_l2g, s->S.f[RXN_F_TOTAL], s->ld, c->d_T,
+      c->d_T + (size_t)n * c->R.nconn, d_res);
+  ++g_launches;
+  return check_launch(s, true);
+}
+
+int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val) {
+  int rc = flux_ready(s, c, RXN_F_DTOTAL, "dtotal");
+  if (rc != RXN_OK) return rc;
+  if (!d_val) return fail(RXN_ERR_INVALID, "null output");
+  if (c->R.nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const int n = c->n;
+  const size_t smem = (size_t)32 * ((n * n) | 1) * 8;
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_flux_jacobian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_flux_jacobian<<<nblocks(c->R.nlocal, 32), 256, smem, s->stream>>>(n, c->R.nlocal, c->R.nconn, c->R.maxdeg, c->d_row_ptr, c->d_col,
+                                                                      c->d_ent, c->d_l2g, s->S.f[RXN_F_DTOTAL], s->ld, c->d_T,
+                                                                      c->d_T + (size_t)n * c->R.nconn, d_val);
+  ++g_launches;
+  return check_launch(s, true);
+}
+
+int rxn_flux_residual_batch(RxnState *s, RxnConnSet *c, double *res_out) {
+  if (!s || !c || !res_out) return fail(RXN_ERR_INVALID, "bad argument");
+  if (c->R.nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const size_t bytes = (size_t)c->R.nlocal * c->n * 8;
+  void *d;
+  int rc = ensure_scratch(s, 1, bytes, &d);
+  if (rc != RXN_OK) return rc;
+  if ((rc = rxn_flux_residual_batch_device(s, c, (double *)d)) != RXN_OK) return rc;
+  CU(cudaMemcpyAsync(res_out, d, bytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return RXN_OK;
+}
+
+int rxn_flux_jacobian_batch(RxnState *s, RxnConnSet *c, double *val_out) {
+  if (!s || !c || !val_out) return fail(RXN_ERR_INVALID, "bad argument");
+  if (c->R.nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const size_t bytes = (size_t)c->R.nnzb * c->n * c->n * 8;
+  void *d;
+  int rc = ensure_scratch(s, 2, bytes, &d);
+  if (rc != RXN_OK) return rc;
+  if ((rc = rxn_flux_jacobian_batch_device(s, c, (double *)d)) != RXN_OK) return rc;
+  CU(cudaMemcpyAsync(val_out, d, bytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
   return RXN_OK;
 }
 

@@ -1,0 +1,160 @@
+// rxn_flux.h — flux side of the global-implicit transport residual / Jacobian on the device.
+//
+// Reference: the interior-connection loops of RTResidualFlux (reactive_transport.F90:2252-2310) and RTJacobianFlux
+// (:3094-3140) with TFluxCoef (transport.F90:756-819), TFlux (:368-439) and TFluxDerivative (:529-622), liquid phase.
+// The reference walks the connections and scatters +Res / -Res (and four Jacobian blocks) into the two cells of each
+// connection.  Here the loop is turned inside out: the host builds, once per grid, the ROW view of the connection
+// list — for every local cell its connections in connection order, with the side the cell is on — so that one GPU
+// thread owns a row and adds its contributions in exactly the order the reference's scatter would (bit-identical
+// sums, no atomics).  The same row view IS the block-CSR structure of the transport Jacobian (MATBAIJ: slot 0 of a
+// row = diagonal block, then one block per connection of the row), so the Jacobian kernel writes matrix values in
+// place, block by block, column-major as MatSetValuesBlockedLocal receives them.
+//
+// This header is pure C++ for the structure builder (also compiled by the CPU-only test harness) plus the per-element
+// arithmetic shared by the kernels (rxn_flux.cuh) and that harness.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#ifndef RXN_FLUX_FN
+#ifdef __CUDACC__
+#define RXN_FLUX_FN __host__ __device__ __forceinline__
+#else
+#define RXN_FLUX_FN inline
+#endif
+#endif
+
+namespace rxn {
+
+// products and sums are kept unfused so that the device result is the reference's (and the oracle's) bit for bit
+RXN_FLUX_FN double fl_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+RXN_FLUX_FN double fl_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+
+// TFluxCoef, transport.F90:786-814, one component of one connection
+RXN_FLUX_FN void flux_coef(double q, double hd, double area, double fraction_upwind, int use_upwinding, double *T_up, double *T_dn) {
+  double cu, cd;
+  if (use_upwinding) {
+    if (q > 0.0) { cu = fl_add(hd, q); cd = -hd; }
+    else { cu = hd; cd = fl_add(-hd, q); }
+  } else {
+    cu = fl_add(hd, fl_mul(fl_add(1.0, -fraction_upwind), q));
+    cd = fl_add(-hd, fl_mul(fraction_upwind, q));
+  }
+  *T_up = fl_mul(fl_mul(cu, area), 1000.0);
+  *T_dn = fl_mul(fl_mul(cd, area), 1000.0);
+}
+
+// TFlux, transport.F90:402-403
+RXN_FLUX_FN double flux_res(double T_up, double tot_up, double T_dn, double tot_dn) {
+  return fl_add(fl_mul(T_up, tot_up), fl_mul(T_dn, tot_dn));
+}
+
+// Row view of the connection list.  ent packs (connection << 1) | side, side 0: the row cell is the upwind cell of
+// the connection (contributes +), 1: the downwind cell (contributes -).
+struct FluxRows {
+  int64_t nlocal = 0, nconn = 0, nghosted = 0, nnzb = 0;
+  int maxdeg = 0;
+  std::vector<int32_t> row_ptr;   // nlocal + 1, in blocks (diagonal block first)
+  std::vector<int32_t> col;       // nnzb: ghosted id of the column cell
+  std::vector<int32_t> ent;       // nnzb: entry of the slot; -1 in the diagonal slot
+  std::vector<int32_t> l2g;       // nlocal: ghosted id of the row cell
+  std::string err;
+};
+
+// id_up / id_dn: ghosted ids, 0-based.  g2l: ghosted -> local (0-based, < 0: ghost), NULL = identity (nlocal = nghosted).
+// active: imat > 0 per ghosted cell, NULL = all; a connection with an inactive side is skipped (reactive_transport.F90:2264).
+inline bool flux_rows_build(int64_t nghosted, int64_t nlocal, int64_t nconn, const int32_t *id_up, const int32_t *id_dn,
+                            const int32_t *g2l, const uint8_t *active, FluxRows *R) {
+  R->nlocal = nlocal; R->nconn = nconn; R->nghosted = nghosted;
+  if (nconn >= (1LL << 30)) { R->err = "more than 2^30 connections"; return false; }
+  if (!g2l && nlocal != nghosted) { R->err = "identity ghosted->local map needs nlocal == ncells_ghosted"; return false; }
+  auto loc = [&](int64_t g) { return g2l ? (int64_t)g2l[g] : g; };
+  std::vector<int32_t> deg(nlocal, 1);
+  R->l2g.assign(nlocal, -1);
+  for (int64_t g = 0; g < nghosted; ++g) {
+    const int64_t l = loc(g);
+    if (l >= nlocal) { R->err = "ghosted->local map points outside the local range"; return false; }
+    if (l >= 0) {
+      if (R->l2g[l] >= 0) { R->err = "two ghosted cells map to one local cell"; return false; }
+      R->l2g[l] = (int32_t)g;
+    }
+  }
+  for (int64_t l = 0; l < nlocal; ++l) if (R->l2g[l] < 0) { R->err = "a local cell has no ghosted id"; return false; }
+  auto live = [&](int64_t c) { return !active || (active[id_up[c]] && active[id_dn[c]]); };
+  for (int64_t c = 0; c < nconn; ++c) {
+    if (id_up[c] < 0 || id_up[c] >= nghosted || id_dn[c] < 0 || id_dn[c] >= nghosted) { R->err = "connection id out of range"; return false; }
+    if (!live(c)) continue;
+    if (loc(id_up[c]) >= 0) ++deg[loc(id_up[c])];
+    if (loc(id_dn[c]) >= 0) ++deg[loc(id_dn[c])];
+  }
+  R->row_ptr.assign(nlocal + 1, 0);
+  int64_t acc = 0;
+  R->maxdeg = 0;
+  for (int64_t l = 0; l < nlocal; ++l) {
+    acc += deg[l];
+    if (acc > 0x7fffffffLL) { R->err = "more than 2^31 Jacobian blocks"; return false; }
+    R->row_ptr[l + 1] = (int32_t)acc;
+    if (deg[l] - 1 > R->maxdeg) R->maxdeg = deg[l] - 1;
+  }
+  R->nnzb = acc;
+  R->col.assign(acc, -1);
+  R->ent.assign(acc, -1);
+  std::vector<int32_t> cur(nlocal);
+  for (int64_t l = 0; l < nlocal; ++l) { cur[l] = R->row_ptr[l] + 1; R->col[R->row_ptr[l]] = R->l2g[l]; }
+  for (int64_t c = 0; c < nconn; ++c) {
+    if (!live(c)) continue;
+    const int64_t lu = loc(id_up[c]), ld = loc(id_dn[c]);
+    if (lu >= 0) { R->col[cur[lu]] = id_dn[c]; R->ent[cur[lu]++] = (int32_t)(c << 1); }
+    if (ld >= 0) { R->col[cur[ld]] = id_up[c]; R->ent[cur[ld]++] = (int32_t)((c << 1) | 1); }
+  }
+  return true;
+}
+
+// ---- per-row arithmetic (device layout: T_up/T_dn SoA [component][connection]; state SoA [row][cell]) ----
+
+// residual of component i of one row: the row's connections in connection order, r = r +/- Res
+RXN_FLUX_FN double flux_row_residual(const int32_t *ent, const int32_t *col, int s0, int s1, int32_t own, const double *tot_i /* total(i, :) */,
+                                     const double *Tu_i, const double *Td_i) {
+  double r = 0.0;
+  const double t_own = tot_i[own];
+  for (int s = s0 + 1; s < s1; ++s) {
+    const int32_t e = ent[s];
+    const int32_t c = e >> 1;
+    const double t_nb = tot_i[col[s]];
+    if (e & 1) r = fl_add(r, -flux_res(Tu_i[c], t_nb, Td_i[c], t_own));   // row cell is dn: up = neighbour
+    else r = fl_add(r, flux_res(Tu_i[c], t_own, Td_i[c], t_nb));
+  }
+  return r;
+}
+
+// diagonal block, element (i, j) of one row: sum over the row's connections of +Jup (row is up) / -Jdn (row is dn)
+RXN_FLUX_FN double flux_row_jac_diag(const int32_t *ent, int s0, int s1, double D_own_ij, const double *Tu_i, const double *Td_i) {
+  double a = 0.0;
+  for (int s = s0 + 1; s < s1; ++s) {
+    const int32_t e = ent[s];
+    const int32_t c = e >> 1;
+    a = fl_add(a, (e & 1) ? -fl_mul(D_own_ij, Td_i[c]) : fl_mul(D_own_ij, Tu_i[c]));
+  }
+  return a;
+}
+
+// off-diagonal block of slot s, element (i, j): +Jdn of the neighbour (row is up) / -Jup of the neighbour (row is dn)
+RXN_FLUX_FN double flux_row_jac_off(int32_t e, double D_nb_ij, const double *Tu_i, const double *Td_i) {
+  const int32_t c = e >> 1;
+  return (e & 1) ? -fl_mul(D_nb_ij, Tu_i[c]) : fl_mul(D_nb_ij, Td_i[c]);
+}
+
+}  // namespace rxn

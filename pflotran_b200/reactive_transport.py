@@ -58,6 +58,14 @@ def lib():
         L.rxn_react_kernel_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
         L.rxn_update_auxvars_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.rxn_residual_jacobian_blocks_batch_device.argtypes = [C.c_void_p, C.c_void_p, c_i64, C.c_double, C.c_void_p, C.c_void_p]
+        L.rxn_connset_create.argtypes = [C.c_void_p, c_i64, c_ip, c_ip, c_ip, c_i64, C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]
+        L.rxn_connset_destroy.argtypes = [C.c_void_p]
+        L.rxn_connset_structure.argtypes = [C.c_void_p, C.POINTER(c_i64), c_ip, c_ip]
+        L.rxn_connset_flux_coefs.argtypes = [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_int]
+        L.rxn_flux_residual_batch.argtypes = [C.c_void_p, C.c_void_p, c_dp]
+        L.rxn_flux_jacobian_batch.argtypes = [C.c_void_p, C.c_void_p, c_dp]
+        L.rxn_flux_residual_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rxn_flux_jacobian_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rxn_equilibrate_constraint_batch.argtypes = [C.c_void_p, c_ip, c_dp, c_i64, c_ip, c_dp, C.c_int, C.c_int, c_ip, c_i64,
                                                        c_dp, c_ip, c_ip]
         L.rxn_state_upload.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
@@ -131,6 +139,54 @@ class Reaction:
         if self.h:
             lib().rxn_tables_destroy(self.h)
             self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ConnectionSet:
+    """Interior connections of a grid (grid%internal_connection_set_list flattened in loop order) bound to a Realization:
+    the row view / block-CSR structure of the flux Jacobian and the TFluxCoef coefficients live on the GPU
+    (include/rxn_b200.h "Flux side")."""
+
+    def __init__(self, realization: 'Realization', id_up: np.ndarray, id_dn: np.ndarray, nlocal: int,
+                 ghost_to_local: Optional[np.ndarray] = None, active: Optional[np.ndarray] = None):
+        self.rz = realization
+        self.nlocal = int(nlocal)
+        self.nconn = len(id_up)
+        id_up = np.ascontiguousarray(id_up, dtype=np.int32)
+        id_dn = np.ascontiguousarray(id_dn, dtype=np.int32)
+        g2l = None if ghost_to_local is None else np.ascontiguousarray(ghost_to_local, dtype=np.int32)
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
+        h = C.c_void_p()
+        _ck(lib().rxn_connset_create(realization.h, self.nconn, _ip(id_up), _ip(id_dn), _ip(g2l), self.nlocal,
+                                     act.ctypes.data_as(C.POINTER(C.c_uint8)) if act is not None else None, C.byref(h)))
+        self.h = h
+        nnzb = c_i64(0)
+        _ck(lib().rxn_connset_structure(self.h, C.byref(nnzb), None, None))
+        self.nnz_blocks = nnzb.value
+
+    def structure(self):
+        row_ptr = np.zeros(self.nlocal + 1, dtype=np.int32)
+        col = np.zeros(self.nnz_blocks, dtype=np.int32)
+        _ck(lib().rxn_connset_structure(self.h, None, _ip(row_ptr), _ip(col)))
+        return row_ptr, col
+
+    def TFluxCoef(self, area, velocity, disp_over_dist, fraction_upwind=None, use_upwinding: bool = True):
+        a = np.ascontiguousarray(area, dtype=np.float64)
+        q = np.ascontiguousarray(velocity, dtype=np.float64)
+        d = np.ascontiguousarray(disp_over_dist, dtype=np.float64)
+        assert a.shape == (self.nconn,) and q.shape == (self.nconn,) and d.shape == (self.nconn, self.rz.reaction.desc.naqcomp)
+        f = None if fraction_upwind is None else np.ascontiguousarray(fraction_upwind, dtype=np.float64)
+        _ck(lib().rxn_connset_flux_coefs(self.h, _dp(a), _dp(q), _dp(d), _dp(f), int(use_upwinding)))
+
+    def close(self):
+        if getattr(self, 'h', None):
+            lib().rxn_connset_destroy(self.h)
+            self.h = None
 
     def __del__(self):
         try:
@@ -310,6 +366,25 @@ class Realization:
     def RTResidualJacobianNonFlux_device(self, nlocal: int, dt: float, d_res: int = 0, d_jac: int = 0, d_l2g: int = 0):
         _ck(lib().rxn_residual_jacobian_blocks_batch_device(self.h, C.c_void_p(d_l2g or None), nlocal, dt,
                                                             C.c_void_p(d_res or None), C.c_void_p(d_jac or None)))
+
+    def RTResidualFlux(self, conn: 'ConnectionSet') -> np.ndarray:
+        """Interior-flux part of RTResidualFlux: r_p [nlocal, ncomp]."""
+        r = np.zeros((conn.nlocal, self.ncomp))
+        _ck(lib().rxn_flux_residual_batch(self.h, conn.h, _dp(r)))
+        return r
+
+    def RTJacobianFlux(self, conn: 'ConnectionSet') -> np.ndarray:
+        """Interior-flux part of RTJacobianFlux: block values [nnz_blocks, ncomp*ncomp] in conn.structure()."""
+        n = self.ncomp
+        val = np.zeros((conn.nnz_blocks, n * n))
+        _ck(lib().rxn_flux_jacobian_batch(self.h, conn.h, _dp(val)))
+        return val
+
+    def RTResidualFlux_device(self, conn: 'ConnectionSet', d_res: int):
+        _ck(lib().rxn_flux_residual_batch_device(self.h, conn.h, C.c_void_p(d_res)))
+
+    def RTJacobianFlux_device(self, conn: 'ConnectionSet', d_val: int):
+        _ck(lib().rxn_flux_jacobian_batch_device(self.h, conn.h, C.c_void_p(d_val)))
 
     def RTReact_device(self, d_xx: int, nlocal: int, dt: float, dt_mode: int = abi.RXN_DT_CONSISTENT,
                        d_l2g: int = 0, d_iters: int = 0, d_flags: int = 0):

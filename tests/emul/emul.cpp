@@ -19,6 +19,7 @@ using std::isfinite;
 #undef RXN_IDEAL_GAS_CONSTANT
 #define RXN_LANE_HOST 1
 #include "../../pflotran_b200/csrc/rxn_lane_dev.cuh"
+#include "../../pflotran_b200/csrc/rxn_flux.h"
 
 using namespace rxn;
 
@@ -313,4 +314,40 @@ int emu_update_kinetic_state_batch(void *h, const HostView *v, const uint8_t *ac
   return 0;
 }
 
+// Flux side (rxn_flux.h): the structure builder and the per-row arithmetic the kernels of rxn_flux.cuh call, run in
+// plain loops with the kernels' index maps (coefficients SoA [component][connection], block CSR output).
+// Returns the number of Jacobian blocks, < 0 on a structure error; row_ptr (nlocal+1) is always written, the other
+// outputs only when non-NULL.
+int64_t emu_flux(const HostView *v, const uint8_t *active, int n, int64_t nconn, const int32_t *id_up, const int32_t *id_dn,
+                 const int32_t *g2l, int64_t nlocal, const double *area, const double *velocity, const double *disp,
+                 const double *fraction_upwind, int use_upwinding, int32_t *row_ptr, int32_t *col, double *res, double *val) {
+  FluxRows R;
+  if (!flux_rows_build(v->ncells, nlocal, nconn, id_up, id_dn, g2l, active, &R)) return -1;
+  memcpy(row_ptr, R.row_ptr.data(), R.row_ptr.size() * 4);
+  if (col) memcpy(col, R.col.data(), R.col.size() * 4);
+  std::vector<double> Tu((size_t)n * nconn), Td((size_t)n * nconn);
+  for (int64_t c = 0; c < nconn; ++c)
+    for (int i = 0; i < n; ++i)
+      flux_coef(velocity[c], disp[c * n + i], area[c], use_upwinding ? 0.0 : fraction_upwind[c], use_upwinding, &Tu[(size_t)i * nconn + c],
+                &Td[(size_t)i * nconn + c]);
+  const double *tot = v->f[RXN_F_TOTAL], *D = v->f[RXN_F_DTOTAL];
+  for (int64_t r = 0; r < nlocal; ++r) {
+    const int s0 = R.row_ptr[r], s1 = R.row_ptr[r + 1];
+    const int32_t own = R.l2g[r];
+    if (res)
+      for (int i = 0; i < n; ++i)
+        res[r * n + i] = flux_row_residual(R.ent.data(), R.col.data(), s0, s1, own, tot + (int64_t)i * v->ld, &Tu[(size_t)i * nconn], &Td[(size_t)i * nconn]);
+    if (val)
+      for (int k = 0; k < s1 - s0; ++k)
+        for (int e = 0; e < n * n; ++e) {
+          const int i = e % n;
+          double *dst = val + (int64_t)(s0 + k) * n * n;
+          dst[e] = k == 0 ? flux_row_jac_diag(R.ent.data(), s0, s1, D[(int64_t)e * v->ld + own], &Tu[(size_t)i * nconn], &Td[(size_t)i * nconn])
+                          : flux_row_jac_off(R.ent[s0 + k], D[(int64_t)e * v->ld + R.col[s0 + k]], &Tu[(size_t)i * nconn], &Td[(size_t)i * nconn]);
+        }
+  }
+  return R.nnzb;
+}
+
 }  // extern "C"
+

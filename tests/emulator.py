@@ -19,7 +19,7 @@ _LIB = None
 def build(force=False):
     so = os.path.join(_HERE, 'libemul.so')
     deps = [os.path.join(_HERE, 'emul.cpp')] + [os.path.join(_ROOT, 'pflotran_b200', 'csrc', f)
-                                                 for f in ('rxn_device.cuh', 'rxn_pack.h', 'rxn_tab.h', 'rxn_lane.h', 'rxn_lane_dev.cuh')] + \
+                                                 for f in ('rxn_device.cuh', 'rxn_pack.h', 'rxn_tab.h', 'rxn_lane.h', 'rxn_lane_dev.cuh', 'rxn_flux.h')] + \
         [os.path.join(_ROOT, 'include', 'rxn_b200.h')]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-pthread',
@@ -154,3 +154,27 @@ class Emulator:
     def update_kinetic_state(self, st, dt):
         v = st.view()
         assert lib().emu_update_kinetic_state_batch(self.h, C.byref(v), _p(st.active, C.c_uint8), C.c_double(dt)) == 0
+
+
+def flux(st, conn, nlocal, use_upwinding=True):
+    """Flux residual / Jacobian through the structure builder and per-row arithmetic of rxn_flux.h (the code the CUDA kernels call).
+    conn: dict(id_up, id_dn, g2l|None, area, velocity, disp [nconn, naq], fraction_upwind).  Returns row_ptr, col, res, val."""
+    n = st.t.naqcomp
+    nconn = len(conn['id_up'])
+    v = st.view()
+    L = lib()
+    L.emu_flux.restype = C.c_int64
+    row_ptr = np.zeros(nlocal + 1, dtype=np.int32)
+    args = lambda col, res, val: (C.byref(v), _p(st.active, C.c_uint8), C.c_int(n), C.c_int64(nconn), _p(conn['id_up'], C.c_int32),
+                                  _p(conn['id_dn'], C.c_int32), _p(conn.get('g2l'), C.c_int32), C.c_int64(nlocal),
+                                  _p(conn['area'], C.c_double), _p(conn['velocity'], C.c_double), _p(conn['disp'], C.c_double),
+                                  _p(conn['fraction_upwind'], C.c_double), C.c_int(int(use_upwinding)), _p(row_ptr, C.c_int32),
+                                  _p(col, C.c_int32), _p(res, C.c_double), _p(val, C.c_double))
+    nnzb = L.emu_flux(*args(None, None, None))
+    if nnzb < 0:
+        raise ValueError('connection set rejected')
+    col = np.zeros(nnzb, dtype=np.int32)
+    res = np.zeros((nlocal, n))
+    val = np.zeros((nnzb, n * n))
+    assert L.emu_flux(*args(col, res, val)) == nnzb
+    return row_ptr, col, res, val

@@ -1,0 +1,105 @@
+"""GPU tests of the flux side: rxn_connset_* / rxn_flux_*_batch through the C ABI against the oracle's
+restatement of the RTResidualFlux / RTJacobianFlux interior loops.  With the same total / dtotal in the state the kernels add
+in the reference's order, so the comparison is bit for bit."""
+import numpy as np
+import pytest
+
+from pflotran_b200 import synth, reactive_transport as rt
+from oracle.pyoracle import Oracle
+from common import workload_cells, RTOL
+from flux_common import structured_connections
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(name, nx, ny, nz, ghost, inactive, seed=11):
+    g = ghost
+    ncell = (nx + 2 * g) * (ny + 2 * g) * (nz + 2 * g)
+    w, cells = workload_cells(name, ncell)
+    st = synth.host_state(w, cells)
+    rng = np.random.default_rng(seed)
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.2 * rng.standard_normal((ncell, w.ncomp))))
+    conn, nghosted, nlocal, active = structured_connections(nx, ny, nz, w.tables.naqcomp, ghost_layers=g, inactive_fraction=inactive)
+    st.active = active
+    return w, st, xx, conn, nlocal
+
+
+@pytest.mark.parametrize('name,dims,ghost,inactive,upwind', [
+    ('calcite', (37, 9, 5), 0, 0.0, True), ('calcite', (33, 7, 3), 1, 0.1, False),
+    ('hanford300a_eq', (19, 6, 5), 1, 0.05, True), ('hanford300a_eq', (65, 3, 2), 0, 0.0, False),
+    ('hanford300a_mr', (8, 4, 3), 0, 0.0, True), ('hpt_calcite', (31, 1, 1), 0, 0.0, True)])
+def test_flux_residual_and_jacobian_bitwise(name, dims, ghost, inactive, upwind):
+    w, st, xx, conn, nlocal = _setup(name, *dims, ghost, inactive)
+    o = Oracle(w.tables)
+    o.update_auxvars(st, xx, True)
+    n = w.tables.naqcomp
+    Tu, Td = o.flux_coefs(conn, n, use_upwinding=upwind)
+    r_o = o.flux_residual(st, conn, Tu, Td, nlocal)
+    rp_o, col_o, val_o = o.flux_jacobian(st, conn, Tu, Td, nlocal)
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, st.ncells)
+    rz.upload_host_state(st)
+    rz.upload('DTOTAL', st['DTOTAL'])
+    cs = rt.ConnectionSet(rz, conn['id_up'], conn['id_dn'], nlocal, conn['g2l'], st.active)
+    rp, col = cs.structure()
+    np.testing.assert_array_equal(rp, rp_o)
+    np.testing.assert_array_equal(col, col_o)
+    cs.TFluxCoef(conn['area'], conn['velocity'], conn['disp'], conn['fraction_upwind'], upwind)
+    r_g = rz.RTResidualFlux(cs)
+    val_g = rz.RTJacobianFlux(cs)
+    np.testing.assert_array_equal(r_g, r_o)
+    np.testing.assert_array_equal(val_g, val_o)
+    # device-resident outputs (PETSc VECCUDA / MATSEQBAIJ value array on the GPU)
+    d_r = rz.device_alloc(r_o.nbytes)
+    d_v = rz.device_alloc(val_o.nbytes)
+    rz.RTResidualFlux_device(cs, d_r)
+    rz.RTJacobianFlux_device(cs, d_v)
+    r_d = np.zeros_like(r_o); v_d = np.zeros_like(val_o)
+    rz.device_copy(r_d, d_r, r_o.nbytes, 1)
+    rz.device_copy(v_d, d_v, val_o.nbytes, 1)
+    np.testing.assert_array_equal(r_d, r_o)
+    np.testing.assert_array_equal(v_d, val_o)
+    rz.device_free(d_r); rz.device_free(d_v)
+    cs.close()
+
+
+def test_flux_after_device_auxvars():
+    """The live sequence of a Newton iteration: RTUpdateAuxVars on the device (total, dtotal), then the flux kernels, against the
+    oracle doing the same on the host; compared on the scale of the flux terms (a cell's fluxes nearly cancel)."""
+    w, st, xx, conn, nlocal = _setup('hanford300a_eq', 12, 6, 5, 0, 0.0)
+    n = w.tables.naqcomp
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, st.ncells)
+    rz.upload_host_state(st)
+    rz.materialize('DTOTAL')
+    rz.RTUpdateAuxVars(xx, True)
+    cs = rt.ConnectionSet(rz, conn['id_up'], conn['id_dn'], nlocal)
+    cs.TFluxCoef(conn['area'], conn['velocity'], conn['disp'])
+    r_g = rz.RTResidualFlux(cs)
+    val_g = rz.RTJacobianFlux(cs)
+    o = Oracle(w.tables)
+    o.update_auxvars(st, xx, True)
+    Tu, Td = o.flux_coefs(conn, n)
+    r_o = o.flux_residual(st, conn, Tu, Td, nlocal)
+    _, _, val_o = o.flux_jacobian(st, conn, Tu, Td, nlocal)
+    tmag = np.abs(st['PRI_MOLAL']).T + (np.abs(st['TOTAL']).T)      # scale of total_i (cancelling stoichiometries)
+    rscale = 6 * np.abs(Tu).max(axis=0)[None, :] * tmag.max(axis=0)[None, :]
+    assert (np.abs(r_g - r_o) <= RTOL * rscale).all()
+    vscale = np.abs(val_o).max(axis=0)[None, :]
+    assert (np.abs(val_g - val_o) <= RTOL * np.maximum(np.abs(val_o), vscale)).all()
+
+
+def test_flux_entry_point_errors():
+    w, st, xx, conn, nlocal = _setup('calcite', 4, 3, 2, 0, 0.0)
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, st.ncells)
+    rz.upload_host_state(st)
+    cs = rt.ConnectionSet(rz, conn['id_up'], conn['id_dn'], nlocal)
+    with pytest.raises(rt.RxnError):            # coefficients not set
+        rz.RTResidualFlux(cs)
+    cs.TFluxCoef(conn['area'], conn['velocity'], conn['disp'])
+    with pytest.raises(rt.RxnError):            # dtotal not materialised
+        rz.RTJacobianFlux(cs)
+    bad = conn['id_dn'].copy(); bad[0] = 10 ** 6
+    with pytest.raises(rt.RxnError):
+        rt.ConnectionSet(rz, conn['id_up'], bad, nlocal)
