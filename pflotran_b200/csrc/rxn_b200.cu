@@ -77,6 +77,7 @@ struct RxnState {
   enum { NCHUNK = 8 };
   cudaStream_t h2d = nullptr, d2h = nullptr;
   cudaEvent_t ev_in[NCHUNK] = {}, ev_k[NCHUNK] = {};
+  int flux_generic = 0;    // RXN_FLUX_GENERIC=1: flux Jacobian through the run-time-n kernel (tests)
   int gi_kernel = 0;       // residual/Jacobian blocks: 0 auto (resident-lane layout if the tables allow it), 1 thread per cell
 };
 
@@ -250,6 +251,7 @@ int rxn_state_create(const RxnTables *t, int64_t ncells, RxnState **out) {
   s->S.ld = s->ld; s->S.ncells = ncells;
   if (const char *e = getenv("RXN_REACT_KERNEL")) s->react_kernel = atoi(e);
   if (const char *e = getenv("RXN_GI_KERNEL")) s->gi_kernel = atoi(e);
+  if (const char *e = getenv("RXN_FLUX_GENERIC")) s->flux_generic = atoi(e);
   int rc = RXN_OK;
   if (cudaStreamCreate(&s->stream) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
     rc = fail(RXN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -853,12 +855,25 @@ int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val) {
   if (c->R.nlocal == 0) return RXN_OK;
   CU(cudaSetDevice(s->t->device));
   const int n = c->n;
-  const size_t smem = (size_t)32 * ((n * n) | 1) * 8;
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_flux_jacobian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CU(cudaEventRecord(s->ev0, s->stream));
-  k_flux_jacobian<<<nblocks(c->R.nlocal, 32), 256, smem, s->stream>>>(n, c->R.nlocal, c->R.nconn, c->R.maxdeg, c->d_row_ptr, c->d_col,
-                                                                      c->d_ent, c->d_l2g, s->S.f[RXN_F_DTOTAL], s->ld, c->d_T,
-                                                                      c->d_T + (size_t)n * c->R.nconn, d_val);
+  const unsigned tiles = nblocks(c->R.nlocal, 32);
+#define FLUX_JAC_T(N_, JC_)                                                                                                    \
+  k_flux_jacobian_t<N_, JC_><<<tiles * (N_ / JC_), 128, 0, s->stream>>>(c->R.nlocal, c->R.nconn, c->d_row_ptr, c->d_col, c->d_ent, \
+                                                                          c->d_l2g, s->S.f[RXN_F_DTOTAL], s->ld, c->d_T,       \
+                                                                          c->d_T + (size_t)n * c->R.nconn, d_val)
+  if (n == 15 && !s->flux_generic) FLUX_JAC_T(15, 5);
+  else if (n == 4 && !s->flux_generic) FLUX_JAC_T(4, 4);
+  else if (n == 3 && !s->flux_generic) FLUX_JAC_T(3, 3);
+  else {
+    // column chunks of about 80 elements of a block per CTA (rxn_flux.cuh)
+    int nchunk = (n * n + 79) / 80;
+    const int jc = std::min((n + nchunk - 1) / nchunk, (int)FLUX_JC);
+    nchunk = (n + jc - 1) / jc;
+    const size_t smem = (size_t)32 * ((jc * n) | 1) * 8;
+    k_flux_jacobian<<<dim3(tiles, nchunk), 128, smem, s->stream>>>(n, jc, c->R.nlocal, c->R.nconn, c->d_row_ptr, c->d_col, c->d_ent, c->d_l2g,
+                                                                   s->S.f[RXN_F_DTOTAL], s->ld, c->d_T, c->d_T + (size_t)n * c->R.nconn, d_val);
+  }
+#undef FLUX_JAC_T
   ++g_launches;
   return check_launch(s, true);
 }

@@ -33,6 +33,22 @@ __global__ void __launch_bounds__(256) k_flux_coefs(int n, long long nconn, cons
 }
 
 // Flux residual of every local row: one warp per tile of 32 rows, lane = row.  r: AoS [nlocal][n].
+// The first FLUX_Q entries of a row (6 on a structured grid) are kept in registers across the component loop.
+enum { FLUX_Q = 6, FLUX_JC = 8 };
+
+// dtotal is read up to 7 times (the cell itself and its neighbours' rows) while the matrix streams through L2 once:
+// loads ask L2 to keep the line (evict_last), stores are streaming (st.global.cs)
+__device__ __forceinline__ unsigned long long flux_keep_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double flux_ld_keep(const double *p, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 __global__ void __launch_bounds__(128) k_flux_residual(int n, long long nlocal, long long nconn, const int32_t *__restrict__ row_ptr,
                                                       const int32_t *__restrict__ col, const int32_t *__restrict__ ent,
                                                       const int32_t *__restrict__ l2g, const double *__restrict__ total, long long ld,
@@ -45,63 +61,239 @@ __global__ void __launch_bounds__(128) k_flux_residual(int n, long long nlocal, 
   if (row0 >= nlocal) return;
   const long long row = row0 + lane;
   if (row < nlocal) {
-    const int s0 = row_ptr[row], s1 = row_ptr[row + 1];
+    const int s0 = row_ptr[row], s1 = row_ptr[row + 1], deg = s1 - s0 - 1;
     const int32_t own = l2g[row];
-    for (int i = 0; i < n; ++i)
-      tile[lane * ldp + i] = flux_row_residual(ent, col, s0, s1, own, total + (long long)i * ld, T_up + (long long)i * nconn,
-                                               T_dn + (long long)i * nconn);
+    int32_t en[FLUX_Q], nb[FLUX_Q];
+#pragma unroll
+    for (int q = 0; q < FLUX_Q; ++q) {
+      en[q] = q < deg ? ent[s0 + 1 + q] : 0;
+      nb[q] = q < deg ? col[s0 + 1 + q] : own;
+    }
+    for (int i = 0; i < n; ++i) {
+      const double *tot_i = total + (long long)i * ld, *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn;
+      const double t_own = tot_i[own];
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < FLUX_Q; ++q)
+        if (q < deg) {
+          const int32_t c = en[q] >> 1;
+          const double t_nb = tot_i[nb[q]];
+          acc = (en[q] & 1) ? fl_add(acc, -flux_res(Tu_i[c], t_nb, Td_i[c], t_own)) : fl_add(acc, flux_res(Tu_i[c], t_own, Td_i[c], t_nb));
+        }
+      for (int s = s0 + 1 + FLUX_Q; s < s1; ++s) {       // rows with more connections than the register window
+        const int32_t e = ent[s], c = e >> 1;
+        const double t_nb = tot_i[col[s]];
+        acc = (e & 1) ? fl_add(acc, -flux_res(Tu_i[c], t_nb, Td_i[c], t_own)) : fl_add(acc, flux_res(Tu_i[c], t_own, Td_i[c], t_nb));
+      }
+      tile[lane * ldp + i] = acc;
+    }
   }
   __syncwarp();
   const long long span = min((long long)32, nlocal - row0) * n;
   for (long long k = lane; k < span; k += 32) r[row0 * n + k] = tile[(k / n) * ldp + k % n];
 }
 
-// Flux Jacobian in block CSR.  One CTA (8 warps) per tile of 32 rows; slot by slot (0 = diagonal block) the tile's
-// blocks are computed with lane = row (coalesced dtotal reads of the row cell / its neighbour), staged in shared
-// memory and written out with lane = element of the block.  val: [nnzb][n*n], blocks column-major.
-__global__ void __launch_bounds__(256) k_flux_jacobian(int n, long long nlocal, long long nconn, int maxdeg,
+// Flux Jacobian in block CSR.  val: [nnzb][n*n], blocks column-major.
+// grid = (tiles of 32 rows, column chunks of the block): a CTA of 4 warps owns jc columns (cw = jc*n elements) of every block of
+// its 32 rows.  Slot by slot (0 = diagonal block) the chunk is computed with lane = row — coalesced cell-fastest reads of
+// dtotal of the row cell / its neighbour, the jc loads of a block row issued together, the coefficient of (slot, i) loaded
+// once — staged in shared memory ([32][cw | 1], conflict free both ways) and written with lane = element as contiguous runs of
+// cw doubles per block, streaming (the matrix is written once and not read here: keep L2 for the neighbours' dtotal).
+__global__ void __launch_bounds__(128) k_flux_jacobian(int n, int jc, long long nlocal, long long nconn,
                                                       const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                                                       const int32_t *__restrict__ ent, const int32_t *__restrict__ l2g,
                                                       const double *__restrict__ dtotal, long long ld,
                                                       const double *__restrict__ T_up, const double *__restrict__ T_dn,
                                                       double *__restrict__ val) {
-  extern __shared__ double sh[];               // [32][n*n | 1]
-  const int nn = n * n, ldp = nn | 1, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  extern __shared__ double sh[];               // [32][cw | 1]
+  __shared__ int sh_s0[32], sh_ns[32];
+  const int nn = n * n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j0 = blockIdx.y * jc, jn = min(jc, n - j0);           // columns j0 .. j0+jn-1 of every block
+  const int cw = jn * n, ldp = (jc * n) | 1;
   const long long row0 = (long long)blockIdx.x * 32;
   const long long row = row0 + lane;
   int s0 = 0, s1 = 0;
   int32_t own = 0;
   if (row < nlocal) { s0 = row_ptr[row]; s1 = row_ptr[row + 1]; own = l2g[row]; }
-  // number of slots any row of the tile has (uniform across the CTA)
-  int nslot = s1 - s0;
+  const int ns = s1 - s0, deg = ns - 1;
+  if (w == 0) { sh_s0[lane] = s0; sh_ns[lane] = ns; }
+  int nslot = ns;                                                 // slots of the longest row of the tile (CTA uniform)
   for (int o = 16; o; o >>= 1) nslot = max(nslot, __shfl_xor_sync(0xffffffffu, nslot, o));
   const int rows_here = (int)min((long long)32, nlocal - row0);
+  const int lsh = cw > 16 ? 5 : cw > 8 ? 4 : cw > 4 ? 3 : 2;      // log2 of the lanes that write one row's run
+  int32_t en[FLUX_Q];
+#pragma unroll
+  for (int q = 0; q < FLUX_Q; ++q) en[q] = q < deg ? ent[s0 + 1 + q] : 0;
+  const double *D0 = dtotal + (long long)j0 * n * ld;             // element (i, j0 + jj) of cell c at D0[(jj*n + i)*ld + c]
   for (int k = 0; k < nslot; ++k) {
-    if (k < s1 - s0) {
+    if (k < ns) {
       if (k == 0) {
-        for (int e = w; e < nn; e += 8) {
-          const int i = e % n;
-          sh[lane * ldp + e] = flux_row_jac_diag(ent, s0, s1, dtotal[(long long)e * ld + own], T_up + (long long)i * nconn,
-                                                 T_dn + (long long)i * nconn);
+        for (int i = w; i < n; i += 4) {
+          const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn;
+          double d[FLUX_JC], sc[FLUX_Q];
+#pragma unroll
+          for (int jj = 0; jj < FLUX_JC; ++jj) d[jj] = jj < jn ? D0[(long long)(jj * n + i) * ld + own] : 0.0;
+#pragma unroll
+          for (int q = 0; q < FLUX_Q; ++q) sc[q] = q < deg ? ((en[q] & 1) ? -Td_i[en[q] >> 1] : Tu_i[en[q] >> 1]) : 0.0;
+#pragma unroll
+          for (int jj = 0; jj < FLUX_JC; ++jj)
+            if (jj < jn) {
+              double a = 0.0;
+#pragma unroll
+              for (int q = 0; q < FLUX_Q; ++q) if (q < deg) a = fl_add(a, fl_mul(d[jj], sc[q]));
+              for (int s = s0 + 1 + FLUX_Q; s < s1; ++s) {
+                const int32_t e = ent[s];
+                a = fl_add(a, fl_mul(d[jj], (e & 1) ? -Td_i[e >> 1] : Tu_i[e >> 1]));
+              }
+              sh[lane * ldp + jj * n + i] = a;
+            }
         }
       } else {
-        const int32_t en = ent[s0 + k], nb = col[s0 + k];
-        for (int e = w; e < nn; e += 8) {
-          const int i = e % n;
-          sh[lane * ldp + e] = flux_row_jac_off(en, dtotal[(long long)e * ld + nb], T_up + (long long)i * nconn,
-                                                T_dn + (long long)i * nconn);
+        const int32_t e = k <= FLUX_Q ? 0 : ent[s0 + k];
+        int32_t ek = e;
+#pragma unroll
+        for (int q = 0; q < FLUX_Q; ++q) if (k == q + 1) ek = en[q];
+        const int32_t nb = col[s0 + k], c = ek >> 1;
+        for (int i = w; i < n; i += 4) {
+          const double so = (ek & 1) ? -T_up[(long long)i * nconn + c] : T_dn[(long long)i * nconn + c];
+          double d[FLUX_JC];
+#pragma unroll
+          for (int jj = 0; jj < FLUX_JC; ++jj) d[jj] = jj < jn ? D0[(long long)(jj * n + i) * ld + nb] : 0.0;
+#pragma unroll
+          for (int jj = 0; jj < FLUX_JC; ++jj) if (jj < jn) sh[lane * ldp + jj * n + i] = fl_mul(d[jj], so);
         }
       }
     }
     __syncthreads();
-    for (int rr = w; rr < rows_here; rr += 8) {
-      const int t0 = __shfl_sync(0xffffffffu, s0, rr), t1 = __shfl_sync(0xffffffffu, s1, rr);
-      if (k < t1 - t0) {
-        double *dst = val + (long long)(t0 + k) * nn;
-        for (int e = lane; e < nn; e += 32) dst[e] = sh[rr * ldp + e];
+    // lpr lanes per row (a power of two >= min(cw, 32)): 32/lpr rows per warp pass
+    for (int rr = w * (32 >> lsh) + (lane >> lsh); rr < rows_here; rr += 4 * (32 >> lsh))
+      if (k < sh_ns[rr]) {
+        double *dst = val + (long long)(sh_s0[rr] + k) * nn + j0 * n;
+        const double *src = sh + rr * ldp;
+        for (int e = lane & ((1 << lsh) - 1); e < cw; e += 1 << lsh) __stcs(dst + e, src[e]);
+      }
+    __syncthreads();
+  }
+}
+
+// Same kernel with the block size known at compile time (the BASELINE chemistries: N = 15 in chunks of 5 columns, N = 4 and
+// N = 3 whole): every index is an immediate, the loops are unrolled, and the staging tile is double buffered so that one
+// barrier per slot suffices and the loads of slot k+1 are in flight while slot k is written out.
+#ifndef FLUX_MINB
+#define FLUX_MINB 4
+#endif
+template <int N, int JC>
+__global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nlocal, long long nconn, const int32_t *__restrict__ row_ptr,
+                                                        const int32_t *__restrict__ col, const int32_t *__restrict__ ent,
+                                                        const int32_t *__restrict__ l2g, const double *__restrict__ dtotal, long long ld,
+                                                        const double *__restrict__ T_up, const double *__restrict__ T_dn,
+                                                        double *__restrict__ val) {
+  static_assert(N % JC == 0, "column chunks must tile the block");
+  constexpr int NN = N * N, CW = JC * N, LDP = CW | 1;
+  constexpr int LSH = CW > 16 ? 5 : CW > 8 ? 4 : CW > 4 ? 3 : 2, LPR = 1 << LSH, RPP = 32 >> LSH;   // lanes per row run, rows per warp pass
+  __shared__ double sh[2][32 * LDP];
+  __shared__ int sh_s0[32], sh_ns[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int NCH = N / JC;                                      // the chunks of a tile are adjacent blocks: their partial
+  const int j0 = (int)(blockIdx.x % NCH) * JC;                     // sectors at the chunk seams meet in L2
+  const long long row0 = (long long)(blockIdx.x / NCH) * 32;
+  const unsigned long long keep = flux_keep_policy();
+  const long long row = row0 + lane;
+  int s0 = 0, s1 = 0;
+  int32_t own = 0;
+  if (row < nlocal) { s0 = row_ptr[row]; s1 = row_ptr[row + 1]; own = l2g[row]; }
+  const int ns = s1 - s0, deg = ns - 1;
+  if (w == 0) { sh_s0[lane] = s0; sh_ns[lane] = ns; }
+  int nslot = ns;
+  for (int o = 16; o; o >>= 1) nslot = max(nslot, __shfl_xor_sync(0xffffffffu, nslot, o));
+  const int rows_here = (int)min((long long)32, nlocal - row0);
+  int32_t en[FLUX_Q];
+#pragma unroll
+  for (int q = 0; q < FLUX_Q; ++q) en[q] = q < deg ? ent[s0 + 1 + q] : 0;
+  const long long sj = (long long)N * ld;                          // stride of one block column in dtotal
+  const double *D0 = dtotal + (long long)j0 * sj;
+  for (int k = 0; k < nslot; ++k) {
+    double *tile = sh[k & 1] + lane * LDP;
+    if (k < ns) {
+      if (k == 0) {
+        // two block rows at a time: their 2*(JC + FLUX_Q) loads are issued together
+        constexpr int NI = (N + 3) / 4;
+#pragma unroll
+        for (int i2 = 0; i2 < NI; i2 += 2) {
+          double d[2][JC], sc[2][FLUX_Q];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = w + 4 * (i2 + u);
+            if (i2 + u < NI && i < N) {
+              const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn, *p = D0 + (long long)i * ld + own;
+#pragma unroll
+              for (int jj = 0; jj < JC; ++jj) d[u][jj] = flux_ld_keep(p + jj * sj, keep);
+#pragma unroll
+              for (int q = 0; q < FLUX_Q; ++q) sc[u][q] = q < deg ? ((en[q] & 1) ? -Td_i[en[q] >> 1] : Tu_i[en[q] >> 1]) : 0.0;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = w + 4 * (i2 + u);
+            if (i2 + u < NI && i < N) {
+              const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn;
+#pragma unroll
+              for (int jj = 0; jj < JC; ++jj) {
+                double a = 0.0;
+#pragma unroll
+                for (int q = 0; q < FLUX_Q; ++q) if (q < deg) a = fl_add(a, fl_mul(d[u][jj], sc[u][q]));
+                for (int s = s0 + 1 + FLUX_Q; s < s1; ++s) {
+                  const int32_t e = ent[s];
+                  a = fl_add(a, fl_mul(d[u][jj], (e & 1) ? -Td_i[e >> 1] : Tu_i[e >> 1]));
+                }
+                tile[jj * N + i] = a;
+              }
+            }
+          }
+        }
+      } else {
+        int32_t ek = k <= FLUX_Q ? 0 : ent[s0 + k];
+#pragma unroll
+        for (int q = 0; q < FLUX_Q; ++q) if (k == q + 1) ek = en[q];
+        const int32_t nb = col[s0 + k];
+        const double *To = ((ek & 1) ? T_up : T_dn) + (ek >> 1);
+        const double sgn = (ek & 1) ? -1.0 : 1.0;                  // exact: -(D T) == D (-T)
+        // all loads of the slot first (NI*JC + NI independent requests per thread), then the products
+        constexpr int NI = (N + 3) / 4;
+        double d[NI][JC], so[NI];
+#pragma unroll
+        for (int ii = 0; ii < NI; ++ii) {
+          const int i = w + 4 * ii;
+          if (i < N) {
+            const double *p = D0 + (long long)i * ld + nb;
+#pragma unroll
+            for (int jj = 0; jj < JC; ++jj) d[ii][jj] = flux_ld_keep(p + jj * sj, keep);
+            so[ii] = To[(long long)i * nconn];
+          }
+        }
+#pragma unroll
+        for (int ii = 0; ii < NI; ++ii) {
+          const int i = w + 4 * ii;
+          if (i < N) {
+            const double sv = sgn * so[ii];
+#pragma unroll
+            for (int jj = 0; jj < JC; ++jj) tile[jj * N + i] = fl_mul(d[ii][jj], sv);
+          }
+        }
       }
     }
     __syncthreads();
+    const double *stage = sh[k & 1];
+    for (int rr = w * RPP + (lane >> LSH); rr < rows_here; rr += 4 * RPP)
+      if (k < sh_ns[rr]) {
+        double *dst = val + (long long)(sh_s0[rr] + k) * NN + j0 * N;
+        const double *src = stage + rr * LDP;
+#pragma unroll
+        for (int t = 0; t < (CW + LPR - 1) / LPR; ++t) {
+          const int e = (lane & (LPR - 1)) + t * LPR;
+          if (e < CW) __stcs(dst + e, src[e]);
+        }
+      }
   }
 }
 

@@ -28,7 +28,10 @@ def _setup(name, nx, ny, nz, ghost, inactive, seed=11):
     ('calcite', (37, 9, 5), 0, 0.0, True), ('calcite', (33, 7, 3), 1, 0.1, False),
     ('hanford300a_eq', (19, 6, 5), 1, 0.05, True), ('hanford300a_eq', (65, 3, 2), 0, 0.0, False),
     ('hanford300a_mr', (8, 4, 3), 0, 0.0, True), ('hpt_calcite', (31, 1, 1), 0, 0.0, True)])
-def test_flux_residual_and_jacobian_bitwise(name, dims, ghost, inactive, upwind):
+@pytest.mark.parametrize('generic', [0, 1])
+def test_flux_residual_and_jacobian_bitwise(name, dims, ghost, inactive, upwind, generic, monkeypatch):
+    """generic = 1: the run-time-n Jacobian kernel (any chemistry) instead of the compile-time-n instantiation."""
+    monkeypatch.setenv('RXN_FLUX_GENERIC', str(generic))
     w, st, xx, conn, nlocal = _setup(name, *dims, ghost, inactive)
     o = Oracle(w.tables)
     o.update_auxvars(st, xx, True)
