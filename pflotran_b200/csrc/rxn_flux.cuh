@@ -182,6 +182,20 @@ __global__ void __launch_bounds__(128) k_flux_jacobian(int n, int jc, long long 
 #ifndef FLUX_MINB
 #define FLUX_MINB 4
 #endif
+// FLUX_MODE (experiments only, profiles/): 1 = no matrix stores, 2 = no dtotal loads
+#ifndef FLUX_MODE
+#define FLUX_MODE 0
+#endif
+#if FLUX_MODE == 2
+#define FLUX_LD(p, pol) ((double)((p) - (const double *)0) * 1e-30)
+#else
+#define FLUX_LD(p, pol) flux_ld_keep(p, pol)
+#endif
+#if FLUX_MODE == 1
+#define FLUX_ST(p, v) do { if ((v) == 1.2345e-300) __stcs(p, v); } while (0)
+#else
+#define FLUX_ST(p, v) __stcs(p, v)
+#endif
 template <int N, int JC>
 __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nlocal, long long nconn, const int32_t *__restrict__ row_ptr,
                                                         const int32_t *__restrict__ col, const int32_t *__restrict__ ent,
@@ -212,88 +226,115 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
   for (int q = 0; q < FLUX_Q; ++q) en[q] = q < deg ? ent[s0 + 1 + q] : 0;
   const long long sj = (long long)N * ld;                          // stride of one block column in dtotal
   const double *D0 = dtotal + (long long)j0 * sj;
-  for (int k = 0; k < nslot; ++k) {
+  constexpr int NI = (N + 3) / 4;
+  int32_t nbr[FLUX_Q];
+#pragma unroll
+  for (int q = 0; q < FLUX_Q; ++q) nbr[q] = q < deg ? col[s0 + 1 + q] : own;
+  double d[NI][JC], so[NI];
+  // loads of off-diagonal slot k (all NI*JC + NI requests of the thread back to back); the signed coefficient of the
+  // neighbour's side is applied in finish(): -(D T) == D (-T) exactly
+  double sgn = 1.0;
+  auto issue = [&](int k) {
+    if (k >= ns) return;
+    int32_t ek = k <= FLUX_Q ? 0 : ent[s0 + k], nb = k <= FLUX_Q ? own : col[s0 + k];
+#pragma unroll
+    for (int q = 0; q < FLUX_Q; ++q) if (k == q + 1) { ek = en[q]; nb = nbr[q]; }
+    const double *To = ((ek & 1) ? T_up : T_dn) + (ek >> 1);
+    sgn = (ek & 1) ? -1.0 : 1.0;
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii) {
+      const int i = w + 4 * ii;
+      if (i < N) {
+        const double *p = D0 + (long long)i * ld + nb;
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj) d[ii][jj] = FLUX_LD(p + jj * sj, keep);
+        so[ii] = To[(long long)i * nconn];
+      }
+    }
+  };
+  auto finish = [&](int k) {
+    if (k >= ns) return;
     double *tile = sh[k & 1] + lane * LDP;
-    if (k < ns) {
-      if (k == 0) {
-        // two block rows at a time: their 2*(JC + FLUX_Q) loads are issued together
-        constexpr int NI = (N + 3) / 4;
 #pragma unroll
-        for (int i2 = 0; i2 < NI; i2 += 2) {
-          double d[2][JC], sc[2][FLUX_Q];
+    for (int ii = 0; ii < NI; ++ii) {
+      const int i = w + 4 * ii;
+      if (i < N) {
+        const double sv = sgn * so[ii];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = w + 4 * (i2 + u);
-            if (i2 + u < NI && i < N) {
-              const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn, *p = D0 + (long long)i * ld + own;
+        for (int jj = 0; jj < JC; ++jj) tile[jj * N + i] = fl_mul(d[ii][jj], sv);
+      }
+    }
+  };
+  // rows of the tile this lane helps to write (RPP rows per warp pass): slot count and element offset of slot 0 in registers
+  constexpr int NP = 32 / (4 * RPP);
+  int wns[NP];
+  long long wbase[NP];
+  __syncthreads();
 #pragma unroll
-              for (int jj = 0; jj < JC; ++jj) d[u][jj] = flux_ld_keep(p + jj * sj, keep);
+  for (int t = 0; t < NP; ++t) {
+    const int rr = w * RPP + (lane >> LSH) + t * 4 * RPP;
+    wns[t] = rr < rows_here ? sh_ns[rr] : 0;
+    wbase[t] = (long long)sh_s0[rr] * NN + j0 * N + (lane & (LPR - 1));
+  }
+  auto write_out = [&](int k) {
+    const double *stage = sh[k & 1] + (lane & (LPR - 1));
 #pragma unroll
-              for (int q = 0; q < FLUX_Q; ++q) sc[u][q] = q < deg ? ((en[q] & 1) ? -Td_i[en[q] >> 1] : Tu_i[en[q] >> 1]) : 0.0;
-            }
-          }
+    for (int t = 0; t < NP; ++t)
+      if (k < wns[t]) {
+        const int rr = w * RPP + (lane >> LSH) + t * 4 * RPP;
+        double *dst = val + wbase[t] + (long long)k * NN;
+        const double *src = stage + rr * LDP;
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = w + 4 * (i2 + u);
-            if (i2 + u < NI && i < N) {
-              const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn;
+        for (int u = 0; u < (CW + LPR - 1) / LPR; ++u)
+          if ((lane & (LPR - 1)) + u * LPR < CW) FLUX_ST(dst + u * LPR, src[u * LPR]);
+      }
+  };
+  // slot 0, the diagonal block: two block rows at a time, their 2*(JC + FLUX_Q) loads issued together
+  if (ns > 0) {
+    double *tile = sh[0] + lane * LDP;
 #pragma unroll
-              for (int jj = 0; jj < JC; ++jj) {
-                double a = 0.0;
+    for (int i2 = 0; i2 < NI; i2 += 2) {
+      double dd[2][JC], sc[2][FLUX_Q];
 #pragma unroll
-                for (int q = 0; q < FLUX_Q; ++q) if (q < deg) a = fl_add(a, fl_mul(d[u][jj], sc[u][q]));
-                for (int s = s0 + 1 + FLUX_Q; s < s1; ++s) {
-                  const int32_t e = ent[s];
-                  a = fl_add(a, fl_mul(d[u][jj], (e & 1) ? -Td_i[e >> 1] : Tu_i[e >> 1]));
-                }
-                tile[jj * N + i] = a;
-              }
-            }
-          }
+      for (int u = 0; u < 2; ++u) {
+        const int i = w + 4 * (i2 + u);
+        if (i2 + u < NI && i < N) {
+          const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn, *p = D0 + (long long)i * ld + own;
+#pragma unroll
+          for (int jj = 0; jj < JC; ++jj) dd[u][jj] = FLUX_LD(p + jj * sj, keep);
+#pragma unroll
+          for (int q = 0; q < FLUX_Q; ++q) sc[u][q] = q < deg ? ((en[q] & 1) ? -Td_i[en[q] >> 1] : Tu_i[en[q] >> 1]) : 0.0;
         }
-      } else {
-        int32_t ek = k <= FLUX_Q ? 0 : ent[s0 + k];
+      }
 #pragma unroll
-        for (int q = 0; q < FLUX_Q; ++q) if (k == q + 1) ek = en[q];
-        const int32_t nb = col[s0 + k];
-        const double *To = ((ek & 1) ? T_up : T_dn) + (ek >> 1);
-        const double sgn = (ek & 1) ? -1.0 : 1.0;                  // exact: -(D T) == D (-T)
-        // all loads of the slot first (NI*JC + NI independent requests per thread), then the products
-        constexpr int NI = (N + 3) / 4;
-        double d[NI][JC], so[NI];
+      for (int u = 0; u < 2; ++u) {
+        const int i = w + 4 * (i2 + u);
+        if (i2 + u < NI && i < N) {
+          const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn;
 #pragma unroll
-        for (int ii = 0; ii < NI; ++ii) {
-          const int i = w + 4 * ii;
-          if (i < N) {
-            const double *p = D0 + (long long)i * ld + nb;
+          for (int jj = 0; jj < JC; ++jj) {
+            double a = 0.0;
 #pragma unroll
-            for (int jj = 0; jj < JC; ++jj) d[ii][jj] = flux_ld_keep(p + jj * sj, keep);
-            so[ii] = To[(long long)i * nconn];
-          }
-        }
-#pragma unroll
-        for (int ii = 0; ii < NI; ++ii) {
-          const int i = w + 4 * ii;
-          if (i < N) {
-            const double sv = sgn * so[ii];
-#pragma unroll
-            for (int jj = 0; jj < JC; ++jj) tile[jj * N + i] = fl_mul(d[ii][jj], sv);
+            for (int q = 0; q < FLUX_Q; ++q) if (q < deg) a = fl_add(a, fl_mul(dd[u][jj], sc[u][q]));
+            for (int s = s0 + 1 + FLUX_Q; s < s1; ++s) {
+              const int32_t e = ent[s];
+              a = fl_add(a, fl_mul(dd[u][jj], (e & 1) ? -Td_i[e >> 1] : Tu_i[e >> 1]));
+            }
+            tile[jj * N + i] = a;
           }
         }
       }
     }
+  }
+  // off-diagonal slots, software pipelined: the loads of slot k+1 are in flight while slot k crosses the barrier and is written
+  issue(1);
+  __syncthreads();
+  write_out(0);
+  for (int k = 1; k < nslot; ++k) {
+    finish(k);
+    issue(k + 1);
     __syncthreads();
-    const double *stage = sh[k & 1];
-    for (int rr = w * RPP + (lane >> LSH); rr < rows_here; rr += 4 * RPP)
-      if (k < sh_ns[rr]) {
-        double *dst = val + (long long)(sh_s0[rr] + k) * NN + j0 * N;
-        const double *src = stage + rr * LDP;
-#pragma unroll
-        for (int t = 0; t < (CW + LPR - 1) / LPR; ++t) {
-          const int e = (lane & (LPR - 1)) + t * LPR;
-          if (e < CW) __stcs(dst + e, src[e]);
-        }
-      }
+    write_out(k);
   }
 }
 
