@@ -5,11 +5,11 @@ timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/pyt
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 timeout 600 python bench.py > gpurun_out/bench_300a.json 2> gpurun_out/bench_300a.err
 timeout 300 python bench.py --workload calcite > gpurun_out/bench_calcite.json 2> gpurun_out/bench_calcite.err
-timeout 300 python bench.py --workload hanford300a_mr > gpurun_out/bench_mr.json 2> gpurun_out/bench_mr.err
-timeout 300 python bench.py --workload hpt_calcite > gpurun_out/bench_hpt.json 2> gpurun_out/bench_hpt.err
+timeout 300 python profiles/bench_flux.py hanford300a_eq 128 128 64 > gpurun_out/bench_flux_300a.json 2> gpurun_out/bench_flux_300a.err
+timeout 300 python profiles/bench_flux.py hanford300a_eq 100 100 100 > gpurun_out/bench_flux_300a_100.json 2> gpurun_out/bench_flux_300a_100.err
+timeout 300 python profiles/bench_flux.py calcite 100 100 100 > gpurun_out/bench_flux_calcite_100.json 2> gpurun_out/bench_flux_calcite_100.err
+timeout 300 python profiles/bench_flux.py calcite 256 256 128 > gpurun_out/bench_flux_calcite.json 2> gpurun_out/bench_flux_calcite.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-  python bench.py --steps 2 --warmup 1 --cells 2000000 > gpurun_out/ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_react_lane -s 2 -c 1 -o gpurun_out/lane_final \
-  python bench.py --steps 1 --warmup 1 --cells 600000 > gpurun_out/ncu_full.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_flux.csv \
+  python profiles/bench_flux.py hanford300a_eq 96 96 48 > gpurun_out/ncu_launches_flux.log 2>&1
 cat gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log
