@@ -106,3 +106,57 @@ def test_flux_entry_point_errors():
     bad = conn['id_dn'].copy(); bad[0] = 10 ** 6
     with pytest.raises(rt.RxnError):
         rt.ConnectionSet(rz, conn['id_up'], bad, nlocal)
+
+
+def test_flux_full_size_properties():
+    """BASELINE config 2 size (100 x 100 x 100, calcite): size-independent properties of the whole-grid result — interior
+    fluxes cancel in the sum over cells; row r's diagonal block is minus the sum of the blocks its neighbours hold for
+    column r (each connection contributes +J to one row and -J to the other); a seeded sample of rows equals the oracle
+    loop restricted to those rows' connections bit for bit."""
+    nx = ny = nz = 100
+    n_cells = nx * ny * nz
+    w, cells = workload_cells('calcite', n_cells)
+    n = w.tables.naqcomp
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, n_cells)
+    for f, v in w.base.items():
+        rz.broadcast(f, v)
+    rz.set_cell_scalars(porosity=cells['porosity'], temp=cells['temp'], pres=cells['pres'])
+    rz.upload('MNRL_VOLFRAC', cells['volfrac'])
+    rz.materialize('DTOTAL')
+    rng = np.random.default_rng(3)
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.2 * rng.standard_normal((n_cells, n))))
+    rz.RTUpdateAuxVars(xx, True)
+    conn, nghosted, nlocal, active = structured_connections(nx, ny, nz, n)
+    cs = rt.ConnectionSet(rz, conn['id_up'], conn['id_dn'], nlocal)
+    cs.TFluxCoef(conn['area'], conn['velocity'], conn['disp'])
+    r = rz.RTResidualFlux(cs)
+    val = rz.RTJacobianFlux(cs)
+    row_ptr, col = cs.structure()
+    assert cs.nnz_blocks == n_cells + 2 * len(conn['id_up'])
+    tot = rz.download('TOTAL')
+    Tmax = (np.abs(conn['velocity']).max() + conn['disp'].max()) * conn['area'].max() * 1000.0
+    assert (np.abs(r.sum(axis=0)) <= 1e-9 * Tmax * np.abs(tot).max(axis=1) * np.sqrt(len(conn['id_up']))).all()
+    # column sums of the block matrix vanish: sum over rows of block (row, c) = 0 for every column cell c
+    colsum = np.zeros((n_cells, n * n))
+    np.add.at(colsum, col, val)
+    scale = np.zeros((n_cells, n * n))
+    np.add.at(scale, col, np.abs(val))
+    assert (np.abs(colsum) <= 1e-12 * scale + 1e-300).all()
+    # sampled rows against the oracle's connection loop on the sub-list of connections that touch them
+    st = synth.host_state(w, cells)
+    st['TOTAL'][:] = tot
+    st['DTOTAL'][:] = rz.download('DTOTAL')
+    sample = np.sort(rng.choice(n_cells, 2000, replace=False))
+    mark = np.zeros(n_cells, dtype=bool); mark[sample] = True
+    keep = mark[conn['id_up']] | mark[conn['id_dn']]
+    sub = {k: (v[keep] if isinstance(v, np.ndarray) and len(v) == len(keep) else v) for k, v in conn.items()}
+    o = Oracle(w.tables)
+    Tu, Td = o.flux_coefs(sub, n)
+    r_o = o.flux_residual(st, sub, Tu, Td, n_cells)
+    np.testing.assert_array_equal(r[sample], r_o[sample])
+    rp_o, col_o, val_o = o.flux_jacobian(st, sub, Tu, Td, n_cells)
+    for c in sample[:500]:
+        np.testing.assert_array_equal(col[row_ptr[c]:row_ptr[c + 1]], col_o[rp_o[c]:rp_o[c + 1]])
+        np.testing.assert_array_equal(val[row_ptr[c]:row_ptr[c + 1]], val_o[rp_o[c]:rp_o[c + 1]])
+    cs.close()
