@@ -337,7 +337,8 @@ int rxn_residual_jacobian_blocks_batch_device(RxnState *s, const int32_t *d_l2g,
  * into the row view (per local cell: its connections in connection order), which is also the block-CSR structure of
  * the flux Jacobian: slot row_ptr[r] is the diagonal block of local row r, slots row_ptr[r]+1 .. row_ptr[r+1]-1 its
  * connections in connection order; col = ghosted id of the column cell; blocks n x n column-major, as
- * MatSetValuesBlockedLocal receives Jup / Jdn. */
+ * MatSetValuesBlockedLocal receives Jup / Jdn.  A set is bound to the state it was created on (other states are rejected);
+ * destroy it before or after that state, but do not pass it to a call once the state is gone. */
 typedef struct RxnConnSet RxnConnSet;
 int rxn_connset_create(RxnState *s, int64_t nconn, const int32_t *id_up, const int32_t *id_dn, const int32_t *ghost_to_local,
                        int64_t nlocal, const uint8_t *active, RxnConnSet **out);

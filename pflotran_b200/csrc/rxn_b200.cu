@@ -85,7 +85,7 @@ struct RxnState {
 struct RxnConnSet {
   RxnState *s = nullptr;
   FluxRows R;
-  int n = 0;
+  int n = 0, device = 0;      // device kept here: the set may outlive its state
   int32_t *d_row_ptr = nullptr, *d_col = nullptr, *d_ent = nullptr, *d_l2g = nullptr;
   double *d_T = nullptr;        // [T_up | T_dn], each SoA [component][connection]
   bool have_coefs = false;
@@ -756,6 +756,7 @@ int rxn_connset_create(RxnState *s, int64_t nconn, const int32_t *id_up, const i
   RxnConnSet *c = new RxnConnSet();
   c->s = s;
   c->n = s->t->h.naq;
+  c->device = s->t->device;
   if (!flux_rows_build(s->ncells, nlocal, nconn, id_up, id_dn, ghost_to_local, active, &c->R)) {
     const std::string e = c->R.err;
     delete c;
@@ -781,7 +782,7 @@ int rxn_connset_create(RxnState *s, int64_t nconn, const int32_t *id_up, const i
 
 int rxn_connset_destroy(RxnConnSet *c) {
   if (!c) return RXN_OK;
-  cudaSetDevice(c->s->t->device);
+  cudaSetDevice(c->device);
   cudaFree(c->d_row_ptr); cudaFree(c->d_col); cudaFree(c->d_ent); cudaFree(c->d_l2g); cudaFree(c->d_T);
   delete c;
   return RXN_OK;
