@@ -175,6 +175,12 @@ __global__ void __launch_bounds__(128) k_flux_jacobian(int n, int jc, long long 
 #else
 #define FLUX_ST(p, v) __stcs(p, v)
 #endif
+#ifndef FLUX_DU
+#define FLUX_DU 2
+#endif
+#ifndef FLUX_EARLY
+#define FLUX_EARLY 0
+#endif
 template <int N, int JC>
 __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nlocal, long long nconn, const int32_t *__restrict__ row_ptr,
                                                         const int32_t *__restrict__ col, const int32_t *__restrict__ ent,
@@ -268,14 +274,15 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
           if ((lane & (LPR - 1)) + u * LPR < CW) FLUX_ST(dst + u * LPR, src[u * LPR]);
       }
   };
+  if (FLUX_EARLY) issue(1);
   // slot 0, the diagonal block: two block rows at a time, their 2*(JC + FLUX_Q) loads issued together
   if (ns > 0) {
     double *tile = sh[0] + lane * LDP;
 #pragma unroll
-    for (int i2 = 0; i2 < NI; i2 += 2) {
-      double dd[2][JC], sc[2][FLUX_Q];
+    for (int i2 = 0; i2 < NI; i2 += FLUX_DU) {
+      double dd[FLUX_DU][JC], sc[FLUX_DU][FLUX_Q];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < FLUX_DU; ++u) {
         const int i = w + 4 * (i2 + u);
         if (i2 + u < NI && i < N) {
           const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn, *p = D0 + (long long)i * ld + own;
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < FLUX_DU; ++u) {
         const int i = w + 4 * (i2 + u);
         if (i2 + u < NI && i < N) {
           const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn;
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
     }
   }
   // off-diagonal slots, software pipelined: the loads of slot k+1 are in flight while slot k crosses the barrier and is written
-  issue(1);
+  if (!FLUX_EARLY) issue(1);
   __syncthreads();
   write_out(0);
   for (int k = 1; k < nslot; ++k) {
