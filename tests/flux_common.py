@@ -41,3 +41,28 @@ def structured_connections(nx, ny, nz, naq, seed=3, ghost_layers=0, inactive_fra
     if inactive_fraction > 0:
         active[rng.random(nghosted) < inactive_fraction] = 0
     return conn, nghosted, nlocal, active
+
+
+def random_connections(ncells, nconn, naq, seed=9, nghost=0):
+    """Unstructured connectivity: nconn random pairs (repeats of a pair allowed, as two faces between the same cells), a few hub
+    cells with many connections (rows far longer than a structured grid's six), the last nghost ghosted cells not local."""
+    rng = np.random.default_rng(seed)
+    up = rng.integers(0, ncells, nconn)
+    dn = rng.integers(0, ncells, nconn)
+    hubs = rng.choice(ncells, 3, replace=False)
+    up[::7] = hubs[0]
+    dn[3::11] = hubs[1]
+    same = up == dn
+    dn[same] = (dn[same] + 1) % ncells
+    g2l = None
+    nlocal = ncells
+    if nghost:
+        g2l = np.arange(ncells, dtype=np.int32)
+        g2l[ncells - nghost:] = -1
+        nlocal = ncells - nghost
+    conn = {
+        'id_up': up.astype(np.int32), 'id_dn': dn.astype(np.int32), 'g2l': g2l,
+        'area': rng.uniform(0.5, 2.0, nconn), 'velocity': rng.normal(0.0, 1.0e-6, nconn),
+        'disp': rng.uniform(1.0e-9, 1.0e-7, (nconn, naq)), 'fraction_upwind': rng.uniform(0.3, 0.7, nconn),
+    }
+    return conn, ncells, nlocal, np.ones(ncells, dtype=np.uint8)

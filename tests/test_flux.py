@@ -9,7 +9,7 @@ from pflotran_b200 import synth
 from oracle.pyoracle import Oracle
 import emulator
 from common import workload_cells
-from flux_common import structured_connections
+from flux_common import structured_connections, random_connections
 
 
 def _state_with_totals(name, n, seed=11):
@@ -120,6 +120,25 @@ def test_row_view_matches_connection_loop(name, ghost, inactive, upwind):
         l2g = np.where(conn['g2l'] >= 0)[0] if conn['g2l'] is not None else np.arange(nlocal)
         dead = np.where(active[l2g] == 0)[0]
         assert len(dead) > 0 and (r_o[dead] == 0).all()
+
+
+@pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq'])
+def test_row_view_unstructured_long_rows(name):
+    """Rows with many more connections than a structured grid's six (hub cells), repeated pairs and ghost cells."""
+    ncells = 300
+    w, st = _state_with_totals(name, ncells)
+    n = w.tables.naqcomp
+    conn, nghosted, nlocal, active = random_connections(ncells, 1500, n, nghost=20)
+    o = Oracle(w.tables)
+    Tu, Td = o.flux_coefs(conn, n)
+    r_o = o.flux_residual(st, conn, Tu, Td, nlocal)
+    rp_o, col_o, val_o = o.flux_jacobian(st, conn, Tu, Td, nlocal)
+    rp_e, col_e, r_e, val_e = emulator.flux(st, conn, nlocal)
+    assert np.diff(rp_o).max() > 50                      # the hub rows
+    np.testing.assert_array_equal(rp_e, rp_o)
+    np.testing.assert_array_equal(col_e, col_o)
+    np.testing.assert_array_equal(r_e, r_o)
+    np.testing.assert_array_equal(val_e, val_o)
 
 
 def test_connection_set_rejects_bad_maps():

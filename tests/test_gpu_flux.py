@@ -7,7 +7,7 @@ import pytest
 from pflotran_b200 import synth, reactive_transport as rt
 from oracle.pyoracle import Oracle
 from common import workload_cells, RTOL
-from flux_common import structured_connections
+from flux_common import structured_connections, random_connections
 
 pytestmark = pytest.mark.gpu
 
@@ -63,6 +63,38 @@ def test_flux_residual_and_jacobian_bitwise(name, dims, ghost, inactive, upwind,
     np.testing.assert_array_equal(r_d, r_o)
     np.testing.assert_array_equal(v_d, val_o)
     rz.device_free(d_r); rz.device_free(d_v)
+    cs.close()
+
+
+@pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq', 'hanford300a_mr'])
+@pytest.mark.parametrize('generic', [0, 1])
+def test_flux_unstructured_long_rows(name, generic, monkeypatch):
+    """Unstructured connectivity with hub cells (rows of 100+ connections: beyond the kernels' register window of six entries, and
+    tiles whose rows have very different lengths), repeated pairs and ghost cells; bit for bit against the oracle loop."""
+    monkeypatch.setenv('RXN_FLUX_GENERIC', str(generic))
+    ncells = 1000
+    w, cells = workload_cells(name, ncells)
+    st = synth.host_state(w, cells)
+    n = w.tables.naqcomp
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.2 * np.random.default_rng(1).standard_normal((ncells, n))))
+    o = Oracle(w.tables)
+    o.update_auxvars(st, xx, True)
+    conn, nghosted, nlocal, active = random_connections(ncells, 6000, n, nghost=37)
+    Tu, Td = o.flux_coefs(conn, n)
+    r_o = o.flux_residual(st, conn, Tu, Td, nlocal)
+    rp_o, col_o, val_o = o.flux_jacobian(st, conn, Tu, Td, nlocal)
+    assert np.diff(rp_o).max() > 100
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, ncells)
+    rz.upload_host_state(st)
+    rz.upload('DTOTAL', st['DTOTAL'])
+    cs = rt.ConnectionSet(rz, conn['id_up'], conn['id_dn'], nlocal, conn['g2l'])
+    rp, col = cs.structure()
+    np.testing.assert_array_equal(rp, rp_o)
+    np.testing.assert_array_equal(col, col_o)
+    cs.TFluxCoef(conn['area'], conn['velocity'], conn['disp'])
+    np.testing.assert_array_equal(rz.RTResidualFlux(cs), r_o)
+    np.testing.assert_array_equal(rz.RTJacobianFlux(cs), val_o)
     cs.close()
 
 
