@@ -33,8 +33,11 @@ __global__ void __launch_bounds__(256) k_flux_coefs(int n, long long nconn, cons
 }
 
 // Flux residual of every local row: one warp per tile of 32 rows, lane = row.  r: AoS [nlocal][n].
-// (Keeping the row's entries in registers across the component loop measured slower: 0.52 against 0.41 ms per 10^6 rows.)
+// (Keeping the row's entries in registers across the whole component loop measured slower: 0.52 against 0.41 ms per 10^6 rows.)
 enum { FLUX_Q = 6, FLUX_JC = 8 };
+#ifndef FLUX_RC
+#define FLUX_RC 2
+#endif
 
 // dtotal is read up to 7 times (the cell itself and its neighbours' rows) while the matrix streams through L2 once:
 // loads ask L2 to keep the line (evict_last), stores are streaming (st.global.cs)
@@ -63,7 +66,26 @@ __global__ void __launch_bounds__(128) k_flux_residual(int n, long long nlocal, 
   if (row < nlocal) {
     const int s0 = row_ptr[row], s1 = row_ptr[row + 1];
     const int32_t own = l2g[row];
-    for (int i = 0; i < n; ++i)
+    // FLUX_RC components per walk of the row: the entry / neighbour loads are shared and 3*FLUX_RC value loads are independent;
+    // each component's sum is formed in connection order as flux_row_residual (rxn_flux.h) does
+    int i = 0;
+    for (; i + FLUX_RC <= n; i += FLUX_RC) {
+      double acc[FLUX_RC], t_own[FLUX_RC];
+#pragma unroll
+      for (int u = 0; u < FLUX_RC; ++u) { acc[u] = 0.0; t_own[u] = total[(long long)(i + u) * ld + own]; }
+      for (int s = s0 + 1; s < s1; ++s) {
+        const int32_t e = ent[s], c = e >> 1, nb = col[s];
+#pragma unroll
+        for (int u = 0; u < FLUX_RC; ++u) {
+          const double t_nb = total[(long long)(i + u) * ld + nb];
+          const double tu = T_up[(long long)(i + u) * nconn + c], td = T_dn[(long long)(i + u) * nconn + c];
+          acc[u] = (e & 1) ? fl_add(acc[u], -flux_res(tu, t_nb, td, t_own[u])) : fl_add(acc[u], flux_res(tu, t_own[u], td, t_nb));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < FLUX_RC; ++u) tile[lane * ldp + i + u] = acc[u];
+    }
+    for (; i < n; ++i)
       tile[lane * ldp + i] = flux_row_residual(ent, col, s0, s1, own, total + (long long)i * ld, T_up + (long long)i * nconn,
                                                T_dn + (long long)i * nconn);
   }

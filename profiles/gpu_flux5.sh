@@ -1,7 +1,7 @@
 #!/bin/bash
 for lib in librxn_b200.so librxn_b200_alt.so librxn_b200_alt2.so; do
   export RXN_B200_LIB=$PWD/pflotran_b200/$lib
-  timeout 300 python profiles/bench_flux.py hanford300a_eq 128 64 64 2>&1 | python -c "
+  timeout 300 python profiles/bench_flux.py hanford300a_eq 100 100 100 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
