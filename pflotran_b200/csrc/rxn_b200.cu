@@ -862,7 +862,10 @@ int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val) {
   k_flux_jacobian_t<N_, JC_><<<tiles * (N_ / JC_), 128, 0, s->stream>>>(c->R.nlocal, c->R.nconn, c->d_row_ptr, c->d_col, c->d_ent, \
                                                                           c->d_l2g, s->S.f[RXN_F_DTOTAL], s->ld, c->d_T,       \
                                                                           c->d_T + (size_t)n * c->R.nconn, d_val)
-  if (n == 15 && !s->flux_generic) FLUX_JAC_T(15, 5);
+#ifndef FLUX_JC15
+#define FLUX_JC15 5
+#endif
+  if (n == 15 && !s->flux_generic) FLUX_JAC_T(15, FLUX_JC15);
   else if (n == 4 && !s->flux_generic) FLUX_JAC_T(4, 4);
   else if (n == 3 && !s->flux_generic) FLUX_JAC_T(3, 3);
   else {
