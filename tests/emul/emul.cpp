@@ -314,8 +314,8 @@ int emu_update_kinetic_state_batch(void *h, const HostView *v, const uint8_t *ac
   return 0;
 }
 
-// Flux side (rxn_flux.h): the structure builder and the per-row arithmetic the kernels of rxn_flux.cuh call, run in
-// plain loops with the kernels' index maps (coefficients SoA [component][connection], block CSR output).
+// Flux side (rxn_flux.h): the structure builder the library runs and the per-row arithmetic the kernels of rxn_flux.cuh
+// implement (k_flux_residual's remainder path calls it; the unrolled paths restate it), run in plain loops with the kernels' index maps (coefficients SoA [component][connection], block CSR output).
 // Returns the number of Jacobian blocks, < 0 on a structure error; row_ptr (nlocal+1) is always written, the other
 // outputs only when non-NULL.
 int64_t emu_flux(const HostView *v, const uint8_t *active, int n, int64_t nconn, const int32_t *id_up, const int32_t *id_dn,

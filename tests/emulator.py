@@ -157,7 +157,7 @@ class Emulator:
 
 
 def flux(st, conn, nlocal, use_upwinding=True):
-    """Flux residual / Jacobian through the structure builder and per-row arithmetic of rxn_flux.h (the code the CUDA kernels call).
+    """Flux residual / Jacobian through the structure builder and per-row arithmetic of rxn_flux.h (what the CUDA kernels implement).
     conn: dict(id_up, id_dn, g2l|None, area, velocity, disp [nconn, naq], fraction_upwind).  Returns row_ptr, col, res, val."""
     n = st.t.naqcomp
     nconn = len(conn['id_up'])

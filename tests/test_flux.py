@@ -1,6 +1,7 @@
 """Flux side of the global-implicit path on the CPU: the oracle's restatement of TFluxCoef / TFlux /
 TFluxDerivative and of the RTResidualFlux / RTJacobianFlux interior loops against hand-computed connections and
-conservation, and the row-view code the CUDA kernels call (rxn_flux.h, compiled for the host) against the oracle, bit for bit.
+conservation, and the row view of rxn_flux.h compiled for the host — the structure builder the library runs and the per-row
+arithmetic the kernels of rxn_flux.cuh implement (the kernels themselves are compared in test_gpu_flux.py) — against the oracle, bit for bit.
 The reference has no unit test or gold file for these routines alone: parity of this part is pinned by these properties."""
 import numpy as np
 import pytest
@@ -95,7 +96,7 @@ def test_flux_conservation_and_jacobian_consistency(name):
 @pytest.mark.parametrize('name,ghost,inactive,upwind', [('calcite', 0, 0.0, True), ('calcite', 1, 0.1, False),
                                                         ('hanford300a_eq', 1, 0.05, True), ('hanford300a_eq', 0, 0.0, False)])
 def test_row_view_matches_connection_loop(name, ghost, inactive, upwind):
-    """rxn_flux.h (structure builder + per-row sums, the code the kernels run) against the oracle's connection loop: same
+    """rxn_flux.h (structure builder + per-row sums, the arithmetic the kernels implement) against the oracle's connection loop: same
     block-CSR structure, residual and Jacobian identical bit for bit (the row view adds in the reference's order)."""
     nx, ny, nz = 7, 5, 4
     g = ghost
