@@ -859,7 +859,7 @@ int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val) {
   CU(cudaEventRecord(s->ev0, s->stream));
   const unsigned tiles = nblocks(c->R.nlocal, 32);
 #define FLUX_JAC_T(N_, JC_)                                                                                                    \
-  k_flux_jacobian_t<N_, JC_><<<tiles * (N_ / JC_), 128, 0, s->stream>>>(c->R.nlocal, c->R.nconn, c->d_row_ptr, c->d_col, c->d_ent, \
+  k_flux_jacobian_t<N_, JC_><<<tiles * (N_ / JC_), 32 * FLUX_NW, 0, s->stream>>>(c->R.nlocal, c->R.nconn, c->d_row_ptr, c->d_col, c->d_ent, \
                                                                           c->d_l2g, s->S.f[RXN_F_DTOTAL], s->ld, c->d_T,       \
                                                                           c->d_T + (size_t)n * c->R.nconn, d_val)
 #ifndef FLUX_JC15

@@ -203,14 +203,17 @@ __global__ void __launch_bounds__(128) k_flux_jacobian(int n, int jc, long long 
 #ifndef FLUX_EARLY
 #define FLUX_EARLY 0
 #endif
+#ifndef FLUX_NW
+#define FLUX_NW 4
+#endif
 template <int N, int JC>
-__global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nlocal, long long nconn, const int32_t *__restrict__ row_ptr,
+__global__ void __launch_bounds__(32 * FLUX_NW, FLUX_MINB) k_flux_jacobian_t(long long nlocal, long long nconn, const int32_t *__restrict__ row_ptr,
                                                         const int32_t *__restrict__ col, const int32_t *__restrict__ ent,
                                                         const int32_t *__restrict__ l2g, const double *__restrict__ dtotal, long long ld,
                                                         const double *__restrict__ T_up, const double *__restrict__ T_dn,
                                                         double *__restrict__ val) {
   static_assert(N % JC == 0, "column chunks must tile the block");
-  constexpr int NN = N * N, CW = JC * N, LDP = CW | 1;
+  constexpr int NN = N * N, CW = JC * N, LDP = CW | 1, NW = FLUX_NW;   // NW warps per CTA
   constexpr int LSH = CW > 16 ? 5 : CW > 8 ? 4 : CW > 4 ? 3 : 2, LPR = 1 << LSH, RPP = 32 >> LSH;   // lanes per row run, rows per warp pass
   __shared__ double sh[2][32 * LDP];
   __shared__ int sh_s0[32], sh_ns[32];
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
   for (int q = 0; q < FLUX_Q; ++q) en[q] = q < deg ? ent[s0 + 1 + q] : 0;
   const long long sj = (long long)N * ld;                          // stride of one block column in dtotal
   const double *D0 = dtotal + (long long)j0 * sj;
-  constexpr int NI = (N + 3) / 4;
+  constexpr int NI = (N + NW - 1) / NW;
   int32_t nbr[FLUX_Q];
 #pragma unroll
   for (int q = 0; q < FLUX_Q; ++q) nbr[q] = q < deg ? col[s0 + 1 + q] : own;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
     sgn = (ek & 1) ? -1.0 : 1.0;
 #pragma unroll
     for (int ii = 0; ii < NI; ++ii) {
-      const int i = w + 4 * ii;
+      const int i = w + NW * ii;
       if (i < N) {
         const double *p = D0 + (long long)i * ld + nb;
 #pragma unroll
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
     double *tile = sh[k & 1] + lane * LDP;
 #pragma unroll
     for (int ii = 0; ii < NI; ++ii) {
-      const int i = w + 4 * ii;
+      const int i = w + NW * ii;
       if (i < N) {
         const double sv = sgn * so[ii];
 #pragma unroll
@@ -273,22 +276,22 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
     }
   };
   // rows of the tile this lane helps to write (RPP rows per warp pass): slot count and element offset of slot 0 in registers
-  constexpr int NP = 32 / (4 * RPP);
+  constexpr int NP = (32 + NW * RPP - 1) / (NW * RPP);
   int wns[NP];
   long long wbase[NP];
   __syncthreads();
 #pragma unroll
   for (int t = 0; t < NP; ++t) {
-    const int rr = w * RPP + (lane >> LSH) + t * 4 * RPP;
+    const int rr = w * RPP + (lane >> LSH) + t * NW * RPP;
     wns[t] = rr < rows_here ? sh_ns[rr] : 0;
-    wbase[t] = (long long)sh_s0[rr] * NN + j0 * N + (lane & (LPR - 1));
+    wbase[t] = (long long)sh_s0[rr < 32 ? rr : 0] * NN + j0 * N + (lane & (LPR - 1));
   }
   auto write_out = [&](int k) {
     const double *stage = sh[k & 1] + (lane & (LPR - 1));
 #pragma unroll
     for (int t = 0; t < NP; ++t)
       if (k < wns[t]) {
-        const int rr = w * RPP + (lane >> LSH) + t * 4 * RPP;
+        const int rr = w * RPP + (lane >> LSH) + t * NW * RPP;
         double *dst = val + wbase[t] + (long long)k * NN;
         const double *src = stage + rr * LDP;
 #pragma unroll
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
       double dd[FLUX_DU][JC], sc[FLUX_DU][FLUX_Q];
 #pragma unroll
       for (int u = 0; u < FLUX_DU; ++u) {
-        const int i = w + 4 * (i2 + u);
+        const int i = w + NW * (i2 + u);
         if (i2 + u < NI && i < N) {
           const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn, *p = D0 + (long long)i * ld + own;
 #pragma unroll
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(128, FLUX_MINB) k_flux_jacobian_t(long long nl
       }
 #pragma unroll
       for (int u = 0; u < FLUX_DU; ++u) {
-        const int i = w + 4 * (i2 + u);
+        const int i = w + NW * (i2 + u);
         if (i2 + u < NI && i < N) {
           const double *Tu_i = T_up + (long long)i * nconn, *Td_i = T_dn + (long long)i * nconn;
 #pragma unroll
