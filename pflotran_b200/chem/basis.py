@@ -353,7 +353,7 @@ def build_tables(deck: dk.Deck, database_path: str = None, isothermal: bool = Tr
     t.database = os.path.basename(database_path)
     t.reference_temperature = float(tref)
     t.reference_pressure = float(pref)
-    t.reference_water_density = water_density_ifc67(tref, pref)
+    t.reference_water_density = water_density_ifc67(tref, pref) if deck.reference_density is None else float(deck.reference_density)
     t.naqcomp = naq
     t.ncomp = naq
     t.primary_species_names = list(chem.primary_species)

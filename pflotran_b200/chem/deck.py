@@ -235,6 +235,7 @@ class Deck:
     reference_temperature: float = 25.0
     reference_pressure: float = 101325.0
     path: str = ''
+    reference_density: Optional[float] = None    # REFERENCE_DENSITY (factory_subsurface.F90:1734); None: IFC-67 at the reference T, P (:995)
 
 
 def _read_names(rd: LineReader) -> List[str]:
@@ -573,6 +574,7 @@ def read_deck(path: str) -> Deck:
     porosity = None
     ref_t = 25.0
     ref_p = 101325.0
+    ref_den = None
     while True:
         toks = rd.next()
         if toks is None:
@@ -597,6 +599,8 @@ def read_deck(path: str) -> Deck:
             ref_t = fnum(toks[1])
         elif kw == 'REFERENCE_PRESSURE':
             ref_p = fnum(toks[1])
+        elif kw == 'REFERENCE_DENSITY':
+            ref_den = fnum(toks[1])
     if chem is None:
         raise DeckError('no CHEMISTRY card in ' + path)
-    return Deck(chem, constraints, porosity, ref_t, ref_p, path)
+    return Deck(chem, constraints, porosity, ref_t, ref_p, path, ref_den)

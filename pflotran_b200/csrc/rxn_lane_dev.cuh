@@ -67,7 +67,15 @@ static thread_local int g_hl = 0;
 #define GSL(S, field, row, cell) ((S).f[field][(long long)(row) * (S).ld + (cell)])
 
 // ---------------------------------------------------------------------------------------------
-// group primitives
+// group primitives.  The G lanes of a cell are 32/G lanes apart in their warp (lane = l*(32/G) + column):
+// every half-warp of an 8-byte access and every quarter-warp of a 16-byte access then touches DISTINCT
+// cell columns of one element row, so the lanes of a cell never meet in a shared-memory bank (adjacent lanes
+// collided on every access: 43 % of the wavefronts of round 1's G = 2 kernel were replays).
+#ifndef LANE_ADJACENT
+#define LANE_STRIDE(G) (32 / (G))
+#else
+#define LANE_STRIDE(G) 1
+#endif
 template <int G> LANE_DEV void grp_sync(unsigned gm) {
 #ifndef RXN_LANE_HOST
   if (G > 1) __syncwarp(gm);
@@ -93,7 +101,7 @@ template <int G, class OP> static inline double host_butterfly(double v, OP op) 
 template <int G> LANE_DEV double grp_sum(double v, unsigned gm) {
 #ifndef RXN_LANE_HOST
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o, G);
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o * LANE_STRIDE(G));
   return v;
 #else
   (void)gm;
@@ -103,7 +111,7 @@ template <int G> LANE_DEV double grp_sum(double v, unsigned gm) {
 template <int G> LANE_DEV double grp_max(double v, unsigned gm) {
 #ifndef RXN_LANE_HOST
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gm, v, o, G));
+  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gm, v, o * LANE_STRIDE(G)));
   return v;
 #else
   (void)gm;
@@ -113,7 +121,7 @@ template <int G> LANE_DEV double grp_max(double v, unsigned gm) {
 template <int G> LANE_DEV double grp_min(double v, unsigned gm) {
 #ifndef RXN_LANE_HOST
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(gm, v, o, G));
+  for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(gm, v, o * LANE_STRIDE(G)));
   return v;
 #else
   (void)gm;
@@ -134,8 +142,8 @@ template <int G> LANE_DEV void grp_argmax_last(double &best, int &bidx, unsigned
 #ifndef RXN_LANE_HOST
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(gm, best, o, G);
-    const int oi = __shfl_xor_sync(gm, bidx, o, G);
+    const double ob = __shfl_xor_sync(gm, best, o * LANE_STRIDE(G));
+    const int oi = __shfl_xor_sync(gm, bidx, o * LANE_STRIDE(G));
     if (ob > best || (ob == best && oi > bidx)) { best = ob; bidx = oi; }
   }
 #else

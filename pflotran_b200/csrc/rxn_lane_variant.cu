@@ -24,9 +24,21 @@ k_react_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab 
   for (int w = threadIdx.x; w < words; w += blockDim.x) tsm[w] = pblob[w];
   __syncthreads();
   const int t = threadIdx.x, ln = t & 31;
+#ifndef LANE_ADJACENT
+  constexpr int W = 32 / G;                                    // cell columns per warp; lane = l*W + column
+  const int col = ln % W, l = ln / W, s = (t >> 5) * W + col;
+  const unsigned gm = (G == 1 ? 1u : G == 2 ? 0x00010001u : G == 4 ? 0x01010101u : G == 8 ? 0x11111111u : 0x55555555u) << col;
+  const unsigned below = (1u << col) - 1u;                     // leaders of the groups before this one
+#else
   const int s = t / G, l = t % G;
   const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (ln & ~(G - 1)));
+  const unsigned below = (1u << (ln & ~(G - 1))) - 1u;
+#endif
+#ifndef LANE_ADJACENT
+  const unsigned leaders = G == 1 ? 0xffffffffu : (1u << W) - 1u;
+#else
   const unsigned leaders = G == 1 ? 0xffffffffu : G == 2 ? 0x55555555u : G == 4 ? 0x11111111u : G == 8 ? 0x01010101u : 0x00010001u;
+#endif
   const double *bd = blob;
   const int *bi = reinterpret_cast<const int *>(blob + h.ndbl);
   Lane<N, G> c;
@@ -47,7 +59,7 @@ k_react_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab 
       if (ln == leader) base = atomicAdd(counter, (unsigned long long)__popc(wm));
       base = __shfl_sync(0xffffffffu, base, leader);
       if (want) {
-        const long long i = (long long)base + __popc(wm & ((1u << (ln & ~(G - 1))) - 1u));
+        const long long i = (long long)base + __popc(wm & below);
         if (i >= nlocal) {
           exhausted = true;
         } else {
@@ -120,8 +132,16 @@ k_gi_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h, 
   for (int w = threadIdx.x; w < words; w += blockDim.x) tsm[w] = pblob[w];
   __syncthreads();
   const int t = threadIdx.x, ln = t & 31;
+#ifndef LANE_ADJACENT
+  constexpr int W = 32 / G;                                    // cell columns per warp; lane = l*W + column
+  const int col = ln % W, l = ln / W, s = (t >> 5) * W + col;
+  const unsigned gm = (G == 1 ? 1u : G == 2 ? 0x00010001u : G == 4 ? 0x01010101u : G == 8 ? 0x11111111u : 0x55555555u) << col;
+  const unsigned below = (1u << col) - 1u;                     // leaders of the groups before this one
+#else
   const int s = t / G, l = t % G;
   const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (ln & ~(G - 1)));
+  const unsigned below = (1u << (ln & ~(G - 1))) - 1u;
+#endif
   const double *bd = blob;
   const int *bi = reinterpret_cast<const int *>(blob + h.ndbl);
   Lane<N, G> c;

@@ -42,6 +42,8 @@ WORKLOADS = {
                         'regression_tests/ascem/batch/ca-carbonate-debye-huckel-activity.regression.gold'),
     'calcite_kinetics': ('regression_tests/ascem/batch/calcite-kinetics.in', 'initial',
                          'regression_tests/ascem/batch/calcite-kinetics.regression.gold'),
+    'calcite_kinetics_vf': ('regression_tests/ascem/batch/calcite-kinetics-volume-fractions.in', 'initial',
+                            'regression_tests/ascem/batch/calcite-kinetics-volume-fractions.regression.gold'),
     'ion_exchange': ('regression_tests/ascem/batch/ion-exchange-valocchi.in', 'initial',
                      'regression_tests/ascem/batch/ion-exchange-valocchi.regression.gold'),
     'surface_complexation': ('regression_tests/ascem/batch/surface-complexation-1.in', 'initial',
@@ -53,8 +55,31 @@ WORKLOADS = {
 }
 
 
+def time_block(path):
+    """TIME card (FINAL_TIME / INITIAL_TIMESTEP_SIZE / MAXIMUM_TIMESTEP_SIZE, converted to seconds as
+    units.F90 does) and TS_ACCELERATION of the TIMESTEPPER card: what tests/gi_driver.run_deck needs."""
+    import re
+    from pflotran_b200.chem.units import units_convert_to_internal
+    out = {'iaccel': 5}
+    for line in open(path):
+        line = line.split('!')[0].split('#')[0]
+        m = re.match(r'\s*(FINAL_TIME|INITIAL_TIMESTEP_SIZE|MAXIMUM_TIMESTEP_SIZE)\s+(\S+)\s+(\S+)', line)
+        if m:
+            out[m.group(1)] = float(m.group(2).lower().replace('d', 'e')) * units_convert_to_internal(m.group(3), 's')
+        m = re.match(r'\s*TS_ACCELERATION\s+(\d+)', line)
+        if m:
+            out['iaccel'] = int(m.group(1))
+        m = re.match(r'\s*MAX_STEPS\s+(-?\d+)', line)
+        if m:
+            out['MAX_STEPS'] = int(m.group(1))
+    return out
+
+
 def main():
+    only = set(sys.argv[1:])
     for name, (deck, constraint, gold) in WORKLOADS.items():
+        if only and name not in only:
+            continue
         path = os.path.join(REF, deck)
         d, t, orc, st, xx, nit, cst = kat.initial_cell(path, constraint=constraint)
         base = {f: [repr(float(x)) for x in st[f][:, 0]] for f in abi.FIELDS
@@ -68,7 +93,7 @@ def main():
         out = {
             'constraint_arrays': cons,
             'name': name, 'deck': deck, 'constraint': constraint, 'equilibrate_iterations': int(nit),
-            'porosity': d.porosity, 'tables': t.to_dict(), 'base': base,
+            'porosity': d.porosity, 'tables': t.to_dict(), 'base': base, 'time': time_block(path),
         }
         if gold:
             g = kat.read_gold(os.path.join(REF, gold))

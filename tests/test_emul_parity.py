@@ -225,6 +225,41 @@ def test_equilibrate_constraint_device_code_hits_reference_gold(name):
     assert_state_close(cst, cst_o, what=name + ' constraint cell', tables=w.tables)
 
 
+class _EmuGI:
+    """global-implicit entry points of the host-compiled device routines (tests/gi_driver.py backend)"""
+
+    def __init__(self, t, st):
+        self.emu, self.st = Emulator(t), st
+
+    def fixed_accum(self, xx):
+        return self.emu.fixed_accum(self.st, xx)
+
+    def update_auxvars(self, xx, act):
+        self.emu.update_auxvars(self.st, xx, act)
+
+    def residual_jacobian(self, dt):
+        return self.emu.residual_jacobian(self.st, dt)
+
+    def update_kinetic_state(self, dt):
+        self.emu.update_kinetic_state(self.st, dt)
+
+    def state(self):
+        return self.st
+
+
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral'])
+def test_time_stepped_device_code_hits_reference_gold(name):
+    """The device routines behind rxn_fixed_accum / update_auxvars / residual_jacobian_blocks / update_kinetic_state
+    (host compilation) driven through the reference's 1-cell global-implicit time loop reproduce
+    calcite-kinetics(.volume-fractions).regression.gold and solute_KD_{w,wo}_mineral.regression.gold at 1e-12 with the
+    reference's own time-step and Newton-iteration counts."""
+    import gi_driver
+    import kat
+    w = synth.Workload(name)
+    t, be, st, xx, nit, cst = kat.initial_cell_from_fixture(w, backend=_EmuBackend(w.tables))
+    assert gi_driver.check_time_stepped_gold(w, _EmuGI(t, st), t, xx) >= 1
+
+
 @pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite'])
 def test_equilibrate_constraint_batch_per_cell_concentrations(name):
     """A batch of cells with their own constraint concentrations, water density and temperature against the oracle."""

@@ -293,6 +293,31 @@ def test_equilibrate_constraint_gpu_hits_reference_gold(name):
     assert checked >= 4
 
 
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral'])
+def test_time_stepped_gpu_hits_reference_gold(name):
+    """rxn_fixed_accum_batch -> rxn_update_auxvars_batch -> rxn_residual_jacobian_blocks_batch -> block solve ->
+    rxn_update_kinetic_state_batch, stepped as the reference's 1-cell global-implicit run (tests/gi_driver.py), reproduce the
+    reference's time-stepped gold files (calcite-kinetics: 500 steps / 1000 Newton iterations, ...) at the reference's
+    own 1e-12.  Two identical cells: cell 1 checks that nothing leaks between cells."""
+    import gi_driver
+    import kat
+    w = synth.Workload(name)
+    t, be, st, xx, nit, cst = kat.initial_cell_from_fixture(w, backend=_GpuBackend(w.tables))
+    st2 = abi.HostState(t, 2)
+    for f in abi.FIELDS:
+        if st2[f].shape[0]:
+            st2[f][:] = st[f][:, :1]
+    xx2 = np.ascontiguousarray(np.tile(xx, (2, 1)))
+    rx = rt.Reaction(t)
+    rz = rt.Realization(rx, 2)
+    dev = gi_driver.DeviceGI(rz, st2)
+    assert gi_driver.check_time_stepped_gold(w, dev, t, xx2, tol=1.0e-12) >= 1
+    s = dev.state()
+    for f in ('PRI_MOLAL', 'TOTAL', 'MNRL_VOLFRAC', 'MNRL_RATE'):
+        if s[f].shape[0]:
+            assert (s[f][:, 0] == s[f][:, 1]).all()
+
+
 @pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite'])
 def test_equilibrate_constraint_gpu_batch(name):
     import kat

@@ -40,6 +40,18 @@ def test_gold_initial_speciation(name):
     _check(name)
 
 
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral'])
+def test_gold_time_stepped(name):
+    """Kinetic side of the oracle (RTAccumulation, RKineticMineral, RTotalSorbKD, RUpdateKineticState and the
+    accumulation/reaction Jacobian blocks) pinned to the reference's time-stepped gold files through the 1-cell
+    global-implicit loop (tests/gi_driver.py): every printed value at the reference's own 1e-12, and the same number
+    of time steps and Newton iterations as the reference's SNES took (500/1000, 62/164, 2/2, 2/2)."""
+    import gi_driver
+    w = synth.Workload(name)
+    t, orc, st, xx, nit, cst = kat.initial_cell_from_fixture(w)
+    assert gi_driver.check_time_stepped_gold(w, gi_driver.OracleGI(t, st), t, xx) >= 1
+
+
 def test_gold_values_spot():
     """The three numbers SURVEY.md 8c quotes explicitly."""
     out = _check('carbonate_dh')
