@@ -386,7 +386,11 @@ int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
   const RxnTables *t = s->t;
   const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
   const bool tile_ok = t->tile.usable && no_dtotal, lane_ok = t->lane.plan.usable && no_dtotal;
-  if (lane_ok && (s->react_kernel == 0 || s->react_kernel == 3))
+  if (lane_ok && t->lane.plan_tm.usable && (s->react_kernel == 0 || s->react_kernel == 3))
+    snprintf(buf, (size_t)len, "tensor-memory N=%d cells/CTA=%d warps/cell=%d threads=%d smem=%zu B plan=%zu B J in TMEM (spec %d, planA %d, planB %d terms)",
+             t->lane.plan_tm.lt.N, t->lane.plan_tm.lt.CPB, t->lane.G_tm, 128 * t->lane.G_tm, t->lane.plan_tm.smem_bytes,
+             t->lane.plan_tm.blob.size(), t->lane.plan_tm.terms_spec, t->lane.plan_tm.terms_A, t->lane.plan_tm.terms_B);
+  else if (lane_ok && (s->react_kernel == 0 || s->react_kernel == 3))
     snprintf(buf, (size_t)len, "resident-lane N=%d cells/CTA=%d lanes/cell=%d threads=%d smem=%zu B plan=%zu B (spec %d, planA %d, planB %d terms)",
              t->lane.plan.lt.N, t->lane.plan.lt.CPB, t->lane.G, ((t->lane.plan.lt.CPB * t->lane.G + 31) / 32) * 32, t->lane.plan.smem_bytes,
              t->lane.plan.blob.size(), t->lane.plan.terms_spec, t->lane.plan.terms_A, t->lane.plan.terms_B);

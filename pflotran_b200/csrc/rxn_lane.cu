@@ -18,6 +18,50 @@ RXN_LANE_SHAPES(RXN_LANE_DECL)
 RXN_LANE_SHAPES(RXN_LANE_DECL)
 #undef RXN_LANE_DECL
 
+#define RXN_TM_DECL(n, q, g)                                                                                                   \
+  template <> int tm_launch_variant<n, q, g>(const LaneTab &, size_t, int, const DevTab &, const double *, const double *,     \
+                                             const DevState &, double *, const int32_t *, long long, double, int, int32_t *,   \
+                                             int32_t *, unsigned long long *, long long, cudaStream_t);
+RXN_TM_SHAPES(RXN_TM_DECL)
+#undef RXN_TM_DECL
+
+// tensor-memory kernel: same plan with J in TMEM; the first compiled shape (N, QUADS, G) whose vectors fit
+static int tm_kernel_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, const cudaDeviceProp &prop,
+                           int N, LaneKernel *k) {
+  LanePlan &p = k->plan_tm;
+  p.usable = false;
+  p.err = "tensor-memory kernel disabled (RXN_TM=0)";
+  if (const char *e = getenv("RXN_TM")) { if (atoi(e) == 0) return RXN_OK; }
+  if (prop.major != 10) { p.err = "tensor memory needs sm_100"; return RXN_OK; }
+  int force_g = 2, force_q = 0;                                  // measured on B200, 300A chemistry: see DESIGN.md 4.3
+  if (const char *e = getenv("RXN_TM_G")) force_g = atoi(e);
+  if (const char *e = getenv("RXN_TM_QUADS")) force_q = atoi(e);
+  struct Shape { int N, Q, G; };
+  static const Shape shapes[] = {
+#define RXN_TM_ROW(n, q, g) {n, q, g},
+      RXN_TM_SHAPES(RXN_TM_ROW)
+#undef RXN_TM_ROW
+  };
+  p.err = "no tensor-memory shape for this matrix dimension";
+  for (const Shape &s : shapes) {
+    if (s.N != N || s.G != force_g) continue;
+    if (force_q && s.Q != force_q) continue;
+    int rc = lane_plan_build(h, bd, bi, s.N, 32 * s.Q, prop.sharedMemPerBlockOptin - 1024, &p, false, s.G);
+    if (rc != RXN_OK) return rc;
+    k->G_tm = s.G; k->quads_tm = s.Q;
+    if (p.usable) break;
+    if (p.err.find("does not fit") == std::string::npos) break;
+  }
+  if (!p.usable) return RXN_OK;
+  if (cudaMalloc(&k->d_blob_tm, p.blob.size()) != cudaSuccess ||
+      cudaMemcpy(k->d_blob_tm, p.blob.data(), p.blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    p.usable = false;
+    p.err = std::string("plan upload failed: ") + cudaGetErrorString(cudaGetLastError());
+    return RXN_ERR_CUDA;
+  }
+  return RXN_OK;
+}
+
 int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, int device, LaneKernel *k) {
   LanePlan &p = k->plan;
   p.usable = false;
@@ -49,6 +93,8 @@ int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std:
     return (int)RXN_OK;
   };
   int rc0 = pick(p, k->G, false);
+  if (rc0 != RXN_OK) return rc0;
+  rc0 = tm_kernel_build(h, bd, bi, prop, N, k);
   if (rc0 != RXN_OK) return rc0;
   rc0 = pick(k->plan_gi, k->G_gi, true);
   if (rc0 != RXN_OK) return rc0;
@@ -88,8 +134,9 @@ int lane_kernel_build(const DevTab &h, const std::vector<double> &bd, const std:
 void lane_kernel_free(LaneKernel *k) {
   if (k->d_blob) cudaFree(k->d_blob);
   if (k->d_blob_gi) cudaFree(k->d_blob_gi);
-  k->d_blob = k->d_blob_gi = nullptr;
-  k->plan.usable = k->plan_gi.usable = false;
+  if (k->d_blob_tm) cudaFree(k->d_blob_tm);
+  k->d_blob = k->d_blob_gi = k->d_blob_tm = nullptr;
+  k->plan.usable = k->plan_gi.usable = k->plan_tm.usable = false;
 }
 
 static void lane_set_mrK1(const LaneKernel &k, LaneTab &lt, double dt) {
@@ -123,9 +170,20 @@ int lane_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const Dev
 int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
                       long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
                       cudaStream_t stream, long long cell0) {
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXN_ERR_CUDA;
+  if (k.plan_tm.usable) {
+    LaneTab lt = k.plan_tm.lt;
+    lane_set_mrK1(k, lt, dt);
+#define RXN_TM_CASE(n, q, g)                                                                                                     \
+    if (lt.N == n && k.quads_tm == q && k.G_tm == g)                                                                              \
+      return tm_launch_variant<n, q, g>(lt, k.plan_tm.smem_bytes, k.sm_count, h, k.d_blob_tm, blob, S, tran_xx, l2g, nlocal, dt,  \
+                                        dt_mode, iters, flags, counter, cell0, stream);
+    RXN_TM_SHAPES(RXN_TM_CASE)
+#undef RXN_TM_CASE
+    return RXN_ERR_UNSUPPORTED;
+  }
   LaneTab lt = k.plan.lt;
   lane_set_mrK1(k, lt, dt);
-  if (cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXN_ERR_CUDA;
 #define RXN_LANE_CASE(n, cpb, g)                                                                                                 \
   if (lt.N == n && lt.CPB == cpb && k.G == g)                                                                                    \
     return lane_launch_variant<n, cpb, g>(lt, k.plan.smem_bytes, k.sm_count, h, k.d_blob, blob, S, tran_xx, l2g, nlocal, dt, dt_mode, \

@@ -18,7 +18,15 @@ namespace rxn {
   X(16, 64, 2) X(16, 56, 2) X(16, 48, 2) X(16, 64, 4) X(16, 64, 1) \
   X(24, 32, 2) X(24, 28, 2) X(24, 24, 2) X(24, 16, 2) X(24, 28, 4) X(24, 28, 1)
 
+// tensor-memory kernel shapes (rxn_tm_dev.cuh): X(N, QUADS, G) = matrix dimension (<= 15), 32-cell quads per CTA, member warps
+// per cell; per N the first shape whose vectors fit in shared memory is used (keep in sync with TM_SHAPES in the Makefile)
+#define RXN_TM_SHAPES(X) \
+  X(15, 4, 2) X(15, 3, 2) X(15, 2, 2) X(15, 4, 4) X(15, 3, 4) X(15, 2, 4) X(15, 4, 1)
+
 struct LaneKernel {
+  LanePlan plan_tm;      // tensor-memory kernel (preferred when usable)
+  int G_tm = 0, quads_tm = 0;
+  double *d_blob_tm = nullptr;
   LanePlan plan;
   int G = 1;             // lanes per cell of the selected shape
   LanePlan plan_gi;      // global-implicit residual/Jacobian kernel: same streams, activity coefficients from the state
@@ -35,6 +43,11 @@ template <int N, int CPB, int G>
 int lane_launch_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
                         const DevState &S, double *tran_xx, const int32_t *l2g, long long nlocal, double dt, int dt_mode,
                         int32_t *iters, int32_t *flags, unsigned long long *counter, long long cell0, cudaStream_t stream);
+
+template <int N, int QUADS, int G>
+int tm_launch_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
+                      const DevState &S, double *tran_xx, const int32_t *l2g, long long nlocal, double dt, int dt_mode, int32_t *iters,
+                      int32_t *flags, unsigned long long *counter, long long cell0, cudaStream_t stream);
 
 template <int N, int CPB, int G>
 int lane_launch_gi_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,

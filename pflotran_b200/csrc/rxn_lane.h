@@ -59,6 +59,9 @@ struct LaneTab {
   int o_J2, o_vec, smem_dbl;
   int s_m, s_lna, s_lng, s_sm, s_tot, s_scr, s_sc, s_free, s_mnrl, s_r0, s_seq, s_lk;
   int jsink;            // J-region sink element (double index relative to 2*t) for padded plan-B closers
+  int tm, tmG;          // tensor-memory kernel (rxn_tm_dev.cuh): J lives in TMEM (row i, column j at 32-bit column 2*(16 i + j)),
+                        // plan-B closers are {column of (i,j), column of (j,i), offset of m_i for diagonal entries or -1, 0}
+  int s_res, s_x;       // TMEM kernel: residual / right-hand side / solution vector (N), exchange slots of the G member warps (4 G)
   // term streams
   LaneStream spec, planA, planB;
   int d_coef, i_off;    // coef blocks (4 doubles per step, init block first) / offset blocks (4 ints per step, BYTE offsets
@@ -97,7 +100,7 @@ inline int lane_N_for(int naq) {
 // shared memory one CTA may use.  Returns RXN_OK and sets p->usable (false + p->err if this chemistry
 // or shape cannot use the kernel).
 inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, int N, int CPB,
-                           size_t smem_max, LanePlan *p, bool gamma_state = false) {
+                           size_t smem_max, LanePlan *p, bool gamma_state = false, int tmG = 0) {
   p->usable = false;
   LaneTab &lt = p->lt;
   memset(&lt, 0, sizeof lt);
@@ -108,6 +111,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
   if (h.nionx > 0 || h.nkd > 0) return unusable("ion exchange / KD isotherms run on the thread-per-cell kernel");
   if (h.maxpref > 0) return unusable("mineral prefactors run on the cooperative kernel");
   if (n > N) return unusable("naq exceeds the shape");
+  if (tmG > 0 && N > 15) return unusable("tensor-memory kernel: a row [J_i | b_i] must fit 16 doubles (N <= 15)");
   lt.N = N; lt.CPB = CPB; lt.LDJ2 = (N + 2) / 2;
   lt.n = n; lt.ncplx = h.ncplx; lt.nkin = h.nkin; lt.nsrf = h.nsrf; lt.nrxn = h.nrxn; lt.neq = h.neq; lt.nmr = h.nmr;
   lt.neqsorb = h.neqsorb;
@@ -119,6 +123,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
   lt.logK_mode = h.logK_mode; lt.ncoef = h.ncoef;
   lt.coop_io = h.ncplx >= 32 || h.nmr > 0;
   lt.gamma_state = gamma_state;
+  lt.tm = tmG > 0; lt.tmG = tmG;
   lt.debyeA = h.debyeA; lt.debyeB = h.debyeB; lt.debyeBdot = h.debyeBdot;
   lt.max_dlnC = h.max_dlnC; lt.rel_tol = h.rel_tol; lt.res_tol = h.res_tol;
 
@@ -172,18 +177,23 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
   lt.s_mnrl = slot(3 * h.nkin);           // volfrac | area | rate
   lt.s_r0 = slot(h.nmr * N); lt.s_seq = slot(h.nmr * N);
   lt.s_lk = slot(lt.percell_logK ? (h.ncplx + h.nkin + h.nsrf) : 0);
+  lt.s_res = slot(tmG > 0 ? N : 0);
+  lt.s_x = slot(tmG > 0 ? 4 * tmG : 0);
   const int nslots = s;
-  const int jpairs = N * lt.LDJ2 + 1;     // + one sink pair
+  const int jpairs = tmG > 0 ? 0 : N * lt.LDJ2 + 1;     // + one sink pair; the TMEM kernel keeps no J in shared memory
 
   // element offsets (double index; add the lane id t, or 2*t inside the J region)
   // J region starts at double2 index o_J2; vector region at double index o_vec (set below, after the blob size is known):
   // offsets are stored relative to those bases and rebased at the end.
   auto voff = [&](int sl, int e) { return (sl + e) * CPB; };                       // + o_vec
-  auto joff = [&](int i, int j) { return 2 * ((i * lt.LDJ2 + (j >> 1)) * CPB) + (j & 1); };   // + 2*o_J2
-  const int jsink_rel = 2 * (N * lt.LDJ2 * CPB);
+  auto joff = [&](int i, int j) {
+    if (tmG > 0) return 2 * (16 * i + j);                                           // TMEM column (32-bit units), not rebased
+    return 2 * ((i * lt.LDJ2 + (j >> 1)) * CPB) + (j & 1);                          // + 2*o_J2
+  };
+  const int jsink_rel = tmG > 0 ? 2 * (16 * 15) : 2 * (N * lt.LDJ2 * CPB);          // TMEM: row 15 is never a matrix row
 
   // ---- term streams
-  struct Entry { int dest0, dest1; std::vector<std::pair<int, double>> terms; double init; int kk; };
+  struct Entry { int dest0, dest1; std::vector<std::pair<int, double>> terms; double init; int kk; int moff = -1; };
   struct Built { std::vector<int32_t> hdr; int ng = 0; int nterms = 0, nsteps = 0; };
   std::vector<double> coef;      // blocks: [init[4]] [steps][4]
   std::vector<int32_t> toff;     // blocks: [steps][4]
@@ -223,6 +233,11 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
         closers.push_back(0);
       } else if (ndest == 1) {
         closers.push_back(e ? e->dest0 : voff(lt.s_sm, h.ncplx + 1));
+      } else if (ndest == 4) {             // TMEM plan B: {column (i,j), column (j,i), m_i offset (diagonal) or -1, 0}
+        closers.push_back(e ? e->dest0 : jsink_rel);
+        closers.push_back(e ? e->dest1 : jsink_rel);
+        closers.push_back(e ? e->moff : -1);
+        closers.push_back(0);
       } else {
         closers.push_back(e ? e->dest0 : jsink_rel);
         closers.push_back(e ? e->dest1 : jsink_rel);
@@ -284,11 +299,24 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
         }
       }
     for (int i = 0; i < N; ++i) EA.push_back(rowsA[i]);       // rows without terms still write tot_i = 0
+    if (tmG > 0) {
+      // every diagonal entry exists (also for species in no complex and for the padding rows of the shape) and carries the
+      // offset of m_i: its closer forms Jln_ii = fma(m_i, dp, D_ii dp) in one store, no read-modify-write on TMEM
+      for (int i = 0; i < N; ++i) {
+        auto it = bmap.find((i << 8) | i);
+        if (it == bmap.end()) {
+          it = bmap.insert({(i << 8) | i, (int)EB.size()}).first;
+          Entry e; e.dest0 = joff(i, i); e.dest1 = joff(i, i); e.init = 0.0; e.kk = 0;
+          EB.push_back(e);
+        }
+        EB[it->second].moff = voff(lt.s_m, i);
+      }
+    }
   }
   Built BS, BA, BB;
   build_stream(ES, 3, false, BS, lt.spec);
   build_stream(EA, 1, true, BA, lt.planA);
-  build_stream(EB, 2, true, BB, lt.planB);
+  build_stream(EB, tmG > 0 ? 4 : 2, true, BB, lt.planB);
   p->terms_spec = BS.nterms; p->terms_A = BA.nterms; p->terms_B = BB.nterms;
   p->steps_spec = BS.nsteps; p->steps_A = BA.nsteps; p->steps_B = BB.nsteps;
 
@@ -348,7 +376,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
   }
   lt.smem_dbl = (int)(need / 8);
   p->smem_bytes = need;
-  lt.jsink = 2 * lt.o_J2 + jsink_rel;
+  lt.jsink = tmG > 0 ? jsink_rel : 2 * lt.o_J2 + jsink_rel;
   // rebase offsets: vector-region offsets += o_vec ; J-region offsets += 2*o_J2
   {
     int32_t *ti = pi.data();
@@ -365,6 +393,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
         int32_t *c = ti + i_closers + hd[4];
         for (int a = 0; a < nmem; ++a) {
           if (ndest == 3) { c[a * 4] += lt.o_vec; c[a * 4 + 1] += lt.o_vec; }
+          else if (ndest == 4) { if (c[a * 4 + 2] >= 0) c[a * 4 + 2] += lt.o_vec; }
           else if (ndest == 1) c[a] += lt.o_vec;
           else { c[a * 2] += 2 * lt.o_J2; c[a * 2 + 1] += 2 * lt.o_J2; }
         }
@@ -373,7 +402,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
         hd[4] = i_closers + hd[4];
       }
     };
-    fix_closers(lt.spec, 3); fix_closers(lt.planA, 1); fix_closers(lt.planB, 2);
+    fix_closers(lt.spec, 3); fix_closers(lt.planA, 1); fix_closers(lt.planB, tmG > 0 ? 4 : 2);
   }
   if (lt.d_coef != 0 || (lt.i_off & 3) || (i_closers & 3) || (i_ghdr & 3)) return unusable("internal: plan blob misaligned");
   p->blob.resize((size_t)lt.blob_dbl * 8 + (size_t)lt.blob_int * 4);

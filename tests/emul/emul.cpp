@@ -19,6 +19,8 @@ using std::isfinite;
 #undef RXN_IDEAL_GAS_CONSTANT
 #define RXN_LANE_HOST 1
 #include "../../pflotran_b200/csrc/rxn_lane_dev.cuh"
+#define RXN_TM_HOST 1
+#include "../../pflotran_b200/csrc/rxn_tm_dev.cuh"
 #include "../../pflotran_b200/csrc/rxn_flux.h"
 
 using namespace rxn;
@@ -189,7 +191,107 @@ static void lane_cells_g(const LaneJob &J, int G) {
   else lane_cells<N, 4>(J);
 }
 
+// tensor-memory RReact kernel (rxn_tm_dev.cuh): plan built for one resident cell (CPB = 1, J in the emulated TMEM lane); the G
+// member warps of the cell are G host threads (one lane each) that run the rounds of k_react_tm: load -> trips (run, then
+// closing after an abnormal exit) -> finish, meeting at a barrier where the device has the quad's named barrier.
+template <int N, int G>
+static void tm_thread(const LaneJob *J, LaneTab lt, int l) {
+  using namespace rxn::tmk;
+  const DevTab &h = J->e->R.h;
+  const DevState &S = *J->S;
+  const double inv_dt = 1.0 / J->dt;
+  Ctx<N, G> c;
+  tm_bind<N, 1, G>(lt, c, 0, l, 0, 0u);
+  tm_init_column<N, 1, G>(lt, c);
+  for (long long i = 0; i < J->nlocal; ++i) {
+    const long long cell = J->l2g ? J->l2g[i] : i;
+    if (S.active && !S.active[cell]) {
+      if (l == 0) {
+        if (J->iters) J->iters[i] = 0;
+        if (J->flags) J->flags[i] = RXN_FLAG_INACTIVE;
+      }
+      continue;
+    }
+    tm_load<N, 1, G>(lt, c, S, J->e->T.d, J->e->T.i, h, i, cell, J->tran_xx, J->dt);
+    bool closing = false;
+    int pending = 0;
+    for (;;) {
+      grp_sync<G>(c);
+      int st;
+      bool recompute;
+      tm_trip<N, 1, G>(lt, c, S, J->dt, inv_dt, J->dt_mode, !closing, closing, st, recompute);
+      bool fin = false;
+      int status = 0;
+      if (closing) { fin = true; status = pending; }
+      else if (st != 0) {
+        if (recompute) { pending = st; closing = true; }
+        else { fin = true; status = st; }
+      }
+      if (fin) {
+        tm_finish<N, 1, G>(lt, c, S, h, J->tran_xx, J->iters, J->flags, true, status);
+        break;
+      }
+    }
+  }
+}
+template <int N, int G>
+static void tm_cells(const LaneJob &J) {
+  using namespace rxn::tmk;
+  LaneTab lt = J.P->lt;
+  const DevTab &h = J.e->R.h;
+  for (int ikr = 0; ikr < lt.nmr && ikr < 2; ++ikr) {
+    double K1 = 0.0;
+    for (int irate = 0; irate < J.e->T.i[h.o_mr_nrate + ikr]; ++irate) {
+      const double rate = J.e->T.d[h.o_mr_rate + ikr * h.mr_ld + irate], frac = J.e->T.d[h.o_mr_frac + ikr * h.mr_ld + irate];
+      const double kdt = rate * J.dt;
+      const double one_plus_kdt = 1.0 + kdt;
+      const double kk = rate / one_plus_kdt;
+      K1 = K1 + kk * frac;
+    }
+    lt.mrK1[ikr] = K1;
+  }
+  std::vector<double> sm((size_t)lt.smem_dbl + 16, 0.0), tmem(256, 0.0);
+  memcpy(sm.data(), J.P->blob.data(), J.P->blob.size());
+  rxn::tmk::tsm = sm.data();
+  rxn::tmk::tmh = tmem.data();
+  rxn::tmk::HostGroup hg;
+  pthread_barrier_init(&hg.bar, nullptr, G);
+  rxn::tmk::g_hg = &hg;
+  std::vector<std::thread> th;
+  for (int l = 1; l < G; ++l) th.emplace_back(tm_thread<N, G>, &J, lt, l);
+  tm_thread<N, G>(&J, lt, 0);
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&hg.bar);
+  rxn::tmk::g_hg = nullptr;
+  rxn::tmk::tsm = nullptr;
+  rxn::tmk::tmh = nullptr;
+}
+template <int N>
+static void tm_cells_g(const LaneJob &J, int G) {
+  if (G == 1) tm_cells<N, 1>(J);
+  else if (G == 2) tm_cells<N, 2>(J);
+  else tm_cells<N, 4>(J);
+}
+
 extern "C" {
+
+int emu_react_tm(void *hh, const HostView *v, double *tran_xx, const uint8_t *active, const int32_t *l2g, int64_t nlocal, double dt,
+                 int dt_mode, int32_t *iters, int32_t *flags, int G, int forceN, char *err, int errlen) {
+  Emu *e = (Emu *)hh;
+  DevState S = mk_state(v, active);
+  LanePlan P;
+  const int N = forceN >= e->R.h.naq ? forceN : (e->R.h.naq <= 12 ? 12 : 15);
+  if (G != 1 && G != 2 && G != 4) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4"); return RXN_ERR_INVALID; }
+  int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P, false, G);
+  if (rc != RXN_OK || !P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
+  LaneJob J{&P, e, &S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags};
+  switch (N) {
+    case 12: tm_cells_g<12>(J, G); break;
+    case 15: tm_cells_g<15>(J, G); break;
+    default: if (err) snprintf(err, errlen, "no tensor-memory shape N=%d in the harness", N); return RXN_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
 
 void *emu_create(const RxnTablesDesc *d, char *err, int errlen) {
   Emu *e = new Emu();

@@ -53,6 +53,44 @@ def test_react_resident_lane(name, dt, mode, G):
     assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
 
 
+@pytest.mark.parametrize('name', LANE_WORKLOADS)
+@pytest.mark.parametrize('dt,mode', [(3600.0, abi.RXN_DT_CONSISTENT), (1.0, abi.RXN_DT_AS_WRITTEN)])
+@pytest.mark.parametrize('G', [1, 2, 4])
+def test_react_tensor_memory_routines(name, dt, mode, G):
+    """Routines of the tensor-memory kernel (rxn_tm_dev.cuh: J rows in the emulated TMEM lane, k-unrolled LU with select
+    swaps, predicated trips, exchange-slot reductions) with G member warps per cell (host threads, one lane each),
+    against the oracle.  Chemistries with fewer than 13 primaries run on the padded N = 12 shape."""
+    w, cells = workload_cells(name, 300 if G > 1 else 600)
+    st_o = synth.host_state(w, cells)
+    st_e = st_o.copy()
+    xo = cells['tran_xx'].copy()
+    xe = xo.copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, dt, mode, maxit=10000)
+    it_e, fl_e = Emulator(w.tables).react_tm(st_e, xe, dt, mode, G=G)
+    assert (it_o == it_e).all() and (fl_o == fl_e).all()
+    ok = (fl_o & ~3) == 0
+    assert rel_err(xe[ok], xo[ok]).max() <= RTOL
+    assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
+
+
+@pytest.mark.parametrize('G', [1, 2, 4])
+def test_tensor_memory_iteration_cap_and_inactive(G):
+    """Abnormal exit (iteration cap) in the predicated trip: the lane turns `closing`, redoes RTotal, then finishes."""
+    w, cells = workload_cells('hanford300a_eq', 200)
+    st_o = synth.host_state(w, cells)
+    st_o.active[::7] = 0
+    st_e = st_o.copy()
+    xo = cells['tran_xx'].copy()
+    xe = xo.copy()
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=3)
+    it_e, fl_e = Emulator(w.tables).react_tm(st_e, xe, 3600.0, abi.RXN_DT_CONSISTENT, maxit=3, G=G)
+    assert (fl_e & abi.RXN_FLAG_CAPPED).any() and (fl_e[::7] == abi.RXN_FLAG_INACTIVE).all()
+    assert (it_o == it_e).all() and (fl_o == fl_e).all()
+    act = np.where(st_o.active != 0)[0]
+    assert rel_err(xe[act], xo[act]).max() <= RTOL
+    assert_state_close(st_e, st_o, cells=act, what='capped', tables=w.tables)
+
+
 @pytest.mark.parametrize('G', [1, 4])
 def test_resident_lane_iteration_cap_and_inactive(G):
     """Abnormal exit (iteration cap): pri_molal moved after the last RTotal, so the closing pass must redo it."""

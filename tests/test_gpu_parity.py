@@ -54,6 +54,7 @@ def test_react_resident_lane_group_widths(name, G, monkeypatch):
     """Resident-lane kernel with 1, 2 and 4 lanes per cell (RXN_LANE_G picks the compiled shape), enough cells
     that every lane group takes several cells from the work counter."""
     monkeypatch.setenv('RXN_LANE_G', str(G))
+    monkeypatch.setenv('RXN_TM', '0')          # the shared-memory-J kernel (the tensor-memory kernel is the default for N <= 15)
     n = 30000
     w, cells = workload_cells(name, n)
     st_o = synth.host_state(w, cells)
@@ -61,6 +62,30 @@ def test_react_resident_lane_group_widths(name, G, monkeypatch):
     rx, rz = _gpu_state(w, st_g)
     rz.set_react_kernel(3)
     assert 'lanes/cell=%d' % G in rz.react_kernel_info()
+    xo = cells['tran_xx'].copy()
+    xg = xo.copy()
+    it_g, fl_g = rz.RTReact(xg, 3600.0, abi.RXN_DT_CONSISTENT)
+    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=10000, nthreads=8)
+    rz.download_host_state(st_g)
+    assert (it_o == it_g).all() and (fl_o == fl_g).all()
+    ok = (fl_o & ~3) == 0
+    assert rel_err(xg[ok], xo[ok]).max() <= RTOL
+    assert_state_close(st_g, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
+
+
+@pytest.mark.parametrize('G', [1, 2, 4])
+@pytest.mark.parametrize('name', ['hanford300a_eq', 'hanford300a_mr'])
+def test_react_tensor_memory_kernel(name, G, monkeypatch):
+    """Tensor-memory kernel (J in TMEM, rxn_tm_dev.cuh) with 1, 2 and 4 member warps per cell; enough cells that every lane
+    takes several cells from the work counter and cells of one warp sit in different Newton iterations."""
+    monkeypatch.setenv('RXN_TM_G', str(G))
+    n = 40000
+    w, cells = workload_cells(name, n)
+    st_o = synth.host_state(w, cells)
+    st_g = st_o.copy()
+    rx, rz = _gpu_state(w, st_g)
+    rz.set_react_kernel(3)
+    assert 'tensor-memory' in rz.react_kernel_info() and 'warps/cell=%d' % G in rz.react_kernel_info()
     xo = cells['tran_xx'].copy()
     xg = xo.copy()
     it_g, fl_g = rz.RTReact(xg, 3600.0, abi.RXN_DT_CONSISTENT)
