@@ -897,8 +897,15 @@ TM_DEV void tm_load(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, const do
 #pragma unroll 1
     for (int k = c.l; k < lt.ncplx; k += G) tsm[c.vlng + (n + k) * CPB] = c_log(GSL(S, RXN_F_SEC_ACT_COEF, k, cell));
   } else {
+    // lagged sec_molal (for the ionic strength): straight from HBM into the cell's column, all copies in flight at once
+#ifndef RXN_TM_HOST
 #pragma unroll 4
-    for (int k = c.l; k < lt.ncplx; k += G) tsm[c.vsm + k * CPB] = GSL(S, RXN_F_SEC_MOLAL, k, cell);   // lagged, for I
+    for (int k = c.l; k < lt.ncplx; k += G)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tsm[c.vsm + k * CPB])),
+                   "l"(&GSL(S, RXN_F_SEC_MOLAL, k, cell)) : "memory");
+#else
+    for (int k = c.l; k < lt.ncplx; k += G) tsm[c.vsm + k * CPB] = GSL(S, RXN_F_SEC_MOLAL, k, cell);
+#endif
   }
 #pragma unroll 1
   for (int q = c.l; q < lt.nrxn; q += G) tsm[c.vfree + q * CPB] = GSL(S, RXN_F_FREE_SITE_CONC, q, cell);
@@ -909,25 +916,64 @@ TM_DEV void tm_load(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, const do
   }
   if (lt.percell_logK)
     tm_percell_logK<CPB, G>(c.l, lt.ncoef, lt.logK_mode, c.vlk, c.temp, GSL(S, RXN_F_PRES, 0, cell), blob_d, h.cplx, h.kin, h.srf);
-  // multirate sorption: R0_i = sum_r k_r/(1+k_r dt) S_r,i (multirate_prepare, rxn_device.cuh; REASSOC: even and odd rates
-  // summed separately, then added, as lane_coop_in_mr)
+#ifndef RXN_TM_HOST
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
+// multirate sorption of a cell just taken: R0_i = sum_r k_r/(1+k_r dt) S_r,i (multirate_prepare, rxn_device.cuh; REASSOC: even
+// and odd rates summed separately, then added, as lane_coop_in_mr).  750 doubles per 300A cell: every lane of the warp loads
+// for ONE cell at a time - lane (ii, half) sums the even (half 0) or odd (half 1) rates of row l + G ii, all its loads in
+// flight before the first add - and the sum lands in that cell's column.  W = lanes of the warp (host: 1).
+template <int N, int CPB, int G>
+TM_DEV void tm_coop_in_mr(const LaneTab &lt, const DevState &S, const DevTab &h, const double *blob_d, const int *blob_i, int l, int slot,
+                          long long cell, double tran_dt, int w, int W) {
+  const int vr0 = lt.o_vec + lt.s_r0 * CPB + slot;
+  const int n = lt.n;
+  const int H = W >= 32 ? 2 : 1, per = W / H;
 #pragma unroll 1
   for (int ikr = 0; ikr < lt.nmr; ++ikr) {
     const int nrate = blob_i[h.o_mr_nrate + ikr];
     const long long row0 = ((long long)ikr * (h.mr_ld + 1) + 1) * n;
 #pragma unroll 1
-    for (int i = c.l; i < n; i += G) {
+    for (int i0 = l; i0 < n; i0 += G * per) {
+      const int i = i0 + G * (w % per), half = w / per;
       double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 2
-      for (int irate = 0; irate < nrate; irate += 2) {
-        const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
-        acc0 = acc0 + rate / (1.0 + rate * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell);
-        if (irate + 1 < nrate) {
-          const double rate1 = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate + 1];
-          acc1 = acc1 + rate1 / (1.0 + rate1 * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)(irate + 1) * n + i, cell);
+      if (i < n) {
+        if (H == 2) {
+#pragma unroll 1
+          for (int r0 = half; r0 < nrate; r0 += 16) {           // 8 loads of this lane in flight
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int irate = r0 + 2 * u;
+              v[u] = irate < nrate ? GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int irate = r0 + 2 * u;
+              if (irate < nrate) {
+                const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
+                acc0 = acc0 + rate / (1.0 + rate * tran_dt) * v[u];
+              }
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int irate = 0; irate < nrate; irate += 2) {
+            const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
+            acc0 = acc0 + rate / (1.0 + rate * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell);
+            if (irate + 1 < nrate) {
+              const double rate1 = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate + 1];
+              acc1 = acc1 + rate1 / (1.0 + rate1 * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)(irate + 1) * n + i, cell);
+            }
+          }
         }
       }
-      tsm[c.vr0 + (ikr * N + i) * CPB] = acc0 + acc1;
+#ifndef RXN_TM_HOST
+      if (H == 2) acc1 = __shfl_xor_sync(0xffffffffu, acc0, per);   // the odd-rate sum of lane (ii, 1)
+#endif
+      if (i < n && half == 0) tsm[vr0 + (ikr * N + i) * CPB] = acc0 + acc1;
     }
   }
 }

@@ -46,6 +46,7 @@ k_react_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h,
     const double inv_dt = 1.0 / dt;
 #pragma unroll 1
     for (;;) {
+      bool fresh = false;                                       // this lane took a cell in this round
 #pragma unroll 1
       for (;;) {                                                // hand out work to the idle lanes of this warp
         const bool want = !has && !exhausted;
@@ -74,13 +75,21 @@ k_react_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h,
               }
             } else {
               tm_load<N, CPB, G>(lt, c, S, bd, bi, h, i, cell, tran_xx, dt);
-              has = true; closing = false; pending = 0;
+              has = true; closing = false; pending = 0; fresh = true;
             }
           }
         }
         __syncwarp();
       }
       if (!__any_sync(0xffffffffu, has)) break;
+      if (lt.nmr > 0) {                                         // the multirate sorbed totals of the cells just taken, one cell after the other
+        for (unsigned fm = __ballot_sync(0xffffffffu, fresh); fm != 0u; fm &= fm - 1u) {
+          const int g = __ffs(fm) - 1;
+          const int slot = __shfl_sync(0xffffffffu, c.s, g);
+          const long long cell = __shfl_sync(0xffffffffu, c.cell, g);
+          tm_coop_in_mr<N, CPB, G>(lt, S, h, bd, bi, l, slot, cell, dt, ln, 32);
+        }
+      }
       grp_sync<G>(c);                                           // the loads of every member are in shared memory
       int st;
       bool recompute;

@@ -213,6 +213,7 @@ static void tm_thread(const LaneJob *J, LaneTab lt, int l) {
       continue;
     }
     tm_load<N, 1, G>(lt, c, S, J->e->T.d, J->e->T.i, h, i, cell, J->tran_xx, J->dt);
+    if (lt.nmr > 0) tm_coop_in_mr<N, 1, G>(lt, S, h, J->e->T.d, J->e->T.i, l, 0, cell, J->dt, 0, 1);
     bool closing = false;
     int pending = 0;
     for (;;) {

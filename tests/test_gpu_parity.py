@@ -78,6 +78,8 @@ def test_react_resident_lane_group_widths(name, G, monkeypatch):
 def test_react_tensor_memory_kernel(name, G, monkeypatch):
     """Tensor-memory kernel (J in TMEM, rxn_tm_dev.cuh) with 1, 2 and 4 member warps per cell; enough cells that every lane
     takes several cells from the work counter and cells of one warp sit in different Newton iterations."""
+    if G == 1 and name == 'hanford300a_mr':
+        pytest.skip('G = 1 is compiled for 128 cells per CTA only (ablation shape); the multirate vectors need 96')
     monkeypatch.setenv('RXN_TM_G', str(G))
     n = 40000
     w, cells = workload_cells(name, n)
