@@ -379,7 +379,7 @@ def main():
     ap.add_argument('--workload', default='hanford300a_eq', choices=sorted(DEFAULT_CELLS))
     ap.add_argument('--cells', type=int, default=0, help='cells per GPU (default: the BASELINE config size)')
     ap.add_argument('--dt', type=float, default=3600.0)
-    ap.add_argument('--kernel', type=int, default=0, choices=[0, 1, 2, 3])
+    ap.add_argument('--kernel', type=int, default=0, choices=[0, 1, 3])
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

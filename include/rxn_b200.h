@@ -231,10 +231,10 @@ int64_t rxn_state_ncells(const RxnState *s);
  * flux-side consumers (TFluxDerivative, transport.F90:368-626) need them, RReact does not.
  * After this call rxn_update_auxvars_batch / rxn_react_batch also store that field. */
 int rxn_state_materialize(RxnState *s, int field);
-/* RReact kernel: 0 = automatic (resident-lane if the tables allow it, else cooperative, else thread per cell),
- * 1 = one thread per cell with per-thread arrays in local memory, 2 = cooperative lane-group per cell,
- * 3 = resident-lane (cell state in shared memory, persistent lanes); 2 and 3 fail if the tables do not fit them.
- * Benchmark / test control only; results are the same path. */
+/* RReact kernel: 0 = automatic (the tensor-memory kernel when the Newton matrix fits a TMEM lane, N <= 15; else the
+ * resident-lane kernel; else thread per cell), 1 = one thread per cell with per-thread arrays in local memory,
+ * 3 = on-chip kernels only (tensor memory / resident lane; fails if the tables do not fit them).  2 was round 1's cooperative
+ * kernel and is rejected.  Benchmark / test control only; results are the same path. */
 int rxn_set_react_kernel(RxnState *s, int which);
 /* constraint types of ReactionEquilibrateConstraint (transport_constraint.F90:217-330, reaction_aux.F90 CONSTRAINT_*) */
 enum { RXN_CONSTRAINT_NULL = 0, RXN_CONSTRAINT_FREE = 1, RXN_CONSTRAINT_TOTAL = 2, RXN_CONSTRAINT_LOG = 3, RXN_CONSTRAINT_PH = 4,

@@ -18,7 +18,6 @@
 #include "../../include/rxn_b200.h"
 #include "rxn_kernels.cuh"
 #include "rxn_pack.h"
-#include "rxn_tile.cuh"
 #include "rxn_lane.cuh"
 #include "rxn_flux.cuh"
 
@@ -51,7 +50,6 @@ int fail(int code, const char *fmt, ...) {
 
 struct RxnTables {
   DevTab h;
-  TilePlan tile;           // cooperative (lane-group per cell) kernel plan, rxn_tile.cuh
   mutable LaneKernel lane; // resident-lane (thread per cell, state in shared memory) kernel, rxn_lane.cuh
   double *d_blob = nullptr;
   size_t blob_bytes = 0;
@@ -71,7 +69,7 @@ struct RxnState {
   // grow-only scratch for the host-buffer entry points
   void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[4] = {0, 0, 0, 0};
-  int react_kernel = 0;    // 0 auto, 1 thread-per-cell, 2 cooperative tile, 3 resident lane
+  int react_kernel = 0;    // 0 auto, 1 thread-per-cell, 3 resident lane / tensor memory (2: the cooperative kernel of round 1, removed)
   unsigned long long *d_counter = nullptr;   // work counter of the resident-lane kernel
   // host-buffer RReact: chunks of the batch move over PCIe while the previous / next chunk is being solved
   enum { NCHUNK = 8 };
@@ -204,10 +202,8 @@ int rxn_tables_create(const RxnTablesDesc *d, int device, RxnTables **out) {
     delete t;
     return rc2;
   }
-  rc = tile_plan_build(d, h, P.d, P.i, t->blob_bytes, device, &t->tile);
-  if (rc != RXN_OK) { int rc2 = fail(rc, "tile plan: %s", t->tile.err.c_str()); cudaFree(t->d_blob); delete t; return rc2; }
   rc = lane_kernel_build(h, P.d, P.i, device, &t->lane);
-  if (rc != RXN_OK) { int rc2 = fail(rc, "lane plan: %s", t->lane.plan.err.c_str()); tile_plan_free(&t->tile); cudaFree(t->d_blob); delete t; return rc2; }
+  if (rc != RXN_OK) { int rc2 = fail(rc, "lane plan: %s", t->lane.plan.err.c_str()); lane_kernel_free(&t->lane); cudaFree(t->d_blob); delete t; return rc2; }
   *out = t;
   return RXN_OK;
 }
@@ -216,7 +212,6 @@ int rxn_tables_destroy(RxnTables *t) {
   if (!t) return RXN_OK;
   cudaSetDevice(t->device);
   if (t->d_blob) cudaFree(t->d_blob);
-  tile_plan_free(&t->tile);
   lane_kernel_free(&t->lane);
   delete t;
   return RXN_OK;
@@ -385,7 +380,7 @@ int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
   if (!s || !buf || len < 1) return fail(RXN_ERR_INVALID, "bad argument");
   const RxnTables *t = s->t;
   const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
-  const bool tile_ok = t->tile.usable && no_dtotal, lane_ok = t->lane.plan.usable && no_dtotal;
+  const bool lane_ok = t->lane.plan.usable && no_dtotal;
   if (lane_ok && t->lane.plan_tm.usable && (s->react_kernel == 0 || s->react_kernel == 3))
     snprintf(buf, (size_t)len, "tensor-memory N=%d cells/CTA=%d warps/cell=%d threads=%d smem=%zu B plan=%zu B J in TMEM (spec %d, planA %d, planB %d terms)",
              t->lane.plan_tm.lt.N, t->lane.plan_tm.lt.CPB, t->lane.G_tm, 128 * t->lane.G_tm, t->lane.plan_tm.smem_bytes,
@@ -394,12 +389,9 @@ int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
     snprintf(buf, (size_t)len, "resident-lane N=%d cells/CTA=%d lanes/cell=%d threads=%d smem=%zu B plan=%zu B (spec %d, planA %d, planB %d terms)",
              t->lane.plan.lt.N, t->lane.plan.lt.CPB, t->lane.G, ((t->lane.plan.lt.CPB * t->lane.G + 31) / 32) * 32, t->lane.plan.smem_bytes,
              t->lane.plan.blob.size(), t->lane.plan.terms_spec, t->lane.plan.terms_A, t->lane.plan.terms_B);
-  else if (tile_ok && s->react_kernel != 1 && s->react_kernel != 3)
-    snprintf(buf, (size_t)len, "cooperative lane-group G=%d cells/CTA=%d threads=%d smem=%zu B", t->tile.tt.G, t->tile.tt.cpb,
-             t->tile.tt.threads, t->tile.smem_bytes);
   else
-    snprintf(buf, (size_t)len, "thread-per-cell N<=%d (lane: %s; tile: %s)", t->nvariant,
-             t->lane.plan.usable ? "DTOTAL materialised" : t->lane.plan.err.c_str(), t->tile.usable ? "DTOTAL materialised" : t->tile.err.c_str());
+    snprintf(buf, (size_t)len, "thread-per-cell N<=%d (lane: %s)", t->nvariant,
+             t->lane.plan.usable ? "DTOTAL materialised" : t->lane.plan.err.c_str());
   return RXN_OK;
 }
 
@@ -408,13 +400,11 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
   const RxnTables *t = s->t;
   // the shared-memory kernels keep dtotal only as Newton scratch: states with DTOTAL materialised use thread-per-cell
   const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
-  const bool tile_ok = t->tile.usable && no_dtotal, lane_ok = t->lane.plan.usable && no_dtotal;
-  if (s->react_kernel == 2 && !tile_ok)
-    return fail(RXN_ERR_UNSUPPORTED, "cooperative kernel unavailable: %s", t->tile.usable ? "DTOTAL is materialised" : t->tile.err.c_str());
+  const bool lane_ok = t->lane.plan.usable && no_dtotal;
+  if (s->react_kernel == 2) return fail(RXN_ERR_UNSUPPORTED, "the cooperative kernel of round 1 has been removed (use 0, 1 or 3)");
   if (s->react_kernel == 3 && !lane_ok)
     return fail(RXN_ERR_UNSUPPORTED, "resident-lane kernel unavailable: %s", t->lane.plan.usable ? "DTOTAL is materialised" : t->lane.plan.err.c_str());
   const bool use_lane = lane_ok && (s->react_kernel == 0 || s->react_kernel == 3);
-  const bool use_tile = !use_lane && tile_ok && s->react_kernel != 1;
   if (use_lane) {
     if (!s->d_counter) CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
     int rc = lane_launch_react(t->lane, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->d_counter, s->stream);
@@ -423,11 +413,7 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
     ++g_launches;
     return RXN_OK;
   }
-  if (use_tile) {
-    int rc = tile_launch_react(t->tile, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->stream);
-    if (rc != RXN_OK) return fail(rc, "no cooperative kernel variant for G=%d", t->tile.tt.G);
-    ++g_launches;
-  } else {
+  {
     int threads = t->nvariant <= 8 ? 128 : 64;
     if (const char *e = getenv("RXN_TPC_BLOCK")) threads = std::max(32, atoi(e));
     unsigned grid = nblocks(nlocal, threads);

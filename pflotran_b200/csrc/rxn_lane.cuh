@@ -11,11 +11,11 @@ namespace rxn {
 // per N in order of preference - the first shape whose per-cell state fits in shared memory is used
 // (measured on B200, 300A chemistry: G = 2 > G = 1 > G = 4; keep in sync with LANE_SHAPES in the Makefile)
 #define RXN_LANE_SHAPES(X) \
-  X(4, 512, 1) X(4, 448, 1) X(4, 384, 1) X(4, 256, 1) X(4, 128, 1) \
-  X(8, 192, 1) X(8, 128, 1) X(8, 64, 1) X(8, 128, 2) \
-  X(12, 96, 2) X(12, 64, 2) X(12, 96, 1) X(12, 64, 1) X(12, 64, 4) \
-  X(15, 64, 2) X(15, 60, 2) X(15, 56, 2) X(15, 48, 2) X(15, 64, 4) X(15, 60, 4) X(15, 64, 1) X(15, 60, 1) \
-  X(16, 64, 2) X(16, 56, 2) X(16, 48, 2) X(16, 64, 4) X(16, 64, 1) \
+  X(4, 448, 1) X(4, 256, 1) X(4, 128, 1) \
+  X(8, 192, 1) X(8, 128, 1) X(8, 64, 1) \
+  X(12, 96, 2) X(12, 64, 2) X(12, 64, 1) X(12, 64, 4) \
+  X(15, 64, 2) X(15, 60, 2) X(15, 48, 2) X(15, 64, 4) X(15, 64, 1) \
+  X(16, 64, 2) X(16, 48, 2) \
   X(24, 32, 2) X(24, 28, 2) X(24, 24, 2) X(24, 16, 2) X(24, 28, 4) X(24, 28, 1)
 
 // tensor-memory kernel shapes (rxn_tm_dev.cuh): X(N, QUADS, G) = matrix dimension (<= 15), 32-cell quads per CTA, member warps

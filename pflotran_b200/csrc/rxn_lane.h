@@ -7,8 +7,8 @@
 // (element e of lane t at  e*CPB + t : every warp access is conflict free and needs no address
 // arithmetic beyond an immediate), while the fixed accumulation and the per-cell scalars stay in
 // registers.  Because all 32 lanes of a warp walk the chemistry tables in lock step, a table read is
-// one shared-memory broadcast and the loop control is shared by 32 cells (the cooperative kernel,
-// rxn_tile.cuh, pays it once per 4 cells).  Lanes are PERSISTENT: a lane whose cell has converged
+// one shared-memory broadcast and the loop control is shared by 32 cells (round 1's cooperative kernel, 8 lanes per
+// cell, paid it once per 4 cells).  Lanes are PERSISTENT: a lane whose cell has converged
 // writes it back and takes the next cell from a global counter, so a warp never waits for its
 // slowest cell (trip efficiency ~100 % instead of max-of-32 iterations).
 //
@@ -109,7 +109,7 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
   if (!gamma_state && h.act_alg == RXN_ACT_COEF_ALGORITHM_NEWTON && h.act_freq != RXN_ACT_COEF_FREQUENCY_OFF)
     return unusable("NEWTON activity-coefficient algorithm runs on the thread-per-cell kernel");
   if (h.nionx > 0 || h.nkd > 0) return unusable("ion exchange / KD isotherms run on the thread-per-cell kernel");
-  if (h.maxpref > 0) return unusable("mineral prefactors run on the cooperative kernel");
+  if (h.maxpref > 0) return unusable("mineral prefactors run on the thread-per-cell kernel");
   if (n > N) return unusable("naq exceeds the shape");
   if (tmG > 0 && N > 15) return unusable("tensor-memory kernel: a row [J_i | b_i] must fit 16 doubles (N <= 15)");
   lt.N = N; lt.CPB = CPB; lt.LDJ2 = (N + 2) / 2;
