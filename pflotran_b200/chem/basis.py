@@ -332,10 +332,13 @@ def build_tables(deck: dk.Deck, database_path: str = None, isothermal: bool = Tr
     for sub in gas_names + sec_names:
         subrxn = sec_stoich[sub]
         for mn in chem.minerals:
-            if mn in chem.mineral_kinetics:
-                m = db.minerals[mn]
-                while sub in m.dbaserxn.spec_name:
-                    _sub_species(sub, subrxn, m.dbaserxn, True)
+            # The snapshot substitutes only into minerals with a kinetic rate law (`associated(cur_mineral%tstrxn)`,
+            # reaction_database.F90:1401,1467) and would then stop in BasisAlignSpeciesInRxn for a non-kinetic mineral written
+            # in a secondary species (Goethite / Fe+++ in example_problems/ascem_chemistry).  That deck's own pflotran.out
+            # ("Final Basis", :4886) shows the substitution applied to every mineral: followed here (identical for kinetic ones).
+            m = db.minerals[mn]
+            while sub in m.dbaserxn.spec_name:
+                _sub_species(sub, subrxn, m.dbaserxn, True)
         for sn in srf_names:
             s = db.srfcplx[sn]
             while sub in s.dbaserxn.spec_name:

@@ -235,6 +235,7 @@ class Deck:
     reference_temperature: float = 25.0
     reference_pressure: float = 101325.0
     path: str = ''
+    rock_density: Optional[float] = None         # ROCK_DENSITY of the first MATERIAL_PROPERTY -> material_auxvar%soil_particle_density
     reference_density: Optional[float] = None    # REFERENCE_DENSITY (factory_subsurface.F90:1734); None: IFC-67 at the reference T, P (:995)
 
 
@@ -575,6 +576,7 @@ def read_deck(path: str) -> Deck:
     ref_t = 25.0
     ref_p = 101325.0
     ref_den = None
+    rock_den = None
     while True:
         toks = rd.next()
         if toks is None:
@@ -591,6 +593,8 @@ def read_deck(path: str) -> Deck:
                         porosity = fnum(t[1])
                     except ValueError:      # POROSITY DATASET name: per-cell values, not ours
                         porosity = None
+                elif t[0].upper() == 'ROCK_DENSITY' and rock_den is None:
+                    rock_den = fnum(t[1])
                 elif t[0].upper() in ('PERMEABILITY', 'SATURATION_FUNCTION'):
                     # nested blocks
                     if len(t) == 1 or t[0].upper() == 'PERMEABILITY':
@@ -603,4 +607,4 @@ def read_deck(path: str) -> Deck:
             ref_den = fnum(toks[1])
     if chem is None:
         raise DeckError('no CHEMISTRY card in ' + path)
-    return Deck(chem, constraints, porosity, ref_t, ref_p, path, ref_den)
+    return Deck(chem, constraints, porosity, ref_t, ref_p, path, rock_den, ref_den)

@@ -69,8 +69,12 @@ def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, w
             continue
         if cells is not None:
             a, b = a[:, cells], b[:, cells]
-        # values far below the row's scale are differences of O(1) sums: compare them on that scale
-        scale = np.maximum(np.abs(b), 1e-13 * np.max(np.abs(b), axis=1, keepdims=True))
+        if f in ('PRI_MOLAL', 'MNRL_VOLFRAC'):
+            # the north-star quantities: pure relative comparison, no floor
+            scale = np.abs(b)
+        else:
+            # derived values far below the row's scale are differences of O(1) sums: compare them on that scale
+            scale = np.maximum(np.abs(b), 1e-13 * np.max(np.abs(b), axis=1, keepdims=True))
         if f == 'TOTAL' and tables is not None and tables.neqcplx:
             # total_i = m_i + sum_k nu_ik sec_molal_k (reaction.F90:4095-4124) cancels when nu changes sign (H+):
             # a relative perturbation eps of the terms moves it by eps * (m_i + sum_k |nu_ik| sec_molal_k)

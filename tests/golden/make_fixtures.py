@@ -52,7 +52,90 @@ WORKLOADS = {
                      'regression_tests/default/batch/solute_KD_w_mineral.regression.gold'),
     'kd_wo_mineral': ('regression_tests/default/batch/solute_KD_wo_mineral.in', 'initial',
                       'regression_tests/default/batch/solute_KD_wo_mineral.regression.gold'),
+    # mineral prefactors (reaction_mineral.F90:743-782) on primary species, 9 primaries / 57 complexes / 6 kinetic minerals
+    'mineral_prefactor': ('regression_tests/default/column/mineral_prefactor.in', 'initial_ore', None),
+    # non-isothermal run: 5-term logK fit evaluated per cell (reaction_aux.F90:1336-1408, 1461-1488) + Arrhenius factor
+    'calcite_fit5': ('regression_tests/default/anisothermal/thc_1d.in', 'initial_constraint', None),
+    # BASELINE config 1: 22 primaries / 164 complexes (example_problems/ascem_chemistry, savannah_river.dat)
+    'ascem': ('example_problems/ascem_chemistry/pflotran.in', 'initial', None),
 }
+NON_ISOTHERMAL = {'calcite_fit5'}
+
+
+# Decks the reference does not ship: a reference deck with a documented text patch, so that every coded branch of the path is
+# reached by a fixture (NEWTON activity algorithm, ACTIVITY_WATER, free-site inner Newton, Langmuir / Freundlich
+# isotherms, the optional mineral rate-law parameters).  (base deck, constraint, [(old text, new text), ...])
+_MR_BLOCK_START = '    SURFACE_COMPLEXATION_RXN'
+VARIANTS = {
+    # RActivityCoefficients NEWTON algorithm at every Newton iteration (reaction.F90:3846-3990) + activity of water (:4043-4050)
+    'hanford300a_act_newton': ('regression_tests/default/543/543_hanford_srfcplx_base.in', 'groundwater',
+                               [('ACTIVITY_COEFFICIENTS NEWTON_ITERATION', 'ACTIVITY_COEFFICIENTS NEWTON NEWTON_ITERATION\n  ACTIVITY_WATER')]),
+    # surface complexes with two free sites per complex: srfcplxrxn_stoich_flag, inner Newton on the free-site
+    # concentration (reaction_surf_complex.F90:793-818); database complexes >S2---, >SO2UO2, >SO2UO2CO3-- on site >S(OH)2
+    'hanford300a_stoich': ('regression_tests/default/543/543_hanford_srfcplx_base.in', 'groundwater',
+                           [('      SITE >SOH 152.64d0', '      SITE >S(OH)2 152.64d0'),
+                            ('        >SOUO2OH\n        >SOHUO2CO3\n', '        >S2---\n        >SO2UO2\n        >SO2UO2CO3--\n')]),
+    # RTotalSorbKD Langmuir and Freundlich isotherms (reaction.F90:4220-4301).  The reader resets the type to LINEAR on
+    # every keyword of the block (reaction.F90:535), so the keyword that sets the type has to come last.
+    'kd_langmuir': ('regression_tests/default/batch/solute_KD_w_mineral.in', 'initial',
+                    [('KD_MINERAL_NAME A(s)', 'KD_MINERAL_NAME A(s)\n        LANGMUIR_B 2.5d5')]),
+    'kd_freundlich': ('regression_tests/default/batch/solute_KD_w_mineral.in', 'initial',
+                      [('KD_MINERAL_NAME A(s)', 'KD_MINERAL_NAME A(s)\n        FREUNDLICH_N 0.8d0')]),
+    # RKineticMineral optional rate-law parameters (reaction_mineral.F90:699-870): Temkin constant, mineral scale factor,
+    # affinity power and threshold, rate limiter, Arrhenius activation energy
+    'calcite_rate_laws': ('regression_tests/ascem/batch/calcite-kinetics.in', 'initial',
+                          [('      RATE_CONSTANT 1.d-13 mol/cm^2-sec\n',
+                            '      RATE_CONSTANT 1.d-13 mol/cm^2-sec\n      ACTIVATION_ENERGY 40.d0\n      AFFINITY_THRESHOLD 1.d-3\n'
+                            '      AFFINITY_POWER 1.5d0\n      TEMKIN_CONSTANT 2.d0\n      MINERAL_SCALE_FACTOR 1.2d0\n      RATE_LIMITER 1.d-9\n')]),
+}
+
+for _v in VARIANTS:
+    WORKLOADS[_v] = (None, VARIANTS[_v][1], None)
+
+
+def variant_deck(name):
+    base, constraint, patches = VARIANTS[name]
+    src = os.path.join(REF, base)
+    text = open(src).read()
+    for old, new in patches:
+        assert text.count(old) >= 1, (name, old)
+        text = text.replace(old, new)
+    # the variant lives in a scratch directory: make the database path absolute
+    import re
+    m = re.search(r'^\s*DATABASE\s+(\S+)', text, re.M)
+    dbase = os.path.normpath(os.path.join(os.path.dirname(src), m.group(1)))
+    text = text.replace(m.group(0), '  DATABASE ' + dbase)
+    out = os.path.join('/tmp', 'rxn_b200_variant_' + name + '.in')
+    with open(out, 'w') as f:
+        f.write(text)
+    return out, constraint, 'variant of %s: %s' % (base, '; '.join('%r -> %r' % (o.strip(), n.strip()) for o, n in patches))
+
+
+def ascem_kat(out_path, constraint):
+    """Speciation of `constraint` as the reference printed it (ReactionPrintConstraint, 5 significant figures):
+    example_problems/ascem_chemistry/pflotran.out:5811-5870 - iteration count, free / total molality of every primary
+    species, molality of the listed complexes."""
+    import re
+    lines = open(out_path).read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if l.strip() == 'Constraint: ' + constraint)
+    kat = {'iterations': None, 'primary': {}, 'complex': {}, 'source': 'example_problems/ascem_chemistry/pflotran.out:%d' % (i0 + 1)}
+    mode = None
+    for l in lines[i0:i0 + 400]:
+        m = re.match(r'\s*iterations:\s+(\d+)', l)
+        if m:
+            kat['iterations'] = int(m.group(1))
+        if l.strip().startswith('species') and 'molal' in l:
+            mode = 'primary'; continue
+        if l.strip().startswith('complex') and 'molality' in l and 'logK' in l:
+            mode = 'complex'; continue
+        if l.strip().startswith('primary species:'):
+            break
+        f = l.split()
+        if mode == 'primary' and len(f) >= 4 and re.match(r'^-?\d\.\d+E[+-]\d+$', f[1]):
+            kat['primary'][f[0]] = [float(f[1]), float(f[2])]
+        elif mode == 'complex' and len(f) >= 4 and re.match(r'^-?\d\.\d+E[+-]\d+$', f[1]):
+            kat['complex'][f[0]] = float(f[1])
+    return kat
 
 
 def time_block(path):
@@ -80,8 +163,11 @@ def main():
     for name, (deck, constraint, gold) in WORKLOADS.items():
         if only and name not in only:
             continue
-        path = os.path.join(REF, deck)
-        d, t, orc, st, xx, nit, cst = kat.initial_cell(path, constraint=constraint)
+        if deck is None:
+            path, constraint, deck = variant_deck(name)
+        else:
+            path = os.path.join(REF, deck)
+        d, t, orc, st, xx, nit, cst = kat.initial_cell(path, constraint=constraint, isothermal=name not in NON_ISOTHERMAL)
         base = {f: [repr(float(x)) for x in st[f][:, 0]] for f in abi.FIELDS
                 if f not in ('DTOTAL', 'DTOTAL_SORB_EQ')}
         from pflotran_b200.chem.setup import constraint_arrays, mineral_arrays
@@ -93,8 +179,10 @@ def main():
         out = {
             'constraint_arrays': cons,
             'name': name, 'deck': deck, 'constraint': constraint, 'equilibrate_iterations': int(nit),
-            'porosity': d.porosity, 'tables': t.to_dict(), 'base': base, 'time': time_block(path),
+            'porosity': d.porosity, 'rock_density': d.rock_density, 'tables': t.to_dict(), 'base': base, 'time': time_block(path),
         }
+        if name == 'ascem':
+            out['kat'] = ascem_kat(os.path.join(REF, 'example_problems/ascem_chemistry/pflotran.out'), constraint)
         if gold:
             g = kat.read_gold(os.path.join(REF, gold))
             out['gold_file'] = gold

@@ -42,32 +42,32 @@ def read_gold(path):
     return out
 
 
-def fill_scalars(st, t, porosity, volume=1.0):
+def fill_scalars(st, t, porosity, volume=1.0, rock_density=None):
     st['DEN_KG'][:] = t.reference_water_density
     st['SAT'][:] = 1.0
     st['TEMP'][:] = t.reference_temperature
     st['PRES'][:] = t.reference_pressure
     st['VOLUME'][:] = volume
     st['POROSITY'][:] = porosity
-    st['SOIL_PARTICLE_DENSITY'][:] = -999.0
+    st['SOIL_PARTICLE_DENSITY'][:] = -999.0 if rock_density is None else rock_density   # UNINITIALIZED_DOUBLE unless ROCK_DENSITY
 
 
-def initial_cell(deck_path, constraint='initial', porosity=None, volume=1.0):
+def initial_cell(deck_path, constraint='initial', porosity=None, volume=1.0, isothermal=True, database_path=None):
     deck = read_deck(deck_path)
-    t = build_tables(deck)
+    t = build_tables(deck, database_path=database_path, isothermal=isothermal)
     orc = Oracle(t)
     c = deck.constraints[constraint]
     ctype, conc, cid, guess = constraint_arrays(t, c)
     vf, area = mineral_arrays(t, c)
     # 1. coupler auxvar
     cst = abi.HostState(t, 1)
-    fill_scalars(cst, t, 0.25, volume)
+    fill_scalars(cst, t, 0.25, volume, deck.rock_density)
     cst['MNRL_VOLFRAC'][:, 0] = vf
     cst['MNRL_AREA'][:, 0] = area
     basis_molarity, nit = orc.equilibrate(cst, 0, ctype, conc, cid, guess, use_prev=False)
     # 2. the grid cell
     st = abi.HostState(t, 1)
-    fill_scalars(st, t, deck.porosity if porosity is None else porosity, volume)
+    fill_scalars(st, t, deck.porosity if porosity is None else porosity, volume, deck.rock_density)
     st['MNRL_VOLFRAC'][:, 0] = vf
     st['MNRL_AREA'][:, 0] = area
     if t.nkinmrsrfcplxrxn > 0:
@@ -114,12 +114,12 @@ def initial_cell_from_fixture(w, porosity=None, volume=1.0, backend=None):
     orc = backend or OracleBackend(t)
     ctype, conc, cid, guess, vf, area = fixture_constraint(w)
     cst = abi.HostState(t, 1)
-    fill_scalars(cst, t, 0.25, volume)
+    fill_scalars(cst, t, 0.25, volume, w.meta.get('rock_density'))
     cst['MNRL_VOLFRAC'][:, 0] = vf
     cst['MNRL_AREA'][:, 0] = area
     basis_molarity, nit = orc.equilibrate(cst, ctype, conc, cid, guess)
     st = abi.HostState(t, 1)
-    fill_scalars(st, t, w.meta['porosity'] if porosity is None else porosity, volume)
+    fill_scalars(st, t, w.meta['porosity'] if porosity is None else porosity, volume, w.meta.get('rock_density'))
     st['MNRL_VOLFRAC'][:, 0] = vf
     st['MNRL_AREA'][:, 0] = area
     if t.nkinmrsrfcplxrxn > 0:
@@ -155,3 +155,24 @@ def outputs(t, st, cell=0):
     for i, n in enumerate(t.srfcplxrxn_site_names):
         o['Free ' + n] = st['FREE_SITE_CONC'][i, cell]
     return o
+
+
+def check_speciation_kat(w, t, cst, nit, rtol=6.0e-5):
+    """Constraint speciation as the reference printed it (fixture key `kat`, from the deck's own pflotran.out: iteration
+    count, free and total molality of every primary species, molality of every listed complex; 5 significant figures,
+    hence rtol 6e-5).  cst: the equilibrated constraint auxvar.  Returns the number of values checked."""
+    k = w.meta['kat']
+    assert nit == k['iterations'], (nit, k['iterations'])
+    den = cst['DEN_KG'][0, 0]
+    checked = 0
+    for i, n in enumerate(t.primary_species_names):
+        free, tot = k['primary'][n]
+        assert abs(cst['PRI_MOLAL'][i, 0] - free) <= rtol * abs(free), (n, cst['PRI_MOLAL'][i, 0], free)
+        assert abs(cst['TOTAL'][i, 0] / den * 1000.0 - tot) <= rtol * abs(tot), (n, cst['TOTAL'][i, 0] / den * 1000.0, tot)
+        checked += 2
+    names = list(t.secondary_species_names)
+    for n, v in k['complex'].items():
+        j = names.index(n)
+        assert abs(cst['SEC_MOLAL'][j, 0] - v) <= rtol * abs(v), (n, cst['SEC_MOLAL'][j, 0], v)
+        checked += 1
+    return checked

@@ -12,6 +12,13 @@ from common import assert_state_close, workload_cells, RTOL, rel_err, total_magn
 
 WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation',
              'calcite_kinetics', 'kd_wo_mineral']
+# fixtures that reach the branches no reference batch deck exercises (tests/golden/make_fixtures.py: VARIANTS and the
+# prefactor / non-isothermal / 22-primary decks): NEWTON activity algorithm + activity of water, free-site inner Newton,
+# Langmuir / Freundlich isotherms, Temkin / scale factor / affinity power / threshold / rate limiter / Arrhenius, mineral
+# prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes)
+BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem']
+WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
+GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 
 
 @pytest.mark.parametrize('name', WORKLOADS)
@@ -136,7 +143,7 @@ def test_resident_lane_rejects_what_it_does_not_cover():
             Emulator(w.tables).react_lane(st, cells['tran_xx'].copy(), 3600.0)
 
 
-@pytest.mark.parametrize('name', ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'])
+@pytest.mark.parametrize('name', GI_WORKLOADS)
 def test_global_implicit_entry_points(name):
     w, cells = workload_cells(name, 300)
     st_o = synth.host_state(w, cells)
@@ -261,6 +268,14 @@ def test_equilibrate_constraint_device_code_hits_reference_gold(name):
         g = vals['1']
         assert abs(out[var] - g) <= 1.0e-12 * max(1.0, abs(g)), '%s %s: %.14e gold %.14e' % (name, var, out[var], g)
     assert_state_close(cst, cst_o, what=name + ' constraint cell', tables=w.tables)
+
+
+def test_ascem_speciation_device_code_hits_reference_kat():
+    """cell_equilibrate (N = 24 variant) on the 22 / 164 chemistry: the reference's 179 iterations and printed speciation."""
+    import kat
+    w = synth.Workload('ascem')
+    t, be, st, xx, nit, cst = kat.initial_cell_from_fixture(w, backend=_EmuBackend(w.tables))
+    assert kat.check_speciation_kat(w, t, cst, nit) == 2 * 22 + 157
 
 
 class _EmuGI:

@@ -12,6 +12,13 @@ pytestmark = pytest.mark.gpu
 
 WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation',
              'calcite_kinetics', 'kd_wo_mineral']
+# fixtures that reach the branches no reference batch deck exercises (tests/golden/make_fixtures.py: VARIANTS and the
+# prefactor / non-isothermal / 22-primary decks): NEWTON activity algorithm + activity of water, free-site inner Newton,
+# Langmuir / Freundlich isotherms, Temkin / scale factor / affinity power / threshold / rate limiter / Arrhenius, mineral
+# prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes)
+BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem']
+WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
+GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 
 
 def _gpu_state(w, st):
@@ -152,7 +159,7 @@ def test_react_iteration_cap_takes_the_closing_pass(kernel, monkeypatch):
     assert rel_err(xg[capped], xo[capped]).max() <= 1.0e-3
 
 
-@pytest.mark.parametrize('name', ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'])
+@pytest.mark.parametrize('name', GI_WORKLOADS)
 def test_global_implicit_entry_points(name):
     n = 3000
     w, cells = workload_cells(name, n)
@@ -318,6 +325,15 @@ def test_equilibrate_constraint_gpu_hits_reference_gold(name):
         assert abs(out[var] - g) <= RTOL * max(1.0, abs(g)), '%s %s: %.14e gold %.14e' % (name, var, out[var], g)
         checked += 1
     assert checked >= 4
+
+
+def test_ascem_speciation_gpu_hits_reference_kat():
+    """rxn_equilibrate_constraint_batch on BASELINE config 1 (22 primaries / 164 complexes): the reference's own printed
+    speciation (example_problems/ascem_chemistry/pflotran.out:5811-5870), `iterations: 179` included."""
+    import kat
+    w = synth.Workload('ascem')
+    t, be, st, xx, nit, cst = kat.initial_cell_from_fixture(w, backend=_GpuBackend(w.tables))
+    assert kat.check_speciation_kat(w, t, cst, nit) == 2 * 22 + 157
 
 
 @pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral'])

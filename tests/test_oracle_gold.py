@@ -52,6 +52,16 @@ def test_gold_time_stepped(name):
     assert gi_driver.check_time_stepped_gold(w, gi_driver.OracleGI(t, st), t, xx) >= 1
 
 
+def test_ascem_22_primaries_164_complexes_kat():
+    """BASELINE config 1: the 22-primary / 164-complex chemistry of example_problems/ascem_chemistry equilibrated by the
+    oracle reproduces the reference's own printed speciation (pflotran.out:5811-5870): `iterations: 179` exactly and all
+    201 printed molalities to the 5 figures printed."""
+    w = synth.Workload('ascem')
+    t, orc, st, xx, nit, cst = kat.initial_cell_from_fixture(w)
+    assert (t.naqcomp, t.neqcplx) == (22, 164)
+    assert kat.check_speciation_kat(w, t, cst, nit) == 2 * 22 + 157
+
+
 def test_gold_values_spot():
     """The three numbers SURVEY.md 8c quotes explicitly."""
     out = _check('carbonate_dh')
