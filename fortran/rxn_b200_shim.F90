@@ -33,7 +33,8 @@ module Rxn_B200_module
     RXN_F_EQIONX_REF_CATION_SORBED_CONC = 10, RXN_F_EQIONX_CONC = 11, RXN_F_MNRL_VOLFRAC = 12, &
     RXN_F_MNRL_AREA = 13, RXN_F_MNRL_RATE = 14, RXN_F_DEN_KG = 15, RXN_F_SAT = 16, RXN_F_TEMP = 17, &
     RXN_F_PRES = 18, RXN_F_VOLUME = 19, RXN_F_POROSITY = 20, RXN_F_SOIL_PARTICLE_DENSITY = 21, &
-    RXN_F_DTOTAL = 22, RXN_F_DTOTAL_SORB_EQ = 23
+    RXN_F_DTOTAL = 22, RXN_F_DTOTAL_SORB_EQ = 23, RXN_F_KINSRFCPLX_CONC = 24, RXN_F_KINSRFCPLX_CONC_KP1 = 25, &
+    RXN_F_KINSRFCPLX_FREE_SITE_CONC = 26
 
   ! struct RxnSpecList
   type, bind(C), public :: rxn_spec_list_type
@@ -127,6 +128,26 @@ module Rxn_B200_module
     integer(c_int32_t) :: nactive_gas, nimmobile, ncoll, ngeneral_rxn, nradiodecay_rxn, nmicrobial_rxn, &
                           nimmobile_decay_rxn, has_sandbox, has_clm, has_solid_solution, co2_flow_mode, &
                           numerical_derivatives
+    ! general reactions (reaction%general*), radioactive decay (reaction%radiodecay*), kinetic surface complexation
+    integer(c_int32_t) :: general_ld
+    integer(c_int32_t) :: radiodecay_ld
+    type(c_ptr) :: generalspecid
+    type(c_ptr) :: generalstoich
+    type(c_ptr) :: generalforwardspecid
+    type(c_ptr) :: generalforwardstoich
+    type(c_ptr) :: generalbackwardspecid
+    type(c_ptr) :: generalbackwardstoich
+    type(c_ptr) :: general_kf
+    type(c_ptr) :: general_kr
+    type(c_ptr) :: radiodecayspecid
+    type(c_ptr) :: radiodecaystoich
+    type(c_ptr) :: radiodecayforwardspecid
+    type(c_ptr) :: radiodecay_kf
+    type(c_ptr) :: kinsrfcplxrxn_to_srfcplxrxn
+    type(c_ptr) :: kinsrfcplx_forward_rate
+    type(c_ptr) :: kinsrfcplx_backward_rate
+    integer(c_int32_t) :: kinsrfcplx_ld
+    integer(c_int32_t) :: reserved2
   end type rxn_tables_desc_type
 
   public :: rxn_tables_create, rxn_tables_destroy, rxn_state_create, rxn_state_destroy, &

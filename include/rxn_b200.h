@@ -157,7 +157,7 @@ typedef struct RxnTablesDesc {
   const double *kinmr_rate;                   /* (maxrate, nkinmr) */
   const double *kinmr_frac;                   /* (maxrate, nkinmr) */
   int32_t kinmr_ld;                           /* = maxrate */
-  int32_t nkinsrfcplxrxn;                     /* must be 0 (RKineticSurfCplx: next) */
+  int32_t nkinsrfcplxrxn;                     /* 0 or 1: tables at the end of this struct */
 
   /* ion exchange: eqionx_rxn_cationid(0:mc,n), eqionx_rxn_k(mc,n) */
   int32_t neqionxrxn;
@@ -179,11 +179,37 @@ typedef struct RxnTablesDesc {
   const double *eqkdfreundlichn;
 
   /* reaction types outside the path: all must be 0, else RXN_ERR_UNSUPPORTED
-   * (active gas/RTotalGas, immobile, colloids, general, radioactive decay, microbial,
-   * immobile decay, sandbox, CLM, solid solution, CO2 flow modes -> RTotalCO2). */
+   * (active gas/RTotalGas, immobile, colloids, microbial, immobile decay, sandbox, CLM, solid solution,
+   * CO2 flow modes -> RTotalCO2).  ngeneral_rxn and nradiodecay_rxn are COUNTS of supported reactions (tables below). */
   int32_t nactive_gas, nimmobile, ncoll, ngeneral_rxn, nradiodecay_rxn, nmicrobial_rxn,
           nimmobile_decay_rxn, has_sandbox, has_clm, has_solid_solution, co2_flow_mode,
           numerical_derivatives;
+
+  /* general forward/backward-rate reactions, RGeneral (reaction.F90:4694-4831; tables reaction_database.F90:3011-3135) */
+  int32_t general_ld;                         /* = m: generalspecid(0:m,n), generalstoich(m,n); forward/backward alike */
+  int32_t radiodecay_ld;                      /* = m: radiodecayspecid(0:m,n), radiodecaystoich(m,n) */
+  const int32_t *generalspecid;
+  const double *generalstoich;
+  const int32_t *generalforwardspecid;
+  const double *generalforwardstoich;
+  const int32_t *generalbackwardspecid;
+  const double *generalbackwardstoich;
+  const double *general_kf;                   /* [ngeneral_rxn] */
+  const double *general_kr;
+  /* radioactive decay with one reactant, RRadioactiveDecay (reaction.F90:4607-4690; tables reaction_database.F90:2915-3006) */
+  const int32_t *radiodecayspecid;
+  const double *radiodecaystoich;
+  const int32_t *radiodecayforwardspecid;     /* [nradiodecay_rxn] */
+  const double *radiodecay_kf;                /* [nradiodecay_rxn] 1/s */
+  /* kinetic surface complexation, RKineticSurfCplx (reaction_surf_complex.F90:938-1137): nkinsrfcplxrxn (above) must be 0 or 1
+   * - the reference allocates the per-cell concentrations for one kinetic reaction (reactive_transport_aux.F90:284-290) -
+   * and that reaction must be surface complexation reaction 1 on mineral surface 1 (the reference indexes the site arrays
+   * with the mineral id and the rate tables with the global complex id). */
+  const int32_t *kinsrfcplxrxn_to_srfcplxrxn; /* [nkinsrfcplxrxn] */
+  const double *kinsrfcplx_forward_rate;      /* (kinsrfcplx_ld, nkinsrfcplxrxn) */
+  const double *kinsrfcplx_backward_rate;
+  int32_t kinsrfcplx_ld;
+  int32_t reserved2;
 } RxnTablesDesc;
 
 /* Per-cell state fields (reactive_transport_auxvar_type, reference
@@ -210,6 +236,9 @@ typedef enum RxnField {
   RXN_F_VOLUME, RXN_F_POROSITY, RXN_F_SOIL_PARTICLE_DENSITY,
   RXN_F_DTOTAL,               /* naqcomp^2, column-major: row = j*naq + i (GI entry points only) */
   RXN_F_DTOTAL_SORB_EQ,       /* naqcomp^2, column-major                                         */
+  RXN_F_KINSRFCPLX_CONC,      /* nkinsrfcplx (complexes of the kinetic surface complexation reaction): S^k     */
+  RXN_F_KINSRFCPLX_CONC_KP1,  /* nkinsrfcplx: S^{k+1}, becomes S^k in rxn_update_kinetic_state_batch (reaction.F90:5411-5419) */
+  RXN_F_KINSRFCPLX_FREE_SITE_CONC, /* nkinsrfcplxrxn */
   RXN_F_COUNT
 } RxnField;
 

@@ -82,6 +82,13 @@ struct Tables {
   int nionx = 0, ionx_ld = 0; std::vector<std::vector<int>> ionx_cat; std::vector<std::vector<double>> ionx_k;
   std::vector<double> ionx_CEC; std::vector<int> ionx_Zflag, ionx_to_surf;
   int nkd = 0; std::vector<int> kd_spec, kd_type, kd_mnrl; std::vector<double> kd_coef, kd_b, kd_n;
+  // general / radioactive decay reactions: species lists (0-based ids) as the reference's (0:m,n) tables
+  int ngen = 0, ndecay = 0;
+  std::vector<std::vector<int>> gen_id, genf_id, genb_id, dec_id; std::vector<std::vector<double>> gen_st, genf_st, genb_st, dec_st;
+  std::vector<double> gen_kf, gen_kr, dec_kf; std::vector<int> dec_fwd;
+  // kinetic surface complexation (one reaction): its srfcplxrxn (0-based), rates per complex
+  int nkinrxn = 0; std::vector<int> kin_rxn; std::vector<double> kin_kf, kin_kb; int kin_ld = 0;
+  int nkinsrf() const { return nkinrxn ? (int)rxn_cplx[kin_rxn[0]].size() : 0; }
   int neqsorb() const { return nionx + nkd + (int)eq_rxn.size(); }
   int nkinmr() const { return (int)mr_rxn.size(); }
 };
@@ -144,6 +151,32 @@ Tables *load_tables(const RxnTablesDesc *d) {
   t->nkd = d->neqkdrxn;
   cp(t->kd_spec, d->eqkdspecid, t->nkd); cp(t->kd_type, d->eqkdtype, t->nkd); cp(t->kd_mnrl, d->eqkdmineral, t->nkd);
   cp(t->kd_coef, d->eqkddistcoef, t->nkd); cp(t->kd_b, d->eqkdlangmuirb, t->nkd); cp(t->kd_n, d->eqkdfreundlichn, t->nkd);
+  auto lists = [](const int32_t *ids, const double *st, int ld, int nr, std::vector<std::vector<int>> &oid, std::vector<std::vector<double>> &ost) {
+    oid.assign(nr, {}); ost.assign(nr, {});
+    for (int r = 0; r < nr; ++r) {
+      int n = ids[(size_t)r * (ld + 1)];
+      for (int k = 1; k <= n; ++k) { oid[r].push_back(ids[(size_t)r * (ld + 1) + k] - 1); ost[r].push_back(st[(size_t)r * ld + k - 1]); }
+    }
+  };
+  t->ngen = d->ngeneral_rxn; t->ndecay = d->nradiodecay_rxn;
+  if (t->ngen > 0) {
+    lists(d->generalspecid, d->generalstoich, d->general_ld, t->ngen, t->gen_id, t->gen_st);
+    lists(d->generalforwardspecid, d->generalforwardstoich, d->general_ld, t->ngen, t->genf_id, t->genf_st);
+    lists(d->generalbackwardspecid, d->generalbackwardstoich, d->general_ld, t->ngen, t->genb_id, t->genb_st);
+    cp(t->gen_kf, d->general_kf, t->ngen); cp(t->gen_kr, d->general_kr, t->ngen);
+  }
+  if (t->ndecay > 0) {
+    lists(d->radiodecayspecid, d->radiodecaystoich, d->radiodecay_ld, t->ndecay, t->dec_id, t->dec_st);
+    cp(t->dec_kf, d->radiodecay_kf, t->ndecay);
+    for (int r = 0; r < t->ndecay; ++r) t->dec_fwd.push_back(d->radiodecayforwardspecid[r] - 1);
+  }
+  t->nkinrxn = d->nkinsrfcplxrxn;
+  if (t->nkinrxn > 0) {
+    for (int i = 0; i < t->nkinrxn; ++i) t->kin_rxn.push_back(d->kinsrfcplxrxn_to_srfcplxrxn[i] - 1);
+    t->kin_ld = d->kinsrfcplx_ld;
+    cp(t->kin_kf, d->kinsrfcplx_forward_rate, (size_t)t->kin_ld * t->nkinrxn);
+    cp(t->kin_kb, d->kinsrfcplx_backward_rate, (size_t)t->kin_ld * t->nkinrxn);
+  }
   return t;
 }
 
@@ -156,6 +189,7 @@ struct AuxVar {
   std::vector<double> kinmr_total_sorb;  // [rxn][rate 0..maxrate][naq]
   std::vector<double> ionx_ref_sorbed, ionx_conc;
   std::vector<double> mnrl_volfrac, mnrl_area, mnrl_rate;
+  std::vector<double> kinsrfcplx_conc, kinsrfcplx_conc_kp1, kinsrfcplx_free_site_conc;   // (nkinsrfcplx,1), (nkinsrfcplx,1), (nkinsrfcplxrxn)
   double den_kg = 0, sat = 0, temp = 0, pres = 0, volume = 0, porosity = 0, soil_density = 0;
   int flags = 0;
 };
@@ -169,6 +203,7 @@ void init_auxvar(const Tables &t, AuxVar &a) {
   a.kinmr_total_sorb.assign((size_t)t.nkinmr() * (t.mr_ld + 1) * n, 0);
   a.ionx_ref_sorbed.assign(t.nionx, 1e-9); a.ionx_conc.assign((size_t)t.nionx * std::max(t.ionx_ld, 1), 0);
   a.mnrl_volfrac.assign(t.kin.n, 0); a.mnrl_area.assign(t.kin.n, 0); a.mnrl_rate.assign(t.kin.n, 0);
+  a.kinsrfcplx_conc.assign(t.nkinsrf(), 0); a.kinsrfcplx_conc_kp1.assign(t.nkinsrf(), 0); a.kinsrfcplx_free_site_conc.assign(t.nkinrxn, 0);
 }
 
 // ---------------------------------------------------------------- utility.F90:393-476
@@ -866,10 +901,161 @@ void RMultiRateSorption(const Tables &t, AuxVar &a, double tran_dt, double *Res,
   }
 }
 
+// ---------------------------------------------------------------- reaction_surf_complex.F90:938-1137
+// One kinetic reaction on mineral surface 1, = surface complexation reaction 1 (the only configuration in which the
+// reference's indices are in bounds, rxn_pack.h): isite = ikinrxn = 1, global complex id = position in the reaction.
+void RKineticSurfCplx(const Tables &t, AuxVar &a, double dt, double *Res, double *Jac, bool compute_derivative) {
+  const int n = t.ncomp, naq = t.naq;
+  std::vector<double> ln_conc(naq), ln_act(naq);
+  for (int i = 0; i < naq; ++i) { ln_conc[i] = std::log(a.pri_molal[i]); ln_act[i] = ln_conc[i] + std::log(a.pri_act_coef[i]); }
+  const int irxn = t.kin_rxn[0];
+  const std::vector<int> &cplx = t.rxn_cplx[irxn];
+  const int ncplx = (int)cplx.size();
+  std::vector<double> lnQ(t.srf.n, 0.0), Q(t.srf.n, 0.0);
+  for (int k = 0; k < ncplx; ++k) {
+    const int icplx = cplx[k];
+    if (t.srf.h2oid[icplx] > 0) lnQ[icplx] = lnQ[icplx] + t.srf.h2ost[icplx] * a.ln_act_h2o;
+    for (size_t i = 0; i < t.srf.id[icplx].size(); ++i) lnQ[icplx] = lnQ[icplx] + t.srf.st[icplx][i] * ln_act[t.srf.id[icplx][i]];
+    Q[icplx] = std::exp(lnQ[icplx]);
+  }
+  const double *kf = t.kin_kf.data(), *kb = t.kin_kb.data();       // (icplx, ikinrxn = 1)
+  double numerator_sum = 0.0;
+  for (int k = 0; k < ncplx; ++k) {
+    const int icplx = cplx[k];
+    numerator_sum = numerator_sum + a.kinsrfcplx_conc[icplx] / (1.0 + kb[icplx] * dt);
+  }
+  numerator_sum = t.rxn_site_density[0] - numerator_sum;           // srfcplxrxn_site_density(isite), isite = 1
+  double denominator_sum = 1.0;
+  for (int k = 0; k < ncplx; ++k) {
+    const int icplx = cplx[k];
+    denominator_sum = denominator_sum + (kf[icplx] * dt) / (1.0 + kb[icplx] * dt) * Q[icplx];
+  }
+  std::vector<double> conc_kp1(t.srf.n, 0.0);
+  for (int k = 0; k < ncplx; ++k) {
+    const int icplx = cplx[k];
+    const double conc_k = a.kinsrfcplx_conc[icplx];
+    const double denominator = 1.0 + kb[icplx] * dt;
+    conc_kp1[icplx] = (conc_k + kf[icplx] * dt * numerator_sum / denominator_sum * Q[icplx]) / denominator;
+    a.kinsrfcplx_conc_kp1[icplx] = conc_kp1[icplx];
+  }
+  a.kinsrfcplx_free_site_conc[0] = numerator_sum / denominator_sum;
+  for (int k = 0; k < ncplx; ++k) {
+    const int icplx = cplx[k];
+    for (size_t i = 0; i < t.srf.id[icplx].size(); ++i) {
+      const int icomp = t.srf.id[icplx][i];
+      Res[icomp] = Res[icomp] + t.srf.st[icplx][i] * (conc_kp1[icplx] - a.kinsrfcplx_conc[icplx]) / dt * a.volume;
+    }
+  }
+  if (compute_derivative) {
+    std::vector<double> fac_sum(naq, 0.0);
+    for (int k = 0; k < ncplx; ++k) {
+      const int icplx = cplx[k];
+      const double denominator = 1.0 + kb[icplx] * dt;
+      const double fac = kf[icplx] / denominator;
+      for (size_t j = 0; j < t.srf.id[icplx].size(); ++j)
+        fac_sum[t.srf.id[icplx][j]] = fac_sum[t.srf.id[icplx][j]] + t.srf.st[icplx][j] * fac * Q[icplx];
+    }
+    for (int k = 0; k < ncplx; ++k) {
+      const int icplx = cplx[k];
+      const double denominator = 1.0 + kb[icplx] * dt;
+      const double fac = kf[icplx] / denominator;
+      for (size_t j = 0; j < t.srf.id[icplx].size(); ++j) {
+        const int jcomp = t.srf.id[icplx][j];
+        for (size_t l = 0; l < t.srf.id[icplx].size(); ++l) {
+          const int lcomp = t.srf.id[icplx][l];
+          Jac[jcomp + (size_t)lcomp * n] = Jac[jcomp + (size_t)lcomp * n] +
+              (t.srf.st[icplx][j] * fac * numerator_sum * Q[icplx] * (t.srf.st[icplx][l] - dt * fac_sum[lcomp] / denominator_sum)) /
+                  denominator_sum * std::exp(-ln_conc[lcomp]) * a.volume;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- reaction.F90:4607-4690
+void RRadioactiveDecay(const Tables &t, AuxVar &a, double *Res, double *Jac, bool compute_derivative) {
+  const int n = t.ncomp, naq = t.naq;
+  const double L_water = a.porosity * a.sat * a.volume * 1.0e3;
+  for (int irxn = 0; irxn < t.ndecay; ++irxn) {
+    int icomp = t.dec_fwd[irxn];
+    double sum = a.total[icomp] * L_water;
+    sum = sum + a.total_sorb_eq[icomp] * a.volume;              // total_sorb_eq is always associated here (zero without sorption)
+    const double rate = sum * t.dec_kf[irxn];
+    const int ncomp = (int)t.dec_id[irxn].size();
+    for (int i = 0; i < ncomp; ++i) {
+      icomp = t.dec_id[irxn][i];
+      Res[icomp] = Res[icomp] - t.dec_st[irxn][i] * rate;
+    }
+    if (!compute_derivative) continue;
+    const double tempreal = -1.0 * t.dec_kf[irxn];
+    const int jcomp = t.dec_fwd[irxn];
+    for (int i = 0; i < ncomp; ++i) {
+      icomp = t.dec_id[irxn][i];
+      for (int j = 0; j < naq; ++j)
+        Jac[icomp + (size_t)j * n] = Jac[icomp + (size_t)j * n] +
+            tempreal * t.dec_st[irxn][i] * (a.dtotal[jcomp + (size_t)j * naq] * L_water + a.dtotal_sorb_eq[jcomp + (size_t)j * naq] * a.volume);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- reaction.F90:4694-4831
+void RGeneral(const Tables &t, AuxVar &a, double *Res, double *Jac, bool compute_derivative) {
+  const int n = t.ncomp, naq = t.naq;
+  std::vector<double> ln_conc(naq), ln_act(naq);
+  for (int i = 0; i < naq; ++i) { ln_conc[i] = std::log(a.pri_molal[i]); ln_act[i] = ln_conc[i] + std::log(a.pri_act_coef[i]); }
+  for (int irxn = 0; irxn < t.ngen; ++irxn) {
+    const double kf = t.gen_kf[irxn], kr = t.gen_kr[irxn];
+    double Qkf, lnQkf = 0.0, Qkr, lnQkr = 0.0;
+    if (kf > 0.0) {
+      lnQkf = std::log(kf);
+      for (size_t i = 0; i < t.genf_id[irxn].size(); ++i) lnQkf = lnQkf + t.genf_st[irxn][i] * ln_act[t.genf_id[irxn][i]];
+      Qkf = std::exp(lnQkf);
+    } else {
+      Qkf = 0.0;
+    }
+    if (kr > 0.0) {
+      lnQkr = std::log(kr);
+      for (size_t i = 0; i < t.genb_id[irxn].size(); ++i) lnQkr = lnQkr + t.genb_st[irxn][i] * ln_act[t.genb_id[irxn][i]];
+      Qkr = std::exp(lnQkr);
+    } else {
+      Qkr = 0.0;
+    }
+    const double por_den_sat_vol = a.porosity * a.den_kg * a.sat * a.volume;
+    for (size_t i = 0; i < t.gen_id[irxn].size(); ++i) {
+      const int icomp = t.gen_id[irxn][i];
+      Res[icomp] = Res[icomp] - t.gen_st[irxn][i] * (Qkf - Qkr) * por_den_sat_vol;
+    }
+    if (!compute_derivative) continue;
+    if (kf > 0.0) {
+      for (size_t j = 0; j < t.genf_id[irxn].size(); ++j) {
+        const int jcomp = t.genf_id[irxn][j];
+        const double tempreal = -1.0 * t.genf_st[irxn][j] * std::exp(lnQkf - ln_conc[jcomp]) * por_den_sat_vol;
+        for (size_t i = 0; i < t.gen_id[irxn].size(); ++i) {
+          const int icomp = t.gen_id[irxn][i];
+          Jac[icomp + (size_t)jcomp * n] = Jac[icomp + (size_t)jcomp * n] + t.gen_st[irxn][i] * tempreal;
+        }
+      }
+    }
+    if (kr > 0.0) {
+      for (size_t j = 0; j < t.genb_id[irxn].size(); ++j) {
+        const int jcomp = t.genb_id[irxn][j];
+        const double tempreal = t.genb_st[irxn][j] * std::exp(lnQkr - ln_conc[jcomp]) * por_den_sat_vol;
+        for (size_t i = 0; i < t.gen_id[irxn].size(); ++i) {
+          const int icomp = t.gen_id[irxn][i];
+          Jac[icomp + (size_t)jcomp * n] = Jac[icomp + (size_t)jcomp * n] + t.gen_st[irxn][i] * tempreal;
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- reaction.F90:3515-3584
 void RReaction(const Tables &t, AuxVar &a, double tran_dt, double *Res, double *Jac, bool derivative) {
   if (t.kin.n > 0) RKineticMineral(t, a, Res, Jac, derivative);
   if (t.nkinmr() > 0) RMultiRateSorption(t, a, tran_dt, Res, Jac, derivative);
+  if (t.nkinrxn > 0) RKineticSurfCplx(t, a, tran_dt, Res, Jac, derivative);
+  if (t.ndecay > 0) RRadioactiveDecay(t, a, Res, Jac, derivative);
+  if (t.ngen > 0) RGeneral(t, a, Res, Jac, derivative);
 }
 
 // ---------------------------------------------------------------- reaction.F90:3322-3511
@@ -959,6 +1145,9 @@ void RUpdateKineticState(const Tables &t, AuxVar &a, double tran_dt) {
       const double *S0 = &a.kinmr_total_sorb[ikr * blk];
       for (int i = 0; i < naq; ++i) Sr[i] = (Sr[i] + kdt * frac * S0[i]) / one_plus_kdt;
     }
+  }
+  if (t.nkinrxn > 0) {                                          // :5411-5419
+    for (int icplx : t.rxn_cplx[t.kin_rxn[0]]) a.kinsrfcplx_conc[icplx] = a.kinsrfcplx_conc_kp1[icplx];
   }
 }
 
@@ -1170,6 +1359,8 @@ void gather(const Tables &t, const View &v, int64_t c, AuxVar &a) {
   g1(RXN_F_DEN_KG, a.den_kg); g1(RXN_F_SAT, a.sat); g1(RXN_F_TEMP, a.temp); g1(RXN_F_PRES, a.pres);
   g1(RXN_F_VOLUME, a.volume); g1(RXN_F_POROSITY, a.porosity); g1(RXN_F_SOIL_PARTICLE_DENSITY, a.soil_density);
   g(RXN_F_DTOTAL, a.dtotal); g(RXN_F_DTOTAL_SORB_EQ, a.dtotal_sorb_eq);
+  g(RXN_F_KINSRFCPLX_CONC, a.kinsrfcplx_conc); g(RXN_F_KINSRFCPLX_CONC_KP1, a.kinsrfcplx_conc_kp1);
+  g(RXN_F_KINSRFCPLX_FREE_SITE_CONC, a.kinsrfcplx_free_site_conc);
   (void)naq;
   a.flags = 0;
 }
@@ -1187,6 +1378,8 @@ void scatter(const Tables &t, const View &v, int64_t c, const AuxVar &a) {
   if (t.nionx > 0) s(RXN_F_EQIONX_CONC, a.ionx_conc);
   s(RXN_F_MNRL_VOLFRAC, a.mnrl_volfrac); s(RXN_F_MNRL_RATE, a.mnrl_rate);
   s(RXN_F_DTOTAL, a.dtotal); s(RXN_F_DTOTAL_SORB_EQ, a.dtotal_sorb_eq);
+  s(RXN_F_KINSRFCPLX_CONC, a.kinsrfcplx_conc); s(RXN_F_KINSRFCPLX_CONC_KP1, a.kinsrfcplx_conc_kp1);
+  s(RXN_F_KINSRFCPLX_FREE_SITE_CONC, a.kinsrfcplx_free_site_conc);
 }
 
 template <class F> void parallel_cells(int64_t n, int nthreads, F body) {

@@ -29,6 +29,7 @@ FIELDS = [
     'EQIONX_REF_CATION_SORBED_CONC', 'EQIONX_CONC', 'MNRL_VOLFRAC', 'MNRL_AREA', 'MNRL_RATE',
     'DEN_KG', 'SAT', 'TEMP', 'PRES', 'VOLUME', 'POROSITY', 'SOIL_PARTICLE_DENSITY',
     'DTOTAL', 'DTOTAL_SORB_EQ',
+    'KINSRFCPLX_CONC', 'KINSRFCPLX_CONC_KP1', 'KINSRFCPLX_FREE_SITE_CONC',
 ]
 F = {name: i for i, name in enumerate(FIELDS)}
 RXN_F_COUNT = len(FIELDS)
@@ -85,6 +86,16 @@ class RxnTablesDesc(C.Structure):
         ('nimmobile_decay_rxn', C.c_int32), ('has_sandbox', C.c_int32), ('has_clm', C.c_int32),
         ('has_solid_solution', C.c_int32), ('co2_flow_mode', C.c_int32),
         ('numerical_derivatives', C.c_int32),
+        ('general_ld', C.c_int32), ('radiodecay_ld', C.c_int32),
+        ('generalspecid', c_i32p), ('generalstoich', c_f64p),
+        ('generalforwardspecid', c_i32p), ('generalforwardstoich', c_f64p),
+        ('generalbackwardspecid', c_i32p), ('generalbackwardstoich', c_f64p),
+        ('general_kf', c_f64p), ('general_kr', c_f64p),
+        ('radiodecayspecid', c_i32p), ('radiodecaystoich', c_f64p),
+        ('radiodecayforwardspecid', c_i32p), ('radiodecay_kf', c_f64p),
+        ('kinsrfcplxrxn_to_srfcplxrxn', c_i32p), ('kinsrfcplx_forward_rate', c_f64p),
+        ('kinsrfcplx_backward_rate', c_f64p),
+        ('kinsrfcplx_ld', C.c_int32), ('reserved2', C.c_int32),
     ]
 
 
@@ -192,8 +203,24 @@ def make_desc(t) -> RxnTablesDesc:
     d.nactive_gas = int(any('ACTIVE_GAS' in u for u in uns))
     d.nimmobile = int(any('IMMOBILE_SPECIES' in u for u in uns))
     d.ncoll = int(any('COLLOID' in u for u in uns))
-    d.ngeneral_rxn = int(any('GENERAL_REACTION' in u for u in uns))
-    d.nradiodecay_rxn = int(any('RADIOACTIVE' in u for u in uns))
+    # general reactions / radioactive decay / kinetic surface complexation (fixtures older than round 2 have none)
+    d.ngeneral_rxn = int(getattr(t, 'ngeneral_rxn', 0))
+    d.nradiodecay_rxn = int(getattr(t, 'nradiodecay_rxn', 0))
+    if d.ngeneral_rxn:
+        d.general_ld = t.generalstoich.shape[1]
+        d.generalspecid = I(t.generalspecid); d.generalstoich = D(t.generalstoich)
+        d.generalforwardspecid = I(t.generalforwardspecid); d.generalforwardstoich = D(t.generalforwardstoich)
+        d.generalbackwardspecid = I(t.generalbackwardspecid); d.generalbackwardstoich = D(t.generalbackwardstoich)
+        d.general_kf = D(t.general_kf); d.general_kr = D(t.general_kr)
+    if d.nradiodecay_rxn:
+        d.radiodecay_ld = t.radiodecaystoich.shape[1]
+        d.radiodecayspecid = I(t.radiodecayspecid); d.radiodecaystoich = D(t.radiodecaystoich)
+        d.radiodecayforwardspecid = I(t.radiodecayforwardspecid); d.radiodecay_kf = D(t.radiodecay_kf)
+    if t.nkinsrfcplxrxn:
+        d.kinsrfcplx_ld = t.kinsrfcplx_forward_rate.shape[1]
+        d.kinsrfcplxrxn_to_srfcplxrxn = I(t.kinsrfcplxrxn_to_srfcplxrxn)
+        d.kinsrfcplx_forward_rate = D(t.kinsrfcplx_forward_rate)
+        d.kinsrfcplx_backward_rate = D(t.kinsrfcplx_backward_rate)
     d.nmicrobial_rxn = int(any('MICROBIAL' in u for u in uns))
     d.nimmobile_decay_rxn = int(any('IMMOBILE_DECAY' in u for u in uns))
     d.has_sandbox = int(any('SANDBOX' in u for u in uns))
@@ -216,6 +243,8 @@ def field_rows(t) -> Dict[str, int]:
         'MNRL_VOLFRAC': t.nkinmnrl, 'MNRL_AREA': t.nkinmnrl, 'MNRL_RATE': t.nkinmnrl,
         'DEN_KG': 1, 'SAT': 1, 'TEMP': 1, 'PRES': 1, 'VOLUME': 1, 'POROSITY': 1,
         'SOIL_PARTICLE_DENSITY': 1, 'DTOTAL': naq * naq, 'DTOTAL_SORB_EQ': naq * naq,
+        'KINSRFCPLX_CONC': getattr(t, 'nkinsrfcplx', 0), 'KINSRFCPLX_CONC_KP1': getattr(t, 'nkinsrfcplx', 0),
+        'KINSRFCPLX_FREE_SITE_CONC': t.nkinsrfcplxrxn,
     }
 
 

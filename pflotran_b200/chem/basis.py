@@ -547,8 +547,19 @@ def build_tables(deck: dk.Deck, database_path: str = None, isothermal: bool = Tr
     t.kinmr_nrate = np.array([mxr] + [len(rxns[i - 1].rates) for i in mr], dtype=np.int32)
     t.kinmr_rate = starray1([rxns[i - 1].rates for i in mr], mxr)
     t.kinmr_frac = starray1([rxns[i - 1].site_fractions for i in mr], mxr)
-    if kn:
-        t.unsupported.append('KINETIC surface complexation')
+    # kinetic surface complexation (reaction_database.F90:2568-2655): rates stored per (complex position in its reaction,
+    # kinetic reaction); the backward rate is the deck's (the `Uninitialized` test at :2633 looks at the freshly zeroed table,
+    # so the Kb = Kf * Keq branch is never taken)
+    t.nkinsrfcplx = sum(len(rxns[i - 1].complexes) for i in kn)
+    t.kinsrfcplxrxn_to_srfcplxrxn = np.array(kn, dtype=np.int32)
+    mxk = max([len(rxns[i - 1].complexes) for i in kn], default=0)
+    t.kinsrfcplx_forward_rate = np.zeros((len(kn), max(mxk, 1)), dtype=np.float64)
+    t.kinsrfcplx_backward_rate = np.zeros((len(kn), max(mxk, 1)), dtype=np.float64)
+    for ik, i in enumerate(kn):
+        for ic, cname in enumerate(rxns[i - 1].complexes):
+            ck = rxns[i - 1].complex_kinetics.get(cname, {})
+            t.kinsrfcplx_forward_rate[ik, ic] = ck.get('forward', 0.0)
+            t.kinsrfcplx_backward_rate[ik, ic] = ck.get('backward', -999.0)     # UNINITIALIZED_DOUBLE when the deck omits it
 
     # --- ion exchange
     nix = len(chem.ionx_rxns)
@@ -589,6 +600,66 @@ def build_tables(deck: dk.Deck, database_path: str = None, isothermal: bool = Tr
     t.eqkddistcoef = np.array([r.Kd for r in chem.kd_rxns], dtype=np.float64)
     t.eqkdlangmuirb = np.array([r.Langmuir_b for r in chem.kd_rxns], dtype=np.float64)
     t.eqkdfreundlichn = np.array([r.Freundlich_n for r in chem.kd_rxns], dtype=np.float64)
+
+    # --- radioactive decay and general reactions (reaction_database.F90:2915-3135): the REACTION string gives the species in
+    # the order written, reactants negative (database_rxn from DatabaseRxnCreateFromRxnString, reaction_database_aux.F90:59-274)
+    def rxn_from_string(text):
+        names, st = [], []
+        negative, value, right = False, None, False
+        for w in text.split():
+            if w == '+':
+                continue
+            if w == '-':
+                negative = not negative
+                continue
+            if w in ('=', '<=>', '<->'):
+                right = True
+                continue
+            if not w[0].isalpha():
+                value = fnum_py(w)
+                continue
+            if w.upper() == 'H2O':
+                value, negative = None, False
+                continue
+            v = 1.0 if value is None else value
+            if negative:
+                v = -v
+            if not right:
+                v = -v
+            if w not in chem.primary_species:
+                raise RuntimeError('Species %s in reaction "%s" not found among primary species' % (w, text))
+            names.append(w); st.append(v)
+            value, negative = None, False
+        return [chem.primary_species.index(n) + 1 for n in names], st
+
+    def fnum_py(tok):
+        return float(tok.replace('d', 'e').replace('D', 'e'))
+
+    g_ids, g_st, gf_ids, gf_st, gb_ids, gb_st = [], [], [], [], [], []
+    for r in chem.general_rxns:
+        ids, st = rxn_from_string(r.reaction)
+        g_ids.append(ids); g_st.append(st)
+        gf_ids.append([i for i, v in zip(ids, st) if v < 0.0]); gf_st.append([abs(v) for v in st if v < 0.0])
+        gb_ids.append([i for i, v in zip(ids, st) if v > 0.0]); gb_st.append([v for v in st if v > 0.0])
+    t.ngeneral_rxn = len(chem.general_rxns)
+    mg = max([len(x) for x in g_ids], default=0)
+    t.generalspecid = idarray(g_ids, mg + 1); t.generalstoich = starray1(g_st, mg)
+    t.generalforwardspecid = idarray(gf_ids, mg + 1); t.generalforwardstoich = starray1(gf_st, mg)
+    t.generalbackwardspecid = idarray(gb_ids, mg + 1); t.generalbackwardstoich = starray1(gb_st, mg)
+    t.general_kf = np.array([r.forward_rate for r in chem.general_rxns], dtype=np.float64)
+    t.general_kr = np.array([r.backward_rate for r in chem.general_rxns], dtype=np.float64)
+    d_ids, d_st, d_fwd = [], [], []
+    for r in chem.radiodecay_rxns:
+        ids, st = rxn_from_string(r.reaction)
+        if sum(1 for v in st if v < 0.0) > 1:
+            raise RuntimeError('Cannot have more than one reactant in radioactive decay reaction: (%s).' % r.reaction)
+        d_ids.append(ids); d_st.append(st)
+        d_fwd.append(([i for i, v in zip(ids, st) if v < 0.0] or [0])[-1])
+    t.nradiodecay_rxn = len(chem.radiodecay_rxns)
+    md = max([len(x) for x in d_ids], default=0)
+    t.radiodecayspecid = idarray(d_ids, md + 1); t.radiodecaystoich = starray1(d_st, md)
+    t.radiodecayforwardspecid = np.array(d_fwd, dtype=np.int32)
+    t.radiodecay_kf = np.array([r.rate_constant for r in chem.radiodecay_rxns], dtype=np.float64)
     t.eqkdmineral = np.array(
         [kin.index(r.kd_mineral_name) + 1 if len(r.kd_mineral_name) > 1 else 0
          for r in chem.kd_rxns], dtype=np.int32)

@@ -14,6 +14,7 @@ chemistry tables from the reference's own decks:
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -190,6 +191,15 @@ class KDRxn:
 
 
 @dataclass
+class RateRxn:
+    """GENERAL_REACTION (forward / backward rate) or RADIOACTIVE_DECAY_REACTION (rate_constant) block"""
+    reaction: str = ''
+    forward_rate: float = 0.0
+    backward_rate: float = 0.0
+    rate_constant: Optional[float] = None
+
+
+@dataclass
 class Chemistry:
     primary_species: List[str] = field(default_factory=list)
     secondary_species: List[str] = field(default_factory=list)
@@ -201,6 +211,8 @@ class Chemistry:
     srfcplx_rxns: List[SrfCplxRxn] = field(default_factory=list)
     ionx_rxns: List[IonxRxn] = field(default_factory=list)
     kd_rxns: List[KDRxn] = field(default_factory=list)
+    general_rxns: List[RateRxn] = field(default_factory=list)
+    radiodecay_rxns: List[RateRxn] = field(default_factory=list)
     database: str = ''
     use_log_formulation: bool = False
     use_geothermal_hpt: bool = False
@@ -502,7 +514,40 @@ def _read_chemistry(rd: LineReader) -> Chemistry:
             chem.max_residual_tolerance = fnum(toks[1])
         elif kw == 'OUTPUT':
             rd.skip_block()
-        elif kw in ('GENERAL_REACTION', 'RADIOACTIVE_DECAY_REACTION', 'MICROBIAL_REACTION',
+        elif kw == 'GENERAL_REACTION':                      # reaction.F90:315-358
+            r = RateRxn()
+            for t in rd.block():
+                k = t[0].upper()
+                if k == 'REACTION':
+                    r.reaction = ' '.join(t[1:])
+                elif k == 'FORWARD_RATE':
+                    r.forward_rate = fnum(t[1])
+                elif k == 'BACKWARD_RATE':
+                    r.backward_rate = fnum(t[1])
+                else:
+                    raise DeckError('GENERAL_REACTION keyword ' + k)
+            chem.general_rxns.append(r)
+        elif kw == 'RADIOACTIVE_DECAY_REACTION':            # reaction.F90:254-314
+            r = RateRxn()
+            for t in rd.block():
+                k = t[0].upper()
+                if k == 'REACTION':
+                    r.reaction = ' '.join(t[1:])
+                elif k == 'RATE_CONSTANT':
+                    r.rate_constant = fnum(t[1])
+                    if len(t) > 2 and t[2][0] not in '!#':
+                        r.rate_constant = r.rate_constant * units_convert_to_internal(t[2], 'unitless/sec')
+                elif k == 'HALF_LIFE':
+                    hl = fnum(t[1])
+                    if len(t) > 2 and t[2][0] not in '!#':
+                        hl = hl * units_convert_to_internal(t[2], 'sec')
+                    r.rate_constant = -1.0 * math.log(0.5) / hl
+                else:
+                    raise DeckError('RADIOACTIVE_DECAY_REACTION keyword ' + k)
+            if r.rate_constant is None:
+                raise DeckError('RATE_CONSTANT or HALF_LIFE must be set in RADIOACTIVE_DECAY_REACTION.')
+            chem.radiodecay_rxns.append(r)
+        elif kw in ('MICROBIAL_REACTION',
                     'IMMOBILE_SPECIES', 'IMMOBILE_DECAY_REACTION', 'COLLOIDS',
                     'REACTION_SANDBOX', 'CLM_REACTION', 'SOLID_SOLUTIONS'):
             chem.unsupported.append(kw)

@@ -28,6 +28,8 @@ _INT_FIELDS = {
     'eqionx_rxn_cationid', 'eqionx_rxn_Z_flag', 'eqionx_rxn_to_surf',
     'eqkdspecid', 'eqkdtype', 'eqkdmineral',
     'paseqspecid', 'paseqh2oid',
+    'generalspecid', 'generalforwardspecid', 'generalbackwardspecid', 'radiodecayspecid', 'radiodecayforwardspecid',
+    'kinsrfcplxrxn_to_srfcplxrxn',
 }
 
 

@@ -641,6 +641,145 @@ __device__ void multirate_sorption(const Tab &T, const DevState &S, Cell<N> &c, 
 // ---------------------------------------------------------------------------------------------
 // ludcmp / lubksb — utility.F90:393-476, 480-523 (Crout, implicit scaling, partial pivoting,
 // `>=` tie-break = last maximum wins, tiny = 1e-20).  A column-major n x n.
+// ---------------------------------------------------------------------------------------------
+// RKineticSurfCplx — reaction_surf_complex.F90:938-1137.  One kinetic reaction = surface complexation reaction 1 on
+// mineral surface 1 (rxn_pack.h: the only configuration in which the reference's site / complex indices are in bounds);
+// S^k, S^{k+1} and the free-site concentration live in the state (KINSRFCPLX_*), S^k -> S^{k+1} in RUpdateKineticState.
+template <int N>
+__device__ void kinetic_surfcplx(const Tab &T, const DevState &S, Cell<N> &c, double dt, double *Res, double *Jac, bool compute_derivative) {
+  const DevTab &h = *T.h;
+  const int n = h.naq;
+  const int c0 = T.i[h.o_rxn_cptr + h.kin_rxn], c1 = T.i[h.o_rxn_cptr + h.kin_rxn + 1];
+  const int *sptr = T.i + h.srf.o_ptr, *sid = T.i + h.srf.o_id;
+  const double *sst = T.d + h.srf.o_st, *sh2o = T.d + h.srf.o_h2ost, *kf = T.d + h.o_kin_kf, *kb = T.d + h.o_kin_kb;
+  double Q[RXN_MAX_SRFCPLX_PER_RXN];
+  for (int j = c0; j < c1; ++j) {
+    const int icplx = T.i[h.o_rxn_cid + j];
+    double lnQ = 0.0;
+    if (sh2o[icplx] != 0.0) lnQ = lnQ + sh2o[icplx] * c.ln_act_h2o;
+    for (int p = sptr[icplx]; p < sptr[icplx + 1]; ++p) lnQ = lnQ + sst[p] * c.lna[sid[p]];
+    Q[j - c0] = exp(lnQ);
+  }
+  double numerator_sum = 0.0;
+  for (int j = c0; j < c1; ++j) {
+    const int icplx = T.i[h.o_rxn_cid + j];
+    numerator_sum = numerator_sum + G(S, RXN_F_KINSRFCPLX_CONC, icplx, c.cell) / (1.0 + kb[icplx] * dt);
+  }
+  numerator_sum = T.d[h.o_rxn_density + 0] - numerator_sum;
+  double denominator_sum = 1.0;
+  for (int j = c0; j < c1; ++j) {
+    const int icplx = T.i[h.o_rxn_cid + j];
+    denominator_sum = denominator_sum + (kf[icplx] * dt) / (1.0 + kb[icplx] * dt) * Q[j - c0];
+  }
+  for (int j = c0; j < c1; ++j) {
+    const int icplx = T.i[h.o_rxn_cid + j];
+    const double conc_k = G(S, RXN_F_KINSRFCPLX_CONC, icplx, c.cell);
+    const double denominator = 1.0 + kb[icplx] * dt;
+    const double conc_kp1 = (conc_k + kf[icplx] * dt * numerator_sum / denominator_sum * Q[j - c0]) / denominator;
+    G(S, RXN_F_KINSRFCPLX_CONC_KP1, icplx, c.cell) = conc_kp1;
+    for (int p = sptr[icplx]; p < sptr[icplx + 1]; ++p)
+      Res[sid[p]] = Res[sid[p]] + sst[p] * (conc_kp1 - conc_k) / dt * c.volume;
+  }
+  G(S, RXN_F_KINSRFCPLX_FREE_SITE_CONC, 0, c.cell) = numerator_sum / denominator_sum;
+  if (compute_derivative) {
+    double fac_sum[N];
+    for (int i = 0; i < n; ++i) fac_sum[i] = 0.0;
+    for (int j = c0; j < c1; ++j) {
+      const int icplx = T.i[h.o_rxn_cid + j];
+      const double denominator = 1.0 + kb[icplx] * dt;
+      const double fac = kf[icplx] / denominator;
+      for (int p = sptr[icplx]; p < sptr[icplx + 1]; ++p) fac_sum[sid[p]] = fac_sum[sid[p]] + sst[p] * fac * Q[j - c0];
+    }
+    for (int j = c0; j < c1; ++j) {
+      const int icplx = T.i[h.o_rxn_cid + j];
+      const double denominator = 1.0 + kb[icplx] * dt;
+      const double fac = kf[icplx] / denominator;
+      for (int p = sptr[icplx]; p < sptr[icplx + 1]; ++p) {
+        const int jcomp = sid[p];
+        for (int q = sptr[icplx]; q < sptr[icplx + 1]; ++q) {
+          const int lcomp = sid[q];
+          Jac[jcomp + lcomp * n] = Jac[jcomp + lcomp * n] +
+              (sst[p] * fac * numerator_sum * Q[j - c0] * (sst[q] - dt * fac_sum[lcomp] / denominator_sum)) / denominator_sum *
+                  exp(-c.lnc[lcomp]) * c.volume;
+        }
+      }
+    }
+  }
+}
+
+// RRadioactiveDecay — reaction.F90:4607-4690.  dtot / dsorb: d total / d free-ion and d total_sorb_eq / d free-ion
+// (column-major) of this iterate.
+template <int N>
+__device__ void radioactive_decay(const Tab &T, const Cell<N> &c, const double *dtot, const double *dsorb, double *Res, double *Jac,
+                                  bool compute_derivative) {
+  const DevTab &h = *T.h;
+  const int n = h.naq;
+  const double L_water = c.porosity * c.sat * c.volume * 1.0e3;
+  for (int irxn = 0; irxn < h.ndecay; ++irxn) {
+    const int jcomp = T.i[h.o_dec_fwd + irxn];
+    double sum = c.total[jcomp] * L_water;
+    sum = sum + (h.neqsorb > 0 ? c.tsorb[jcomp] : 0.0) * c.volume;
+    const double kf = T.d[h.o_dec_kf + irxn];
+    const double rate = sum * kf;
+    const int p0 = T.i[h.o_dec_ptr + irxn], p1 = T.i[h.o_dec_ptr + irxn + 1];
+    for (int p = p0; p < p1; ++p) Res[T.i[h.o_dec_id + p]] = Res[T.i[h.o_dec_id + p]] - T.d[h.o_dec_st + p] * rate;
+    if (!compute_derivative) continue;
+    const double tempreal = -1.0 * kf;
+    for (int p = p0; p < p1; ++p) {
+      const int icomp = T.i[h.o_dec_id + p];
+      for (int j = 0; j < n; ++j)
+        Jac[icomp + j * n] = Jac[icomp + j * n] + tempreal * T.d[h.o_dec_st + p] *
+                                                      (dtot[jcomp + j * n] * L_water + (h.neqsorb > 0 ? dsorb[jcomp + j * n] : 0.0) * c.volume);
+    }
+  }
+}
+
+// RGeneral — reaction.F90:4694-4831
+template <int N>
+__device__ void general_reaction(const Tab &T, const Cell<N> &c, double *Res, double *Jac, bool compute_derivative) {
+  const DevTab &h = *T.h;
+  const int n = h.naq;
+  for (int irxn = 0; irxn < h.ngen; ++irxn) {
+    const double kf = T.d[h.o_gen_kf + irxn], kr = T.d[h.o_gen_kr + irxn];
+    const int f0 = T.i[h.o_genf_ptr + irxn], f1 = T.i[h.o_genf_ptr + irxn + 1];
+    const int b0 = T.i[h.o_genb_ptr + irxn], b1 = T.i[h.o_genb_ptr + irxn + 1];
+    const int g0 = T.i[h.o_gen_ptr + irxn], g1 = T.i[h.o_gen_ptr + irxn + 1];
+    double Qkf, lnQkf = 0.0, Qkr, lnQkr = 0.0;
+    if (kf > 0.0) {
+      lnQkf = log(kf);
+      for (int p = f0; p < f1; ++p) lnQkf = lnQkf + T.d[h.o_genf_st + p] * c.lna[T.i[h.o_genf_id + p]];
+      Qkf = exp(lnQkf);
+    } else {
+      Qkf = 0.0;
+    }
+    if (kr > 0.0) {
+      lnQkr = log(kr);
+      for (int p = b0; p < b1; ++p) lnQkr = lnQkr + T.d[h.o_genb_st + p] * c.lna[T.i[h.o_genb_id + p]];
+      Qkr = exp(lnQkr);
+    } else {
+      Qkr = 0.0;
+    }
+    const double por_den_sat_vol = c.porosity * c.den_kg * c.sat * c.volume;
+    for (int p = g0; p < g1; ++p)
+      Res[T.i[h.o_gen_id + p]] = Res[T.i[h.o_gen_id + p]] - T.d[h.o_gen_st + p] * (Qkf - Qkr) * por_den_sat_vol;
+    if (!compute_derivative) continue;
+    if (kf > 0.0) {
+      for (int q = f0; q < f1; ++q) {
+        const int jcomp = T.i[h.o_genf_id + q];
+        const double tempreal = -1.0 * T.d[h.o_genf_st + q] * exp(lnQkf - c.lnc[jcomp]) * por_den_sat_vol;
+        for (int p = g0; p < g1; ++p) Jac[T.i[h.o_gen_id + p] + jcomp * n] = Jac[T.i[h.o_gen_id + p] + jcomp * n] + T.d[h.o_gen_st + p] * tempreal;
+      }
+    }
+    if (kr > 0.0) {
+      for (int q = b0; q < b1; ++q) {
+        const int jcomp = T.i[h.o_genb_id + q];
+        const double tempreal = T.d[h.o_genb_st + q] * exp(lnQkr - c.lnc[jcomp]) * por_den_sat_vol;
+        for (int p = g0; p < g1; ++p) Jac[T.i[h.o_gen_id + p] + jcomp * n] = Jac[T.i[h.o_gen_id + p] + jcomp * n] + T.d[h.o_gen_st + p] * tempreal;
+      }
+    }
+  }
+}
+
 template <int N>
 __device__ int ludcmp(double *A, int n, int *indx) {
   const double tiny = 1.0e-20;
@@ -772,6 +911,7 @@ __device__ int rreact(const Tab &T, const DevState &S, Cell<N> &c, double *tran_
   const int n = h.naq, naq = h.naq;
   double residual[N], fixed_accum[N], prev_solution[N], new_solution[N];
   double mrK1[2], mrR0[2 * N];   // nmr <= 2 enforced at table creation
+  double dtot[N * N];            // d total / d free-ion of the iterate (RRadioactiveDecay reads it after J has been scaled)
   int num_iterations = 0;
   *exit_reason = 0;
   for (int i = 0; i < naq; ++i) c.total[i] = tran_xx[i];                       // :3370
@@ -787,6 +927,7 @@ __device__ int rreact(const Tab &T, const DevState &S, Cell<N> &c, double *tran_
     num_iterations = num_iterations + 1;
     if (h.act_freq == RXN_ACT_COEF_FREQUENCY_NEWTON_ITER) activity_coefficients<N>(T, S, c);
     auxvar_compute<N>(T, S, c, J, dsorb);                                      // J <- dtotal
+    if (h.ndecay > 0) for (int e = 0; e < naq * naq; ++e) dtot[e] = J[e];
     for (int i = 0; i < naq; ++i) residual[i] = psv_t * c.total[i];
     for (int i = 0; i < n; ++i) residual[i] = residual[i] - fixed_accum[i];
     for (int e = 0; e < naq * naq; ++e) J[e] = J[e] * psvd_t;                  // RTAccumulationDerivative
@@ -799,6 +940,9 @@ __device__ int rreact(const Tab &T, const DevState &S, Cell<N> &c, double *tran_
     // RReaction (:3515-3584): minerals, then multirate
     if (h.nkin > 0) kinetic_mineral<N>(T, S, c, residual, J, true);
     if (h.nmr > 0) multirate_sorption<N>(T, S, c, mrK1, mrR0, residual, J, true, dsorb);
+    if (h.nkinrxn > 0) kinetic_surfcplx<N>(T, S, c, tran_dt, residual, J, true);
+    if (h.ndecay > 0) radioactive_decay<N>(T, c, dtot, dsorb, residual, J, true);
+    if (h.ngen > 0) general_reaction<N>(T, c, residual, J, true);
     double mx = 0.0;
     bool nonfinite = false;
     for (int i = 0; i < n; ++i) { mx = fmax(mx, fabs(residual[i])); if (!isfinite(residual[i])) nonfinite = true; }
@@ -919,6 +1063,7 @@ __device__ void cell_residual_jacobian(const Tab &T, const DevState &S, long lon
   load_cell<N>(T, S, cell, c);
   const int n = tab.naq;
   auxvar_compute<N>(T, S, c, J, dsorb);
+  if (tab.ndecay > 0) for (int e = 0; e < n * n; ++e) J2[e] = J[e];          // d total / d free-ion for RRadioactiveDecay
   const double psv_t = c.porosity * c.sat * 1000.0 * c.volume;
   const double psvd_t = c.porosity * c.sat * 1000.0 * c.volume / dt;
   const double v_t = c.volume / dt;
@@ -930,12 +1075,20 @@ __device__ void cell_residual_jacobian(const Tab &T, const DevState &S, long lon
   }
   for (int k = 0; k < n; ++k) { Res[k] = Res[k] / dt; Res2[k] = 0.0; }
   const bool deriv = jac_out != nullptr;
+  if (tab.ndecay > 0) {
+    // the decay terms read d total / d free-ion (kept in J2 so far): add them into the accumulation block first -
+    // REASSOC: the reference adds the two blocks entry by entry in MatSetValuesBlockedLocal(ADD_VALUES); the sum of an
+    // entry's terms is taken in the order accumulation, decay, minerals, ... instead of accumulation + (minerals + ... + decay)
+    radioactive_decay<N>(T, c, J2, dsorb, Res2, J, deriv);
+  }
   for (int e = 0; e < n * n; ++e) J2[e] = 0.0;
   if (tab.nkin > 0) kinetic_mineral<N>(T, S, c, Res2, J2, deriv);
   if (tab.nmr > 0) {
     multirate_prepare<N>(T, S, c, dt, mrK1, mrR0);
     multirate_sorption<N>(T, S, c, mrK1, mrR0, Res2, J2, deriv, dsorb);
   }
+  if (tab.nkinrxn > 0) kinetic_surfcplx<N>(T, S, c, dt, Res2, J2, deriv);
+  if (tab.ngen > 0) general_reaction<N>(T, c, Res2, J2, deriv);
   if (res_out) for (int k = 0; k < n; ++k) res_out[i * n + k] = Res[k] + Res2[k];
   if (jac_out) for (int e = 0; e < n * n; ++e) jac_out[i * (long long)(n * n) + e] = J[e] + J2[e];
   store_cell<N>(T, S, c, nullptr, nullptr);   // totals + warm-start free sites stay consistent
@@ -973,6 +1126,12 @@ __device__ void cell_update_kinetic_state(const Tab &T, const DevState &S, long 
         const double S0 = G(S, RXN_F_KINMR_TOTAL_SORB, blk + k, cell);
         Sr = (Sr + kdt * frac * S0) / one_plus_kdt;
       }
+    }
+  }
+  if (tab.nkinrxn > 0) {                                                     // :5411-5419
+    for (int j = T.i[tab.o_rxn_cptr + tab.kin_rxn]; j < T.i[tab.o_rxn_cptr + tab.kin_rxn + 1]; ++j) {
+      const int icplx = T.i[tab.o_rxn_cid + j];
+      G(S, RXN_F_KINSRFCPLX_CONC, icplx, cell) = G(S, RXN_F_KINSRFCPLX_CONC_KP1, icplx, cell);
     }
   }
 }

@@ -79,16 +79,20 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
   if (d->struct_size != (int)sizeof(RxnTablesDesc))
     return R.fail(RXN_ERR_INVALID, "RxnTablesDesc.struct_size %d != %d", d->struct_size, (int)sizeof(RxnTablesDesc));
   // reaction types outside the path
-  if (d->nactive_gas || d->nimmobile || d->ncoll || d->ngeneral_rxn || d->nradiodecay_rxn || d->nmicrobial_rxn ||
+  if (d->nactive_gas || d->nimmobile || d->ncoll || d->nmicrobial_rxn ||
       d->nimmobile_decay_rxn || d->has_sandbox || d->has_clm || d->has_solid_solution || d->co2_flow_mode ||
-      d->numerical_derivatives || d->nkinsrfcplxrxn)
+      d->numerical_derivatives)
     return R.fail(RXN_ERR_UNSUPPORTED,
-                  "tables enable a reaction type outside the B200 path (active gas %d, immobile %d, colloids %d, general %d, "
-                  "radioactive decay %d, microbial %d, immobile decay %d, sandbox %d, CLM %d, solid solution %d, CO2 flow mode %d, "
-                  "numerical Jacobian %d, kinetic surface complexation %d)",
-                  d->nactive_gas, d->nimmobile, d->ncoll, d->ngeneral_rxn, d->nradiodecay_rxn, d->nmicrobial_rxn,
+                  "tables enable a reaction type outside the B200 path (active gas %d, immobile %d, colloids %d, "
+                  "microbial %d, immobile decay %d, sandbox %d, CLM %d, solid solution %d, CO2 flow mode %d, "
+                  "numerical Jacobian %d)",
+                  d->nactive_gas, d->nimmobile, d->ncoll, d->nmicrobial_rxn,
                   d->nimmobile_decay_rxn, d->has_sandbox, d->has_clm, d->has_solid_solution, d->co2_flow_mode,
-                  d->numerical_derivatives, d->nkinsrfcplxrxn);
+                  d->numerical_derivatives);
+  if (d->ngeneral_rxn < 0 || d->nradiodecay_rxn < 0 || d->nkinsrfcplxrxn < 0) return R.fail(RXN_ERR_INVALID, "negative reaction count");
+  if (d->nkinsrfcplxrxn > 1)
+    return R.fail(RXN_ERR_UNSUPPORTED, "more than one KINETIC surface complexation reaction: the reference keeps the kinetic "
+                                       "concentrations of one reaction only (kinsrfcplx_conc(:,1), reactive_transport_aux.F90:284-290)");
   if (d->naqcomp < 1 || d->ncomp != d->naqcomp)
     return R.fail(RXN_ERR_UNSUPPORTED, "ncomp (%d) must equal naqcomp (%d) >= 1", d->ncomp, d->naqcomp);
   if (d->naqcomp > RXN_MAX_NAQ) return R.fail(RXN_ERR_UNSUPPORTED, "naqcomp %d > %d", d->naqcomp, (int)RXN_MAX_NAQ);
@@ -160,6 +164,7 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
     std::vector<int32_t> cptr(1, 0), cid;
     for (int r = 0; r < h.nrxn; ++r) {
       const int ld = d->srfcplxrxn_to_complex_ld, n = d->srfcplxrxn_to_complex[(size_t)r * ld];
+      if (n < 0 || n > ld - 1) return R.fail(RXN_ERR_INVALID, "surface complexation reaction %d: complex count %d out of range", r + 1, n);
       if (n > RXN_MAX_SRFCPLX_PER_RXN)
         return R.fail(RXN_ERR_UNSUPPORTED, "surface complexation reaction %d has %d complexes (> %d)", r + 1, n, (int)RXN_MAX_SRFCPLX_PER_RXN);
       for (int k = 1; k <= n; ++k) {
@@ -175,10 +180,17 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
     }
     h.o_rxn_cptr = P.I(cptr.data(), cptr.size()); h.o_rxn_cid = P.I(cid.data(), cid.size());
     std::vector<int32_t> eq, mr, mrn;
-    for (int i = 0; i < h.neq; ++i) eq.push_back(d->eqsrfcplxrxn_to_srfcplxrxn[i] - 1);
+    for (int i = 0; i < h.neq; ++i) {
+      const int ir = d->eqsrfcplxrxn_to_srfcplxrxn[i];
+      if (ir < 1 || ir > h.nrxn) return R.fail(RXN_ERR_INVALID, "eqsrfcplxrxn_to_srfcplxrxn[%d] = %d out of range", i, ir);
+      eq.push_back(ir - 1);
+    }
     for (int i = 0; i < h.nmr; ++i) {
-      mr.push_back(d->kinmrsrfcplxrxn_to_srfcplxrxn[i] - 1);
-      mrn.push_back(d->kinmr_nrate[i + 1]);
+      const int ir = d->kinmrsrfcplxrxn_to_srfcplxrxn[i], nr = d->kinmr_nrate[i + 1];
+      if (ir < 1 || ir > h.nrxn) return R.fail(RXN_ERR_INVALID, "kinmrsrfcplxrxn_to_srfcplxrxn[%d] = %d out of range", i, ir);
+      if (nr < 0 || nr > h.mr_ld) return R.fail(RXN_ERR_INVALID, "kinmr_nrate[%d] = %d exceeds the leading dimension %d", i + 1, nr, h.mr_ld);
+      mr.push_back(ir - 1);
+      mrn.push_back(nr);
     }
     h.o_eq_rxn = P.I(eq.data(), eq.size()); h.o_mr_rxn = P.I(mr.data(), mr.size()); h.o_mr_nrate = P.I(mrn.data(), mrn.size());
     h.o_mr_rate = P.D(d->kinmr_rate, (size_t)h.nmr * h.mr_ld); h.o_mr_frac = P.D(d->kinmr_frac, (size_t)h.nmr * h.mr_ld);
@@ -188,6 +200,7 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
     std::vector<double> kk;
     for (int r = 0; r < h.nionx; ++r) {
       const int ld = h.ionx_ld + 1, n = d->eqionx_rxn_cationid[(size_t)r * ld];
+      if (n < 0 || n > h.ionx_ld) return R.fail(RXN_ERR_INVALID, "ion exchange reaction %d: cation count %d exceeds the leading dimension %d", r + 1, n, h.ionx_ld);
       for (int k = 1; k <= n; ++k) {
         const int ic = d->eqionx_rxn_cationid[(size_t)r * ld + k];
         if (ic < 1 || ic > naq) return R.fail(RXN_ERR_INVALID, "ion exchange reaction %d: cation id %d out of range", r + 1, ic);
@@ -208,6 +221,66 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
   }
   h.o_kd_spec = P.I(d->eqkdspecid, h.nkd); h.o_kd_type = P.I(d->eqkdtype, h.nkd); h.o_kd_mnrl = P.I(d->eqkdmineral, h.nkd);
   h.o_kd_coef = P.D(d->eqkddistcoef, h.nkd); h.o_kd_b = P.D(d->eqkdlangmuirb, h.nkd); h.o_kd_n = P.D(d->eqkdfreundlichn, h.nkd);
+  // general reactions / radioactive decay: Fortran (0:m, n) id tables -> CSR with 0-based ids
+  {
+    auto csr = [&](const int32_t *ids, const double *st, int ld, int nr, int &o_ptr, int &o_id, int &o_st, const char *what) {
+      std::vector<int32_t> ptr(1, 0), id;
+      std::vector<double> sv;
+      for (int r = 0; r < nr; ++r) {
+        const int n = ids ? ids[(size_t)r * (ld + 1)] : 0;
+        if (n < 0 || n > ld) return R.fail(RXN_ERR_INVALID, "%s %d: species count %d out of range", what, r + 1, n);
+        for (int k = 1; k <= n; ++k) {
+          const int sp = ids[(size_t)r * (ld + 1) + k];
+          if (sp < 1 || sp > naq) return R.fail(RXN_ERR_INVALID, "%s %d: species id %d out of range", what, r + 1, sp);
+          id.push_back(sp - 1);
+          sv.push_back(st ? st[(size_t)r * ld + k - 1] : 0.0);
+        }
+        ptr.push_back((int32_t)id.size());
+      }
+      o_ptr = P.I(ptr.data(), ptr.size()); o_id = P.I(id.data(), id.size()); o_st = P.D(sv.data(), sv.size());
+      return (int)RXN_OK;
+    };
+    h.ngen = d->ngeneral_rxn; h.ndecay = d->nradiodecay_rxn;
+    if (h.ngen > 0 && (!d->generalspecid || !d->generalstoich || !d->generalforwardspecid || !d->generalforwardstoich ||
+                       !d->generalbackwardspecid || !d->generalbackwardstoich || !d->general_kf || !d->general_kr || d->general_ld < 1))
+      return R.fail(RXN_ERR_INVALID, "ngeneral_rxn = %d without the general reaction tables", h.ngen);
+    if (h.ndecay > 0 && (!d->radiodecayspecid || !d->radiodecaystoich || !d->radiodecayforwardspecid || !d->radiodecay_kf || d->radiodecay_ld < 1))
+      return R.fail(RXN_ERR_INVALID, "nradiodecay_rxn = %d without the radioactive decay tables", h.ndecay);
+    RXN_TRY(csr(d->generalspecid, d->generalstoich, d->general_ld, h.ngen, h.o_gen_ptr, h.o_gen_id, h.o_gen_st, "general reaction"));
+    RXN_TRY(csr(d->generalforwardspecid, d->generalforwardstoich, d->general_ld, h.ngen, h.o_genf_ptr, h.o_genf_id, h.o_genf_st, "general reaction (forward)"));
+    RXN_TRY(csr(d->generalbackwardspecid, d->generalbackwardstoich, d->general_ld, h.ngen, h.o_genb_ptr, h.o_genb_id, h.o_genb_st, "general reaction (backward)"));
+    h.o_gen_kf = P.D(d->general_kf, h.ngen); h.o_gen_kr = P.D(d->general_kr, h.ngen);
+    RXN_TRY(csr(d->radiodecayspecid, d->radiodecaystoich, d->radiodecay_ld, h.ndecay, h.o_dec_ptr, h.o_dec_id, h.o_dec_st, "radioactive decay reaction"));
+    std::vector<int32_t> fwd;
+    for (int r = 0; r < h.ndecay; ++r) {
+      const int sp = d->radiodecayforwardspecid ? d->radiodecayforwardspecid[r] : 0;
+      if (sp < 1 || sp > naq) return R.fail(RXN_ERR_INVALID, "radioactive decay reaction %d: reactant id %d out of range", r + 1, sp);
+      fwd.push_back(sp - 1);
+    }
+    h.o_dec_fwd = P.I(fwd.data(), fwd.size()); h.o_dec_kf = P.D(d->radiodecay_kf, h.ndecay);
+  }
+  // kinetic surface complexation: RKineticSurfCplx indexes numerator_sum / denominator_sum / srfcplxrxn_site_density /
+  // kinsrfcplx_free_site_conc with isite = srfcplxrxn_to_surf(irxn) and the rate tables with the GLOBAL complex id
+  // (reaction_surf_complex.F90:1022-1075) although they are dimensioned by kinetic reaction and by position in the reaction.
+  // Those indices are in bounds and mean what the routine intends only when the kinetic reaction is surface complexation
+  // reaction 1 (its complexes are then 1..n in the master list) on mineral surface 1: anything else is rejected.
+  h.nkinrxn = d->nkinsrfcplxrxn; h.nkinsrf = 0; h.kin_rxn = 0;
+  if (h.nkinrxn == 1) {
+    if (!d->kinsrfcplxrxn_to_srfcplxrxn || !d->kinsrfcplx_forward_rate || !d->kinsrfcplx_backward_rate || h.nrxn < 1)
+      return R.fail(RXN_ERR_INVALID, "nkinsrfcplxrxn = 1 without the kinetic surface complexation tables");
+    const int ir = d->kinsrfcplxrxn_to_srfcplxrxn ? d->kinsrfcplxrxn_to_srfcplxrxn[0] : 0;
+    if (ir != 1 || h.nrxn < 1)
+      return R.fail(RXN_ERR_UNSUPPORTED, "the KINETIC surface complexation reaction must be the first surface complexation reaction (it is %d)", ir);
+    if (d->srfcplxrxn_surf_type[0] != RXN_MINERAL_SURFACE || d->srfcplxrxn_to_surf[0] != 1)
+      return R.fail(RXN_ERR_UNSUPPORTED, "the KINETIC surface complexation reaction must sit on kinetic mineral 1 "
+                                         "(RKineticSurfCplx uses the mineral id as site index)");
+    const int nc = d->srfcplxrxn_to_complex[0];
+    for (int k = 1; k <= nc; ++k)
+      if (d->srfcplxrxn_to_complex[k] != k) return R.fail(RXN_ERR_UNSUPPORTED, "complexes of the KINETIC reaction must be complexes 1..n of the master list");
+    if (nc > d->kinsrfcplx_ld) return R.fail(RXN_ERR_INVALID, "kinsrfcplx_ld %d < %d complexes", d->kinsrfcplx_ld, nc);
+    h.nkinsrf = nc; h.kin_rxn = 0;
+    h.o_kin_kf = P.D(d->kinsrfcplx_forward_rate, nc); h.o_kin_kb = P.D(d->kinsrfcplx_backward_rate, nc);
+  }
 #undef RXN_TRY
   if (P.i.size() & 1) P.i.push_back(0);
   h.ndbl = (int)P.d.size(); h.nint = (int)P.i.size();
@@ -223,6 +296,7 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
   r[RXN_F_DEN_KG] = r[RXN_F_SAT] = r[RXN_F_TEMP] = r[RXN_F_PRES] = r[RXN_F_VOLUME] = r[RXN_F_POROSITY] =
       r[RXN_F_SOIL_PARTICLE_DENSITY] = 1;
   r[RXN_F_DTOTAL] = naq * naq; r[RXN_F_DTOTAL_SORB_EQ] = naq * naq;
+  r[RXN_F_KINSRFCPLX_CONC] = h.nkinsrf; r[RXN_F_KINSRFCPLX_CONC_KP1] = h.nkinsrf; r[RXN_F_KINSRFCPLX_FREE_SITE_CONC] = h.nkinrxn;
   return RXN_OK;
 }
 

@@ -44,6 +44,15 @@ struct DevTab {
   int o_ionx_k, o_ionx_CEC;                                                 // dbl
   int o_kd_spec, o_kd_type, o_kd_mnrl;                                      // int
   int o_kd_coef, o_kd_b, o_kd_n;                                            // dbl
+  // general reactions (RGeneral), radioactive decay (RRadioactiveDecay): CSR lists, 0-based ids
+  int ngen, ndecay;
+  int o_gen_ptr, o_gen_id, o_genf_ptr, o_genf_id, o_genb_ptr, o_genb_id;   // int
+  int o_gen_st, o_genf_st, o_genb_st, o_gen_kf, o_gen_kr;                   // dbl
+  int o_dec_ptr, o_dec_id, o_dec_fwd;                                       // int ([ndecay] reactant id, 0-based)
+  int o_dec_st, o_dec_kf;                                                   // dbl
+  // kinetic surface complexation (RKineticSurfCplx): at most one reaction, = surface complexation reaction kin_rxn (0-based)
+  int nkinrxn, nkinsrf, kin_rxn;
+  int o_kin_kf, o_kin_kb;                                                   // dbl [nkinsrf]
 };
 
 // SoA FP64 state in HBM: f[field][row*ld + cell]; NULL when the field has no rows or is

@@ -6,7 +6,7 @@ from pflotran_b200 import abi, synth
 
 STATE_FIELDS = ['PRI_MOLAL', 'TOTAL', 'SEC_MOLAL', 'PRI_ACT_COEF', 'SEC_ACT_COEF', 'LN_ACT_H2O', 'TOTAL_SORB_EQ',
                 'FREE_SITE_CONC', 'EQSRFCPLX_CONC', 'KINMR_TOTAL_SORB', 'EQIONX_REF_CATION_SORBED_CONC', 'EQIONX_CONC',
-                'MNRL_VOLFRAC', 'MNRL_RATE']
+                'MNRL_VOLFRAC', 'MNRL_RATE', 'KINSRFCPLX_CONC', 'KINSRFCPLX_CONC_KP1', 'KINSRFCPLX_FREE_SITE_CONC']
 
 # north_star: relative 1e-10 on converged free-ion and mineral concentrations, identical flags
 RTOL = 1.0e-10

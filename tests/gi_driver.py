@@ -105,12 +105,13 @@ def run_deck(t, be, xx, final_time, dt0, dt_max, iaccel=5, tolerance=0.1, **kw):
         time = target
         steps += 1
         newton += n
-        if n <= iaccel:
-            dtt = TFAC[n - 1] * dt if n <= len(TFAC) else 0.5 * dt
-        else:
-            dtt = 0.5 * dt
-        dtt = min(dtt, 2.0 * dt, dt_max)
-        dt = dtt
+        if iaccel != 0:                        # TimestepperBEUpdateDT (timestepper_BE.F90:238): TS_ACCELERATION 0 keeps dt
+            if n <= iaccel:
+                dtt = TFAC[n - 1] * dt if n <= len(TFAC) else 0.5 * dt
+            else:
+                dtt = 0.5 * dt
+            dtt = min(dtt, 2.0 * dt, dt_max)
+            dt = dtt
     return steps, newton
 
 
@@ -169,7 +170,7 @@ def run(t, be, xx, dts, atol=1.0e-50, rtol=1.0e-8, stol=1.0e-8, maxit=50):
     return newton
 
 
-TIME_STEPPED_GOLD = ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral']
+TIME_STEPPED_GOLD = ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction']
 
 
 def check_time_stepped_gold(w, be, t, xx, tol=1.0e-12):
@@ -178,7 +179,8 @@ def check_time_stepped_gold(w, be, t, xx, tol=1.0e-12):
     1e-12 absolute; relative above 1), time-step and Newton-iteration counters equal, solution 2-norm."""
     import kat
     tm = w.meta['time']
-    steps, newton = run_deck(t, be, xx, tm['FINAL_TIME'], tm['INITIAL_TIMESTEP_SIZE'], tm['MAXIMUM_TIMESTEP_SIZE'], tm['iaccel'])
+    kw = {k.lower(): tm[k] for k in ('ATOL', 'RTOL', 'STOL') if k in tm}          # NEWTON_SOLVER card of the deck
+    steps, newton = run_deck(t, be, xx, tm['FINAL_TIME'], tm['INITIAL_TIMESTEP_SIZE'], tm['MAXIMUM_TIMESTEP_SIZE'], tm['iaccel'], **kw)
     out = kat.outputs(t, be.state())
     gold = w.gold
     assert steps == gold['Transport']['Time Steps'] and newton == gold['Transport']['Newton Iterations'], (steps, newton)
@@ -192,3 +194,20 @@ def check_time_stepped_gold(w, be, t, xx, tol=1.0e-12):
         assert abs(out[var] - g) <= tol * max(1.0, abs(g)), '%s %s: %.14e gold %.14e' % (w.name, var, out[var], g)
         checked += 1
     return checked
+
+
+def check_decay_closed_form(w, be, t, xx, rtol=1.0e-12):
+    """Radioactive decay A -> B stepped by backward Euler has the closed form A_n = A_0 / (1 + k dt)^n, B_n = B_0 + A_0 - A_n
+    (linear problem: one Newton iteration per step).  Fixture `decay_ab`: the first-order reaction of the reference's
+    general-reaction.in written as RADIOACTIVE_DECAY_REACTION with the same rate (half life ln 2 / k)."""
+    import kat
+    tm = w.meta['time']
+    kw = {k.lower(): tm[k] for k in ('ATOL', 'RTOL', 'STOL') if k in tm}
+    a0, b0 = float(xx[0, 0]), float(xx[0, 1])
+    steps, newton = run_deck(t, be, xx, tm['FINAL_TIME'], tm['INITIAL_TIMESTEP_SIZE'], tm['MAXIMUM_TIMESTEP_SIZE'], tm['iaccel'], **kw)
+    assert steps == 500 and newton == 500
+    k = float(t.radiodecay_kf[0])
+    an = a0 / (1.0 + k * tm['INITIAL_TIMESTEP_SIZE']) ** steps
+    st = be.state()
+    assert abs(st['PRI_MOLAL'][0, 0] - an) <= rtol * an, (st['PRI_MOLAL'][0, 0], an)
+    assert abs(st['PRI_MOLAL'][1, 0] - (b0 + a0 - an)) <= rtol * (b0 + a0), (st['PRI_MOLAL'][1, 0], b0 + a0 - an)

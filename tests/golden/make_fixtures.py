@@ -54,6 +54,9 @@ WORKLOADS = {
                       'regression_tests/default/batch/solute_KD_wo_mineral.regression.gold'),
     # mineral prefactors (reaction_mineral.F90:743-782) on primary species, 9 primaries / 57 complexes / 6 kinetic minerals
     'mineral_prefactor': ('regression_tests/default/column/mineral_prefactor.in', 'initial_ore', None),
+    # RGeneral (reaction.F90:4694-4831), linear formulation, 500 steps of 0.1 d with the deck's own Newton tolerances
+    'general_reaction': ('regression_tests/ascem/batch/general-reaction.in', 'Initial',
+                         'regression_tests/ascem/batch/general-reaction.regression.gold'),
     # non-isothermal run: 5-term logK fit evaluated per cell (reaction_aux.F90:1336-1408, 1461-1488) + Arrhenius factor
     'calcite_fit5': ('regression_tests/default/anisothermal/thc_1d.in', 'initial_constraint', None),
     # BASELINE config 1: 22 primaries / 164 complexes (example_problems/ascem_chemistry, savannah_river.dat)
@@ -83,6 +86,16 @@ VARIANTS = {
                       [('KD_MINERAL_NAME A(s)', 'KD_MINERAL_NAME A(s)\n        FREUNDLICH_N 0.8d0')]),
     # RKineticMineral optional rate-law parameters (reaction_mineral.F90:699-870): Temkin constant, mineral scale factor,
     # affinity power and threshold, rate limiter, Arrhenius activation energy
+    # RRadioactiveDecay (reaction.F90:4607-4690): the first-order A -> B reaction of general-reaction.in as a decay reaction
+    'decay_ab': ('regression_tests/ascem/batch/general-reaction.in', 'Initial',
+                 [('  GENERAL_REACTION\n    REACTION A(aq) <-> B(aq)\n    FORWARD_RATE 1.15741d-6 ! 0.1 1/d\n    BACKWARD_RATE 0.d0\n  /',
+                   '  RADIOACTIVE_DECAY_REACTION\n    REACTION A(aq) <-> B(aq)\n    HALF_LIFE 6.9314718056 d\n  /')]),
+    # RKineticSurfCplx (reaction_surf_complex.F90:938-1137): the 300A surface complexation reaction (reaction 1, on kinetic
+    # mineral 1 = Calcite) with forward / backward rates instead of equilibrium
+    'hanford300a_kinsrf': ('regression_tests/default/543/543_hanford_srfcplx_base.in', 'groundwater',
+                           [('      MINERAL Calcite\n', '      KINETIC\n      COMPLEX_KINETICS\n        >SOUO2OH\n          FORWARD_RATE_CONSTANT 2.d-3\n'
+                             '          BACKWARD_RATE_CONSTANT 1.d-4\n        /\n        >SOHUO2CO3\n          FORWARD_RATE_CONSTANT 5.d-2\n'
+                             '          BACKWARD_RATE_CONSTANT 2.d-4\n        /\n      /\n      MINERAL Calcite\n')]),
     'calcite_rate_laws': ('regression_tests/ascem/batch/calcite-kinetics.in', 'initial',
                           [('      RATE_CONSTANT 1.d-13 mol/cm^2-sec\n',
                             '      RATE_CONSTANT 1.d-13 mol/cm^2-sec\n      ACTIVATION_ENERGY 40.d0\n      AFFINITY_THRESHOLD 1.d-3\n'
@@ -155,6 +168,14 @@ def time_block(path):
         m = re.match(r'\s*MAX_STEPS\s+(-?\d+)', line)
         if m:
             out['MAX_STEPS'] = int(m.group(1))
+    # NEWTON_SOLVER TRANSPORT card: RTOL / ATOL / STOL (solver.F90:842-851)
+    text = open(path).read()
+    m = re.search(r'^NEWTON_SOLVER\s+TRANSPORT(.*?)^/', text, re.M | re.S)
+    if m:
+        for key in ('RTOL', 'ATOL', 'STOL'):
+            mm = re.search(r'^\s*%s\s+(\S+)' % key, m.group(1), re.M)
+            if mm:
+                out[key] = float(mm.group(1).lower().replace('d', 'e'))
     return out
 
 
@@ -170,6 +191,9 @@ def main():
         d, t, orc, st, xx, nit, cst = kat.initial_cell(path, constraint=constraint, isothermal=name not in NON_ISOTHERMAL)
         base = {f: [repr(float(x)) for x in st[f][:, 0]] for f in abi.FIELDS
                 if f not in ('DTOTAL', 'DTOTAL_SORB_EQ')}
+        if name == 'hanford300a_kinsrf':
+            # a state with sorbed kinetic complexes (the deck starts from none): S^k = 2 % and 5 % of the site density
+            base['KINSRFCPLX_CONC'] = [repr(0.02 * float(t.srfcplxrxn_site_density[0])), repr(0.05 * float(t.srfcplxrxn_site_density[0]))]
         from pflotran_b200.chem.setup import constraint_arrays, mineral_arrays
         ctype, conc, cid, guess = constraint_arrays(t, d.constraints[constraint])
         vf, area = mineral_arrays(t, d.constraints[constraint])

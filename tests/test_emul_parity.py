@@ -15,8 +15,9 @@ WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_
 # fixtures that reach the branches no reference batch deck exercises (tests/golden/make_fixtures.py: VARIANTS and the
 # prefactor / non-isothermal / 22-primary decks): NEWTON activity algorithm + activity of water, free-site inner Newton,
 # Langmuir / Freundlich isotherms, Temkin / scale factor / affinity power / threshold / rate limiter / Arrhenius, mineral
-# prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes)
-BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem']
+# prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes), general (forward / backward rate)
+# reactions, radioactive decay, kinetic surface complexation
+BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf']
 WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
 GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 
@@ -222,13 +223,22 @@ def test_inactive_cells_and_l2g():
 def test_packer_rejects_unsupported():
     w = synth.Workload('calcite')
     d = abi.make_desc(w.tables)
-    for fld in ['nactive_gas', 'nimmobile', 'ncoll', 'ngeneral_rxn', 'nradiodecay_rxn', 'nmicrobial_rxn',
+    for fld in ['nactive_gas', 'nimmobile', 'ncoll', 'nmicrobial_rxn',
                 'nimmobile_decay_rxn', 'has_sandbox', 'has_clm', 'has_solid_solution', 'co2_flow_mode',
-                'numerical_derivatives', 'nkinsrfcplxrxn']:
+                'numerical_derivatives']:
         setattr(d, fld, 1)
         rc, msg = pack_status(d)
         assert rc == abi.RXN_ERR_UNSUPPORTED and 'outside the B200 path' in msg, fld
         setattr(d, fld, 0)
+    # counts of the supported rate reactions without their tables, and more kinetic surface complexation reactions than the
+    # reference's state holds
+    for fld in ['ngeneral_rxn', 'nradiodecay_rxn', 'nkinsrfcplxrxn']:
+        setattr(d, fld, 1)
+        assert pack_status(d)[0] == abi.RXN_ERR_INVALID, fld
+        setattr(d, fld, 0)
+    d.nkinsrfcplxrxn = 2
+    assert pack_status(d)[0] == abi.RXN_ERR_UNSUPPORTED
+    d.nkinsrfcplxrxn = 0
     assert pack_status(d)[0] == abi.RXN_OK
     d.struct_size = 8
     assert pack_status(d)[0] == abi.RXN_ERR_INVALID
@@ -300,7 +310,7 @@ class _EmuGI:
         return self.st
 
 
-@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral'])
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction'])
 def test_time_stepped_device_code_hits_reference_gold(name):
     """The device routines behind rxn_fixed_accum / update_auxvars / residual_jacobian_blocks / update_kinetic_state
     (host compilation) driven through the reference's 1-cell global-implicit time loop reproduce
@@ -311,6 +321,14 @@ def test_time_stepped_device_code_hits_reference_gold(name):
     w = synth.Workload(name)
     t, be, st, xx, nit, cst = kat.initial_cell_from_fixture(w, backend=_EmuBackend(w.tables))
     assert gi_driver.check_time_stepped_gold(w, _EmuGI(t, st), t, xx) >= 1
+
+
+def test_radioactive_decay_device_code_closed_form():
+    import gi_driver
+    import kat
+    w = synth.Workload('decay_ab')
+    t, be, st, xx, nit, cst = kat.initial_cell_from_fixture(w, backend=_EmuBackend(w.tables))
+    gi_driver.check_decay_closed_form(w, _EmuGI(t, st), t, xx)
 
 
 @pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite'])

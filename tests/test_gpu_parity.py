@@ -15,8 +15,9 @@ WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_
 # fixtures that reach the branches no reference batch deck exercises (tests/golden/make_fixtures.py: VARIANTS and the
 # prefactor / non-isothermal / 22-primary decks): NEWTON activity algorithm + activity of water, free-site inner Newton,
 # Langmuir / Freundlich isotherms, Temkin / scale factor / affinity power / threshold / rate limiter / Arrhenius, mineral
-# prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes)
-BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem']
+# prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes), general (forward / backward rate)
+# reactions, radioactive decay, kinetic surface complexation
+BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf']
 WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
 GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 
@@ -336,7 +337,7 @@ def test_ascem_speciation_gpu_hits_reference_kat():
     assert kat.check_speciation_kat(w, t, cst, nit) == 2 * 22 + 157
 
 
-@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral'])
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction'])
 def test_time_stepped_gpu_hits_reference_gold(name):
     """rxn_fixed_accum_batch -> rxn_update_auxvars_batch -> rxn_residual_jacobian_blocks_batch -> block solve ->
     rxn_update_kinetic_state_batch, stepped as the reference's 1-cell global-implicit run (tests/gi_driver.py), reproduce the
@@ -359,6 +360,17 @@ def test_time_stepped_gpu_hits_reference_gold(name):
     for f in ('PRI_MOLAL', 'TOTAL', 'MNRL_VOLFRAC', 'MNRL_RATE'):
         if s[f].shape[0]:
             assert (s[f][:, 0] == s[f][:, 1]).all()
+
+
+def test_radioactive_decay_gpu_closed_form():
+    """RRadioactiveDecay on the GPU through the C ABI: 500 backward-Euler steps hit A_0 / (1 + k dt)^500 at 1e-12."""
+    import gi_driver
+    import kat
+    w = synth.Workload('decay_ab')
+    t, be, st, xx, nit, cst = kat.initial_cell_from_fixture(w, backend=_GpuBackend(w.tables))
+    rx = rt.Reaction(t)
+    rz = rt.Realization(rx, 1)
+    gi_driver.check_decay_closed_form(w, gi_driver.DeviceGI(rz, st), t, xx)
 
 
 @pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite'])

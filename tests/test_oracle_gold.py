@@ -40,7 +40,7 @@ def test_gold_initial_speciation(name):
     _check(name)
 
 
-@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral'])
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction'])
 def test_gold_time_stepped(name):
     """Kinetic side of the oracle (RTAccumulation, RKineticMineral, RTotalSorbKD, RUpdateKineticState and the
     accumulation/reaction Jacobian blocks) pinned to the reference's time-stepped gold files through the 1-cell
@@ -50,6 +50,14 @@ def test_gold_time_stepped(name):
     w = synth.Workload(name)
     t, orc, st, xx, nit, cst = kat.initial_cell_from_fixture(w)
     assert gi_driver.check_time_stepped_gold(w, gi_driver.OracleGI(t, st), t, xx) >= 1
+
+
+def test_radioactive_decay_closed_form():
+    """RRadioactiveDecay through the 1-cell global-implicit loop: 500 backward-Euler steps hit A_0 / (1 + k dt)^500 at 1e-12."""
+    import gi_driver
+    w = synth.Workload('decay_ab')
+    t, orc, st, xx, nit, cst = kat.initial_cell_from_fixture(w)
+    gi_driver.check_decay_closed_form(w, gi_driver.OracleGI(t, st), t, xx)
 
 
 def test_ascem_22_primaries_164_complexes_kat():
