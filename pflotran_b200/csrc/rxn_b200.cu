@@ -77,6 +77,7 @@ struct RxnState {
   cudaEvent_t ev_in[NCHUNK] = {}, ev_k[NCHUNK] = {};
   int flux_generic = 0;    // RXN_FLUX_GENERIC=1: flux Jacobian through the run-time-n kernel (tests)
   int gi_kernel = 0;       // residual/Jacobian blocks: 0 auto (resident-lane layout if the tables allow it), 1 thread per cell
+  unsigned int *d_fail = nullptr;   // OR of the cell flags of the running global-implicit launch (DevState::fail)
 };
 
 // Row view of a connection list + the flux coefficients of the current flow field (rxn_flux.h)
@@ -156,6 +157,32 @@ int check_launch(RxnState *s, bool timed) {
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
   if (timed) CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+  return RXN_OK;
+}
+
+// Global-implicit entry points: the cells OR their flags into one device word (rxn_device.cuh: report_cell_flags).  The
+// reference stops in these cases (activity-coefficient Newton diverged, a sorption iteration that never ends) or would go on
+// with NaNs; here the call returns RXN_ERR_CELL_FAILED with the flags in rxn_last_error.
+// host-buffer entry points: every l2g entry must name a cell of the state (device-pointer variants are not checked)
+int check_l2g(const RxnState *s, const int32_t *l2g, int64_t nlocal) {
+  if (!l2g) return RXN_OK;
+  for (int64_t i = 0; i < nlocal; ++i)
+    if (l2g[i] < 0 || l2g[i] >= s->ncells) return fail(RXN_ERR_INVALID, "l2g[%lld] = %d is outside the state's %lld cells", (long long)i, l2g[i], s->ncells);
+  return RXN_OK;
+}
+int begin_cell_flags(RxnState *s) {
+  if (!s->d_fail) { CU(cudaMalloc(&s->d_fail, sizeof(unsigned int))); s->S.fail = s->d_fail; }
+  CU(cudaMemsetAsync(s->d_fail, 0, sizeof(unsigned int), s->stream));
+  return RXN_OK;
+}
+int end_cell_flags(RxnState *s, const char *what) {           // after the stream has been synchronised
+  unsigned int fl = 0;
+  CU(cudaMemcpy(&fl, s->d_fail, sizeof fl, cudaMemcpyDeviceToHost));
+  if (fl != 0)
+    return fail(RXN_ERR_CELL_FAILED, "%s: at least one cell failed (flags 0x%x:%s%s%s%s)", what, fl,
+                (fl & RXN_FLAG_ACT_DIVERGED) ? " activity-coefficient iteration diverged" : "",
+                (fl & RXN_FLAG_CAPPED) ? " sorption iteration capped" : "", (fl & RXN_FLAG_NONFINITE) ? " non-finite result" : "",
+                (fl & RXN_FLAG_LU_ZERO_ROW) ? " singular matrix" : "");
   return RXN_OK;
 }
 
@@ -266,6 +293,7 @@ int rxn_state_destroy(RxnState *s) {
   for (int f = 0; f < RXN_F_COUNT; ++f) if (s->S.f[f]) cudaFree(s->S.f[f]);
   if (s->d_active) cudaFree(s->d_active);
   if (s->d_counter) cudaFree(s->d_counter);
+  if (s->d_fail) cudaFree(s->d_fail);
   if (s->h2d) cudaStreamDestroy(s->h2d);
   if (s->d2h) cudaStreamDestroy(s->d2h);
   for (int c = 0; c < RxnState::NCHUNK; ++c) {
@@ -440,6 +468,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
                     int32_t *iters_out, int32_t *flags_out) {
   if (!s || !tran_xx || nlocal < 0 || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
+  { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
   CU(cudaSetDevice(s->t->device));
   const int n = s->t->h.naq;
   void *d_xx, *d_l2g = nullptr, *d_it, *d_fl;
@@ -464,35 +493,47 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
         CU(cudaEventCreateWithFlags(&s->ev_k[c], cudaEventDisableTiming));
       }
     }
-    if (!s->d_counter) CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
-    CU(cudaStreamSynchronize(s->stream));                       // the l2g copy above / earlier work on the scratch buffers
+    // an error inside the pipeline must not leave copies or kernels running on the caller's tran_xx / iters / flags:
+    // drain the three streams before returning
+    auto drain = [&]() { cudaStreamSynchronize(s->h2d); cudaStreamSynchronize(s->stream); cudaStreamSynchronize(s->d2h); };
+#define CUP(call)                                                                              \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      drain();                                                                                  \
+      return fail(RXN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    }                                                                                           \
+  } while (0)
+    if (!s->d_counter) CUP(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+    CUP(cudaStreamSynchronize(s->stream));                       // the l2g copy above / earlier work on the scratch buffers
     const int64_t chunk = (((nlocal + RxnState::NCHUNK - 1) / RxnState::NCHUNK) + 63) / 64 * 64;
     int nch = 0;
     for (int64_t off = 0; off < nlocal; off += chunk, ++nch) {
       const int64_t len = std::min<int64_t>(chunk, nlocal - off);
-      CU(cudaMemcpyAsync((double *)d_xx + off * n, tran_xx + off * n, (size_t)len * n * 8, cudaMemcpyHostToDevice, s->h2d));
-      CU(cudaEventRecord(s->ev_in[nch], s->h2d));
+      CUP(cudaMemcpyAsync((double *)d_xx + off * n, tran_xx + off * n, (size_t)len * n * 8, cudaMemcpyHostToDevice, s->h2d));
+      CUP(cudaEventRecord(s->ev_in[nch], s->h2d));
     }
-    CU(cudaEventRecord(s->ev0, s->stream));
+    CUP(cudaEventRecord(s->ev0, s->stream));
     int c = 0;
     for (int64_t off = 0; off < nlocal; off += chunk, ++c) {
       const int64_t len = std::min<int64_t>(chunk, nlocal - off);
-      CU(cudaStreamWaitEvent(s->stream, s->ev_in[c], 0));
+      CUP(cudaStreamWaitEvent(s->stream, s->ev_in[c], 0));
       rc = lane_launch_react(t->lane, t->h, t->d_blob, s->S, (double *)d_xx + off * n, d_l2g ? (const int32_t *)d_l2g + off : nullptr,
                              len, dt, dt_mode, (int32_t *)d_it + off, (int32_t *)d_fl + off, s->d_counter, s->stream, d_l2g ? 0 : off);
-      if (rc != RXN_OK) return fail(rc, "resident-lane kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      if (rc != RXN_OK) { drain(); return fail(rc, "resident-lane kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
       ++g_launches;
-      CU(cudaEventRecord(s->ev_k[c], s->stream));
-      CU(cudaStreamWaitEvent(s->d2h, s->ev_k[c], 0));
-      CU(cudaMemcpyAsync(tran_xx + off * n, (double *)d_xx + off * n, (size_t)len * n * 8, cudaMemcpyDeviceToHost, s->d2h));
-      if (iters_out) CU(cudaMemcpyAsync(iters_out + off, (int32_t *)d_it + off, (size_t)len * 4, cudaMemcpyDeviceToHost, s->d2h));
-      if (flags_out) CU(cudaMemcpyAsync(flags_out + off, (int32_t *)d_fl + off, (size_t)len * 4, cudaMemcpyDeviceToHost, s->d2h));
+      CUP(cudaEventRecord(s->ev_k[c], s->stream));
+      CUP(cudaStreamWaitEvent(s->d2h, s->ev_k[c], 0));
+      CUP(cudaMemcpyAsync(tran_xx + off * n, (double *)d_xx + off * n, (size_t)len * n * 8, cudaMemcpyDeviceToHost, s->d2h));
+      if (iters_out) CUP(cudaMemcpyAsync(iters_out + off, (int32_t *)d_it + off, (size_t)len * 4, cudaMemcpyDeviceToHost, s->d2h));
+      if (flags_out) CUP(cudaMemcpyAsync(flags_out + off, (int32_t *)d_fl + off, (size_t)len * 4, cudaMemcpyDeviceToHost, s->d2h));
     }
-    CU(cudaEventRecord(s->ev1, s->stream));
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s->d2h));
-    CU(cudaStreamSynchronize(s->stream));
+    CUP(cudaEventRecord(s->ev1, s->stream));
+    CUP(cudaGetLastError());
+    CUP(cudaStreamSynchronize(s->d2h));
+    CUP(cudaStreamSynchronize(s->stream));
     CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+#undef CUP
     return RXN_OK;
   }
   CU(cudaMemcpyAsync(d_xx, tran_xx, (size_t)nlocal * n * 8, cudaMemcpyHostToDevice, s->stream));
@@ -519,16 +560,19 @@ int rxn_update_auxvars_batch(RxnState *s, const double *xx_loc, int update_act_c
     if (rc != RXN_OK) return rc;
     CU(cudaMemcpyAsync(d_xx, xx_loc, (size_t)s->ncells * t->h.naq * 8, cudaMemcpyHostToDevice, s->stream));
   }
+  { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
   const int threads = t->nvariant <= 8 ? 128 : 64;
   const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
   RXN_DISPATCH(t->nvariant, run_update_auxvars, L, t->h, (const double *)t->d_blob, s->S, (const double *)d_xx, update_act_coefs);
-  return check_launch(s, true);
+  { const int rcl = check_launch(s, true); if (rcl != RXN_OK) return rcl; }
+  return end_cell_flags(s, "RTUpdateAuxVars");
 }
 
 int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int64_t nlocal, double *accum_out) {
   if (!s || !accum_out || nlocal < 0) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
+  { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
   const int n = t->h.naq;
@@ -544,6 +588,7 @@ int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int
     CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
   }
   CU(cudaMemsetAsync(d_out, 0, (size_t)nlocal * n * 8, s->stream));
+  { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
   const int threads = t->nvariant <= 8 ? 128 : 64;
   const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
@@ -554,7 +599,7 @@ int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-  return RXN_OK;
+  return end_cell_flags(s, "RTUpdateFixedAccumulation");
 }
 
 static int launch_residual_jacobian(RxnState *s, const int32_t *d_l2g, int64_t nlocal, double dt, double *d_res, double *d_jac) {
@@ -579,27 +624,32 @@ int rxn_residual_jacobian_blocks_batch_device(RxnState *s, const int32_t *d_l2g,
   if (!s || nlocal < 0 || !(dt > 0.0) || (!d_res && !d_jac)) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
   CU(cudaSetDevice(s->t->device));
+  { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
   int rc = launch_residual_jacobian(s, d_l2g, nlocal, dt, d_res, d_jac);
   if (rc != RXN_OK) return rc;
-  return check_launch(s, true);
+  { const int rcl = check_launch(s, true); if (rcl != RXN_OK) return rcl; }
+  return end_cell_flags(s, "RTResidual/RTJacobian blocks");
 }
 
 int rxn_update_auxvars_batch_device(RxnState *s, const double *d_xx_loc, int update_act_coefs) {
   if (!s) return fail(RXN_ERR_INVALID, "null state");
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
+  { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
   const int threads = t->nvariant <= 8 ? 128 : 64;
   const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
   RXN_DISPATCH(t->nvariant, run_update_auxvars, L, t->h, (const double *)t->d_blob, s->S, d_xx_loc, update_act_coefs);
-  return check_launch(s, true);
+  { const int rcl = check_launch(s, true); if (rcl != RXN_OK) return rcl; }
+  return end_cell_flags(s, "RTUpdateAuxVars");
 }
 
 int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt, double *res_out,
                                        double *jac_out) {
   if (!s || nlocal < 0 || !(dt > 0.0) || (!res_out && !jac_out)) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
+  { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
   const int n = t->h.naq;
@@ -611,6 +661,7 @@ int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t 
     if ((rc = ensure_scratch(s, 1, (size_t)nlocal * 4, &d_l2g)) != RXN_OK) return rc;
     CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
   }
+  { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
   if ((rc = launch_residual_jacobian(s, (const int32_t *)d_l2g, nlocal, dt, (double *)d_res, (double *)d_jac)) != RXN_OK) return rc;
   CU(cudaEventRecord(s->ev1, s->stream));
@@ -619,7 +670,7 @@ int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t 
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-  return RXN_OK;
+  return end_cell_flags(s, "RTResidual/RTJacobian blocks");
 }
 
 int rxn_residual_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt, double *res_out) {
@@ -640,6 +691,7 @@ int rxn_equilibrate_constraint_batch(RxnState *s, const int32_t *constraint_type
   const int n = t->h.naq;
   if (conc_stride != 0 && conc_stride < n) return fail(RXN_ERR_INVALID, "conc_stride must be 0 or >= naqcomp");
   if (nlocal == 0) return RXN_OK;
+  { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
   for (int i = 0; i < n; ++i) {
     if (constraint_type[i] == RXN_CONSTRAINT_MINERAL && (constraint_id[i] < 1 || constraint_id[i] > t->h.mnrl.n))
       return fail(RXN_ERR_INVALID, "constraint %d: mineral id %d out of range", i + 1, constraint_id[i]);
@@ -686,11 +738,13 @@ int rxn_update_kinetic_state_batch(RxnState *s, double dt) {
   if (!s || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
+  { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
   const int threads = 128;
   const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
   RXN_DISPATCH(t->nvariant, run_update_kinetic_state, L, t->h, (const double *)t->d_blob, s->S, dt);
-  return check_launch(s, true);
+  { const int rcl = check_launch(s, true); if (rcl != RXN_OK) return rcl; }
+  return end_cell_flags(s, "RTUpdateKineticState");
 }
 
 int rxn_timer_start(RxnState *s) {

@@ -37,6 +37,19 @@ __device__ __forceinline__ double &G(const DevState &S, int field, long long row
   return S.f[field][row * S.ld + cell];
 }
 
+// A cell of a global-implicit entry point raised a flag the reference would stop on (activity-coefficient Newton diverged,
+// reaction.F90:3864; free-site / ion-exchange iteration that never ends; non-finite result): OR it into the launch's word, the
+// entry point then returns RXN_ERR_CELL_FAILED.  (RReact reports per cell through flags_out instead.)
+__device__ __forceinline__ void report_cell_flags(const DevState &S, int flags) {
+  if (flags != 0 && S.fail) {
+#ifdef __CUDA_ARCH__
+    atomicOr(S.fail, (unsigned int)flags);
+#else
+    __atomic_fetch_or(S.fail, (unsigned int)flags, __ATOMIC_RELAXED);
+#endif
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // logK at the cell's T (and P): reaction_aux.F90:1461-1488 (5-term fit), :1529-1571 (hpt).
 // The reference overwrites the shared tables per cell (reaction.F90:5433-5524); here it is a
@@ -1022,6 +1035,8 @@ __device__ void cell_update_auxvars(const Tab &T, const DevState &S, long long c
   if (update_act_coefs) activity_coefficients<N>(T, S, c);
   auxvar_compute<N>(T, S, c, dtot, dsorb);
   store_cell<N>(T, S, c, dtot, dsorb);
+  for (int k = 0; k < n; ++k) if (!isfinite(c.total[k])) c.flags |= RXN_FLAG_NONFINITE;
+  report_cell_flags(S, c.flags);
 }
 
 // RTUpdateFixedAccumulation (reactive_transport.F90:786-843)
@@ -1040,8 +1055,10 @@ __device__ void cell_fixed_accum(const Tab &T, const DevState &S, long long i, c
     double r = psv_t * c.total[k];
     if (T.h->neqsorb > 0) r = r + c.tsorb[k] * c.volume;
     accum_out[i * n + k] = r;
+    if (!isfinite(r)) c.flags |= RXN_FLAG_NONFINITE;
   }
   store_cell<N>(T, S, c, dtot, dsorb);
+  report_cell_flags(S, c.flags);
 }
 
 // accumulation + reaction loops of RTResidualNonFlux (reactive_transport.F90:2545-2586, 2735-2758)
@@ -1089,9 +1106,11 @@ __device__ void cell_residual_jacobian(const Tab &T, const DevState &S, long lon
   }
   if (tab.nkinrxn > 0) kinetic_surfcplx<N>(T, S, c, dt, Res2, J2, deriv);
   if (tab.ngen > 0) general_reaction<N>(T, c, Res2, J2, deriv);
+  for (int k = 0; k < n; ++k) if (!isfinite(Res[k] + Res2[k])) c.flags |= RXN_FLAG_NONFINITE;
   if (res_out) for (int k = 0; k < n; ++k) res_out[i * n + k] = Res[k] + Res2[k];
   if (jac_out) for (int e = 0; e < n * n; ++e) jac_out[i * (long long)(n * n) + e] = J[e] + J2[e];
   store_cell<N>(T, S, c, nullptr, nullptr);   // totals + warm-start free sites stay consistent
+  report_cell_flags(S, c.flags);
 }
 
 // RTUpdateKineticState loop (reactive_transport.F90:692-705) = RUpdateKineticState (reaction.F90:5320-5429)
@@ -1134,6 +1153,8 @@ __device__ void cell_update_kinetic_state(const Tab &T, const DevState &S, long 
       G(S, RXN_F_KINSRFCPLX_CONC, icplx, cell) = G(S, RXN_F_KINSRFCPLX_CONC_KP1, icplx, cell);
     }
   }
+  for (int im = 0; im < tab.nkin; ++im) if (!isfinite(G(S, RXN_F_MNRL_VOLFRAC, im, cell))) c.flags |= RXN_FLAG_NONFINITE;
+  report_cell_flags(S, c.flags);
 }
 
 // RTotalSorbMultiRateAsEQ — reaction_surf_complex.F90:506-562

@@ -1199,6 +1199,19 @@ LANE_DEV void lane_gi_cell(const LaneTab &lt, Lane<N, G> &c, const DevState &S, 
   }
   grp_sync<G>(c.gm);
   // outputs
+  {
+    bool bad = false;
+#pragma unroll 1
+    for (int i = c.l; i < n; i += G) if (!isfinite(tsm[bcol + i * brow])) bad = true;
+    int fl = c.flags | (bad ? RXN_FLAG_NONFINITE : 0);
+    if (fl != 0 && S.fail) {
+#ifndef RXN_LANE_HOST
+      atomicOr(S.fail, (unsigned int)fl);
+#else
+      __atomic_fetch_or(S.fail, (unsigned int)fl, __ATOMIC_RELAXED);
+#endif
+    }
+  }
   if (res_out) {
 #pragma unroll 1
     for (int i = c.l; i < n; i += G) res_out[item * n + i] = tsm[bcol + i * brow];

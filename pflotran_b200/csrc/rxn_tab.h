@@ -62,6 +62,7 @@ struct DevState {
   long long ld;
   long long ncells;
   const uint8_t *active;   // NULL = all active
+  unsigned int *fail;      // OR of the RXN_FLAG_* raised by the cells of a global-implicit launch (NULL: not collected)
 };
 
 // hard limits of the per-thread scratch (tables beyond them are rejected at create time)

@@ -34,10 +34,12 @@ struct Emu {
   int nv;
 };
 
+static unsigned int g_cell_flags = 0;   // DevState::fail of the emulated launches (OR of the cell flags)
 static DevState mk_state(const HostView *v, const uint8_t *active) {
   DevState S;
   for (int f = 0; f < RXN_F_COUNT; ++f) S.f[f] = v->f[f];
   S.ld = v->ld; S.ncells = v->ncells; S.active = active;
+  S.fail = &g_cell_flags;
   return S;
 }
 
@@ -316,6 +318,7 @@ int emu_pack_status(const RxnTablesDesc *d, char *err, int errlen) {
   if (rc != RXN_OK && err && errlen > 0) { strncpy(err, R.err.c_str(), errlen - 1); err[errlen - 1] = 0; }
   return rc;
 }
+unsigned int emu_cell_flags(int reset) { const unsigned int v = g_cell_flags; if (reset) g_cell_flags = 0; return v; }
 int emu_field_rows(void *h, int f) { return ((Emu *)h)->R.rows[f]; }
 void emu_set_maxit(void *h, int maxit) { ((Emu *)h)->R.h.maxit = maxit; }
 
