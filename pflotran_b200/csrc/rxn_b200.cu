@@ -136,12 +136,17 @@ __global__ void k_broadcast(double *dst, long long ld, long long ncells, int row
   if (c >= ncells) return;
   for (int r = 0; r < rows; ++r) dst[r * ld + c] = vals[r];
 }
-// FP64 FMA throughput probe (roofline denominator measured on the box): 8 independent chains/thread
+// FP64 FMA throughput probe (roofline denominator measured on the box): 8 independent chains per thread, 4 rounds per loop
+// trip so that loop control is 3 % of the issue slots (round 1's probe spent 20 % on it and read 33.8 TFLOP/s where the
+// DFMA pipe delivers 36.6 = 98 % of 148 SMs x 64 lanes x 2 x 1.965 GHz, profiles/r02_ubench_tmem.txt)
 __global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-  for (int i = 0; i < iters; ++i) {
-    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
   }
   out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
@@ -769,7 +774,7 @@ int rxn_probe_fp64(RxnState *s, double *tflops) {
   CU(cudaSetDevice(s->t->device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, s->t->device));
-  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 17;
   void *out;
   int rc = ensure_scratch(s, 3, (size_t)blocks * threads * 8, &out);
   if (rc != RXN_OK) return rc;

@@ -21,7 +21,7 @@ namespace rxn {
 // tensor-memory kernel shapes (rxn_tm_dev.cuh): X(N, QUADS, G) = matrix dimension (<= 15), 32-cell quads per CTA, member warps
 // per cell; per N the first shape whose vectors fit in shared memory is used (keep in sync with TM_SHAPES in the Makefile)
 #define RXN_TM_SHAPES(X) \
-  X(15, 4, 2) X(15, 3, 2) X(15, 2, 2) X(15, 4, 4) X(15, 3, 4) X(15, 2, 4) X(15, 4, 1)
+  X(15, 4, 2) X(15, 3, 2) X(15, 2, 2) X(15, 4, 4) X(15, 3, 4) X(15, 2, 4) X(15, 4, 3) X(15, 3, 3) X(15, 4, 1)
 
 struct LaneKernel {
   LanePlan plan_tm;      // tensor-memory kernel (preferred when usable)

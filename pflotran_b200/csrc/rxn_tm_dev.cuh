@@ -249,6 +249,7 @@ template <int CPB, int G, class C> TM_DEV double grp_sum(C &c, double v) {
   grp_gather<CPB, G>(c, v, o);
   if (G == 1) return o[0];
   if (G == 2) return o[0] + o[G - 1];
+  if (G == 3) return (o[0] + o[1]) + o[G - 1];
   return (o[0] + o[2 % G]) + (o[1 % G] + o[3 % G]);
 }
 template <int CPB, int G, class C> TM_DEV double grp_max(C &c, double v) {
@@ -521,7 +522,7 @@ TM_DEV void tm_srf_rxn(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, int i
 #pragma unroll 1
       for (int p = TI(lt, lt.i_sptr + icplx); p < p1; ++p) {
         const int row = TI(lt, lt.i_sid + p);
-        if (G > 1 && (row & (G - 1)) != c.l) continue;
+        if (G > 1 && (row % G) != c.l) continue;
         const int o = c.vscr + row * CPB;
         tsm[o] = tsm[o] + TD(lt, lt.d_sst + p) * site_st * sc;
       }
@@ -542,7 +543,7 @@ TM_DEV void tm_srf_rxn(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, int i
 #pragma unroll 1
     for (int p = p0; p < p1; ++p) {
       const int row = TI(lt, lt.i_sid + p);
-      if (G > 1 && (row & (G - 1)) != c.l) continue;
+      if (G > 1 && (row % G) != c.l) continue;
       const double stp = TD(lt, lt.d_sst + p);
       const int o = tb + row * CPB;
       tsm[o] = tsm[o] + (stp * sc) * lv;
@@ -622,7 +623,7 @@ TM_DEV void tm_kinetic_mineral(const LaneTab &lt, Ctx<N, G> &c, bool keep) {
 #pragma unroll 1
     for (int p = p0; p < p1; ++p) {
       const int ip = TI(lt, lt.i_kid + p);
-      if (G > 1 && (ip & (G - 1)) != c.l) continue;            // owner member of primary ip
+      if (G > 1 && (ip % G) != c.l) continue;            // owner member of primary ip
       const double stp = TD(lt, lt.d_kst + p);
       tsm[c.vres + ip * CPB] = tsm[c.vres + ip * CPB] + stp * Im;
 #pragma unroll 1
@@ -651,6 +652,24 @@ TM_DEV void tm_kinetic_mineral(const LaneTab &lt, Ctx<N, G> &c, bool keep) {
 // by member 0.  A row swap cannot be an address swap (TMEM addresses are warp-uniform): each member exchanges its
 // column slice of rows k and imax through a select, visiting only the rows some lane of the warp pivots to
 // (300A: row 4 at step 0 in 87 % of the solves, otherwise no swap at all).
+// column slice [e0, e0 + W) of rows K and imax exchanged through a select; only the rows some lane of the warp pivots to are visited
+template <int N, int G, int K, int W>
+TM_DEV void tm_swap_slice(Ctx<N, G> &c, int e0, int imax) {
+  if (e0 + W <= K) return;                                      // the whole slice is dead
+  double pk[W], ri[W];
+  tm_ld<W>(c.tb, K, e0, pk);
+#pragma unroll 1
+  for (int i = K + 1; i < N; ++i) {
+    if (!warp_any(imax == i)) continue;
+    tm_ld<W>(c.tb, i, e0, ri);
+    const bool sel = imax == i;
+#pragma unroll
+    for (int e = 0; e < W; ++e) { const double a = ri[e], b = pk[e]; ri[e] = sel ? b : a; pk[e] = sel ? a : b; }
+    tm_st<W>(c.tb, i, e0, ri);
+  }
+  tm_st<W>(c.tb, K, e0, pk);
+}
+
 template <int N, int CPB, int G, int K>
 TM_DEV void tm_lu_step(Ctx<N, G> &c, double &best, int &imax) {
   constexpr int HALF = (K >= 8) ? 1 : 0;
@@ -659,24 +678,15 @@ TM_DEV void tm_lu_step(Ctx<N, G> &c, double &best, int &imax) {
   grp_argmax_last<CPB, G>(c, best, imax);                       // also orders step K-1's row updates before the loads below
   if (imax < 0) imax = K;
   if (warp_any(imax != K)) {
-    // swap rows K and imax from column K on (columns left of it are never read again)
-    constexpr int W = TM_LD / G;                                // slice width of a member
-    const int e0 = c.l * W;
-    if (e0 + W > K) {
-      double pk[W], ri[W];
-      tm_ld<W>(c.tb, K, e0, pk);
-#pragma unroll 1
-      for (int i = K + 1; i < N; ++i) {
-        if (!warp_any(imax == i)) continue;
-        tm_ld<W>(c.tb, i, e0, ri);
-        const bool sel = imax == i;
-#pragma unroll
-        for (int e = 0; e < W; ++e) { const double a = ri[e], b = pk[e]; ri[e] = sel ? b : a; pk[e] = sel ? a : b; }
-        tm_st<W>(c.tb, i, e0, ri);
-      }
-      tm_st<W>(c.tb, K, e0, pk);
-      tm_wait_st();
+    // swap rows K and imax from column K on (columns left of it are never read again): member l takes the column slice
+    // [e0, e0 + W) of both rows; slices of 16/G doubles, for G = 3: 8, 4, 4 (tcgen05 shapes are powers of two)
+    if (G == 3) {
+      if (c.l == 0) tm_swap_slice<N, G, K, 8>(c, 0, imax);
+      else tm_swap_slice<N, G, K, 4>(c, 4 + 4 * c.l, imax);
+    } else {
+      tm_swap_slice<N, G, K, TM_LD / (G == 3 ? 4 : G)>(c, c.l * (TM_LD / (G == 3 ? 4 : G)), imax);
     }
+    tm_wait_st();
     if (c.l == 0 && imax != K) tsm[c.vscr + imax * CPB] = tsm[c.vscr + K * CPB];
     warp_converge();
     grp_sync<G>(c);
@@ -752,8 +762,8 @@ TM_DEV bool tm_rsolve(const LaneTab &lt, Ctx<N, G> &c) {
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         const double av = fabs(r[j]), v = av * invm[j];
-        if (v > mx) mx = v;
-        if (av > mraw) mraw = av;
+        mx = fmax(mx, v);                                       // = if (v > mx) mx = v for the finite values the solve sees
+        mraw = fmax(mraw, av);
       }
       const double norm = 1.0 / ((mx > 1.0) ? mx : 1.0);
 #pragma unroll

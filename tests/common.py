@@ -147,8 +147,10 @@ def assert_state_close(st_a, st_b, rtol=RTOL, fields=STATE_FIELDS, cells=None, w
             sm = st_b['SEC_MOLAL'] if cells is None else st_b['SEC_MOLAL'][:, cells]
             mag = np.abs(st_b['PRI_MOLAL'] if cells is None else st_b['PRI_MOLAL'][:, cells]).copy()
             for k in range(tables.neqcplx):
+                # ... and sec_molal_k itself carries eps * sum_j |nu_kj| (see SEC_MOLAL below)
+                amp_k = max(1.0, sum(abs(st[k, q]) for q in range(1, ids[k, 0] + 1)))
                 for q in range(1, ids[k, 0] + 1):
-                    mag[ids[k, q] - 1] += abs(st[k, q]) * np.abs(sm[k])
+                    mag[ids[k, q] - 1] += abs(st[k, q]) * np.abs(sm[k]) * amp_k
             den = (st_b['DEN_KG'] if cells is None else st_b['DEN_KG'][:, cells]) * 1.0e-3
             scale = np.maximum(scale, mag * den)
         if f == 'SEC_MOLAL' and tables is not None and tables.neqcplx:

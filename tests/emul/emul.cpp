@@ -273,6 +273,7 @@ template <int N>
 static void tm_cells_g(const LaneJob &J, int G) {
   if (G == 1) tm_cells<N, 1>(J);
   else if (G == 2) tm_cells<N, 2>(J);
+  else if (G == 3) tm_cells<N, 3>(J);
   else tm_cells<N, 4>(J);
 }
 
@@ -284,7 +285,7 @@ int emu_react_tm(void *hh, const HostView *v, double *tran_xx, const uint8_t *ac
   DevState S = mk_state(v, active);
   LanePlan P;
   const int N = forceN >= e->R.h.naq ? forceN : (e->R.h.naq <= 12 ? 12 : 15);
-  if (G != 1 && G != 2 && G != 4) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4"); return RXN_ERR_INVALID; }
+  if (G != 1 && G != 2 && G != 3 && G != 4) { if (err) snprintf(err, errlen, "G must be 1, 2, 3 or 4"); return RXN_ERR_INVALID; }
   int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P, false, G);
   if (rc != RXN_OK || !P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
   LaneJob J{&P, e, &S, tran_xx, l2g, nlocal, dt, dt_mode, iters, flags};

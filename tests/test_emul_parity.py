@@ -64,7 +64,7 @@ def test_react_resident_lane(name, dt, mode, G):
 
 @pytest.mark.parametrize('name', LANE_WORKLOADS)
 @pytest.mark.parametrize('dt,mode', [(3600.0, abi.RXN_DT_CONSISTENT), (1.0, abi.RXN_DT_AS_WRITTEN)])
-@pytest.mark.parametrize('G', [1, 2, 4])
+@pytest.mark.parametrize('G', [1, 2, 3, 4])
 def test_react_tensor_memory_routines(name, dt, mode, G):
     """Routines of the tensor-memory kernel (rxn_tm_dev.cuh: J rows in the emulated TMEM lane, k-unrolled LU with select
     swaps, predicated trips, exchange-slot reductions) with G member warps per cell (host threads, one lane each),
@@ -82,7 +82,7 @@ def test_react_tensor_memory_routines(name, dt, mode, G):
     assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
 
 
-@pytest.mark.parametrize('G', [1, 2, 4])
+@pytest.mark.parametrize('G', [1, 2, 3, 4])
 def test_tensor_memory_iteration_cap_and_inactive(G):
     """Abnormal exit (iteration cap) in the predicated trip: the lane turns `closing`, redoes RTotal, then finishes."""
     w, cells = workload_cells('hanford300a_eq', 200)
