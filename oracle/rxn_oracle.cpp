@@ -29,6 +29,24 @@
 
 namespace {
 
+// Scratch of the per-cell routines: the Fortran uses automatic (stack) arrays (e.g. reaction.F90:3339-3346,
+// utility.F90:405); so does the port - the heap is only touched by chemistries beyond CAP entries.
+template <class T, int CAP> struct Stk {
+  T buf[CAP];
+  T *p;
+  size_t n;
+  explicit Stk(size_t n_, T v = T()) : p(n_ <= (size_t)CAP ? buf : new T[n_]), n(n_) { for (size_t i = 0; i < n; ++i) p[i] = v; }
+  ~Stk() { if (p != buf) delete[] p; }
+  Stk(const Stk &) = delete;
+  Stk &operator=(const Stk &) = delete;
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
+  T *data() { return p; }
+  T *begin() { return p; }
+  T *end() { return p + n; }
+  size_t size() const { return n; }
+};
+
 const double LOG_TO_LN = 2.30258509299;     // pflotran_constants.F90:48
 const double IDEAL_GAS_CONSTANT = 8.31446;  // pflotran_constants.F90:53
 
@@ -209,7 +227,7 @@ void init_auxvar(const Tables &t, AuxVar &a) {
 // ---------------------------------------------------------------- utility.F90:393-476
 int ludcmp(double *A, int N, int *indx) {  // A column-major N x N; returns 1 on all-zero row
   const double tiny = 1.0e-20;
-  std::vector<double> vv(N);
+  Stk<double, 32> vv(N);
 #define AA(i, j) A[(i) + (size_t)(j) * N]
   for (int i = 0; i < N; ++i) {
     double aamax = 0.0;
@@ -270,8 +288,8 @@ void lubksb(const double *A, int N, const int *indx, double *B) {
 
 // ---------------------------------------------------------------- reaction.F90:4835-4880
 int RSolve(double *Res, double *Jac, const double *conc, double *update, int n, bool use_log) {
-  std::vector<int> indices(n);
-  std::vector<double> rhs(n);
+  Stk<int, 32> indices(n);
+  Stk<double, 32> rhs(n);
   for (int i = 0; i < n; ++i) {
     double mx = 0.0;
     for (int j = 0; j < n; ++j) mx = std::max(mx, std::fabs(Jac[i + (size_t)j * n]));
@@ -329,7 +347,7 @@ void RActivityCoefficients(const Tables &t, AuxVar &a) {
       if (j + 1 != t.h2o_aq_id) sum_pri_molal = sum_pri_molal + a.pri_molal[j];
   }
   if (t.act_alg == RXN_ACT_COEF_ALGORITHM_NEWTON) {
-    std::vector<double> ln_conc(naq), ln_act(naq);
+    Stk<double, 32> ln_conc(naq), ln_act(naq);
     for (int j = 0; j < naq; ++j) { ln_conc[j] = std::log(a.pri_molal[j]); ln_act[j] = ln_conc[j] + std::log(a.pri_act_coef[j]); }
     double fpri = 0.0;
     for (int j = 0; j < naq; ++j) fpri = fpri + a.pri_molal[j] * t.Z[j] * t.Z[j];
@@ -429,7 +447,7 @@ void RActivityCoefficients(const Tables &t, AuxVar &a) {
 // ---------------------------------------------------------------- reaction.F90:4057-4158
 void RTotal(const Tables &t, AuxVar &a) {
   const int naq = t.naq;
-  std::vector<double> ln_conc(naq), ln_act(naq);
+  Stk<double, 32> ln_conc(naq), ln_act(naq);
   const double xmass = 1.0;
   const double den_kg_per_L = a.den_kg * xmass * 1.0e-3;
   for (int i = 0; i < naq; ++i) { ln_conc[i] = std::log(a.pri_molal[i]); ln_act[i] = ln_conc[i] + std::log(a.pri_act_coef[i]); }
@@ -464,7 +482,8 @@ void RTotalSorbEqSurfCplx1(const Tables &t, AuxVar &a, int irxn, double &externa
                            double *external_dtotal_sorb) {
   const int naq = t.naq;
   const double tol = 1.0e-12;
-  std::vector<double> ln_conc(naq), ln_act(naq), srfcplx_conc(t.srf.n, 0.0), dSx_dmi(naq);
+  Stk<double, 32> ln_conc(naq), ln_act(naq), dSx_dmi(naq);
+  Stk<double, 256> srfcplx_conc(t.srf.n, 0.0);
   for (int i = 0; i < naq; ++i) { ln_conc[i] = std::log(a.pri_molal[i]); ln_act[i] = ln_conc[i] + std::log(a.pri_act_coef[i]); }
   const std::vector<int> &cl = t.rxn_cplx[irxn];
   const int ncplx = (int)cl.size();
@@ -563,7 +582,7 @@ void RTotalSorbEqIonx(const Tables &t, AuxVar &a) {
     double omega;
     if (t.ionx_to_surf[irxn] > 0) omega = std::max(t.ionx_CEC[irxn] * a.mnrl_volfrac[t.ionx_to_surf[irxn] - 1], 1.0e-40);
     else omega = t.ionx_CEC[irxn];
-    std::vector<double> cation_X(naq, 0.0);
+    Stk<double, 32> cation_X(naq, 0.0);
     if (t.ionx_Zflag[irxn]) {
       int icomp = cat[0];
       double ref_cation_conc = a.pri_molal[icomp] * a.pri_act_coef[icomp];
@@ -669,7 +688,8 @@ void RTotalSorb(const Tables &t, AuxVar &a) {
 // ------------------------------------------------- reaction_surf_complex.F90:506-562
 void RTotalSorbMultiRateAsEQ(const Tables &t, AuxVar &a) {
   const int naq = t.naq;
-  std::vector<double> total_sorb_eq(naq), dtotal_sorb_eq((size_t)naq * naq);
+  Stk<double, 32> total_sorb_eq(naq);
+  Stk<double, 1024> dtotal_sorb_eq((size_t)naq * naq);
   for (int ikr = 0; ikr < t.nkinmr(); ++ikr) {
     int irxn = t.mr_rxn[ikr];
     std::fill(total_sorb_eq.begin(), total_sorb_eq.end(), 0.0);
@@ -715,7 +735,8 @@ void RAccumulationSorbDerivative(const Tables &t, const AuxVar &a, double tran_d
 // ------------------------------------------------- reaction_mineral.F90:564-1000
 void RKineticMineral(const Tables &t, AuxVar &a, double *Res, double *Jac, bool compute_derivative) {
   const int naq = t.naq, n = t.ncomp, ncplx_all = t.cplx.n;
-  std::vector<double> ln_conc(naq), ln_act(naq), ln_sec_act(ncplx_all);
+  Stk<double, 32> ln_conc(naq), ln_act(naq);
+  Stk<double, 512> ln_sec_act(ncplx_all);
   for (int i = 0; i < naq; ++i) { ln_conc[i] = std::log(a.pri_molal[i]); ln_act[i] = ln_conc[i] + std::log(a.pri_act_coef[i]); }
   for (int k = 0; k < ncplx_all; ++k) ln_sec_act[k] = std::log(a.sec_molal[k]) + std::log(a.sec_act_coef[k]);
   for (int im = 0; im < t.kin.n; ++im) a.mnrl_rate[im] = 0.0;
@@ -875,7 +896,8 @@ void RKineticMineral(const Tables &t, AuxVar &a, double *Res, double *Jac, bool 
 // ------------------------------------------------- reaction_surf_complex.F90:566-654
 void RMultiRateSorption(const Tables &t, AuxVar &a, double tran_dt, double *Res, double *Jac, bool compute_derivative) {
   const int naq = t.naq, n = t.ncomp;
-  std::vector<double> total_sorb_eq(naq), dtotal_sorb_eq((size_t)naq * naq);
+  Stk<double, 32> total_sorb_eq(naq);
+  Stk<double, 1024> dtotal_sorb_eq((size_t)naq * naq);
   const size_t blk = (size_t)(t.mr_ld + 1) * naq;
   for (int ikr = 0; ikr < t.nkinmr(); ++ikr)
     for (int i = 0; i < naq; ++i) a.kinmr_total_sorb[ikr * blk + i] = 0.0;
@@ -906,12 +928,12 @@ void RMultiRateSorption(const Tables &t, AuxVar &a, double tran_dt, double *Res,
 // reference's indices are in bounds, rxn_pack.h): isite = ikinrxn = 1, global complex id = position in the reaction.
 void RKineticSurfCplx(const Tables &t, AuxVar &a, double dt, double *Res, double *Jac, bool compute_derivative) {
   const int n = t.ncomp, naq = t.naq;
-  std::vector<double> ln_conc(naq), ln_act(naq);
+  Stk<double, 32> ln_conc(naq), ln_act(naq);
   for (int i = 0; i < naq; ++i) { ln_conc[i] = std::log(a.pri_molal[i]); ln_act[i] = ln_conc[i] + std::log(a.pri_act_coef[i]); }
   const int irxn = t.kin_rxn[0];
   const std::vector<int> &cplx = t.rxn_cplx[irxn];
   const int ncplx = (int)cplx.size();
-  std::vector<double> lnQ(t.srf.n, 0.0), Q(t.srf.n, 0.0);
+  Stk<double, 256> lnQ(t.srf.n, 0.0), Q(t.srf.n, 0.0);
   for (int k = 0; k < ncplx; ++k) {
     const int icplx = cplx[k];
     if (t.srf.h2oid[icplx] > 0) lnQ[icplx] = lnQ[icplx] + t.srf.h2ost[icplx] * a.ln_act_h2o;
@@ -947,7 +969,7 @@ void RKineticSurfCplx(const Tables &t, AuxVar &a, double dt, double *Res, double
     }
   }
   if (compute_derivative) {
-    std::vector<double> fac_sum(naq, 0.0);
+    Stk<double, 32> fac_sum(naq, 0.0);
     for (int k = 0; k < ncplx; ++k) {
       const int icplx = cplx[k];
       const double denominator = 1.0 + kb[icplx] * dt;
@@ -1001,7 +1023,7 @@ void RRadioactiveDecay(const Tables &t, AuxVar &a, double *Res, double *Jac, boo
 // ---------------------------------------------------------------- reaction.F90:4694-4831
 void RGeneral(const Tables &t, AuxVar &a, double *Res, double *Jac, bool compute_derivative) {
   const int n = t.ncomp, naq = t.naq;
-  std::vector<double> ln_conc(naq), ln_act(naq);
+  Stk<double, 32> ln_conc(naq), ln_act(naq);
   for (int i = 0; i < naq; ++i) { ln_conc[i] = std::log(a.pri_molal[i]); ln_act[i] = ln_conc[i] + std::log(a.pri_act_coef[i]); }
   for (int irxn = 0; irxn < t.ngen; ++irxn) {
     const double kf = t.gen_kf[irxn], kr = t.gen_kr[irxn];
@@ -1061,7 +1083,8 @@ void RReaction(const Tables &t, AuxVar &a, double tran_dt, double *Res, double *
 // ---------------------------------------------------------------- reaction.F90:3322-3511
 int RReact(Tables &t, AuxVar &a, double *tran_xx, double tran_dt, int dt_mode, int maxit, int *exit_reason) {
   const int n = t.ncomp, naq = t.naq;
-  std::vector<double> residual(n), J((size_t)n * n), prev_solution(n), new_solution(n), update(n), fixed_accum(n);
+  Stk<double, 32> residual(n), prev_solution(n), new_solution(n), update(n), fixed_accum(n);
+  Stk<double, 1024> J((size_t)n * n);
   int num_iterations = 0;
   *exit_reason = 0;
   for (int i = 0; i < naq; ++i) a.total[i] = tran_xx[i];
@@ -1127,7 +1150,8 @@ int RReact(Tables &t, AuxVar &a, double *tran_xx, double tran_dt, int dt_mode, i
 void RUpdateKineticState(const Tables &t, AuxVar &a, double tran_dt) {
   const int n = t.ncomp, naq = t.naq;
   if (t.kin.n > 0) {
-    std::vector<double> res(n, 0.0), jac((size_t)n * n, 0.0);
+    Stk<double, 32> res(n, 0.0);
+    Stk<double, 1024> jac((size_t)n * n, 0.0);
     RKineticMineral(t, a, res.data(), jac.data(), false);
     for (int im = 0; im < t.kin.n; ++im) {
       double delta_volfrac = a.mnrl_rate[im] * t.k_molar_vol[im] * tran_dt;
