@@ -46,9 +46,23 @@ WORKLOAD_DESC = {
     'calcite': 'example_problems/100_100_100 calcite chemistry (4 primaries, 5 complexes, 1 kinetic mineral)',
     'hpt_calcite': 'geothermal-hpt.dat calcite chemistry, per-cell T,P dependent logK',
 }
-# DRAM bytes per cell-update of the react kernel from the committed `ncu --set full` captures
-# (dram__bytes_read.sum + dram__bytes_write.sum over the cells of the profiled launch): profiles/r01_r9_lane_g2.metrics.csv
-NCU_DRAM_BYTES_PER_CELL = {'hanford300a_eq': (758.277120e6 + 1237.866e6) / 600000}
+# DRAM bytes per cell-update of the react kernel: a CONSTANT taken from the committed `ncu --set full` capture of the named kernel
+# (dram__bytes_read.sum + dram__bytes_write.sum over the cells of the profiled launch), not measured in the run; reported only
+# when the kernel the run used is the captured one (same name prefix), else null
+NCU_DRAM_BYTES_PER_CELL = {
+    'hanford300a_eq': [('tensor-memory N=15 cells/CTA=128', (932.234496e6 + 1454.456e6) / 600000, 'profiles/r02_f_tm_g4.metrics.txt'),
+                       ('resident-lane N=15 cells/CTA=64 lanes/cell=2', (758.277120e6 + 1237.866e6) / 600000,
+                        'profiles/r01_r9_lane_g2.metrics.csv')],
+}
+
+
+def ncu_traffic(workload, kernel_info, ncells):
+    for prefix, per_cell, src in NCU_DRAM_BYTES_PER_CELL.get(workload, []):
+        if kernel_info.startswith(prefix):
+            return per_cell * ncells, 'constant from the ncu --set full capture of this kernel (%s), per cell x cells of one launch; not measured in this run' % src
+    return None, 'no ncu capture of this kernel/workload committed'
+
+
 RESET_FIELDS = ['PRI_MOLAL', 'PRI_ACT_COEF', 'SEC_MOLAL', 'SEC_ACT_COEF', 'LN_ACT_H2O', 'TOTAL_SORB_EQ', 'FREE_SITE_CONC',
                 'EQIONX_REF_CATION_SORBED_CONC']
 
@@ -327,6 +341,8 @@ def run_ours(args):
         kern_s = kern_ms_max * 1e-3
         fp64_ach = wm['flop_eq_per_cell'] * n / kern_s / 1e12
         hbm_ach = wm['bytes_per_cell'] * n / kern_s / 1e9
+        kinfo = rz.react_kernel_info()
+        traffic, traffic_src = ncu_traffic(args.workload, kinfo, n)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -336,24 +352,20 @@ def run_ours(args):
                        'mean_newton_iterations': wm['mean_newton_iterations'], 'cells_with_nonreference_flags': bad_all,
                        'l2_policy': 'inputs (%.1f GB of cell state per GPU) larger than L2; no flush needed'
                                     % (n * wm['bytes_per_cell'] / 1e9),
-                       'kernel': rz.react_kernel_info()},
+                       'kernel': kinfo},
             'e2e': {'value': total_cells * args.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': nb,
                     'd2h_bytes_per_step': nb + 2 * n * 4},
             'gpu_launches': int(launches * world),
             'clocks': clocks,
             'roofline': {'bound': 'fp64', 'achieved': fp64_ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': fp64_ach / fp64_peak,
-                         'traffic': (NCU_DRAM_BYTES_PER_CELL[args.workload] * n if args.workload in NCU_DRAM_BYTES_PER_CELL
-                                     and not args.kernel else None),
+                         'traffic': traffic, 'traffic_source': traffic_src,
                          'note': 'FP64 CUDA-core path: achieved = flop-equivalents (SURVEY.md 8d, W=20 per exp/log/sqrt/pow) x cells '
                                  '/ react-kernel time (CUDA events); peak = DFMA probe measured in this run (rxn_probe_fp64)',
                          'kernel_ms': kern_ms_max, 'flop_eq_per_cell': wm['flop_eq_per_cell'],
                          'transcendentals_per_cell': wm['transcendentals_per_cell']},
             'roofline_hbm': {'bound': 'hbm', 'achieved': hbm_ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                              'frac': hbm_ach / peaks['hbm_gbs'],
-                             'traffic': (NCU_DRAM_BYTES_PER_CELL[args.workload] * n if args.workload in NCU_DRAM_BYTES_PER_CELL
-                                         and not args.kernel else None),
-                             'traffic_source': 'ncu --set full capture of this kernel, per cell x cells of one launch '
-                                               '(profiles/r01_r9_lane_g2.metrics.csv)', 'peak_source': peak_src,
+                             'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                              'bytes_per_cell': wm['bytes_per_cell']},
         }
         # CPU baseline: bounded sample on the host cores of this box

@@ -5,6 +5,7 @@
 // There is NO CPU fallback: without a usable CUDA device every entry point fails with
 // RXN_ERR_NO_DEVICE / RXN_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3 (dlopens the tool's injection library; a no-op without a profiler)
 
 #include <algorithm>
 #include <cmath>
@@ -37,6 +38,13 @@ int fail(int code, const char *fmt, ...) {
   g_err = buf;
   return code;
 }
+
+// NVTX ranges named after the reference's PetscLogEvents (logging.F90:327-381): a timeline of the GPU path reads like
+// the reference's -log_view
+struct Nvtx {
+  explicit Nvtx(const char *name) { nvtxRangePushA(name); }
+  ~Nvtx() { nvtxRangePop(); }
+};
 
 #define CU(call)                                                                              \
   do {                                                                                        \
@@ -460,6 +468,7 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
 
 int rxn_react_batch_device(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
                            int32_t *d_iters, int32_t *d_flags) {
+  Nvtx nvtx_("RTReact");
   if (!s || !d_xx || nlocal < 0 || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
   CU(cudaSetDevice(s->t->device));
@@ -471,6 +480,7 @@ int rxn_react_batch_device(RxnState *s, double *d_xx, const int32_t *d_l2g, int6
 
 int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nlocal, double dt, int dt_mode,
                     int32_t *iters_out, int32_t *flags_out) {
+  Nvtx nvtx_("RTReact");
   if (!s || !tran_xx || nlocal < 0 || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
   { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
@@ -556,6 +566,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
 }
 
 int rxn_update_auxvars_batch(RxnState *s, const double *xx_loc, int update_act_coefs) {
+  Nvtx nvtx_("RTAuxVars");
   if (!s) return fail(RXN_ERR_INVALID, "null state");
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
@@ -575,6 +586,7 @@ int rxn_update_auxvars_batch(RxnState *s, const double *xx_loc, int update_act_c
 }
 
 int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int64_t nlocal, double *accum_out) {
+  Nvtx nvtx_("RTUpdateFixedAccumulation");
   if (!s || !accum_out || nlocal < 0) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
   { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
@@ -626,6 +638,7 @@ static int launch_residual_jacobian(RxnState *s, const int32_t *d_l2g, int64_t n
 // caller owns; blocks of inactive cells are left untouched
 int rxn_residual_jacobian_blocks_batch_device(RxnState *s, const int32_t *d_l2g, int64_t nlocal, double dt, double *d_res,
                                               double *d_jac) {
+  Nvtx nvtx_("RTResReaction+RTJacReaction+RTJacobianAccum");
   if (!s || nlocal < 0 || !(dt > 0.0) || (!d_res && !d_jac)) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
   CU(cudaSetDevice(s->t->device));
@@ -638,6 +651,7 @@ int rxn_residual_jacobian_blocks_batch_device(RxnState *s, const int32_t *d_l2g,
 }
 
 int rxn_update_auxvars_batch_device(RxnState *s, const double *d_xx_loc, int update_act_coefs) {
+  Nvtx nvtx_("RTAuxVars");
   if (!s) return fail(RXN_ERR_INVALID, "null state");
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
@@ -652,6 +666,7 @@ int rxn_update_auxvars_batch_device(RxnState *s, const double *d_xx_loc, int upd
 
 int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t nlocal, double dt, double *res_out,
                                        double *jac_out) {
+  Nvtx nvtx_("RTResReaction+RTJacReaction+RTJacobianAccum");
   if (!s || nlocal < 0 || !(dt > 0.0) || (!res_out && !jac_out)) return fail(RXN_ERR_INVALID, "bad argument");
   if (nlocal == 0) return RXN_OK;
   { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
@@ -691,6 +706,7 @@ int rxn_equilibrate_constraint_batch(RxnState *s, const int32_t *constraint_type
                                      const int32_t *constraint_id, const double *free_ion_guess, int use_prev_soln_as_guess,
                                      int initialize_with_molality, const int32_t *l2g, int64_t nlocal, double *basis_molarity_out,
                                      int32_t *iters_out, int32_t *status_out) {
+  Nvtx nvtx_("ReactionEquilibrateConstraint");
   if (!s || !constraint_type || !constraint_conc || !constraint_id || nlocal < 0) return fail(RXN_ERR_INVALID, "bad argument");
   const RxnTables *t = s->t;
   const int n = t->h.naq;
@@ -740,6 +756,7 @@ int rxn_equilibrate_constraint_batch(RxnState *s, const int32_t *constraint_type
 }
 
 int rxn_update_kinetic_state_batch(RxnState *s, double dt) {
+  Nvtx nvtx_("RTUpdateKineticState");
   if (!s || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
@@ -854,6 +871,7 @@ int rxn_connset_device_structure(const RxnConnSet *c, const int32_t **d_row_ptr,
 
 int rxn_connset_flux_coefs(RxnConnSet *c, const double *area, const double *velocity, const double *disp_over_dist,
                            const double *fraction_upwind, int use_upwinding) {
+  Nvtx nvtx_("TFluxCoef");
   if (!c || !area || !velocity || !disp_over_dist || (!use_upwinding && !fraction_upwind)) return fail(RXN_ERR_INVALID, "bad argument");
   RxnState *s = c->s;
   const long long nc = c->R.nconn;
@@ -884,6 +902,7 @@ static int flux_ready(RxnState *s, RxnConnSet *c, int field, const char *what) {
 }
 
 int rxn_flux_residual_batch_device(RxnState *s, RxnConnSet *c, double *d_res) {
+  Nvtx nvtx_("RTResidualFlux");
   int rc = flux_ready(s, c, RXN_F_TOTAL, "total");
   if (rc != RXN_OK) return rc;
   if (!d_res) return fail(RXN_ERR_INVALID, "null output");
@@ -899,6 +918,7 @@ int rxn_flux_residual_batch_device(RxnState *s, RxnConnSet *c, double *d_res) {
 }
 
 int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val) {
+  Nvtx nvtx_("RTJacobianFlux");
   int rc = flux_ready(s, c, RXN_F_DTOTAL, "dtotal");
   if (rc != RXN_OK) return rc;
   if (!d_val) return fail(RXN_ERR_INVALID, "null output");
@@ -932,6 +952,7 @@ int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val) {
 }
 
 int rxn_flux_residual_batch(RxnState *s, RxnConnSet *c, double *res_out) {
+  Nvtx nvtx_("RTResidualFlux");
   if (!s || !c || !res_out) return fail(RXN_ERR_INVALID, "bad argument");
   if (c->R.nlocal == 0) return RXN_OK;
   CU(cudaSetDevice(s->t->device));
@@ -946,6 +967,7 @@ int rxn_flux_residual_batch(RxnState *s, RxnConnSet *c, double *res_out) {
 }
 
 int rxn_flux_jacobian_batch(RxnState *s, RxnConnSet *c, double *val_out) {
+  Nvtx nvtx_("RTJacobianFlux");
   if (!s || !c || !val_out) return fail(RXN_ERR_INVALID, "bad argument");
   if (c->R.nlocal == 0) return RXN_OK;
   CU(cudaSetDevice(s->t->device));

@@ -33,7 +33,7 @@ static int tm_kernel_build(const DevTab &h, const std::vector<double> &bd, const
   p.err = "tensor-memory kernel disabled (RXN_TM=0)";
   if (const char *e = getenv("RXN_TM")) { if (atoi(e) == 0) return RXN_OK; }
   if (prop.major != 10) { p.err = "tensor memory needs sm_100"; return RXN_OK; }
-  int force_g = 4, force_q = 0;                                  // measured on B200, 300A chemistry: G = 4 > 2 > 1
+  int force_g = 3, force_q = 0;                                  // measured on B200, 300A chemistry: G = 3 > 4 > 2 > 1
   if (const char *e = getenv("RXN_TM_G")) force_g = atoi(e);
   if (const char *e = getenv("RXN_TM_QUADS")) force_q = atoi(e);
   struct Shape { int N, Q, G; };

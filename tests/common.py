@@ -91,7 +91,12 @@ def iteration_parity(it_a, fl_a, it_o, fl_o, perturbed, max_fraction=0.01, facto
     number of cells (mismatches <= factor x that number, and <= max_fraction of the batch).  Measured: 300A, calcite, hpt,
     ion exchange, surface complexation, prefactor chemistries: 0 cells, i.e. strict equality; the 22-primary ascem redox
     chemistry (cells that take up to 2688 damped iterations): the oracle flips 17 of 3000 cells, FMA contraction 16."""
-    same = (it_a == it_o) & (fl_a == fl_o)
+    # a cell whose arithmetic left the finite range (RXN_FLAG_NONFINITE in both; the reference itself would spin or abort there)
+    # is compared on the iteration count and on that flag: whether the closing RTotalSorb then also runs its free-site loop
+    # into the 100000-iteration guard (RXN_FLAG_CAPPED) depends on which garbage value the singular Newton step produced
+    # (measured: cell 2415 of hanford300a_stoich, |update| differs 10x between summation orders at iteration 3)
+    nf = ((fl_a & abi.RXN_FLAG_NONFINITE) != 0) & ((fl_o & abi.RXN_FLAG_NONFINITE) != 0)
+    same = (it_a == it_o) & ((fl_a == fl_o) | (nf & (((fl_a ^ fl_o) & ~abi.RXN_FLAG_CAPPED) == 0)))
     if same.all():
         return same
     _, it_p, fl_p = perturbed.run()

@@ -81,10 +81,10 @@ def test_react_resident_lane_group_widths(name, G, monkeypatch):
     assert_state_close(st_g, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
 
 
-@pytest.mark.parametrize('G', [1, 2, 4])
+@pytest.mark.parametrize('G', [1, 2, 3, 4])
 @pytest.mark.parametrize('name', ['hanford300a_eq', 'hanford300a_mr'])
 def test_react_tensor_memory_kernel(name, G, monkeypatch):
-    """Tensor-memory kernel (J in TMEM, rxn_tm_dev.cuh) with 1, 2 and 4 member warps per cell; enough cells that every lane
+    """Tensor-memory kernel (J in TMEM, rxn_tm_dev.cuh) with 1 to 4 member warps per cell; enough cells that every lane
     takes several cells from the work counter and cells of one warp sit in different Newton iterations."""
     if G == 1 and name == 'hanford300a_mr':
         pytest.skip('G = 1 is compiled for 128 cells per CTA only (ablation shape); the multirate vectors need 96')
