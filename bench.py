@@ -50,7 +50,8 @@ WORKLOAD_DESC = {
 # (dram__bytes_read.sum + dram__bytes_write.sum over the cells of the profiled launch), not measured in the run; reported only
 # when the kernel the run used is the captured one (same name prefix), else null
 NCU_DRAM_BYTES_PER_CELL = {
-    'hanford300a_eq': [('tensor-memory N=15 cells/CTA=128', (932.234496e6 + 1454.456e6) / 600000, 'profiles/r02_f_tm_g4.metrics.txt'),
+    'hanford300a_eq': [('tensor-memory N=15 cells/CTA=128 warps/cell=3', (905.745152e6 + 1396.868e6) / 600000, 'profiles/r02_g_tm_g3.metrics.txt'),
+                       ('tensor-memory N=15 cells/CTA=128 warps/cell=4', (932.234496e6 + 1454.456e6) / 600000, 'profiles/r02_f_tm_g4.metrics.txt'),
                        ('resident-lane N=15 cells/CTA=64 lanes/cell=2', (758.277120e6 + 1237.866e6) / 600000,
                         'profiles/r01_r9_lane_g2.metrics.csv')],
 }

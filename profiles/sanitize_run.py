@@ -1,0 +1,81 @@
+"""Workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every kernel family of the library on batches
+small enough for the tools' slowdown, large enough that persistent lanes take several cells from the work counter
+(k_react_tm: 148 CTAs x 128 cells = 18 944 resident cells).  No oracle, no timing: the tools' reports are the result.
+
+  compute-sanitizer --tool racecheck python profiles/sanitize_run.py [react|gi|flux|all] [ncells]
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+from pflotran_b200 import abi, synth, reactive_transport as rt  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else 'all'
+ncells = int(sys.argv[2]) if len(sys.argv) > 2 else 60000
+
+
+def react(name, n, kernel=3):
+    w = synth.Workload(name)
+    cells = synth.make_cells(w, 0, n)
+    st = synth.host_state(w, cells)
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, n)
+    rz.upload_host_state(st)
+    rz.set_react_kernel(kernel)
+    xx = cells['tran_xx'].copy()
+    it, fl = rz.RTReact(xx, 3600.0, abi.RXN_DT_CONSISTENT)
+    print('react %-16s %6d cells  %s  mean its %.2f  non-reference flags %d' % (name, n, rz.react_kernel_info()[:60], it.mean(),
+                                                                               int(((fl != 1) & (fl != 2)).sum())))
+    return w, cells, st, rx, rz
+
+
+if what in ('react', 'all'):
+    react('hanford300a_eq', ncells)            # tensor-memory kernel (named barriers, TMEM, persistent lanes, atomicAdd work counter)
+    react('hanford300a_mr', ncells // 2)       # + warp-cooperative multirate loads
+    os.environ['RXN_TM'] = '0'
+    react('hanford300a_eq', ncells // 2)       # resident-lane kernel, J in shared memory (sub-warp __syncwarp groups)
+    del os.environ['RXN_TM']
+    react('calcite', ncells)                   # resident-lane kernel G = 1, 448 cells per CTA
+    react('ion_exchange', ncells // 4, 1)      # thread-per-cell kernel
+
+if what in ('gi', 'all'):
+    for name in ('hanford300a_eq', 'hanford300a_mr', 'calcite'):
+        w = synth.Workload(name)
+        n = ncells // 4
+        cells = synth.make_cells(w, 0, n)
+        st = synth.host_state(w, cells)
+        rx = rt.Reaction(w.tables)
+        rz = rt.Realization(rx, n)
+        rz.upload_host_state(st)
+        xx = np.ascontiguousarray(cells['tran_xx'])
+        rz.RTUpdateAuxVars(st['PRI_MOLAL'].T.copy(), True)
+        acc = rz.RTUpdateFixedAccumulation(None)
+        res, jac = rz.RTResidualJacobianNonFlux(3600.0)
+        rz.RTUpdateKineticState(3600.0)
+        print('gi    %-16s %6d cells  |res| max %.3e' % (name, n, np.abs(res).max()))
+
+if what in ('flux', 'all'):
+    from flux_common import structured_connections
+    w = synth.Workload('hanford300a_eq')
+    nx, ny, nz = 24, 16, 12
+    n = nx * ny * nz
+    cells = synth.make_cells(w, 0, n)
+    st = synth.host_state(w, cells)
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, n)
+    rz.upload_host_state(st)
+    rz.materialize('DTOTAL')
+    rz.RTUpdateAuxVars(st['PRI_MOLAL'].T.copy(), True)
+    conn, _, nlocal, _ = structured_connections(nx, ny, nz, w.tables.naqcomp)
+    cs = rt.ConnectionSet(rz, conn['id_up'], conn['id_dn'], nlocal)
+    cs.TFluxCoef(conn['area'], conn['velocity'], conn['disp'])
+    r = rz.RTResidualFlux(cs)
+    v = rz.RTJacobianFlux(cs)
+    print('flux  %d cells, %d blocks, |res| max %.3e' % (n, cs.nnz_blocks, np.abs(r).max()))
+    cs.close()
+print('sanitize_run done')
