@@ -201,6 +201,234 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# Global-implicit mode (BASELINE config 4): one step = the per-Newton-iteration cell loops of the global-implicit transport
+# solve: RTUpdateAuxVars with activity-coefficient update (reactive_transport.F90:3790-3846, 3620-3700) on a new free-ion
+# iterate, then the accumulation + reaction residual and Jacobian blocks of RTResidualNonFlux / RTJacobianNonFlux
+# (:2545-2586, 2735-2758, 3342-3389, 3445-3465) for every cell.
+GI_METRIC = 'global-implicit reaction residual+Jacobian blocks/sec'
+GI_UNIT = 'cell-blocks/s'
+GI_DEFAULT_CELLS = {'hpt_calcite': 4_000_000, 'calcite': 4_000_000, 'hanford300a_eq': 1_000_000, 'hanford300a_mr': 500_000}
+
+
+def gi_work_model(t):
+    """Algorithmic work of one global-implicit step per cell (same accounting as work_model: SURVEY.md 8d, W = 20
+    flop-equivalents per transcendental): RTotal + RTotalSorb are evaluated twice (RTUpdateAuxVars, and again inside the block
+    evaluation, which keeps no naq^2 array in HBM), activity coefficients once, minerals once."""
+    naq, ncplx, nkin = t.naqcomp, t.neqcplx, t.nkinmnrl
+    S = int(sum(t.eqcplxspecid[k, 0] for k in range(ncplx)))
+    S2 = int(sum(int(t.eqcplxspecid[k, 0]) ** 2 for k in range(ncplx)))
+    nsrf, nrxn = t.nsrfcplx, t.nsrfcplxrxn
+    nrate = t.kinmr_max_nrate if t.nkinmrsrfcplxrxn else 0
+    srf_n2 = int(sum(int(t.srfcplxspecid[k, 0]) ** 2 for k in range(nsrf)))
+    kin_n2 = int(sum(int(t.kinmnrlspecid[k, 0]) ** 2 for k in range(nkin)))
+    F_rtotal = 7 * S + 2 * ncplx + 2 * S2 + naq + naq * naq
+    F_sorb = 12 * srf_n2 + 4 * naq * (1 + (1 if nrate else 0)) if nsrf else 0
+    F_min = 20 * nkin + 2 * kin_n2
+    F = 2 * (F_rtotal + F_sorb) + F_min + 4 * naq * naq + 15 * (naq + ncplx) + 2 * naq * nrate * t.nkinmrsrfcplxrxn
+    Nt = 2 * (2 * naq + ncplx + S + nsrf * 2) + 2 * nkin + (naq + ncplx + 1)
+    if t.logK_mode != 0:                     # per-cell logK: 17-term / 5-term fit per reaction, evaluated in both kernels
+        nrx = ncplx + nkin + nsrf
+        F += 2 * 40 * nrx
+        Nt += 2 * 3
+    mr = naq * nrate * t.nkinmrsrfcplxrxn
+    rd1 = naq + ncplx + 7 + nkin + nrxn                                    # xx, lagged sec_molal, scalars, volfrac, free sites
+    wr1 = 3 * naq + 2 * ncplx + naq + nrxn + nsrf + 1                      # pri_molal, total, gamma; sec_molal, gamma_k; sorbed; ...
+    rd2 = 2 * naq + ncplx + 7 + 2 * nkin + nrxn + mr
+    wr2 = naq + naq * naq + naq + ncplx + nrxn + nkin + naq + nsrf + naq * t.nkinmrsrfcplxrxn
+    return {'flop_eq_per_cell': F + 20.0 * Nt, 'flops_per_cell': F, 'transcendentals_per_cell': Nt,
+            'bytes_per_cell': 8.0 * (rd1 + wr1 + rd2 + wr2)}
+
+
+def gi_inputs(w, cells):
+    """Free-ion iterate of the step: the base state's molalities under the workload's per-cell perturbation."""
+    return np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * (cells['tran_xx'] / w.base['TOTAL'][None, :]))
+
+
+def cpu_gi_rate(w, ncells_sample, dt, threads):
+    from oracle.pyoracle import Oracle
+    cells = synth.make_cells(w, 0, ncells_sample)
+    orc = Oracle(w.tables)
+    st = synth.host_state(w, cells)
+    xx = gi_inputs(w, cells)
+    t0 = time.perf_counter()
+    orc.update_auxvars(st, xx, True, nthreads=threads)
+    orc.residual_jacobian(st, dt, nthreads=threads)
+    el = time.perf_counter() - t0
+    return ncells_sample / el, el
+
+
+class GiBench:
+    """State + buffers of one global-implicit benchmark instance (used by --mode gi and by the extra configs of the default run)."""
+
+    def __init__(self, rt, name, n, device, start=0):
+        self.rt, self.n = rt, n
+        self.w = w = synth.Workload(name)
+        self.t = t = w.tables
+        self.cells = cells = synth.make_cells(w, start, n)
+        self.rx = rt.Reaction(t, device=device)
+        self.rz = rz = rt.Realization(self.rx, n)
+        for f, v in w.base.items():
+            rz.broadcast(f, v)
+        rz.set_cell_scalars(porosity=cells['porosity'], temp=cells['temp'], pres=cells['pres'])
+        if t.nkinmnrl:
+            rz.upload('MNRL_VOLFRAC', cells['volfrac'])
+        nc = t.ncomp
+        self.xx_host = rt.pinned_empty((n, nc))
+        self.xx_host[:] = gi_inputs(w, cells)
+        self.res_host = rt.pinned_empty((n, nc))
+        self.jac_host = rt.pinned_empty((n, nc * nc))
+        self.d_xx = rz.device_alloc(n * nc * 8)
+        self.d_res = rz.device_alloc(n * nc * 8)
+        self.d_jac = rz.device_alloc(n * nc * nc * 8)
+        rz.device_copy(self.d_xx, self.xx_host, n * nc * 8, 0)
+        self.h2d = n * nc * 8
+        self.d2h = n * (nc + nc * nc) * 8
+
+    def restore(self):
+        for f in RESET_FIELDS:
+            if self.rx.field_rows(f):
+                self.rz.broadcast(f, self.w.base[f])
+
+    def step_device(self, dt):
+        self.restore()
+        self.rz.RTUpdateAuxVars_device(self.d_xx, True)
+        k1 = self.rz.last_kernel_ms()
+        self.rz.RTResidualJacobianNonFlux_device(self.n, dt, self.d_res, self.d_jac)
+        return k1 + self.rz.last_kernel_ms()
+
+    def step_e2e(self, dt):
+        self.restore()
+        self.rz.RTUpdateAuxVars(self.xx_host, True)
+        self.rz.RTResidualJacobianNonFlux(dt, res=self.res_host, jac=self.jac_host)
+
+    def measure(self, steps, warmup, dt, barrier=lambda: None):
+        rz = self.rz
+        for _ in range(max(warmup, 3)):
+            self.step_device(dt)
+        barrier()
+        rz.timer_start()
+        kern = [self.step_device(dt) for _ in range(steps)]
+        dev_ms = rz.timer_stop()
+        barrier()
+        self.step_e2e(dt)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step_e2e(dt)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        return dev_ms, statistics.mean(kern), e2e_s
+
+    def rooflines(self, kern_ms, fp64_peak, hbm_peak):
+        wm = gi_work_model(self.t)
+        ks = kern_ms * 1e-3
+        f_ach = wm['flop_eq_per_cell'] * self.n / ks / 1e12
+        b_ach = wm['bytes_per_cell'] * self.n / ks / 1e9
+        fp = {'bound': 'fp64', 'achieved': f_ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': f_ach / fp64_peak, 'traffic': None,
+              'kernel_ms': kern_ms, 'flop_eq_per_cell': wm['flop_eq_per_cell'],
+              'kernels': 'update_auxvars + residual/Jacobian blocks (sum of the two launches, CUDA events)'}
+        hb = {'bound': 'hbm', 'achieved': b_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': b_ach / hbm_peak, 'traffic': None,
+              'kernel_ms': kern_ms, 'bytes_per_cell': wm['bytes_per_cell']}
+        # the binding limit is the one that would take longer at its peak
+        return (fp, hb) if f_ach / fp64_peak >= b_ach / hbm_peak else (hb, fp)
+
+
+def run_gi(args):
+    import torch
+    import torch.distributed as dist
+    from pflotran_b200 import reactive_transport as rt
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    name = args.workload if args.workload_given else 'hpt_calcite'
+    n = args.cells or GI_DEFAULT_CELLS[name]
+    g = GiBench(rt, name, n, local_rank, start=rank * n)
+    fp64_peak = g.rz.probe_fp64_tflops()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = rt.launch_count()
+    tw0 = time.perf_counter()
+    dev_ms, kern_ms, e2e_s = g.measure(args.steps, args.warmup, args.gi_dt, barrier)
+    tw1 = time.perf_counter()
+    launches = rt.launch_count() - l0
+    clocks = sampler.stop(tw0, tw1)
+    dev_ms = max_over_ranks(dev_ms); kern_ms = max_over_ranks(kern_ms); e2e_s = max_over_ranks(e2e_s)
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        r1, r2 = g.rooflines(kern_ms, fp64_peak, peaks['hbm_gbs'])
+        total = n * world
+        line = {
+            'metric': GI_METRIC, 'value': total * args.steps / (dev_ms * 1e-3), 'unit': GI_UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD_DESC[name] + '; global-implicit step: RTUpdateAuxVars (activity update) + reaction '
+                                   'residual and Jacobian block of every cell', 'name': name, 'mode': 'gi', 'cells_per_gpu': n,
+                       'total_cells': total, 'dt_s': args.gi_dt,
+                       'l2_policy': 'cell state + output blocks per GPU larger than L2 (%.1f GB); no flush needed'
+                                    % (n * gi_work_model(g.t)['bytes_per_cell'] / 1e9)},
+            'e2e': {'value': total * (args.steps) / e2e_s, 'unit': GI_UNIT, 'h2d_bytes_per_step': g.h2d, 'd2h_bytes_per_step': g.d2h},
+            'gpu_launches': int(launches * world), 'clocks': clocks,
+            'roofline': dict(r1, peak_source=peak_src if r1['bound'] == 'hbm' else 'DFMA probe measured in this run (rxn_probe_fp64)'),
+            'roofline_other': r2,
+        }
+        threads = os.cpu_count() or 1
+        rate0, _ = cpu_gi_rate(g.w, 4096 * max(1, threads // 4), args.gi_dt, threads)
+        sample = int(max(4096, min(n, rate0 * 10.0)) // 4096 * 4096)
+        rate, el = cpu_gi_rate(g.w, sample, args.gi_dt, threads)
+        line['cpu_baseline'] = {'value': rate, 'unit': GI_UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': 'first %d cells of the same workload, %.1f s, C++ restatement of RTUpdateAuxVars + the '
+                                          'accumulation/reaction loops of RTResidual/RTJacobian (oracle/)' % (sample, el)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_gi_reference(args):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    name = args.workload if args.workload_given else 'hpt_calcite'
+    w = synth.Workload(name)
+    threads = os.cpu_count() or 1
+    rate0, _ = cpu_gi_rate(w, 4096 * max(1, threads // 4), args.gi_dt, threads)
+    sample = int(max(4096, min(GI_DEFAULT_CELLS[name], rate0 * 6.0)) // 4096 * 4096)
+    for _ in range(args.warmup):
+        cpu_gi_rate(w, min(sample, 8192 * threads), args.gi_dt, threads)
+    t_tot = 0.0
+    for _ in range(args.steps):
+        _, el = cpu_gi_rate(w, sample, args.gi_dt, threads)
+        t_tot += el
+    value = sample * args.steps / t_tot
+    print(json.dumps({
+        'impl': 'reference', 'metric': GI_METRIC, 'value': value, 'unit': GI_UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD_DESC[name], 'name': name, 'mode': 'gi', 'cells_per_step': sample, 'dt_s': args.gi_dt},
+        'cpu_baseline': {'value': value, 'unit': GI_UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': 'first %d cells per step, C++ restatement (oracle/), %d host threads' % (sample, threads)},
+        'e2e': {'value': value, 'unit': GI_UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -377,10 +605,92 @@ def run_ours(args):
         line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                 'sample': 'first %d cells of the same workload, %.1f s, C++ restatement of the reference loop '
                                           '(no Fortran compiler in the image)' % (sample, el)}
+        if world == 1 and not args.no_extra and not args.workload_given and not args.cells:
+            line['other_configs'] = extra_configs(rt, rz, local_rank, args, fp64_peak, peaks['hbm_gbs'])
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_configs(rt, rz_main, device, args, fp64_peak, hbm_peak):
+    """The other single-GPU BASELINE configurations, measured in the same run after the headline (short: 3 steps each), so
+    that the driver's default invocation records them: config 2 (calcite chemistry on the 100^3 grid, operator-split RTReact)
+    and config 4 (geothermal-hpt chemistry, global-implicit residual/Jacobian blocks).  Same timing rules as the headline."""
+    out = []
+    try:
+        name, n = 'calcite', DEFAULT_CELLS['calcite']
+        w = synth.Workload(name)
+        t = w.tables
+        cells = synth.make_cells(w, 0, n)
+        rx = rt.Reaction(t, device=device)
+        rz = rt.Realization(rx, n)
+        for f, v in w.base.items():
+            rz.broadcast(f, v)
+        rz.set_cell_scalars(porosity=cells['porosity'], temp=cells['temp'], pres=cells['pres'])
+        if t.nkinmnrl:
+            rz.upload('MNRL_VOLFRAC', cells['volfrac'])
+        nb = n * t.ncomp * 8
+        xx_host = rt.pinned_empty((n, t.ncomp)); it_host = rt.pinned_empty((n,), np.int32); fl_host = rt.pinned_empty((n,), np.int32)
+        d_xx0 = rz.device_alloc(nb); d_xx = rz.device_alloc(nb); d_it = rz.device_alloc(n * 4); d_fl = rz.device_alloc(n * 4)
+        rz.device_copy(d_xx0, cells['tran_xx'], nb, 0)
+
+        def restore():
+            for f in RESET_FIELDS:
+                if rx.field_rows(f):
+                    rz.broadcast(f, w.base[f])
+
+        def step():
+            restore()
+            rz.device_copy(d_xx, d_xx0, nb, 2)
+            rz.RTReact_device(d_xx, n, args.dt, abi.RXN_DT_CONSISTENT, 0, d_it, d_fl)
+            return rz.last_kernel_ms()
+        for _ in range(3):
+            step()
+        K = 10
+        rz.timer_start()
+        km = [step() for _ in range(K)]
+        dev_ms = rz.timer_stop()
+        rz.device_copy(it_host, d_it, n * 4, 1)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            restore()
+            xx_host[:] = cells['tran_xx']
+            rz.RTReact(xx_host, args.dt, abi.RXN_DT_CONSISTENT, iters=it_host, flags=fl_host)
+        e2e_s = time.perf_counter() - t0
+        wm = work_model(t, float(it_host.sum(dtype=np.int64)), n)
+        ks = statistics.mean(km) * 1e-3
+        fa = wm['flop_eq_per_cell'] * n / ks / 1e12
+        threads = os.cpu_count() or 1
+        rate, el, _ = cpu_reference_rate(w, 65536 * max(1, threads // 4), 0, args.dt, threads)
+        out.append({'config': 'BASELINE config 2', 'metric': METRIC, 'unit': UNIT, 'name': name, 'workload': WORKLOAD_DESC[name],
+                    'cells': n, 'steps': K, 'value': n * K / (dev_ms * 1e-3),
+                    'e2e': {'value': n * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': nb, 'd2h_bytes_per_step': nb + 8 * n,
+                            'note': 'includes the host memcpy that refills the caller buffer each step'},
+                    'roofline': {'bound': 'fp64', 'achieved': fa, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': fa / fp64_peak,
+                                 'kernel_ms': statistics.mean(km), 'traffic': None},
+                    'roofline_hbm_frac': wm['bytes_per_cell'] * n / ks / 1e9 / hbm_peak,
+                    'mean_newton_iterations': wm['mean_newton_iterations'], 'kernel': rz.react_kernel_info(),
+                    'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': '%.1f s' % el}})
+        del rz, rx
+    except Exception as e:                                  # the headline line must not be lost to an extra configuration
+        out.append({'config': 'BASELINE config 2', 'error': repr(e)})
+    try:
+        name, n = 'hpt_calcite', GI_DEFAULT_CELLS['hpt_calcite']
+        g = GiBench(rt, name, n, device)
+        K = 5
+        dev_ms, kern_ms, e2e_s = g.measure(K, 3, args.gi_dt)
+        r1, r2 = g.rooflines(kern_ms, fp64_peak, hbm_peak)
+        threads = os.cpu_count() or 1
+        rate, el = cpu_gi_rate(g.w, 65536 * max(1, threads // 4), args.gi_dt, threads)
+        out.append({'config': 'BASELINE config 4', 'metric': GI_METRIC, 'unit': GI_UNIT, 'name': name, 'workload': WORKLOAD_DESC[name],
+                    'cells': n, 'steps': K, 'value': n * K / (dev_ms * 1e-3),
+                    'e2e': {'value': n * K / e2e_s, 'unit': GI_UNIT, 'h2d_bytes_per_step': g.h2d, 'd2h_bytes_per_step': g.d2h},
+                    'roofline': r1, 'roofline_other': r2,
+                    'cpu_baseline': {'value': rate, 'unit': GI_UNIT, 'cores': threads, 'kind': 'port', 'sample': '%.1f s' % el}})
+    except Exception as e:
+        out.append({'config': 'BASELINE config 4', 'error': repr(e)})
+    return out
 
 
 def main():
@@ -393,8 +703,18 @@ def main():
     ap.add_argument('--cells', type=int, default=0, help='cells per GPU (default: the BASELINE config size)')
     ap.add_argument('--dt', type=float, default=3600.0)
     ap.add_argument('--kernel', type=int, default=0, choices=[0, 1, 3])
+    ap.add_argument('--mode', default='react', choices=['react', 'gi'],
+                    help='react: operator-split RTReact (headline); gi: global-implicit auxvars + residual/Jacobian blocks (config 4)')
+    ap.add_argument('--gi-dt', type=float, default=1800.0, dest='gi_dt')
+    ap.add_argument('--no-extra', action='store_true', help='headline only: skip the short runs of BASELINE configs 2 and 4')
     args = ap.parse_args()
-    if args.impl == 'reference':
+    args.workload_given = any(a == '--workload' or a.startswith('--workload=') for a in sys.argv[1:])
+    if args.mode == 'gi':
+        if args.impl == 'reference':
+            run_gi_reference(args)
+        else:
+            run_gi(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)

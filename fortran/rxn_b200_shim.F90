@@ -159,6 +159,9 @@ module Rxn_B200_module
             rxn_residual_jacobian_blocks_batch_device, rxn_connset_create, rxn_connset_destroy, &
             rxn_connset_structure, rxn_connset_device_structure, rxn_connset_flux_coefs, rxn_flux_residual_batch, &
             rxn_flux_jacobian_batch, rxn_flux_residual_batch_device, rxn_flux_jacobian_batch_device, &
+            rxn_couplerset_create, rxn_couplerset_destroy, rxn_couplerset_bc_coefs, rxn_couplerset_ss_coefs, &
+            rxn_couplerset_set_totals, rxn_couplerset_totals_from_state, rxn_coupler_residual_batch, &
+            rxn_coupler_jacobian_batch, rxn_coupler_residual_batch_device, rxn_coupler_jacobian_batch_device, &
             rxn_last_kernel_ms, rxn_last_error
 
   interface
@@ -389,6 +392,71 @@ module Rxn_B200_module
     integer(c_int) function rxn_flux_jacobian_batch_device(state, connset, d_val) bind(C, name='rxn_flux_jacobian_batch_device')
       import :: c_int, c_ptr
       type(c_ptr), value :: state, connset, d_val
+    end function
+
+    ! boundary conditions (RTResidualFlux :2347-2430, RTJacobianFlux :3176-3240) and source/sinks (RTResidualNonFlux :2623-2672,
+    ! RTJacobianNonFlux :3394-3436): kind 0 = patch%boundary_condition_list, 1 = patch%source_sink_list, flattened in loop order
+    ! (sum_connection); id_dn = 0-based ghosted id of the cell of each connection
+    integer(c_int) function rxn_couplerset_create(state, kind, nconn, id_dn, ghost_to_local, nlocal, active, couplerset) &
+        bind(C, name='rxn_couplerset_create')
+      import :: c_int, c_int64_t, c_ptr
+      type(c_ptr), value :: state
+      integer(c_int), value :: kind
+      integer(c_int64_t), value :: nconn, nlocal
+      type(c_ptr), value :: id_dn, ghost_to_local, active
+      type(c_ptr) :: couplerset
+    end function
+
+    integer(c_int) function rxn_couplerset_destroy(couplerset) bind(C, name='rxn_couplerset_destroy')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: couplerset
+    end function
+
+    ! area = connection%area, velocity = patch%boundary_velocities(1,:), disp_over_dist = patch%boundary_tran_coefs(:,1,:)
+    integer(c_int) function rxn_couplerset_bc_coefs(couplerset, area, velocity, disp_over_dist, use_upwinding) &
+        bind(C, name='rxn_couplerset_bc_coefs')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: couplerset, area, velocity, disp_over_dist
+      integer(c_int), value :: use_upwinding
+    end function
+
+    ! qsrc = patch%ss_flow_vol_fluxes(1,:), tran_src_sink_type = source_sink%tran_condition%itype per connection
+    integer(c_int) function rxn_couplerset_ss_coefs(couplerset, qsrc, tran_src_sink_type) bind(C, name='rxn_couplerset_ss_coefs')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: couplerset, qsrc, tran_src_sink_type
+    end function
+
+    integer(c_int) function rxn_couplerset_set_totals(couplerset, total) bind(C, name='rxn_couplerset_set_totals')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: couplerset, total
+    end function
+
+    ! bc_state: the state that replaces rt_auxvars_bc(:) (one cell per boundary connection)
+    integer(c_int) function rxn_couplerset_totals_from_state(couplerset, bc_state) bind(C, name='rxn_couplerset_totals_from_state')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: couplerset, bc_state
+    end function
+
+    integer(c_int) function rxn_coupler_residual_batch(state, couplerset, res_inout, flux_out) bind(C, name='rxn_coupler_residual_batch')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, couplerset, res_inout, flux_out
+    end function
+
+    integer(c_int) function rxn_coupler_jacobian_batch(state, connset, couplerset, val_inout) bind(C, name='rxn_coupler_jacobian_batch')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, connset, couplerset, val_inout
+    end function
+
+    integer(c_int) function rxn_coupler_residual_batch_device(state, couplerset, d_res, d_flux_out) &
+        bind(C, name='rxn_coupler_residual_batch_device')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, couplerset, d_res, d_flux_out
+    end function
+
+    integer(c_int) function rxn_coupler_jacobian_batch_device(state, connset, couplerset, d_val) &
+        bind(C, name='rxn_coupler_jacobian_batch_device')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: state, connset, couplerset, d_val
     end function
 
     real(c_float) function rxn_last_kernel_ms(state) bind(C, name='rxn_last_kernel_ms')

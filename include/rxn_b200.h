@@ -388,6 +388,50 @@ int rxn_flux_jacobian_batch(RxnState *s, RxnConnSet *c, double *val_out);
 int rxn_flux_residual_batch_device(RxnState *s, RxnConnSet *c, double *d_res);
 int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val);
 
+/* ---- Boundary conditions and source/sinks ("coupler" connections; SURVEY.md 8f.3 remainder) -------------------------
+ * replaces: the boundary-connection loops of RTResidualFlux (reactive_transport.F90:2347-2430) and RTJacobianFlux
+ * (:3176-3240), and the source/sink loops of RTResidualNonFlux (:2623-2672) and RTJacobianNonFlux (:3394-3436).
+ *
+ * A coupler set is the flattened connection list of patch%boundary_condition_list (kind RXN_COUPLER_BOUNDARY) or of
+ * patch%source_sink_list (RXN_COUPLER_SRC_SINK) in loop order (sum_connection): id_dn = ghosted id (0-based) of the cell of
+ * each connection, ghost_to_local / active as for rxn_connset_create.  Every connection carries an EXTERNAL TOTAL vector:
+ * rt_auxvars_bc(sum_connection)%total for a boundary connection - the reference keeps a second auxvar array for the
+ * boundary faces (reactive_transport.F90:3851-4030); here that is a second RxnState with one cell per connection, updated
+ * with rxn_update_auxvars_batch / rxn_equilibrate_constraint_batch and handed over by rxn_couplerset_totals_from_state -
+ * or tran_condition%cur_constraint_coupler%rt_auxvar%total for a source/sink (rxn_couplerset_set_totals).
+ *   boundary   : Res = coef_up total_ext + coef_dn total_cell ; r_p -= Res ; diagonal block -= dtotal_cell(i,:) coef_dn(i)
+ *   source/sink: Res = coef_in total_cell + coef_out total_ext ; r_p += Res ; diagonal block += coef_in dtotal_cell
+ * The residual / Jacobian calls ADD onto the arrays the interior-flux (or accumulation) calls produced, in connection
+ * order, as the reference's loops do after the interior loop. */
+typedef struct RxnCouplerSet RxnCouplerSet;
+enum { RXN_COUPLER_BOUNDARY = 0, RXN_COUPLER_SRC_SINK = 1 };
+/* tran_condition%itype values TSrcSinkCoef distinguishes (pflotran_constants.F90:139,144); anything else: volumetric rate */
+enum { RXN_SS_MASS_RATE = 7, RXN_SS_EQUILIBRIUM = 12 };
+int rxn_couplerset_create(RxnState *s, int kind, int64_t nconn, const int32_t *id_dn, const int32_t *ghost_to_local, int64_t nlocal,
+                          const uint8_t *active, RxnCouplerSet **out);
+int rxn_couplerset_destroy(RxnCouplerSet *b);
+/* boundary: TFluxCoef (transport.F90:756-819) with fraction_upwind = 0.5 as reactive_transport.F90:2369-2373.  Host arrays:
+ * area (connection%area), velocity (patch%boundary_velocities(1,:)), disp_over_dist (patch%boundary_tran_coefs(:,1,:),
+ * nconn x naqcomp, component fastest) */
+int rxn_couplerset_bc_coefs(RxnCouplerSet *b, const double *area, const double *velocity, const double *disp_over_dist,
+                            int use_upwinding);
+/* source/sink: TSrcSinkCoef (transport.F90:901-954); qsrc = patch%ss_flow_vol_fluxes(1,:), type = tran_condition%itype */
+int rxn_couplerset_ss_coefs(RxnCouplerSet *b, const double *qsrc, const int32_t *tran_src_sink_type);
+/* external totals: host array nconn x naqcomp (component fastest), or the TOTAL field of a state with >= nconn cells on the
+ * same device (cell c of that state = connection c) */
+int rxn_couplerset_set_totals(RxnCouplerSet *b, const double *total);
+int rxn_couplerset_totals_from_state(RxnCouplerSet *b, const RxnState *bc_state);
+/* res_inout: AoS nlocal x ncomp (r_p); flux_out: optional nconn x ncomp (patch%boundary_tran_fluxes = -Res resp.
+ * patch%ss_tran_fluxes = Res; rows of connections on inactive cells are left untouched) */
+int rxn_coupler_residual_batch(RxnState *s, RxnCouplerSet *b, double *res_inout, double *flux_out);
+/* Jacobian: adds into the diagonal blocks.  With a connection set: val_inout = its block-CSR value array (nnz_blocks x
+ * ncomp x ncomp; the diagonal block of local row r is slot row_ptr[r]); with c = NULL: val_inout = nlocal x ncomp x ncomp
+ * diagonal blocks (the layout of rxn_jacobian_blocks_batch). */
+int rxn_coupler_jacobian_batch(RxnState *s, RxnConnSet *c, RxnCouplerSet *b, double *val_inout);
+/* same on arrays resident on the state's device */
+int rxn_coupler_residual_batch_device(RxnState *s, RxnCouplerSet *b, double *d_res, double *d_flux_out);
+int rxn_coupler_jacobian_batch_device(RxnState *s, RxnConnSet *c, RxnCouplerSet *b, double *d_val);
+
 /* timing of the last batched kernel sequence on the handle's stream, in ms (CUDA events). */
 float rxn_last_kernel_ms(const RxnState *s);
 /* CUDA-event bracket on the handle's stream around any sequence of calls (bench.py) */

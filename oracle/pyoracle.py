@@ -160,6 +160,31 @@ class Oracle:
         assert L.orc_flux_jacobian(*a(col, val)) == nnzb
         return row_ptr, col, val
 
+    # ---- boundary-condition / source-sink connections (reactive_transport.F90:2347-2430, 3176-3240, 2623-2672, 3394-3436)
+    @staticmethod
+    def ss_coefs(qsrc, ss_type):
+        n = len(qsrc)
+        tin, tout = np.zeros(n), np.zeros(n)
+        assert lib().orc_ss_coefs(C.c_int64(n), _f64(qsrc), _i32(ss_type), _f64(tin), _f64(tout)) == 0
+        return tin, tout
+
+    def coupler_residual(self, st: abi.HostState, kind, id_dn, ext_total, c_ext, c_cell, nlocal, res, g2l=None, want_flux=False):
+        """res [nlocal, naq] updated in place; c_ext / c_cell [nconn, naq]; returns flux_out [nconn, naq] or None."""
+        naq = self.t.naqcomp
+        v = st.view()
+        flux = np.zeros((len(id_dn), naq)) if want_flux else None
+        assert lib().orc_coupler_residual(C.byref(v), _u8(st.active), C.c_int(kind), C.c_int(naq), C.c_int64(len(id_dn)), _i32(id_dn),
+                                          _i32(g2l), _f64(ext_total), _f64(c_ext), _f64(c_cell), C.c_int64(nlocal), _f64(res),
+                                          _f64(flux)) == 0
+        return flux
+
+    def coupler_jacobian(self, st: abi.HostState, kind, id_dn, c_cell, nlocal, diag, g2l=None):
+        """diag [nlocal, naq*naq] (column-major blocks) updated in place."""
+        naq = self.t.naqcomp
+        v = st.view()
+        assert lib().orc_coupler_jacobian(C.byref(v), _u8(st.active), C.c_int(kind), C.c_int(naq), C.c_int64(len(id_dn)), _i32(id_dn),
+                                          _i32(g2l), _f64(c_cell), C.c_int64(nlocal), _f64(diag)) == 0
+
     @staticmethod
     def rsolve(res, jac, conc, use_log):
         n = len(res)

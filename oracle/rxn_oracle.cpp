@@ -1661,6 +1661,86 @@ int64_t orc_flux_jacobian(const View *v, const uint8_t *active, int naq, int64_t
   return nnzb;
 }
 
+// TSrcSinkCoef, transport.F90:901-954, liquid phase.  type: RXN_SS_* (include/rxn_b200.h).
+int orc_ss_coefs(int64_t nconn, const double *qsrc, const int32_t *type, double *T_in, double *T_out) {
+  for (int64_t c = 0; c < nconn; ++c) {
+    T_in[c] = 0.0; T_out[c] = 0.0;                                       // :922-923
+    switch (type[c]) {
+      case RXN_SS_EQUILIBRIUM:                                            // :926-932
+        T_in[c] = 1.0e-3;
+        T_out[c] = -1.0 * T_in[c];
+        break;
+      case RXN_SS_MASS_RATE:                                              // :933-936
+        T_in[c] = 0.0;
+        T_out[c] = -1.0;
+        break;
+      default:                                                            // :937-947
+        if (qsrc[c] > 0.0) { T_in[c] = 0.0; T_out[c] = -1.0 * qsrc[c] * 1000.0; }
+        else { T_out[c] = 0.0; T_in[c] = -1.0 * qsrc[c] * 1000.0; }
+    }
+  }
+  return 0;
+}
+
+// Boundary-connection loop of RTResidualFlux, reactive_transport.F90:2347-2430 (kind 0: r_p = r_p - Res with
+// Res = TFlux(up = boundary auxvar, dn = cell), patch%boundary_tran_fluxes = -Res) and the source/sink loop of
+// RTResidualNonFlux, :2623-2672 (kind 1: Res = coef_in total_cell + coef_out total_ss, r_p = r_p + Res,
+// patch%ss_tran_fluxes = Res).  id_dn: ghosted id of the cell of each connection; ext_total [nconn][naq]: total of the
+// boundary auxvar / of the source-sink constraint; c_ext / c_cell [nconn][naq]: coef_up / coef_dn (kind 0), coef_out /
+// coef_in repeated per component (kind 1).  r [nlocal][naq] is updated in place; flux_out may be NULL.
+int orc_coupler_residual(const View *v, const uint8_t *active, int kind, int naq, int64_t nconn, const int32_t *id_dn,
+                         const int32_t *g2l, const double *ext_total, const double *c_ext, const double *c_cell, int64_t nlocal,
+                         double *r, double *flux_out) {
+  const double *tot = v->f[RXN_F_TOTAL];
+  std::vector<double> Res(naq);
+  for (int64_t c = 0; c < nconn; ++c) {
+    const int64_t g = id_dn[c];
+    if (active && !active[g]) continue;                                 // :2360, :2636
+    const int64_t l = g2l ? g2l[g] : g;
+    if (l < 0 || l >= nlocal) return 1;                                 // coupler connections sit on local cells
+    if (kind == 0) {
+      for (int i = 0; i < naq; ++i)                                      // transport.F90:402-403
+        Res[i] = c_ext[c * naq + i] * ext_total[c * naq + i] + c_cell[c * naq + i] * tot[i * v->ld + g];
+      for (int i = 0; i < naq; ++i) r[l * naq + i] = r[l * naq + i] - Res[i];                 // :2382
+      if (flux_out) for (int i = 0; i < naq; ++i) flux_out[c * naq + i] = -Res[i];            // :2421-2424
+    } else {
+      for (int i = 0; i < naq; ++i)                                      // :2648-2653
+        Res[i] = c_cell[c * naq + i] * tot[i * v->ld + g] + c_ext[c * naq + i] * ext_total[c * naq + i];
+      for (int i = 0; i < naq; ++i) r[l * naq + i] = r[l * naq + i] + Res[i];                 // :2661
+      if (flux_out) for (int i = 0; i < naq; ++i) flux_out[c * naq + i] = Res[i];             // :2662-2664
+    }
+  }
+  return 0;
+}
+
+// Boundary-connection loop of RTJacobianFlux, reactive_transport.F90:3176-3240 (kind 0: Jdn(i,j) = dtotal(i,j) coef_dn(i),
+// Jdn = -Jdn, added to the diagonal block) and the source/sink loop of RTJacobianNonFlux, :3394-3436 (kind 1:
+// Jup = coef_in dtotal, added to the diagonal block).  diag [nlocal][naq*naq] column-major blocks, updated in place.
+int orc_coupler_jacobian(const View *v, const uint8_t *active, int kind, int naq, int64_t nconn, const int32_t *id_dn,
+                         const int32_t *g2l, const double *c_cell, int64_t nlocal, double *diag) {
+  const double *D = v->f[RXN_F_DTOTAL];
+  const int nn = naq * naq;
+  std::vector<double> J(nn);
+  for (int64_t c = 0; c < nconn; ++c) {
+    const int64_t g = id_dn[c];
+    if (active && !active[g]) continue;
+    const int64_t l = g2l ? g2l[g] : g;
+    if (l < 0 || l >= nlocal) return 1;
+    for (int j = 0; j < naq; ++j)
+      for (int i = 0; i < naq; ++i) {
+        if (kind == 0) {
+          J[j * naq + i] = 0.0 + D[(int64_t)(j * naq + i) * v->ld + g] * c_cell[c * naq + i];   // transport.F90:572-582
+          J[j * naq + i] = -J[j * naq + i];                                                      // :3215
+        } else {
+          J[j * naq + i] = 0.0 + c_cell[c * naq + i] * D[(int64_t)(j * naq + i) * v->ld + g];   // :3425-3429
+        }
+      }
+    double *dg = diag + l * nn;
+    for (int e = 0; e < nn; ++e) dg[e] = dg[e] + J[e];                  // MatSetValuesBlockedLocal(ADD_VALUES) :3217, :3430
+  }
+  return 0;
+}
+
 int orc_desc_size(void) { return (int)sizeof(RxnTablesDesc); }
 
 }  // extern "C"

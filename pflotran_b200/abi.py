@@ -283,3 +283,7 @@ class HostState:
             arr = self.a[name]
             v.f[i] = arr.ctypes.data_as(c_f64p) if arr.size else c_f64p()
         return v
+
+# coupler (boundary / source-sink) connection sets, include/rxn_b200.h
+RXN_COUPLER_BOUNDARY, RXN_COUPLER_SRC_SINK = 0, 1
+RXN_SS_MASS_RATE, RXN_SS_EQUILIBRIUM = 7, 12

@@ -98,6 +98,15 @@ struct RxnConnSet {
   bool have_coefs = false;
 };
 
+struct RxnCouplerSet {
+  RxnState *s = nullptr;
+  CouplerRows R;
+  int kind = 0, n = 0, device = 0;
+  int32_t *d_row = nullptr, *d_own = nullptr, *d_row_ptr = nullptr, *d_conn = nullptr;
+  double *d_ext = nullptr, *d_cx = nullptr, *d_cc = nullptr;   // external totals, coef_ext, coef_cell: SoA [component][connection]
+  bool have_coefs = false, have_totals = false;
+};
+
 namespace {
 
 int ensure_scratch(RxnState *s, int k, size_t bytes, void **out) {
@@ -982,6 +991,206 @@ int rxn_flux_jacobian_batch(RxnState *s, RxnConnSet *c, double *val_out) {
 }
 
 float rxn_last_kernel_ms(const RxnState *s) { return s ? s->last_ms : -1.f; }
+
+// ------------------------------------------------------------------ boundary conditions / source-sinks (rxn_flux.h)
+int rxn_couplerset_create(RxnState *s, int kind, int64_t nconn, const int32_t *id_dn, const int32_t *ghost_to_local, int64_t nlocal,
+                          const uint8_t *active, RxnCouplerSet **out) {
+  if (!s || !out || nconn < 0 || nlocal < 0 || (nconn > 0 && !id_dn) || (kind != RXN_COUPLER_BOUNDARY && kind != RXN_COUPLER_SRC_SINK))
+    return fail(RXN_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  CU(cudaSetDevice(s->t->device));
+  RxnCouplerSet *b = new RxnCouplerSet();
+  b->s = s; b->kind = kind; b->n = s->t->h.naq; b->device = s->t->device;
+  if (!coupler_rows_build(s->ncells, nlocal, nconn, id_dn, ghost_to_local, active, &b->R)) {
+    const std::string e = b->R.err;
+    delete b;
+    return fail(RXN_ERR_INVALID, "coupler set: %s", e.c_str());
+  }
+  auto up = [&](int32_t **d, const std::vector<int32_t> &v) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, std::max<size_t>(v.size(), 1) * 4);
+    if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(*d, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+    return e;
+  };
+  cudaError_t e = up(&b->d_row, b->R.row);
+  if (e == cudaSuccess) e = up(&b->d_own, b->R.own);
+  if (e == cudaSuccess) e = up(&b->d_row_ptr, b->R.row_ptr);
+  if (e == cudaSuccess) e = up(&b->d_conn, b->R.conn);
+  const size_t nb = std::max<size_t>((size_t)b->n * nconn, 1) * 8;
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_ext, nb);
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_cx, nb);
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_cc, nb);
+  if (e != cudaSuccess) {
+    rxn_couplerset_destroy(b);
+    return fail(RXN_ERR_CUDA, "coupler set upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = b;
+  return RXN_OK;
+}
+
+int rxn_couplerset_destroy(RxnCouplerSet *b) {
+  if (!b) return RXN_OK;
+  cudaSetDevice(b->device);
+  cudaFree(b->d_row); cudaFree(b->d_own); cudaFree(b->d_row_ptr); cudaFree(b->d_conn);
+  cudaFree(b->d_ext); cudaFree(b->d_cx); cudaFree(b->d_cc);
+  delete b;
+  return RXN_OK;
+}
+
+int rxn_couplerset_bc_coefs(RxnCouplerSet *b, const double *area, const double *velocity, const double *disp_over_dist,
+                            int use_upwinding) {
+  Nvtx nvtx_("TFluxCoef (boundary)");
+  if (!b || !area || !velocity || !disp_over_dist) return fail(RXN_ERR_INVALID, "bad argument");
+  if (b->kind != RXN_COUPLER_BOUNDARY) return fail(RXN_ERR_INVALID, "not a boundary coupler set");
+  RxnState *s = b->s;
+  const long long nc = b->R.nconn;
+  const int n = b->n;
+  if (nc == 0) { b->have_coefs = true; return RXN_OK; }
+  CU(cudaSetDevice(s->t->device));
+  void *tmp;
+  int rc = ensure_scratch(s, 0, (size_t)nc * (n + 3) * 8, &tmp);
+  if (rc != RXN_OK) return rc;
+  double *d_area = (double *)tmp, *d_vel = d_area + nc, *d_fu = d_vel + nc, *d_disp = d_fu + nc;
+  CU(cudaMemcpyAsync(d_area, area, (size_t)nc * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_vel, velocity, (size_t)nc * 8, cudaMemcpyHostToDevice, s->stream));
+  k_fill<<<nblocks(nc, 256), 256, 0, s->stream>>>(d_fu, nc, 0.5);                // fraction upwind of a boundary face (:2372)
+  CU(cudaMemcpyAsync(d_disp, disp_over_dist, (size_t)nc * n * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_flux_coefs<<<nblocks(nc, 256), 256, (size_t)256 * (n | 1) * 8, s->stream>>>(n, nc, d_area, d_vel, d_disp, d_fu, use_upwinding, b->d_cx,
+                                                                                b->d_cc);
+  g_launches += 2;
+  b->have_coefs = true;
+  return check_launch(s, true);
+}
+
+int rxn_couplerset_ss_coefs(RxnCouplerSet *b, const double *qsrc, const int32_t *tran_src_sink_type) {
+  Nvtx nvtx_("TSrcSinkCoef");
+  if (!b || !qsrc || !tran_src_sink_type) return fail(RXN_ERR_INVALID, "bad argument");
+  if (b->kind != RXN_COUPLER_SRC_SINK) return fail(RXN_ERR_INVALID, "not a source/sink coupler set");
+  RxnState *s = b->s;
+  const long long nc = b->R.nconn;
+  if (nc == 0) { b->have_coefs = true; return RXN_OK; }
+  CU(cudaSetDevice(s->t->device));
+  void *tmp;
+  int rc = ensure_scratch(s, 0, (size_t)nc * 12, &tmp);
+  if (rc != RXN_OK) return rc;
+  double *d_q = (double *)tmp;
+  int32_t *d_t = (int32_t *)(d_q + nc);
+  CU(cudaMemcpyAsync(d_q, qsrc, (size_t)nc * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_t, tran_src_sink_type, (size_t)nc * 4, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_coupler_ss_coefs<<<nblocks(nc, 256), 256, 0, s->stream>>>(b->n, nc, d_q, d_t, b->d_cx, b->d_cc);
+  ++g_launches;
+  b->have_coefs = true;
+  return check_launch(s, true);
+}
+
+int rxn_couplerset_set_totals(RxnCouplerSet *b, const double *total) {
+  if (!b || !total) return fail(RXN_ERR_INVALID, "bad argument");
+  RxnState *s = b->s;
+  const long long nc = b->R.nconn;
+  if (nc == 0) { b->have_totals = true; return RXN_OK; }
+  CU(cudaSetDevice(s->t->device));
+  void *tmp;
+  int rc = ensure_scratch(s, 0, (size_t)nc * b->n * 8, &tmp);
+  if (rc != RXN_OK) return rc;
+  CU(cudaMemcpyAsync(tmp, total, (size_t)nc * b->n * 8, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_coupler_totals<<<nblocks(nc * b->n, 256), 256, 0, s->stream>>>(b->n, nc, (const double *)tmp, 0, b->d_ext);
+  ++g_launches;
+  b->have_totals = true;
+  return check_launch(s, true);
+}
+
+int rxn_couplerset_totals_from_state(RxnCouplerSet *b, const RxnState *bc) {
+  if (!b || !bc) return fail(RXN_ERR_INVALID, "bad argument");
+  RxnState *s = b->s;
+  const long long nc = b->R.nconn;
+  if (bc->t->device != s->t->device) return fail(RXN_ERR_INVALID, "the boundary state lives on another device");
+  if (bc->t->h.naq != b->n) return fail(RXN_ERR_INVALID, "the boundary state has %d components, the coupler set %d", bc->t->h.naq, b->n);
+  if (bc->ncells < nc) return fail(RXN_ERR_INVALID, "the boundary state has %lld cells for %lld connections", (long long)bc->ncells, nc);
+  if (nc == 0) { b->have_totals = true; return RXN_OK; }
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaStreamSynchronize(bc->stream));                         // the boundary state's update runs on its own stream
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_coupler_totals<<<nblocks(nc * b->n, 256), 256, 0, s->stream>>>(b->n, nc, bc->S.f[RXN_F_TOTAL], bc->ld, b->d_ext);
+  ++g_launches;
+  b->have_totals = true;
+  return check_launch(s, true);
+}
+
+static int coupler_ready(RxnState *s, RxnCouplerSet *b, int field, const char *what) {
+  if (!s || !b || b->s != s) return fail(RXN_ERR_INVALID, "bad argument (the coupler set belongs to another state)");
+  if (!b->have_coefs) return fail(RXN_ERR_INVALID, "rxn_couplerset_bc_coefs / rxn_couplerset_ss_coefs has not been called");
+  if (!s->S.f[field]) return fail(RXN_ERR_INVALID, "%s is not materialised (rxn_state_materialize, then rxn_update_auxvars_batch)", what);
+  return RXN_OK;
+}
+
+int rxn_coupler_residual_batch_device(RxnState *s, RxnCouplerSet *b, double *d_res, double *d_flux_out) {
+  Nvtx nvtx_(b && b->kind == RXN_COUPLER_SRC_SINK ? "RTResidual (source/sink)" : "RTResidualFlux (boundary)");
+  int rc = coupler_ready(s, b, RXN_F_TOTAL, "total");
+  if (rc != RXN_OK) return rc;
+  if (!b->have_totals) return fail(RXN_ERR_INVALID, "the external totals have not been set (rxn_couplerset_set_totals / _totals_from_state)");
+  if (!d_res) return fail(RXN_ERR_INVALID, "null residual");
+  if (b->R.nrows == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_coupler_residual<<<nblocks(b->R.nrows * b->n, 128), 128, 0, s->stream>>>(
+      b->n, b->R.nrows, b->R.nconn, b->kind == RXN_COUPLER_BOUNDARY ? -1.0 : 1.0, b->d_row, b->d_own, b->d_row_ptr, b->d_conn,
+      s->S.f[RXN_F_TOTAL], s->ld, b->d_ext, b->d_cx, b->d_cc, d_res, d_flux_out);
+  ++g_launches;
+  return check_launch(s, true);
+}
+
+int rxn_coupler_jacobian_batch_device(RxnState *s, RxnConnSet *c, RxnCouplerSet *b, double *d_val) {
+  Nvtx nvtx_(b && b->kind == RXN_COUPLER_SRC_SINK ? "RTJacobianSS" : "RTJacobianFluxBC");
+  int rc = coupler_ready(s, b, RXN_F_DTOTAL, "dtotal");
+  if (rc != RXN_OK) return rc;
+  if (c && (c->s != s || c->R.nlocal != b->R.nlocal)) return fail(RXN_ERR_INVALID, "the connection set and the coupler set describe different grids");
+  if (!d_val) return fail(RXN_ERR_INVALID, "null matrix values");
+  if (b->R.nrows == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  k_coupler_jacobian<<<nblocks(b->R.nrows * b->n * b->n, 128), 128, 0, s->stream>>>(
+      b->n, b->R.nrows, b->R.nconn, b->kind == RXN_COUPLER_BOUNDARY ? -1.0 : 1.0, b->d_row, b->d_own, b->d_row_ptr, b->d_conn,
+      c ? c->d_row_ptr : nullptr, s->S.f[RXN_F_DTOTAL], s->ld, b->d_cc, d_val);
+  ++g_launches;
+  return check_launch(s, true);
+}
+
+int rxn_coupler_residual_batch(RxnState *s, RxnCouplerSet *b, double *res_inout, double *flux_out) {
+  if (!s || !b || !res_inout) return fail(RXN_ERR_INVALID, "bad argument");
+  if (b->R.nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const size_t bytes = (size_t)b->R.nlocal * b->n * 8, fbytes = (size_t)b->R.nconn * b->n * 8;
+  void *d, *df = nullptr;
+  int rc = ensure_scratch(s, 1, bytes, &d);
+  if (rc != RXN_OK) return rc;
+  if (flux_out && fbytes) {
+    if ((rc = ensure_scratch(s, 2, fbytes, &df)) != RXN_OK) return rc;
+    CU(cudaMemcpyAsync(df, flux_out, fbytes, cudaMemcpyHostToDevice, s->stream));   // rows of skipped connections keep the caller's values
+  }
+  CU(cudaMemcpyAsync(d, res_inout, bytes, cudaMemcpyHostToDevice, s->stream));
+  if ((rc = rxn_coupler_residual_batch_device(s, b, (double *)d, (double *)df)) != RXN_OK) return rc;
+  CU(cudaMemcpyAsync(res_inout, d, bytes, cudaMemcpyDeviceToHost, s->stream));
+  if (df) CU(cudaMemcpyAsync(flux_out, df, fbytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return RXN_OK;
+}
+
+int rxn_coupler_jacobian_batch(RxnState *s, RxnConnSet *c, RxnCouplerSet *b, double *val_inout) {
+  if (!s || !b || !val_inout) return fail(RXN_ERR_INVALID, "bad argument");
+  if (b->R.nlocal == 0) return RXN_OK;
+  CU(cudaSetDevice(s->t->device));
+  const size_t bytes = (size_t)(c ? c->R.nnzb : b->R.nlocal) * b->n * b->n * 8;
+  void *d;
+  int rc = ensure_scratch(s, 0, bytes, &d);
+  if (rc != RXN_OK) return rc;
+  CU(cudaMemcpyAsync(d, val_inout, bytes, cudaMemcpyHostToDevice, s->stream));
+  if ((rc = rxn_coupler_jacobian_batch_device(s, c, b, (double *)d)) != RXN_OK) return rc;
+  CU(cudaMemcpyAsync(val_inout, d, bytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return RXN_OK;
+}
 
 int rxn_state_device_ptr(RxnState *s, int field, double **d_ptr, int64_t *ld) {
   if (!s || field < 0 || field >= RXN_F_COUNT || !d_ptr) return fail(RXN_ERR_INVALID, "bad argument");

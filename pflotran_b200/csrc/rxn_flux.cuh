@@ -349,4 +349,70 @@ __global__ void __launch_bounds__(32 * FLUX_NW, FLUX_MINB) k_flux_jacobian_t(lon
   }
 }
 
+// ---- coupler connections (boundary conditions, source/sinks; rxn_flux.h) ---------------------------------------------
+// The sets are small (a grid's faces / wells): one thread per (row, component) resp. (row, block element); the row's
+// connections are added in connection order onto the values the interior kernels left in r / in the diagonal block.
+
+// TSrcSinkCoef per connection, coefficients repeated per component so that both kinds share the residual/Jacobian kernels
+__global__ void __launch_bounds__(256) k_coupler_ss_coefs(int n, long long nconn, const double *__restrict__ qsrc,
+                                                         const int32_t *__restrict__ type, double *__restrict__ c_ext,
+                                                         double *__restrict__ c_cell) {
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (c >= nconn) return;
+  double tin, tout;
+  ss_coef(qsrc[c], type[c], &tin, &tout);
+  for (int i = 0; i < n; ++i) { c_ext[(long long)i * nconn + c] = tout; c_cell[(long long)i * nconn + c] = tin; }
+}
+
+// AoS [connection][component] -> SoA [component][connection] (external totals handed over by the host or taken from the
+// TOTAL field of a boundary state: src_ld > 0 means src is SoA [component][src_ld] already and is copied row by row)
+__global__ void __launch_bounds__(256) k_coupler_totals(int n, long long nconn, const double *__restrict__ src, long long src_ld,
+                                                       double *__restrict__ ext) {
+  const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (k >= nconn * n) return;
+  const long long c = k / n;
+  const int i = (int)(k % n);
+  ext[(long long)i * nconn + c] = src_ld > 0 ? src[(long long)i * src_ld + c] : src[k];
+}
+
+__global__ void __launch_bounds__(128) k_coupler_residual(int n, long long nrows, long long nconn, double sgn,
+                                                         const int32_t *__restrict__ row, const int32_t *__restrict__ own,
+                                                         const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ conn,
+                                                         const double *__restrict__ total, long long ld,
+                                                         const double *__restrict__ ext, const double *__restrict__ c_ext,
+                                                         const double *__restrict__ c_cell, double *__restrict__ r,
+                                                         double *__restrict__ flux_out) {
+  const long long k = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (k >= nrows * n) return;
+  const long long q = k / n;
+  const int i = (int)(k % n);
+  const int s0 = row_ptr[q], s1 = row_ptr[q + 1];
+  const double t_own = total[(long long)i * ld + own[q]];
+  const double *ext_i = ext + (long long)i * nconn, *cx_i = c_ext + (long long)i * nconn, *cc_i = c_cell + (long long)i * nconn;
+  double *rp = r + (long long)row[q] * n + i;
+  *rp = coupler_row_residual(*rp, conn, s0, s1, sgn, ext_i, cx_i, cc_i, t_own);
+  if (flux_out)                                                 // patch%boundary_tran_fluxes = -Res / patch%ss_tran_fluxes = Res
+    for (int s = s0; s < s1; ++s) {
+      const int32_t c = conn[s];
+      flux_out[(long long)c * n + i] = fl_mul(sgn, coupler_res(cx_i[c], ext_i[c], cc_i[c], t_own));
+    }
+}
+
+// diag: base of the block array, blk[q] = index of the diagonal block of row q in it (block-CSR slot row_ptr[row] of the
+// connection set, or the local row itself for a plain [nlocal][n*n] array)
+__global__ void __launch_bounds__(128) k_coupler_jacobian(int n, long long nrows, long long nconn, double sgn,
+                                                         const int32_t *__restrict__ row, const int32_t *__restrict__ own,
+                                                         const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ conn,
+                                                         const int32_t *__restrict__ csr_row_ptr, const double *__restrict__ dtotal,
+                                                         long long ld, const double *__restrict__ c_cell, double *__restrict__ val) {
+  const int nn = n * n;
+  const long long k = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (k >= nrows * nn) return;
+  const long long q = k / nn;
+  const int e = (int)(k % nn), i = e % n;                       // e = j*n + i (column-major block)
+  const long long blk = csr_row_ptr ? (long long)csr_row_ptr[row[q]] : (long long)row[q];
+  double *vp = val + blk * nn + e;
+  *vp = coupler_row_jac(*vp, conn, row_ptr[q], row_ptr[q + 1], sgn, c_cell + (long long)i * nconn, dtotal[(long long)e * ld + own[q]]);
+}
+
 }  // namespace rxn

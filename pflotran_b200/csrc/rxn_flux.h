@@ -157,4 +157,85 @@ RXN_FLUX_FN double flux_row_jac_off(int32_t e, double D_nb_ij, const double *Tu_
   return (e & 1) ? -fl_mul(D_nb_ij, Tu_i[c]) : fl_mul(D_nb_ij, Td_i[c]);
 }
 
+// ---- one-sided ("coupler") connections: boundary conditions and source/sinks -----------------------------------------
+// Reference: the boundary-connection loops of RTResidualFlux (reactive_transport.F90:2347-2430) and RTJacobianFlux
+// (:3176-3240) and the source/sink loops of RTResidualNonFlux (:2623-2672) and RTJacobianNonFlux (:3394-3436).  A coupler
+// connection joins one local cell with an external total (the boundary auxvar / the source-sink constraint):
+//   boundary   : Res = coef_up total_ext + coef_dn total_cell, r_p -= Res, diagonal block -= dtotal_cell(i,:) coef_dn(i)
+//   source/sink: Res = coef_in total_cell + coef_out total_ext, r_p += Res, diagonal block += coef_in dtotal_cell
+// Several connections may sit on one cell (corners; a well in a boundary cell): as for the interior connections the
+// host builds the row view, and one thread adds a row's contributions in connection order - the order of the reference's
+// scatter - onto what the interior loop left there.
+enum { COUPLER_BOUNDARY = 0, COUPLER_SRC_SINK = 1 };
+
+// TSrcSinkCoef, transport.F90:901-954 (liquid phase); type: tran_condition%itype (EQUILIBRIUM_SS = 12, MASS_RATE_SS = 7)
+RXN_FLUX_FN void ss_coef(double qsrc, int type, double *T_in, double *T_out) {
+  if (type == 12) { *T_in = 1.0e-3; *T_out = fl_mul(-1.0, 1.0e-3); }
+  else if (type == 7) { *T_in = 0.0; *T_out = -1.0; }
+  else if (qsrc > 0.0) { *T_in = 0.0; *T_out = fl_mul(fl_mul(-1.0, qsrc), 1000.0); }
+  else { *T_out = 0.0; *T_in = fl_mul(fl_mul(-1.0, qsrc), 1000.0); }
+}
+
+struct CouplerRows {
+  int64_t nlocal = 0, nconn = 0, nrows = 0;
+  std::vector<int32_t> row;       // nrows: local row of the cells that have coupler connections, ascending
+  std::vector<int32_t> own;       // nrows: ghosted id of that cell
+  std::vector<int32_t> row_ptr;   // nrows + 1 into conn
+  std::vector<int32_t> conn;      // connection ids, per row in connection order (inactive cells' connections dropped)
+  std::string err;
+};
+
+inline bool coupler_rows_build(int64_t nghosted, int64_t nlocal, int64_t nconn, const int32_t *id_dn, const int32_t *g2l,
+                               const uint8_t *active, CouplerRows *R) {
+  R->nlocal = nlocal; R->nconn = nconn;
+  if (nconn >= (1LL << 31)) { R->err = "more than 2^31 coupler connections"; return false; }
+  if (!g2l && nlocal != nghosted) { R->err = "identity ghosted->local map needs nlocal == ncells_ghosted"; return false; }
+  std::vector<int32_t> cnt(nlocal, 0), gid(nlocal, -1);
+  for (int64_t c = 0; c < nconn; ++c) {
+    const int64_t g = id_dn[c];
+    if (g < 0 || g >= nghosted) { R->err = "coupler connection id out of range"; return false; }
+    const int64_t l = g2l ? (int64_t)g2l[g] : g;
+    if (l < 0 || l >= nlocal) { R->err = "a coupler connection sits on a ghost cell"; return false; }
+    if (active && !active[g]) continue;                          // imat <= 0: cycle
+    ++cnt[l]; gid[l] = (int32_t)g;
+  }
+  std::vector<int32_t> slot(nlocal, -1);
+  R->row.clear(); R->own.clear(); R->row_ptr.assign(1, 0);
+  for (int64_t l = 0; l < nlocal; ++l)
+    if (cnt[l] > 0) {
+      slot[l] = (int32_t)R->row.size();
+      R->row.push_back((int32_t)l); R->own.push_back(gid[l]);
+      R->row_ptr.push_back(R->row_ptr.back() + cnt[l]);
+    }
+  R->nrows = (int64_t)R->row.size();
+  R->conn.assign(R->row_ptr.back(), -1);
+  std::vector<int32_t> cur(R->row_ptr.begin(), R->row_ptr.end() - 1);
+  for (int64_t c = 0; c < nconn; ++c) {
+    const int64_t g = id_dn[c];
+    if (active && !active[g]) continue;
+    const int64_t l = g2l ? (int64_t)g2l[g] : g;
+    R->conn[cur[slot[l]]++] = (int32_t)c;
+  }
+  return true;
+}
+
+// Res of component i of connection c (kind decides nothing here: the sum of the two products commutes)
+RXN_FLUX_FN double coupler_res(double c_ext, double tot_ext, double c_cell, double tot_cell) {
+  return fl_add(fl_mul(c_ext, tot_ext), fl_mul(c_cell, tot_cell));
+}
+// r_p of component i after the row's coupler connections; sgn = -1 (boundary) / +1 (source/sink).  x - y == x + (-y) exactly.
+RXN_FLUX_FN double coupler_row_residual(double r, const int32_t *conn, int s0, int s1, double sgn, const double *ext_i, const double *cx_i,
+                                        const double *cc_i, double tot_own) {
+  for (int s = s0; s < s1; ++s) {
+    const int32_t c = conn[s];
+    r = fl_add(r, fl_mul(sgn, coupler_res(cx_i[c], ext_i[c], cc_i[c], tot_own)));   // sgn = +-1: the product is exact
+  }
+  return r;
+}
+// diagonal-block element (i, j) after the row's coupler connections
+RXN_FLUX_FN double coupler_row_jac(double a, const int32_t *conn, int s0, int s1, double sgn, const double *cc_i, double D_own_ij) {
+  for (int s = s0; s < s1; ++s) a = fl_add(a, fl_mul(sgn, fl_mul(D_own_ij, cc_i[conn[s]])));
+  return a;
+}
+
 }  // namespace rxn

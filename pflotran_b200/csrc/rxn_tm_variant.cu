@@ -22,18 +22,21 @@ k_react_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h,
            const double *__restrict__ blob, DevState S, double *tran_xx, const int32_t *__restrict__ l2g, long long nlocal, double dt,
            int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter, long long cell0) {
   constexpr int CPB = 32 * QUADS;
-  __shared__ unsigned tmem_base_s;
+#ifndef TM_ALLOC_SLOT
+#define TM_ALLOC_SLOT 0            /* experiment hook: which word receives the tcgen05.alloc result (compute-sanitizer synccheck reports it as a barrier) */
+#endif
+  __shared__ unsigned tmem_base_w[4];
   const int words = lt.blob_dbl + lt.blob_int / 2;
   for (int w = threadIdx.x; w < words; w += blockDim.x) tsm[w] = pblob[w];
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_s)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_w[TM_ALLOC_SLOT])));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n");
-  const unsigned tmem_base = tmem_base_s;
+  const unsigned tmem_base = tmem_base_w[TM_ALLOC_SLOT];
   const int quad = warp & 3, l = warp >> 2;
   if (quad < QUADS) {
     const double *bd = blob;

@@ -66,6 +66,16 @@ def lib():
         L.rxn_flux_jacobian_batch.argtypes = [C.c_void_p, C.c_void_p, c_dp]
         L.rxn_flux_residual_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rxn_flux_jacobian_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rxn_couplerset_create.argtypes = [C.c_void_p, C.c_int, c_i64, c_ip, c_ip, c_i64, C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]
+        L.rxn_couplerset_destroy.argtypes = [C.c_void_p]
+        L.rxn_couplerset_bc_coefs.argtypes = [C.c_void_p, c_dp, c_dp, c_dp, C.c_int]
+        L.rxn_couplerset_ss_coefs.argtypes = [C.c_void_p, c_dp, c_ip]
+        L.rxn_couplerset_set_totals.argtypes = [C.c_void_p, c_dp]
+        L.rxn_couplerset_totals_from_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.rxn_coupler_residual_batch.argtypes = [C.c_void_p, C.c_void_p, c_dp, c_dp]
+        L.rxn_coupler_jacobian_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, c_dp]
+        L.rxn_coupler_residual_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rxn_coupler_jacobian_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.rxn_equilibrate_constraint_batch.argtypes = [C.c_void_p, c_ip, c_dp, c_i64, c_ip, c_dp, C.c_int, C.c_int, c_ip, c_i64,
                                                        c_dp, c_ip, c_ip]
         L.rxn_state_upload.argtypes = [C.c_void_p, C.c_int, c_dp, c_i64, c_i64]
@@ -195,6 +205,51 @@ class ConnectionSet:
             pass
 
 
+class CouplerSet:
+    """Flattened patch%boundary_condition_list (kind abi.RXN_COUPLER_BOUNDARY) or patch%source_sink_list
+    (abi.RXN_COUPLER_SRC_SINK) of a realization: one-sided connections between a local cell and an external total
+    (reactive_transport.F90:2347-2430, 3176-3240; :2623-2672, 3394-3436)."""
+
+    def __init__(self, realization: 'Realization', kind: int, id_dn: np.ndarray, nlocal: int,
+                 ghost_to_local: Optional[np.ndarray] = None, active: Optional[np.ndarray] = None):
+        self.rz, self.kind, self.nlocal, self.nconn = realization, kind, int(nlocal), len(id_dn)
+        self.h = C.c_void_p()
+        dn = np.ascontiguousarray(id_dn, dtype=np.int32)
+        g2l = None if ghost_to_local is None else np.ascontiguousarray(ghost_to_local, dtype=np.int32)
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
+        _ck(lib().rxn_couplerset_create(realization.h, kind, self.nconn, _ip(dn), _ip(g2l), self.nlocal,
+                                        act.ctypes.data_as(C.POINTER(C.c_uint8)) if act is not None else None, C.byref(self.h)))
+
+    def TFluxCoefBC(self, area, velocity, disp_over_dist, use_upwinding: bool = True):
+        """TFluxCoef with fraction_upwind = 0.5 (reactive_transport.F90:2369-2373)."""
+        _ck(lib().rxn_couplerset_bc_coefs(self.h, _dp(np.ascontiguousarray(area)), _dp(np.ascontiguousarray(velocity)),
+                                          _dp(np.ascontiguousarray(disp_over_dist)), int(use_upwinding)))
+
+    def TSrcSinkCoef(self, qsrc, tran_src_sink_type):
+        """transport.F90:901-954."""
+        _ck(lib().rxn_couplerset_ss_coefs(self.h, _dp(np.ascontiguousarray(qsrc, dtype=np.float64)),
+                                          _ip(np.ascontiguousarray(tran_src_sink_type, dtype=np.int32))))
+
+    def set_totals(self, total: np.ndarray):
+        assert total.shape == (self.nconn, self.rz.ncomp)
+        _ck(lib().rxn_couplerset_set_totals(self.h, _dp(np.ascontiguousarray(total))))
+
+    def totals_from_state(self, bc_realization: 'Realization'):
+        """rt_auxvars_bc(:)%total of the boundary realization (one cell per connection)."""
+        _ck(lib().rxn_couplerset_totals_from_state(self.h, bc_realization.h))
+
+    def close(self):
+        if self.h:
+            lib().rxn_couplerset_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Realization:
     """Per-rank cell state (rt_auxvars + global/material auxvars of the ghosted cells,
     reactive_transport.F90:271-274) resident in HBM, with the reference's cell loops as methods."""
@@ -315,12 +370,18 @@ class Realization:
         _ck(lib().rxn_fixed_accum_batch(self.h, _dp(xx), _ip(l2g), n, _dp(out)))
         return out
 
-    def RTResidualJacobianNonFlux(self, dt: float, l2g: Optional[np.ndarray] = None, residual=True, jacobian=True):
+    def RTResidualJacobianNonFlux(self, dt: float, l2g: Optional[np.ndarray] = None, residual=True, jacobian=True,
+                                  res: Optional[np.ndarray] = None, jac: Optional[np.ndarray] = None):
         """Accumulation + reaction parts of RTResidualNonFlux (:2436) and RTJacobianNonFlux (:3247):
-        res [nlocal, ncomp], jac [nlocal, ncomp*ncomp] (column-major blocks)."""
+        res [nlocal, ncomp], jac [nlocal, ncomp*ncomp] (column-major blocks); `res` / `jac`: caller-owned output buffers
+        (e.g. pinned), else new arrays."""
         n = self.ncells if l2g is None else len(l2g)
-        res = np.zeros((n, self.ncomp)) if residual else None
-        jac = np.zeros((n, self.ncomp * self.ncomp)) if jacobian else None
+        if res is None:
+            res = np.zeros((n, self.ncomp)) if residual else None
+        if jac is None:
+            jac = np.zeros((n, self.ncomp * self.ncomp)) if jacobian else None
+        assert res is None or res.shape == (n, self.ncomp)
+        assert jac is None or jac.shape == (n, self.ncomp * self.ncomp)
         _ck(lib().rxn_residual_jacobian_blocks_batch(self.h, _ip(l2g), n, dt, _dp(res), _dp(jac)))
         return res, jac
 
@@ -379,6 +440,30 @@ class Realization:
         val = np.zeros((conn.nnz_blocks, n * n))
         _ck(lib().rxn_flux_jacobian_batch(self.h, conn.h, _dp(val)))
         return val
+
+    def RTResidualCoupler(self, cs: 'CouplerSet', res: np.ndarray, want_flux: bool = False):
+        """Boundary part of RTResidualFlux (:2347-2430) / source-sink part of RTResidualNonFlux (:2623-2672): res [nlocal, ncomp]
+        is updated in place; returns patch%boundary_tran_fluxes / patch%ss_tran_fluxes [nconn, ncomp] when asked."""
+        assert res.shape == (cs.nlocal, self.ncomp) and res.flags.c_contiguous
+        flux = np.zeros((cs.nconn, self.ncomp)) if want_flux else None
+        _ck(lib().rxn_coupler_residual_batch(self.h, cs.h, _dp(res), _dp(flux)))
+        return flux
+
+    def RTJacobianCoupler(self, cs: 'CouplerSet', val: np.ndarray, conn: Optional['ConnectionSet'] = None):
+        """Boundary part of RTJacobianFlux (:3176-3240) / source-sink part of RTJacobianNonFlux (:3394-3436), added into the
+        diagonal blocks of `val`: the block-CSR values of `conn`, or [nlocal, ncomp*ncomp] diagonal blocks without it."""
+        assert val.flags.c_contiguous and val.shape == ((conn.nnz_blocks if conn is not None else cs.nlocal), self.ncomp * self.ncomp)
+        _ck(lib().rxn_coupler_jacobian_batch(self.h, conn.h if conn is not None else None, cs.h, _dp(val)))
+
+    def boundary_free_ion(self, bc_type, basis_molarity, den_kg_bc, boundary_velocity, xx_loc_cells):
+        """xxbc of every boundary connection as RTUpdateAuxVars builds it (reactive_transport.F90:3935-3990, liquid phase, no
+        colloids): DIRICHLET (1) / CONCENTRATION_SS / NEUMANN -> basis_molarity / den_kg * 1000; ZERO_GRADIENT (4) -> the
+        cell's free-ion molalities; DIRICHLET_ZERO_GRADIENT (3) -> Dirichlet where the boundary velocity is >= 0 (inflow), else
+        zero gradient.  Pure data movement for the call that follows it: bc.RTUpdateAuxVars(xxbc, ...) on the boundary realization."""
+        bc_type = np.asarray(bc_type)
+        dirichlet = basis_molarity / np.asarray(den_kg_bc)[:, None] * 1000.0
+        zero_grad = (bc_type == 4) | ((bc_type == 3) & ~(np.asarray(boundary_velocity) >= 0.0))
+        return np.ascontiguousarray(np.where(zero_grad[:, None], xx_loc_cells, dirichlet))
 
     def RTResidualFlux_device(self, conn: 'ConnectionSet', d_res: int):
         _ck(lib().rxn_flux_residual_batch_device(self.h, conn.h, C.c_void_p(d_res)))

@@ -456,5 +456,42 @@ int64_t emu_flux(const HostView *v, const uint8_t *active, int n, int64_t nconn,
   return R.nnzb;
 }
 
+// Coupler connections (boundary / source-sink) through the row view and per-row arithmetic of rxn_flux.h, i.e. what
+// k_coupler_residual / k_coupler_jacobian implement.  c_ext / c_cell: nconn x n coefficient arrays for kind 0 (from
+// flux_coef with fraction_upwind = 0.5, computed here from area / velocity / disp) or qsrc / type for kind 1.
+// res [nlocal][n] and diag [nlocal][n*n] are updated in place; flux_out [nconn][n] optional.  Returns 0, < 0 on a structure error.
+int emu_coupler(const HostView *v, const uint8_t *active, int kind, int n, int64_t nconn, const int32_t *id_dn, const int32_t *g2l,
+                int64_t nlocal, const double *area, const double *velocity, const double *disp, int use_upwinding, const double *qsrc,
+                const int32_t *ss_type, const double *ext_total, double *res, double *flux_out, double *diag) {
+  CouplerRows R;
+  if (!coupler_rows_build(v->ncells, nlocal, nconn, id_dn, g2l, active, &R)) return -1;
+  std::vector<double> cx((size_t)n * nconn), cc((size_t)n * nconn), ext((size_t)n * nconn);
+  for (int64_t c = 0; c < nconn; ++c)
+    for (int i = 0; i < n; ++i) {
+      if (kind == COUPLER_BOUNDARY) flux_coef(velocity[c], disp[c * n + i], area[c], 0.5, use_upwinding, &cx[(size_t)i * nconn + c], &cc[(size_t)i * nconn + c]);
+      else ss_coef(qsrc[c], ss_type[c], &cc[(size_t)i * nconn + c], &cx[(size_t)i * nconn + c]);
+      ext[(size_t)i * nconn + c] = ext_total[c * n + i];
+    }
+  const double sgn = kind == COUPLER_BOUNDARY ? -1.0 : 1.0;
+  const double *tot = v->f[RXN_F_TOTAL], *D = v->f[RXN_F_DTOTAL];
+  for (int64_t q = 0; q < R.nrows; ++q) {
+    const int s0 = R.row_ptr[q], s1 = R.row_ptr[q + 1];
+    const int64_t row = R.row[q], own = R.own[q];
+    for (int i = 0; i < n; ++i) {
+      const double t_own = tot[(int64_t)i * v->ld + own];
+      if (res) res[row * n + i] = coupler_row_residual(res[row * n + i], R.conn.data(), s0, s1, sgn, &ext[(size_t)i * nconn], &cx[(size_t)i * nconn], &cc[(size_t)i * nconn], t_own);
+      if (flux_out)
+        for (int s = s0; s < s1; ++s) {
+          const int32_t c = R.conn[s];
+          flux_out[(int64_t)c * n + i] = fl_mul(sgn, coupler_res(cx[(size_t)i * nconn + c], ext[(size_t)i * nconn + c], cc[(size_t)i * nconn + c], t_own));
+        }
+    }
+    if (diag)
+      for (int e = 0; e < n * n; ++e)
+        diag[row * n * n + e] = coupler_row_jac(diag[row * n * n + e], R.conn.data(), s0, s1, sgn, &cc[(size_t)(e % n) * nconn], D[(int64_t)e * v->ld + own]);
+  }
+  return 0;
+}
+
 }  // extern "C"
 

@@ -194,3 +194,20 @@ def flux(st, conn, nlocal, use_upwinding=True):
     val = np.zeros((nnzb, n * n))
     assert L.emu_flux(*args(col, res, val)) == nnzb
     return row_ptr, col, res, val
+
+
+def coupler(st, kind, id_dn, nlocal, ext_total, g2l=None, area=None, velocity=None, disp=None, use_upwinding=True, qsrc=None, ss_type=None,
+            res=None, diag=None, want_flux=False):
+    """Boundary (kind 0) / source-sink (kind 1) connections through the row view and per-row arithmetic of rxn_flux.h.
+    res [nlocal, n] and diag [nlocal, n*n] are updated in place; returns flux_out [nconn, n] or None."""
+    n = st.t.naqcomp
+    nconn = len(id_dn)
+    v = st.view()
+    flux = np.zeros((nconn, n)) if want_flux else None
+    rc = lib().emu_coupler(C.byref(v), _p(st.active, C.c_uint8), C.c_int(kind), C.c_int(n), C.c_int64(nconn), _p(id_dn, C.c_int32),
+                           _p(g2l, C.c_int32), C.c_int64(nlocal), _p(area, C.c_double), _p(velocity, C.c_double), _p(disp, C.c_double),
+                           C.c_int(int(use_upwinding)), _p(qsrc, C.c_double), _p(ss_type, C.c_int32), _p(ext_total, C.c_double),
+                           _p(res, C.c_double), _p(flux, C.c_double), _p(diag, C.c_double))
+    if rc != 0:
+        raise ValueError('coupler set rejected')
+    return flux

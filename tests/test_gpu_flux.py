@@ -7,7 +7,8 @@ import pytest
 from pflotran_b200 import synth, reactive_transport as rt
 from oracle.pyoracle import Oracle
 from common import workload_cells, RTOL
-from flux_common import structured_connections, random_connections
+from flux_common import structured_connections, random_connections, boundary_connections, source_sinks
+from pflotran_b200 import abi
 
 pytestmark = pytest.mark.gpu
 
@@ -192,3 +193,92 @@ def test_flux_full_size_properties():
         np.testing.assert_array_equal(col[row_ptr[c]:row_ptr[c + 1]], col_o[rp_o[c]:rp_o[c + 1]])
         np.testing.assert_array_equal(val[row_ptr[c]:row_ptr[c + 1]], val_o[rp_o[c]:rp_o[c + 1]])
     cs.close()
+
+
+@pytest.mark.parametrize('name,dims,ghost,inactive,upwind', [('calcite', (17, 9, 5), 0, 0.0, True), ('calcite', (13, 7, 3), 1, 0.1, False),
+                                                             ('hanford300a_eq', (9, 6, 5), 1, 0.05, True)])
+def test_boundary_and_source_sink_bitwise(name, dims, ghost, inactive, upwind):
+    """Boundary-condition and source/sink connections (rxn_couplerset_* / rxn_coupler_*_batch) on top of the interior-flux
+    result, against the oracle's restatement of the reference loops: bit for bit, corner cells (three faces on one cell), two
+    wells in one cell and inactive cells included.  The boundary auxvars are a second realization with one cell per
+    connection, built as RTUpdateAuxVars does (reactive_transport.F90:3851-4030: Dirichlet / zero gradient / Dirichlet-zero-
+    gradient faces) and updated on the GPU; its totals are handed over on the device."""
+    w, st, xx, conn, nlocal = _setup(name, *dims, ghost, inactive)
+    n = w.tables.naqcomp
+    o = Oracle(w.tables)
+    o.update_auxvars(st, xx, True)
+    Tu, Td = o.flux_coefs(conn, n, use_upwinding=upwind)
+    r_o = o.flux_residual(st, conn, Tu, Td, nlocal)
+    rp_o, col_o, val_o = o.flux_jacobian(st, conn, Tu, Td, nlocal)
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, st.ncells)
+    rz.upload_host_state(st)
+    rz.upload('DTOTAL', st['DTOTAL'])
+    cs = rt.ConnectionSet(rz, conn['id_up'], conn['id_dn'], nlocal, conn['g2l'], st.active)
+    cs.TFluxCoef(conn['area'], conn['velocity'], conn['disp'], conn['fraction_upwind'], upwind)
+    r_g = rz.RTResidualFlux(cs)
+    val_g = rz.RTJacobianFlux(cs)
+    # ---- boundary faces: the boundary realization
+    bc = boundary_connections(*dims, n, ghost_layers=ghost)
+    nb = len(bc['id_dn'])
+    basis_molarity = np.tile(w.base['PRI_MOLAL'] * w.base['DEN_KG'][0] * 1.0e-3 * 1.2, (nb, 1))
+    den_bc = np.full(nb, w.base['DEN_KG'][0])
+    xxbc = rz.boundary_free_ion(bc['bc_type'], basis_molarity, den_bc, bc['velocity'], xx[bc['id_dn']])
+    zg = (bc['bc_type'] == 4) | ((bc['bc_type'] == 3) & (bc['velocity'] < 0))
+    assert (xxbc[zg] == xx[bc['id_dn']][zg]).all() and (xxbc[~zg] != xx[bc['id_dn']][~zg]).any()
+    wb, cells_b = workload_cells(name, nb)
+    st_b = synth.host_state(wb, cells_b)
+    bz = rt.Realization(rx, nb)
+    bz.upload_host_state(st_b)
+    bz.RTUpdateAuxVars(xxbc, True)
+    o.update_auxvars(st_b, xxbc, True)
+    ext = np.ascontiguousarray(st_b['TOTAL'].T)
+    np.testing.assert_allclose(bz.download('TOTAL').T, ext, rtol=1e-12)
+    bs = rt.CouplerSet(rz, abi.RXN_COUPLER_BOUNDARY, bc['id_dn'], nlocal, conn['g2l'], st.active)
+    bs.TFluxCoefBC(bc['area'], bc['velocity'], bc['disp'], upwind)
+    bs.set_totals(ext)                                     # the oracle's totals, so that the comparison below is bit for bit
+    cu, cd = Oracle.flux_coefs({**bc, 'fraction_upwind': np.full(nb, 0.5)}, n, use_upwinding=upwind)
+    f_o = o.coupler_residual(st, 0, bc['id_dn'], ext, cu, cd, nlocal, r_o, g2l=conn['g2l'], want_flux=True)
+    d_o = np.ascontiguousarray(val_o[rp_o[:-1]])
+    o.coupler_jacobian(st, 0, bc['id_dn'], cd, nlocal, d_o, g2l=conn['g2l'])
+    val_o[rp_o[:-1]] = d_o
+    f_g = rz.RTResidualCoupler(bs, r_g, want_flux=True)
+    rz.RTJacobianCoupler(bs, val_g, cs)
+    np.testing.assert_array_equal(r_g, r_o)
+    live = st.active[bc['id_dn']] != 0
+    np.testing.assert_array_equal(f_g[live], f_o[live])
+    np.testing.assert_array_equal(val_g, val_o)
+    # the same faces with the totals taken from the boundary realization on the device: same result to rounding of its totals
+    bs.totals_from_state(bz)
+    r2 = rz.RTResidualFlux(cs)
+    rz.RTResidualCoupler(bs, r2)
+    scale = np.abs(cu).max() * np.abs(ext).max(axis=0)
+    assert (np.abs(r2 - r_o) <= 1e-11 * scale[None, :]).all()
+    # ---- source/sinks, onto plain diagonal blocks (the layout of rxn_jacobian_blocks_batch)
+    local_g = np.where(conn['g2l'] >= 0)[0] if conn['g2l'] is not None else np.arange(nlocal)
+    ss = source_sinks(local_g, n)
+    tin, tout = Oracle.ss_coefs(ss['qsrc'], ss['ss_type'])
+    ext_s = np.ascontiguousarray(np.tile(w.base['TOTAL'] * 0.7, (len(tin), 1)))
+    c_in, c_out = np.repeat(tin[:, None], n, 1).copy(), np.repeat(tout[:, None], n, 1).copy()
+    o.coupler_residual(st, 1, ss['id_dn'], ext_s, c_out, c_in, nlocal, r_o, g2l=conn['g2l'])
+    diag_o = np.zeros((nlocal, n * n))
+    o.coupler_jacobian(st, 1, ss['id_dn'], c_in, nlocal, diag_o, g2l=conn['g2l'])
+    sk = rt.CouplerSet(rz, abi.RXN_COUPLER_SRC_SINK, ss['id_dn'], nlocal, conn['g2l'], st.active)
+    sk.TSrcSinkCoef(ss['qsrc'], ss['ss_type'])
+    sk.set_totals(ext_s)
+    rz.RTResidualCoupler(sk, r_g)
+    diag_g = np.zeros((nlocal, n * n))
+    rz.RTJacobianCoupler(sk, diag_g)
+    np.testing.assert_array_equal(r_g, r_o)
+    np.testing.assert_array_equal(diag_g, diag_o)
+    assert np.abs(diag_o).max() > 0
+    # misuse: coefficients / totals missing, foreign state
+    b2 = rt.CouplerSet(rz, abi.RXN_COUPLER_BOUNDARY, bc['id_dn'], nlocal, conn['g2l'], st.active)
+    with pytest.raises(rt.RxnError) as e:
+        rz.RTResidualCoupler(b2, r_g)
+    assert e.value.status == abi.RXN_ERR_INVALID
+    with pytest.raises(rt.RxnError) as e:
+        bz.RTResidualCoupler(bs, np.zeros((nlocal, n)))
+    assert e.value.status == abi.RXN_ERR_INVALID
+    for x in (b2, sk, bs, cs):
+        x.close()

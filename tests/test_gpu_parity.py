@@ -208,6 +208,7 @@ def test_global_implicit_entry_points_report_failed_cells():
         rz.RTResidualJacobianNonFlux(1800.0)
     assert e.value.status == abi.RXN_ERR_CELL_FAILED
     xx[17, 0] = w.base['PRI_MOLAL'][0]
+    rz.upload_host_state(st)                           # the NaN cell poisoned its lagged sec_molal (as it would in the reference)
     rz.RTUpdateAuxVars(xx, True)                       # the flag word is per call
     l2g = np.array([0, 5, 256], dtype=np.int32)
     with pytest.raises(rt.RxnError) as e:
