@@ -84,7 +84,7 @@ struct RxnState {
   cudaStream_t h2d = nullptr, d2h = nullptr;
   cudaEvent_t ev_in[NCHUNK] = {}, ev_k[NCHUNK] = {};
   int flux_generic = 0;    // RXN_FLUX_GENERIC=1: flux Jacobian through the run-time-n kernel (tests)
-  int gi_kernel = 0;       // residual/Jacobian blocks: 0 auto (resident-lane layout if the tables allow it), 1 thread per cell
+  int gi_kernel = 0;       // global-implicit loops (RXN_GI_KERNEL): 0 auto (tensor-memory layout, else resident lanes, else thread per cell), 1 thread per cell, 2 resident lanes
   unsigned int *d_fail = nullptr;   // OR of the cell flags of the running global-implicit launch (DevState::fail)
 };
 
@@ -574,6 +574,38 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
   return RXN_OK;
 }
 
+// RTUpdateAuxVars / RTUpdateFixedAccumulation cell loops: the tensor-memory layout when the tables allow it (tm_gi_cell,
+// rxn_tm_dev.cuh), else one thread per cell (rxn_device.cuh)
+static int launch_update_auxvars(RxnState *s, const double *d_xx, int update_act_coefs) {
+  const RxnTables *t = s->t;
+  if (s->gi_kernel == 0 && tm_gi_usable(t->lane, update_act_coefs)) {
+    const GiArgs a{GI_AUX, update_act_coefs, d_xx, 0, nullptr, nullptr, nullptr, 1.0};
+    int rc = tm_launch_gi(t->lane, t->h, t->d_blob, s->S, nullptr, s->ncells, a, s->stream);
+    if (rc != RXN_OK) return fail(rc, "tensor-memory auxvar kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ++g_launches;
+    return RXN_OK;
+  }
+  const int threads = t->nvariant <= 8 ? 128 : 64;
+  const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
+  RXN_DISPATCH(t->nvariant, run_update_auxvars, L, t->h, (const double *)t->d_blob, s->S, d_xx, update_act_coefs);
+  return RXN_OK;
+}
+
+static int launch_fixed_accum(RxnState *s, const double *d_xx, const int32_t *d_l2g, int64_t nlocal, double *d_out) {
+  const RxnTables *t = s->t;
+  if (s->gi_kernel == 0 && tm_gi_usable(t->lane, 0)) {
+    const GiArgs a{GI_AUX, 0, d_xx, 1, d_out, nullptr, nullptr, 1.0};
+    int rc = tm_launch_gi(t->lane, t->h, t->d_blob, s->S, d_l2g, (long long)nlocal, a, s->stream);
+    if (rc != RXN_OK) return fail(rc, "tensor-memory accumulation kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ++g_launches;
+    return RXN_OK;
+  }
+  const int threads = t->nvariant <= 8 ? 128 : 64;
+  const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
+  RXN_DISPATCH(t->nvariant, run_fixed_accum, L, t->h, (const double *)t->d_blob, s->S, d_xx, (const int *)d_l2g, (long long)nlocal, d_out);
+  return RXN_OK;
+}
+
 int rxn_update_auxvars_batch(RxnState *s, const double *xx_loc, int update_act_coefs) {
   Nvtx nvtx_("RTAuxVars");
   if (!s) return fail(RXN_ERR_INVALID, "null state");
@@ -587,9 +619,7 @@ int rxn_update_auxvars_batch(RxnState *s, const double *xx_loc, int update_act_c
   }
   { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
-  const int threads = t->nvariant <= 8 ? 128 : 64;
-  const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
-  RXN_DISPATCH(t->nvariant, run_update_auxvars, L, t->h, (const double *)t->d_blob, s->S, (const double *)d_xx, update_act_coefs);
+  { const int rcu = launch_update_auxvars(s, (const double *)d_xx, update_act_coefs); if (rcu != RXN_OK) return rcu; }
   { const int rcl = check_launch(s, true); if (rcl != RXN_OK) return rcl; }
   return end_cell_flags(s, "RTUpdateAuxVars");
 }
@@ -616,10 +646,7 @@ int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int
   CU(cudaMemsetAsync(d_out, 0, (size_t)nlocal * n * 8, s->stream));
   { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
-  const int threads = t->nvariant <= 8 ? 128 : 64;
-  const LaunchCfg L{nblocks(nlocal, threads), threads, t->blob_bytes, s->stream};
-  RXN_DISPATCH(t->nvariant, run_fixed_accum, L, t->h, (const double *)t->d_blob, s->S, (const double *)d_xx, (const int *)d_l2g,
-               (long long)nlocal, (double *)d_out);
+  if ((rc = launch_fixed_accum(s, (const double *)d_xx, (const int32_t *)d_l2g, nlocal, (double *)d_out)) != RXN_OK) return rc;
   CU(cudaEventRecord(s->ev1, s->stream));
   CU(cudaMemcpyAsync(accum_out, d_out, (size_t)nlocal * n * 8, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaGetLastError());
@@ -630,7 +657,12 @@ int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int
 
 static int launch_residual_jacobian(RxnState *s, const int32_t *d_l2g, int64_t nlocal, double dt, double *d_res, double *d_jac) {
   const RxnTables *t = s->t;
-  if (t->lane.plan_gi.usable && s->gi_kernel != 1) {
+  if (s->gi_kernel == 0 && tm_gi_usable(t->lane, 0)) {
+    const GiArgs a{GI_RJ, 0, nullptr, 0, nullptr, d_res, d_jac, dt};
+    int rc = tm_launch_gi(t->lane, t->h, t->d_blob, s->S, d_l2g, (long long)nlocal, a, s->stream);
+    if (rc != RXN_OK) return fail(rc, "tensor-memory residual/Jacobian kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ++g_launches;
+  } else if (t->lane.plan_gi.usable && s->gi_kernel != 1) {
     int rc = lane_launch_gi(t->lane, t->h, t->d_blob, s->S, d_l2g, (long long)nlocal, dt, d_res, d_jac, s->stream);
     if (rc != RXN_OK) return fail(rc, "resident-lane residual/Jacobian kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ++g_launches;
@@ -666,9 +698,7 @@ int rxn_update_auxvars_batch_device(RxnState *s, const double *d_xx_loc, int upd
   const RxnTables *t = s->t;
   { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
-  const int threads = t->nvariant <= 8 ? 128 : 64;
-  const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
-  RXN_DISPATCH(t->nvariant, run_update_auxvars, L, t->h, (const double *)t->d_blob, s->S, d_xx_loc, update_act_coefs);
+  { const int rcu = launch_update_auxvars(s, d_xx_loc, update_act_coefs); if (rcu != RXN_OK) return rcu; }
   { const int rcl = check_launch(s, true); if (rcl != RXN_OK) return rcl; }
   return end_cell_flags(s, "RTUpdateAuxVars");
 }

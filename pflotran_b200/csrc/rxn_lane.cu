@@ -25,6 +25,12 @@ RXN_LANE_SHAPES(RXN_LANE_DECL)
 RXN_TM_SHAPES(RXN_TM_DECL)
 #undef RXN_TM_DECL
 
+#define RXN_TM_DECL(n, q, g)                                                                                                   \
+  template <> int tm_launch_gi_variant<n, q, g>(const LaneTab &, size_t, int, const DevTab &, const double *, const double *,  \
+                                                const DevState &, const int32_t *, long long, const GiArgs &, cudaStream_t);
+RXN_TM_SHAPES(RXN_TM_DECL)
+#undef RXN_TM_DECL
+
 // tensor-memory kernel: same plan with J in TMEM; the first compiled shape (N, QUADS, G) whose vectors fit
 static int tm_kernel_build(const DevTab &h, const std::vector<double> &bd, const std::vector<int32_t> &bi, const cudaDeviceProp &prop,
                            int N, LaneKernel *k) {
@@ -152,6 +158,24 @@ static void lane_set_mrK1(const LaneKernel &k, LaneTab &lt, double dt) {
     }
     lt.mrK1[ikr] = K1;
   }
+}
+
+bool tm_gi_usable(const LaneKernel &k, int update_act) {
+  if (!k.plan_tm.usable) return false;
+  if (const char *e = getenv("RXN_GI_TM")) { if (atoi(e) == 0) return false; }
+  return !(k.plan_tm.lt.act_off && update_act);
+}
+
+int tm_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, const int32_t *l2g, long long nlocal,
+                 const GiArgs &a, cudaStream_t stream) {
+  LaneTab lt = k.plan_tm.lt;
+  lane_set_mrK1(k, lt, a.dt);
+#define RXN_TM_CASE(n, q, g)                                                                                                   \
+  if (lt.N == n && k.quads_tm == q && k.G_tm == g)                                                                              \
+    return tm_launch_gi_variant<n, q, g>(lt, k.plan_tm.smem_bytes, k.sm_count, h, k.d_blob_tm, blob, S, l2g, nlocal, a, stream);
+  RXN_TM_SHAPES(RXN_TM_CASE)
+#undef RXN_TM_CASE
+  return RXN_ERR_UNSUPPORTED;
 }
 
 int lane_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, const int32_t *l2g, long long nlocal, double dt,

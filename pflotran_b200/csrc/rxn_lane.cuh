@@ -49,6 +49,10 @@ int tm_launch_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const 
                       const DevState &S, double *tran_xx, const int32_t *l2g, long long nlocal, double dt, int dt_mode, int32_t *iters,
                       int32_t *flags, unsigned long long *counter, long long cell0, cudaStream_t stream);
 
+template <int N, int QUADS, int G>
+int tm_launch_gi_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
+                         const DevState &S, const int32_t *l2g, long long nlocal, const GiArgs &a, cudaStream_t stream);
+
 template <int N, int CPB, int G>
 int lane_launch_gi_variant(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob, const double *blob,
                            const DevState &S, const int32_t *l2g, long long nlocal, double dt, double *res_out, double *jac_out,
@@ -59,6 +63,12 @@ void lane_kernel_free(LaneKernel *k);
 int lane_launch_react(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, double *tran_xx, const int32_t *l2g,
                       long long nlocal, double dt, int dt_mode, int32_t *iters, int32_t *flags, unsigned long long *counter,
                       cudaStream_t stream, long long cell0 = 0);
+
+// global-implicit pass on the tensor-memory layout: usable when the tensor-memory plan is, except for an activity update with
+// activity coefficients switched off in the tables (one class per species: nothing to compute them from)
+bool tm_gi_usable(const LaneKernel &k, int update_act);
+int tm_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, const int32_t *l2g, long long nlocal,
+                 const GiArgs &a, cudaStream_t stream);
 
 int lane_launch_gi(LaneKernel &k, const DevTab &h, const double *blob, const DevState &S, const int32_t *l2g, long long nlocal, double dt,
                    double *res_out, double *jac_out, cudaStream_t stream);

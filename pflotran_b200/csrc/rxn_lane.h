@@ -77,6 +77,17 @@ struct LaneTab {
   double mrK1[2];       // sum_r k_r/(1+k_r dt) f_r of the multirate reactions: set per launch (depends on dt)
 };
 
+// arguments of the global-implicit pass on the tensor-memory layout (tm_gi_cell, rxn_tm_dev.cuh)
+enum { GI_AUX = 1, GI_RJ = 2 };
+struct GiArgs {
+  int mode, update_act;
+  const double *xx;        // free-ion iterate, AoS [row][n] (row = cell for the auxvar update, item for the accumulation), or NULL
+  int xx_by_item;
+  double *accum_out;       // GI_AUX: [item][n] fixed accumulation, or NULL
+  double *res_out, *jac_out;   // GI_RJ
+  double dt;
+};
+
 struct LanePlan {
   bool usable = false;
   std::string err = "not built";

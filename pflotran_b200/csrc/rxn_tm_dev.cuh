@@ -1219,5 +1219,272 @@ TM_DEV void tm_finish(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, const 
   grp_sync<G>(c);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Global-implicit cell loops on the same layout (cell = TMEM lane, G member warps, uniform warps): ONE pass per cell, no
+// Newton loop.  Three entry points share it (GiArgs::mode):
+//   GI_AUX  RTUpdateAuxVars cells part (reactive_transport.F90:3790-3846) [+ RActivityCoefficients, :3620-3700] and
+//           RTUpdateFixedAccumulation (:786-843): RTAuxVarCompute = RTotal + RTotalSorb from a new free-ion iterate; optional
+//           dtotal / dtotal_sorb_eq blocks for the flux side (DTOTAL materialised), optional accumulation output
+//   GI_RJ   accumulation + reaction parts of RTResidualNonFlux (:2545-2586, 2735-2758) and RTJacobianNonFlux (:3342-3389,
+//           3445-3465), as lane_gi_cell (rxn_lane_dev.cuh) / cell_residual_jacobian (rxn_device.cuh)
+// Activity coefficients: `update_act` -> LAG Debye-Hueckel per class (tm_act_coefs) from the lagged sec_molal, written back
+// per species; else the state's per-species values are used: ln a_i = ln m_i + ln gamma_i in the cell's column, a complex
+// reads its own gamma_k from HBM at the one place it is needed (sec_molal_k = exp(lnQK_k) / gamma_k, reaction.F90:4112) -
+// consecutive lanes are consecutive cells, so that read is coalesced and no per-species slot is needed on chip.
+// Every lane of a warp walks the same code; `on` = this lane holds a cell of the batch (stores and flags are predicated).
+// (GiArgs, GI_AUX, GI_RJ: rxn_lane.h)
+
+// Jln rows of this member -> a cell-fastest SoA block (DTOTAL / DTOTAL_SORB_EQ: element (i, j) at row j*n + i): divided by m_j
+template <int N, int CPB, int G>
+TM_DEV void tm_gi_store_block(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, int field, bool on) {
+  const int n = lt.n;
+  double invm[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) invm[j] = 1.0 / tsm[c.vm + j * CPB];
+#pragma unroll 1
+  for (int i = c.l; i < n; i += G) {
+    double r[TM_LD];
+    tm_ld<TM_LD>(c.tb, i, 0, r);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j < n && on) GSL(S, field, j * n + i, c.cell) = r[j] * invm[j];
+  }
+}
+template <int N, int CPB, int G>
+TM_DEV void tm_gi_zero_J(Ctx<N, G> &c) {
+  double z[TM_LD];
+#pragma unroll
+  for (int j = 0; j < TM_LD; ++j) z[j] = 0.0;
+#pragma unroll 1
+  for (int i = c.l; i < N; i += G) tm_st<TM_LD>(c.tb, i, 0, z);
+  tm_wait_st();
+}
+
+template <int N, int CPB, int G>
+TM_DEV void tm_gi_cell(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, const DevTab &h, const double *blob_d, const int *blob_i,
+                       const GiArgs &a, long long item, long long cell, bool on) {
+  const int n = lt.n, s = c.s;
+  const bool rj = a.mode == GI_RJ;
+  const bool from_state = !lt.act_off && !a.update_act;        // per-species gamma of the state with the class-based plan
+  const double dt = a.dt;
+  c.item = item; c.cell = cell; c.flags = 0; c.iter = 0;
+  c.ln_act_h2o = GSL(S, RXN_F_LN_ACT_H2O, 0, cell);
+  c.den_kg = GSL(S, RXN_F_DEN_KG, 0, cell);
+  c.temp = GSL(S, RXN_F_TEMP, 0, cell);
+  c.volume = GSL(S, RXN_F_VOLUME, 0, cell);
+  c.porosity = GSL(S, RXN_F_POROSITY, 0, cell);
+  c.soil_density = GSL(S, RXN_F_SOIL_PARTICLE_DENSITY, 0, cell);
+  const double sat = GSL(S, RXN_F_SAT, 0, cell);
+  c.psv = c.porosity * sat * 1000.0 * c.volume;
+  c.psvd = rj ? c.porosity * sat * 1000.0 * c.volume / dt : 1.0;
+  c.v_t = rj ? c.volume / dt : 1.0;
+  c.den_kg_per_L = c.den_kg * 1.0 * 1.0e-3;
+  grp_sync<G>(c);                                              // the previous cell of this column is done everywhere
+  const long long xrow = a.xx_by_item ? item : cell;
+#pragma unroll 1
+  for (int i = c.l; i < N; i += G) {
+    double mm = 1.0;                                           // padding rows of the shape: m = 1 (as tm_load)
+    if (i < n) mm = a.xx ? a.xx[xrow * n + i] : GSL(S, RXN_F_PRI_MOLAL, i, cell);
+    tsm[c.vm + i * CPB] = mm;
+  }
+  if (c.l == 0) {
+    tsm[c.vlna + n * CPB] = 0.0;
+    tsm[c.vlna + (n + 1) * CPB] = c.ln_act_h2o;
+    tsm[c.vsm + lt.ncplx * CPB] = 0.0;
+  }
+  if (lt.act_off) {                                            // one class per species: ln gamma from the state
+#pragma unroll 1
+    for (int i = c.l; i < n; i += G) tsm[c.vlng + i * CPB] = c_log(GSL(S, RXN_F_PRI_ACT_COEF, i, cell));
+#pragma unroll 1
+    for (int k = c.l; k < lt.ncplx; k += G) tsm[c.vlng + (n + k) * CPB] = c_log(GSL(S, RXN_F_SEC_ACT_COEF, k, cell));
+  } else if (a.update_act) {                                   // lagged sec_molal for the ionic strength
+#pragma unroll 4
+    for (int k = c.l; k < lt.ncplx; k += G) tsm[c.vsm + k * CPB] = GSL(S, RXN_F_SEC_MOLAL, k, cell);
+  }
+#pragma unroll 1
+  for (int q = c.l; q < lt.nrxn; q += G) tsm[c.vfree + q * CPB] = GSL(S, RXN_F_FREE_SITE_CONC, q, cell);
+#pragma unroll 1
+  for (int q = c.l; q < lt.nkin; q += G) {
+    tsm[c.vmnrl + q * CPB] = GSL(S, RXN_F_MNRL_VOLFRAC, q, cell);
+    tsm[c.vmnrl + (lt.nkin + q) * CPB] = GSL(S, RXN_F_MNRL_AREA, q, cell);
+  }
+  if (lt.percell_logK)
+    tm_percell_logK<CPB, G>(c.l, lt.ncoef, lt.logK_mode, c.vlk, c.temp, GSL(S, RXN_F_PRES, 0, cell), blob_d, h.cplx, h.kin, h.srf);
+  if (rj && lt.nmr > 0) {                                      // multirate_prepare: R0_i = sum_r k_r/(1+k_r dt) S_r,i (even / odd rates)
+#pragma unroll 1
+    for (int ikr = 0; ikr < lt.nmr; ++ikr) {
+      const int nrate = blob_i[h.o_mr_nrate + ikr];
+#pragma unroll 1
+      for (int i = c.l; i < n; i += G) {
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 4
+        for (int irate = 0; irate < nrate; irate += 2) {
+          const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
+          acc0 = acc0 + rate / (1.0 + rate * dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + irate + 1) * n + i, cell);
+          if (irate + 1 < nrate) {
+            const double rate1 = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate + 1];
+            acc1 = acc1 + rate1 / (1.0 + rate1 * dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + irate + 2) * n + i, cell);
+          }
+        }
+        tsm[c.vr0 + (ikr * N + i) * CPB] = acc0 + acc1;
+      }
+    }
+  }
+  const bool want_dtot = !rj && S.f[RXN_F_DTOTAL] != nullptr;
+  const bool want_dsorb = !rj && lt.neqsorb > 0 && S.f[RXN_F_DTOTAL_SORB_EQ] != nullptr;
+  const bool want_J = rj && a.jac_out != nullptr;
+  // plan B writes (i, j) and (j, i), i.e. into rows of the other members: the rows are zeroed here, ordered before plan B by
+  // the barriers of the speciation (as in tm_trip)
+  if (want_dtot || want_J) tm_gi_zero_J<N, CPB, G>(c);
+  grp_sync<G>(c);
+  if (!lt.act_off && a.update_act) tm_act_coefs<N, CPB, G>(lt, c, true);     // RActivityCoefficients, LAG (:3994-4050)
+  // RTotal (:4057-4158): ln a_i, then sec_molal_k
+  if (from_state) {
+#pragma unroll 2
+    for (int i = c.l; i < n; i += G)
+      tsm[c.vlna + i * CPB] = log(tsm[c.vm + i * CPB]) + log(GSL(S, RXN_F_PRI_ACT_COEF, i, cell));    // :4090
+    grp_sync<G>(c);
+#pragma unroll 1
+    for (int g = c.l; g < lt.spec.ng; g += G) {
+      const int4 hd = TI4(lt, (lt.spec.g0 >> 2) + 2 * g), h2 = TI4(lt, (lt.spec.g0 >> 2) + 2 * g + 1);
+      const int c0 = hd.x, o0 = hd.y, nsteps = hd.z, cb = h2.x >> 2;
+      const int4 m0 = TI4(lt, cb), m1 = TI4(lt, cb + 1), m2 = TI4(lt, cb + 2), m3 = TI4(lt, cb + 3);
+      // the state's gamma_k of the 4 complexes of the group (padding members: 1), issued before the sums
+      const double g0 = m0.z >= 0 ? GSL(S, RXN_F_SEC_ACT_COEF, m0.z, cell) : 1.0, g1 = m1.z >= 0 ? GSL(S, RXN_F_SEC_ACT_COEF, m1.z, cell) : 1.0,
+                   g2 = m2.z >= 0 ? GSL(S, RXN_F_SEC_ACT_COEF, m2.z, cell) : 1.0, g3 = m3.z >= 0 ? GSL(S, RXN_F_SEC_ACT_COEF, m3.z, cell) : 1.0;
+      double a0, a1, a2, a3;
+      if (lt.percell_logK) {
+        a0 = tsm[c.vlk + (m0.z < 0 ? 0 : m0.z) * CPB]; a1 = tsm[c.vlk + (m1.z < 0 ? 0 : m1.z) * CPB];
+        a2 = tsm[c.vlk + (m2.z < 0 ? 0 : m2.z) * CPB]; a3 = tsm[c.vlk + (m3.z < 0 ? 0 : m3.z) * CPB];
+      } else {
+        const double2 ia = TD2(lt, c0 * 2), ib = TD2(lt, c0 * 2 + 1);
+        a0 = ia.x; a1 = ia.y; a2 = ib.x; a3 = ib.y;
+      }
+      tm_run_group(lt, s, c0, o0, nsteps, a0, a1, a2, a3);
+      tsm[m0.x + s] = exp(a0) / g0; tsm[m1.x + s] = exp(a1) / g1; tsm[m2.x + s] = exp(a2) / g2; tsm[m3.x + s] = exp(a3) / g3;   // :4112
+    }
+    grp_sync<G>(c);
+  } else {
+    tm_speciate<N, CPB, G>(lt, c);
+  }
+  tm_planA<N, CPB, G>(lt, c);
+  if (want_dtot || want_J)
+    tm_planB<N, CPB, G>(lt, c, rj ? c.den_kg_per_L * c.psvd : c.den_kg_per_L);      // dtotal [* psvd_t, RTAccumulationDerivative :5189-5204]
+  if (want_dtot) {
+    grp_sync<G>(c);
+    tm_gi_store_block<N, CPB, G>(lt, c, S, RXN_F_DTOTAL, on);
+  }
+  if (want_dsorb) { grp_sync<G>(c); tm_gi_zero_J<N, CPB, G>(c); }
+#pragma unroll 1
+  for (int i = c.l; i < N; i += G) tsm[c.vres + i * CPB] = 0.0;
+  if (lt.neq > 0 && on) {                                      // RZeroSorb :4162-4178
+#pragma unroll 1
+    for (int k = c.l; k < lt.nsrf; k += G) GSL(S, RXN_F_EQSRFCPLX_CONC, k, cell) = 0.0;
+  }
+  grp_sync<G>(c);
+  // RTotalSorb (:4182-4216); GI_RJ: + the equilibrium part of the multirate reactions (RMultiRateSorption)
+  const int ntask = lt.neq + (rj ? lt.nmr : 0);
+#pragma unroll 1
+  for (int task = 0; task < ntask; ++task) {
+    const bool eq = task < lt.neq;
+    const int ikr = task - lt.neq;
+    int tb = c.vres;
+    double fac = rj ? c.v_t : 1.0;
+    if (!eq) {
+      tb = c.vseq + ikr * N * CPB;
+      fac = c.volume * lt.mrK1[ikr];
+#pragma unroll 1
+      for (int i = c.l; i < n; i += G) tsm[tb + i * CPB] = 0.0;
+    }
+    tm_srf_rxn<N, CPB, G>(lt, c, S, TI(lt, (eq ? lt.i_eq_rxn : lt.i_mr_rxn - lt.neq) + task), fac, eq ? (want_J || want_dsorb) : want_J, eq, on, tb);
+  }
+  tm_wait_st();
+  grp_sync<G>(c);
+  if (want_dsorb) { tm_gi_store_block<N, CPB, G>(lt, c, S, RXN_F_DTOTAL_SORB_EQ, on); grp_sync<G>(c); }
+  bool bad = false;
+#pragma unroll 1
+  for (int i = c.l; i < n; i += G) {
+    const double mm = tsm[c.vm + i * CPB];
+    const double tot = (mm + tsm[c.vtot + i * CPB]) * c.den_kg_per_L;               // :4095, 4124, 4148
+    const double tsorb = lt.neqsorb > 0 ? tsm[c.vres + i * CPB] : 0.0;
+    double acc = c.psv * tot;                                                       // RTAccumulation :5072-5148
+    if (lt.neqsorb > 0) acc = acc + tsorb * c.volume;                               // RAccumulationSorb :4539-4568
+    if (!isfinite(tot) || !isfinite(acc)) bad = true;
+    if (on) {
+      GSL(S, RXN_F_TOTAL, i, cell) = tot;
+      if (lt.neqsorb > 0) GSL(S, RXN_F_TOTAL_SORB_EQ, i, cell) = tsorb;
+      if (!rj) {
+        if (a.xx) GSL(S, RXN_F_PRI_MOLAL, i, cell) = mm;
+        if (a.accum_out) a.accum_out[item * n + i] = acc;
+        if (!lt.act_off && a.update_act) GSL(S, RXN_F_PRI_ACT_COEF, i, cell) = c_exp(tsm[c.vlng + TI(lt, lt.i_pcls + i) * CPB]);
+      }
+    }
+    if (rj) tsm[c.vres + i * CPB] = acc / dt;
+  }
+  if (rj) {
+    // RReaction :3515-3584 (minerals, then multirate)
+    if (lt.nkin > 0) { grp_sync<G>(c); tm_kinetic_mineral<N, CPB, G>(lt, c, true); }
+#pragma unroll 1
+    for (int ikr = 0; ikr < lt.nmr; ++ikr) {
+#pragma unroll 1
+      for (int i = c.l; i < n; i += G) {
+        tsm[c.vres + i * CPB] += c.volume * (lt.mrK1[ikr] * tsm[c.vseq + (ikr * N + i) * CPB] - tsm[c.vr0 + (ikr * N + i) * CPB]);
+        if (on) GSL(S, RXN_F_KINMR_TOTAL_SORB, (long long)ikr * (h.mr_ld + 1) * n + i, cell) = tsm[c.vseq + (ikr * N + i) * CPB];
+      }
+    }
+    tm_wait_st();
+    grp_sync<G>(c);
+#pragma unroll 1
+    for (int i = c.l; i < n; i += G) {
+      const double r = tsm[c.vres + i * CPB];
+      if (!isfinite(r)) bad = true;
+      if (a.res_out && on) a.res_out[item * n + i] = r;
+    }
+    if (want_J) {
+      // block column-major, with respect to m_j: Jln_ij / m_j.  A member writes whole COLUMNS of the block (n contiguous
+      // doubles of the caller's array) instead of the rows it assembled: column j of the cell's TMEM lane is read element by
+      // element (a row write would scatter n 8-byte stores over n sectors: measured 35 % of this kernel's stall samples)
+#pragma unroll 1
+      for (int j = c.l; j < n; j += G) {
+        const double invm = 1.0 / tsm[c.vm + j * CPB];
+        double col[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) col[i] = tm_ld_el(c.tb, i, j) * invm;
+        double *dst = a.jac_out + item * (long long)(n * n) + j * n;
+        if (on) {
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            if (i < n) dst[i] = col[i];
+        }
+      }
+    }
+#pragma unroll 1
+    for (int q = c.l; q < lt.nkin; q += G)
+      if (on) GSL(S, RXN_F_MNRL_RATE, q, cell) = tsm[c.vmnrl + (2 * lt.nkin + q) * CPB];
+  }
+#pragma unroll 2
+  for (int k = c.l; k < lt.ncplx; k += G) {
+    if (on) {
+      GSL(S, RXN_F_SEC_MOLAL, k, cell) = tsm[c.vsm + k * CPB];
+      if (!rj && !lt.act_off && a.update_act) GSL(S, RXN_F_SEC_ACT_COEF, k, cell) = c_exp(tsm[c.vlng + TI(lt, lt.i_ccls + k) * CPB]);
+    }
+  }
+#pragma unroll 1
+  for (int q = c.l; q < lt.nrxn; q += G)
+    if (on) GSL(S, RXN_F_FREE_SITE_CONC, q, cell) = tsm[c.vfree + q * CPB];
+  if (c.l == 0 && on && !rj && a.update_act) GSL(S, RXN_F_LN_ACT_H2O, 0, cell) = c.ln_act_h2o;
+  {
+    const int fl = c.flags | (bad ? RXN_FLAG_NONFINITE : 0);
+    if (fl != 0 && on && S.fail) {
+#ifndef RXN_TM_HOST
+      atomicOr(S.fail, (unsigned int)fl);
+#else
+      __atomic_fetch_or(S.fail, (unsigned int)fl, __ATOMIC_RELAXED);
+#endif
+    }
+  }
+  warp_converge();
+}
+
 }  // namespace tmk
 }  // namespace rxn

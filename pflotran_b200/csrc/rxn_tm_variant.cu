@@ -119,7 +119,61 @@ k_react_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h,
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base));
 }
 
+// Global-implicit pass (tm_gi_cell): every lane takes the cells base + column, base + column + grid * CPB, ... - one pass per
+// cell, so the rounds of a CTA are uniform and no work counter is needed.
+template <int N, int QUADS, int G>
+__global__ void __launch_bounds__(128 * G, 1)
+k_gi_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h, const double *__restrict__ pblob,
+        const double *__restrict__ blob, DevState S, const int32_t *__restrict__ l2g, long long nlocal, const __grid_constant__ GiArgs a) {
+  constexpr int CPB = 32 * QUADS;
+  __shared__ unsigned tmem_base_w[4];
+  const int words = lt.blob_dbl + lt.blob_int / 2;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) tsm[w] = pblob[w];
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_w[0])));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  const unsigned tmem_base = tmem_base_w[0];
+  const int quad = warp & 3, l = warp >> 2;
+  if (quad < QUADS) {
+    const double *bd = blob;
+    const int *bi = reinterpret_cast<const int *>(blob + h.ndbl);
+    Ctx<N, G> c;
+    tm_bind<N, CPB, G>(lt, c, quad * 32 + ln, l, quad, tmem_base);
+    tm_init_column<N, CPB, G>(lt, c);
+#pragma unroll 1
+    for (long long base = (long long)blockIdx.x * CPB; base < nlocal; base += (long long)gridDim.x * CPB) {
+      const long long item = base + c.s;
+      bool on = item < nlocal;
+      const long long itc = on ? item : nlocal - 1;             // a lane beyond the batch walks a valid cell with its stores off
+      const long long cell = l2g ? l2g[itc] : itc;
+      if (S.active && !S.active[cell]) on = false;              // imat <= 0: cycle
+      tm_gi_cell<N, CPB, G>(lt, c, S, h, bd, bi, a, itc, cell, on);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base));
+}
+
 }  // namespace tmk
+
+template <>
+int tm_launch_gi_variant<TM_N, TM_QUADS, TM_G>(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob,
+                                               const double *blob, const DevState &S, const int32_t *l2g, long long nlocal,
+                                               const GiArgs &a, cudaStream_t stream) {
+  auto kern = tmk::k_gi_tm<TM_N, TM_QUADS, TM_G>;
+  constexpr int threads = 128 * TM_G;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return RXN_ERR_CUDA;
+  const long long want = (nlocal + 32 * TM_QUADS - 1) / (32 * TM_QUADS);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sm_count));
+  kern<<<grid, threads, smem_bytes, stream>>>(lt, h, pblob, blob, S, l2g, nlocal, a);
+  return RXN_OK;
+}
 
 template <>
 int tm_launch_variant<TM_N, TM_QUADS, TM_G>(const LaneTab &lt, size_t smem_bytes, int sm_count, const DevTab &h, const double *pblob,

@@ -277,7 +277,84 @@ static void tm_cells_g(const LaneJob &J, int G) {
   else tm_cells<N, 4>(J);
 }
 
+// global-implicit pass on the tensor-memory layout (tm_gi_cell): G host threads per cell as above
+struct TmGiJob {
+  const LanePlan *P; Emu *e; DevState *S; const int32_t *l2g; int64_t nlocal; rxn::GiArgs a;
+};
+template <int N, int G>
+static void tm_gi_thread(const TmGiJob *J, LaneTab lt, int l) {
+  using namespace rxn::tmk;
+  const DevTab &h = J->e->R.h;
+  const DevState &S = *J->S;
+  Ctx<N, G> c;
+  tm_bind<N, 1, G>(lt, c, 0, l, 0, 0u);
+  tm_init_column<N, 1, G>(lt, c);
+  for (long long i = 0; i < J->nlocal; ++i) {
+    const long long cell = J->l2g ? J->l2g[i] : i;
+    const bool on = !(S.active && !S.active[cell]);            // an inactive cell is walked with its stores off, as on the device
+    tm_gi_cell<N, 1, G>(lt, c, S, h, J->e->T.d, J->e->T.i, J->a, i, cell, on);
+  }
+}
+template <int N, int G>
+static void tm_gi_cells(const TmGiJob &J) {
+  LaneTab lt = J.P->lt;
+  const DevTab &h = J.e->R.h;
+  for (int ikr = 0; ikr < lt.nmr && ikr < 2; ++ikr) {
+    double K1 = 0.0;
+    for (int irate = 0; irate < J.e->T.i[h.o_mr_nrate + ikr]; ++irate) {
+      const double rate = J.e->T.d[h.o_mr_rate + ikr * h.mr_ld + irate], frac = J.e->T.d[h.o_mr_frac + ikr * h.mr_ld + irate];
+      const double kdt = rate * J.a.dt;
+      const double one_plus_kdt = 1.0 + kdt;
+      const double kk = rate / one_plus_kdt;
+      K1 = K1 + kk * frac;
+    }
+    lt.mrK1[ikr] = K1;
+  }
+  std::vector<double> sm((size_t)lt.smem_dbl + 16, 0.0), tmem(256, 0.0);
+  memcpy(sm.data(), J.P->blob.data(), J.P->blob.size());
+  rxn::tmk::tsm = sm.data();
+  rxn::tmk::tmh = tmem.data();
+  rxn::tmk::HostGroup hg;
+  pthread_barrier_init(&hg.bar, nullptr, G);
+  rxn::tmk::g_hg = &hg;
+  std::vector<std::thread> th;
+  for (int l = 1; l < G; ++l) th.emplace_back(tm_gi_thread<N, G>, &J, lt, l);
+  tm_gi_thread<N, G>(&J, lt, 0);
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&hg.bar);
+  rxn::tmk::g_hg = nullptr;
+  rxn::tmk::tsm = nullptr;
+  rxn::tmk::tmh = nullptr;
+}
+template <int N>
+static void tm_gi_cells_g(const TmGiJob &J, int G) {
+  if (G == 1) tm_gi_cells<N, 1>(J);
+  else if (G == 2) tm_gi_cells<N, 2>(J);
+  else if (G == 3) tm_gi_cells<N, 3>(J);
+  else tm_gi_cells<N, 4>(J);
+}
+
 extern "C" {
+
+// mode: 1 = GI_AUX (auxvar update / fixed accumulation), 2 = GI_RJ (residual + Jacobian blocks); see rxn_lane.h GiArgs
+int emu_gi_tm(void *hh, const HostView *v, const uint8_t *active, const int32_t *l2g, int64_t nlocal, int mode, int update_act,
+              const double *xx, int xx_by_item, double *accum_out, double *res_out, double *jac_out, double dt, int G, char *err,
+              int errlen) {
+  Emu *e = (Emu *)hh;
+  DevState S = mk_state(v, active);
+  LanePlan P;
+  const int N = e->R.h.naq <= 12 ? 12 : 15;
+  if (G < 1 || G > 4) { if (err) snprintf(err, errlen, "G must be 1, 2, 3 or 4"); return RXN_ERR_INVALID; }
+  int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P, false, G);
+  if (rc != RXN_OK || !P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
+  if (P.lt.act_off && update_act) { if (err) snprintf(err, errlen, "activity update with activity coefficients off"); return RXN_ERR_UNSUPPORTED; }
+  TmGiJob J{&P, e, &S, l2g, nlocal, rxn::GiArgs{mode, update_act, xx, xx_by_item, accum_out, res_out, jac_out, dt}};
+  switch (N) {
+    case 12: tm_gi_cells_g<12>(J, G); break;
+    default: tm_gi_cells_g<15>(J, G); break;
+  }
+  return 0;
+}
 
 int emu_react_tm(void *hh, const HostView *v, double *tran_xx, const uint8_t *active, const int32_t *l2g, int64_t nlocal, double dt,
                  int dt_mode, int32_t *iters, int32_t *flags, int G, int forceN, char *err, int errlen) {

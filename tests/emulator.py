@@ -115,6 +115,23 @@ class Emulator:
             raise NotImplementedError(buf.value.decode())
         return iters, flags
 
+    def gi_tm(self, st, mode, G=3, update_act=False, xx=None, xx_by_item=False, dt=1.0, l2g=None, want_accum=False):
+        """Global-implicit pass on the tensor-memory layout (tm_gi_cell, rxn_tm_dev.cuh): mode 1 = auxvar update / fixed
+        accumulation, 2 = residual + Jacobian blocks.  Returns (accum | None) for mode 1, (res, jac) for mode 2."""
+        n = st.ncells if l2g is None else len(l2g)
+        nc = self.t.ncomp
+        acc = np.zeros((n, nc)) if (mode == 1 and want_accum) else None
+        res = np.zeros((n, nc)) if mode == 2 else None
+        jac = np.zeros((n, nc * nc)) if mode == 2 else None
+        v = st.view()
+        buf = C.create_string_buffer(512)
+        rc = lib().emu_gi_tm(self.h, C.byref(v), _p(st.active, C.c_uint8), _p(l2g, C.c_int32), C.c_int64(n), C.c_int(mode),
+                             C.c_int(int(update_act)), _p(xx, C.c_double), C.c_int(int(xx_by_item)), _p(acc, C.c_double),
+                             _p(res, C.c_double), _p(jac, C.c_double), C.c_double(dt), C.c_int(G), buf, 512)
+        if rc != 0:
+            raise NotImplementedError(buf.value.decode())
+        return acc if mode == 1 else (res, jac)
+
     def update_auxvars(self, st, xx_loc, update_act_coefs):
         v = st.view()
         assert lib().emu_update_auxvars_batch(self.h, C.byref(v), _p(xx_loc, C.c_double), _p(st.active, C.c_uint8),

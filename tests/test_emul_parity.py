@@ -197,6 +197,66 @@ def test_global_implicit_blocks_resident_lane(name, G):
     assert_state_close(st_e, st_o, what=name + ' residual/Jacobian state', tables=w.tables)
 
 
+@pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'surface_complexation', 'hanford300a_stoich',
+                                  'calcite_rate_laws', 'calcite_fit5'])
+@pytest.mark.parametrize('G', [1, 2, 3, 4])
+def test_global_implicit_tensor_memory_routines(name, G):
+    """The global-implicit cell loops on the tensor-memory layout (tm_gi_cell: one pass per cell, class-based Debye-Hueckel
+    update or the state's per-species activity coefficients, dtotal / dtotal_sorb_eq blocks from the ln-m Jacobian in the
+    cell's TMEM lane) against the oracle: RTUpdateAuxVars with and without activity update, RTUpdateFixedAccumulation, residual
+    and Jacobian blocks, including every state side effect."""
+    nc = 150
+    w, cells = workload_cells(name, nc)
+    st_o = synth.host_state(w, cells)
+    orc, emu = Oracle(w.tables), Emulator(w.tables)
+    rng = np.random.default_rng(7)
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((nc, w.ncomp))))
+    st_e = st_o.copy()
+    orc.update_auxvars(st_o, xx, True)
+    emu.gi_tm(st_e, 1, G=G, update_act=True, xx=xx)
+    assert_state_close(st_e, st_o, what=name + ' update_auxvars(act)', tables=w.tables)
+    for f in ('DTOTAL', 'DTOTAL_SORB_EQ'):
+        if st_o[f].size:
+            sc = np.maximum(np.abs(st_o[f]), 1e-12 * np.abs(st_o[f]).max(axis=0, keepdims=True))
+            assert (np.abs(st_e[f] - st_o[f]) / np.maximum(sc, 1e-300)).max() <= RTOL, f
+    # a second iterate with the activity coefficients of the state (lagged), then the accumulation from a third
+    xx2 = np.ascontiguousarray(xx * np.exp(0.05 * rng.standard_normal(xx.shape)))
+    orc.update_auxvars(st_o, xx2, False)
+    emu.gi_tm(st_e, 1, G=G, update_act=False, xx=xx2)
+    assert_state_close(st_e, st_o, what=name + ' update_auxvars(lagged)', tables=w.tables)
+    a_o = orc.fixed_accum(st_o, xx)
+    a_e = emu.gi_tm(st_e, 1, G=G, xx=xx, xx_by_item=True, want_accum=True)
+    a_scale = np.maximum(np.abs(a_o), (st_o['POROSITY'] * st_o['SAT'] * 1000.0 * st_o['VOLUME'] * total_magnitude(st_o, w.tables)).T)
+    assert (np.abs(a_e - a_o) / np.maximum(a_scale, 1e-300)).max() <= RTOL
+    assert_state_close(st_e, st_o, what=name + ' fixed accumulation state', tables=w.tables)
+    r_o, j_o = orc.residual_jacobian(st_o, 1800.0)
+    r_e, j_e = emu.gi_tm(st_e, 2, G=G, dt=1800.0)
+    rs = residual_scale(st_o, w.tables, r_o, a_o, 1800.0)
+    assert (np.abs(r_e - r_o) / np.maximum(rs, 1e-300)).max() <= RTOL
+    js = jacobian_scale(st_o, j_o, w.ncomp)
+    assert (np.abs(j_e - j_o) / np.maximum(js, 1e-300)).max() <= RTOL
+    assert_state_close(st_e, st_o, what=name + ' residual/Jacobian state', tables=w.tables)
+
+
+def test_global_implicit_tensor_memory_inactive_and_l2g():
+    w, cells = workload_cells('hanford300a_eq', 40)
+    st_o = synth.host_state(w, cells)
+    st_o.active = np.ones(40, dtype=np.uint8); st_o.active[[3, 17]] = 0
+    orc, emu = Oracle(w.tables), Emulator(w.tables)
+    xx = np.ascontiguousarray(np.tile(w.base['PRI_MOLAL'] * 1.05, (40, 1)))
+    st_e = st_o.copy()
+    orc.update_auxvars(st_o, xx, True)
+    emu.gi_tm(st_e, 1, G=3, update_act=True, xx=xx)
+    assert_state_close(st_e, st_o, what='inactive', tables=w.tables)
+    assert (st_e['PRI_MOLAL'][:, 3] == w.base['PRI_MOLAL']).all()          # untouched
+    l2g = np.array([5, 2, 17, 30], dtype=np.int32)
+    r_e, j_e = emu.gi_tm(st_e, 2, G=3, dt=900.0, l2g=l2g)
+    r_o, j_o = orc.residual_jacobian(st_o, 900.0)
+    live = [0, 1, 3]
+    assert (np.abs(r_e[live] - r_o[l2g[live]]) <= 1e-9 * np.abs(r_o[l2g[live]]).max()).all()
+    assert (r_e[2] == 0).all() and (j_e[2] == 0).all()                      # inactive cell: block left as the caller zeroed it
+
+
 def test_inactive_cells_and_l2g():
     w, cells = workload_cells('calcite', 64)
     st_o = synth.host_state(w, cells)

@@ -191,6 +191,43 @@ def test_global_implicit_entry_points(name):
     assert_state_close(st_g, st_o, what=name + ' RTUpdateKineticState', tables=w.tables, kinetic_dt=1800.0)
 
 
+@pytest.mark.parametrize('name', ['hanford300a_eq', 'hanford300a_mr', 'hanford300a_stoich', 'calcite'])
+@pytest.mark.parametrize('gi_kernel', [0, 1])
+def test_global_implicit_auxvars_with_derivative_blocks(name, gi_kernel, monkeypatch):
+    """RTUpdateAuxVars with dtotal / dtotal_sorb_eq materialised (what the flux Jacobian consumes), with the activity update and
+    with the state's lagged activity coefficients, then the fixed accumulation through an l2g map: the tensor-memory layout
+    (gi_kernel 0, where the tables allow it: k_gi_tm) and the thread-per-cell kernels (1) against the oracle."""
+    monkeypatch.setenv('RXN_GI_KERNEL', str(gi_kernel))
+    n = 20000
+    w, cells = workload_cells(name, n)
+    st_o = synth.host_state(w, cells)
+    st_g = st_o.copy()
+    rx, rz = _gpu_state(w, st_g)
+    rz.materialize('DTOTAL')
+    if rx.field_rows('DTOTAL_SORB_EQ'):
+        rz.materialize('DTOTAL_SORB_EQ')
+    orc = Oracle(w.tables)
+    rng = np.random.default_rng(7)
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((n, w.ncomp))))
+    for update, x in ((True, xx), (False, np.ascontiguousarray(xx * np.exp(0.05 * rng.standard_normal(xx.shape))))):
+        orc.update_auxvars(st_o, x, update, nthreads=8)
+        rz.RTUpdateAuxVars(x, update)
+        rz.download_host_state(st_g)
+        assert_state_close(st_g, st_o, what='%s RTUpdateAuxVars(%s)' % (name, update), tables=w.tables)
+        for f in ('DTOTAL', 'DTOTAL_SORB_EQ'):
+            if rx.field_rows(f):
+                d_g, d_o = rz.download(f), st_o[f]
+                sc = np.maximum(np.abs(d_o), 1e-12 * np.abs(d_o).max(axis=0, keepdims=True))
+                assert (np.abs(d_g - d_o) / np.maximum(sc, 1e-300)).max() <= RTOL, f
+    l2g = np.ascontiguousarray(rng.permutation(n)[:n // 3].astype(np.int32))
+    xa = np.ascontiguousarray(xx[l2g])
+    a_g = rz.RTUpdateFixedAccumulation(xa, l2g)
+    st_sub = st_o.copy()
+    a_o = orc.fixed_accum(st_sub, np.ascontiguousarray(np.where(np.isin(np.arange(n), l2g)[:, None], xx, st_o['PRI_MOLAL'].T)), nthreads=8)
+    a_scale = np.maximum(np.abs(a_o), (st_sub['POROSITY'] * st_sub['SAT'] * 1000.0 * st_sub['VOLUME'] * total_magnitude(st_sub, w.tables)).T)
+    assert (np.abs(a_g - a_o[l2g]) / np.maximum(a_scale[l2g], 1e-300)).max() <= RTOL
+
+
 def test_global_implicit_entry_points_report_failed_cells():
     """A cell whose global-implicit evaluation is not finite (or raises a flag the reference stops on) makes the entry point
     return RXN_ERR_CELL_FAILED instead of handing NaN residuals to the caller; an out-of-range l2g entry is RXN_ERR_INVALID."""
