@@ -931,13 +931,30 @@ TM_DEV void tm_load(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, const do
 #endif
 }
 
+// k_r / (1 + k_r dt) of rate r of multirate reaction ikr: the same for every cell of a launch, so the CTA forms the table once
+// (kk, TM_MR_KK entries in shared memory; NULL: more rates than the table holds, evaluated in place - same rounding either way)
+#ifndef TM_MR_KK
+#define TM_MR_KK 100
+#endif
+TM_DEV double tm_mr_kk(const double *kk, const double *blob_d, const DevTab &h, int ikr, int irate, double tran_dt) {
+  if (kk) return kk[ikr * h.mr_ld + irate];
+  const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
+  return rate / (1.0 + rate * tran_dt);
+}
+TM_DEV void tm_mr_kk_fill(double *kk, int first, int stride, const double *blob_d, const DevTab &h, double tran_dt) {
+  for (int w = first; w < h.nmr * h.mr_ld && w < TM_MR_KK; w += stride) {
+    const double rate = blob_d[h.o_mr_rate + w];
+    kk[w] = rate / (1.0 + rate * tran_dt);
+  }
+}
+
 // multirate sorption of a cell just taken: R0_i = sum_r k_r/(1+k_r dt) S_r,i (multirate_prepare, rxn_device.cuh; REASSOC: even
 // and odd rates summed separately, then added, as lane_coop_in_mr).  750 doubles per 300A cell: every lane of the warp loads
 // for ONE cell at a time - lane (ii, half) sums the even (half 0) or odd (half 1) rates of row l + G ii, all its loads in
 // flight before the first add - and the sum lands in that cell's column.  W = lanes of the warp (host: 1).
 template <int N, int CPB, int G>
 TM_DEV void tm_coop_in_mr(const LaneTab &lt, const DevState &S, const DevTab &h, const double *blob_d, const int *blob_i, int l, int slot,
-                          long long cell, double tran_dt, int w, int W) {
+                          long long cell, double tran_dt, int w, int W, const double *kk) {
   const int vr0 = lt.o_vec + lt.s_r0 * CPB + slot;
   const int n = lt.n;
   const int H = W >= 32 ? 2 : 1, per = W / H;
@@ -963,20 +980,16 @@ TM_DEV void tm_coop_in_mr(const LaneTab &lt, const DevState &S, const DevTab &h,
             for (int u = 0; u < 8; ++u) {
               const int irate = r0 + 2 * u;
               if (irate < nrate) {
-                const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
-                acc0 = acc0 + rate / (1.0 + rate * tran_dt) * v[u];
+                acc0 = acc0 + tm_mr_kk(kk, blob_d, h, ikr, irate, tran_dt) * v[u];
               }
             }
           }
         } else {
 #pragma unroll 1
           for (int irate = 0; irate < nrate; irate += 2) {
-            const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
-            acc0 = acc0 + rate / (1.0 + rate * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell);
-            if (irate + 1 < nrate) {
-              const double rate1 = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate + 1];
-              acc1 = acc1 + rate1 / (1.0 + rate1 * tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)(irate + 1) * n + i, cell);
-            }
+            acc0 = acc0 + tm_mr_kk(kk, blob_d, h, ikr, irate, tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)irate * n + i, cell);
+            if (irate + 1 < nrate)
+              acc1 = acc1 + tm_mr_kk(kk, blob_d, h, ikr, irate + 1, tran_dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, row0 + (long long)(irate + 1) * n + i, cell);
           }
         }
       }
@@ -1262,7 +1275,7 @@ TM_DEV void tm_gi_zero_J(Ctx<N, G> &c) {
 
 template <int N, int CPB, int G>
 TM_DEV void tm_gi_cell(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, const DevTab &h, const double *blob_d, const int *blob_i,
-                       const GiArgs &a, long long item, long long cell, bool on) {
+                       const GiArgs &a, long long item, long long cell, bool on, const double *kk) {
   const int n = lt.n, s = c.s;
   const bool rj = a.mode == GI_RJ;
   const bool from_state = !lt.act_off && !a.update_act;        // per-species gamma of the state with the class-based plan
@@ -1317,14 +1330,11 @@ TM_DEV void tm_gi_cell(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, const
 #pragma unroll 1
       for (int i = c.l; i < n; i += G) {
         double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 4
+#pragma unroll 8
         for (int irate = 0; irate < nrate; irate += 2) {
-          const double rate = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate];
-          acc0 = acc0 + rate / (1.0 + rate * dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + irate + 1) * n + i, cell);
-          if (irate + 1 < nrate) {
-            const double rate1 = blob_d[h.o_mr_rate + ikr * h.mr_ld + irate + 1];
-            acc1 = acc1 + rate1 / (1.0 + rate1 * dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + irate + 2) * n + i, cell);
-          }
+          acc0 = acc0 + tm_mr_kk(kk, blob_d, h, ikr, irate, dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + irate + 1) * n + i, cell);
+          if (irate + 1 < nrate)
+            acc1 = acc1 + tm_mr_kk(kk, blob_d, h, ikr, irate + 1, dt) * GSL(S, RXN_F_KINMR_TOTAL_SORB, ((long long)ikr * (h.mr_ld + 1) + irate + 2) * n + i, cell);
         }
         tsm[c.vr0 + (ikr * N + i) * CPB] = acc0 + acc1;
       }

@@ -26,8 +26,11 @@ k_react_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h,
 #define TM_ALLOC_SLOT 0            /* experiment hook: which word receives the tcgen05.alloc result (compute-sanitizer synccheck reports it as a barrier) */
 #endif
   __shared__ unsigned tmem_base_w[4];
+  __shared__ double mr_kk[TM_MR_KK];
   const int words = lt.blob_dbl + lt.blob_int / 2;
   for (int w = threadIdx.x; w < words; w += blockDim.x) tsm[w] = pblob[w];
+  tm_mr_kk_fill(mr_kk, threadIdx.x, blockDim.x, blob, h, dt);
+  const double *kk = h.nmr * h.mr_ld <= TM_MR_KK ? mr_kk : nullptr;
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_w[TM_ALLOC_SLOT])));
@@ -90,7 +93,7 @@ k_react_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h,
           const int g = __ffs(fm) - 1;
           const int slot = __shfl_sync(0xffffffffu, c.s, g);
           const long long cell = __shfl_sync(0xffffffffu, c.cell, g);
-          tm_coop_in_mr<N, CPB, G>(lt, S, h, bd, bi, l, slot, cell, dt, ln, 32);
+          tm_coop_in_mr<N, CPB, G>(lt, S, h, bd, bi, l, slot, cell, dt, ln, 32, kk);
         }
       }
       grp_sync<G>(c);                                           // the loads of every member are in shared memory
@@ -127,8 +130,11 @@ k_gi_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h, co
         const double *__restrict__ blob, DevState S, const int32_t *__restrict__ l2g, long long nlocal, const __grid_constant__ GiArgs a) {
   constexpr int CPB = 32 * QUADS;
   __shared__ unsigned tmem_base_w[4];
+  __shared__ double mr_kk[TM_MR_KK];
   const int words = lt.blob_dbl + lt.blob_int / 2;
   for (int w = threadIdx.x; w < words; w += blockDim.x) tsm[w] = pblob[w];
+  tm_mr_kk_fill(mr_kk, threadIdx.x, blockDim.x, blob, h, a.dt);
+  const double *kk = h.nmr * h.mr_ld <= TM_MR_KK ? mr_kk : nullptr;
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_w[0])));
@@ -152,7 +158,7 @@ k_gi_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h, co
       const long long itc = on ? item : nlocal - 1;             // a lane beyond the batch walks a valid cell with its stores off
       const long long cell = l2g ? l2g[itc] : itc;
       if (S.active && !S.active[cell]) on = false;              // imat <= 0: cycle
-      tm_gi_cell<N, CPB, G>(lt, c, S, h, bd, bi, a, itc, cell, on);
+      tm_gi_cell<N, CPB, G>(lt, c, S, h, bd, bi, a, itc, cell, on, kk);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");

@@ -193,6 +193,9 @@ static void lane_cells_g(const LaneJob &J, int G) {
   else lane_cells<N, 4>(J);
 }
 
+static const double *g_mr_kk = nullptr;     // the CTA's table of k_r/(1 + k_r dt) (tm_mr_kk_fill)
+template <class JOB> static double tm_job_dt(const JOB &J) { return J.dt; }
+#define TM_JOB_DT(J) tm_job_dt(J)
 // tensor-memory RReact kernel (rxn_tm_dev.cuh): plan built for one resident cell (CPB = 1, J in the emulated TMEM lane); the G
 // member warps of the cell are G host threads (one lane each) that run the rounds of k_react_tm: load -> trips (run, then
 // closing after an abnormal exit) -> finish, meeting at a barrier where the device has the quad's named barrier.
@@ -215,7 +218,7 @@ static void tm_thread(const LaneJob *J, LaneTab lt, int l) {
       continue;
     }
     tm_load<N, 1, G>(lt, c, S, J->e->T.d, J->e->T.i, h, i, cell, J->tran_xx, J->dt);
-    if (lt.nmr > 0) tm_coop_in_mr<N, 1, G>(lt, S, h, J->e->T.d, J->e->T.i, l, 0, cell, J->dt, 0, 1);
+    if (lt.nmr > 0) tm_coop_in_mr<N, 1, G>(lt, S, h, J->e->T.d, J->e->T.i, l, 0, cell, J->dt, 0, 1, (cell & 1) ? g_mr_kk : nullptr);   // both forms of k_r/(1 + k_r dt)
     bool closing = false;
     int pending = 0;
     for (;;) {
@@ -255,6 +258,9 @@ static void tm_cells(const LaneJob &J) {
   }
   std::vector<double> sm((size_t)lt.smem_dbl + 16, 0.0), tmem(256, 0.0);
   memcpy(sm.data(), J.P->blob.data(), J.P->blob.size());
+  static double kk_tab[TM_MR_KK];
+  rxn::tmk::tm_mr_kk_fill(kk_tab, 0, 1, J.e->T.d, h, TM_JOB_DT(J));
+  g_mr_kk = h.nmr * h.mr_ld <= TM_MR_KK ? kk_tab : nullptr;
   rxn::tmk::tsm = sm.data();
   rxn::tmk::tmh = tmem.data();
   rxn::tmk::HostGroup hg;
@@ -281,6 +287,7 @@ static void tm_cells_g(const LaneJob &J, int G) {
 struct TmGiJob {
   const LanePlan *P; Emu *e; DevState *S; const int32_t *l2g; int64_t nlocal; rxn::GiArgs a;
 };
+static double tm_job_dt(const TmGiJob &J) { return J.a.dt; }
 template <int N, int G>
 static void tm_gi_thread(const TmGiJob *J, LaneTab lt, int l) {
   using namespace rxn::tmk;
@@ -292,7 +299,7 @@ static void tm_gi_thread(const TmGiJob *J, LaneTab lt, int l) {
   for (long long i = 0; i < J->nlocal; ++i) {
     const long long cell = J->l2g ? J->l2g[i] : i;
     const bool on = !(S.active && !S.active[cell]);            // an inactive cell is walked with its stores off, as on the device
-    tm_gi_cell<N, 1, G>(lt, c, S, h, J->e->T.d, J->e->T.i, J->a, i, cell, on);
+    tm_gi_cell<N, 1, G>(lt, c, S, h, J->e->T.d, J->e->T.i, J->a, i, cell, on, (cell & 1) ? g_mr_kk : nullptr);
   }
 }
 template <int N, int G>
@@ -312,6 +319,9 @@ static void tm_gi_cells(const TmGiJob &J) {
   }
   std::vector<double> sm((size_t)lt.smem_dbl + 16, 0.0), tmem(256, 0.0);
   memcpy(sm.data(), J.P->blob.data(), J.P->blob.size());
+  static double kk_tab[TM_MR_KK];
+  rxn::tmk::tm_mr_kk_fill(kk_tab, 0, 1, J.e->T.d, h, TM_JOB_DT(J));
+  g_mr_kk = h.nmr * h.mr_ld <= TM_MR_KK ? kk_tab : nullptr;
   rxn::tmk::tsm = sm.data();
   rxn::tmk::tmh = tmem.data();
   rxn::tmk::HostGroup hg;
