@@ -84,6 +84,7 @@ struct RxnState {
   cudaStream_t h2d = nullptr, d2h = nullptr;
   cudaEvent_t ev_in[NCHUNK] = {}, ev_k[NCHUNK] = {};
   int flux_generic = 0;    // RXN_FLUX_GENERIC=1: flux Jacobian through the run-time-n kernel (tests)
+  int flux_rows = 0;       // RXN_FLUX_ROWS=1: N = 15 flux Jacobian by block rows (k_flux_jacobian_t) instead of block columns
   int gi_kernel = 0;       // global-implicit loops (RXN_GI_KERNEL): 0 auto (tensor-memory layout, else resident lanes, else thread per cell), 1 thread per cell, 2 resident lanes
   unsigned int *d_fail = nullptr;   // OR of the cell flags of the running global-implicit launch (DevState::fail)
 };
@@ -94,6 +95,7 @@ struct RxnConnSet {
   FluxRows R;
   int n = 0, device = 0;      // device kept here: the set may outlive its state
   int32_t *d_row_ptr = nullptr, *d_col = nullptr, *d_ent = nullptr, *d_l2g = nullptr;
+  int32_t *d_col_ptr = nullptr, *d_tgt_slot = nullptr, *d_tgt_ent = nullptr, *d_col_row = nullptr;   // column view (FluxCols)
   double *d_T = nullptr;        // [T_up | T_dn], each SoA [component][connection]
   bool have_coefs = false;
 };
@@ -296,6 +298,7 @@ int rxn_state_create(const RxnTables *t, int64_t ncells, RxnState **out) {
   if (const char *e = getenv("RXN_REACT_KERNEL")) s->react_kernel = atoi(e);
   if (const char *e = getenv("RXN_GI_KERNEL")) s->gi_kernel = atoi(e);
   if (const char *e = getenv("RXN_FLUX_GENERIC")) s->flux_generic = atoi(e);
+  if (const char *e = getenv("RXN_FLUX_ROWS")) s->flux_rows = atoi(e);
   int rc = RXN_OK;
   if (cudaStreamCreate(&s->stream) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
     rc = fail(RXN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -876,6 +879,14 @@ int rxn_connset_create(RxnState *s, int64_t nconn, const int32_t *id_up, const i
   if (e == cudaSuccess) e = up(&c->d_col, c->R.col);
   if (e == cudaSuccess) e = up(&c->d_ent, c->R.ent);
   if (e == cudaSuccess) e = up(&c->d_l2g, c->R.l2g);
+  {
+    FluxCols C;
+    flux_cols_build(c->R, &C);
+    if (e == cudaSuccess) e = up(&c->d_col_ptr, C.col_ptr);
+    if (e == cudaSuccess) e = up(&c->d_tgt_slot, C.tgt_slot);
+    if (e == cudaSuccess) e = up(&c->d_tgt_ent, C.tgt_ent);
+    if (e == cudaSuccess) e = up(&c->d_col_row, C.col_row);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&c->d_T, std::max<size_t>((size_t)2 * c->n * nconn, 1) * 8);
   if (e != cudaSuccess) {
     rxn_connset_destroy(c);
@@ -889,6 +900,7 @@ int rxn_connset_destroy(RxnConnSet *c) {
   if (!c) return RXN_OK;
   cudaSetDevice(c->device);
   cudaFree(c->d_row_ptr); cudaFree(c->d_col); cudaFree(c->d_ent); cudaFree(c->d_l2g); cudaFree(c->d_T);
+  cudaFree(c->d_col_ptr); cudaFree(c->d_tgt_slot); cudaFree(c->d_tgt_ent); cudaFree(c->d_col_row);
   delete c;
   return RXN_OK;
 }
@@ -973,7 +985,13 @@ int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val) {
 #ifndef FLUX_JC15
 #define FLUX_JC15 5
 #endif
-  if (n == 15 && !s->flux_generic) FLUX_JAC_T(15, FLUX_JC15);
+  if (n == 15 && !s->flux_generic && s->flux_rows == 0) {
+    // by block columns: every dtotal sector read once, blocks written from registers (rxn_flux.cuh)
+    const long long quads = (c->R.nghosted + 3) / 4;
+    k_flux_jacobian_cols<15><<<nblocks(quads, 4), 128, 0, s->stream>>>(c->R.nghosted, c->R.nconn, c->d_col_ptr, c->d_tgt_slot, c->d_tgt_ent,
+                                                                    c->d_col_row, c->d_row_ptr, c->d_ent, s->S.f[RXN_F_DTOTAL], s->ld, c->d_T,
+                                                                    c->d_T + (size_t)n * c->R.nconn, d_val);
+  } else if (n == 15 && !s->flux_generic) FLUX_JAC_T(15, FLUX_JC15);
   else if (n == 4 && !s->flux_generic) FLUX_JAC_T(4, 4);
   else if (n == 3 && !s->flux_generic) FLUX_JAC_T(3, 3);
   else {

@@ -349,6 +349,104 @@ __global__ void __launch_bounds__(32 * FLUX_NW, FLUX_MINB) k_flux_jacobian_t(lon
   }
 }
 
+// Flux Jacobian by block COLUMNS (FluxCols, rxn_flux.h): a warp owns 4 consecutive ghosted cells.  Lane = element of the
+// n x n block, e = lane + LW p with LW = the largest multiple of n that fits a warp (n = 15: 30 lanes, 8 passes), so that a
+// lane's block row i = e mod n is the same in every pass: ONE coefficient per lane and block.  The 4 cells' dtotal values of an
+// element share one 32-byte sector of the cell-fastest field: each lane loads them with two 16-byte loads - every dtotal
+// sector crosses the memory system once - and keeps them in registers (NP x 4 doubles); then every block of the 4 block columns
+// is a product by the slot's coefficient (diagonal: the sum over the row's own connections, in connection order) written as NP
+// coalesced runs of LW doubles, straight from registers: no shared-memory staging, no barrier, no neighbour reads.  Entries
+// are taken in chunks of 8 - lane u reads the descriptor of entry u, then every lane fetches its coefficient of all 8 entries
+// back to back (one round trip to L2 per chunk, not per block).  Same products and sums as the row walk (flux_row_jac_*).
+template <int N>
+__global__ void __launch_bounds__(128, 4) k_flux_jacobian_cols(long long nghosted, long long nconn, const int32_t *__restrict__ col_ptr,
+                                                              const int32_t *__restrict__ tgt_slot, const int32_t *__restrict__ tgt_ent,
+                                                              const int32_t *__restrict__ col_row, const int32_t *__restrict__ row_ptr,
+                                                              const int32_t *__restrict__ ent, const double *__restrict__ dtotal, long long ld,
+                                                              const double *__restrict__ T_up, const double *__restrict__ T_dn,
+                                                              double *__restrict__ val) {
+  constexpr int NN = N * N, LW = (32 / N) * N, NP = (NN + LW - 1) / LW;
+  static_assert(N <= 32, "one block row per lane");
+  const int lane = threadIdx.x & 31;
+  const long long c0 = 4 * ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (c0 >= nghosted) return;
+  int cp[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) cp[q] = col_ptr[min(c0 + q, nghosted)];
+  if (cp[4] == cp[0]) return;                                     // no block column here (ghost cells away from the local rows)
+  const bool work = lane < LW;
+  const long long irow = (long long)(lane % N) * nconn;           // this lane's block row in the coefficient arrays
+  double dq[NP][4];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int e = lane + LW * p;                                  // e = j*N + i
+    dq[p][0] = dq[p][1] = dq[p][2] = dq[p][3] = 0.0;
+    if (work && e < NN) {
+      const double2 *src = reinterpret_cast<const double2 *>(dtotal + (long long)e * ld + c0);   // ld is a multiple of 32: aligned
+      const double2 a = __ldg(src), b = __ldg(src + 1);
+      dq[p][0] = a.x; dq[p][1] = a.y; dq[p][2] = b.x; dq[p][3] = b.y;
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    int diag_slot = -1;
+#pragma unroll 1
+    for (int t0 = cp[cc]; t0 < cp[cc + 1]; t0 += 8) {
+      int my_ent = -2, my_slot = 0;
+      if (lane < 8 && t0 + lane < cp[cc + 1]) { my_ent = tgt_ent[t0 + lane]; my_slot = tgt_slot[t0 + lane]; }
+      double cf[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int en = __shfl_sync(0xffffffffu, my_ent, u);
+        cf[u] = 0.0;
+        if (en >= 0 && work) cf[u] = ((en & 1) ? -1.0 : 1.0) * __ldg(((en & 1) ? T_up : T_dn) + (en >> 1) + irow);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int en = __shfl_sync(0xffffffffu, my_ent, u);
+        const int slot = __shfl_sync(0xffffffffu, my_slot, u);
+        if (en == -1) diag_slot = slot;
+        if (en >= 0) {                                            // off-diagonal block of the slot's row: +Jdn / -Jup of this cell
+          double *dst = val + (long long)slot * NN + lane;
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+            if (work && lane + LW * p < NN) __stcs(dst + LW * p, fl_mul(dq[p][cc], cf[u]));
+        }
+      }
+    }
+    if (diag_slot >= 0) {                                         // diagonal block: the row's connections in connection order
+      const int row = col_row[c0 + cc];
+      const int s0 = row_ptr[row] + 1, s1 = row_ptr[row + 1];
+      double a[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) a[p] = 0.0;
+#pragma unroll 1
+      for (int sb = s0; sb < s1; sb += 8) {
+        int es_mine = -2;
+        if (lane < 8 && sb + lane < s1) es_mine = ent[sb + lane];
+        double sc[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const int es = __shfl_sync(0xffffffffu, es_mine, v);
+          sc[v] = 0.0;
+          if (es >= 0 && work) sc[v] = ((es & 1) ? -1.0 : 1.0) * __ldg(((es & 1) ? T_dn : T_up) + (es >> 1) + irow);
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          if (sb + v < s1) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) a[p] = fl_add(a[p], fl_mul(dq[p][cc], sc[v]));
+          }
+        }
+      }
+      double *dst = val + (long long)diag_slot * NN + lane;
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+        if (work && lane + LW * p < NN) __stcs(dst + LW * p, a[p]);
+    }
+  }
+}
+
 // ---- coupler connections (boundary conditions, source/sinks; rxn_flux.h) ---------------------------------------------
 // The sets are small (a grid's faces / wells): one thread per (row, component) resp. (row, block element); the row's
 // connections are added in connection order onto the values the interior kernels left in r / in the diagonal block.

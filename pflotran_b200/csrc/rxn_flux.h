@@ -123,6 +123,36 @@ inline bool flux_rows_build(int64_t nghosted, int64_t nlocal, int64_t nconn, con
   return true;
 }
 
+// Column view of the same structure, for the Jacobian: block (r, c) of the flux Jacobian depends on dtotal of the COLUMN cell c
+// alone (TFluxDerivative: Jup = dtotal_up coef_up, Jdn = dtotal_dn coef_dn) - the diagonal block on the row's own connections,
+// an off-diagonal block on the one connection of its slot.  Walking the matrix by block columns, a cell's dtotal is read
+// from HBM exactly once (the row walk reads it once per referencing row: measured 3.1x the algorithmic bytes on a 100^3 grid,
+// the z-neighbours' rows having left L2) and every block is still written whole.  Per ghosted cell c: the slots (r, c) of the
+// block-CSR value array and the entry of each (connection << 1 | side of the ROW cell; -1 in the diagonal slot).
+struct FluxCols {
+  int64_t nghosted = 0;
+  std::vector<int32_t> col_ptr;    // nghosted + 1
+  std::vector<int32_t> tgt_slot;   // nnzb: slot index in the block-CSR value array
+  std::vector<int32_t> tgt_ent;    // nnzb: FluxRows::ent of that slot
+  std::vector<int32_t> col_row;    // nghosted: local row of the ghosted cell, -1 for a ghost cell
+};
+inline void flux_cols_build(const FluxRows &R, FluxCols *C) {
+  C->nghosted = R.nghosted;
+  C->col_ptr.assign(R.nghosted + 1, 0);
+  C->col_row.assign(R.nghosted, -1);
+  for (int64_t r = 0; r < R.nlocal; ++r) C->col_row[R.l2g[r]] = (int32_t)r;
+  for (int64_t s = 0; s < R.nnzb; ++s) ++C->col_ptr[R.col[s] + 1];
+  for (int64_t c = 0; c < R.nghosted; ++c) C->col_ptr[c + 1] += C->col_ptr[c];
+  C->tgt_slot.assign(R.nnzb, 0);
+  C->tgt_ent.assign(R.nnzb, 0);
+  std::vector<int32_t> cur(C->col_ptr.begin(), C->col_ptr.end() - 1);
+  for (int64_t s = 0; s < R.nnzb; ++s) {                          // slots in ascending order: a column's blocks in row order
+    const int32_t c = R.col[s];
+    C->tgt_slot[cur[c]] = (int32_t)s;
+    C->tgt_ent[cur[c]++] = R.ent[s];
+  }
+}
+
 // ---- per-row arithmetic (device layout: T_up/T_dn SoA [component][connection]; state SoA [row][cell]) ----
 
 // residual of component i of one row: the row's connections in connection order, r = r +/- Res

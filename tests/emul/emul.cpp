@@ -543,6 +543,41 @@ int64_t emu_flux(const HostView *v, const uint8_t *active, int n, int64_t nconn,
   return R.nnzb;
 }
 
+// The flux Jacobian by block COLUMNS (FluxCols: the traversal of k_flux_jacobian_cols) - same products and sums as the row
+// walk, every block written once.  val [nnzb][n*n] must be sized by a previous emu_flux call.  Returns nnzb, < 0 on error.
+int64_t emu_flux_cols(const HostView *v, const uint8_t *active, int n, int64_t nconn, const int32_t *id_up, const int32_t *id_dn,
+                      const int32_t *g2l, int64_t nlocal, const double *area, const double *velocity, const double *disp,
+                      const double *fraction_upwind, int use_upwinding, double *val) {
+  FluxRows R;
+  if (!flux_rows_build(v->ncells, nlocal, nconn, id_up, id_dn, g2l, active, &R)) return -1;
+  FluxCols C;
+  flux_cols_build(R, &C);
+  std::vector<double> Tu((size_t)n * nconn), Td((size_t)n * nconn);
+  for (int64_t c = 0; c < nconn; ++c)
+    for (int i = 0; i < n; ++i)
+      flux_coef(velocity[c], disp[c * n + i], area[c], use_upwinding ? 0.0 : fraction_upwind[c], use_upwinding, &Tu[(size_t)i * nconn + c],
+                &Td[(size_t)i * nconn + c]);
+  const double *D = v->f[RXN_F_DTOTAL];
+  std::vector<char> written(R.nnzb, 0);
+  for (int64_t c = 0; c < C.nghosted; ++c)
+    for (int t = C.col_ptr[c]; t < C.col_ptr[c + 1]; ++t) {
+      const int32_t en = C.tgt_ent[t], slot = C.tgt_slot[t];
+      if (written[slot]++) return -2;
+      double *dst = val + (int64_t)slot * n * n;
+      for (int e = 0; e < n * n; ++e) {
+        const int i = e % n;
+        const double d = D[(int64_t)e * v->ld + c];
+        if (en >= 0) dst[e] = flux_row_jac_off(en, d, &Tu[(size_t)i * nconn], &Td[(size_t)i * nconn]);
+        else {
+          const int row = C.col_row[c];
+          dst[e] = flux_row_jac_diag(R.ent.data(), R.row_ptr[row], R.row_ptr[row + 1], d, &Tu[(size_t)i * nconn], &Td[(size_t)i * nconn]);
+        }
+      }
+    }
+  for (int64_t s = 0; s < R.nnzb; ++s) if (!written[s]) return -3;
+  return R.nnzb;
+}
+
 // Coupler connections (boundary / source-sink) through the row view and per-row arithmetic of rxn_flux.h, i.e. what
 // k_coupler_residual / k_coupler_jacobian implement.  c_ext / c_cell: nconn x n coefficient arrays for kind 0 (from
 // flux_coef with fraction_upwind = 0.5, computed here from area / velocity / disp) or qsrc / type for kind 1.

@@ -210,6 +210,14 @@ def flux(st, conn, nlocal, use_upwinding=True):
     res = np.zeros((nlocal, n))
     val = np.zeros((nnzb, n * n))
     assert L.emu_flux(*args(col, res, val)) == nnzb
+    # the same Jacobian by block columns (the traversal of k_flux_jacobian_cols): every block written exactly once, same values
+    L.emu_flux_cols.restype = C.c_int64
+    val_c = np.full((nnzb, n * n), np.nan)
+    assert L.emu_flux_cols(C.byref(v), _p(st.active, C.c_uint8), C.c_int(n), C.c_int64(nconn), _p(conn['id_up'], C.c_int32),
+                           _p(conn['id_dn'], C.c_int32), _p(conn.get('g2l'), C.c_int32), C.c_int64(nlocal), _p(conn['area'], C.c_double),
+                           _p(conn['velocity'], C.c_double), _p(conn['disp'], C.c_double), _p(conn['fraction_upwind'], C.c_double),
+                           C.c_int(int(use_upwinding)), _p(val_c, C.c_double)) == nnzb
+    assert np.array_equal(val_c, val), 'column walk and row walk of the flux Jacobian differ'
     return row_ptr, col, res, val
 
 
