@@ -465,8 +465,10 @@ def run_ours(args):
     w = synth.Workload(args.workload)
     t = w.tables
     n = args.cells or DEFAULT_CELLS[args.workload]
+    if args.scaling == 'strong':           # the total stays that of one GPU: every rank takes its contiguous share
+        n = (n + world - 1) // world
     ncomp = t.ncomp
-    start = rank * n                       # weak scaling: every rank owns n cells, globally numbered
+    start = rank * n                       # every rank owns n cells, globally numbered (weak: n fixed; strong: n = total / ranks)
     cells = synth.make_cells(w, start, n)
     rx = rt.Reaction(t, device=local_rank)
     rz = rt.Realization(rx, n)
@@ -574,7 +576,7 @@ def run_ours(args):
         traffic, traffic_src = ncu_traffic(args.workload, kinfo, n)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': WORKLOAD_DESC[args.workload], 'name': args.workload, 'cells_per_gpu': n,
                        'total_cells': total_cells, 'dt_s': args.dt, 'dt_mode': 'DT_CONSISTENT',
@@ -706,6 +708,8 @@ def main():
     ap.add_argument('--mode', default='react', choices=['react', 'gi'],
                     help='react: operator-split RTReact (headline); gi: global-implicit auxvars + residual/Jacobian blocks (config 4)')
     ap.add_argument('--gi-dt', type=float, default=1800.0, dest='gi_dt')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak (default, the driver\'s scaling run): cells per GPU fixed; strong: the single-GPU batch split over the ranks')
     ap.add_argument('--no-extra', action='store_true', help='headline only: skip the short runs of BASELINE configs 2 and 4')
     args = ap.parse_args()
     args.workload_given = any(a == '--workload' or a.startswith('--workload=') for a in sys.argv[1:])
