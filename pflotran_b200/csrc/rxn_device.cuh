@@ -58,13 +58,23 @@ __device__ __forceinline__ double logK_fit5(const double *c, double temp) {
   double tk = temp + 273.15;
   return c[0] * log(tk) + c[1] + c[2] * tk + c[3] / tk + c[4] / (tk * tk);
 }
+// x / d with r = RN(1/d): q = RN(x r) is within 1 ulp, the remainder fma(-d, q, x) is exact, and RN(q + rem r) is the correctly
+// rounded quotient (Markstein) - the same bits as the division, at 3 FMA-class instructions instead of a ~25-instruction DDIV.
+__device__ __forceinline__ double div_by(double x, double d, double r) {
+  const double q = x * r;
+  return fma(fma(-d, q, x), r, q);
+}
+// hpt form, reaction_aux.F90:1529-1571.  The reference's expression term by term; the 9 divisions by tr / pr go through
+// div_by (identical results: the fit's terms cancel, so no term may change even in its last bit - a precomputed-basis dot
+// product moved TOTAL by 3.8e-10 and was rejected).
 __device__ __forceinline__ double logK_hpt(const double *c, double temp, double pres) {
   double tk = temp + 273.15, tr = tk / 273.15, pr = pres / 1.0e7;
   double logtr = log(tr) / log(10.0);
-  return c[0] + c[1] * tr + c[2] / tr + c[3] * logtr + c[4] * tr * tr + c[5] / tr / tr +
-         c[6] * sqrt(tr) + c[7] * pr + c[8] * pr * tr + c[9] * pr / tr + c[10] * pr * logtr +
-         c[11] / pr + c[12] / pr * tr + c[13] / pr / tr + c[14] * pr * pr + c[15] * pr * pr * tr +
-         c[16] * pr * pr / tr;
+  const double itr = 1.0 / tr, ipr = 1.0 / pr;
+  return c[0] + c[1] * tr + div_by(c[2], tr, itr) + c[3] * logtr + c[4] * tr * tr + div_by(div_by(c[5], tr, itr), tr, itr) +
+         c[6] * sqrt(tr) + c[7] * pr + c[8] * pr * tr + div_by(c[9] * pr, tr, itr) + c[10] * pr * logtr +
+         div_by(c[11], pr, ipr) + div_by(c[12], pr, ipr) * tr + div_by(div_by(c[13], pr, ipr), tr, itr) + c[14] * pr * pr + c[15] * pr * pr * tr +
+         div_by(c[16] * pr * pr, tr, itr);
 }
 // srf_list: surface-complex logK is temperature-updated only for the 5-term form
 // (reaction.F90:5517-5521: hpt not implemented there).

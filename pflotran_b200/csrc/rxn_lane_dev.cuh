@@ -683,6 +683,16 @@ LANE_DEV int lane_rsolve(const LaneTab &lt, Lane<N, G> &c) {
 // ---------------------------------------------------------------------------------------------
 // lane life cycle: load a cell -> trips (one Newton iteration each) -> finish (closing RTAuxVarCompute + write back)
 
+// x / d with r = RN(1/d): RN(q + fma(-d, q, x) r), q = RN(x r), is the correctly rounded quotient (Markstein)
+LANE_DEV double hpt_div(double x, double d, double r) {
+#ifndef RXN_LANE_HOST
+  const double q = x * r;
+  return fma(fma(-d, q, x), r, q);
+#else
+  (void)r;
+  return x / d;
+#endif
+}
 // RUpdateTempDependentCoefs reaction.F90:5433-5524 -> -logK*LOG_TO_LN of this cell's T (and P)
 template <int CPB, int G>
 LANE_COLD void lane_percell_logK(int l, int ncoef, int logK_mode, int vlk, double temp, double pres, const double *blob_d, DSpec s0,
@@ -700,11 +710,15 @@ LANE_COLD void lane_percell_logK(int l, int ncoef, int logK_mode, int vlk, doubl
       else {
         const double *cf = blob_d + sp.o_coef + r * ncoef;
         if (logK_mode == RXN_LOGK_HPT) {                      // reaction_aux.F90:1529-1571
+          // the reference's expression term by term; divisions by tr / pr as Markstein-corrected products with the reciprocal
+          // (hpt_div: the correctly rounded quotient, i.e. the division's own bits - the fit's terms cancel, so none may change)
           const double tr = tk / 273.15, pr = pres / 1.0e7;
           const double logtr = log(tr) / log(10.0);
-          lk = cf[0] + cf[1] * tr + cf[2] / tr + cf[3] * logtr + cf[4] * tr * tr + cf[5] / tr / tr + cf[6] * sqrt(tr) + cf[7] * pr +
-               cf[8] * pr * tr + cf[9] * pr / tr + cf[10] * pr * logtr + cf[11] / pr + cf[12] / pr * tr + cf[13] / pr / tr +
-               cf[14] * pr * pr + cf[15] * pr * pr * tr + cf[16] * pr * pr / tr;
+          const double itr = 1.0 / tr, ipr = 1.0 / pr;
+          lk = cf[0] + cf[1] * tr + hpt_div(cf[2], tr, itr) + cf[3] * logtr + cf[4] * tr * tr + hpt_div(hpt_div(cf[5], tr, itr), tr, itr) +
+               cf[6] * sqrt(tr) + cf[7] * pr + cf[8] * pr * tr + hpt_div(cf[9] * pr, tr, itr) + cf[10] * pr * logtr + hpt_div(cf[11], pr, ipr) +
+               hpt_div(cf[12], pr, ipr) * tr + hpt_div(hpt_div(cf[13], pr, ipr), tr, itr) + cf[14] * pr * pr + cf[15] * pr * pr * tr +
+               hpt_div(cf[16] * pr * pr, tr, itr);
         } else {                                              // reaction_aux.F90:1461-1488
           lk = cf[0] * log(tk) + cf[1] + cf[2] * tk + cf[3] / tk + cf[4] / (tk * tk);
         }

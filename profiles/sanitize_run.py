@@ -77,5 +77,21 @@ if what in ('flux', 'all'):
     r = rz.RTResidualFlux(cs)
     v = rz.RTJacobianFlux(cs)
     print('flux  %d cells, %d blocks, |res| max %.3e' % (n, cs.nnz_blocks, np.abs(r).max()))
+    # boundary faces and wells (coupler sets) on top
+    from flux_common import boundary_connections, source_sinks
+    bc = boundary_connections(nx, ny, nz, w.tables.naqcomp)
+    bs = rt.CouplerSet(rz, abi.RXN_COUPLER_BOUNDARY, bc['id_dn'], nlocal)
+    bs.TFluxCoefBC(bc['area'], bc['velocity'], bc['disp'])
+    bs.set_totals(np.ascontiguousarray(np.tile(w.base['TOTAL'] * 1.1, (len(bc['id_dn']), 1))))
+    rz.RTResidualCoupler(bs, r, want_flux=True)
+    rz.RTJacobianCoupler(bs, v, cs)
+    ss = source_sinks(np.arange(nlocal), w.tables.naqcomp)
+    sk = rt.CouplerSet(rz, abi.RXN_COUPLER_SRC_SINK, ss['id_dn'], nlocal)
+    sk.TSrcSinkCoef(ss['qsrc'], ss['ss_type'])
+    sk.set_totals(np.ascontiguousarray(np.tile(w.base['TOTAL'] * 0.7, (len(ss['id_dn']), 1))))
+    rz.RTResidualCoupler(sk, r)
+    rz.RTJacobianCoupler(sk, v, cs)
+    print('coupler %d boundary faces, %d wells, |res| max %.3e' % (len(bc['id_dn']), len(ss['id_dn']), np.abs(r).max()))
+    bs.close(); sk.close()
     cs.close()
 print('sanitize_run done')
