@@ -285,6 +285,26 @@ template <int CPB, int G, class C> TM_DEV void grp_argmax_last(C &c, double &bes
   }
 }
 
+#ifndef RXN_TM_HOST
+TM_DEV long long tm_bits(double x) { return __double_as_longlong(x); }
+TM_DEV double tm_from_bits(long long b) { return __longlong_as_double(b); }
+#else
+TM_DEV long long tm_bits(double x) { long long b; memcpy(&b, &x, 8); return b; }
+TM_DEV double tm_from_bits(long long b) { double x; memcpy(&x, &b, 8); return x; }
+#endif
+TM_DEV long long tm_max_ll(long long a, long long b) { return a > b ? a : b; }
+
+// x / d with r = 1/d precomputed (one Newton correction: the quotient the division unit returns, bar double rounding)
+TM_DEV double tm_div(double x, double d, double r) {
+#ifndef RXN_TM_HOST
+  const double q = x * r;
+  return fma(fma(-d, q, x), r, q);
+#else
+  (void)r;
+  return x / d;
+#endif
+}
+
 TM_COLD double c_exp(double x) { return exp(x); }
 TM_COLD double c_log(double x) { return log(x); }
 TM_COLD double c_pow_slow(double x, double y) { return pow(x, y); }
@@ -530,8 +550,11 @@ TM_DEV void tm_srf_rxn(const LaneTab &lt, Ctx<N, G> &c, const DevState &S, int i
     }
     tempreal = tempreal / free_site_conc;
     tempreal = tempreal + 1.0;
+    {
+      const double itemp = 1.0 / tempreal;                       // the quotients below are the correctly rounded ones (tm_div)
 #pragma unroll 1
-    for (int row = c.l; row < n; row += G) tsm[c.vscr + row * CPB] = -tsm[c.vscr + row * CPB] / tempreal;   // dSx/d ln m_row
+      for (int row = c.l; row < n; row += G) tsm[c.vscr + row * CPB] = tm_div(-tsm[c.vscr + row * CPB], tempreal, itemp);   // dSx/d ln m_row
+    }
     grp_sync<G>(c);
   }
 #pragma unroll 1
@@ -758,13 +781,16 @@ TM_DEV bool tm_rsolve(const LaneTab &lt, Ctx<N, G> &c) {
     for (int i = c.l; i < N; i += G) {
       double r[TM_LD];
       tm_ld<TM_LD>(c.tb, i, 0, r);
-      double mx = 0.0, mraw = 0.0;
+      // maxima of non-negative values: their IEEE bit patterns order like integers (a 64-bit integer max is 4 instructions, fmax
+      // on doubles 7); = if (v > mx) mx = v for the finite values the solve sees
+      long long mxi = 0, mri = 0;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         const double av = fabs(r[j]), v = av * invm[j];
-        mx = fmax(mx, v);                                       // = if (v > mx) mx = v for the finite values the solve sees
-        mraw = fmax(mraw, av);
+        mxi = tm_max_ll(mxi, tm_bits(v));
+        mri = tm_max_ll(mri, tm_bits(av));
       }
+      const double mx = tm_from_bits(mxi), mraw = tm_from_bits(mri);
       const double norm = 1.0 / ((mx > 1.0) ? mx : 1.0);
 #pragma unroll
       for (int j = 0; j < N; ++j) {
@@ -1013,17 +1039,6 @@ TM_DEV void tm_coop_in_mr(const LaneTab &lt, const DevState &S, const DevTab &h,
       if (i < n && half == 0) tsm[vr0 + (ikr * N + i) * CPB] = acc0 + acc1;
     }
   }
-}
-
-// x / d with r = 1/d precomputed (one Newton correction: the quotient the division unit returns, bar double rounding)
-TM_DEV double tm_div(double x, double d, double r) {
-#ifndef RXN_TM_HOST
-  const double q = x * r;
-  return fma(fma(-d, q, x), r, q);
-#else
-  (void)r;
-  return x / d;
-#endif
 }
 
 // One trip of the warp through the Newton loop of RReact (reaction.F90:3411-3500).  Per lane: `run` - a normal
