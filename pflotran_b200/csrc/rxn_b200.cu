@@ -238,7 +238,11 @@ int rxn_tables_create(const RxnTablesDesc *d, int device, RxnTables **out) {
   Packer &P = R.P;
   memcpy(t->rows, R.rows, sizeof t->rows);
   t->blob_bytes = (size_t)h.ndbl * 8 + (size_t)h.nint * 4;
-  if (t->blob_bytes > 160 * 1024) { delete t; return fail(RXN_ERR_UNSUPPORTED, "chemistry tables (%zu bytes) exceed the shared-memory staging budget", t->blob_bytes); }
+  if (t->blob_bytes > 160 * 1024) {
+    const size_t nb = t->blob_bytes;
+    delete t;
+    return fail(RXN_ERR_UNSUPPORTED, "chemistry tables (%zu bytes) exceed the shared-memory staging budget", nb);
+  }
   std::vector<unsigned char> blob = blob_bytes(R);
   t->nvariant = variant_for(h.naq);
 
