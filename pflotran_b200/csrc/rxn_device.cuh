@@ -29,6 +29,7 @@ struct Cell {
   double total[N];    // total(:,1) [mol/L]
   double tsorb[N];    // total_sorb_eq
   double ln_act_h2o, den_kg, sat, temp, pres, volume, porosity, soil_density;
+  double hpt[6];      // tr, pr, log10(tr), sqrt(tr), 1/tr, 1/pr of this cell (hpt logK fit; filled by load_cell for RXN_LOGK_HPT tables)
   long long cell;     // state index
   int flags;
 };
@@ -67,12 +68,14 @@ __device__ __forceinline__ double div_by(double x, double d, double r) {
 // hpt form, reaction_aux.F90:1529-1571.  The reference's expression term by term; the 9 divisions by tr / pr go through
 // div_by (identical results: the fit's terms cancel, so no term may change even in its last bit - a precomputed-basis dot
 // product moved TOTAL by 3.8e-10 and was rejected).
-__device__ __forceinline__ double logK_hpt(const double *c, double temp, double pres) {
-  double tk = temp + 273.15, tr = tk / 273.15, pr = pres / 1.0e7;
-  double logtr = log(tr) / log(10.0);
-  const double itr = 1.0 / tr, ipr = 1.0 / pr;
+__device__ __forceinline__ void hpt_terms(double temp, double pres, double *t) {
+  const double tk = temp + 273.15, tr = tk / 273.15, pr = pres / 1.0e7;
+  t[0] = tr; t[1] = pr; t[2] = log(tr) / log(10.0); t[3] = sqrt(tr); t[4] = 1.0 / tr; t[5] = 1.0 / pr;
+}
+__device__ __forceinline__ double logK_hpt(const double *c, const double *t) {
+  const double tr = t[0], pr = t[1], logtr = t[2], sqtr = t[3], itr = t[4], ipr = t[5];
   return c[0] + c[1] * tr + div_by(c[2], tr, itr) + c[3] * logtr + c[4] * tr * tr + div_by(div_by(c[5], tr, itr), tr, itr) +
-         c[6] * sqrt(tr) + c[7] * pr + c[8] * pr * tr + div_by(c[9] * pr, tr, itr) + c[10] * pr * logtr +
+         c[6] * sqtr + c[7] * pr + c[8] * pr * tr + div_by(c[9] * pr, tr, itr) + c[10] * pr * logtr +
          div_by(c[11], pr, ipr) + div_by(c[12], pr, ipr) * tr + div_by(div_by(c[13], pr, ipr), tr, itr) + c[14] * pr * pr + c[15] * pr * pr * tr +
          div_by(c[16] * pr * pr, tr, itr);
 }
@@ -84,7 +87,7 @@ __device__ __forceinline__ double logK_of(const Tab &T, const DSpec &s, int r, c
   if (h.logK_mode == RXN_LOGK_FIXED || s.o_coef < 0) return T.d[s.o_logK + r];
   if (h.logK_mode == RXN_LOGK_HPT) {
     if (srf_list) return T.d[s.o_logK + r];
-    return logK_hpt(T.d + s.o_coef + r * h.ncoef, c.temp, c.pres);
+    return logK_hpt(T.d + s.o_coef + r * h.ncoef, c.hpt);
   }
   return logK_fit5(T.d + s.o_coef + r * h.ncoef, c.temp);
 }
@@ -903,6 +906,7 @@ __device__ void load_cell(const Tab &T, const DevState &S, long long cell, Cell<
   c.sat = G(S, RXN_F_SAT, 0, cell);
   c.temp = G(S, RXN_F_TEMP, 0, cell);
   c.pres = G(S, RXN_F_PRES, 0, cell);
+  if (T.h->logK_mode == RXN_LOGK_HPT) hpt_terms(c.temp, c.pres, c.hpt);
   c.volume = G(S, RXN_F_VOLUME, 0, cell);
   c.porosity = G(S, RXN_F_POROSITY, 0, cell);
   c.soil_density = G(S, RXN_F_SOIL_PARTICLE_DENSITY, 0, cell);

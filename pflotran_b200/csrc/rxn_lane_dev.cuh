@@ -698,6 +698,10 @@ template <int CPB, int G>
 LANE_COLD void lane_percell_logK(int l, int ncoef, int logK_mode, int vlk, double temp, double pres, const double *blob_d, DSpec s0,
                                  DSpec s1, DSpec s2) {
   const double tk = temp + 273.15;
+  // the cell's T, P terms of the hpt fit, once per cell (the same values the reference forms inside every evaluation)
+  const double tr = tk / 273.15, pr = pres / 1.0e7;
+  double logtr = 0.0, sqtr = 0.0, itr = 0.0, ipr = 0.0;
+  if (logK_mode == RXN_LOGK_HPT) { logtr = log(tr) / log(10.0); sqtr = sqrt(tr); itr = 1.0 / tr; ipr = 1.0 / pr; }
   int o0 = 0;
 #pragma unroll 1
   for (int q = 0; q < 3; ++q) {
@@ -712,11 +716,8 @@ LANE_COLD void lane_percell_logK(int l, int ncoef, int logK_mode, int vlk, doubl
         if (logK_mode == RXN_LOGK_HPT) {                      // reaction_aux.F90:1529-1571
           // the reference's expression term by term; divisions by tr / pr as Markstein-corrected products with the reciprocal
           // (hpt_div: the correctly rounded quotient, i.e. the division's own bits - the fit's terms cancel, so none may change)
-          const double tr = tk / 273.15, pr = pres / 1.0e7;
-          const double logtr = log(tr) / log(10.0);
-          const double itr = 1.0 / tr, ipr = 1.0 / pr;
           lk = cf[0] + cf[1] * tr + hpt_div(cf[2], tr, itr) + cf[3] * logtr + cf[4] * tr * tr + hpt_div(hpt_div(cf[5], tr, itr), tr, itr) +
-               cf[6] * sqrt(tr) + cf[7] * pr + cf[8] * pr * tr + hpt_div(cf[9] * pr, tr, itr) + cf[10] * pr * logtr + hpt_div(cf[11], pr, ipr) +
+               cf[6] * sqtr + cf[7] * pr + cf[8] * pr * tr + hpt_div(cf[9] * pr, tr, itr) + cf[10] * pr * logtr + hpt_div(cf[11], pr, ipr) +
                hpt_div(cf[12], pr, ipr) * tr + hpt_div(hpt_div(cf[13], pr, ipr), tr, itr) + cf[14] * pr * pr + cf[15] * pr * pr * tr +
                hpt_div(cf[16] * pr * pr, tr, itr);
         } else {                                              // reaction_aux.F90:1461-1488
