@@ -71,3 +71,17 @@ def test_shard_generation_is_partition_independent():
         for k in whole:
             a = whole[k][start:start + n] if whole[k].ndim == 1 or k == 'tran_xx' else whole[k][:, start:start + n]
             np.testing.assert_array_equal(part[k], a)
+
+
+def test_strong_scaling_split_covers_the_single_rank_batch():
+    """bench.py --scaling strong: every rank takes ceil(total / world) contiguous, globally numbered cells - the union is the
+    single-rank batch (plus at most world - 1 cells beyond it), shard by shard identical to the corresponding slice."""
+    w = synth.Workload('calcite')
+    total = 10007
+    whole = synth.make_cells(w, 0, total + 8)
+    for world in (2, 4, 8):
+        n = (total + world - 1) // world
+        assert n * world >= total and n * world - total < world
+        for rank in range(world):
+            part = synth.make_cells(w, rank * n, n)
+            np.testing.assert_array_equal(part['tran_xx'], whole['tran_xx'][rank * n:(rank + 1) * n])
