@@ -97,6 +97,7 @@ struct RxnConnSet {
   int32_t *d_row_ptr = nullptr, *d_col = nullptr, *d_ent = nullptr, *d_l2g = nullptr;
   int32_t *d_col_ptr = nullptr, *d_tgt_slot = nullptr, *d_tgt_ent = nullptr, *d_col_row = nullptr;   // column view (FluxCols)
   double *d_T = nullptr;        // [T_up | T_dn], each SoA [component][connection]
+  double *d_Ta = nullptr;       // the same coefficients AoS [connection][up | dn][component] (column walk of the Jacobian)
   bool have_coefs = false;
 };
 
@@ -892,6 +893,7 @@ int rxn_connset_create(RxnState *s, int64_t nconn, const int32_t *id_up, const i
     if (e == cudaSuccess) e = up(&c->d_col_row, C.col_row);
   }
   if (e == cudaSuccess) e = cudaMalloc(&c->d_T, std::max<size_t>((size_t)2 * c->n * nconn, 1) * 8);
+  if (e == cudaSuccess && c->n == 15) e = cudaMalloc(&c->d_Ta, std::max<size_t>((size_t)2 * c->n * nconn, 1) * 8);
   if (e != cudaSuccess) {
     rxn_connset_destroy(c);
     return fail(RXN_ERR_CUDA, "connection set upload failed: %s", cudaGetErrorString(e));
@@ -904,6 +906,7 @@ int rxn_connset_destroy(RxnConnSet *c) {
   if (!c) return RXN_OK;
   cudaSetDevice(c->device);
   cudaFree(c->d_row_ptr); cudaFree(c->d_col); cudaFree(c->d_ent); cudaFree(c->d_l2g); cudaFree(c->d_T);
+  cudaFree(c->d_Ta);
   cudaFree(c->d_col_ptr); cudaFree(c->d_tgt_slot); cudaFree(c->d_tgt_ent); cudaFree(c->d_col_row);
   delete c;
   return RXN_OK;
@@ -943,7 +946,7 @@ int rxn_connset_flux_coefs(RxnConnSet *c, const double *area, const double *velo
   CU(cudaMemcpyAsync(d_disp, disp_over_dist, (size_t)nc * n * 8, cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev0, s->stream));
   k_flux_coefs<<<nblocks(nc, 256), 256, (size_t)256 * (n | 1) * 8, s->stream>>>(n, nc, d_area, d_vel, d_disp, d_fu, use_upwinding, c->d_T,
-                                                                                c->d_T + (size_t)n * nc);
+                                                                                c->d_T + (size_t)n * nc, c->d_Ta);
   ++g_launches;
   c->have_coefs = true;
   return check_launch(s, true);
@@ -993,8 +996,7 @@ int rxn_flux_jacobian_batch_device(RxnState *s, RxnConnSet *c, double *d_val) {
     // by block columns: every dtotal sector read once, blocks written from registers (rxn_flux.cuh)
     const long long quads = (c->R.nghosted + 3) / 4;
     k_flux_jacobian_cols<15><<<nblocks(quads, 4), 128, 0, s->stream>>>(c->R.nghosted, c->R.nconn, c->d_col_ptr, c->d_tgt_slot, c->d_tgt_ent,
-                                                                    c->d_col_row, c->d_row_ptr, c->d_ent, s->S.f[RXN_F_DTOTAL], s->ld, c->d_T,
-                                                                    c->d_T + (size_t)n * c->R.nconn, d_val);
+                                                                    c->d_col_row, c->d_row_ptr, c->d_ent, s->S.f[RXN_F_DTOTAL], s->ld, c->d_Ta, d_val);
   } else if (n == 15 && !s->flux_generic) FLUX_JAC_T(15, FLUX_JC15);
   else if (n == 4 && !s->flux_generic) FLUX_JAC_T(4, 4);
   else if (n == 3 && !s->flux_generic) FLUX_JAC_T(3, 3);

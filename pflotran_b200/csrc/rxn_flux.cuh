@@ -14,7 +14,7 @@ namespace rxn {
 __global__ void __launch_bounds__(256) k_flux_coefs(int n, long long nconn, const double *__restrict__ area,
                                                    const double *__restrict__ velocity, const double *__restrict__ disp,
                                                    const double *__restrict__ fraction_upwind, int use_upwinding,
-                                                   double *__restrict__ T_up, double *__restrict__ T_dn) {
+                                                   double *__restrict__ T_up, double *__restrict__ T_dn, double *__restrict__ T_aos = nullptr) {
   extern __shared__ double sh[];               // [256][n | 1]
   const int ldp = n | 1;
   const long long c0 = (long long)blockIdx.x * 256;
@@ -22,13 +22,26 @@ __global__ void __launch_bounds__(256) k_flux_coefs(int n, long long nconn, cons
   for (long long k = threadIdx.x; k < span; k += 256) sh[(k / n) * ldp + k % n] = disp[c0 * n + k];   // coalesced AoS read
   __syncthreads();
   const long long c = c0 + threadIdx.x;
-  if (c >= nconn) return;
-  const double q = velocity[c], a = area[c], fu = use_upwinding ? 0.0 : fraction_upwind[c];
-  for (int i = 0; i < n; ++i) {
-    double tu, td;
-    flux_coef(q, sh[threadIdx.x * ldp + i], a, fu, use_upwinding, &tu, &td);
-    T_up[(long long)i * nconn + c] = tu;
-    T_dn[(long long)i * nconn + c] = td;
+  if (c < nconn) {
+    const double q = velocity[c], a = area[c], fu = use_upwinding ? 0.0 : fraction_upwind[c];
+    for (int i = 0; i < n; ++i) {
+      double tu, td;
+      flux_coef(q, sh[threadIdx.x * ldp + i], a, fu, use_upwinding, &tu, &td);
+      T_up[(long long)i * nconn + c] = tu;
+      T_dn[(long long)i * nconn + c] = td;
+    }
+  }
+  if (T_aos) {
+    // the same coefficients as [connection][up | dn][component] (what the Jacobian's column walk gathers: 4 sectors per entry instead
+    // of n), written with one lane per element of the CTA's contiguous range; the element is re-evaluated (same operations, same bits)
+    const long long span2 = min((long long)256, nconn - c0) * 2 * n;
+    for (long long k = threadIdx.x; k < span2; k += 256) {
+      const int cl = (int)(k / (2 * n)), r = (int)(k % (2 * n)), i = r % n;
+      const long long cc = c0 + cl;
+      double tu, td;
+      flux_coef(velocity[cc], sh[cl * ldp + i], area[cc], use_upwinding ? 0.0 : fraction_upwind[cc], use_upwinding, &tu, &td);
+      T_aos[c0 * 2 * n + k] = r < n ? tu : td;
+    }
   }
 }
 
@@ -363,8 +376,7 @@ __global__ void __launch_bounds__(128, 4) k_flux_jacobian_cols(long long nghoste
                                                               const int32_t *__restrict__ tgt_slot, const int32_t *__restrict__ tgt_ent,
                                                               const int32_t *__restrict__ col_row, const int32_t *__restrict__ row_ptr,
                                                               const int32_t *__restrict__ ent, const double *__restrict__ dtotal, long long ld,
-                                                              const double *__restrict__ T_up, const double *__restrict__ T_dn,
-                                                              double *__restrict__ val) {
+                                                              const double *__restrict__ T_aos, double *__restrict__ val) {
   constexpr int NN = N * N, LW = (32 / N) * N, NP = (NN + LW - 1) / LW;
   static_assert(N <= 32, "one block row per lane");
   const int lane = threadIdx.x & 31;
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(128, 4) k_flux_jacobian_cols(long long nghoste
   for (int q = 0; q < 5; ++q) cp[q] = col_ptr[min(c0 + q, nghosted)];
   if (cp[4] == cp[0]) return;                                     // no block column here (ghost cells away from the local rows)
   const bool work = lane < LW;
-  const long long irow = (long long)(lane % N) * nconn;           // this lane's block row in the coefficient arrays
+  const double *Trow = T_aos + lane % N;                          // this lane's block row in the [connection][up | dn][component] coefficients
   double dq[NP][4];
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
@@ -399,7 +411,8 @@ __global__ void __launch_bounds__(128, 4) k_flux_jacobian_cols(long long nghoste
       for (int u = 0; u < 8; ++u) {
         const int en = __shfl_sync(0xffffffffu, my_ent, u);
         cf[u] = 0.0;
-        if (en >= 0 && work) cf[u] = ((en & 1) ? -1.0 : 1.0) * __ldg(((en & 1) ? T_up : T_dn) + (en >> 1) + irow);
+        // row is dn (odd entry): -Jup of this cell = -(D T_up); row is up: +Jdn = D T_dn.  Slot of (connection, side) = 2 c + side
+        if (en >= 0 && work) cf[u] = ((en & 1) ? -1.0 : 1.0) * __ldg(Trow + (long long)(en ^ 1) * N);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(128, 4) k_flux_jacobian_cols(long long nghoste
         for (int v = 0; v < 8; ++v) {
           const int es = __shfl_sync(0xffffffffu, es_mine, v);
           sc[v] = 0.0;
-          if (es >= 0 && work) sc[v] = ((es & 1) ? -1.0 : 1.0) * __ldg(((es & 1) ? T_dn : T_up) + (es >> 1) + irow);
+          if (es >= 0 && work) sc[v] = ((es & 1) ? -1.0 : 1.0) * __ldg(Trow + (long long)es * N);   // own side: up for an even entry, dn for an odd one
         }
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
