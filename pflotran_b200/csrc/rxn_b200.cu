@@ -20,7 +20,6 @@
 #include "rxn_kernels.cuh"
 #include "rxn_pack.h"
 #include "rxn_lane.cuh"
-#include "rxn_small.cuh"
 #include "rxn_flux.cuh"
 
 using namespace rxn;
@@ -60,7 +59,6 @@ struct Nvtx {
 struct RxnTables {
   DevTab h;
   mutable LaneKernel lane; // resident-lane (thread per cell, state in shared memory) kernel, rxn_lane.cuh
-  SmallPlan small;         // register kernel for small chemistries (naq <= 4, no sorption), rxn_small.h
   double *d_blob = nullptr;
   size_t blob_bytes = 0;
   int device = 0;
@@ -260,7 +258,6 @@ int rxn_tables_create(const RxnTablesDesc *d, int device, RxnTables **out) {
     delete t;
     return rc2;
   }
-  small_plan_build(h, P.d, P.i, &t->small);
   rc = lane_kernel_build(h, P.d, P.i, device, &t->lane);
   if (rc != RXN_OK) { int rc2 = fail(rc, "lane plan: %s", t->lane.plan.err.c_str()); lane_kernel_free(&t->lane); cudaFree(t->d_blob); delete t; return rc2; }
   *out = t;
@@ -437,25 +434,12 @@ int rxn_set_react_kernel(RxnState *s, int which) {
   return RXN_OK;
 }
 
-// the register kernel for small chemistries is preferred where it applies; RXN_SMALL=0 or an explicit resident-lane shape
-// request (RXN_LANE_N / _G / _CPB: tests and ablations of that kernel) switch it off
-static bool small_ok(const RxnState *s) {
-  if (!s->t->small.usable || s->S.f[RXN_F_DTOTAL] || s->S.f[RXN_F_DTOTAL_SORB_EQ]) return false;
-  if (!(s->react_kernel == 0 || s->react_kernel == 3)) return false;
-  if (const char *e = getenv("RXN_SMALL")) { if (atoi(e) == 0) return false; }
-  if (getenv("RXN_LANE_N") || getenv("RXN_LANE_G") || getenv("RXN_LANE_CPB")) return false;
-  return true;
-}
-
 int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
   if (!s || !buf || len < 1) return fail(RXN_ERR_INVALID, "bad argument");
   const RxnTables *t = s->t;
   const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
   const bool lane_ok = t->lane.plan.usable && no_dtotal;
-  if (small_ok(s))
-    snprintf(buf, (size_t)len, "register kernel (small chemistry: naq=%d, %d complexes, %d minerals; one thread per cell, tables as kernel parameter, "
-             "Newton matrix in registers) threads=128", t->small.st.n, t->small.st.ncplx, t->small.st.nkin);
-  else if (lane_ok && t->lane.plan_tm.usable && (s->react_kernel == 0 || s->react_kernel == 3))
+  if (lane_ok && t->lane.plan_tm.usable && (s->react_kernel == 0 || s->react_kernel == 3))
     snprintf(buf, (size_t)len, "tensor-memory N=%d cells/CTA=%d warps/cell=%d threads=%d smem=%zu B plan=%zu B J in TMEM (spec %d, planA %d, planB %d terms)",
              t->lane.plan_tm.lt.N, t->lane.plan_tm.lt.CPB, t->lane.G_tm, 128 * t->lane.G_tm, t->lane.plan_tm.smem_bytes,
              t->lane.plan_tm.blob.size(), t->lane.plan_tm.terms_spec, t->lane.plan_tm.terms_A, t->lane.plan_tm.terms_B);
@@ -476,12 +460,6 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
   const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
   const bool lane_ok = t->lane.plan.usable && no_dtotal;
   if (s->react_kernel == 2) return fail(RXN_ERR_UNSUPPORTED, "the cooperative kernel of round 1 has been removed (use 0, 1 or 3)");
-  if (small_ok(s)) {
-    int rc = small_launch_react(t->small, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->stream, cell0);
-    if (rc != RXN_OK) return fail(rc, "register kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    ++g_launches;
-    return RXN_OK;
-  }
   if (s->react_kernel == 3 && !lane_ok)
     return fail(RXN_ERR_UNSUPPORTED, "resident-lane kernel unavailable: %s", t->lane.plan.usable ? "DTOTAL is materialised" : t->lane.plan.err.c_str());
   const bool use_lane = lane_ok && (s->react_kernel == 0 || s->react_kernel == 3);
@@ -535,8 +513,8 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
     CU(cudaMemcpyAsync(d_l2g, l2g, (size_t)nlocal * 4, cudaMemcpyHostToDevice, s->stream));
   }
   const RxnTables *t = s->t;
-  const bool lane = small_ok(s) || (t->lane.plan.usable && !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ] &&
-                                    (s->react_kernel == 0 || s->react_kernel == 3));
+  const bool lane = t->lane.plan.usable && !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ] &&
+                    (s->react_kernel == 0 || s->react_kernel == 3);
   if (lane && nlocal >= 262144 && !getenv("RXN_NO_PIPELINE")) {
     // resident-lane kernel on a large batch: NCHUNK chunks; chunk c+1 crosses PCIe while chunk c is solved and chunk
     // c-1 returns (full duplex), so the host-buffer call costs about the kernel time

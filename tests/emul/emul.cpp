@@ -22,8 +22,6 @@ using std::isfinite;
 #define RXN_TM_HOST 1
 #include "../../pflotran_b200/csrc/rxn_tm_dev.cuh"
 #include "../../pflotran_b200/csrc/rxn_flux.h"
-#define RXN_SMALL_HOST 1
-#include "../../pflotran_b200/csrc/rxn_small_dev.cuh"
 
 using namespace rxn;
 
@@ -578,26 +576,6 @@ int64_t emu_flux_cols(const HostView *v, const uint8_t *active, int n, int64_t n
     }
   for (int64_t s = 0; s < R.nnzb; ++s) if (!written[s]) return -3;
   return R.nnzb;
-}
-
-// register kernel for small chemistries (rxn_small_dev.cuh): one cell after the other
-int emu_react_small(void *hh, const HostView *v, double *tran_xx, const uint8_t *active, const int32_t *l2g, int64_t nlocal, double dt,
-                    int dt_mode, int32_t *iters, int32_t *flags, char *err, int errlen) {
-  Emu *e = (Emu *)hh;
-  DevState S = mk_state(v, active);
-  SmallPlan P;
-  small_plan_build(e->R.h, e->R.P.d, e->R.P.i, &P);
-  if (!P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
-  for (long long i = 0; i < nlocal; ++i) {
-    const long long cell = l2g ? l2g[i] : i;
-    if (S.active && !S.active[cell]) {
-      if (iters) iters[i] = 0;
-      if (flags) flags[i] = RXN_FLAG_INACTIVE;
-      continue;
-    }
-    rxn::small::small_react_cell<SMALL_N>(P.st, S, i, cell, tran_xx, dt, dt_mode, iters, flags);
-  }
-  return 0;
 }
 
 // Coupler connections (boundary / source-sink) through the row view and per-row arithmetic of rxn_flux.h, i.e. what

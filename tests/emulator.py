@@ -19,7 +19,7 @@ _LIB = None
 def build(force=False):
     so = os.path.join(_HERE, 'libemul.so')
     deps = [os.path.join(_HERE, 'emul.cpp')] + [os.path.join(_ROOT, 'pflotran_b200', 'csrc', f)
-                                                 for f in ('rxn_device.cuh', 'rxn_pack.h', 'rxn_tab.h', 'rxn_lane.h', 'rxn_lane_dev.cuh', 'rxn_tm_dev.cuh', 'rxn_flux.h', 'rxn_small.h', 'rxn_small_dev.cuh')] + \
+                                                 for f in ('rxn_device.cuh', 'rxn_pack.h', 'rxn_tab.h', 'rxn_lane.h', 'rxn_lane_dev.cuh', 'rxn_tm_dev.cuh', 'rxn_flux.h')] + \
         [os.path.join(_ROOT, 'include', 'rxn_b200.h')]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-pthread',
@@ -111,21 +111,6 @@ class Emulator:
         rc = lib().emu_react_tm(self.h, C.byref(v), _p(tran_xx, C.c_double), _p(st.active, C.c_uint8),
                                 _p(l2g, C.c_int32), C.c_int64(n), C.c_double(dt), C.c_int(dt_mode),
                                 _p(iters, C.c_int32), _p(flags, C.c_int32), C.c_int(G), C.c_int(N), buf, 512)
-        if rc != 0:
-            raise NotImplementedError(buf.value.decode())
-        return iters, flags
-
-    def react_small(self, st, tran_xx, dt, dt_mode=abi.RXN_DT_CONSISTENT, l2g=None, maxit=None):
-        """RReact through the register kernel's routine for small chemistries (rxn_small_dev.cuh)."""
-        if maxit is not None:
-            lib().emu_set_maxit(self.h, maxit)
-        n = tran_xx.shape[0]
-        iters = np.zeros(n, dtype=np.int32)
-        flags = np.zeros(n, dtype=np.int32)
-        v = st.view()
-        buf = C.create_string_buffer(512)
-        rc = lib().emu_react_small(self.h, C.byref(v), _p(tran_xx, C.c_double), _p(st.active, C.c_uint8), _p(l2g, C.c_int32), C.c_int64(n),
-                                   C.c_double(dt), C.c_int(dt_mode), _p(iters, C.c_int32), _p(flags, C.c_int32), buf, 512)
         if rc != 0:
             raise NotImplementedError(buf.value.decode())
         return iters, flags

@@ -82,54 +82,6 @@ def test_react_tensor_memory_routines(name, dt, mode, G):
     assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
 
 
-SMALL_WORKLOADS = ['calcite', 'hpt_calcite', 'calcite_kinetics', 'calcite_kinetics_vf', 'calcite_rate_laws', 'calcite_fit5', 'carbonate_unit',
-                   'carbonate_dh', 'ca_carbonate_unit', 'ca_carbonate_dh']
-
-
-@pytest.mark.parametrize('name', SMALL_WORKLOADS)
-@pytest.mark.parametrize('dt,mode', [(3600.0, abi.RXN_DT_CONSISTENT), (1.0, abi.RXN_DT_AS_WRITTEN)])
-def test_react_register_kernel_small_chemistries(name, dt, mode):
-    """The register kernel's routine for small chemistries (rxn_small_dev.cuh: dense tables as kernel parameter, everything of
-    a cell in registers, ludcmp with select pivoting) against the oracle - or, where the tables are outside it, its refusal."""
-    w, cells = workload_cells(name, 1500)
-    t = w.tables
-    fits = t.naqcomp <= 4 and t.neqcplx <= 8 and t.nkinmnrl <= 2 and t.nsrfcplxrxn == 0
-    st_o = synth.host_state(w, cells)
-    st_e = st_o.copy()
-    xo = cells['tran_xx'].copy()
-    xe = xo.copy()
-    if not fits:
-        with pytest.raises(NotImplementedError):
-            Emulator(w.tables).react_small(st_e, xe, dt, mode)
-        return
-    it_o, fl_o = Oracle(w.tables).react(st_o, xo, dt, mode, maxit=10000)
-    it_e, fl_e = Emulator(w.tables).react_small(st_e, xe, dt, mode)
-    assert (it_o == it_e).all() and (fl_o == fl_e).all()
-    ok = (fl_o & ~3) == 0
-    assert rel_err(xe[ok], xo[ok]).max() <= RTOL
-    assert_state_close(st_e, st_o, cells=np.where(ok)[0], what=name, tables=w.tables)
-
-
-def test_register_kernel_iteration_cap_inactive_and_refusals():
-    w, cells = workload_cells('calcite', 300)
-    st_o = synth.host_state(w, cells)
-    st_o.active[::7] = 0
-    st_e = st_o.copy()
-    xo = cells['tran_xx'].copy()
-    xe = xo.copy()
-    it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=2)
-    it_e, fl_e = Emulator(w.tables).react_small(st_e, xe, 3600.0, abi.RXN_DT_CONSISTENT, maxit=2)
-    assert (fl_e & abi.RXN_FLAG_CAPPED).any() and (fl_e[::7] == abi.RXN_FLAG_INACTIVE).all()
-    assert (it_o == it_e).all() and (fl_o == fl_e).all()
-    act = np.where(st_o.active != 0)[0]
-    assert rel_err(xe[act], xo[act]).max() <= RTOL
-    assert_state_close(st_e, st_o, cells=act, what='capped', tables=w.tables)
-    for name in ('hanford300a_eq', 'surface_complexation', 'ion_exchange', 'mineral_prefactor'):
-        w2, c2 = workload_cells(name, 4)
-        with pytest.raises(NotImplementedError):
-            Emulator(w2.tables).react_small(synth.host_state(w2, c2), c2['tran_xx'].copy(), 3600.0)
-
-
 @pytest.mark.parametrize('G', [1, 2, 3, 4])
 def test_tensor_memory_iteration_cap_and_inactive(G):
     """Abnormal exit (iteration cap) in the predicated trip: the lane turns `closing`, redoes RTotal, then finishes."""
