@@ -228,6 +228,38 @@ def test_global_implicit_auxvars_with_derivative_blocks(name, gi_kernel, monkeyp
     assert (np.abs(a_g - a_o[l2g]) / np.maximum(a_scale[l2g], 1e-300)).max() <= RTOL
 
 
+@pytest.mark.parametrize('gi_kernel', [0, 2, 1])
+def test_global_implicit_blocks_inactive_cells_and_l2g(gi_kernel, monkeypatch):
+    """Residual / Jacobian blocks through an l2g map with inactive cells, on the tensor-memory layout (0), the resident lanes (2)
+    and one thread per cell (1): blocks of inactive cells stay as the call zeroed them, every other block meets the oracle; a batch
+    that does not fill the last round of a CTA (lanes beyond the batch walk a valid cell with their stores off)."""
+    monkeypatch.setenv('RXN_GI_KERNEL', str(gi_kernel))
+    n = 128 * 148 + 77                                     # one full round of k_gi_tm on a B200 + a ragged tail
+    w, cells = workload_cells('hanford300a_eq', n)
+    st_o = synth.host_state(w, cells)
+    st_o.active = np.ones(n, dtype=np.uint8)
+    st_o.active[::13] = 0
+    st_g = st_o.copy()
+    rx, rz = _gpu_state(w, st_g)
+    rz.set_cell_scalars(active=st_o.active)
+    orc = Oracle(w.tables)
+    rng = np.random.default_rng(5)
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((n, w.ncomp))))
+    orc.update_auxvars(st_o, xx, True, nthreads=8)
+    rz.RTUpdateAuxVars(xx, True)
+    l2g = np.ascontiguousarray(rng.permutation(n)[:n - 1000].astype(np.int32))
+    r_g, j_g = rz.RTResidualJacobianNonFlux(900.0, l2g=l2g)
+    a_o = orc.fixed_accum(st_o.copy(), xx, nthreads=8)
+    r_o, j_o = orc.residual_jacobian(st_o, 900.0, nthreads=8)
+    dead = st_o.active[l2g] == 0
+    assert dead.any() and (r_g[dead] == 0).all() and (j_g[dead] == 0).all()
+    live = ~dead
+    rs = residual_scale(st_o, w.tables, r_o, a_o, 900.0)
+    assert (np.abs(r_g[live] - r_o[l2g[live]]) / np.maximum(rs[l2g[live]], 1e-300)).max() <= RTOL
+    js = jacobian_scale(st_o, j_o, w.ncomp)
+    assert (np.abs(j_g[live] - j_o[l2g[live]]) / np.maximum(js[l2g[live]], 1e-300)).max() <= RTOL
+
+
 def test_global_implicit_entry_points_report_failed_cells():
     """A cell whose global-implicit evaluation is not finite (or raises a flag the reference stops on) makes the entry point
     return RXN_ERR_CELL_FAILED instead of handing NaN residuals to the caller; an out-of-range l2g entry is RXN_ERR_INVALID."""
