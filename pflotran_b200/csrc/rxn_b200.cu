@@ -702,7 +702,6 @@ int rxn_update_auxvars_batch_device(RxnState *s, const double *d_xx_loc, int upd
   Nvtx nvtx_("RTAuxVars");
   if (!s) return fail(RXN_ERR_INVALID, "null state");
   CU(cudaSetDevice(s->t->device));
-  const RxnTables *t = s->t;
   { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
   { const int rcu = launch_update_auxvars(s, d_xx_loc, update_act_coefs); if (rcu != RXN_OK) return rcu; }

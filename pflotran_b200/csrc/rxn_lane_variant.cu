@@ -136,11 +136,9 @@ k_gi_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h, 
   constexpr int W = 32 / G;                                    // cell columns per warp; lane = l*W + column
   const int col = ln % W, l = ln / W, s = (t >> 5) * W + col;
   const unsigned gm = (G == 1 ? 1u : G == 2 ? 0x00010001u : G == 4 ? 0x01010101u : G == 8 ? 0x11111111u : 0x55555555u) << col;
-  const unsigned below = (1u << col) - 1u;                     // leaders of the groups before this one
 #else
   const int s = t / G, l = t % G;
   const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (ln & ~(G - 1)));
-  const unsigned below = (1u << (ln & ~(G - 1))) - 1u;
 #endif
   const double *bd = blob;
   const int *bi = reinterpret_cast<const int *>(blob + h.ndbl);
