@@ -383,6 +383,47 @@ def test_full_size_sampled_against_oracle(name, n):
                        st_o, fields=['TOTAL', 'SEC_MOLAL'], cells=np.where(ok)[0], what=name + ' full size', tables=w.tables)
 
 
+@pytest.mark.parametrize('name,n', [('hanford300a_eq', 1_000_000), ('hpt_calcite', 2_000_000)])
+def test_full_size_global_implicit_sampled_against_oracle(name, n):
+    """BASELINE-size global-implicit step (config 4 and its 300A counterpart): RTUpdateAuxVars with activity update + the residual
+    and Jacobian blocks of every cell on the GPU (device-resident outputs), a seeded sample of cells re-run by the oracle, and the
+    size-independent properties everywhere: finite blocks, no failed cell, a positive diagonal (d accumulation_i / d m_i dominates)."""
+    w, cells = workload_cells(name, n)
+    t = w.tables
+    nc = t.ncomp
+    rx = rt.Reaction(t)
+    rz = rt.Realization(rx, n)
+    for f, v in w.base.items():
+        rz.broadcast(f, v)
+    rz.set_cell_scalars(porosity=cells['porosity'], temp=cells['temp'], pres=cells['pres'])
+    if t.nkinmnrl:
+        rz.upload('MNRL_VOLFRAC', cells['volfrac'])
+    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * (cells['tran_xx'] / w.base['TOTAL'][None, :]))
+    rz.RTUpdateAuxVars(xx, True)
+    d_res = rz.device_alloc(n * nc * 8)
+    d_jac = rz.device_alloc(n * nc * nc * 8)
+    rz.RTResidualJacobianNonFlux_device(n, 1800.0, d_res, d_jac)       # raises RXN_ERR_CELL_FAILED on any non-finite cell
+    sample = np.sort(np.random.default_rng(13).choice(n, 2000, replace=False))
+    # the sampled rows of the device arrays (contiguous chunks around the sample would need n round trips: copy everything once)
+    res = np.empty((n, nc)); jac = np.empty((n, nc * nc))
+    rz.device_copy(res, d_res, res.nbytes, 1)
+    rz.device_copy(jac, d_jac, jac.nbytes, 1)
+    assert np.isfinite(res).all() and np.isfinite(jac).all()
+    diag = jac.reshape(n, nc, nc)[:, np.arange(nc), np.arange(nc)]
+    assert (diag[:, :t.naqcomp] > 0).all()                             # d(accumulation_i)/d m_i dominates every diagonal entry
+    sub = {k: (v[sample] if v.ndim == 1 else (v[sample] if k == 'tran_xx' else v[:, sample])) for k, v in cells.items()}
+    st_o = synth.host_state(w, sub)
+    orc = Oracle(t)
+    orc.update_auxvars(st_o, np.ascontiguousarray(xx[sample]), True, nthreads=8)
+    a_o = orc.fixed_accum(st_o.copy(), np.ascontiguousarray(xx[sample]), nthreads=8)
+    r_o, j_o = orc.residual_jacobian(st_o, 1800.0, nthreads=8)
+    rs = residual_scale(st_o, t, r_o, a_o, 1800.0)
+    assert (np.abs(res[sample] - r_o) / np.maximum(rs, 1e-300)).max() <= RTOL
+    js = jacobian_scale(st_o, j_o, nc)
+    assert (np.abs(jac[sample] - j_o) / np.maximum(js, 1e-300)).max() <= RTOL
+    rz.device_free(d_res); rz.device_free(d_jac)
+
+
 # ---- ReactionEquilibrateConstraint batched on the GPU (SURVEY.md 8f.1) -----------------------------------------------
 class _GpuBackend:
     """equilibrate / update_auxvars of the KAT start-up sequence through the C ABI."""
