@@ -34,7 +34,7 @@ module Rxn_B200_module
     RXN_F_MNRL_AREA = 13, RXN_F_MNRL_RATE = 14, RXN_F_DEN_KG = 15, RXN_F_SAT = 16, RXN_F_TEMP = 17, &
     RXN_F_PRES = 18, RXN_F_VOLUME = 19, RXN_F_POROSITY = 20, RXN_F_SOIL_PARTICLE_DENSITY = 21, &
     RXN_F_DTOTAL = 22, RXN_F_DTOTAL_SORB_EQ = 23, RXN_F_KINSRFCPLX_CONC = 24, RXN_F_KINSRFCPLX_CONC_KP1 = 25, &
-    RXN_F_KINSRFCPLX_FREE_SITE_CONC = 26
+    RXN_F_KINSRFCPLX_FREE_SITE_CONC = 26, RXN_F_IMMOBILE = 27
 
   ! struct RxnSpecList
   type, bind(C), public :: rxn_spec_list_type
@@ -148,6 +148,28 @@ module Rxn_B200_module
     type(c_ptr) :: kinsrfcplx_backward_rate
     integer(c_int32_t) :: kinsrfcplx_ld
     integer(c_int32_t) :: reserved2
+    ! immobile decay (reaction%immobile%decay*), microbial reactions (reaction%microbial%*)
+    type(c_ptr) :: immobile_decayspecid
+    type(c_ptr) :: immobile_decay_rate_constant
+    integer(c_int32_t) :: microbial_ld
+    integer(c_int32_t) :: microbial_monod_ld
+    integer(c_int32_t) :: microbial_inhibition_ld
+    integer(c_int32_t) :: nmicrobial_monod, nmicrobial_inhibition, reserved3
+    type(c_ptr) :: microbial_specid
+    type(c_ptr) :: microbial_stoich
+    type(c_ptr) :: microbial_rate_constant
+    type(c_ptr) :: microbial_activation_energy
+    type(c_ptr) :: microbial_biomassid
+    type(c_ptr) :: microbial_biomass_yield
+    type(c_ptr) :: microbial_monodid
+    type(c_ptr) :: microbial_inhibitionid
+    type(c_ptr) :: microbial_monod_specid
+    type(c_ptr) :: microbial_monod_K
+    type(c_ptr) :: microbial_monod_Cth
+    type(c_ptr) :: microbial_inhibition_type
+    type(c_ptr) :: microbial_inhibition_specid
+    type(c_ptr) :: microbial_inhibition_C
+    type(c_ptr) :: microbial_inhibition_C2
   end type rxn_tables_desc_type
 
   public :: rxn_tables_create, rxn_tables_destroy, rxn_state_create, rxn_state_destroy, &

@@ -94,7 +94,7 @@ typedef struct RxnSpecList {
 typedef struct RxnTablesDesc {
   int32_t struct_size;            /* = sizeof(RxnTablesDesc) */
   int32_t naqcomp;
-  int32_t ncomp;                  /* must equal naqcomp (no immobile/colloid dofs) */
+  int32_t ncomp;                  /* = naqcomp + nimmobile (reaction%ncomp; immobile dofs follow the aqueous ones, offset_immobile = naqcomp; no colloid dofs) */
   int32_t logK_mode;              /* RXN_LOGK_*            */
   int32_t num_logK_coef;
   int32_t use_log_formulation;
@@ -178,9 +178,10 @@ typedef struct RxnTablesDesc {
   const double *eqkdlangmuirb;
   const double *eqkdfreundlichn;
 
-  /* reaction types outside the path: all must be 0, else RXN_ERR_UNSUPPORTED
-   * (active gas/RTotalGas, immobile, colloids, microbial, immobile decay, sandbox, CLM, solid solution,
-   * CO2 flow modes -> RTotalCO2).  ngeneral_rxn and nradiodecay_rxn are COUNTS of supported reactions (tables below). */
+  /* reaction types outside the path: must be 0, else RXN_ERR_UNSUPPORTED
+   * (active gas/RTotalGas, colloids, sandbox, CLM, solid solution, CO2 flow modes -> RTotalCO2, numerical Jacobian).
+   * ngeneral_rxn, nradiodecay_rxn, nmicrobial_rxn, nimmobile_decay_rxn and nimmobile are COUNTS of supported reactions /
+   * immobile species (tables below). */
   int32_t nactive_gas, nimmobile, ncoll, ngeneral_rxn, nradiodecay_rxn, nmicrobial_rxn,
           nimmobile_decay_rxn, has_sandbox, has_clm, has_solid_solution, co2_flow_mode,
           numerical_derivatives;
@@ -210,7 +211,35 @@ typedef struct RxnTablesDesc {
   const double *kinsrfcplx_backward_rate;
   int32_t kinsrfcplx_ld;
   int32_t reserved2;
+  /* immobile species (reaction_immobile_aux.F90:29-60; rt_auxvar%immobile [mol/m^3 bulk], dofs naqcomp+1 .. ncomp) and their
+   * first-order decay, RImmobileDecay (reaction_immobile.F90:240-293) */
+  const int32_t *immobile_decayspecid;        /* [nimmobile_decay_rxn] 1-based immobile species id */
+  const double *immobile_decay_rate_constant; /* [nimmobile_decay_rxn] 1/s */
+  /* microbial reactions, RMicrobial (reaction_microbial.F90:236-450; tables reaction_microbial_aux.F90:62-82, built at
+   * reaction_database.F90:3126-3333).  Species ids run over the ncomp dofs (an immobile species i is naqcomp + i). */
+  int32_t microbial_ld;                       /* = m: specid(0:m,n), stoich(m,n) */
+  int32_t microbial_monod_ld;                 /* = m: monodid(0:m,n) */
+  int32_t microbial_inhibition_ld;            /* = m: inhibitionid(0:m,n) */
+  int32_t nmicrobial_monod, nmicrobial_inhibition, reserved3;
+  const int32_t *microbial_specid;
+  const double *microbial_stoich;
+  const double *microbial_rate_constant;      /* [nmicrobial_rxn] */
+  const double *microbial_activation_energy;  /* [nmicrobial_rxn] J/mol, or NULL (allocated only if some reaction sets one) */
+  const int32_t *microbial_biomassid;         /* [nmicrobial_rxn] 1-based immobile species id, 0 = no biomass term */
+  const double *microbial_biomass_yield;      /* [nmicrobial_rxn] */
+  const int32_t *microbial_monodid;           /* 1-based ids into the monod_* arrays */
+  const int32_t *microbial_inhibitionid;
+  const int32_t *microbial_monod_specid;      /* [nmicrobial_monod] primary species */
+  const double *microbial_monod_K;
+  const double *microbial_monod_Cth;
+  const int32_t *microbial_inhibition_type;   /* [nmicrobial_inhibition] RXN_INHIBITION_* */
+  const int32_t *microbial_inhibition_specid;
+  const double *microbial_inhibition_C;
+  const double *microbial_inhibition_C2;
 } RxnTablesDesc;
+
+/* reaction_microbial_aux.F90:13-16 */
+enum { RXN_INHIBITION_THRESHOLD = 1, RXN_INHIBITION_THERMODYNAMIC = 2, RXN_INHIBITION_MONOD = 3, RXN_INHIBITION_INVERSE_MONOD = 4 };
 
 /* Per-cell state fields (reactive_transport_auxvar_type, reference
  * src/pflotran/reactive_transport_aux.F90:18-73; global_auxvar_type global_aux.F90:11-33;
@@ -239,6 +268,7 @@ typedef enum RxnField {
   RXN_F_KINSRFCPLX_CONC,      /* nkinsrfcplx (complexes of the kinetic surface complexation reaction): S^k     */
   RXN_F_KINSRFCPLX_CONC_KP1,  /* nkinsrfcplx: S^{k+1}, becomes S^k in rxn_update_kinetic_state_batch (reaction.F90:5411-5419) */
   RXN_F_KINSRFCPLX_FREE_SITE_CONC, /* nkinsrfcplxrxn */
+  RXN_F_IMMOBILE,             /* nimmobile: rt_auxvar%immobile [mol/m^3 bulk] (reactive_transport_aux.F90:56) */
   RXN_F_COUNT
 } RxnField;
 

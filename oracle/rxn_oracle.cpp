@@ -107,6 +107,12 @@ struct Tables {
   // kinetic surface complexation (one reaction): its srfcplxrxn (0-based), rates per complex
   int nkinrxn = 0; std::vector<int> kin_rxn; std::vector<double> kin_kf, kin_kb; int kin_ld = 0;
   int nkinsrf() const { return nkinrxn ? (int)rxn_cplx[kin_rxn[0]].size() : 0; }
+  // immobile species (dofs naq .. ncomp-1) and their decay; microbial reactions (0-based ids; species ids over the ncomp dofs)
+  int nim = 0, nimdecay = 0; std::vector<int> imdec_id; std::vector<double> imdec_k;
+  int nmic = 0; bool mic_has_Ea = false;
+  std::vector<std::vector<int>> mic_id, mic_monod, mic_inhib; std::vector<std::vector<double>> mic_st;
+  std::vector<double> mic_k, mic_Ea, mic_yield; std::vector<int> mic_biomass;   // mic_biomass: 0-based immobile id or -1
+  std::vector<int> monod_spec, inhib_spec, inhib_type; std::vector<double> monod_K, monod_Cth, inhib_C, inhib_C2;
   int neqsorb() const { return nionx + nkd + (int)eq_rxn.size(); }
   int nkinmr() const { return (int)mr_rxn.size(); }
 };
@@ -195,6 +201,28 @@ Tables *load_tables(const RxnTablesDesc *d) {
     cp(t->kin_kf, d->kinsrfcplx_forward_rate, (size_t)t->kin_ld * t->nkinrxn);
     cp(t->kin_kb, d->kinsrfcplx_backward_rate, (size_t)t->kin_ld * t->nkinrxn);
   }
+  t->nim = d->nimmobile; t->nimdecay = d->nimmobile_decay_rxn;
+  for (int r = 0; r < t->nimdecay; ++r) { t->imdec_id.push_back(d->immobile_decayspecid[r] - 1); t->imdec_k.push_back(d->immobile_decay_rate_constant[r]); }
+  t->nmic = d->nmicrobial_rxn;
+  if (t->nmic > 0) {
+    lists(d->microbial_specid, d->microbial_stoich, d->microbial_ld, t->nmic, t->mic_id, t->mic_st);
+    cp(t->mic_k, d->microbial_rate_constant, t->nmic);
+    t->mic_has_Ea = d->microbial_activation_energy != nullptr; cp(t->mic_Ea, d->microbial_activation_energy, t->nmic);
+    cp(t->mic_yield, d->microbial_biomass_yield, t->nmic);
+    t->mic_monod.assign(t->nmic, {}); t->mic_inhib.assign(t->nmic, {});
+    for (int r = 0; r < t->nmic; ++r) {
+      t->mic_biomass.push_back(d->microbial_biomassid ? d->microbial_biomassid[r] - 1 : -1);
+      const int nm = d->microbial_monodid ? d->microbial_monodid[(size_t)r * (d->microbial_monod_ld + 1)] : 0;
+      for (int k = 1; k <= nm; ++k) t->mic_monod[r].push_back(d->microbial_monodid[(size_t)r * (d->microbial_monod_ld + 1) + k] - 1);
+      const int ni = d->microbial_inhibitionid ? d->microbial_inhibitionid[(size_t)r * (d->microbial_inhibition_ld + 1)] : 0;
+      for (int k = 1; k <= ni; ++k) t->mic_inhib[r].push_back(d->microbial_inhibitionid[(size_t)r * (d->microbial_inhibition_ld + 1) + k] - 1);
+    }
+    for (int k = 0; k < d->nmicrobial_monod; ++k) t->monod_spec.push_back(d->microbial_monod_specid[k] - 1);
+    cp(t->monod_K, d->microbial_monod_K, d->nmicrobial_monod); cp(t->monod_Cth, d->microbial_monod_Cth, d->nmicrobial_monod);
+    for (int k = 0; k < d->nmicrobial_inhibition; ++k) t->inhib_spec.push_back(d->microbial_inhibition_specid[k] - 1);
+    cp(t->inhib_type, d->microbial_inhibition_type, d->nmicrobial_inhibition);
+    cp(t->inhib_C, d->microbial_inhibition_C, d->nmicrobial_inhibition); cp(t->inhib_C2, d->microbial_inhibition_C2, d->nmicrobial_inhibition);
+  }
   return t;
 }
 
@@ -208,6 +236,7 @@ struct AuxVar {
   std::vector<double> ionx_ref_sorbed, ionx_conc;
   std::vector<double> mnrl_volfrac, mnrl_area, mnrl_rate;
   std::vector<double> kinsrfcplx_conc, kinsrfcplx_conc_kp1, kinsrfcplx_free_site_conc;   // (nkinsrfcplx,1), (nkinsrfcplx,1), (nkinsrfcplxrxn)
+  std::vector<double> immobile;          // nimmobile [mol/m^3 bulk]
   double den_kg = 0, sat = 0, temp = 0, pres = 0, volume = 0, porosity = 0, soil_density = 0;
   int flags = 0;
 };
@@ -222,6 +251,7 @@ void init_auxvar(const Tables &t, AuxVar &a) {
   a.ionx_ref_sorbed.assign(t.nionx, 1e-9); a.ionx_conc.assign((size_t)t.nionx * std::max(t.ionx_ld, 1), 0);
   a.mnrl_volfrac.assign(t.kin.n, 0); a.mnrl_area.assign(t.kin.n, 0); a.mnrl_rate.assign(t.kin.n, 0);
   a.kinsrfcplx_conc.assign(t.nkinsrf(), 0); a.kinsrfcplx_conc_kp1.assign(t.nkinsrf(), 0); a.kinsrfcplx_free_site_conc.assign(t.nkinrxn, 0);
+  a.immobile.assign(t.nim, 0);
 }
 
 // ---------------------------------------------------------------- utility.F90:393-476
@@ -711,6 +741,7 @@ void RTAccumulation(const Tables &t, const AuxVar &a, double *Res) {
   double psv_t = a.porosity * a.sat * 1000.0 * a.volume;
   for (int i = 0; i < t.ncomp; ++i) Res[i] = 0.0;
   for (int i = 0; i < t.naq; ++i) Res[i] = psv_t * a.total[i];
+  for (int iimob = 0; iimob < t.nim; ++iimob) Res[t.naq + iimob] = Res[t.naq + iimob] + a.immobile[iimob] * a.volume;   // :5117-5125
 }
 // ---------------------------------------------------------------- reaction.F90:5152-5232
 void RTAccumulationDerivative(const Tables &t, const AuxVar &a, double tran_dt, double *J) {
@@ -719,6 +750,7 @@ void RTAccumulationDerivative(const Tables &t, const AuxVar &a, double tran_dt, 
   double psvd_t = a.porosity * a.sat * 1000.0 * a.volume / tran_dt;
   for (int j = 0; j < naq; ++j)
     for (int i = 0; i < naq; ++i) J[i + (size_t)j * n] = a.dtotal[i + (size_t)j * naq] * psvd_t;
+  for (int iimob = 0; iimob < t.nim; ++iimob) J[(naq + iimob) + (size_t)(naq + iimob) * n] = a.volume / tran_dt;        // :5201-5206
 }
 // ---------------------------------------------------------------- reaction.F90:4539-4568
 void RAccumulationSorb(const Tables &t, const AuxVar &a, double *Res) {
@@ -1071,6 +1103,116 @@ void RGeneral(const Tables &t, AuxVar &a, double *Res, double *Jac, bool compute
   }
 }
 
+// ---------------------------------------------------------------- reaction_microbial.F90:236-450
+void RMicrobial(const Tables &t, AuxVar &a, double *Res, double *Jac, bool compute_derivative) {
+  const int n = t.ncomp, naq = t.naq;
+  const double PI = 3.14159265359;               // pflotran_constants.F90:55 (truncated on purpose, as LOG_TO_LN)
+  double monod[10], inhibition[10];
+  for (int irxn = 0; irxn < t.nmic; ++irxn) {
+    const int ncomp = (int)t.mic_id[irxn].size();
+    double rate_constant = t.mic_k[irxn];
+    double Im = rate_constant;
+    if (t.mic_has_Ea)
+      Im = Im * std::exp(t.mic_Ea[irxn] / IDEAL_GAS_CONSTANT * (1.0 / 298.15 - 1.0 / (a.temp + 273.15)));
+    double yield = 0.0, biomass_conc = 0.0;
+    const std::vector<int> &mon = t.mic_monod[irxn], &inh = t.mic_inhib[irxn];
+    for (size_t ii = 0; ii < mon.size(); ++ii) {
+      const int imonod = mon[ii], icomp = t.monod_spec[imonod];
+      const double activity = a.pri_molal[icomp] * a.pri_act_coef[icomp];
+      monod[ii] = (activity - t.monod_Cth[imonod]) / (t.monod_K[imonod] + activity - t.monod_Cth[imonod]);
+      Im = Im * monod[ii];
+    }
+    for (size_t ii = 0; ii < inh.size(); ++ii) {
+      const int iinhibition = inh[ii], icomp = t.inhib_spec[iinhibition];
+      const double activity = a.pri_molal[icomp] * a.pri_act_coef[icomp];
+      switch (t.inhib_type[iinhibition]) {
+        case RXN_INHIBITION_MONOD: inhibition[ii] = t.inhib_C[iinhibition] / (t.inhib_C[iinhibition] + activity); break;
+        case RXN_INHIBITION_INVERSE_MONOD: inhibition[ii] = activity / (t.inhib_C[iinhibition] + activity); break;
+        case RXN_INHIBITION_THRESHOLD:
+          inhibition[ii] = 0.5 + std::atan((activity - t.inhib_C[iinhibition]) * t.inhib_C2[iinhibition]) / PI;
+          break;
+        default: inhibition[ii] = 0.0;   // the reference's select has no default (a stale value): such tables are rejected at create time
+      }
+      Im = Im * inhibition[ii];
+    }
+    const int ibiomass = t.mic_biomass[irxn];
+    int immobile_id = -1;
+    if (ibiomass >= 0) {
+      immobile_id = naq + ibiomass;
+      biomass_conc = a.immobile[ibiomass];
+      yield = t.mic_yield[irxn];
+      Im = Im * biomass_conc;
+    }
+    const double por_sat_vol = a.porosity * a.sat * a.volume;
+    Im = Im * 1.0e3 * por_sat_vol;
+    for (int i = 0; i < ncomp; ++i) { const int icomp = t.mic_id[irxn][i]; Res[icomp] = Res[icomp] - t.mic_st[irxn][i] * Im; }
+    if (ibiomass >= 0) Res[immobile_id] = Res[immobile_id] - yield * Im;
+    if (!compute_derivative) continue;
+    for (size_t ii = 0; ii < mon.size(); ++ii) {
+      const int imonod = mon[ii], jcomp = t.monod_spec[imonod];
+      const double act_coef = a.pri_act_coef[jcomp], activity = a.pri_molal[jcomp] * act_coef;
+      const double dR_dX = Im / monod[ii];
+      const double denominator = t.monod_K[imonod] + activity - t.monod_Cth[imonod];
+      const double dX_dc = act_coef / denominator - act_coef * (activity - t.monod_Cth[imonod]) / (denominator * denominator);
+      const double dR_dc = -1.0 * dR_dX * dX_dc;
+      for (int i = 0; i < ncomp; ++i) {
+        const int icomp = t.mic_id[irxn][i];
+        Jac[icomp + (size_t)jcomp * n] = Jac[icomp + (size_t)jcomp * n] + t.mic_st[irxn][i] * dR_dc;
+      }
+      if (ibiomass >= 0) Jac[immobile_id + (size_t)jcomp * n] = Jac[immobile_id + (size_t)jcomp * n] + yield * dR_dc;
+    }
+    for (size_t ii = 0; ii < inh.size(); ++ii) {
+      const int iinhibition = inh[ii], jcomp = t.inhib_spec[iinhibition];
+      const double act_coef = a.pri_act_coef[jcomp], activity = a.pri_molal[jcomp] * act_coef;
+      const double dR_dX = Im / inhibition[ii];
+      double dX_dc = 0.0;
+      switch (t.inhib_type[iinhibition]) {
+        case RXN_INHIBITION_MONOD: {
+          const double denominator = t.inhib_C[iinhibition] + activity;
+          dX_dc = -1.0 * act_coef * t.inhib_C[iinhibition] / (denominator * denominator);
+        } break;
+        case RXN_INHIBITION_INVERSE_MONOD: {
+          const double denominator = t.inhib_C[iinhibition] + activity;
+          dX_dc = act_coef / denominator - act_coef * activity / (denominator * denominator);
+        } break;
+        case RXN_INHIBITION_THRESHOLD: {
+          const double tempreal = (activity - t.inhib_C[iinhibition]) * t.inhib_C2[iinhibition];
+          dX_dc = (t.inhib_C2[iinhibition] * act_coef / (1.0 + tempreal * tempreal)) / PI;
+        } break;
+      }
+      const double dR_dc = -1.0 * dR_dX * dX_dc;
+      for (int i = 0; i < ncomp; ++i) {
+        const int icomp = t.mic_id[irxn][i];
+        Jac[icomp + (size_t)jcomp * n] = Jac[icomp + (size_t)jcomp * n] + t.mic_st[irxn][i] * dR_dc;
+      }
+      if (ibiomass >= 0) Jac[immobile_id + (size_t)jcomp * n] = Jac[immobile_id + (size_t)jcomp * n] + yield * dR_dc;
+    }
+    if (ibiomass >= 0) {
+      const double dR_dbiomass = -1.0 * Im / biomass_conc;
+      for (int i = 0; i < ncomp; ++i) {
+        const int icomp = t.mic_id[irxn][i];
+        Jac[icomp + (size_t)immobile_id * n] = Jac[icomp + (size_t)immobile_id * n] + t.mic_st[irxn][i] * dR_dbiomass;
+      }
+      Jac[immobile_id + (size_t)immobile_id * n] = Jac[immobile_id + (size_t)immobile_id * n] + yield * dR_dbiomass;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- reaction_immobile.F90:240-293
+void RImmobileDecay(const Tables &t, AuxVar &a, double *Res, double *Jac, bool compute_derivative) {
+  const int n = t.ncomp;
+  const double volume = a.volume;
+  for (int irxn = 0; irxn < t.nimdecay; ++irxn) {
+    const int icomp = t.imdec_id[irxn];
+    const double rate_constant = t.imdec_k[irxn] * volume;
+    const double rate = rate_constant * a.immobile[icomp];
+    const int immobile_id = t.naq + icomp;
+    Res[immobile_id] = Res[immobile_id] + rate;
+    if (!compute_derivative) continue;
+    Jac[immobile_id + (size_t)immobile_id * n] = Jac[immobile_id + (size_t)immobile_id * n] + rate_constant;
+  }
+}
+
 // ---------------------------------------------------------------- reaction.F90:3515-3584
 void RReaction(const Tables &t, AuxVar &a, double tran_dt, double *Res, double *Jac, bool derivative) {
   if (t.kin.n > 0) RKineticMineral(t, a, Res, Jac, derivative);
@@ -1078,6 +1220,8 @@ void RReaction(const Tables &t, AuxVar &a, double tran_dt, double *Res, double *
   if (t.nkinrxn > 0) RKineticSurfCplx(t, a, tran_dt, Res, Jac, derivative);
   if (t.ndecay > 0) RRadioactiveDecay(t, a, Res, Jac, derivative);
   if (t.ngen > 0) RGeneral(t, a, Res, Jac, derivative);
+  if (t.nmic > 0) RMicrobial(t, a, Res, Jac, derivative);
+  if (t.nimdecay > 0) RImmobileDecay(t, a, Res, Jac, derivative);
 }
 
 // ---------------------------------------------------------------- reaction.F90:3322-3511
@@ -1088,6 +1232,7 @@ int RReact(Tables &t, AuxVar &a, double *tran_xx, double tran_dt, int dt_mode, i
   int num_iterations = 0;
   *exit_reason = 0;
   for (int i = 0; i < naq; ++i) a.total[i] = tran_xx[i];
+  for (int i = 0; i < t.nim; ++i) a.immobile[i] = tran_xx[naq + i];                        // :3386-3392
   RUpdateTempDependentCoefs(t, a);
   RTAccumulation(t, a, fixed_accum.data());
   if (t.neqsorb() > 0) RAccumulationSorb(t, a, fixed_accum.data());
@@ -1111,8 +1256,12 @@ int RReact(Tables &t, AuxVar &a, double *tran_xx, double tran_dt, int dt_mode, i
     for (int i = 0; i < n; ++i) { mx = std::max(mx, std::fabs(residual[i])); if (!std::isfinite(residual[i])) nonfinite = true; }
     if (nonfinite) { a.flags |= RXN_FLAG_NONFINITE; break; }
     if (mx < t.res_tol) { *exit_reason = RXN_EXIT_RESIDUAL; break; }
-    if (RSolve(residual.data(), J.data(), a.pri_molal.data(), update.data(), n, t.use_log)) { a.flags |= RXN_FLAG_LU_ZERO_ROW; break; }
     for (int i = 0; i < naq; ++i) prev_solution[i] = a.pri_molal[i];
+    for (int i = 0; i < t.nim; ++i) prev_solution[naq + i] = a.immobile[i];                // :3448-3452
+    // DEVIATION (immobile species + LOG_FORMULATION only): the reference passes rt_auxvar%pri_molal (naqcomp values) as RSolve's
+    // conc(ncomp) (:3445), so the immobile columns are scaled by whatever lies behind that array; the immobile concentration -
+    // what the log formulation means - is used here (prev_solution is [pri_molal, immobile]).
+    if (RSolve(residual.data(), J.data(), prev_solution.data(), update.data(), n, t.use_log)) { a.flags |= RXN_FLAG_LU_ZERO_ROW; break; }
     if (t.use_log) {
       for (int i = 0; i < n; ++i) update[i] = std::copysign(1.0, update[i]) * std::min(std::fabs(update[i]), t.max_dlnC);
       for (int i = 0; i < n; ++i) new_solution[i] = prev_solution[i] * std::exp(-update[i]);
@@ -1139,10 +1288,14 @@ int RReact(Tables &t, AuxVar &a, double *tran_xx, double tran_dt, int dt_mode, i
       for (int i = 0; i < n; ++i) new_solution[i] = scale * (new_solution[i] - prev_solution[i]) + prev_solution[i];
     }
     for (int i = 0; i < naq; ++i) a.pri_molal[i] = new_solution[i];
+    for (int i = 0; i < t.nim; ++i) a.immobile[i] = new_solution[naq + i];                 // :3499-3502
     if (num_iterations >= maxit) { a.flags |= RXN_FLAG_CAPPED; break; }  // oracle/GPU-only guard
   }
   RTAuxVarCompute(t, a);
   for (int i = 0; i < naq; ++i) tran_xx[i] = a.pri_molal[i];  // reactive_transport.F90:1711
+  // :1712-1716 writes the immobile values at tran_xx_p(offset_immobile : ...) without the cell's offset (a reference bug,
+  // SURVEY 8a quirks); the cell's own slots are written here
+  for (int i = 0; i < t.nim; ++i) tran_xx[naq + i] = a.immobile[i];
   return num_iterations;
 }
 
@@ -1385,6 +1538,7 @@ void gather(const Tables &t, const View &v, int64_t c, AuxVar &a) {
   g(RXN_F_DTOTAL, a.dtotal); g(RXN_F_DTOTAL_SORB_EQ, a.dtotal_sorb_eq);
   g(RXN_F_KINSRFCPLX_CONC, a.kinsrfcplx_conc); g(RXN_F_KINSRFCPLX_CONC_KP1, a.kinsrfcplx_conc_kp1);
   g(RXN_F_KINSRFCPLX_FREE_SITE_CONC, a.kinsrfcplx_free_site_conc);
+  g(RXN_F_IMMOBILE, a.immobile);
   (void)naq;
   a.flags = 0;
 }
@@ -1404,6 +1558,7 @@ void scatter(const Tables &t, const View &v, int64_t c, const AuxVar &a) {
   s(RXN_F_DTOTAL, a.dtotal); s(RXN_F_DTOTAL_SORB_EQ, a.dtotal_sorb_eq);
   s(RXN_F_KINSRFCPLX_CONC, a.kinsrfcplx_conc); s(RXN_F_KINSRFCPLX_CONC_KP1, a.kinsrfcplx_conc_kp1);
   s(RXN_F_KINSRFCPLX_FREE_SITE_CONC, a.kinsrfcplx_free_site_conc);
+  s(RXN_F_IMMOBILE, a.immobile);
 }
 
 template <class F> void parallel_cells(int64_t n, int nthreads, F body) {
@@ -1456,6 +1611,7 @@ int orc_update_auxvars_batch(void *h, const View *v, const double *xx_loc, const
       if (active && !active[c]) continue;
       gather(t, *v, c, a);
       if (xx_loc) for (int i = 0; i < t.naq; ++i) a.pri_molal[i] = xx_loc[c * t.ncomp + i];
+      if (xx_loc) for (int i = 0; i < t.nim; ++i) a.immobile[i] = xx_loc[c * t.ncomp + t.naq + i];   // :3801-3805
       RUpdateTempDependentCoefs(t, a);
       if (update_act_coefs) RActivityCoefficients(t, a);
       RTAuxVarCompute(t, a);
@@ -1475,6 +1631,7 @@ int orc_fixed_accum_batch(void *h, const View *v, const double *xx, const uint8_
       if (active && !active[c]) continue;
       gather(t, *v, c, a);
       if (xx) for (int i = 0; i < t.naq; ++i) a.pri_molal[i] = xx[c * t.ncomp + i];
+      if (xx) for (int i = 0; i < t.nim; ++i) a.immobile[i] = xx[c * t.ncomp + t.naq + i];           // :809-813
       RUpdateTempDependentCoefs(t, a);
       RTAuxVarCompute(t, a);
       RTAccumulation(t, a, accum_out + c * t.ncomp);

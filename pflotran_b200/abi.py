@@ -30,6 +30,7 @@ FIELDS = [
     'DEN_KG', 'SAT', 'TEMP', 'PRES', 'VOLUME', 'POROSITY', 'SOIL_PARTICLE_DENSITY',
     'DTOTAL', 'DTOTAL_SORB_EQ',
     'KINSRFCPLX_CONC', 'KINSRFCPLX_CONC_KP1', 'KINSRFCPLX_FREE_SITE_CONC',
+    'IMMOBILE',
 ]
 F = {name: i for i, name in enumerate(FIELDS)}
 RXN_F_COUNT = len(FIELDS)
@@ -96,6 +97,16 @@ class RxnTablesDesc(C.Structure):
         ('kinsrfcplxrxn_to_srfcplxrxn', c_i32p), ('kinsrfcplx_forward_rate', c_f64p),
         ('kinsrfcplx_backward_rate', c_f64p),
         ('kinsrfcplx_ld', C.c_int32), ('reserved2', C.c_int32),
+        ('immobile_decayspecid', c_i32p), ('immobile_decay_rate_constant', c_f64p),
+        ('microbial_ld', C.c_int32), ('microbial_monod_ld', C.c_int32), ('microbial_inhibition_ld', C.c_int32),
+        ('nmicrobial_monod', C.c_int32), ('nmicrobial_inhibition', C.c_int32), ('reserved3', C.c_int32),
+        ('microbial_specid', c_i32p), ('microbial_stoich', c_f64p),
+        ('microbial_rate_constant', c_f64p), ('microbial_activation_energy', c_f64p),
+        ('microbial_biomassid', c_i32p), ('microbial_biomass_yield', c_f64p),
+        ('microbial_monodid', c_i32p), ('microbial_inhibitionid', c_i32p),
+        ('microbial_monod_specid', c_i32p), ('microbial_monod_K', c_f64p), ('microbial_monod_Cth', c_f64p),
+        ('microbial_inhibition_type', c_i32p), ('microbial_inhibition_specid', c_i32p),
+        ('microbial_inhibition_C', c_f64p), ('microbial_inhibition_C2', c_f64p),
     ]
 
 
@@ -201,7 +212,26 @@ def make_desc(t) -> RxnTablesDesc:
     d.eqkdfreundlichn = D(t.eqkdfreundlichn)
     uns = getattr(t, 'unsupported', [])
     d.nactive_gas = int(any('ACTIVE_GAS' in u for u in uns))
-    d.nimmobile = int(any('IMMOBILE_SPECIES' in u for u in uns))
+    # immobile species, their decay and microbial reactions (fixtures older than this feature have none)
+    d.nimmobile = int(getattr(t, 'nimmobile', 0))
+    d.nimmobile_decay_rxn = int(getattr(t, 'nimmobile_decay_rxn', 0))
+    d.nmicrobial_rxn = int(getattr(t, 'nmicrobial_rxn', 0))
+    if d.nimmobile_decay_rxn:
+        d.immobile_decayspecid = I(t.immobile_decayspecid); d.immobile_decay_rate_constant = D(t.immobile_decay_rate_constant)
+    if d.nmicrobial_rxn:
+        d.microbial_ld = t.microbial_stoich.shape[1]
+        d.microbial_monod_ld = t.microbial_monodid.shape[1] - 1
+        d.microbial_inhibition_ld = t.microbial_inhibitionid.shape[1] - 1
+        d.nmicrobial_monod = t.microbial_monod_specid.size; d.nmicrobial_inhibition = t.microbial_inhibition_specid.size
+        d.microbial_specid = I(t.microbial_specid); d.microbial_stoich = D(t.microbial_stoich)
+        d.microbial_rate_constant = D(t.microbial_rate_constant)
+        d.microbial_activation_energy = D(t.microbial_activation_energy) if t.has_microbial_activation_energy else c_f64p()
+        d.microbial_biomassid = I(t.microbial_biomassid); d.microbial_biomass_yield = D(t.microbial_biomass_yield)
+        d.microbial_monodid = I(t.microbial_monodid); d.microbial_inhibitionid = I(t.microbial_inhibitionid)
+        d.microbial_monod_specid = I(t.microbial_monod_specid); d.microbial_monod_K = D(t.microbial_monod_K)
+        d.microbial_monod_Cth = D(t.microbial_monod_Cth)
+        d.microbial_inhibition_type = I(t.microbial_inhibition_type); d.microbial_inhibition_specid = I(t.microbial_inhibition_specid)
+        d.microbial_inhibition_C = D(t.microbial_inhibition_C); d.microbial_inhibition_C2 = D(t.microbial_inhibition_C2)
     d.ncoll = int(any('COLLOID' in u for u in uns))
     # general reactions / radioactive decay / kinetic surface complexation (fixtures older than round 2 have none)
     d.ngeneral_rxn = int(getattr(t, 'ngeneral_rxn', 0))
@@ -221,8 +251,6 @@ def make_desc(t) -> RxnTablesDesc:
         d.kinsrfcplxrxn_to_srfcplxrxn = I(t.kinsrfcplxrxn_to_srfcplxrxn)
         d.kinsrfcplx_forward_rate = D(t.kinsrfcplx_forward_rate)
         d.kinsrfcplx_backward_rate = D(t.kinsrfcplx_backward_rate)
-    d.nmicrobial_rxn = int(any('MICROBIAL' in u for u in uns))
-    d.nimmobile_decay_rxn = int(any('IMMOBILE_DECAY' in u for u in uns))
     d.has_sandbox = int(any('SANDBOX' in u for u in uns))
     d.has_clm = int(any('CLM' in u for u in uns))
     d.has_solid_solution = int(any('SOLID_SOLUTION' in u for u in uns))
@@ -245,6 +273,7 @@ def field_rows(t) -> Dict[str, int]:
         'SOIL_PARTICLE_DENSITY': 1, 'DTOTAL': naq * naq, 'DTOTAL_SORB_EQ': naq * naq,
         'KINSRFCPLX_CONC': getattr(t, 'nkinsrfcplx', 0), 'KINSRFCPLX_CONC_KP1': getattr(t, 'nkinsrfcplx', 0),
         'KINSRFCPLX_FREE_SITE_CONC': t.nkinsrfcplxrxn,
+        'IMMOBILE': getattr(t, 'nimmobile', 0),
     }
 
 

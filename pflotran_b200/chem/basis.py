@@ -626,11 +626,13 @@ def build_tables(deck: dk.Deck, database_path: str = None, isothermal: bool = Tr
                 v = -v
             if not right:
                 v = -v
-            if w not in chem.primary_species:
+            if w not in chem.primary_species and w not in chem.immobile_species:
                 raise RuntimeError('Species %s in reaction "%s" not found among primary species' % (w, text))
             names.append(w); st.append(v)
             value, negative = None, False
-        return [chem.primary_species.index(n) + 1 for n in names], st
+        # immobile species are dofs naqcomp + i (offset_immobile = naqcomp, reaction.F90:105-106)
+        return [chem.primary_species.index(n) + 1 if n in chem.primary_species else naq + chem.immobile_species.index(n) + 1
+                for n in names], st
 
     def fnum_py(tok):
         return float(tok.replace('d', 'e').replace('D', 'e'))
@@ -663,6 +665,59 @@ def build_tables(deck: dk.Deck, database_path: str = None, isothermal: bool = Tr
     t.eqkdmineral = np.array(
         [kin.index(r.kd_mineral_name) + 1 if len(r.kd_mineral_name) > 1 else 0
          for r in chem.kd_rxns], dtype=np.int32)
+
+    # --- immobile species, immobile decay (reaction_database.F90:3336-3370) and microbial reactions (:3126-3333)
+    t.nimmobile = len(chem.immobile_species)
+    t.immobile_names = list(chem.immobile_species)
+    t.ncomp = naq + t.nimmobile
+    t.nimmobile_decay_rxn = len(chem.immobile_decay_rxns)
+    for name, _ in chem.immobile_decay_rxns:
+        if name not in chem.immobile_species:
+            raise RuntimeError('Species "%s" in immobile decay reaction not found among immobile species.' % name)
+    t.immobile_decayspecid = np.array([chem.immobile_species.index(n) + 1 for n, _ in chem.immobile_decay_rxns], dtype=np.int32)
+    t.immobile_decay_rate_constant = np.array([k for _, k in chem.immobile_decay_rxns], dtype=np.float64)
+    t.nmicrobial_rxn = len(chem.microbial_rxns)
+    m_ids, m_st, m_mon, m_inh, bio, yld = [], [], [], [], [], []
+    mon_spec, mon_K, mon_Cth, inh_type, inh_spec, inh_C, inh_C2 = [], [], [], [], [], [], []
+    for r in chem.microbial_rxns:
+        ids, st = rxn_from_string(r.reaction)
+        names = [(chem.primary_species + chem.immobile_species)[i - 1] for i in ids]
+        m_ids.append(ids); m_st.append(st)
+        if r.biomass is not None:
+            if r.biomass[0] not in chem.immobile_species:
+                raise RuntimeError('Biomass species "%s" not found among immobile species.' % r.biomass[0])
+            if r.biomass[0] in names:
+                raise RuntimeError('Biomass species "%s" should not be included in microbial reaction.' % r.biomass[0])
+            bio.append(chem.immobile_species.index(r.biomass[0]) + 1); yld.append(r.biomass[1])
+        else:
+            bio.append(0); yld.append(0.0)
+        row = []
+        for (name, K, Cth) in r.monod:
+            if name not in names:
+                raise RuntimeError('Monod species "%s" not found in microbial reaction.' % name)
+            if st[names.index(name)] > 0.0:
+                raise RuntimeError('Monod species "%s" must be a reactant and not a product in microbial reaction.' % name)
+            mon_spec.append(chem.primary_species.index(name) + 1); mon_K.append(K); mon_Cth.append(Cth)
+            row.append(len(mon_spec))
+        m_mon.append(row)
+        row = []
+        for (name, itype, Cc, C2) in r.inhibition:
+            inh_spec.append(chem.primary_species.index(name) + 1); inh_type.append(itype); inh_C.append(Cc); inh_C2.append(C2)
+            row.append(len(inh_spec))
+        m_inh.append(row)
+    mm = max([len(x) for x in m_ids], default=0)
+    t.microbial_specid = idarray(m_ids, mm + 1); t.microbial_stoich = starray1(m_st, mm)
+    t.microbial_rate_constant = np.array([r.rate_constant for r in chem.microbial_rxns], dtype=np.float64)
+    # allocated only when some reaction sets a positive activation energy (reaction_database.F90:3146-3148, 3168-3171)
+    t.has_microbial_activation_energy = int(any(r.activation_energy > 0.0 for r in chem.microbial_rxns))
+    t.microbial_activation_energy = np.array([r.activation_energy for r in chem.microbial_rxns], dtype=np.float64)
+    t.microbial_biomassid = np.array(bio, dtype=np.int32); t.microbial_biomass_yield = np.array(yld, dtype=np.float64)
+    t.microbial_monodid = idarray(m_mon, max([len(x) for x in m_mon], default=0) + 1)
+    t.microbial_inhibitionid = idarray(m_inh, max([len(x) for x in m_inh], default=0) + 1)
+    t.microbial_monod_specid = np.array(mon_spec, dtype=np.int32)
+    t.microbial_monod_K = np.array(mon_K, dtype=np.float64); t.microbial_monod_Cth = np.array(mon_Cth, dtype=np.float64)
+    t.microbial_inhibition_type = np.array(inh_type, dtype=np.int32); t.microbial_inhibition_specid = np.array(inh_spec, dtype=np.int32)
+    t.microbial_inhibition_C = np.array(inh_C, dtype=np.float64); t.microbial_inhibition_C2 = np.array(inh_C2, dtype=np.float64)
 
     t.neqsorb = nix + nkd + t.neqsrfcplxrxn
     t.nsorb = t.neqsorb + t.nkinmrsrfcplxrxn + t.nkinsrfcplxrxn

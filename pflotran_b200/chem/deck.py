@@ -200,6 +200,20 @@ class RateRxn:
 
 
 @dataclass
+class MicrobialRxn:
+    """MICROBIAL_REACTION block (reaction_microbial.F90:30-233).  monod: (species, K, Cth); inhibition: (species, type, C, C2)"""
+    reaction: str = ''
+    rate_constant: float = 0.0
+    activation_energy: float = 0.0
+    monod: List[tuple] = field(default_factory=list)
+    inhibition: List[tuple] = field(default_factory=list)
+    biomass: Optional[tuple] = None            # (species name, yield)
+
+
+INHIBITION_THRESHOLD, INHIBITION_THERMODYNAMIC, INHIBITION_MONOD, INHIBITION_INVERSE_MONOD = 1, 2, 3, 4   # reaction_microbial_aux.F90:13-16
+
+
+@dataclass
 class Chemistry:
     primary_species: List[str] = field(default_factory=list)
     secondary_species: List[str] = field(default_factory=list)
@@ -213,6 +227,9 @@ class Chemistry:
     kd_rxns: List[KDRxn] = field(default_factory=list)
     general_rxns: List[RateRxn] = field(default_factory=list)
     radiodecay_rxns: List[RateRxn] = field(default_factory=list)
+    immobile_species: List[str] = field(default_factory=list)
+    immobile_decay_rxns: List[tuple] = field(default_factory=list)     # (species name, rate constant 1/s)
+    microbial_rxns: List[MicrobialRxn] = field(default_factory=list)
     database: str = ''
     use_log_formulation: bool = False
     use_geothermal_hpt: bool = False
@@ -237,6 +254,7 @@ class Constraint:
     aux: List[str] = field(default_factory=list)
     free_ion_guess: Optional[Dict[str, float]] = None
     minerals: Dict[str, tuple] = field(default_factory=dict)  # name -> (volfrac, area m^2/m^3)
+    immobile: Dict[str, float] = field(default_factory=dict)  # name -> concentration [mol/m^3 bulk]
 
 
 @dataclass
@@ -547,8 +565,93 @@ def _read_chemistry(rd: LineReader) -> Chemistry:
             if r.rate_constant is None:
                 raise DeckError('RATE_CONSTANT or HALF_LIFE must be set in RADIOACTIVE_DECAY_REACTION.')
             chem.radiodecay_rxns.append(r)
-        elif kw in ('MICROBIAL_REACTION',
-                    'IMMOBILE_SPECIES', 'IMMOBILE_DECAY_REACTION', 'COLLOIDS',
+        elif kw == 'IMMOBILE_SPECIES':                      # reaction_immobile.F90:30-77
+            for t in rd.block():
+                chem.immobile_species.append(t[0])
+        elif kw == 'IMMOBILE_DECAY_REACTION':               # reaction_immobile.F90:81-160
+            name, k = '', None
+            for t in rd.block():
+                key = t[0].upper()
+                if key == 'SPECIES_NAME':
+                    name = t[1]
+                elif key == 'RATE_CONSTANT':
+                    k = fnum(t[1])
+                    if len(t) > 2 and t[2][0] not in '!#':
+                        k = k * units_convert_to_internal(t[2], '1/sec')
+                elif key == 'HALF_LIFE':
+                    hl = fnum(t[1])
+                    if len(t) > 2 and t[2][0] not in '!#':
+                        hl = hl * units_convert_to_internal(t[2], 'sec')
+                    k = -1.0 * math.log(0.5) / hl
+                else:
+                    raise DeckError('IMMOBILE_DECAY_REACTION keyword ' + key)
+            if k is None:
+                raise DeckError('RATE_CONSTANT or HALF_LIFE must be set in IMMOBILE_DECAY_REACTION.')
+            chem.immobile_decay_rxns.append((name, k))
+        elif kw == 'MICROBIAL_REACTION':                    # reaction_microbial.F90:30-233
+            r = MicrobialRxn()
+            for t in rd.block():
+                key = t[0].upper()
+                if key == 'REACTION':
+                    r.reaction = ' '.join(t[1:])
+                elif key == 'RATE_CONSTANT':
+                    r.rate_constant = fnum(t[1])
+                elif key == 'ACTIVATION_ENERGY':
+                    r.activation_energy = fnum(t[1])
+                    if len(t) > 2 and t[2][0] not in '!#':
+                        r.activation_energy = r.activation_energy * units_convert_to_internal(t[2], 'J/mol')
+                elif key == 'MONOD':
+                    name, K, Cth = '', 0.0, 0.0
+                    for u in rd.block():
+                        k2 = u[0].upper()
+                        if k2 == 'SPECIES_NAME':
+                            name = u[1]
+                        elif k2 == 'HALF_SATURATION_CONSTANT':
+                            K = fnum(u[1])
+                        elif k2 == 'THRESHOLD_CONCENTRATION':
+                            Cth = fnum(u[1])
+                        else:
+                            raise DeckError('MICROBIAL_REACTION,MONOD keyword ' + k2)
+                    r.monod.append((name, K, Cth))
+                elif key == 'INHIBITION':
+                    name, itype, Cc, C2 = '', 0, None, 0.0
+                    for u in rd.block():
+                        k2 = u[0].upper()
+                        if k2 == 'SPECIES_NAME':
+                            name = u[1]
+                        elif k2 == 'TYPE':
+                            w = u[1].upper()
+                            if w == 'MONOD':
+                                itype = INHIBITION_MONOD
+                            elif w == 'INVERSE_MONOD':
+                                itype = INHIBITION_INVERSE_MONOD
+                            elif w == 'THRESHOLD':
+                                itype = INHIBITION_THRESHOLD
+                                C2 = fnum(u[2])
+                            else:
+                                raise DeckError('MICROBIAL_REACTION,INHIBITION,TYPE ' + w)
+                        elif k2 == 'INHIBITION_CONSTANT':
+                            Cc = fnum(u[1])
+                        else:
+                            raise DeckError('MICROBIAL_REACTION,INHIBITION keyword ' + k2)
+                    if len(name) < 2 or itype == 0 or Cc is None:
+                        raise DeckError('A SPECIES_NAME, TYPE, and INHIBITION_CONSTANT must be defined for INHIBITION in MICROBIAL_REACTION')
+                    r.inhibition.append((name, itype, Cc, C2))
+                elif key == 'BIOMASS':
+                    name, y = '', 0.0
+                    for u in rd.block():
+                        k2 = u[0].upper()
+                        if k2 == 'SPECIES_NAME':
+                            name = u[1]
+                        elif k2 == 'YIELD':
+                            y = fnum(u[1])
+                        else:
+                            raise DeckError('MICROBIAL_REACTION,BIOMASS keyword ' + k2)
+                    r.biomass = (name, y)
+                else:
+                    raise DeckError('MICROBIAL_REACTION keyword ' + key)
+            chem.microbial_rxns.append(r)
+        elif kw in ('COLLOIDS',
                     'REACTION_SANDBOX', 'CLM_REACTION', 'SOLID_SOLUTIONS'):
             chem.unsupported.append(kw)
             rd.skip_block()
@@ -604,7 +707,10 @@ def _read_constraint(rd: LineReader, name: str) -> Constraint:
                 if len(t) > 3 and t[3][0] not in '!#':
                     area = area * units_convert_to_internal(t[3], 'm^2/m^3')
                 c.minerals[t[0]] = (vf, area)
-        elif kw in ('SURFACE_COMPLEXES', 'COLLOIDS', 'IMMOBILE'):
+        elif kw == 'IMMOBILE':                              # transport_constraint.F90 (IMMOBILE block: name, concentration)
+            for t in rd.block():
+                c.immobile[t[0]] = fnum(t[1])
+        elif kw in ('SURFACE_COMPLEXES', 'COLLOIDS'):
             rd.skip_block()
         else:
             raise DeckError('CONSTRAINT keyword ' + kw)

@@ -30,6 +30,8 @@ _INT_FIELDS = {
     'paseqspecid', 'paseqh2oid',
     'generalspecid', 'generalforwardspecid', 'generalbackwardspecid', 'radiodecayspecid', 'radiodecayforwardspecid',
     'kinsrfcplxrxn_to_srfcplxrxn',
+    'immobile_decayspecid', 'microbial_specid', 'microbial_biomassid', 'microbial_monodid', 'microbial_inhibitionid',
+    'microbial_monod_specid', 'microbial_inhibition_type', 'microbial_inhibition_specid',
 }
 
 

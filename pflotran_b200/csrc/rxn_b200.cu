@@ -245,7 +245,7 @@ int rxn_tables_create(const RxnTablesDesc *d, int device, RxnTables **out) {
     return fail(RXN_ERR_UNSUPPORTED, "chemistry tables (%zu bytes) exceed the shared-memory staging budget", nb);
   }
   std::vector<unsigned char> blob = blob_bytes(R);
-  t->nvariant = variant_for(h.naq);
+  t->nvariant = variant_for(h.ncomp);
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -502,7 +502,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
   if (nlocal == 0) return RXN_OK;
   { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
   CU(cudaSetDevice(s->t->device));
-  const int n = s->t->h.naq;
+  const int n = s->t->h.ncomp;
   void *d_xx, *d_l2g = nullptr, *d_it, *d_fl;
   int rc;
   if ((rc = ensure_scratch(s, 0, (size_t)nlocal * n * 8, &d_xx)) != RXN_OK) return rc;
@@ -620,9 +620,9 @@ int rxn_update_auxvars_batch(RxnState *s, const double *xx_loc, int update_act_c
   const RxnTables *t = s->t;
   void *d_xx = nullptr;
   if (xx_loc) {
-    int rc = ensure_scratch(s, 0, (size_t)s->ncells * t->h.naq * 8, &d_xx);
+    int rc = ensure_scratch(s, 0, (size_t)s->ncells * t->h.ncomp * 8, &d_xx);
     if (rc != RXN_OK) return rc;
-    CU(cudaMemcpyAsync(d_xx, xx_loc, (size_t)s->ncells * t->h.naq * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d_xx, xx_loc, (size_t)s->ncells * t->h.ncomp * 8, cudaMemcpyHostToDevice, s->stream));
   }
   { const int rcf = begin_cell_flags(s); if (rcf != RXN_OK) return rcf; }
   CU(cudaEventRecord(s->ev0, s->stream));
@@ -638,7 +638,7 @@ int rxn_fixed_accum_batch(RxnState *s, const double *xx, const int32_t *l2g, int
   { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
-  const int n = t->h.naq;
+  const int n = t->h.ncomp;
   void *d_xx = nullptr, *d_l2g = nullptr, *d_out;
   int rc;
   if ((rc = ensure_scratch(s, 2, (size_t)nlocal * n * 8, &d_out)) != RXN_OK) return rc;
@@ -717,7 +717,7 @@ int rxn_residual_jacobian_blocks_batch(RxnState *s, const int32_t *l2g, int64_t 
   { const int rcg = check_l2g(s, l2g, nlocal); if (rcg != RXN_OK) return rcg; }
   CU(cudaSetDevice(s->t->device));
   const RxnTables *t = s->t;
-  const int n = t->h.naq;
+  const int n = t->h.ncomp;
   void *d_res = nullptr, *d_jac = nullptr, *d_l2g = nullptr;
   int rc;
   if (res_out) { if ((rc = ensure_scratch(s, 2, (size_t)nlocal * n * 8, &d_res)) != RXN_OK) return rc; CU(cudaMemsetAsync(d_res, 0, (size_t)nlocal * n * 8, s->stream)); }
@@ -863,6 +863,8 @@ int rxn_connset_create(RxnState *s, int64_t nconn, const int32_t *id_up, const i
                        int64_t nlocal, const uint8_t *active, RxnConnSet **out) {
   if (!s || !out || nconn < 0 || nlocal < 0 || (nconn > 0 && (!id_up || !id_dn))) return fail(RXN_ERR_INVALID, "bad argument");
   *out = nullptr;
+  if (s->t->h.nim > 0)
+    return fail(RXN_ERR_UNSUPPORTED, "flux-side blocks are naqcomp x naqcomp: tables with immobile dofs (ncomp %d > naqcomp %d) are not handled by the flux entry points", s->t->h.ncomp, s->t->h.naq);
   CU(cudaSetDevice(s->t->device));
   RxnConnSet *c = new RxnConnSet();
   c->s = s;
@@ -1050,6 +1052,8 @@ int rxn_couplerset_create(RxnState *s, int kind, int64_t nconn, const int32_t *i
   if (!s || !out || nconn < 0 || nlocal < 0 || (nconn > 0 && !id_dn) || (kind != RXN_COUPLER_BOUNDARY && kind != RXN_COUPLER_SRC_SINK))
     return fail(RXN_ERR_INVALID, "bad argument");
   *out = nullptr;
+  if (s->t->h.nim > 0)
+    return fail(RXN_ERR_UNSUPPORTED, "flux-side blocks are naqcomp x naqcomp: tables with immobile dofs (ncomp %d > naqcomp %d) are not handled by the coupler entry points", s->t->h.ncomp, s->t->h.naq);
   CU(cudaSetDevice(s->t->device));
   RxnCouplerSet *b = new RxnCouplerSet();
   b->s = s; b->kind = kind; b->n = s->t->h.naq; b->device = s->t->device;

@@ -30,6 +30,7 @@ struct Cell {
   double tsorb[N];    // total_sorb_eq
   double ln_act_h2o, den_kg, sat, temp, pres, volume, porosity, soil_density;
   double hpt[6];      // tr, pr, log10(tr), sqrt(tr), 1/tr, 1/pr of this cell (hpt logK fit; filled by load_cell for RXN_LOGK_HPT tables)
+  double im[RXN_MAX_IMMOBILE];   // rt_auxvar%immobile [mol/m^3 bulk]: dofs naq .. ncomp-1
   long long cell;     // state index
   int flags;
 };
@@ -889,6 +890,118 @@ __device__ int rsolve(double *Res, double *Jac, const double *conc, int n, bool 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Immobile dofs (reaction%ncomp = naqcomp + nimmobile).  The routines above assemble the naq x naq aqueous block with leading
+// dimension naq; before the routines that touch immobile rows / columns run, the block is re-strided in place to ncomp x ncomp,
+// the new rows and columns zeroed.  RMicrobial and RImmobileDecay come last in RReaction's dispatch order (reaction.F90:3563-3571),
+// so every entry's terms are still summed in the reference's order.
+__device__ __forceinline__ void expand_block(double *J, int naq, int n) {
+  if (n == naq) return;
+  for (int j = n - 1; j >= 0; --j)
+    for (int i = n - 1; i >= 0; --i) J[i + j * n] = (i < naq && j < naq) ? J[i + j * naq] : 0.0;
+}
+
+// RMicrobial - reaction_microbial.F90:236-450.  Jac: ncomp x ncomp column-major.
+template <int N>
+__device__ void microbial_reaction(const Tab &T, const Cell<N> &c, double *Res, double *Jac, bool compute_derivative) {
+  const DevTab &h = *T.h;
+  const int n = h.ncomp, naq = h.naq;
+  const double PI = 3.14159265359;               // pflotran_constants.F90:55
+  double monod[RXN_MAX_MONOD], inhibition[RXN_MAX_MONOD];
+  for (int irxn = 0; irxn < h.nmic; ++irxn) {
+    const int s0 = T.i[h.o_mic_ptr + irxn], s1 = T.i[h.o_mic_ptr + irxn + 1];
+    const int m0 = T.i[h.o_mic_mptr + irxn], m1 = T.i[h.o_mic_mptr + irxn + 1];
+    const int i0 = T.i[h.o_mic_iptr + irxn], i1 = T.i[h.o_mic_iptr + irxn + 1];
+    double Im = T.d[h.o_mic_k + irxn];
+    if (h.mic_has_Ea) Im = Im * exp(T.d[h.o_mic_Ea + irxn] / RXN_IDEAL_GAS_CONSTANT * (1.0 / 298.15 - 1.0 / (c.temp + 273.15)));
+    double yield = 0.0, biomass_conc = 0.0;
+    for (int ii = m0; ii < m1; ++ii) {
+      const int imonod = T.i[h.o_mic_mid + ii], icomp = T.i[h.o_mon_spec + imonod];
+      const double activity = c.m[icomp] * c.gam[icomp], Cth = T.d[h.o_mon_Cth + imonod];
+      monod[ii - m0] = (activity - Cth) / (T.d[h.o_mon_K + imonod] + activity - Cth);
+      Im = Im * monod[ii - m0];
+    }
+    for (int ii = i0; ii < i1; ++ii) {
+      const int iinh = T.i[h.o_mic_iid + ii], icomp = T.i[h.o_inh_spec + iinh];
+      const double activity = c.m[icomp] * c.gam[icomp], C1 = T.d[h.o_inh_C + iinh];
+      double v;
+      switch (T.i[h.o_inh_type + iinh]) {
+        case RXN_INHIBITION_MONOD: v = C1 / (C1 + activity); break;
+        case RXN_INHIBITION_INVERSE_MONOD: v = activity / (C1 + activity); break;
+        default: v = 0.5 + atan((activity - C1) * T.d[h.o_inh_C2 + iinh]) / PI; break;   // RXN_INHIBITION_THRESHOLD (other types rejected)
+      }
+      inhibition[ii - i0] = v;
+      Im = Im * v;
+    }
+    const int ibiomass = T.i[h.o_mic_bio + irxn];
+    const int immobile_id = naq + ibiomass;
+    if (ibiomass >= 0) {
+      biomass_conc = c.im[ibiomass];
+      yield = T.d[h.o_mic_yield + irxn];
+      Im = Im * biomass_conc;
+    }
+    const double por_sat_vol = c.porosity * c.sat * c.volume;
+    Im = Im * 1.0e3 * por_sat_vol;
+    for (int p = s0; p < s1; ++p) Res[T.i[h.o_mic_id + p]] = Res[T.i[h.o_mic_id + p]] - T.d[h.o_mic_st + p] * Im;
+    if (ibiomass >= 0) Res[immobile_id] = Res[immobile_id] - yield * Im;
+    if (!compute_derivative) continue;
+    for (int ii = m0; ii < m1; ++ii) {
+      const int imonod = T.i[h.o_mic_mid + ii], jcomp = T.i[h.o_mon_spec + imonod];
+      const double act_coef = c.gam[jcomp], activity = c.m[jcomp] * act_coef, Cth = T.d[h.o_mon_Cth + imonod];
+      const double dR_dX = Im / monod[ii - m0];
+      const double denominator = T.d[h.o_mon_K + imonod] + activity - Cth;
+      const double dX_dc = act_coef / denominator - act_coef * (activity - Cth) / (denominator * denominator);
+      const double dR_dc = -1.0 * dR_dX * dX_dc;
+      for (int p = s0; p < s1; ++p) Jac[T.i[h.o_mic_id + p] + jcomp * n] = Jac[T.i[h.o_mic_id + p] + jcomp * n] + T.d[h.o_mic_st + p] * dR_dc;
+      if (ibiomass >= 0) Jac[immobile_id + jcomp * n] = Jac[immobile_id + jcomp * n] + yield * dR_dc;
+    }
+    for (int ii = i0; ii < i1; ++ii) {
+      const int iinh = T.i[h.o_mic_iid + ii], jcomp = T.i[h.o_inh_spec + iinh];
+      const double act_coef = c.gam[jcomp], activity = c.m[jcomp] * act_coef, C1 = T.d[h.o_inh_C + iinh];
+      const double dR_dX = Im / inhibition[ii - i0];
+      double dX_dc;
+      switch (T.i[h.o_inh_type + iinh]) {
+        case RXN_INHIBITION_MONOD: {
+          const double denominator = C1 + activity;
+          dX_dc = -1.0 * act_coef * C1 / (denominator * denominator);
+        } break;
+        case RXN_INHIBITION_INVERSE_MONOD: {
+          const double denominator = C1 + activity;
+          dX_dc = act_coef / denominator - act_coef * activity / (denominator * denominator);
+        } break;
+        default: {
+          const double C2 = T.d[h.o_inh_C2 + iinh], tempreal = (activity - C1) * C2;
+          dX_dc = (C2 * act_coef / (1.0 + tempreal * tempreal)) / PI;
+        } break;
+      }
+      const double dR_dc = -1.0 * dR_dX * dX_dc;
+      for (int p = s0; p < s1; ++p) Jac[T.i[h.o_mic_id + p] + jcomp * n] = Jac[T.i[h.o_mic_id + p] + jcomp * n] + T.d[h.o_mic_st + p] * dR_dc;
+      if (ibiomass >= 0) Jac[immobile_id + jcomp * n] = Jac[immobile_id + jcomp * n] + yield * dR_dc;
+    }
+    if (ibiomass >= 0) {
+      const double dR_dbiomass = -1.0 * Im / biomass_conc;
+      for (int p = s0; p < s1; ++p)
+        Jac[T.i[h.o_mic_id + p] + immobile_id * n] = Jac[T.i[h.o_mic_id + p] + immobile_id * n] + T.d[h.o_mic_st + p] * dR_dbiomass;
+      Jac[immobile_id + immobile_id * n] = Jac[immobile_id + immobile_id * n] + yield * dR_dbiomass;
+    }
+  }
+}
+
+// RImmobileDecay - reaction_immobile.F90:240-293
+template <int N>
+__device__ void immobile_decay(const Tab &T, const Cell<N> &c, double *Res, double *Jac, bool compute_derivative) {
+  const DevTab &h = *T.h;
+  const int n = h.ncomp;
+  for (int irxn = 0; irxn < h.nimdecay; ++irxn) {
+    const int icomp = T.i[h.o_imdec_id + irxn];
+    const double rate_constant = T.d[h.o_imdec_k + irxn] * c.volume;
+    const double rate = rate_constant * c.im[icomp];
+    const int immobile_id = h.naq + icomp;
+    Res[immobile_id] = Res[immobile_id] + rate;
+    if (compute_derivative) Jac[immobile_id + immobile_id * n] = Jac[immobile_id + immobile_id * n] + rate_constant;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // load / store of the per-thread part of the state
 template <int N>
 __device__ void load_cell(const Tab &T, const DevState &S, long long cell, Cell<N> &c) {
@@ -901,6 +1014,7 @@ __device__ void load_cell(const Tab &T, const DevState &S, long long cell, Cell<
     c.total[i] = G(S, RXN_F_TOTAL, i, cell);
     c.tsorb[i] = G(S, RXN_F_TOTAL_SORB_EQ, i, cell);
   }
+  for (int i = 0; i < T.h->nim; ++i) c.im[i] = G(S, RXN_F_IMMOBILE, i, cell);
   c.ln_act_h2o = G(S, RXN_F_LN_ACT_H2O, 0, cell);
   c.den_kg = G(S, RXN_F_DEN_KG, 0, cell);
   c.sat = G(S, RXN_F_SAT, 0, cell);
@@ -921,6 +1035,7 @@ __device__ void store_cell(const Tab &T, const DevState &S, const Cell<N> &c, co
     G(S, RXN_F_TOTAL, i, c.cell) = c.total[i];
     G(S, RXN_F_TOTAL_SORB_EQ, i, c.cell) = c.tsorb[i];
   }
+  for (int i = 0; i < T.h->nim; ++i) G(S, RXN_F_IMMOBILE, i, c.cell) = c.im[i];
   G(S, RXN_F_LN_ACT_H2O, 0, c.cell) = c.ln_act_h2o;
   if (S.f[RXN_F_DTOTAL] && dtot)
     for (int e = 0; e < naq * naq; ++e) G(S, RXN_F_DTOTAL, e, c.cell) = dtot[e];
@@ -935,17 +1050,19 @@ template <int N>
 __device__ int rreact(const Tab &T, const DevState &S, Cell<N> &c, double *tran_xx, double tran_dt, int dt_mode,
                       double *J, double *dsorb, int *exit_reason) {
   const DevTab &h = *T.h;
-  const int n = h.naq, naq = h.naq;
+  const int n = h.ncomp, naq = h.naq, nim = h.nim;       // dofs: naq aqueous species, then nim immobile species
   double residual[N], fixed_accum[N], prev_solution[N], new_solution[N];
   double mrK1[2], mrR0[2 * N];   // nmr <= 2 enforced at table creation
   double dtot[N * N];            // d total / d free-ion of the iterate (RRadioactiveDecay reads it after J has been scaled)
   int num_iterations = 0;
   *exit_reason = 0;
   for (int i = 0; i < naq; ++i) c.total[i] = tran_xx[i];                       // :3370
+  for (int i = 0; i < nim; ++i) c.im[i] = tran_xx[naq + i];                    // :3386-3392
   // fixed accumulation: RTAccumulation (:5072-5148) + RAccumulationSorb (:4539-4568)
   const double psv_t = c.porosity * c.sat * 1000.0 * c.volume;
   for (int i = 0; i < naq; ++i) fixed_accum[i] = psv_t * c.total[i];
   if (h.neqsorb > 0) for (int i = 0; i < naq; ++i) fixed_accum[i] = fixed_accum[i] + c.tsorb[i] * c.volume;
+  for (int i = 0; i < nim; ++i) fixed_accum[naq + i] = c.im[i] * c.volume;      // :5117-5125
   if (h.nmr > 0) multirate_prepare<N>(T, S, c, tran_dt, mrK1, mrR0);
   if (h.act_freq != RXN_ACT_COEF_FREQUENCY_OFF) activity_coefficients<N>(T, S, c);
   const double psvd_t = c.porosity * c.sat * 1000.0 * c.volume / tran_dt;    // :5189
@@ -956,6 +1073,7 @@ __device__ int rreact(const Tab &T, const DevState &S, Cell<N> &c, double *tran_
     auxvar_compute<N>(T, S, c, J, dsorb);                                      // J <- dtotal
     if (h.ndecay > 0) for (int e = 0; e < naq * naq; ++e) dtot[e] = J[e];
     for (int i = 0; i < naq; ++i) residual[i] = psv_t * c.total[i];
+    for (int i = 0; i < nim; ++i) residual[naq + i] = c.im[i] * c.volume;
     for (int i = 0; i < n; ++i) residual[i] = residual[i] - fixed_accum[i];
     for (int e = 0; e < naq * naq; ++e) J[e] = J[e] * psvd_t;                  // RTAccumulationDerivative
     if (h.neqsorb > 0) {
@@ -970,14 +1088,23 @@ __device__ int rreact(const Tab &T, const DevState &S, Cell<N> &c, double *tran_
     if (h.nkinrxn > 0) kinetic_surfcplx<N>(T, S, c, tran_dt, residual, J, true);
     if (h.ndecay > 0) radioactive_decay<N>(T, c, dtot, dsorb, residual, J, true);
     if (h.ngen > 0) general_reaction<N>(T, c, residual, J, true);
+    if (nim > 0) {                                                             // immobile rows / columns: :5201-5206, then RMicrobial, RImmobileDecay
+      expand_block(J, naq, n);
+      for (int i = naq; i < n; ++i) J[i + i * n] = c.volume / tran_dt;
+    }
+    if (h.nmic > 0) microbial_reaction<N>(T, c, residual, J, true);
+    if (h.nimdecay > 0) immobile_decay<N>(T, c, residual, J, true);
     double mx = 0.0;
     bool nonfinite = false;
     for (int i = 0; i < n; ++i) { mx = fmax(mx, fabs(residual[i])); if (!isfinite(residual[i])) nonfinite = true; }
     if (nonfinite) { c.flags |= RXN_FLAG_NONFINITE; break; }
     if (mx < h.res_tol) { *exit_reason = RXN_EXIT_RESIDUAL; break; }           // :3443
-    if (rsolve<N>(residual, J, c.m, n, h.use_log != 0)) { c.flags |= RXN_FLAG_LU_ZERO_ROW; break; }
-    double *update = residual;
     for (int i = 0; i < naq; ++i) prev_solution[i] = c.m[i];
+    for (int i = 0; i < nim; ++i) prev_solution[naq + i] = c.im[i];            // :3448-3452
+    // log formulation with immobile dofs: the reference hands RSolve pri_molal (naqcomp values) as conc(ncomp) (:3445); the
+    // immobile concentrations scale their own columns here (include/rxn_b200.h, rxn_react_batch)
+    if (rsolve<N>(residual, J, prev_solution, n, h.use_log != 0)) { c.flags |= RXN_FLAG_LU_ZERO_ROW; break; }
+    double *update = residual;
     if (h.use_log) {                                                           // :3454-3458
       for (int i = 0; i < n; ++i) update[i] = copysign(1.0, update[i]) * fmin(fabs(update[i]), h.max_dlnC);
       for (int i = 0; i < n; ++i) new_solution[i] = prev_solution[i] * exp(-update[i]);
@@ -1004,10 +1131,12 @@ __device__ int rreact(const Tab &T, const DevState &S, Cell<N> &c, double *tran_
       for (int i = 0; i < n; ++i) new_solution[i] = scale * (new_solution[i] - prev_solution[i]) + prev_solution[i];
     }
     for (int i = 0; i < naq; ++i) c.m[i] = new_solution[i];                    // :3498
+    for (int i = 0; i < nim; ++i) c.im[i] = new_solution[naq + i];             // :3499-3502
     if (num_iterations >= h.maxit) { c.flags |= RXN_FLAG_CAPPED; break; }      // GPU-only guard (reference spins)
   }
   auxvar_compute<N>(T, S, c, J, dsorb);                                        // :3507
   for (int i = 0; i < naq; ++i) tran_xx[i] = c.m[i];                           // reactive_transport.F90:1711
+  for (int i = 0; i < nim; ++i) tran_xx[naq + i] = c.im[i];                    // the cell's own slots (:1712-1716 drops the cell offset)
   return num_iterations;
 }
 
@@ -1027,7 +1156,7 @@ __device__ void cell_react(const Tab &T, const DevState &S, long long i, double 
   Cell<N> c;
   double J[N * N], dsorb[N * N], xx[N];
   load_cell<N>(T, S, cell, c);
-  const int n = T.h->naq;
+  const int n = T.h->ncomp;
   for (int k = 0; k < n; ++k) xx[k] = tran_xx[i * n + k];
   int reason = 0;
   const int it = rreact<N>(T, S, c, xx, dt, dt_mode, J, dsorb, &reason);
@@ -1044,8 +1173,9 @@ __device__ void cell_update_auxvars(const Tab &T, const DevState &S, long long c
   Cell<N> c;
   double dtot[N * N], dsorb[N * N];
   load_cell<N>(T, S, cell, c);
-  const int n = T.h->naq;
-  if (xx_loc) for (int k = 0; k < n; ++k) c.m[k] = xx_loc[cell * n + k];
+  const int n = T.h->naq, nc = T.h->ncomp;
+  if (xx_loc) for (int k = 0; k < n; ++k) c.m[k] = xx_loc[cell * nc + k];
+  if (xx_loc) for (int k = n; k < nc; ++k) c.im[k - n] = xx_loc[cell * nc + k];             // :3801-3805
   if (update_act_coefs) activity_coefficients<N>(T, S, c);
   auxvar_compute<N>(T, S, c, dtot, dsorb);
   store_cell<N>(T, S, c, dtot, dsorb);
@@ -1061,16 +1191,18 @@ __device__ void cell_fixed_accum(const Tab &T, const DevState &S, long long i, c
   Cell<N> c;
   double dtot[N * N], dsorb[N * N];
   load_cell<N>(T, S, cell, c);
-  const int n = T.h->naq;
-  if (xx) for (int k = 0; k < n; ++k) c.m[k] = xx[i * n + k];
+  const int n = T.h->naq, nc = T.h->ncomp;
+  if (xx) for (int k = 0; k < n; ++k) c.m[k] = xx[i * nc + k];
+  if (xx) for (int k = n; k < nc; ++k) c.im[k - n] = xx[i * nc + k];                        // :809-813
   auxvar_compute<N>(T, S, c, dtot, dsorb);
   const double psv_t = c.porosity * c.sat * 1000.0 * c.volume;
   for (int k = 0; k < n; ++k) {
     double r = psv_t * c.total[k];
     if (T.h->neqsorb > 0) r = r + c.tsorb[k] * c.volume;
-    accum_out[i * n + k] = r;
+    accum_out[i * nc + k] = r;
     if (!isfinite(r)) c.flags |= RXN_FLAG_NONFINITE;
   }
+  for (int k = n; k < nc; ++k) accum_out[i * nc + k] = c.im[k - n] * c.volume;              // reaction.F90:5117-5125
   store_cell<N>(T, S, c, dtot, dsorb);
   report_cell_flags(S, c.flags);
 }
@@ -1104,7 +1236,9 @@ __device__ void cell_residual_jacobian(const Tab &T, const DevState &S, long lon
     for (int k = 0; k < n; ++k) Res[k] = Res[k] + c.tsorb[k] * c.volume;
     for (int e = 0; e < n * n; ++e) J[e] = J[e] + dsorb[e] * v_t;
   }
-  for (int k = 0; k < n; ++k) { Res[k] = Res[k] / dt; Res2[k] = 0.0; }
+  const int nc = tab.ncomp;
+  for (int k = n; k < nc; ++k) Res[k] = c.im[k - n] * c.volume;               // reaction.F90:5117-5125
+  for (int k = 0; k < nc; ++k) { Res[k] = Res[k] / dt; Res2[k] = 0.0; }
   const bool deriv = jac_out != nullptr;
   if (tab.ndecay > 0) {
     // the decay terms read d total / d free-ion (kept in J2 so far): add them into the accumulation block first -
@@ -1120,9 +1254,16 @@ __device__ void cell_residual_jacobian(const Tab &T, const DevState &S, long lon
   }
   if (tab.nkinrxn > 0) kinetic_surfcplx<N>(T, S, c, dt, Res2, J2, deriv);
   if (tab.ngen > 0) general_reaction<N>(T, c, Res2, J2, deriv);
-  for (int k = 0; k < n; ++k) if (!isfinite(Res[k] + Res2[k])) c.flags |= RXN_FLAG_NONFINITE;
-  if (res_out) for (int k = 0; k < n; ++k) res_out[i * n + k] = Res[k] + Res2[k];
-  if (jac_out) for (int e = 0; e < n * n; ++e) jac_out[i * (long long)(n * n) + e] = J[e] + J2[e];
+  if (nc > n) {                                                                // immobile rows / columns (see expand_block)
+    expand_block(J, n, nc);
+    expand_block(J2, n, nc);
+    for (int k = n; k < nc; ++k) J[k + k * nc] = c.volume / dt;               // reaction.F90:5201-5206
+  }
+  if (tab.nmic > 0) microbial_reaction<N>(T, c, Res2, J2, deriv);
+  if (tab.nimdecay > 0) immobile_decay<N>(T, c, Res2, J2, deriv);
+  for (int k = 0; k < nc; ++k) if (!isfinite(Res[k] + Res2[k])) c.flags |= RXN_FLAG_NONFINITE;
+  if (res_out) for (int k = 0; k < nc; ++k) res_out[i * nc + k] = Res[k] + Res2[k];
+  if (jac_out) for (int e = 0; e < nc * nc; ++e) jac_out[i * (long long)(nc * nc) + e] = J[e] + J2[e];
   store_cell<N>(T, S, c, nullptr, nullptr);   // totals + warm-start free sites stay consistent
   report_cell_flags(S, c.flags);
 }

@@ -121,8 +121,8 @@ inline int lane_plan_build(const DevTab &h, const std::vector<double> &bd, const
     return unusable("NEWTON activity-coefficient algorithm runs on the thread-per-cell kernel");
   if (h.nionx > 0 || h.nkd > 0) return unusable("ion exchange / KD isotherms run on the thread-per-cell kernel");
   if (h.maxpref > 0) return unusable("mineral prefactors run on the thread-per-cell kernel");
-  if (h.ngen > 0 || h.ndecay > 0 || h.nkinrxn > 0)
-    return unusable("general / radioactive decay / kinetic surface complexation reactions run on the thread-per-cell kernel");
+  if (h.ngen > 0 || h.ndecay > 0 || h.nkinrxn > 0 || h.nmic > 0 || h.nim > 0 || h.nimdecay > 0)
+    return unusable("general / radioactive decay / kinetic surface complexation / microbial reactions and immobile species run on the thread-per-cell kernel");
   if (n > N) return unusable("naq exceeds the shape");
   if (tmG > 0 && N > 15) return unusable("tensor-memory kernel: a row [J_i | b_i] must fit 16 doubles (N <= 15)");
   lt.N = N; lt.CPB = CPB; lt.LDJ2 = (N + 2) / 2;

@@ -79,23 +79,23 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
   if (d->struct_size != (int)sizeof(RxnTablesDesc))
     return R.fail(RXN_ERR_INVALID, "RxnTablesDesc.struct_size %d != %d", d->struct_size, (int)sizeof(RxnTablesDesc));
   // reaction types outside the path
-  if (d->nactive_gas || d->nimmobile || d->ncoll || d->nmicrobial_rxn ||
-      d->nimmobile_decay_rxn || d->has_sandbox || d->has_clm || d->has_solid_solution || d->co2_flow_mode ||
+  if (d->nactive_gas || d->ncoll || d->has_sandbox || d->has_clm || d->has_solid_solution || d->co2_flow_mode ||
       d->numerical_derivatives)
     return R.fail(RXN_ERR_UNSUPPORTED,
-                  "tables enable a reaction type outside the B200 path (active gas %d, immobile %d, colloids %d, "
-                  "microbial %d, immobile decay %d, sandbox %d, CLM %d, solid solution %d, CO2 flow mode %d, "
-                  "numerical Jacobian %d)",
-                  d->nactive_gas, d->nimmobile, d->ncoll, d->nmicrobial_rxn,
-                  d->nimmobile_decay_rxn, d->has_sandbox, d->has_clm, d->has_solid_solution, d->co2_flow_mode,
+                  "tables enable a reaction type outside the B200 path (active gas %d, colloids %d, "
+                  "sandbox %d, CLM %d, solid solution %d, CO2 flow mode %d, numerical Jacobian %d)",
+                  d->nactive_gas, d->ncoll, d->has_sandbox, d->has_clm, d->has_solid_solution, d->co2_flow_mode,
                   d->numerical_derivatives);
-  if (d->ngeneral_rxn < 0 || d->nradiodecay_rxn < 0 || d->nkinsrfcplxrxn < 0) return R.fail(RXN_ERR_INVALID, "negative reaction count");
+  if (d->ngeneral_rxn < 0 || d->nradiodecay_rxn < 0 || d->nkinsrfcplxrxn < 0 || d->nimmobile < 0 || d->nmicrobial_rxn < 0 ||
+      d->nimmobile_decay_rxn < 0)
+    return R.fail(RXN_ERR_INVALID, "negative reaction count");
   if (d->nkinsrfcplxrxn > 1)
     return R.fail(RXN_ERR_UNSUPPORTED, "more than one KINETIC surface complexation reaction: the reference keeps the kinetic "
                                        "concentrations of one reaction only (kinsrfcplx_conc(:,1), reactive_transport_aux.F90:284-290)");
-  if (d->naqcomp < 1 || d->ncomp != d->naqcomp)
-    return R.fail(RXN_ERR_UNSUPPORTED, "ncomp (%d) must equal naqcomp (%d) >= 1", d->ncomp, d->naqcomp);
-  if (d->naqcomp > RXN_MAX_NAQ) return R.fail(RXN_ERR_UNSUPPORTED, "naqcomp %d > %d", d->naqcomp, (int)RXN_MAX_NAQ);
+  if (d->naqcomp < 1 || d->ncomp != d->naqcomp + d->nimmobile)
+    return R.fail(RXN_ERR_UNSUPPORTED, "ncomp (%d) must equal naqcomp (%d) >= 1 plus nimmobile (%d): no colloid dofs", d->ncomp, d->naqcomp, d->nimmobile);
+  if (d->ncomp > RXN_MAX_NAQ) return R.fail(RXN_ERR_UNSUPPORTED, "ncomp %d > %d", d->ncomp, (int)RXN_MAX_NAQ);
+  if (d->nimmobile > RXN_MAX_IMMOBILE) return R.fail(RXN_ERR_UNSUPPORTED, "nimmobile %d > %d", d->nimmobile, (int)RXN_MAX_IMMOBILE);
   if (d->nkinmrsrfcplxrxn > 2) return R.fail(RXN_ERR_UNSUPPORTED, "more than 2 multirate surface complexation reactions");
   if (d->max_num_prefactors > RXN_MAX_PREF || d->max_num_prefactor_species > RXN_MAX_PREF_SPEC)
     return R.fail(RXN_ERR_UNSUPPORTED, "mineral prefactor table too large");
@@ -281,6 +281,83 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
     h.nkinsrf = nc; h.kin_rxn = 0;
     h.o_kin_kf = P.D(d->kinsrfcplx_forward_rate, nc); h.o_kin_kb = P.D(d->kinsrfcplx_backward_rate, nc);
   }
+  // immobile decay (reaction_immobile.F90:240-293) and microbial reactions (reaction_microbial.F90:236-450)
+  h.nim = d->nimmobile; h.ncomp = d->ncomp; h.nimdecay = d->nimmobile_decay_rxn; h.nmic = d->nmicrobial_rxn;
+  {
+    std::vector<int32_t> ids;
+    if (h.nimdecay > 0 && (!d->immobile_decayspecid || !d->immobile_decay_rate_constant))
+      return R.fail(RXN_ERR_INVALID, "nimmobile_decay_rxn = %d without the immobile decay tables", h.nimdecay);
+    for (int r = 0; r < h.nimdecay; ++r) {
+      const int sp = d->immobile_decayspecid[r];
+      if (sp < 1 || sp > h.nim) return R.fail(RXN_ERR_INVALID, "immobile decay reaction %d: immobile species id %d out of range", r + 1, sp);
+      ids.push_back(sp - 1);
+    }
+    h.o_imdec_id = P.I(ids.data(), ids.size()); h.o_imdec_k = P.D(d->immobile_decay_rate_constant, h.nimdecay);
+  }
+  if (h.nmic > 0) {
+    if (!d->microbial_specid || !d->microbial_stoich || !d->microbial_rate_constant || !d->microbial_biomassid || !d->microbial_biomass_yield ||
+        !d->microbial_monodid || !d->microbial_inhibitionid || d->microbial_ld < 1 || d->nmicrobial_monod < 0 || d->nmicrobial_inhibition < 0 ||
+        (d->nmicrobial_monod > 0 && (!d->microbial_monod_specid || !d->microbial_monod_K || !d->microbial_monod_Cth)) ||
+        (d->nmicrobial_inhibition > 0 && (!d->microbial_inhibition_type || !d->microbial_inhibition_specid || !d->microbial_inhibition_C ||
+                                          !d->microbial_inhibition_C2)))
+      return R.fail(RXN_ERR_INVALID, "nmicrobial_rxn = %d without the microbial tables", h.nmic);
+    std::vector<int32_t> ptr(1, 0), id, bio, mptr(1, 0), mid, iptr(1, 0), iid, mspec, ispec;
+    std::vector<double> sv;
+    for (int r = 0; r < h.nmic; ++r) {
+      const int ld = d->microbial_ld, n = d->microbial_specid[(size_t)r * (ld + 1)];
+      if (n < 0 || n > ld) return R.fail(RXN_ERR_INVALID, "microbial reaction %d: species count %d out of range", r + 1, n);
+      for (int k = 1; k <= n; ++k) {
+        const int sp = d->microbial_specid[(size_t)r * (ld + 1) + k];
+        if (sp < 1 || sp > h.ncomp) return R.fail(RXN_ERR_INVALID, "microbial reaction %d: species id %d out of range", r + 1, sp);
+        id.push_back(sp - 1);
+        sv.push_back(d->microbial_stoich[(size_t)r * ld + k - 1]);
+      }
+      ptr.push_back((int32_t)id.size());
+      const int b = d->microbial_biomassid[r];
+      if (b < 0 || b > h.nim) return R.fail(RXN_ERR_INVALID, "microbial reaction %d: biomass id %d out of range", r + 1, b);
+      bio.push_back(b - 1);
+      const int nm = d->microbial_monodid[(size_t)r * (d->microbial_monod_ld + 1)], ni = d->microbial_inhibitionid[(size_t)r * (d->microbial_inhibition_ld + 1)];
+      if (nm < 0 || nm > d->microbial_monod_ld || ni < 0 || ni > d->microbial_inhibition_ld)
+        return R.fail(RXN_ERR_INVALID, "microbial reaction %d: Monod / inhibition count out of range", r + 1);
+      if (nm > RXN_MAX_MONOD || ni > RXN_MAX_MONOD)
+        return R.fail(RXN_ERR_UNSUPPORTED, "microbial reaction %d: more than %d Monod or inhibition terms (the reference's monod(10), inhibition(10))", r + 1, (int)RXN_MAX_MONOD);
+      for (int k = 1; k <= nm; ++k) {
+        const int m = d->microbial_monodid[(size_t)r * (d->microbial_monod_ld + 1) + k];
+        if (m < 1 || m > d->nmicrobial_monod) return R.fail(RXN_ERR_INVALID, "microbial reaction %d: Monod id %d out of range", r + 1, m);
+        mid.push_back(m - 1);
+      }
+      mptr.push_back((int32_t)mid.size());
+      for (int k = 1; k <= ni; ++k) {
+        const int m = d->microbial_inhibitionid[(size_t)r * (d->microbial_inhibition_ld + 1) + k];
+        if (m < 1 || m > d->nmicrobial_inhibition) return R.fail(RXN_ERR_INVALID, "microbial reaction %d: inhibition id %d out of range", r + 1, m);
+        iid.push_back(m - 1);
+      }
+      iptr.push_back((int32_t)iid.size());
+    }
+    for (int k = 0; k < d->nmicrobial_monod; ++k) {
+      const int sp = d->microbial_monod_specid[k];
+      if (sp < 1 || sp > naq) return R.fail(RXN_ERR_INVALID, "Monod term %d: species id %d out of range", k + 1, sp);
+      mspec.push_back(sp - 1);
+    }
+    for (int k = 0; k < d->nmicrobial_inhibition; ++k) {
+      const int sp = d->microbial_inhibition_specid[k], ty = d->microbial_inhibition_type[k];
+      if (sp < 1 || sp > naq) return R.fail(RXN_ERR_INVALID, "inhibition term %d: species id %d out of range", k + 1, sp);
+      if (ty != RXN_INHIBITION_THRESHOLD && ty != RXN_INHIBITION_MONOD && ty != RXN_INHIBITION_INVERSE_MONOD)
+        return R.fail(RXN_ERR_UNSUPPORTED, "inhibition term %d: type %d has no branch in RMicrobial (reaction_microbial.F90:322-339)", k + 1, ty);
+      ispec.push_back(sp - 1);
+    }
+    h.o_mic_ptr = P.I(ptr.data(), ptr.size()); h.o_mic_id = P.I(id.data(), id.size()); h.o_mic_st = P.D(sv.data(), sv.size());
+    h.o_mic_bio = P.I(bio.data(), bio.size());
+    h.o_mic_mptr = P.I(mptr.data(), mptr.size()); h.o_mic_mid = P.I(mid.data(), mid.size());
+    h.o_mic_iptr = P.I(iptr.data(), iptr.size()); h.o_mic_iid = P.I(iid.data(), iid.size());
+    h.o_mic_k = P.D(d->microbial_rate_constant, h.nmic);
+    h.mic_has_Ea = d->microbial_activation_energy != nullptr; h.o_mic_Ea = P.D(d->microbial_activation_energy, h.nmic);
+    h.o_mic_yield = P.D(d->microbial_biomass_yield, h.nmic);
+    h.o_mon_spec = P.I(mspec.data(), mspec.size()); h.o_mon_K = P.D(d->microbial_monod_K, d->nmicrobial_monod);
+    h.o_mon_Cth = P.D(d->microbial_monod_Cth, d->nmicrobial_monod);
+    h.o_inh_spec = P.I(ispec.data(), ispec.size()); h.o_inh_type = P.I(d->microbial_inhibition_type, d->nmicrobial_inhibition);
+    h.o_inh_C = P.D(d->microbial_inhibition_C, d->nmicrobial_inhibition); h.o_inh_C2 = P.D(d->microbial_inhibition_C2, d->nmicrobial_inhibition);
+  }
 #undef RXN_TRY
   if (P.i.size() & 1) P.i.push_back(0);
   h.ndbl = (int)P.d.size(); h.nint = (int)P.i.size();
@@ -297,6 +374,7 @@ inline int pack_tables(const RxnTablesDesc *d, PackResult &R) {
       r[RXN_F_SOIL_PARTICLE_DENSITY] = 1;
   r[RXN_F_DTOTAL] = naq * naq; r[RXN_F_DTOTAL_SORB_EQ] = naq * naq;
   r[RXN_F_KINSRFCPLX_CONC] = h.nkinsrf; r[RXN_F_KINSRFCPLX_CONC_KP1] = h.nkinsrf; r[RXN_F_KINSRFCPLX_FREE_SITE_CONC] = h.nkinrxn;
+  r[RXN_F_IMMOBILE] = h.nim;
   return RXN_OK;
 }
 

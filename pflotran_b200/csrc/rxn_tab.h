@@ -53,6 +53,15 @@ struct DevTab {
   // kinetic surface complexation (RKineticSurfCplx): at most one reaction, = surface complexation reaction kin_rxn (0-based)
   int nkinrxn, nkinsrf, kin_rxn;
   int o_kin_kf, o_kin_kb;                                                   // dbl [nkinsrf]
+  // immobile species (dofs naq .. ncomp-1), their decay (RImmobileDecay) and microbial reactions (RMicrobial); 0-based ids,
+  // microbial species ids run over the ncomp dofs
+  int nim, ncomp, nimdecay, nmic, mic_has_Ea;
+  int o_imdec_id;                                                           // int [nimdecay] immobile id
+  int o_imdec_k;                                                            // dbl [nimdecay]
+  int o_mic_ptr, o_mic_id, o_mic_bio, o_mic_mptr, o_mic_mid, o_mic_iptr, o_mic_iid;   // int (o_mic_bio: immobile id or -1)
+  int o_mic_st, o_mic_k, o_mic_Ea, o_mic_yield;                             // dbl
+  int o_mon_spec, o_inh_spec, o_inh_type;                                   // int
+  int o_mon_K, o_mon_Cth, o_inh_C, o_inh_C2;                                // dbl
 };
 
 // SoA FP64 state in HBM: f[field][row*ld + cell]; NULL when the field has no rows or is
@@ -66,6 +75,7 @@ struct DevState {
 };
 
 // hard limits of the per-thread scratch (tables beyond them are rejected at create time)
-enum { RXN_MAX_SRFCPLX_PER_RXN = 32, RXN_MAX_PREF = 10, RXN_MAX_PREF_SPEC = 5, RXN_MAX_NAQ = 24 };
+enum { RXN_MAX_SRFCPLX_PER_RXN = 32, RXN_MAX_PREF = 10, RXN_MAX_PREF_SPEC = 5, RXN_MAX_NAQ = 24,
+       RXN_MAX_IMMOBILE = 4, RXN_MAX_MONOD = 10 /* monod(10), inhibition(10): reaction_microbial.F90:270-271 */ };
 
 }  // namespace rxn

@@ -395,7 +395,7 @@ class Realization:
         conc = np.ascontiguousarray(conc, dtype=np.float64)
         stride = 0 if conc.ndim == 1 else conc.shape[1]
         guess = None if free_ion_guess is None else np.ascontiguousarray(free_ion_guess, dtype=np.float64)
-        basis = np.zeros((n, self.ncomp))
+        basis = np.zeros((n, self.reaction.desc.naqcomp))
         iters = np.zeros(n, dtype=np.int32)
         status = np.zeros(n, dtype=np.int32)
         _ck(lib().rxn_equilibrate_constraint_batch(self.h, _ip(ctype), _dp(conc), stride, _ip(cid), _dp(guess), int(use_prev),

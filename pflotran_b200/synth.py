@@ -51,6 +51,10 @@ class Workload:
     def base_totals(self) -> np.ndarray:
         return self.base['TOTAL'].copy()
 
+    def base_solution(self) -> np.ndarray:
+        """the solution vector of the base state: free-ion molalities, then the immobile concentrations [ncomp]"""
+        return np.concatenate([self.base['PRI_MOLAL'], self.base.get('IMMOBILE', np.zeros(0))])
+
 
 def _block(w: Workload, b: int, sigma: float, front_fraction: float, front_sigma: float, seed: int):
     t = w.tables
@@ -65,6 +69,9 @@ def _block(w: Workload, b: int, sigma: float, front_fraction: float, front_sigma
     uP = rng.random(BLOCK)
     sig = np.where(u_front < front_fraction, front_sigma, sigma)[:, None]
     xx = w.base['TOTAL'][None, :] * np.exp(sig * z)
+    nim = getattr(t, 'nimmobile', 0)
+    if nim > 0:          # immobile dofs follow the aqueous ones; drawn last so that the other streams do not depend on nim
+        xx = np.concatenate([xx, w.base['IMMOBILE'][None, :] * np.exp(sig * rng.standard_normal((BLOCK, nim)))], axis=1)
     vf = np.where(zero, 0.0, vf)[:, :nk]
     if t.logK_mode != 0:
         temp = 25.0 + 125.0 * uT
@@ -80,7 +87,7 @@ def make_cells(w: Workload, start: int, ncells: int, sigma: float = 0.05, front_
     """Per-cell inputs for cells [start, start+ncells): tran_xx [ncells, ncomp] (AoS, C order),
     porosity [ncells], volfrac [nkin, ncells], temp, pres [ncells]."""
     t = w.tables
-    n, nk = t.naqcomp, t.nkinmnrl
+    n, nk = t.ncomp, t.nkinmnrl
     xx = np.empty((ncells, n))
     por = np.empty(ncells)
     vf = np.empty((nk, ncells))

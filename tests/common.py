@@ -6,7 +6,7 @@ from pflotran_b200 import abi, synth
 
 STATE_FIELDS = ['PRI_MOLAL', 'TOTAL', 'SEC_MOLAL', 'PRI_ACT_COEF', 'SEC_ACT_COEF', 'LN_ACT_H2O', 'TOTAL_SORB_EQ',
                 'FREE_SITE_CONC', 'EQSRFCPLX_CONC', 'KINMR_TOTAL_SORB', 'EQIONX_REF_CATION_SORBED_CONC', 'EQIONX_CONC',
-                'MNRL_VOLFRAC', 'MNRL_RATE', 'KINSRFCPLX_CONC', 'KINSRFCPLX_CONC_KP1', 'KINSRFCPLX_FREE_SITE_CONC']
+                'MNRL_VOLFRAC', 'MNRL_RATE', 'KINSRFCPLX_CONC', 'KINSRFCPLX_CONC_KP1', 'KINSRFCPLX_FREE_SITE_CONC', 'IMMOBILE']
 
 # north_star: relative 1e-10 on converged free-ion and mineral concentrations, identical flags
 RTOL = 1.0e-10
@@ -30,6 +30,15 @@ def total_magnitude(st, tables, cells=None):
             for q in range(1, ids[k, 0] + 1):
                 mag[ids[k, q] - 1] += abs(stc[k, q]) * np.abs(sm[k])
     return mag * pick(st['DEN_KG']) * 1.0e-3
+
+
+def accumulation_scale(st, tables, a_o):
+    """Scale of the fixed accumulation phi*s*1000*V*total (+ sorbed*V), reaction.F90:5072-5148: total's own terms for the
+    aqueous dofs, the value itself for the immobile dofs (immobile*V, no cancellation).  [ncells, ncomp]"""
+    aq = (st['POROSITY'] * st['SAT'] * 1000.0 * st['VOLUME'] * total_magnitude(st, tables)).T
+    sc = np.abs(a_o).copy()
+    sc[:, :aq.shape[1]] = np.maximum(sc[:, :aq.shape[1]], aq)
+    return sc
 
 
 def residual_scale(st, tables, r_o, a_o, dt):
@@ -56,7 +65,7 @@ def jacobian_scale(st, j_o, ncomp):
     differences of the accumulation and kinetic derivative terms (they cancel near equilibrium).  [ncells, ncomp^2]"""
     n = j_o.shape[0]
     J = np.abs(j_o).reshape(n, ncomp, ncomp).transpose(0, 2, 1)          # [cell, i, j]
-    m = np.abs(st['PRI_MOLAL']).T[:, None, :]                             # [cell, 1, j]
+    m = np.abs(np.concatenate([st['PRI_MOLAL'], st['IMMOBILE']], axis=0)).T[:, None, :]   # [cell, 1, j]: aqueous, then immobile dofs
     rowmax = (J * m).max(axis=2, keepdims=True)
     sc = np.maximum(J, rowmax / np.maximum(m, 1e-300))
     return sc.transpose(0, 2, 1).reshape(n, ncomp * ncomp)

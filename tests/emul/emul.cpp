@@ -396,7 +396,7 @@ void *emu_create(const RxnTablesDesc *d, char *err, int errlen) {
   e->T.d = reinterpret_cast<const double *>(e->blob.data());
   e->T.i = reinterpret_cast<const int *>(e->blob.data() + (size_t)e->R.h.ndbl * 8);
   e->T.h = &e->R.h;
-  e->nv = variant_for(e->R.h.naq);
+  e->nv = variant_for(e->R.h.ncomp);
   return e;
 }
 void emu_destroy(void *h) { delete (Emu *)h; }

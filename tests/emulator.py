@@ -176,7 +176,7 @@ class Emulator:
         conc = np.ascontiguousarray(conc, dtype=np.float64)
         stride = 0 if conc.ndim == 1 else conc.shape[1]
         guess = None if free_ion_guess is None else np.ascontiguousarray(free_ion_guess, dtype=np.float64)
-        basis = np.zeros((n, self.t.ncomp)); iters = np.zeros(n, dtype=np.int32); status = np.zeros(n, dtype=np.int32)
+        basis = np.zeros((n, self.t.naqcomp)); iters = np.zeros(n, dtype=np.int32); status = np.zeros(n, dtype=np.int32)
         v = st.view()
         assert lib().emu_equilibrate_batch(self.h, C.byref(v), _p(st.active, C.c_uint8), _p(ctype, C.c_int32), _p(conc, C.c_double),
                                            C.c_int64(stride), _p(cid, C.c_int32), _p(guess, C.c_double), C.c_int(int(use_prev)),

@@ -170,7 +170,8 @@ def run(t, be, xx, dts, atol=1.0e-50, rtol=1.0e-8, stol=1.0e-8, maxit=50):
     return newton
 
 
-TIME_STEPPED_GOLD = ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction']
+TIME_STEPPED_GOLD = ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction',
+                     'abcd_microbial', 'abcd_microbial_act_high', 'abcd_microbial_act_low']
 
 
 def check_time_stepped_gold(w, be, t, xx, tol=1.0e-12):

@@ -59,6 +59,18 @@ WORKLOADS = {
                          'regression_tests/ascem/batch/general-reaction.regression.gold'),
     # non-isothermal run: 5-term logK fit evaluated per cell (reaction_aux.F90:1336-1408, 1461-1488) + Arrhenius factor
     'calcite_fit5': ('regression_tests/default/anisothermal/thc_1d.in', 'initial_constraint', None),
+    # RMicrobial (reaction_microbial.F90:236-450) with Monod / inverse-Monod terms, biomass as an immobile species and
+    # RImmobileDecay (reaction_immobile.F90:240-293): log formulation, 111 steps with the reference's step-size controller
+    'abcd_microbial': ('regression_tests/default/batch/ABCD_microbial.in', 'initial',
+                       'regression_tests/default/batch/ABCD_microbial.regression.gold'),
+    # the same with an Arrhenius factor at 35 C / 15 C (activation energy in J/mol resp. kJ/mol)
+    'abcd_microbial_act_high': ('regression_tests/default/batch/ABCD_microbial_activation_high.in', 'initial',
+                                'regression_tests/default/batch/ABCD_microbial_activation_high.regression.gold'),
+    'abcd_microbial_act_low': ('regression_tests/default/batch/ABCD_microbial_activation_low.in', 'initial',
+                               'regression_tests/default/batch/ABCD_microbial_activation_low.regression.gold'),
+    # microbial reaction without biomass (no immobile dof), linear formulation.  Parity fixture only: the deck's gold run drives A(aq)
+    # to 1e-63 with Newton tolerances of 1e-50 and ends each solve on SNES criteria outside this path, so it is not asserted
+    'ab_microbial_linear': ('regression_tests/default/batch/AB_microbial_linear_scaling.in', 'initial', None),
     # BASELINE config 1: 22 primaries / 164 complexes (example_problems/ascem_chemistry, savannah_river.dat)
     'ascem': ('example_problems/ascem_chemistry/pflotran.in', 'initial', None),
 }
@@ -199,7 +211,8 @@ def main():
         vf, area = mineral_arrays(t, d.constraints[constraint])
         cons = {'ctype': [int(x) for x in ctype], 'conc': [repr(float(x)) for x in conc], 'cid': [int(x) for x in cid],
                 'guess': None if guess is None else [repr(float(x)) for x in guess],
-                'volfrac': [repr(float(x)) for x in vf], 'area': [repr(float(x)) for x in area]}
+                'volfrac': [repr(float(x)) for x in vf], 'area': [repr(float(x)) for x in area],
+                'immobile': [repr(float(x)) for x in kat.immobile_array(t, d.constraints[constraint])]}
         out = {
             'constraint_arrays': cons,
             'name': name, 'deck': deck, 'constraint': constraint, 'equilibrate_iterations': int(nit),

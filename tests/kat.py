@@ -74,12 +74,25 @@ def initial_cell(deck_path, constraint='initial', porosity=None, volume=1.0, iso
         st['KINMR_TOTAL_SORB'][:] = cst['KINMR_TOTAL_SORB']
         st['FREE_SITE_CONC'][:] = cst['FREE_SITE_CONC']
     xx = (basis_molarity / t.reference_water_density * 1000.0).reshape(1, -1).copy()
+    xx = with_immobile(t, xx, immobile_array(t, c))
     # 3.
     orc.update_auxvars(st, xx, False)
     if t.act_coef_update_frequency != 0:
         orc.update_auxvars(st, xx, True)
         orc.update_auxvars(st, xx, True)
     return deck, t, orc, st, xx, nit, cst
+
+
+def immobile_array(t, c):
+    """immobile concentrations of a deck constraint in immobile-species order (ImmobileProcessConstraint, reaction_immobile.F90:163-236)"""
+    return np.array([c.immobile.get(n, 0.0) for n in getattr(t, 'immobile_names', [])], dtype=np.float64)
+
+
+def with_immobile(t, xx, im):
+    """solution vector [aqueous free-ion molalities, immobile concentrations] (condition_control.F90:842-856)"""
+    if getattr(t, 'nimmobile', 0) == 0:
+        return xx
+    return np.concatenate([xx, np.tile(np.asarray(im, dtype=np.float64).reshape(1, -1), (xx.shape[0], 1))], axis=1)
 
 
 class OracleBackend:
@@ -106,6 +119,10 @@ def fixture_constraint(w):
     return ctype, conc, cid, guess, vf, area
 
 
+def fixture_immobile(w):
+    return np.array([float(x) for x in w.meta['constraint_arrays'].get('immobile', [])], dtype=np.float64)
+
+
 def initial_cell_from_fixture(w, porosity=None, volume=1.0, backend=None):
     """Same start-up sequence as initial_cell(), driven only by a committed fixture
     (tests/golden/<name>.json): no deck, no database, no /root/reference.  `backend` (default: the oracle)
@@ -126,6 +143,7 @@ def initial_cell_from_fixture(w, porosity=None, volume=1.0, backend=None):
         st['KINMR_TOTAL_SORB'][:] = cst['KINMR_TOTAL_SORB']
         st['FREE_SITE_CONC'][:] = cst['FREE_SITE_CONC']
     xx = (basis_molarity / t.reference_water_density * 1000.0).reshape(1, -1).copy()
+    xx = with_immobile(t, xx, fixture_immobile(w))
     orc.update_auxvars(st, xx, False)
     if t.act_coef_update_frequency != 0:
         orc.update_auxvars(st, xx, True)
@@ -154,6 +172,8 @@ def outputs(t, st, cell=0):
         o[n] = st['EQSRFCPLX_CONC'][i, cell]
     for i, n in enumerate(t.srfcplxrxn_site_names):
         o['Free ' + n] = st['FREE_SITE_CONC'][i, cell]
+    for i, n in enumerate(getattr(t, 'immobile_names', [])):
+        o[n] = st['IMMOBILE'][i, cell]
     return o
 
 

@@ -8,7 +8,7 @@ import pytest
 from pflotran_b200 import abi, synth
 from oracle.pyoracle import Oracle
 from emulator import Emulator, pack_status
-from common import PerturbedOracle, iteration_parity, free_ion_parity, assert_state_close, workload_cells, RTOL, rel_err, total_magnitude, residual_scale, jacobian_scale
+from common import PerturbedOracle, iteration_parity, free_ion_parity, assert_state_close, workload_cells, RTOL, rel_err, total_magnitude, accumulation_scale, residual_scale, jacobian_scale
 
 WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation',
              'calcite_kinetics', 'kd_wo_mineral']
@@ -16,8 +16,10 @@ WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_
 # prefactor / non-isothermal / 22-primary decks): NEWTON activity algorithm + activity of water, free-site inner Newton,
 # Langmuir / Freundlich isotherms, Temkin / scale factor / affinity power / threshold / rate limiter / Arrhenius, mineral
 # prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes), general (forward / backward rate)
-# reactions, radioactive decay, kinetic surface complexation
-BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf']
+# reactions, radioactive decay, kinetic surface complexation, microbial reactions (Monod / inverse-Monod terms, biomass as an
+# immobile dof, Arrhenius factor) with immobile decay, and a microbial reaction without biomass in the linear formulation
+BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf',
+                    'abcd_microbial', 'abcd_microbial_act_high', 'ab_microbial_linear']
 WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
 GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 
@@ -152,7 +154,7 @@ def test_global_implicit_entry_points(name):
     orc, emu = Oracle(w.tables), Emulator(w.tables)
     # a perturbed iterate: free-ion molalities around the base state
     rng = np.random.default_rng(7)
-    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((300, w.ncomp))))
+    xx = np.ascontiguousarray(w.base_solution()[None, :] * np.exp(0.1 * rng.standard_normal((300, w.ncomp))))
     st_e = st_o.copy()
     orc.update_auxvars(st_o, xx, True)
     emu.update_auxvars(st_e, xx, True)
@@ -160,7 +162,7 @@ def test_global_implicit_entry_points(name):
     a_o = orc.fixed_accum(st_o, xx)
     a_e = emu.fixed_accum(st_e, xx)
     # accumulation = phi*s*1000*V*total (+ sorbed*V), reaction.F90:5072-5148: compared on the scale of total's terms
-    a_scale = np.maximum(np.abs(a_o), (st_o['POROSITY'] * st_o['SAT'] * 1000.0 * st_o['VOLUME'] * total_magnitude(st_o, w.tables)).T)
+    a_scale = accumulation_scale(st_o, w.tables, a_o)
     assert (np.abs(a_e - a_o) / np.maximum(a_scale, 1e-300)).max() <= RTOL
     r_o, j_o = orc.residual_jacobian(st_o, 1800.0)
     r_e, j_e = emu.residual_jacobian(st_e, 1800.0)
@@ -226,7 +228,7 @@ def test_global_implicit_tensor_memory_routines(name, G):
     assert_state_close(st_e, st_o, what=name + ' update_auxvars(lagged)', tables=w.tables)
     a_o = orc.fixed_accum(st_o, xx)
     a_e = emu.gi_tm(st_e, 1, G=G, xx=xx, xx_by_item=True, want_accum=True)
-    a_scale = np.maximum(np.abs(a_o), (st_o['POROSITY'] * st_o['SAT'] * 1000.0 * st_o['VOLUME'] * total_magnitude(st_o, w.tables)).T)
+    a_scale = accumulation_scale(st_o, w.tables, a_o)
     assert (np.abs(a_e - a_o) / np.maximum(a_scale, 1e-300)).max() <= RTOL
     assert_state_close(st_e, st_o, what=name + ' fixed accumulation state', tables=w.tables)
     r_o, j_o = orc.residual_jacobian(st_o, 1800.0)
@@ -284,8 +286,7 @@ def test_inactive_cells_and_l2g():
 def test_packer_rejects_unsupported():
     w = synth.Workload('calcite')
     d = abi.make_desc(w.tables)
-    for fld in ['nactive_gas', 'nimmobile', 'ncoll', 'nmicrobial_rxn',
-                'nimmobile_decay_rxn', 'has_sandbox', 'has_clm', 'has_solid_solution', 'co2_flow_mode',
+    for fld in ['nactive_gas', 'ncoll', 'has_sandbox', 'has_clm', 'has_solid_solution', 'co2_flow_mode',
                 'numerical_derivatives']:
         setattr(d, fld, 1)
         rc, msg = pack_status(d)
@@ -293,10 +294,13 @@ def test_packer_rejects_unsupported():
         setattr(d, fld, 0)
     # counts of the supported rate reactions without their tables, and more kinetic surface complexation reactions than the
     # reference's state holds
-    for fld in ['ngeneral_rxn', 'nradiodecay_rxn', 'nkinsrfcplxrxn']:
+    for fld in ['ngeneral_rxn', 'nradiodecay_rxn', 'nkinsrfcplxrxn', 'nmicrobial_rxn', 'nimmobile_decay_rxn']:
         setattr(d, fld, 1)
         assert pack_status(d)[0] == abi.RXN_ERR_INVALID, fld
         setattr(d, fld, 0)
+    d.nimmobile = 1                       # immobile dofs must be counted in ncomp
+    assert pack_status(d)[0] == abi.RXN_ERR_UNSUPPORTED
+    d.nimmobile = 0
     d.nkinsrfcplxrxn = 2
     assert pack_status(d)[0] == abi.RXN_ERR_UNSUPPORTED
     d.nkinsrfcplxrxn = 0
@@ -371,12 +375,14 @@ class _EmuGI:
         return self.st
 
 
-@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction'])
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction',
+                                  'abcd_microbial', 'abcd_microbial_act_high', 'abcd_microbial_act_low'])
 def test_time_stepped_device_code_hits_reference_gold(name):
     """The device routines behind rxn_fixed_accum / update_auxvars / residual_jacobian_blocks / update_kinetic_state
     (host compilation) driven through the reference's 1-cell global-implicit time loop reproduce
-    calcite-kinetics(.volume-fractions).regression.gold and solute_KD_{w,wo}_mineral.regression.gold at 1e-12 with the
-    reference's own time-step and Newton-iteration counts."""
+    calcite-kinetics(.volume-fractions).regression.gold, solute_KD_{w,wo}_mineral.regression.gold and
+    ABCD_microbial(_activation_{high,low}).regression.gold (microbial reaction with biomass as an immobile dof, immobile
+    decay) at 1e-12 with the reference's own time-step and Newton-iteration counts."""
     import gi_driver
     import kat
     w = synth.Workload(name)

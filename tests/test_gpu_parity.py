@@ -6,7 +6,7 @@ import pytest
 
 from pflotran_b200 import abi, synth, reactive_transport as rt
 from oracle.pyoracle import Oracle
-from common import PerturbedOracle, iteration_parity, free_ion_parity, assert_state_close, workload_cells, RTOL, rel_err, total_magnitude, residual_scale, jacobian_scale
+from common import PerturbedOracle, iteration_parity, free_ion_parity, assert_state_close, workload_cells, RTOL, rel_err, total_magnitude, accumulation_scale, residual_scale, jacobian_scale
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +17,8 @@ WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_
 # Langmuir / Freundlich isotherms, Temkin / scale factor / affinity power / threshold / rate limiter / Arrhenius, mineral
 # prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes), general (forward / backward rate)
 # reactions, radioactive decay, kinetic surface complexation
-BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf']
+BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf',
+                    'abcd_microbial', 'abcd_microbial_act_high', 'ab_microbial_linear']   # RMicrobial, immobile dofs, RImmobileDecay
 WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
 GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 
@@ -169,7 +170,7 @@ def test_global_implicit_entry_points(name):
     rx, rz = _gpu_state(w, st_g)
     orc = Oracle(w.tables)
     rng = np.random.default_rng(7)
-    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((n, w.ncomp))))
+    xx = np.ascontiguousarray(w.base_solution()[None, :] * np.exp(0.1 * rng.standard_normal((n, w.ncomp))))
     orc.update_auxvars(st_o, xx, True, nthreads=8)
     rz.RTUpdateAuxVars(xx, True)
     rz.download_host_state(st_g)
@@ -177,7 +178,7 @@ def test_global_implicit_entry_points(name):
     a_o = orc.fixed_accum(st_o, xx, nthreads=8)
     a_g = rz.RTUpdateFixedAccumulation(xx)
     # accumulation = phi*s*1000*V*total (+ sorbed*V), reaction.F90:5072-5148: compared on the scale of total's terms
-    a_scale = np.maximum(np.abs(a_o), (st_o['POROSITY'] * st_o['SAT'] * 1000.0 * st_o['VOLUME'] * total_magnitude(st_o, w.tables)).T)
+    a_scale = accumulation_scale(st_o, w.tables, a_o)
     assert (np.abs(a_g - a_o) / np.maximum(a_scale, 1e-300)).max() <= RTOL
     r_o, j_o = orc.residual_jacobian(st_o, 1800.0, nthreads=8)
     r_g, j_g = rz.RTResidualJacobianNonFlux(1800.0)
@@ -244,7 +245,7 @@ def test_global_implicit_blocks_inactive_cells_and_l2g(gi_kernel, monkeypatch):
     rz.set_cell_scalars(active=st_o.active)
     orc = Oracle(w.tables)
     rng = np.random.default_rng(5)
-    xx = np.ascontiguousarray(w.base['PRI_MOLAL'][None, :] * np.exp(0.1 * rng.standard_normal((n, w.ncomp))))
+    xx = np.ascontiguousarray(w.base_solution()[None, :] * np.exp(0.1 * rng.standard_normal((n, w.ncomp))))
     orc.update_auxvars(st_o, xx, True, nthreads=8)
     rz.RTUpdateAuxVars(xx, True)
     l2g = np.ascontiguousarray(rng.permutation(n)[:n - 1000].astype(np.int32))
@@ -336,11 +337,11 @@ def test_inactive_cells_l2g_and_empty():
 def test_unsupported_tables_rejected():
     w = synth.Workload('calcite')
     d = abi.make_desc(w.tables)
-    d.nmicrobial_rxn = 1                               # a reaction type outside the path (SURVEY 8f.4 "next")
+    d.nactive_gas = 1                                  # a reaction type outside the path (RTotalGas / RTotalCO2)
     with pytest.raises(rt.RxnError) as e:
         rt.Reaction(d)
     assert e.value.status == abi.RXN_ERR_UNSUPPORTED
-    d.nmicrobial_rxn = 0
+    d.nactive_gas = 0
     d.ngeneral_rxn = 1                                 # a supported reaction type without its tables
     with pytest.raises(rt.RxnError) as e:
         rt.Reaction(d)
@@ -477,7 +478,8 @@ def test_ascem_speciation_gpu_hits_reference_kat():
     assert kat.check_speciation_kat(w, t, cst, nit) == 2 * 22 + 157
 
 
-@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction'])
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction',
+                                  'abcd_microbial', 'abcd_microbial_act_high', 'abcd_microbial_act_low'])
 def test_time_stepped_gpu_hits_reference_gold(name):
     """rxn_fixed_accum_batch -> rxn_update_auxvars_batch -> rxn_residual_jacobian_blocks_batch -> block solve ->
     rxn_update_kinetic_state_batch, stepped as the reference's 1-cell global-implicit run (tests/gi_driver.py), reproduce the
@@ -497,7 +499,7 @@ def test_time_stepped_gpu_hits_reference_gold(name):
     dev = gi_driver.DeviceGI(rz, st2)
     assert gi_driver.check_time_stepped_gold(w, dev, t, xx2, tol=1.0e-12) >= 1
     s = dev.state()
-    for f in ('PRI_MOLAL', 'TOTAL', 'MNRL_VOLFRAC', 'MNRL_RATE'):
+    for f in ('PRI_MOLAL', 'TOTAL', 'MNRL_VOLFRAC', 'MNRL_RATE', 'IMMOBILE'):
         if s[f].shape[0]:
             assert (s[f][:, 0] == s[f][:, 1]).all()
 

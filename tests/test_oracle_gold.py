@@ -40,12 +40,16 @@ def test_gold_initial_speciation(name):
     _check(name)
 
 
-@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction'])
+@pytest.mark.parametrize('name', ['calcite_kinetics', 'calcite_kinetics_vf', 'kd_w_mineral', 'kd_wo_mineral', 'general_reaction',
+                                  'abcd_microbial', 'abcd_microbial_act_high', 'abcd_microbial_act_low'])
 def test_gold_time_stepped(name):
     """Kinetic side of the oracle (RTAccumulation, RKineticMineral, RTotalSorbKD, RUpdateKineticState and the
     accumulation/reaction Jacobian blocks) pinned to the reference's time-stepped gold files through the 1-cell
     global-implicit loop (tests/gi_driver.py): every printed value at the reference's own 1e-12, and the same number
-    of time steps and Newton iterations as the reference's SNES took (500/1000, 62/164, 2/2, 2/2)."""
+    of time steps and Newton iterations as the reference's SNES took (500/1000, 62/164, 2/2, 2/2).
+    abcd_microbial*: RMicrobial (Monod, inverse-Monod inhibition, biomass, Arrhenius factor), the immobile dof of the
+    accumulation and RImmobileDecay - regression_tests/default/batch/ABCD_microbial*.regression.gold, 111 steps / 222
+    Newton iterations under the reference's step-size controller."""
     import gi_driver
     w = synth.Workload(name)
     t, orc, st, xx, nit, cst = kat.initial_cell_from_fixture(w)
