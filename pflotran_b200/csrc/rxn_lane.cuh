@@ -9,14 +9,15 @@ namespace rxn {
 
 // shapes compiled into the library: X(N, CPB, G) = matrix dimension, resident cells per CTA, lanes per cell;
 // per N in order of preference - the first shape whose per-cell state fits in shared memory is used
-// (measured on B200, 300A chemistry: G = 2 > G = 1 > G = 4; keep in sync with LANE_SHAPES in the Makefile)
+// (measured on B200, 300A chemistry: G = 2 > G = 1 > G = 4; the 22-primary / 164-complex ascem chemistry holds only 16 cells
+// per SM, where more lanes per cell win: G = 8 > 4 > 2 and 16 no better, profiles/r02_ab_ascem_g*.json, r02_ad_ascem_*.json; keep in sync with LANE_SHAPES in the Makefile)
 #define RXN_LANE_SHAPES(X) \
   X(4, 448, 1) X(4, 256, 1) X(4, 128, 1) \
   X(8, 192, 1) X(8, 128, 1) X(8, 64, 1) \
   X(12, 96, 2) X(12, 64, 2) X(12, 64, 1) X(12, 64, 4) \
   X(15, 64, 2) X(15, 60, 2) X(15, 48, 2) X(15, 64, 4) X(15, 64, 1) \
   X(16, 64, 2) X(16, 48, 2) \
-  X(24, 32, 2) X(24, 28, 2) X(24, 24, 2) X(24, 16, 2) X(24, 28, 4) X(24, 28, 1)
+  X(24, 32, 2) X(24, 28, 2) X(24, 24, 2) X(24, 20, 8) X(24, 16, 8) X(24, 16, 2) X(24, 28, 4) X(24, 28, 1)
 
 // tensor-memory kernel shapes (rxn_tm_dev.cuh): X(N, QUADS, G) = matrix dimension (<= 15), 32-cell quads per CTA, member warps
 // per cell; per N the first shape whose vectors fit in shared memory is used (keep in sync with TM_SHAPES in the Makefile)

@@ -183,6 +183,7 @@ template <int N>
 static void lane_gi_cells_g(const LaneGiJob &J, int G) {
   if (G == 1) lane_gi_cells<N, 1>(J);
   else if (G == 2) lane_gi_cells<N, 2>(J);
+  else if (G == 8) { if constexpr (N == 24) lane_gi_cells<N, 8>(J); }      // the library's 24_20_8 / 24_16_8 shapes
   else lane_gi_cells<N, 4>(J);
 }
 
@@ -190,6 +191,7 @@ template <int N>
 static void lane_cells_g(const LaneJob &J, int G) {
   if (G == 1) lane_cells<N, 1>(J);
   else if (G == 2) lane_cells<N, 2>(J);
+  else if (G == 8) { if constexpr (N == 24) lane_cells<N, 8>(J); }
   else lane_cells<N, 4>(J);
 }
 
@@ -424,7 +426,7 @@ int emu_react_lane(void *hh, const HostView *v, double *tran_xx, const uint8_t *
   LanePlan P;
   const int N = forceN >= e->R.h.naq ? forceN : lane_N_for(e->R.h.naq);
   if (N == 0) { if (err) snprintf(err, errlen, "naq exceeds the compiled shapes"); return RXN_ERR_UNSUPPORTED; }
-  if (G != 1 && G != 2 && G != 4) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4"); return RXN_ERR_INVALID; }
+  if (G != 1 && G != 2 && G != 4 && !(G == 8 && N == 24)) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4 (8 with N = 24)"); return RXN_ERR_INVALID; }
   int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P);
   if (rc != RXN_OK || !P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
   if (stats) {
@@ -451,7 +453,7 @@ int emu_gi_lane(void *hh, const HostView *v, const uint8_t *active, const int32_
   LanePlan P;
   const int N = lane_N_for(e->R.h.naq);
   if (N == 0) { if (err) snprintf(err, errlen, "naq exceeds the compiled shapes"); return RXN_ERR_UNSUPPORTED; }
-  if (G != 1 && G != 2 && G != 4) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4"); return RXN_ERR_INVALID; }
+  if (G != 1 && G != 2 && G != 4 && !(G == 8 && N == 24)) { if (err) snprintf(err, errlen, "G must be 1, 2 or 4 (8 with N = 24)"); return RXN_ERR_INVALID; }
   int rc = lane_plan_build(e->R.h, e->R.P.d, e->R.P.i, N, 1, (size_t)1 << 30, &P, true);
   if (rc != RXN_OK || !P.usable) { if (err) snprintf(err, errlen, "%s", P.err.c_str()); return RXN_ERR_UNSUPPORTED; }
   LaneGiJob J{&P, e, &S, l2g, nlocal, dt, res_out, jac_out};

@@ -120,7 +120,7 @@ def test_resident_lane_iteration_cap_and_inactive(G):
     assert_state_close(st_e, st_o, cells=act, what='capped', tables=w.tables)
 
 
-@pytest.mark.parametrize('name,N,G', [('hanford300a_eq', 16, 2), ('hanford300a_eq', 24, 4), ('calcite', 8, 1), ('calcite', 12, 2)])
+@pytest.mark.parametrize('name,N,G', [('hanford300a_eq', 16, 2), ('hanford300a_eq', 24, 4), ('hanford300a_eq', 24, 8), ('calcite', 8, 1), ('calcite', 12, 2)])
 def test_resident_lane_padded_shapes(name, N, G):
     """naq smaller than the compiled matrix dimension: the padding rows (m = 1, zero residual, decoupled) must not change
     anything - iteration counts, flags and values as with the exact shape."""
@@ -176,8 +176,8 @@ def test_global_implicit_entry_points(name):
     assert_state_close(st_e, st_o, what=name + ' kinetic state', tables=w.tables, kinetic_dt=1800.0)
 
 
-@pytest.mark.parametrize('name', ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'surface_complexation'])
-@pytest.mark.parametrize('G', [1, 2, 4])
+@pytest.mark.parametrize('name,G', [(n, g) for n in ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'surface_complexation']
+                                    for g in [1, 2, 4]] + [('ascem', 8)])     # ascem: the library's N = 24, 8-lanes-per-cell shape
 def test_global_implicit_blocks_resident_lane(name, G):
     """Residual / Jacobian blocks through the resident-lane routines (lane_gi_cell: ln-m Jacobian divided by m_j on the
     way out, activity coefficients taken from the state) against the oracle, including the state side effects."""
