@@ -340,7 +340,12 @@ int rxn_set_cell_scalars(RxnState *s, const double *den_kg, const double *sat, c
 /* replaces: the RTReact cell loop (reactive_transport.F90:1697-1724) = RReact per cell
  * (reaction.F90:3322-3511).  tran_xx: AoS nlocal x ncomp, in: transported totals [mol/L],
  * out: free-ion molalities.  l2g: ghosted (state) index of local cell i, 0-based, or NULL
- * for identity.  iters_out/flags_out: int32[nlocal] or NULL. */
+ * for identity.  iters_out/flags_out: int32[nlocal] or NULL.
+ * Immobile dofs (ncomp > naqcomp): columns naqcomp.. of a row hold the immobile concentrations [mol/m^3 bulk], in and out.  Two
+ * deviations from the reference's (untested) RReact there: the immobile values are written back to the cell's own row
+ * (reactive_transport.F90:1712-1716 drops the cell offset), and with LOG_FORMULATION the immobile columns of the Newton matrix
+ * are scaled by the immobile concentrations (reaction.F90:3445 hands RSolve pri_molal(naqcomp) as conc(ncomp)).  The
+ * global-implicit entry points below have no deviation (pinned by the ABCD_microbial gold files). */
 int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nlocal, double dt,
                     int dt_mode, int32_t *iters_out, int32_t *flags_out);
 /* same, with tran_xx / iters / flags already resident on the state's device (no PCIe). */

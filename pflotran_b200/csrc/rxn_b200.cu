@@ -515,7 +515,11 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
   const RxnTables *t = s->t;
   const bool lane = t->lane.plan.usable && !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ] &&
                     (s->react_kernel == 0 || s->react_kernel == 3);
-  if (lane && nlocal >= 262144 && !getenv("RXN_NO_PIPELINE")) {
+  // chemistries on the N = 24 shapes (more than 16 primaries) are not chunked: a launch ends with the tail of its slowest cells
+  // (ascem: damped redox cells with thousands of Newton iterations, 81 % of a 100 000-cell launch,
+  // profiles/r02_ac2_ascem_lane_g8.metrics.txt), every chunk would pay it again, and the copies are 2 % of the kernel time
+  const bool tail_bound = !t->lane.plan_tm.usable && t->h.naq > 16;
+  if (lane && nlocal >= 262144 && !tail_bound && !getenv("RXN_NO_PIPELINE")) {
     // resident-lane kernel on a large batch: NCHUNK chunks; chunk c+1 crosses PCIe while chunk c is solved and chunk
     // c-1 returns (full duplex), so the host-buffer call costs about the kernel time
     if (!s->h2d) {
