@@ -38,13 +38,15 @@ from pflotran_b200 import abi, synth  # noqa: E402
 METRIC = 'reaction cell-updates/sec'
 UNIT = 'cell-updates/s'
 DEFAULT_CELLS = {'hanford300a_eq': 10_000_000, 'hanford300a_mr': 5_000_000, 'calcite': 1_000_000,
-                 'hpt_calcite': 1_000_000, 'ascem': 1_000_000}
+                 'hpt_calcite': 1_000_000, 'ascem': 1_000_000, 'scco2_brine': 1_000_000}
 WORKLOAD_DESC = {
     'hanford300a_eq': 'hanford/300A U(VI) chemistry (15 primaries, 88 complexes, 2 kinetic minerals, equilibrium surface '
                       'complexation; deck regression_tests/default/543/543_hanford_srfcplx_base.in), synthetic grid',
     'hanford300a_mr': '300A chemistry with 50-rate multirate surface complexation (543_hanford_srfcplx_mr.in)',
     'calcite': 'example_problems/100_100_100 calcite chemistry (4 primaries, 5 complexes, 1 kinetic mineral)',
     'hpt_calcite': 'geothermal-hpt.dat calcite chemistry, per-cell T,P dependent logK',
+    'scco2_brine': 'aqueous chemistry of the MPHASE CO2 deck regression_tests/default/scco2/mphase/mphase_chem.in (8 primaries with CO2(aq) in the '
+                   'basis, 12 complexes, kinetic quartz + calcite, 1 molal NaCl brine), without the supercritical phase',
     'ascem': 'example_problems/ascem_chemistry (BASELINE config 1: 22 primaries, 164 complexes, calcite kinetics; database savannah_river.dat)',
 }
 # DRAM bytes per cell-update of the react kernel: a CONSTANT taken from the committed `ncu --set full` capture of the named kernel
@@ -208,7 +210,8 @@ def run_reference(args):
 # (:2545-2586, 2735-2758, 3342-3389, 3445-3465) for every cell.
 GI_METRIC = 'global-implicit reaction residual+Jacobian blocks/sec'
 GI_UNIT = 'cell-blocks/s'
-GI_DEFAULT_CELLS = {'hpt_calcite': 4_000_000, 'calcite': 4_000_000, 'hanford300a_eq': 1_000_000, 'hanford300a_mr': 500_000, 'ascem': 500_000}
+GI_DEFAULT_CELLS = {'hpt_calcite': 4_000_000, 'calcite': 4_000_000, 'hanford300a_eq': 1_000_000, 'hanford300a_mr': 500_000, 'ascem': 500_000,
+                    'scco2_brine': 2_000_000}
 
 
 def gi_work_model(t):

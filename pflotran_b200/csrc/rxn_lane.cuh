@@ -10,7 +10,8 @@ namespace rxn {
 // shapes compiled into the library: X(N, CPB, G) = matrix dimension, resident cells per CTA, lanes per cell;
 // per N in order of preference - the first shape whose per-cell state fits in shared memory is used
 // (measured on B200, 300A chemistry: G = 2 > G = 1 > G = 4; the 22-primary / 164-complex ascem chemistry holds only 16 cells
-// per SM, where more lanes per cell win: G = 8 > 4 > 2 and 16 no better, profiles/r02_ab_ascem_g*.json, r02_ad_ascem_*.json; keep in sync with LANE_SHAPES in the Makefile)
+// per SM, where more lanes per cell win (for N = 8, 192 cells per SM, they lose: G = 1 / 2 / 4 = 172 / 161 / 117 M cell-updates/s on the
+// scco2_brine chemistry, profiles/r02_ag_*.json): G = 8 > 4 > 2 and 16 no better, profiles/r02_ab_ascem_g*.json, r02_ad_ascem_*.json; keep in sync with LANE_SHAPES in the Makefile)
 #define RXN_LANE_SHAPES(X) \
   X(4, 448, 1) X(4, 256, 1) X(4, 128, 1) \
   X(8, 192, 1) X(8, 128, 1) X(8, 64, 1) \

@@ -108,6 +108,11 @@ VARIANTS = {
                            [('      MINERAL Calcite\n', '      KINETIC\n      COMPLEX_KINETICS\n        >SOUO2OH\n          FORWARD_RATE_CONSTANT 2.d-3\n'
                              '          BACKWARD_RATE_CONSTANT 1.d-4\n        /\n        >SOHUO2CO3\n          FORWARD_RATE_CONSTANT 5.d-2\n'
                              '          BACKWARD_RATE_CONSTANT 2.d-4\n        /\n      /\n      MINERAL Calcite\n')]),
+    # BASELINE config 4's "CO2 style high-ionic-strength chemistry": the aqueous chemistry of the reference's MPHASE CO2 deck
+    # (8 primaries with CO2(aq) swapped into the basis, 12 complexes, kinetic quartz + calcite, 1 molal NaCl brine) without its
+    # ACTIVE_GAS_SPECIES card - the supercritical phase (RTotalCO2, reaction_gas.F90:172-296) is outside the path
+    'scco2_brine': ('regression_tests/default/scco2/mphase/mphase_chem.in', 'initial',
+                    [('  ACTIVE_GAS_SPECIES\n    CO2(g)\n    O2(g)\n  /\n', '')]),
     'calcite_rate_laws': ('regression_tests/ascem/batch/calcite-kinetics.in', 'initial',
                           [('      RATE_CONSTANT 1.d-13 mol/cm^2-sec\n',
                             '      RATE_CONSTANT 1.d-13 mol/cm^2-sec\n      ACTIVATION_ENERGY 40.d0\n      AFFINITY_THRESHOLD 1.d-3\n'

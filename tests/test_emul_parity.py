@@ -19,7 +19,7 @@ WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_
 # reactions, radioactive decay, kinetic surface complexation, microbial reactions (Monod / inverse-Monod terms, biomass as an
 # immobile dof, Arrhenius factor) with immobile decay, and a microbial reaction without biomass in the linear formulation
 BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf',
-                    'abcd_microbial', 'abcd_microbial_act_high', 'ab_microbial_linear']
+                    'abcd_microbial', 'abcd_microbial_act_high', 'ab_microbial_linear', 'scco2_brine']
 WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
 GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 
@@ -41,7 +41,7 @@ def test_react(name, dt, mode):
     assert_state_close(st_e, st_o, cells=good, what=name)
 
 
-LANE_WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'surface_complexation', 'calcite_kinetics']
+LANE_WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'surface_complexation', 'calcite_kinetics', 'scco2_brine']
 
 
 @pytest.mark.parametrize('name', LANE_WORKLOADS)
