@@ -804,6 +804,38 @@ int rxn_equilibrate_constraint_batch(RxnState *s, const int32_t *constraint_type
   return RXN_OK;
 }
 
+// Multirate sorbed totals of RUpdateKineticState (reaction.F90:5394-5408): S_r <- (S_r + k_r dt f_r S_eq) / (1 + k_r dt) for every rate r
+// and component i - 2 x nrate x naq doubles of HBM traffic per cell and one quotient per element, no other state.  One thread
+// per (cell, component) walks the rates, cells fastest: every load and store is a full 128-byte line of one row of the SoA field,
+// S_eq is read once, and the loads of 4 rates are in flight before the first quotient.  The thread-per-cell kernel (which kept
+// the whole cell context in local memory for the mineral rates) ran this loop at 39 % of the HBM peak (profiles/r02_q_kinstate_mr.json).
+__global__ void __launch_bounds__(256)
+k_kinmr_update(DevState S, const double *__restrict__ rate, const double *__restrict__ frac, int naq, int nrate, long long row0, double dt) {
+  const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (cell >= S.ncells || (S.active && !S.active[cell])) return;
+  double *f = S.f[RXN_F_KINMR_TOTAL_SORB];
+  const double S0 = f[(row0 + i) * S.ld + cell];
+  int r = 0;
+  for (; r + 4 <= nrate; r += 4) {
+    double *p[4], v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { p[u] = f + (row0 + (long long)(r + u + 1) * naq + i) * S.ld + cell; v[u] = *p[u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double kdt = rate[r + u] * dt;
+      const double one_plus_kdt = 1.0 + kdt;
+      *p[u] = (v[u] + kdt * frac[r + u] * S0) / one_plus_kdt;
+    }
+  }
+  for (; r < nrate; ++r) {
+    double *p = f + (row0 + (long long)(r + 1) * naq + i) * S.ld + cell;
+    const double kdt = rate[r] * dt;
+    const double one_plus_kdt = 1.0 + kdt;
+    *p = (*p + kdt * frac[r] * S0) / one_plus_kdt;
+  }
+}
+
 int rxn_update_kinetic_state_batch(RxnState *s, double dt) {
   Nvtx nvtx_("RTUpdateKineticState");
   if (!s || !(dt > 0.0)) return fail(RXN_ERR_INVALID, "bad argument");
@@ -813,7 +845,20 @@ int rxn_update_kinetic_state_batch(RxnState *s, double dt) {
   CU(cudaEventRecord(s->ev0, s->stream));
   const int threads = 128;
   const LaunchCfg L{nblocks(s->ncells, threads), threads, t->blob_bytes, s->stream};
-  RXN_DISPATCH(t->nvariant, run_update_kinetic_state, L, t->h, (const double *)t->d_blob, s->S, dt);
+  const bool stream_mr = t->h.nmr > 0 && !getenv("RXN_KINMR_PER_CELL");
+  if (t->h.nkin > 0 || t->h.nkinrxn > 0 || !stream_mr)       // mineral volume fractions, kinetic surface complexes (and the flags of their cells)
+    RXN_DISPATCH(t->nvariant, run_update_kinetic_state, L, t->h, (const double *)t->d_blob, s->S, dt, stream_mr ? 1 : 0);
+  if (stream_mr) {
+    const double *bd = (const double *)t->d_blob;
+    for (int ikr = 0; ikr < t->h.nmr; ++ikr) {
+      const int nrate = t->lane.mr_nrate[ikr];
+      if (nrate <= 0) continue;
+      const dim3 grid(nblocks(s->ncells, 256), (unsigned)t->h.naq);
+      k_kinmr_update<<<grid, 256, 0, s->stream>>>(s->S, bd + t->h.o_mr_rate + (size_t)ikr * t->h.mr_ld, bd + t->h.o_mr_frac + (size_t)ikr * t->h.mr_ld,
+                                                  t->h.naq, nrate, (long long)ikr * (t->h.mr_ld + 1) * t->h.naq, dt);
+      ++g_launches;
+    }
+  }
   { const int rcl = check_launch(s, true); if (rcl != RXN_OK) return rcl; }
   return end_cell_flags(s, "RTUpdateKineticState");
 }

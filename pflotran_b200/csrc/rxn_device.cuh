@@ -1269,8 +1269,9 @@ __device__ void cell_residual_jacobian(const Tab &T, const DevState &S, long lon
 }
 
 // RTUpdateKineticState loop (reactive_transport.F90:692-705) = RUpdateKineticState (reaction.F90:5320-5429)
+// skip_mr: the multirate sorbed totals are advanced by the streaming kernel k_kinmr_update (rxn_b200.cu) instead
 template <int N>
-__device__ void cell_update_kinetic_state(const Tab &T, const DevState &S, long long cell, double dt) {
+__device__ void cell_update_kinetic_state(const Tab &T, const DevState &S, long long cell, double dt, bool skip_mr = false) {
   if (S.active && !S.active[cell]) return;
   const DevTab &tab = *T.h;
   Cell<N> c;
@@ -1288,7 +1289,7 @@ __device__ void cell_update_kinetic_state(const Tab &T, const DevState &S, long 
       G(S, RXN_F_MNRL_VOLFRAC, im, cell) = vf;
     }
   }
-  for (int ikr = 0; ikr < tab.nmr; ++ikr) {                                    // :5394-5408
+  for (int ikr = 0; ikr < (skip_mr ? 0 : tab.nmr); ++ikr) {                    // :5394-5408
     const int nrate = T.i[tab.o_mr_nrate + ikr];
     const long long blk = (long long)ikr * (tab.mr_ld + 1) * n;
     for (int irate = 0; irate < nrate; ++irate) {

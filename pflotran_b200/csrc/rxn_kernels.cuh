@@ -24,7 +24,7 @@ template <int N> void run_fixed_accum(LaunchCfg L, const DevTab &tab, const doub
                                       const int *l2g, long long nlocal, double *accum_out);
 template <int N> void run_residual_jacobian(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S,
                                             const int *l2g, long long nlocal, double dt, double *res_out, double *jac_out);
-template <int N> void run_update_kinetic_state(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S, double dt);
+template <int N> void run_update_kinetic_state(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S, double dt, int skip_mr);
 
 template <int N> void run_equilibrate(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S, const int *ctype,
                                       const double *conc, long long conc_stride, const int *cid, const double *guess, int use_prev,

@@ -60,10 +60,10 @@ k_residual_jacobian(const __grid_constant__ DevTab tab, const double *__restrict
 
 template <int N>
 __global__ void __launch_bounds__(128)
-k_update_kinetic_state(const __grid_constant__ DevTab tab, const double *__restrict__ blob, DevState S, double dt) {
+k_update_kinetic_state(const __grid_constant__ DevTab tab, const double *__restrict__ blob, DevState S, double dt, int skip_mr) {
   Tab T = stage_tables(tab, blob);
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell < S.ncells) cell_update_kinetic_state<N>(T, S, cell, dt);
+  if (cell < S.ncells) cell_update_kinetic_state<N>(T, S, cell, dt, skip_mr != 0);
 }
 
 // ReactionEquilibrateConstraint applied cell by cell (reaction.F90:1308-2046; condition_control.F90:725-741)
@@ -113,9 +113,9 @@ template <> void run_residual_jacobian<RXN_N>(LaunchCfg L, const DevTab &tab, co
   set_smem(k_residual_jacobian<RXN_N>, L.smem);
   k_residual_jacobian<RXN_N><<<L.grid, L.block, L.smem, L.stream>>>(tab, blob, S, l2g, nlocal, dt, res_out, jac_out);
 }
-template <> void run_update_kinetic_state<RXN_N>(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S, double dt) {
+template <> void run_update_kinetic_state<RXN_N>(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S, double dt, int skip_mr) {
   set_smem(k_update_kinetic_state<RXN_N>, L.smem);
-  k_update_kinetic_state<RXN_N><<<L.grid, L.block, L.smem, L.stream>>>(tab, blob, S, dt);
+  k_update_kinetic_state<RXN_N><<<L.grid, L.block, L.smem, L.stream>>>(tab, blob, S, dt, skip_mr);
 }
 
 template <> void run_equilibrate<RXN_N>(LaunchCfg L, const DevTab &tab, const double *blob, const DevState &S, const int *ctype,

@@ -113,6 +113,12 @@ VARIANTS = {
     # ACTIVE_GAS_SPECIES card - the supercritical phase (RTotalCO2, reaction_gas.F90:172-296) is outside the path
     'scco2_brine': ('regression_tests/default/scco2/mphase/mphase_chem.in', 'initial',
                     [('  ACTIVE_GAS_SPECIES\n    CO2(g)\n    O2(g)\n  /\n', '')]),
+    # RMicrobial's other inhibition branches (reaction_microbial.F90:322-339, 393-412): THRESHOLD (atan) and MONOD next to the deck's
+    # INVERSE_MONOD term
+    'abcd_microbial_inhibition': ('regression_tests/default/batch/ABCD_microbial.in', 'initial',
+                                  [('    BIOMASS\n      SPECIES_NAME D(im)', '    INHIBITION\n      SPECIES_NAME B(aq)\n      TYPE THRESHOLD 1.d5\n'
+                                    '      INHIBITION_CONSTANT 9.d-4\n    /\n    INHIBITION\n      SPECIES_NAME A(aq)\n      TYPE MONOD\n'
+                                    '      INHIBITION_CONSTANT 1.d-3\n    /\n    BIOMASS\n      SPECIES_NAME D(im)')]),
     'calcite_rate_laws': ('regression_tests/ascem/batch/calcite-kinetics.in', 'initial',
                           [('      RATE_CONSTANT 1.d-13 mol/cm^2-sec\n',
                             '      RATE_CONSTANT 1.d-13 mol/cm^2-sec\n      ACTIVATION_ENERGY 40.d0\n      AFFINITY_THRESHOLD 1.d-3\n'

@@ -19,7 +19,7 @@ WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_
 # reactions, radioactive decay, kinetic surface complexation, microbial reactions (Monod / inverse-Monod terms, biomass as an
 # immobile dof, Arrhenius factor) with immobile decay, and a microbial reaction without biomass in the linear formulation
 BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf',
-                    'abcd_microbial', 'abcd_microbial_act_high', 'ab_microbial_linear', 'scco2_brine']
+                    'abcd_microbial', 'abcd_microbial_act_high', 'ab_microbial_linear', 'scco2_brine', 'abcd_microbial_inhibition']
 WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
 GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 

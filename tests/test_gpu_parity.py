@@ -18,7 +18,7 @@ WORKLOADS = ['calcite', 'hanford300a_eq', 'hanford300a_mr', 'hpt_calcite', 'ion_
 # prefactors, 5-term logK fit per cell, BASELINE config 1 (22 primaries / 164 complexes), general (forward / backward rate)
 # reactions, radioactive decay, kinetic surface complexation
 BRANCH_WORKLOADS = ['hanford300a_act_newton', 'hanford300a_stoich', 'kd_langmuir', 'kd_freundlich', 'calcite_rate_laws', 'mineral_prefactor', 'calcite_fit5', 'ascem', 'general_reaction', 'decay_ab', 'hanford300a_kinsrf',
-                    'abcd_microbial', 'abcd_microbial_act_high', 'ab_microbial_linear', 'scco2_brine']   # RMicrobial, immobile dofs, RImmobileDecay
+                    'abcd_microbial', 'abcd_microbial_act_high', 'ab_microbial_linear', 'scco2_brine', 'abcd_microbial_inhibition']   # RMicrobial, immobile dofs, RImmobileDecay
 WORKLOADS = WORKLOADS + BRANCH_WORKLOADS
 GI_WORKLOADS = ['calcite', 'hanford300a_mr', 'hpt_calcite', 'ion_exchange', 'surface_complexation'] + BRANCH_WORKLOADS
 
