@@ -2,7 +2,7 @@
 small enough for the tools' slowdown, large enough that persistent lanes take several cells from the work counter
 (k_react_tm: 148 CTAs x 128 cells = 18 944 resident cells).  No oracle, no timing: the tools' reports are the result.
 
-  compute-sanitizer --tool racecheck python profiles/sanitize_run.py [react|gi|flux|all] [ncells]
+  compute-sanitizer --tool racecheck python profiles/sanitize_run.py [react|gi|flux|new|all] [ncells]
 """
 import os
 import sys
@@ -94,4 +94,23 @@ if what in ('flux', 'all'):
     print('coupler %d boundary faces, %d wells, |res| max %.3e' % (len(bc['id_dn']), len(ss['id_dn']), np.abs(r).max()))
     bs.close(); sk.close()
     cs.close()
+if what in ('new', 'all'):
+    # kernels added late in round 2: resident-lane N = 24 with 8 lanes per cell (ascem), thread-per-cell microbial reactions with an
+    # immobile dof (RReact and the global-implicit loops), the streaming multirate update k_kinmr_update
+    react('ascem', max(2000, ncells // 20))
+    react('abcd_microbial', ncells // 4, 1)
+    for name in ('abcd_microbial', 'hanford300a_mr'):
+        w = synth.Workload(name)
+        n = ncells // 4
+        cells = synth.make_cells(w, 0, n)
+        st = synth.host_state(w, cells)
+        rx = rt.Reaction(w.tables)
+        rz = rt.Realization(rx, n)
+        rz.upload_host_state(st)
+        xx = np.ascontiguousarray(np.tile(w.base_solution() * 1.03, (n, 1)))
+        rz.RTUpdateAuxVars(xx, True)
+        acc = rz.RTUpdateFixedAccumulation(xx)
+        res, jac = rz.RTResidualJacobianNonFlux(3600.0)
+        rz.RTUpdateKineticState(3600.0)
+        print('new   %-16s %6d cells  |res| max %.3e  blocks %s' % (name, n, np.abs(res).max(), jac.shape))
 print('sanitize_run done')
