@@ -5,6 +5,7 @@
 // There is NO CPU fallback: without a usable CUDA device every entry point fails with
 // RXN_ERR_NO_DEVICE / RXN_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>   // work order of the resident-lane kernel (react_order)
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3 (dlopens the tool's injection library; a no-op without a profiler)
 
 #include <algorithm>
@@ -87,6 +88,12 @@ struct RxnState {
   int flux_rows = 0;       // RXN_FLUX_ROWS=1: N = 15 flux Jacobian by block rows (k_flux_jacobian_t) instead of block columns
   int gi_kernel = 0;       // global-implicit loops (RXN_GI_KERNEL): 0 auto (tensor-memory layout, else resident lanes, else thread per cell), 1 thread per cell, 2 resident lanes
   unsigned int *d_fail = nullptr;   // OR of the cell flags of the running global-implicit launch (DevState::fail)
+  // work order of the resident-lane RReact kernel for tail-bound chemistries (react_order): items sorted by the Newton iteration
+  // count of the previous call, slowest first
+  int32_t *d_prev_it = nullptr, *d_keys = nullptr, *d_iota = nullptr, *d_order = nullptr;
+  void *d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  long long order_cap = 0, prev_n = 0;     // allocated items; items of the remembered iteration counts (0: none)
 };
 
 // Row view of a connection list + the flux coefficients of the current flow field (rxn_flux.h)
@@ -324,6 +331,8 @@ int rxn_state_destroy(RxnState *s) {
   if (s->d_active) cudaFree(s->d_active);
   if (s->d_counter) cudaFree(s->d_counter);
   if (s->d_fail) cudaFree(s->d_fail);
+  for (int32_t *p : {s->d_prev_it, s->d_keys, s->d_iota, s->d_order}) if (p) cudaFree(p);
+  if (s->d_sort_tmp) cudaFree(s->d_sort_tmp);
   if (s->h2d) cudaStreamDestroy(s->h2d);
   if (s->d2h) cudaStreamDestroy(s->d2h);
   for (int c = 0; c < RxnState::NCHUNK; ++c) {
@@ -444,12 +453,54 @@ int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
              t->lane.plan_tm.lt.N, t->lane.plan_tm.lt.CPB, t->lane.G_tm, 128 * t->lane.G_tm, t->lane.plan_tm.smem_bytes,
              t->lane.plan_tm.blob.size(), t->lane.plan_tm.terms_spec, t->lane.plan_tm.terms_A, t->lane.plan_tm.terms_B);
   else if (lane_ok && (s->react_kernel == 0 || s->react_kernel == 3))
-    snprintf(buf, (size_t)len, "resident-lane N=%d cells/CTA=%d lanes/cell=%d threads=%d smem=%zu B plan=%zu B (spec %d, planA %d, planB %d terms)",
+    snprintf(buf, (size_t)len, "resident-lane N=%d cells/CTA=%d lanes/cell=%d threads=%d smem=%zu B plan=%zu B (spec %d, planA %d, planB %d terms)%s",
              t->lane.plan.lt.N, t->lane.plan.lt.CPB, t->lane.G, ((t->lane.plan.lt.CPB * t->lane.G + 31) / 32) * 32, t->lane.plan.smem_bytes,
-             t->lane.plan.blob.size(), t->lane.plan.terms_spec, t->lane.plan.terms_A, t->lane.plan.terms_B);
+             t->lane.plan.blob.size(), t->lane.plan.terms_spec, t->lane.plan.terms_A, t->lane.plan.terms_B,
+             !t->lane.plan_tm.usable && t->h.naq > 16 && !getenv("RXN_NO_REACT_ORDER") ? " work order: previous call's iteration counts, slowest first" : "");
   else
     snprintf(buf, (size_t)len, "thread-per-cell N<=%d (lane: %s)", t->nvariant,
              t->lane.plan.usable ? "DTOTAL materialised" : t->lane.plan.err.c_str());
+  return RXN_OK;
+}
+
+// Chemistries whose launches end with a tail of slow cells (tail_bound_tables): a cell that needed thousands of damped Newton
+// iterations in one transport step needs them in the next one too, so the lanes take the batch in the order of the previous
+// call's iteration counts, slowest first - the long cells start while the SMs are full and the launch ends when the work does
+// (longest-processing-time-first on the persistent lanes).  A stable 14-bit radix sort (cub) keeps cells with equal counts in
+// index order, so neighbouring lanes still share DRAM sectors.  Results do not depend on the order (cells are independent).
+__global__ void k_iota(int32_t *p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+static bool tail_bound_tables(const RxnTables *t) { return !t->lane.plan_tm.usable && t->h.naq > 16; }
+static int react_order(RxnState *s, int64_t nlocal, const int32_t **order) {
+  *order = nullptr;
+  if (s->prev_n != nlocal || getenv("RXN_NO_REACT_ORDER")) return RXN_OK;
+  size_t need = 0;
+  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, s->d_prev_it, s->d_keys, s->d_iota, s->d_order, (int)nlocal, 0, 14, s->stream));
+  if (need > s->sort_tmp_bytes) {
+    if (s->d_sort_tmp) CU(cudaFree(s->d_sort_tmp));
+    s->d_sort_tmp = nullptr; s->sort_tmp_bytes = 0;
+    CU(cudaMalloc(&s->d_sort_tmp, need));
+    s->sort_tmp_bytes = need;
+  }
+  k_iota<<<nblocks(nlocal, 256), 256, 0, s->stream>>>(s->d_iota, nlocal);
+  CU(cub::DeviceRadixSort::SortPairsDescending(s->d_sort_tmp, need, s->d_prev_it, s->d_keys, s->d_iota, s->d_order, (int)nlocal, 0, 14, s->stream));
+  g_launches += 2;
+  *order = s->d_order;
+  return RXN_OK;
+}
+static int react_remember(RxnState *s, int64_t nlocal, const int32_t *d_iters) {
+  s->prev_n = 0;
+  if (!d_iters || nlocal > 0x7fffffffLL) return RXN_OK;
+  if (nlocal > s->order_cap) {
+    for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) { if (*p) CU(cudaFree(*p)); *p = nullptr; }
+    s->order_cap = 0;
+    for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) CU(cudaMalloc(p, (size_t)nlocal * 4));
+    s->order_cap = nlocal;
+  }
+  CU(cudaMemcpyAsync(s->d_prev_it, d_iters, (size_t)nlocal * 4, cudaMemcpyDeviceToDevice, s->stream));
+  s->prev_n = nlocal;
   return RXN_OK;
 }
 
@@ -465,7 +516,11 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
   const bool use_lane = lane_ok && (s->react_kernel == 0 || s->react_kernel == 3);
   if (use_lane) {
     if (!s->d_counter) CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
-    int rc = lane_launch_react(t->lane, t->h, t->d_blob, s->S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->d_counter, s->stream, cell0);
+    DevState S = s->S;
+    const bool ordered = tail_bound_tables(t) && cell0 == 0;
+    if (ordered) { const int rco = react_order(s, nlocal, &S.order); if (rco != RXN_OK) return rco; }
+    int rc = lane_launch_react(t->lane, t->h, t->d_blob, S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->d_counter, s->stream, cell0);
+    if (rc == RXN_OK && ordered) { const int rcr = react_remember(s, nlocal, d_iters); if (rcr != RXN_OK) return rcr; }
     if (rc != RXN_OK) return fail(rc, "resident-lane kernel launch failed (N=%d CPB=%d): %s", t->lane.plan.lt.N, t->lane.plan.lt.CPB,
                                   cudaGetErrorString(cudaGetLastError()));
     ++g_launches;
@@ -518,7 +573,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
   // chemistries on the N = 24 shapes (more than 16 primaries) are not chunked: a launch ends with the tail of its slowest cells
   // (ascem: damped redox cells with thousands of Newton iterations, 81 % of a 100 000-cell launch,
   // profiles/r02_ac2_ascem_lane_g8.metrics.txt), every chunk would pay it again, and the copies are 2 % of the kernel time
-  const bool tail_bound = !t->lane.plan_tm.usable && t->h.naq > 16;
+  const bool tail_bound = tail_bound_tables(t);
   if (lane && nlocal >= 262144 && !tail_bound && !getenv("RXN_NO_PIPELINE")) {
     // resident-lane kernel on a large batch: NCHUNK chunks; chunk c+1 crosses PCIe while chunk c is solved and chunk
     // c-1 returns (full duplex), so the host-buffer call costs about the kernel time

@@ -59,10 +59,11 @@ k_react_lane(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab 
       if (ln == leader) base = atomicAdd(counter, (unsigned long long)__popc(wm));
       base = __shfl_sync(0xffffffffu, base, leader);
       if (want) {
-        const long long i = (long long)base + __popc(wm & below);
+        long long i = (long long)base + __popc(wm & below);
         if (i >= nlocal) {
           exhausted = true;
         } else {
+          if (S.order) i = S.order[i];                         // slowest cells of the previous call first (rxn_b200.cu: react_order)
           const long long cell = l2g ? l2g[i] : i + cell0;    // cell0: first cell of this chunk of the batch
           if (S.active && !S.active[cell]) {                   // imat <= 0 (reactive_transport.F90:1699)
             if (l == 0) {

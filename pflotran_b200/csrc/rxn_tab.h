@@ -72,6 +72,7 @@ struct DevState {
   long long ncells;
   const uint8_t *active;   // NULL = all active
   unsigned int *fail;      // OR of the RXN_FLAG_* raised by the cells of a global-implicit launch (NULL: not collected)
+  const int32_t *order = nullptr;   // resident-lane RReact: the work counter's n-th item is batch item order[n] (NULL: identity)
 };
 
 // hard limits of the per-thread scratch (tables beyond them are rejected at create time)

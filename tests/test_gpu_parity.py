@@ -619,3 +619,42 @@ def test_global_implicit_device_resident_entry_points():
     np.testing.assert_array_equal(rz2.download('TOTAL'), rz.download('TOTAL'))
     for p in (d_xx, d_res, d_jac):
         rz2.device_free(p)
+
+
+def test_react_work_order_of_tail_bound_chemistries_is_bitwise_neutral():
+    """Chemistries on the N = 24 shapes (ascem: damped redox cells with thousands of Newton iterations) are handed to the lanes in
+    the order of the previous call's iteration counts, slowest first (rxn_b200.cu: react_order).  Cells are independent, so the
+    second (ordered) call must reproduce the first (unordered) one bit for bit - with and without a local-to-ghosted map."""
+    n = 6000
+    w, cells = workload_cells('ascem', n)
+    st0 = synth.host_state(w, cells)
+    rx = rt.Reaction(w.tables)
+    rz = rt.Realization(rx, n)
+    assert 'work order' in rz.react_kernel_info()
+    out = []
+    for call in range(3):
+        rz.upload_host_state(st0)
+        xx = cells['tran_xx'].copy()
+        it, fl = rz.RTReact(xx, 3600.0, abi.RXN_DT_CONSISTENT)
+        st = st0.copy()
+        rz.download_host_state(st)
+        out.append((xx, it.copy(), fl.copy(), st))
+    assert out[0][1].max() > 100                      # the tail the order is for
+    for k in (1, 2):
+        np.testing.assert_array_equal(out[k][0], out[0][0])
+        np.testing.assert_array_equal(out[k][1], out[0][1])
+        np.testing.assert_array_equal(out[k][2], out[0][2])
+        for f in ('PRI_MOLAL', 'TOTAL', 'SEC_MOLAL', 'MNRL_RATE'):
+            np.testing.assert_array_equal(out[k][3][f], out[0][3][f])
+    # local -> ghosted map: 2000 local cells at reversed ghosted slots, twice (the second call ordered)
+    l2g = np.arange(3999, 1999, -1, dtype=np.int32)
+    res = []
+    for call in range(2):
+        rz.upload_host_state(st0)
+        x2 = np.ascontiguousarray(cells['tran_xx'][l2g])
+        it2, fl2 = rz.RTReact(x2, 3600.0, abi.RXN_DT_CONSISTENT, l2g=l2g)
+        res.append((x2, it2.copy(), fl2.copy()))
+    np.testing.assert_array_equal(res[1][0], res[0][0])
+    np.testing.assert_array_equal(res[1][1], res[0][1])
+    np.testing.assert_array_equal(res[0][1], out[0][1][l2g])
+    np.testing.assert_array_equal(res[0][0], out[0][0][l2g])
