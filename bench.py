@@ -597,7 +597,12 @@ def run_ours(args):
                          'note': 'FP64 CUDA-core path: achieved = flop-equivalents (SURVEY.md 8d, W=20 per exp/log/sqrt/pow) x cells '
                                  '/ react-kernel time (CUDA events); peak = DFMA probe measured in this run (rxn_probe_fp64)',
                          'kernel_ms': kern_ms_max, 'flop_eq_per_cell': wm['flop_eq_per_cell'],
-                         'transcendentals_per_cell': wm['transcendentals_per_cell']},
+                         'transcendentals_per_cell': wm['transcendentals_per_cell'],
+                         # the probe's number beside the arithmetic one: SMs x 64 FP64 lanes x 2 flop x the maximum SM clock
+                         # (MEASURED_PEAKS.json has no FP64 entry; NVIDIA's nominal 40 TFLOP/s is this product at 2.1 GHz)
+                         'peak_theoretical': theoretical_fp64_tflops(local_rank, clocks),
+                         'frac_of_theoretical': (fp64_ach / theoretical_fp64_tflops(local_rank, clocks))
+                         if theoretical_fp64_tflops(local_rank, clocks) else None},
             'roofline_hbm': {'bound': 'hbm', 'achieved': hbm_ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                              'frac': hbm_ach / peaks['hbm_gbs'],
                              'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
@@ -617,6 +622,17 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def theoretical_fp64_tflops(device, clocks):
+    """SM count x 64 FP64 FMA lanes per SM x 2 flop x maximum SM clock (None when the clock could not be sampled)."""
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        mhz = clocks.get('sm_max_mhz')
+        return sms * 64 * 2 * mhz * 1e6 / 1e12 if mhz else None
+    except Exception:
+        return None
 
 
 def extra_configs(rt, rz_main, device, args, fp64_peak, hbm_peak):
