@@ -81,8 +81,11 @@ struct RxnState {
   int react_kernel = 0;    // 0 auto, 1 thread-per-cell, 3 resident lane / tensor memory (2: the cooperative kernel of round 1, removed)
   unsigned long long *d_counter = nullptr;   // work counter of the resident-lane kernel
   // host-buffer RReact: chunks of the batch move over PCIe while the previous / next chunk is being solved
-  enum { NCHUNK = 8 };
-  cudaStream_t h2d = nullptr, d2h = nullptr;
+  // (16 chunks; consecutive chunks are solved on two alternating streams with their own work counters, so the persistent CTAs of
+  // chunk c+1 move onto the SMs that chunk c's CTAs have drained instead of waiting for its slowest cell)
+  enum { NCHUNK = 16 };
+  cudaStream_t h2d = nullptr, d2h = nullptr, stream2 = nullptr;
+  unsigned long long *d_counters = nullptr;   // one work counter per chunk
   cudaEvent_t ev_in[NCHUNK] = {}, ev_k[NCHUNK] = {};
   int flux_generic = 0;    // RXN_FLUX_GENERIC=1: flux Jacobian through the run-time-n kernel (tests)
   int flux_rows = 0;       // RXN_FLUX_ROWS=1: N = 15 flux Jacobian by block rows (k_flux_jacobian_t) instead of block columns
@@ -335,6 +338,8 @@ int rxn_state_destroy(RxnState *s) {
   if (s->d_sort_tmp) cudaFree(s->d_sort_tmp);
   if (s->h2d) cudaStreamDestroy(s->h2d);
   if (s->d2h) cudaStreamDestroy(s->d2h);
+  if (s->stream2) cudaStreamDestroy(s->stream2);
+  if (s->d_counters) cudaFree(s->d_counters);
   for (int c = 0; c < RxnState::NCHUNK; ++c) {
     if (s->ev_in[c]) cudaEventDestroy(s->ev_in[c]);
     if (s->ev_k[c]) cudaEventDestroy(s->ev_k[c]);
@@ -505,8 +510,10 @@ static int react_remember(RxnState *s, int64_t nlocal, const int32_t *d_iters) {
 }
 
 static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
-                        int32_t *d_iters, int32_t *d_flags, long long cell0 = 0) {
+                        int32_t *d_iters, int32_t *d_flags, long long cell0 = 0, cudaStream_t stream = nullptr,
+                        unsigned long long *counter = nullptr) {
   const RxnTables *t = s->t;
+  if (!stream) stream = s->stream;
   // the shared-memory kernels keep dtotal only as Newton scratch: states with DTOTAL materialised use thread-per-cell
   const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
   const bool lane_ok = t->lane.plan.usable && no_dtotal;
@@ -515,11 +522,14 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
     return fail(RXN_ERR_UNSUPPORTED, "resident-lane kernel unavailable: %s", t->lane.plan.usable ? "DTOTAL is materialised" : t->lane.plan.err.c_str());
   const bool use_lane = lane_ok && (s->react_kernel == 0 || s->react_kernel == 3);
   if (use_lane) {
-    if (!s->d_counter) CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+    if (!counter) {
+      if (!s->d_counter) CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+      counter = s->d_counter;
+    }
     DevState S = s->S;
     const bool ordered = tail_bound_tables(t) && cell0 == 0;
     if (ordered) { const int rco = react_order(s, nlocal, &S.order); if (rco != RXN_OK) return rco; }
-    int rc = lane_launch_react(t->lane, t->h, t->d_blob, S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, s->d_counter, s->stream, cell0);
+    int rc = lane_launch_react(t->lane, t->h, t->d_blob, S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, counter, stream, cell0);
     if (rc == RXN_OK && ordered) { const int rcr = react_remember(s, nlocal, d_iters); if (rcr != RXN_OK) return rcr; }
     if (rc != RXN_OK) return fail(rc, "resident-lane kernel launch failed (N=%d CPB=%d): %s", t->lane.plan.lt.N, t->lane.plan.lt.CPB,
                                   cudaGetErrorString(cudaGetLastError()));
@@ -531,7 +541,7 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
     if (const char *e = getenv("RXN_TPC_BLOCK")) threads = std::max(32, atoi(e));
     unsigned grid = nblocks(nlocal, threads);
     if (const char *e = getenv("RXN_TPC_GRID")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(e)));
-    const LaunchCfg L{grid, threads, t->blob_bytes, s->stream};
+    const LaunchCfg L{grid, threads, t->blob_bytes, stream};
     RXN_DISPATCH(t->nvariant, run_react, L, t->h, (const double *)t->d_blob, s->S, d_xx, d_l2g, (long long)nlocal, dt, dt_mode,
                  d_iters, d_flags);
   }
@@ -578,7 +588,8 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
     // resident-lane kernel on a large batch: NCHUNK chunks; chunk c+1 crosses PCIe while chunk c is solved and chunk
     // c-1 returns (full duplex), so the host-buffer call costs about the kernel time
     if (!s->h2d) {
-      CU(cudaStreamCreate(&s->h2d)); CU(cudaStreamCreate(&s->d2h));
+      CU(cudaStreamCreate(&s->h2d)); CU(cudaStreamCreate(&s->d2h)); CU(cudaStreamCreate(&s->stream2));
+      CU(cudaMalloc(&s->d_counters, RxnState::NCHUNK * sizeof(unsigned long long)));
       for (int c = 0; c < RxnState::NCHUNK; ++c) {
         CU(cudaEventCreateWithFlags(&s->ev_in[c], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s->ev_k[c], cudaEventDisableTiming));
@@ -586,7 +597,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
     }
     // an error inside the pipeline must not leave copies or kernels running on the caller's tran_xx / iters / flags:
     // drain the three streams before returning
-    auto drain = [&]() { cudaStreamSynchronize(s->h2d); cudaStreamSynchronize(s->stream); cudaStreamSynchronize(s->d2h); };
+    auto drain = [&]() { cudaStreamSynchronize(s->h2d); cudaStreamSynchronize(s->stream); cudaStreamSynchronize(s->stream2); cudaStreamSynchronize(s->d2h); };
 #define CUP(call)                                                                              \
   do {                                                                                          \
     cudaError_t e_ = (call);                                                                    \
@@ -595,9 +606,10 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
       return fail(RXN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     }                                                                                           \
   } while (0)
-    if (!s->d_counter) CUP(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
     CUP(cudaStreamSynchronize(s->stream));                       // the l2g copy above / earlier work on the scratch buffers
-    const int64_t chunk = (((nlocal + RxnState::NCHUNK - 1) / RxnState::NCHUNK) + 63) / 64 * 64;
+    // up to NCHUNK chunks of at least 131 072 cells (several generations of resident cells per launch)
+    const int64_t nchunks = std::min<int64_t>(RxnState::NCHUNK, std::max<int64_t>(2, nlocal / 131072));
+    const int64_t chunk = (((nlocal + nchunks - 1) / nchunks) + 63) / 64 * 64;
     int nch = 0;
     for (int64_t off = 0; off < nlocal; off += chunk, ++nch) {
       const int64_t len = std::min<int64_t>(chunk, nlocal - off);
@@ -606,21 +618,26 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
     }
     CUP(cudaEventRecord(s->ev0, s->stream));
     int c = 0;
+    int last_k[2] = {-1, -1};
     for (int64_t off = 0; off < nlocal; off += chunk, ++c) {
       const int64_t len = std::min<int64_t>(chunk, nlocal - off);
-      CUP(cudaStreamWaitEvent(s->stream, s->ev_in[c], 0));
+      cudaStream_t ks = (c & 1) ? s->stream2 : s->stream;       // chunk c+1 fills the SMs chunk c has drained
+      CUP(cudaStreamWaitEvent(ks, s->ev_in[c], 0));
       rc = launch_react(s, (double *)d_xx + off * n, d_l2g ? (const int32_t *)d_l2g + off : nullptr, len, dt, dt_mode, (int32_t *)d_it + off,
-                        (int32_t *)d_fl + off, d_l2g ? 0 : off);
+                        (int32_t *)d_fl + off, d_l2g ? 0 : off, ks, s->d_counters + c);
       if (rc != RXN_OK) { drain(); return rc; }
-      CUP(cudaEventRecord(s->ev_k[c], s->stream));
+      CUP(cudaEventRecord(s->ev_k[c], ks));
+      last_k[c & 1] = c;
       CUP(cudaStreamWaitEvent(s->d2h, s->ev_k[c], 0));
       CUP(cudaMemcpyAsync(tran_xx + off * n, (double *)d_xx + off * n, (size_t)len * n * 8, cudaMemcpyDeviceToHost, s->d2h));
       if (iters_out) CUP(cudaMemcpyAsync(iters_out + off, (int32_t *)d_it + off, (size_t)len * 4, cudaMemcpyDeviceToHost, s->d2h));
       if (flags_out) CUP(cudaMemcpyAsync(flags_out + off, (int32_t *)d_fl + off, (size_t)len * 4, cudaMemcpyDeviceToHost, s->d2h));
     }
+    if (last_k[1] >= 0) CUP(cudaStreamWaitEvent(s->stream, s->ev_k[last_k[1]], 0));   // ev1 after the kernels of both streams
     CUP(cudaEventRecord(s->ev1, s->stream));
     CUP(cudaGetLastError());
     CUP(cudaStreamSynchronize(s->d2h));
+    CUP(cudaStreamSynchronize(s->stream2));
     CUP(cudaStreamSynchronize(s->stream));
     CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
 #undef CUP
