@@ -2,7 +2,7 @@
 small enough for the tools' slowdown, large enough that persistent lanes take several cells from the work counter
 (k_react_tm: 148 CTAs x 128 cells = 18 944 resident cells).  No oracle, no timing: the tools' reports are the result.
 
-  compute-sanitizer --tool racecheck python profiles/sanitize_run.py [react|gi|flux|new|all] [ncells]
+  compute-sanitizer --tool racecheck python profiles/sanitize_run.py [react|gi|flux|new|pipeline|all] [ncells]
 """
 import os
 import sys
@@ -94,6 +94,8 @@ if what in ('flux', 'all'):
     print('coupler %d boundary faces, %d wells, |res| max %.3e' % (len(bc['id_dn']), len(ss['id_dn']), np.abs(r).max()))
     bs.close(); sk.close()
     cs.close()
+if what in ('pipeline',):
+    react('calcite', 300000)                   # host-buffer RTReact above 262 144 cells: chunked copies, chunk kernels on two alternating streams
 if what in ('new', 'all'):
     # kernels added late in round 2: resident-lane N = 24 with 8 lanes per cell (ascem), thread-per-cell microbial reactions with an
     # immobile dof (RReact and the global-implicit loops), the streaming multirate update k_kinmr_update
