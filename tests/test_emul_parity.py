@@ -426,3 +426,30 @@ def test_equilibrate_constraint_batch_per_cell_concentrations(name):
         assert it == it_e[c] and status[c] == 0
         assert rel_err(basis_e[c], b).max() <= RTOL
     assert_state_close(st, st_o, what=name + ' equilibrated batch', tables=t)
+
+
+def test_packer_validates_microbial_and_immobile_tables():
+    """Range checks of the microbial / immobile tables (rxn_pack.h): ids that would index past the per-cell arrays are rejected with
+    RXN_ERR_INVALID, an inhibition type RMicrobial has no branch for with RXN_ERR_UNSUPPORTED, ncomp must count the immobile dofs."""
+    import copy
+    w = synth.Workload('abcd_microbial')
+    assert pack_status(abi.make_desc(w.tables))[0] == abi.RXN_OK
+
+    def status(mutate):
+        t = copy.deepcopy(w.tables)
+        mutate(t)
+        return pack_status(abi.make_desc(t))[0]
+
+    def set_(name, idx, val):
+        def f(t):
+            a = getattr(t, name).copy(); a[idx] = val; setattr(t, name, a)
+        return f
+    assert status(set_('microbial_specid', (0, 1), 9)) == abi.RXN_ERR_INVALID            # species id beyond ncomp = 4
+    assert status(set_('microbial_biomassid', 0, 2)) == abi.RXN_ERR_INVALID              # one immobile species only
+    assert status(set_('microbial_monod_specid', 0, 4)) == abi.RXN_ERR_INVALID           # Monod terms act on aqueous species
+    assert status(set_('microbial_monodid', (0, 1), 3)) == abi.RXN_ERR_INVALID           # two Monod terms exist
+    assert status(set_('microbial_inhibition_specid', 0, 0)) == abi.RXN_ERR_INVALID
+    assert status(set_('microbial_inhibition_type', 0, 2)) == abi.RXN_ERR_UNSUPPORTED     # INHIBITION_THERMODYNAMIC
+    assert status(set_('immobile_decayspecid', 0, 2)) == abi.RXN_ERR_INVALID
+    assert status(lambda t: setattr(t, 'ncomp', 3)) == abi.RXN_ERR_UNSUPPORTED            # ncomp must be naqcomp + nimmobile
+    assert status(lambda t: setattr(t, 'nimmobile', 5)) == abi.RXN_ERR_UNSUPPORTED
