@@ -558,6 +558,19 @@ def run_ours(args):
     bad_all = int(sum_over_ranks(float(bad)))
     kern_ms_max = max_over_ranks(statistics.mean(kern_ms))
 
+    # the same steps with the work order switched off (RXN_NO_REACT_ORDER: the lanes take the batch as it comes), reported beside
+    # the default so that the share of the order in `value` is visible in the line
+    unordered = None
+    if not os.environ.get('RXN_NO_REACT_ORDER') and 'work order' in rz.react_kernel_info():
+        os.environ['RXN_NO_REACT_ORDER'] = '1'
+        step_device()
+        barrier()
+        rz.timer_start()
+        km_u = [step_device() for _ in range(args.steps)]
+        dev_ms_u = max_over_ranks(rz.timer_stop())
+        del os.environ['RXN_NO_REACT_ORDER']
+        unordered = (dev_ms_u, max_over_ranks(statistics.mean(km_u)))
+
     # end-to-end through the host-buffer call
     xx_host[:] = xx0_host
     step_e2e(0)
@@ -585,6 +598,9 @@ def run_ours(args):
             'config': {'workload': WORKLOAD_DESC[args.workload], 'name': args.workload, 'cells_per_gpu': n,
                        'total_cells': total_cells, 'dt_s': args.dt, 'dt_mode': 'DT_CONSISTENT',
                        'mean_newton_iterations': wm['mean_newton_iterations'], 'cells_with_nonreference_flags': bad_all,
+                       'work_order': ('lanes take the cells sorted by the Newton iteration counts of the previous call (sort inside the timed region); every '
+                                      'step of this benchmark repeats the same inputs, so that prediction is exact here; roofline.unordered = the same '
+                                      'steps without it') if unordered is not None else 'off',
                        'l2_policy': 'inputs (%.1f GB of cell state per GPU) larger than L2; no flush needed'
                                     % (n * wm['bytes_per_cell'] / 1e9),
                        'kernel': kinfo},
@@ -598,6 +614,10 @@ def run_ours(args):
                                  '/ react-kernel time (CUDA events); peak = DFMA probe measured in this run (rxn_probe_fp64)',
                          'kernel_ms': kern_ms_max, 'flop_eq_per_cell': wm['flop_eq_per_cell'],
                          'transcendentals_per_cell': wm['transcendentals_per_cell'],
+                         'unordered': None if unordered is None else {
+                             'value': total_cells * args.steps / (unordered[0] * 1e-3), 'kernel_ms': unordered[1],
+                             'frac': wm['flop_eq_per_cell'] * n / (unordered[1] * 1e-3) / 1e12 / fp64_peak,
+                             'note': 'the same steps with RXN_NO_REACT_ORDER=1 (lanes take the batch in index order)'},
                          # the probe's number beside the arithmetic one: SMs x 64 FP64 lanes x 2 flop x the maximum SM clock
                          # (MEASURED_PEAKS.json has no FP64 entry; NVIDIA's nominal 40 TFLOP/s is this product at 2.1 GHz)
                          'peak_theoretical': theoretical_fp64_tflops(local_rank, clocks),

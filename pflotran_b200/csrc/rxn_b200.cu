@@ -94,9 +94,10 @@ struct RxnState {
   // work order of the resident-lane RReact kernel for tail-bound chemistries (react_order): items sorted by the Newton iteration
   // count of the previous call, slowest first
   int32_t *d_prev_it = nullptr, *d_keys = nullptr, *d_iota = nullptr, *d_order = nullptr;
-  void *d_sort_tmp = nullptr;
-  size_t sort_tmp_bytes = 0;
-  long long order_cap = 0, prev_n = 0;     // allocated items; items of the remembered iteration counts (0: none)
+  void *d_sort_tmp[2] = {nullptr, nullptr};   // one per compute stream of the chunked call
+  size_t sort_tmp_bytes[2] = {0, 0};
+  long long order_cap = 0, prev_n = 0;     // allocated items; items (of the whole batch) of the remembered iteration counts (0: none)
+  long long prev_chunk = 0;                // chunk length of the call that remembered them (0: one launch)
 };
 
 // Row view of a connection list + the flux coefficients of the current flow field (rxn_flux.h)
@@ -335,7 +336,7 @@ int rxn_state_destroy(RxnState *s) {
   if (s->d_counter) cudaFree(s->d_counter);
   if (s->d_fail) cudaFree(s->d_fail);
   for (int32_t *p : {s->d_prev_it, s->d_keys, s->d_iota, s->d_order}) if (p) cudaFree(p);
-  if (s->d_sort_tmp) cudaFree(s->d_sort_tmp);
+  for (void *p : s->d_sort_tmp) if (p) cudaFree(p);
   if (s->h2d) cudaStreamDestroy(s->h2d);
   if (s->d2h) cudaStreamDestroy(s->d2h);
   if (s->stream2) cudaStreamDestroy(s->stream2);
@@ -454,14 +455,15 @@ int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
   const bool no_dtotal = !s->S.f[RXN_F_DTOTAL] && !s->S.f[RXN_F_DTOTAL_SORB_EQ];
   const bool lane_ok = t->lane.plan.usable && no_dtotal;
   if (lane_ok && t->lane.plan_tm.usable && (s->react_kernel == 0 || s->react_kernel == 3))
-    snprintf(buf, (size_t)len, "tensor-memory N=%d cells/CTA=%d warps/cell=%d threads=%d smem=%zu B plan=%zu B J in TMEM (spec %d, planA %d, planB %d terms)",
+    snprintf(buf, (size_t)len, "tensor-memory N=%d cells/CTA=%d warps/cell=%d threads=%d smem=%zu B plan=%zu B J in TMEM (spec %d, planA %d, planB %d terms)%s",
              t->lane.plan_tm.lt.N, t->lane.plan_tm.lt.CPB, t->lane.G_tm, 128 * t->lane.G_tm, t->lane.plan_tm.smem_bytes,
-             t->lane.plan_tm.blob.size(), t->lane.plan_tm.terms_spec, t->lane.plan_tm.terms_A, t->lane.plan_tm.terms_B);
+             t->lane.plan_tm.blob.size(), t->lane.plan_tm.terms_spec, t->lane.plan_tm.terms_A, t->lane.plan_tm.terms_B,
+             getenv("RXN_NO_REACT_ORDER") ? "" : " work order: previous call's iteration counts, slowest first");
   else if (lane_ok && (s->react_kernel == 0 || s->react_kernel == 3))
     snprintf(buf, (size_t)len, "resident-lane N=%d cells/CTA=%d lanes/cell=%d threads=%d smem=%zu B plan=%zu B (spec %d, planA %d, planB %d terms)%s",
              t->lane.plan.lt.N, t->lane.plan.lt.CPB, t->lane.G, ((t->lane.plan.lt.CPB * t->lane.G + 31) / 32) * 32, t->lane.plan.smem_bytes,
              t->lane.plan.blob.size(), t->lane.plan.terms_spec, t->lane.plan.terms_A, t->lane.plan.terms_B,
-             !t->lane.plan_tm.usable && t->h.naq > 16 && !getenv("RXN_NO_REACT_ORDER") ? " work order: previous call's iteration counts, slowest first" : "");
+             getenv("RXN_NO_REACT_ORDER") ? "" : " work order: previous call's iteration counts, slowest first");
   else
     snprintf(buf, (size_t)len, "thread-per-cell N<=%d (lane: %s)", t->nvariant,
              t->lane.plan.usable ? "DTOTAL materialised" : t->lane.plan.err.c_str());
@@ -478,40 +480,45 @@ __global__ void k_iota(int32_t *p, long long n) {
   if (i < n) p[i] = (int32_t)i;
 }
 static bool tail_bound_tables(const RxnTables *t) { return !t->lane.plan_tm.usable && t->h.naq > 16; }
-static int react_order(RxnState *s, int64_t nlocal, const int32_t **order) {
+// [off, off + len): the items of this launch within the batch of `total` items (a chunk of the pipelined call, or the whole batch);
+// the permutation is relative to the launch (values 0 .. len-1), as the kernel's item numbers are
+static int react_order(RxnState *s, int64_t total, int64_t chunk, int64_t off, int64_t len, cudaStream_t stream, int which, const int32_t **order) {
   *order = nullptr;
-  if (s->prev_n != nlocal || getenv("RXN_NO_REACT_ORDER")) return RXN_OK;
+  if (s->prev_n != total || s->prev_chunk != chunk || getenv("RXN_NO_REACT_ORDER")) return RXN_OK;
   size_t need = 0;
-  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, s->d_prev_it, s->d_keys, s->d_iota, s->d_order, (int)nlocal, 0, 14, s->stream));
-  if (need > s->sort_tmp_bytes) {
-    if (s->d_sort_tmp) CU(cudaFree(s->d_sort_tmp));
-    s->d_sort_tmp = nullptr; s->sort_tmp_bytes = 0;
-    CU(cudaMalloc(&s->d_sort_tmp, need));
-    s->sort_tmp_bytes = need;
+  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, s->d_prev_it + off, s->d_keys + off, s->d_iota + off, s->d_order + off, (int)len, 0, 14, stream));
+  if (need > s->sort_tmp_bytes[which]) {
+    if (s->d_sort_tmp[which]) CU(cudaFree(s->d_sort_tmp[which]));
+    s->d_sort_tmp[which] = nullptr; s->sort_tmp_bytes[which] = 0;
+    CU(cudaMalloc(&s->d_sort_tmp[which], need));
+    s->sort_tmp_bytes[which] = need;
   }
-  k_iota<<<nblocks(nlocal, 256), 256, 0, s->stream>>>(s->d_iota, nlocal);
-  CU(cub::DeviceRadixSort::SortPairsDescending(s->d_sort_tmp, need, s->d_prev_it, s->d_keys, s->d_iota, s->d_order, (int)nlocal, 0, 14, s->stream));
+  k_iota<<<nblocks(len, 256), 256, 0, stream>>>(s->d_iota + off, len);
+  CU(cub::DeviceRadixSort::SortPairsDescending(s->d_sort_tmp[which], need, s->d_prev_it + off, s->d_keys + off, s->d_iota + off, s->d_order + off, (int)len, 0,
+                                               14, stream));
   g_launches += 2;
-  *order = s->d_order;
+  *order = s->d_order + off;
   return RXN_OK;
 }
-static int react_remember(RxnState *s, int64_t nlocal, const int32_t *d_iters) {
+// room for the iteration counts of a batch of `total` items (drops what was remembered when it has to grow)
+static int react_order_reserve(RxnState *s, int64_t total) {
+  if (total <= s->order_cap) return RXN_OK;
   s->prev_n = 0;
-  if (!d_iters || nlocal > 0x7fffffffLL) return RXN_OK;
-  if (nlocal > s->order_cap) {
-    for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) { if (*p) CU(cudaFree(*p)); *p = nullptr; }
-    s->order_cap = 0;
-    for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) CU(cudaMalloc(p, (size_t)nlocal * 4));
-    s->order_cap = nlocal;
-  }
-  CU(cudaMemcpyAsync(s->d_prev_it, d_iters, (size_t)nlocal * 4, cudaMemcpyDeviceToDevice, s->stream));
-  s->prev_n = nlocal;
+  for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) { if (*p) CU(cudaFree(*p)); *p = nullptr; }
+  s->order_cap = 0;
+  for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) CU(cudaMalloc(p, (size_t)total * 4));
+  s->order_cap = total;
+  return RXN_OK;
+}
+static int react_remember(RxnState *s, int64_t off, int64_t len, const int32_t *d_iters, cudaStream_t stream) {
+  CU(cudaMemcpyAsync(s->d_prev_it + off, d_iters, (size_t)len * 4, cudaMemcpyDeviceToDevice, stream));
   return RXN_OK;
 }
 
+// total / chunk / off: the batch this launch is a chunk of (pipelined host-buffer call); total < 0: the launch is the batch
 static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
                         int32_t *d_iters, int32_t *d_flags, long long cell0 = 0, cudaStream_t stream = nullptr,
-                        unsigned long long *counter = nullptr) {
+                        unsigned long long *counter = nullptr, int64_t total = -1, int64_t chunk = 0, int64_t off = 0, int which = 0) {
   const RxnTables *t = s->t;
   if (!stream) stream = s->stream;
   // the shared-memory kernels keep dtotal only as Newton scratch: states with DTOTAL materialised use thread-per-cell
@@ -522,15 +529,30 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
     return fail(RXN_ERR_UNSUPPORTED, "resident-lane kernel unavailable: %s", t->lane.plan.usable ? "DTOTAL is materialised" : t->lane.plan.err.c_str());
   const bool use_lane = lane_ok && (s->react_kernel == 0 || s->react_kernel == 3);
   if (use_lane) {
+    const bool single_launch = counter == nullptr;            // not a chunk of the pipelined host-buffer call
     if (!counter) {
       if (!s->d_counter) CU(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
       counter = s->d_counter;
     }
     DevState S = s->S;
-    const bool ordered = tail_bound_tables(t) && cell0 == 0;
-    if (ordered) { const int rco = react_order(s, nlocal, &S.order); if (rco != RXN_OK) return rco; }
+    // work order (react_order): the lanes take the items sorted by the iteration counts of the previous call of the same shape
+    if (single_launch) { total = nlocal; chunk = 0; off = 0; which = 0; }
+    // (the chunks of the pipelined call of a small chemistry are not ordered: calcite solves 143 000 cells in 0.16 ms, less than the
+    // sort's launches cost: e2e 582 -> 555 M cell-updates/s with them, profiles/r02_au_bench_default.json)
+    const bool ordered = d_iters != nullptr && total <= 0x7fffffffLL && (single_launch || t->h.naq >= 8);
+    if (ordered) {
+      if (single_launch) { const int rcv = react_order_reserve(s, total); if (rcv != RXN_OK) return rcv; }
+      const int rco = react_order(s, total, chunk, off, nlocal, stream, which, &S.order);
+      if (rco != RXN_OK) return rco;
+    }
     int rc = lane_launch_react(t->lane, t->h, t->d_blob, S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, counter, stream, cell0);
-    if (rc == RXN_OK && ordered) { const int rcr = react_remember(s, nlocal, d_iters); if (rcr != RXN_OK) return rcr; }
+    if (rc == RXN_OK && ordered) {
+      const int rcr = react_remember(s, off, nlocal, d_iters, stream);
+      if (rcr != RXN_OK) return rcr;
+      if (single_launch) { s->prev_n = total; s->prev_chunk = 0; }
+    } else if (single_launch) {
+      s->prev_n = 0;
+    }
     if (rc != RXN_OK) return fail(rc, "resident-lane kernel launch failed (N=%d CPB=%d): %s", t->lane.plan.lt.N, t->lane.plan.lt.CPB,
                                   cudaGetErrorString(cudaGetLastError()));
     ++g_launches;
@@ -617,6 +639,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
       CUP(cudaEventRecord(s->ev_in[nch], s->h2d));
     }
     CUP(cudaEventRecord(s->ev0, s->stream));
+    { const int rcv = react_order_reserve(s, nlocal); if (rcv != RXN_OK) { drain(); return rcv; } }
     int c = 0;
     int last_k[2] = {-1, -1};
     for (int64_t off = 0; off < nlocal; off += chunk, ++c) {
@@ -624,7 +647,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
       cudaStream_t ks = (c & 1) ? s->stream2 : s->stream;       // chunk c+1 fills the SMs chunk c has drained
       CUP(cudaStreamWaitEvent(ks, s->ev_in[c], 0));
       rc = launch_react(s, (double *)d_xx + off * n, d_l2g ? (const int32_t *)d_l2g + off : nullptr, len, dt, dt_mode, (int32_t *)d_it + off,
-                        (int32_t *)d_fl + off, d_l2g ? 0 : off, ks, s->d_counters + c);
+                        (int32_t *)d_fl + off, d_l2g ? 0 : off, ks, s->d_counters + c, nlocal, chunk, off, c & 1);
       if (rc != RXN_OK) { drain(); return rc; }
       CUP(cudaEventRecord(s->ev_k[c], ks));
       last_k[c & 1] = c;
@@ -639,6 +662,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
     CUP(cudaStreamSynchronize(s->d2h));
     CUP(cudaStreamSynchronize(s->stream2));
     CUP(cudaStreamSynchronize(s->stream));
+    s->prev_n = (nlocal <= 0x7fffffffLL && t->h.naq >= 8) ? nlocal : 0; s->prev_chunk = chunk;   // every chunk has remembered its iteration counts
     CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
 #undef CUP
     return RXN_OK;

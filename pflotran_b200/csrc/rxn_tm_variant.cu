@@ -69,10 +69,11 @@ k_react_tm(const __grid_constant__ LaneTab lt, const __grid_constant__ DevTab h,
         double o[G];
         grp_gather<CPB, G>(c, mine, o);                         // item numbers are exact in a double
         if (want) {
-          const long long i = (long long)o[0];
+          long long i = (long long)o[0];
           if (i >= nlocal) {
             exhausted = true;
           } else {
+            if (S.order) i = S.order[i];                         // slowest cells of the previous call first (rxn_b200.cu: react_order)
             const long long cell = l2g ? l2g[i] : i + cell0;    // cell0: first cell of this chunk of the batch
             if (S.active && !S.active[cell]) {                   // imat <= 0 (reactive_transport.F90:1699)
               if (l == 0) {
