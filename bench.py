@@ -561,7 +561,7 @@ def run_ours(args):
     # the same steps with the work order switched off (RXN_NO_REACT_ORDER: the lanes take the batch as it comes), reported beside
     # the default so that the share of the order in `value` is visible in the line
     unordered = None
-    if not os.environ.get('RXN_NO_REACT_ORDER') and 'work order' in rz.react_kernel_info():
+    if not os.environ.get('RXN_NO_REACT_ORDER') and work_order_active(rz.react_kernel_info(), n, local_rank):
         os.environ['RXN_NO_REACT_ORDER'] = '1'
         step_device()
         barrier()
@@ -600,7 +600,7 @@ def run_ours(args):
                        'mean_newton_iterations': wm['mean_newton_iterations'], 'cells_with_nonreference_flags': bad_all,
                        'work_order': ('lanes take the cells sorted by the Newton iteration counts of the previous call (sort inside the timed region); every '
                                       'step of this benchmark repeats the same inputs, so that prediction is exact here; roofline.unordered = the same '
-                                      'steps without it') if unordered is not None else 'off',
+                                      'steps without it') if unordered is not None else 'off (index order) at this batch size / chemistry',
                        'l2_policy': 'inputs (%.1f GB of cell state per GPU) larger than L2; no flush needed'
                                     % (n * wm['bytes_per_cell'] / 1e9),
                        'kernel': kinfo},
@@ -642,6 +642,19 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def work_order_active(kernel_info, n, device):
+    """Whether the library orders a single launch of n cells by the previous call's iteration counts (rxn_b200.cu: react_ordered):
+    tail-bound chemistries always, chemistries with >= 8 primaries below 16 generations of resident cells; read off the kernel line."""
+    import re
+    if 'work order:' in kernel_info:
+        return True
+    m = re.search(r'cells/CTA=(\d+)', kernel_info)
+    if 'work order below 16 generations' in kernel_info and m:
+        import torch
+        return n < 16 * torch.cuda.get_device_properties(device).multi_processor_count * int(m.group(1))
+    return False
 
 
 def theoretical_fp64_tflops(device, clocks):

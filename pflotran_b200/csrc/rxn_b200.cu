@@ -94,10 +94,9 @@ struct RxnState {
   // work order of the resident-lane RReact kernel for tail-bound chemistries (react_order): items sorted by the Newton iteration
   // count of the previous call, slowest first
   int32_t *d_prev_it = nullptr, *d_keys = nullptr, *d_iota = nullptr, *d_order = nullptr;
-  void *d_sort_tmp[2] = {nullptr, nullptr};   // one per compute stream of the chunked call
-  size_t sort_tmp_bytes[2] = {0, 0};
-  long long order_cap = 0, prev_n = 0;     // allocated items; items (of the whole batch) of the remembered iteration counts (0: none)
-  long long prev_chunk = 0;                // chunk length of the call that remembered them (0: one launch)
+  void *d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  long long order_cap = 0, prev_n = 0;     // allocated items; items of the remembered iteration counts (0: none)
 };
 
 // Row view of a connection list + the flux coefficients of the current flow field (rxn_flux.h)
@@ -336,7 +335,7 @@ int rxn_state_destroy(RxnState *s) {
   if (s->d_counter) cudaFree(s->d_counter);
   if (s->d_fail) cudaFree(s->d_fail);
   for (int32_t *p : {s->d_prev_it, s->d_keys, s->d_iota, s->d_order}) if (p) cudaFree(p);
-  for (void *p : s->d_sort_tmp) if (p) cudaFree(p);
+  if (s->d_sort_tmp) cudaFree(s->d_sort_tmp);
   if (s->h2d) cudaStreamDestroy(s->h2d);
   if (s->d2h) cudaStreamDestroy(s->d2h);
   if (s->stream2) cudaStreamDestroy(s->stream2);
@@ -449,6 +448,7 @@ int rxn_set_react_kernel(RxnState *s, int which) {
   return RXN_OK;
 }
 
+static bool tail_bound_info(const RxnTables *t) { return !t->lane.plan_tm.usable && t->h.naq > 16; }
 int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
   if (!s || !buf || len < 1) return fail(RXN_ERR_INVALID, "bad argument");
   const RxnTables *t = s->t;
@@ -458,67 +458,77 @@ int rxn_react_kernel_info(const RxnState *s, char *buf, int32_t len) {
     snprintf(buf, (size_t)len, "tensor-memory N=%d cells/CTA=%d warps/cell=%d threads=%d smem=%zu B plan=%zu B J in TMEM (spec %d, planA %d, planB %d terms)%s",
              t->lane.plan_tm.lt.N, t->lane.plan_tm.lt.CPB, t->lane.G_tm, 128 * t->lane.G_tm, t->lane.plan_tm.smem_bytes,
              t->lane.plan_tm.blob.size(), t->lane.plan_tm.terms_spec, t->lane.plan_tm.terms_A, t->lane.plan_tm.terms_B,
-             getenv("RXN_NO_REACT_ORDER") ? "" : " work order: previous call's iteration counts, slowest first");
+             getenv("RXN_NO_REACT_ORDER") ? "" : tail_bound_info(t) ? " work order: previous call's iteration counts, slowest first"
+             : t->h.naq >= 8 ? " work order below 16 generations of resident cells: previous call's iteration counts, slowest first" : "");
   else if (lane_ok && (s->react_kernel == 0 || s->react_kernel == 3))
     snprintf(buf, (size_t)len, "resident-lane N=%d cells/CTA=%d lanes/cell=%d threads=%d smem=%zu B plan=%zu B (spec %d, planA %d, planB %d terms)%s",
              t->lane.plan.lt.N, t->lane.plan.lt.CPB, t->lane.G, ((t->lane.plan.lt.CPB * t->lane.G + 31) / 32) * 32, t->lane.plan.smem_bytes,
              t->lane.plan.blob.size(), t->lane.plan.terms_spec, t->lane.plan.terms_A, t->lane.plan.terms_B,
-             getenv("RXN_NO_REACT_ORDER") ? "" : " work order: previous call's iteration counts, slowest first");
+             getenv("RXN_NO_REACT_ORDER") ? "" : tail_bound_info(t) ? " work order: previous call's iteration counts, slowest first"
+             : t->h.naq >= 8 ? " work order below 16 generations of resident cells: previous call's iteration counts, slowest first" : "");
   else
     snprintf(buf, (size_t)len, "thread-per-cell N<=%d (lane: %s)", t->nvariant,
              t->lane.plan.usable ? "DTOTAL materialised" : t->lane.plan.err.c_str());
   return RXN_OK;
 }
 
-// Chemistries whose launches end with a tail of slow cells (tail_bound_tables): a cell that needed thousands of damped Newton
-// iterations in one transport step needs them in the next one too, so the lanes take the batch in the order of the previous
-// call's iteration counts, slowest first - the long cells start while the SMs are full and the launch ends when the work does
-// (longest-processing-time-first on the persistent lanes).  A stable 14-bit radix sort (cub) keeps cells with equal counts in
-// index order, so neighbouring lanes still share DRAM sectors.  Results do not depend on the order (cells are independent).
+// Work order of the on-chip RReact kernels.  The lanes take the items of a launch from a counter; a cell that needed many Newton
+// iterations in one transport step needs them in the next one too, so the launch can be handed out sorted by the iteration counts
+// of the previous call, slowest first (longest-processing-time-first on the persistent lanes): the long cells start while the SMs
+// are full and the launch ends when the work does.  A stable 14-bit radix sort (cub) keeps cells with equal counts in index order.
+// Results do not depend on the order (cells are independent).  What it costs: neighbouring lanes no longer hold neighbouring
+// cells, so their 8-byte accesses stop sharing DRAM sectors.  Measured (profiles/bench_order_prediction.py, r02_av_* / r02_aw_*:
+// every call ordered by the counts of a DIFFERENT noise realisation of the same cells - an imperfect prediction, as in a transport
+// run - beside the exact prediction of a benchmark that repeats its inputs):
+//   300A    5*10^4 / 10^5 / 3*10^5 / 10^6 / 2*10^6 cells: x1.06 / 1.10 / 1.03 / 0.95 / 0.92  (exact prediction: x1.14 / 1.29 / 1.21 / 1.16 / 1.14)
+//   calcite 10^5 / 4*10^6: x0.95 / 0.91;   ascem (tail-bound) 2*10^5 / 10^6: x1.07 / 1.13  (exact: x1.00 / 1.58)
+// Hence the policy (react_ordered): tail-bound chemistries always; chemistries with at least 8 primaries on batches below 16
+// generations of resident cells (300A: 3*10^5 cells - a rank's share of a grid), where removing the tail pays even with the imperfect
+// prediction; large batches and small chemistries are taken in index order.  The gain of an exact prediction on large batches
+// (300A, 10^7 cells: 57.9 -> 65.7 M cell-updates/s, profiles/r02_au_bench_default.json: warps whose 32 cells finish in the same trip
+// run their finish / load rounds at full width) is an artefact of repeated inputs and is not taken.
 __global__ void k_iota(int32_t *p, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = (int32_t)i;
 }
 static bool tail_bound_tables(const RxnTables *t) { return !t->lane.plan_tm.usable && t->h.naq > 16; }
-// [off, off + len): the items of this launch within the batch of `total` items (a chunk of the pipelined call, or the whole batch);
-// the permutation is relative to the launch (values 0 .. len-1), as the kernel's item numbers are
-static int react_order(RxnState *s, int64_t total, int64_t chunk, int64_t off, int64_t len, cudaStream_t stream, int which, const int32_t **order) {
+static int react_order(RxnState *s, int64_t nlocal, cudaStream_t stream, const int32_t **order) {
   *order = nullptr;
-  if (s->prev_n != total || s->prev_chunk != chunk || getenv("RXN_NO_REACT_ORDER")) return RXN_OK;
+  if (s->prev_n != nlocal || getenv("RXN_NO_REACT_ORDER")) return RXN_OK;
   size_t need = 0;
-  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, s->d_prev_it + off, s->d_keys + off, s->d_iota + off, s->d_order + off, (int)len, 0, 14, stream));
-  if (need > s->sort_tmp_bytes[which]) {
-    if (s->d_sort_tmp[which]) CU(cudaFree(s->d_sort_tmp[which]));
-    s->d_sort_tmp[which] = nullptr; s->sort_tmp_bytes[which] = 0;
-    CU(cudaMalloc(&s->d_sort_tmp[which], need));
-    s->sort_tmp_bytes[which] = need;
+  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, s->d_prev_it, s->d_keys, s->d_iota, s->d_order, (int)nlocal, 0, 14, stream));
+  if (need > s->sort_tmp_bytes) {
+    if (s->d_sort_tmp) CU(cudaFree(s->d_sort_tmp));
+    s->d_sort_tmp = nullptr; s->sort_tmp_bytes = 0;
+    CU(cudaMalloc(&s->d_sort_tmp, need));
+    s->sort_tmp_bytes = need;
   }
-  k_iota<<<nblocks(len, 256), 256, 0, stream>>>(s->d_iota + off, len);
-  CU(cub::DeviceRadixSort::SortPairsDescending(s->d_sort_tmp[which], need, s->d_prev_it + off, s->d_keys + off, s->d_iota + off, s->d_order + off, (int)len, 0,
-                                               14, stream));
+  k_iota<<<nblocks(nlocal, 256), 256, 0, stream>>>(s->d_iota, nlocal);
+  CU(cub::DeviceRadixSort::SortPairsDescending(s->d_sort_tmp, need, s->d_prev_it, s->d_keys, s->d_iota, s->d_order, (int)nlocal, 0, 14, stream));
   g_launches += 2;
-  *order = s->d_order + off;
+  *order = s->d_order;
   return RXN_OK;
 }
-// room for the iteration counts of a batch of `total` items (drops what was remembered when it has to grow)
-static int react_order_reserve(RxnState *s, int64_t total) {
-  if (total <= s->order_cap) return RXN_OK;
+// room for the iteration counts of a launch of nlocal items (drops what was remembered when it has to grow)
+static int react_order_reserve(RxnState *s, int64_t nlocal) {
+  if (nlocal <= s->order_cap) return RXN_OK;
   s->prev_n = 0;
   for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) { if (*p) CU(cudaFree(*p)); *p = nullptr; }
   s->order_cap = 0;
-  for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) CU(cudaMalloc(p, (size_t)total * 4));
-  s->order_cap = total;
+  for (int32_t **p : {&s->d_prev_it, &s->d_keys, &s->d_iota, &s->d_order}) CU(cudaMalloc(p, (size_t)nlocal * 4));
+  s->order_cap = nlocal;
   return RXN_OK;
 }
-static int react_remember(RxnState *s, int64_t off, int64_t len, const int32_t *d_iters, cudaStream_t stream) {
-  CU(cudaMemcpyAsync(s->d_prev_it + off, d_iters, (size_t)len * 4, cudaMemcpyDeviceToDevice, stream));
-  return RXN_OK;
+// see the policy above
+static bool react_ordered(const RxnTables *t, int64_t nlocal) {
+  if (tail_bound_tables(t)) return true;
+  const LaneTab &klt = t->lane.plan_tm.usable ? t->lane.plan_tm.lt : t->lane.plan.lt;
+  return t->h.naq >= 8 && nlocal < 16LL * t->lane.sm_count * klt.CPB;
 }
 
-// total / chunk / off: the batch this launch is a chunk of (pipelined host-buffer call); total < 0: the launch is the batch
 static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t nlocal, double dt, int dt_mode,
                         int32_t *d_iters, int32_t *d_flags, long long cell0 = 0, cudaStream_t stream = nullptr,
-                        unsigned long long *counter = nullptr, int64_t total = -1, int64_t chunk = 0, int64_t off = 0, int which = 0) {
+                        unsigned long long *counter = nullptr) {
   const RxnTables *t = s->t;
   if (!stream) stream = s->stream;
   // the shared-memory kernels keep dtotal only as Newton scratch: states with DTOTAL materialised use thread-per-cell
@@ -535,23 +545,17 @@ static int launch_react(RxnState *s, double *d_xx, const int32_t *d_l2g, int64_t
       counter = s->d_counter;
     }
     DevState S = s->S;
-    // work order (react_order): the lanes take the items sorted by the iteration counts of the previous call of the same shape
-    if (single_launch) { total = nlocal; chunk = 0; off = 0; which = 0; }
-    // (the chunks of the pipelined call of a small chemistry are not ordered: calcite solves 143 000 cells in 0.16 ms, less than the
-    // sort's launches cost: e2e 582 -> 555 M cell-updates/s with them, profiles/r02_au_bench_default.json)
-    const bool ordered = d_iters != nullptr && total <= 0x7fffffffLL && (single_launch || t->h.naq >= 8);
+    // work order (react_order; policy: react_ordered): single launches only, never the chunks of the pipelined call
+    const bool ordered = single_launch && d_iters != nullptr && nlocal <= 0x7fffffffLL && react_ordered(t, nlocal);
     if (ordered) {
-      if (single_launch) { const int rcv = react_order_reserve(s, total); if (rcv != RXN_OK) return rcv; }
-      const int rco = react_order(s, total, chunk, off, nlocal, stream, which, &S.order);
-      if (rco != RXN_OK) return rco;
+      const int rcv = react_order_reserve(s, nlocal); if (rcv != RXN_OK) return rcv;
+      const int rco = react_order(s, nlocal, stream, &S.order); if (rco != RXN_OK) return rco;
     }
     int rc = lane_launch_react(t->lane, t->h, t->d_blob, S, d_xx, d_l2g, nlocal, dt, dt_mode, d_iters, d_flags, counter, stream, cell0);
+    if (single_launch) s->prev_n = 0;
     if (rc == RXN_OK && ordered) {
-      const int rcr = react_remember(s, off, nlocal, d_iters, stream);
-      if (rcr != RXN_OK) return rcr;
-      if (single_launch) { s->prev_n = total; s->prev_chunk = 0; }
-    } else if (single_launch) {
-      s->prev_n = 0;
+      CU(cudaMemcpyAsync(s->d_prev_it, d_iters, (size_t)nlocal * 4, cudaMemcpyDeviceToDevice, stream));
+      s->prev_n = nlocal;
     }
     if (rc != RXN_OK) return fail(rc, "resident-lane kernel launch failed (N=%d CPB=%d): %s", t->lane.plan.lt.N, t->lane.plan.lt.CPB,
                                   cudaGetErrorString(cudaGetLastError()));
@@ -639,7 +643,6 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
       CUP(cudaEventRecord(s->ev_in[nch], s->h2d));
     }
     CUP(cudaEventRecord(s->ev0, s->stream));
-    { const int rcv = react_order_reserve(s, nlocal); if (rcv != RXN_OK) { drain(); return rcv; } }
     int c = 0;
     int last_k[2] = {-1, -1};
     for (int64_t off = 0; off < nlocal; off += chunk, ++c) {
@@ -647,7 +650,7 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
       cudaStream_t ks = (c & 1) ? s->stream2 : s->stream;       // chunk c+1 fills the SMs chunk c has drained
       CUP(cudaStreamWaitEvent(ks, s->ev_in[c], 0));
       rc = launch_react(s, (double *)d_xx + off * n, d_l2g ? (const int32_t *)d_l2g + off : nullptr, len, dt, dt_mode, (int32_t *)d_it + off,
-                        (int32_t *)d_fl + off, d_l2g ? 0 : off, ks, s->d_counters + c, nlocal, chunk, off, c & 1);
+                        (int32_t *)d_fl + off, d_l2g ? 0 : off, ks, s->d_counters + c);
       if (rc != RXN_OK) { drain(); return rc; }
       CUP(cudaEventRecord(s->ev_k[c], ks));
       last_k[c & 1] = c;
@@ -662,7 +665,6 @@ int rxn_react_batch(RxnState *s, double *tran_xx, const int32_t *l2g, int64_t nl
     CUP(cudaStreamSynchronize(s->d2h));
     CUP(cudaStreamSynchronize(s->stream2));
     CUP(cudaStreamSynchronize(s->stream));
-    s->prev_n = (nlocal <= 0x7fffffffLL && t->h.naq >= 8) ? nlocal : 0; s->prev_chunk = chunk;   // every chunk has remembered its iteration counts
     CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
 #undef CUP
     return RXN_OK;

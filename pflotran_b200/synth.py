@@ -56,11 +56,13 @@ class Workload:
         return np.concatenate([self.base['PRI_MOLAL'], self.base.get('IMMOBILE', np.zeros(0))])
 
 
-def _block(w: Workload, b: int, sigma: float, front_fraction: float, front_sigma: float, seed: int):
+def _block(w: Workload, b: int, sigma: float, front_fraction: float, front_sigma: float, seed: int, variant: int = 0):
     t = w.tables
     n, nk = t.naqcomp, t.nkinmnrl
     rng = np.random.Generator(np.random.Philox(key=[seed, b]))
     z = rng.standard_normal((BLOCK, n))
+    if variant:          # another noise realisation for the SAME cells (same front membership, porosity, minerals): "the next time step"
+        z = np.random.Generator(np.random.Philox(key=[seed + 7919 * variant, b + (1 << 40)])).standard_normal((BLOCK, n))
     u_front = rng.random(BLOCK)
     por = 0.2 + 0.2 * rng.random(BLOCK)
     vf = 0.2 * rng.random((BLOCK, max(nk, 1)))
@@ -83,7 +85,7 @@ def _block(w: Workload, b: int, sigma: float, front_fraction: float, front_sigma
 
 
 def make_cells(w: Workload, start: int, ncells: int, sigma: float = 0.05, front_fraction: float = 0.1,
-               front_sigma: float = 0.5, seed: int = SEED) -> Dict[str, np.ndarray]:
+               front_sigma: float = 0.5, seed: int = SEED, variant: int = 0) -> Dict[str, np.ndarray]:
     """Per-cell inputs for cells [start, start+ncells): tran_xx [ncells, ncomp] (AoS, C order),
     porosity [ncells], volfrac [nkin, ncells], temp, pres [ncells]."""
     t = w.tables
@@ -95,7 +97,7 @@ def make_cells(w: Workload, start: int, ncells: int, sigma: float = 0.05, front_
     pres = np.empty(ncells)
     b0, b1 = start // BLOCK, (start + ncells - 1) // BLOCK
     for b in range(b0, b1 + 1):
-        bx, bp, bv, bt, bpr = _block(w, b, sigma, front_fraction, front_sigma, seed)
+        bx, bp, bv, bt, bpr = _block(w, b, sigma, front_fraction, front_sigma, seed, variant)
         lo = max(start, b * BLOCK)
         hi = min(start + ncells, (b + 1) * BLOCK)
         s = slice(lo - b * BLOCK, hi - b * BLOCK)

@@ -621,13 +621,14 @@ def test_global_implicit_device_resident_entry_points():
         rz2.device_free(p)
 
 
-@pytest.mark.parametrize('name,n', [('ascem', 6000), ('hanford300a_eq', 30000), ('hanford300a_mr', 20000), ('calcite', 60000),
-                                    ('calcite', 600000), ('hanford300a_eq', 300000)])     # >= 262 144 cells: the chunked host-buffer call, ordered per chunk
+@pytest.mark.parametrize('name,n', [('ascem', 6000), ('hanford300a_eq', 30000), ('hanford300a_mr', 20000), ('scco2_brine', 40000),
+                                    ('hanford300a_eq', 300000)])     # the last one: the chunked host-buffer call (never ordered; repeatable)
 def test_react_work_order_is_bitwise_neutral(name, n):
-    """Chemistries on the N = 24 shapes (ascem: damped redox cells with thousands of Newton iterations), and every chemistry on
-    batches below 64 generations of resident cells, are handed to the lanes (resident-lane and tensor-memory kernel) in the order of
-    the previous call's iteration counts, slowest first (rxn_b200.cu: react_order).  Cells are independent, so the second
-    (ordered) call must reproduce the first (unordered) one bit for bit - with and without a local-to-ghosted map."""
+    """Chemistries on the N = 24 shapes (ascem: damped redox cells with thousands of Newton iterations), and chemistries with at least
+    8 primaries on batches below 16 generations of resident cells, are handed to the lanes (resident-lane and tensor-memory kernel)
+    in the order of the previous call's iteration counts, slowest first (rxn_b200.cu: react_order, react_ordered).  Cells are
+    independent, so the second (ordered) call must reproduce the first (unordered) one bit for bit - with and without a
+    local-to-ghosted map."""
     w, cells = workload_cells(name, n)
     st0 = synth.host_state(w, cells)
     rx = rt.Reaction(w.tables)
