@@ -43,10 +43,15 @@ for name, n in PLAN:
     t0 = time.perf_counter()
     it_o, fl_o = Oracle(w.tables).react(st_o, xo, 3600.0, abi.RXN_DT_CONSISTENT, maxit=10000, nthreads=threads)
     el = time.perf_counter() - t0
-    same = (it_g == it_o) & (fl_g == fl_o)
+    # as tests/common.py iteration_parity: a cell whose arithmetic left the finite range in BOTH (the reference would spin or abort there)
+    # is compared on the iteration count and the NONFINITE flag only (whether the closing free-site loop then also hits its guard
+    # depends on which garbage value the singular step produced)
+    nf = ((fl_g & abi.RXN_FLAG_NONFINITE) != 0) & ((fl_o & abi.RXN_FLAG_NONFINITE) != 0)
+    same = (it_g == it_o) & ((fl_g == fl_o) | (nf & (((fl_g ^ fl_o) & ~abi.RXN_FLAG_CAPPED) == 0)))
+    strict = (it_g == it_o) & (fl_g == fl_o)
     ok = ((fl_o & ~3) == 0) & same
     err = np.abs(xg[ok] - xo[ok]) / np.abs(xo[ok])
-    out = {'workload': name, 'seed': seed, 'cells': n, 'iteration_or_flag_mismatches': int((~same).sum()),
+    out = {'workload': name, 'seed': seed, 'cells': n, 'iteration_or_flag_mismatches': int((~same).sum()), 'nonfinite_in_both_with_other_guard_bit': int((same & ~strict).sum()),
            'cells_with_nonreference_flags': int(((fl_o & ~3) != 0).sum()), 'converged_cells_compared': int(ok.sum()),
            'max_rel_err_free_ion': float(err.max()) if err.size else None,
            'cells_above_1e-10': int((err.max(axis=1) > 1e-10).sum()) if err.size else 0,
